@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- link-updates/s of the batched leapfrog hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (CUDA, libl2b)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU PyTorch path
+
+A "step" is ONE HMC trajectory (N_LF leapfrog steps + both Hamiltonians) over one
+batch of synthetic chains.  Default workload = the configuration the north-star
+target is quoted on, per GPU: 4-D SU(3) 16^4, 64 chains per GPU (BASELINE cfg 4:
+512 chains sharded over 8 GPUs), N_LF = 10, complex128.  Chains are independent:
+ranks share nothing on the data path (weak scaling, no collective); the only
+collectives are the timing barrier and the max-over-ranks of the elapsed time.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (k_force: staples + TAH + kick) algorithmic bytes
+                (3 link-sized transfers = 432 B per link per launch) / its average
+                CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own PyTorch path on this box's host cores, on a
+                bounded sample of the same workload
+  e2e           same metric through the public Dynamics.apply_transition_hmc call
+                with the links in pinned HOST memory: H2D of x and D2H of the
+                accept probabilities inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (group, lattice, chains per GPU, N_LF, dtype, beta)
+    'su3_16x16x16x16_nb64_nlf10_c128': ('SU3', [16, 16, 16, 16], 64, 10, 'f64', 6.0),
+    'su3_8x8x8x8_nb256_nlf10_c128': ('SU3', [8, 8, 8, 8], 256, 10, 'f64', 6.0),
+    'u1_64x64_nb4096_nlf10_f32': ('U1', [64, 64], 4096, 10, 'f32', 4.0),
+    'u1_16x16_nb128_nlf8_f32': ('U1', [16, 16], 128, 8, 'f32', 4.0),
+}
+DEFAULT_WORKLOAD = 'su3_16x16x16x16_nb64_nlf10_c128'
+METRIC = 'link-updates/sec (chains*V*d*Nlf/s)'
+SEED = 9992  # conf/config.yaml:11
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        return float(json.loads(p.read_text())['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+def links_of(lattice, nb, dim):
+    v = 1
+    for s in lattice:
+        v *= s
+    return nb * v * dim
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.idx}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().strip().splitlines():
+            c = [t.strip() for t in line.split(',')]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, val in zip(names, c[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# reference / cpu_baseline arm
+# ---------------------------------------------------------------------------
+def reference_sample(workload: str):
+    """bounded sample of the workload for the CPU arm: same lattice, dtype and
+    integrator, fewer chains and leapfrog steps (cost is linear in both)."""
+    group, lattice, nb, nlf, dtype, beta = WORKLOADS[workload]
+    if group == 'SU3':
+        v = 1
+        for s in lattice:
+            v *= s
+        nb_s = max(1, min(nb, 65536 // v))         # 16^4 -> 1 chain, 8^4 -> 16 chains
+        nlf_s = 2
+    else:
+        nb_s, nlf_s = min(nb, 512), nlf
+    return group, lattice, nb_s, nlf_s, dtype, beta
+
+
+def run_reference_steps(workload: str, steps: int, warmup: int):
+    """Times the reference's own `Dynamics.transition_kernel_hmc` (unmodified
+    modules under oracle/_ref, loaded by oracle/ref_shim.py) on the host cores.
+    Falls back to the numpy oracle port when oracle/_ref did not travel."""
+    import numpy as np
+    import torch
+    group, lattice, nb, nlf, dtype, beta = reference_sample(workload)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    eps = 1.0 / WORKLOADS[workload][3]
+    from oracle import ref_shim
+    kind = 'reference' if ref_shim.available() else 'port'
+    dim = 4 if group == 'SU3' else 2
+    units = links_of(lattice, nb, dim) * nlf
+    if kind == 'reference':
+        ref = ref_shim.load_reference(torch.float64 if dtype == 'f64' else torch.float32)
+        torch.manual_seed(SEED)
+        lat = (ref.LatticeSU3 if group == 'SU3' else ref.LatticeU1)(nb, lattice)
+        cfg = ref.DynamicsConfig(nchains=nb, group=group, latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
+                                 verbose=False, use_split_xnets=False, use_separate_networks=False,
+                                 merge_directions=True)
+        dyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+        x = lat.random().detach()
+        b = torch.tensor(beta)
+
+        def step():
+            v = lat.g.random_momentum(list(cfg.xshape))
+            st = ref.State(x=x, v=v, beta=b)
+            sp, met = dyn.transition_kernel_hmc(st, eps=eps, nleapfrog=nlf)
+            return float(met['acc'].mean())
+    else:
+        from oracle import su3 as osu3, dynamics as od
+        rng = np.random.default_rng(SEED)
+        if group == 'SU3':
+            full = (nb, 4, *lattice, 3, 3)
+            x = osu3.random_su3(rng, full)
+            ops_, mom = od.SU3Ops, (lambda: osu3.random_momentum(rng, full))
+        else:
+            dt = np.float64 if dtype == 'f64' else np.float32
+            x = rng.uniform(-np.pi, np.pi, (nb, 2, *lattice)).astype(dt)
+            ops_, mom = od.U1Ops, (lambda: rng.standard_normal((nb, 2 * lattice[0] * lattice[1])).astype(dt))
+
+        def step():
+            sp, acc = od.transition_kernel_hmc(ops_, od.State(x, mom(), beta), eps, nlf)
+            return float(acc.mean())
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt_s = time.perf_counter() - t0
+    sample = (f'{group} {"x".join(map(str, lattice))}, {nb} chain(s), {nlf} leapfrog steps per trajectory, '
+              f'{dtype}, eps={eps:g}, torch {torch.__version__} CPU, {cores} threads')
+    return {'value': units * steps / dt_s, 'unit': 'link-updates/s', 'cores': cores, 'kind': kind,
+            'sample': sample}, dt_s / steps * 1e3
+
+
+def main_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    base, ms = run_reference_steps(args.workload, args.steps, args.warmup)
+    group, lattice, nb, nlf, dtype, beta = WORKLOADS[args.workload]
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'link-updates/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64' if dtype == 'f64' else 'f32', 'data': 'synthetic',
+        'config': {'workload': args.workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
+                   'nleapfrog': nlf, 'beta': beta, 'sample': base['sample']},
+        'cpu_baseline': base,
+        'e2e': {'value': base['value'], 'unit': 'link-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU; there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from l2hmc_b200 import ops
+    from l2hmc_b200 import _lib
+    from l2hmc_b200.configs import DynamicsConfig
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+
+    group, lattice, nb, nlf, dtype, beta = WORKLOADS[args.workload]
+    su3 = group == 'SU3'
+    dim = 4 if su3 else 2
+    eps = 1.0 / nlf                                           # configs.py:485-487
+    units_rank = links_of(lattice, nb, dim) * nlf             # link-updates per trajectory per GPU
+    torch.manual_seed(SEED + rank)
+    tdt = torch.float64 if dtype == 'f64' else torch.float32
+    torch.set_default_dtype(tdt)
+
+    # synthetic hot-start configuration + momenta, resident in HBM
+    cfg = DynamicsConfig(nchains=nb, group=group, latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
+                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    lat = LatticeSU3(nb, lattice) if su3 else LatticeU1(nb, lattice)
+    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+    x = lat.random()
+    v = lat.random_momentum()
+    field_bytes = x.numel() * x.element_size()
+
+    def traj():
+        if su3:
+            return ops.su3_hmc_trajectory(x, v, beta, eps, nlf)
+        return ops.u1_hmc_trajectory(x, v, beta, eps, nlf, shape=lattice)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        out = traj()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = traj()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t)
+    value = world * units_rank * args.steps / (ms_max * 1e-3)
+    en = out[2]
+    assert torch.isfinite(en).all(), 'non-finite energies'
+
+    # ---- per-kernel CUDA-event timing of the dominant kernel (k_force) ---------
+    roofline = None
+    peak, peak_kind = peaks()
+    if su3:
+        roofline = su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, args.steps, peak, peak_kind,
+                                       ms_max / args.steps)
+    else:
+        # whole trajectory is ONE kernel with the state resident in shared memory:
+        # algorithmic (streaming-model) bytes vs time; real HBM traffic is 4 field passes
+        algo = 24.0 * units_rank
+        ach = algo / (ms_max / args.steps * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': 'k_u1_hmc (whole trajectory on-chip)', 'achieved': ach, 'peak': peak,
+                    'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind, 'traffic': None,
+                    'note': 'streaming model 24 B/link-update; actual DRAM traffic is 16 B/link per TRAJECTORY'}
+
+    # ---- e2e through the public API with host buffers -------------------------
+    xh = x.detach().cpu().pin_memory()
+    acc_h = torch.empty(nb, dtype=torch.float64 if su3 else tdt).pin_memory()
+    bt = torch.tensor(beta)
+
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True)                    # H2D of this step's links
+        xo, met = dyn.apply_transition_hmc((xd, bt), eps=eps, nleapfrog=nlf)
+        acc_h.copy_(met['acc'], non_blocking=True)            # D2H of the step's result
+        return xo
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(1, min(args.steps, 5))
+        e2.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e3.record()
+        barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = world * units_rank * n_e2e / (float(t2) * 1e-3)
+
+    if rank == 0:
+        cpu_base = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base, _ = run_reference_steps(args.workload, 3, 1)
+        gb = 864.0 if su3 else 24.0
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'link-updates/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64' if dtype == 'f64' else 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
+                       'global_chains': nb * world, 'nleapfrog': nlf, 'eps': eps, 'beta': beta,
+                       'start': 'hot (g.random)', 'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
+                       'l2_policy': f'inputs larger than L2 ({field_bytes / 2**20:.0f} MiB per field per GPU), no flush'
+                       if field_bytes > 200 * 2**20 else 'working set fits L2; fields re-read every step (no flush)'},
+            'hbm_model': {'bytes_per_link_update': gb, 'achieved_GBps_per_gpu': value / world * gb / 1e9,
+                          'frac_of_peak': value / world * gb / 1e9 / peak, 'peak_GBps': peak, 'peak_kind': peak_kind},
+            'roofline': roofline, 'cpu_baseline': cpu_base,
+            'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': field_bytes,
+                    'd2h_bytes_per_step': acc_h.numel() * acc_h.element_size(), 'steps': n_e2e,
+                    'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta))'},
+            'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, steps, peak, peak_kind, ms_traj):
+    """Re-runs the same trajectories kernel by kernel (the C ABI's planar step
+    entry points) with CUDA events between launches on the launching stream."""
+    import torch
+    dims = _lib.dims4(lattice)
+    F64 = _lib.L2B_F64
+    nws = _lib.su3_ws_bytes(nb, lattice)
+    ws = torch.empty(nws, dtype=torch.uint8, device=x.device)
+    U, P = torch.empty_like(x), torch.empty_like(x)
+    st = ops._stream()
+    p = ops._ptr
+    _lib.call('l2b_su3_aos_to_soa', p(x), p(U), nb, dims, F64, st)
+    _lib.call('l2b_su3_aos_to_soa', p(v), p(P), nb, dims, F64, st)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    tf, td = [], []
+    for _ in range(max(1, min(steps, 3))):
+        a, b = ev(), ev()
+        a.record()
+        _lib.call('l2b_su3_force_kick_planar', p(U), p(P), float(beta), 0.5 * eps, None, nb, dims, F64, p(ws), nws, st)
+        b.record()
+        tf.append((a, b))
+        for k in range(1, nlf + 1):
+            a, b, c = ev(), ev(), ev()
+            a.record()
+            _lib.call('l2b_su3_drift_planar', p(U), p(P), float(eps), nb, dims, F64, st)
+            b.record()
+            _lib.call('l2b_su3_force_kick_planar', p(U), p(P), float(beta), (0.5 if k == nlf else 1.0) * eps, None,
+                      nb, dims, F64, p(ws), nws, st)
+            c.record()
+            td.append((a, b))
+            tf.append((b, c))
+    torch.cuda.synchronize()
+    ms_f = statistics.mean(a.elapsed_time(b) for a, b in tf)
+    ms_d = statistics.mean(a.elapsed_time(b) for a, b in td)
+    links = x.numel() // 9
+    bytes_f = 3 * 144.0 * links      # read U, read P, write P
+    bytes_d = 3 * 144.0 * links      # read P, read U, write U
+    ach = bytes_f / (ms_f * 1e-3) / 1e9
+    share = (nlf + 1) * ms_f / ms_traj
+    return {'bound': 'hbm', 'kernel': 'k_force<32,true> (staples + TAH + momentum kick)', 'achieved': ach,
+            'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind, 'traffic': None,
+            'algorithmic_bytes_per_launch': bytes_f, 'avg_launch_ms': ms_f, 'share_of_step': share,
+            'other_kernels': {'k_drift': {'avg_launch_ms': ms_d, 'achieved': bytes_d / (ms_d * 1e-3) / 1e9,
+                                          'frac': bytes_d / (ms_d * 1e-3) / 1e9 / peak}}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    ap.add_argument('--workload', choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,197 @@
+/* l2b.h -- C ABI of libl2b (l2hmc_b200/csrc), the B200 (sm_100a) kernels behind
+ * the leapfrog-integrator hot path of saforem2/l2hmc-qcd.
+ *
+ * The reference has no FFI: its hot path is three Python classes built in
+ * trainers/pytorch/trainer.py:490-506,540-562 (LatticeSU3/LatticeU1, Dynamics,
+ * NetworkFactory).  This header is the thin native layer our mirrors of those
+ * classes (l2hmc_b200/{group,lattice,dynamics}) call through ctypes; each entry
+ * point names the reference code it replaces (paths relative to
+ * /root/reference/src/l2hmc).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative L2B_ERR_* code; a
+ *    human-readable message for the calling thread is in l2b_last_error();
+ *  - all pointers are DEVICE pointers unless named host_*; the caller owns and
+ *    allocates every buffer (no hidden allocation, no ownership transfer);
+ *    scratch space is passed in (`ws`, `ws_bytes`) and sized by *_ws_bytes();
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it
+ *    and re-entrant on distinct streams with distinct workspaces;
+ *  - SU(3) fields use the reference layout [nb, 4, T, X, Y, Z, 3, 3] complex,
+ *    interleaved (re, im)  (configs.py:501-507); U(1) fields are [nb, 2, T, X];
+ *  - `dtype` is the REAL scalar type of the field: L2B_F64 (complex128 / float64)
+ *    or L2B_F32.  SU(3) entry points currently implement L2B_F64 only (the only
+ *    SU(3) precision the reference configures, conf/experiment/su3.yaml) and
+ *    return L2B_ERR_UNSUPPORTED otherwise.
+ *  - per-chain reductions are deterministic (fixed-order two-stage sums).
+ */
+#ifndef L2B_H
+#define L2B_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L2B_OK 0
+#define L2B_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size ...) */
+#define L2B_ERR_UNSUPPORTED (-2) /* dtype / option not implemented                     */
+#define L2B_ERR_WORKSPACE (-3)   /* ws_bytes smaller than *_ws_bytes()                  */
+#define L2B_ERR_CUDA (-4)        /* a CUDA runtime call failed                          */
+
+#define L2B_F32 0
+#define L2B_F64 1
+
+const char* l2b_last_error(void);
+int l2b_version(void);
+/* number of kernel launches issued by this library on behalf of the calling
+ * process since load (bench.py reports it as gpu_launches) */
+uint64_t l2b_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* SU(3)                                                                     */
+/* ------------------------------------------------------------------------ */
+
+/* bytes of scratch needed by any SU(3) entry point for `nb` chains of a
+ * T x X x Y x Z lattice (two planar field copies + reduction partials) */
+size_t l2b_su3_ws_bytes(int nb, const int dims[4], int dtype);
+
+/* reference layout <-> internal planar layout (exposed for tests/benchmarks) */
+int l2b_su3_aos_to_soa(const void* x_aos, void* x_soa, int nb, const int dims[4], int dtype, void* stream);
+int l2b_su3_soa_to_aos(const void* x_soa, void* x_aos, int nb, const int dims[4], int dtype, void* stream);
+
+/* LatticeSU3._wilson_loops (lattice/su3/pytorch/lattice.py:157-199, c1 == 0):
+ * wloops[6, nb, T, X, Y, Z] complex, planes ordered (u=1,v=0),(2,0),(2,1),(3,0),(3,1),(3,2) */
+int l2b_su3_wilson_loops(const void* x, void* wloops, int nb, const int dims[4], int dtype,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* LatticeSU3.action / _plaquettes / _int_charges / _sin_charges in one pass
+ * (lattice.py:201-269): sums[nb, 2] = (sum Re tr P, sum Im tr P) per chain.
+ *   action = -(beta/3) sums[:,0];  plaq = sums[:,0]/(18 V);
+ *   intQ = sums[:,1]/(32 pi^2);    sinQ = sums[:,1]/(18 V)                    */
+int l2b_su3_plaq_sums(const void* x, double* sums, int nb, const int dims[4], int dtype,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* LatticeSU3.grad_action (lattice.py:299-308): force[nb,4,T,X,Y,Z,3,3] =
+ * (beta/3) TAH(U A) with analytic staples; optional act_sums[nb] receives
+ * sum Re tr P (so action comes with the force at no cost; may be NULL).       */
+int l2b_su3_force(const void* x, double beta, void* force, double* plaq_sum_or_null, int nb,
+                  const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* SU3.exp (group/su3/pytorch/group.py:88-90): out = matrix_exp(scale * p), n matrices */
+int l2b_su3_exp(const void* p, double scale, void* out, size_t nmat, int dtype, void* stream);
+
+/* SU3.update_gauge / Dynamics._update_x_{fwd,bwd} for SU(3)
+ * (group.py:45-50, dynamics/pytorch/dynamics.py:1420-1425,1468-1474):
+ *   mask == NULL :  x_out = exp(eps p) x
+ *   mask != NULL :  x_out = m*x + exp(eps p) ((1-m)*x),  m = mask[4*V*9] float32,
+ *                   element-wise and shared by all chains (dynamics.py:1101-1110);
+ *                   if mask_complement != 0 the roles of m and 1-m are swapped.
+ * x_out may alias x.                                                          */
+int l2b_su3_update_gauge(const void* x, const void* p, double eps, const float* mask,
+                         int mask_complement, void* x_out, int nb, const int dims[4], int dtype,
+                         void* stream);
+
+/* SU3.projectSU / compat_proj (group/su3/pytorch/utils.py:341-346), and
+ * group_to_vec = su3_to_vec(projectSU(x)) (group.py:138-147) fused:
+ * either output may be NULL.  vec8[nmat, 8] real.                             */
+int l2b_su3_project(const void* x, void* x_proj_or_null, void* vec8_or_null, size_t nmat, int dtype,
+                    void* stream);
+/* su3_to_vec / vec_to_su3 without projection (utils.py:394-445) */
+int l2b_su3_to_vec(const void* x, void* vec8, size_t nmat, int dtype, void* stream);
+int l2b_su3_from_vec(const void* vec8, void* x, size_t nmat, int dtype, void* stream);
+/* SU3.projectTAH (group.py:92-103) */
+int l2b_su3_tah(const void* x, void* out, size_t nmat, int dtype, void* stream);
+/* SU3.kinetic_energy (group.py:125-126): ke[nb] = 0.5 sum_links(|P|_F^2 - 8) */
+int l2b_su3_kinetic(const void* p, double* ke, int nb, const int dims[4], int dtype, void* ws,
+                    size_t ws_bytes, void* stream);
+/* checkSU (utils.py:376-391): avg[nb], max[nb] */
+int l2b_su3_check(const void* x, double* avg, double* max, int nb, const int dims[4], int dtype,
+                  void* ws, size_t ws_bytes, void* stream);
+/* SU3.random_momentum / randTAH3 (utils.py:171-195): Gaussian traceless
+ * anti-Hermitian momenta, <|P|_F^2> = 8, from a counter-based Philox4x32-10
+ * stream keyed by (seed, offset, link index); ke_or_null[nb] as l2b_su3_kinetic. */
+int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or_null, int nb,
+                          const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* Dynamics._update_v_fwd / _update_v_bwd epilogue (dynamics.py:1266-1297) on
+ * complex v, force with REAL s, t, q of shape [nb, 4*V*9] (network outputs):
+ *   forward  (sign=+1): v' = exp(eps s/2) v - eps/2 (F exp(eps q) + t), logdet = +sum eps s/2
+ *   backward (sign=-1): v' = exp(-eps s/2) (v + eps/2 (F exp(eps q) + t)), logdet = -sum eps s/2
+ * s/t/q may be NULL (treated as 0, i.e. a plain HMC half kick). v_out may alias v. */
+int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q,
+                    double eps, int sign, void* v_out, double* logdet, int nb, const int dims[4],
+                    int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* Dynamics.transition_kernel_hmc (dynamics.py:900-954) for SU(3): nlf leapfrog
+ * steps of size eps from (x, v) at coupling beta; kicks between consecutive
+ * drifts are merged (identical up to rounding to the reference's two half
+ * kicks).  Outputs: x_prop, v_prop (reference layout), and
+ * energies[nb, 4] = (KE0, S0, KE1, S1) so that H = KE + S as in
+ * Dynamics.hamiltonian (dynamics.py:1479-1483).                               */
+int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps, int nlf,
+                           void* x_prop, void* v_prop, double* energies, int nb,
+                           const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/* The two kernels of one leapfrog step on fields ALREADY in the planar layout
+ * (l2b_su3_aos_to_soa), for callers that keep the state planar between steps
+ * and for per-kernel timing (bench.py):
+ *   force_kick:  P <- P - eps_kick * (beta/3) TAH(U A); sums_or_null[nb, 2] =
+ *                (sum Re tr P_plaq, sum_links(|P|_F^2 - 8)) after the kick
+ *   drift:       U <- exp(eps P) U                                            */
+int l2b_su3_force_kick_planar(const void* u_planar, void* p_planar, double beta, double eps_kick,
+                              double* sums_or_null, int nb, const int dims[4], int dtype, void* ws,
+                              size_t ws_bytes, void* stream);
+int l2b_su3_drift_planar(void* u_planar, const void* p_planar, double eps, int nb, const int dims[4],
+                         int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* U(1), x[nb, 2, T, X] real angles                                          */
+/* ------------------------------------------------------------------------ */
+size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype);
+
+/* LatticeU1.wilson_loops (lattice/u1/pytorch/lattice.py:154-159): w[nb, T, X] */
+int l2b_u1_wilson_loops(const void* x, void* w, int nb, int T, int X, int dtype, void* stream);
+/* LatticeU1._action / plaqs / _sin_charges / _int_charges in one pass
+ * (lattice.py:80-86,188-228): obs[nb, 4] = (action, plaq, sinQ, intQ), in `dtype` */
+int l2b_u1_observables(const void* x, double beta, void* obs, int nb, int T, int X, int dtype,
+                       void* stream);
+/* LatticeU1.grad_action (lattice.py:102-117), analytic */
+int l2b_u1_force(const void* x, double beta, void* force, int nb, int T, int X, int dtype,
+                 void* stream);
+/* Dynamics.transition_kernel_hmc for U(1): the whole trajectory of one chain
+ * runs inside one thread block with x, v resident in shared memory.
+ * energies[nb, 4] = (KE0, S0, KE1, S1) in `dtype`.                            */
+int l2b_u1_hmc_trajectory(const void* x, const void* v, double beta, double eps, int nlf,
+                          void* x_prop, void* v_prop, void* energies, int nb, int T, int X,
+                          int dtype, void* stream);
+/* Dynamics._update_v_{fwd,bwd} epilogue for real fields (dynamics.py:1266-1297) */
+int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q,
+                   double eps, int sign, void* v_out, void* logdet, int nb, int xdim, int dtype,
+                   void* stream);
+/* Dynamics._update_x_{fwd,bwd} for U(1) (dynamics.py:1398-1419,1443-1467),
+ * use_ncp selects the non-compact-projection update; m = mask[xdim] float32.
+ * x_out is wrapped to [-pi, pi) like g.compat_proj.                           */
+int l2b_u1_xupdate(const void* x, const void* v, const void* s, const void* t, const void* q,
+                   const float* mask, double eps, int sign, int use_ncp, void* x_out, void* logdet,
+                   int nb, int xdim, int dtype, void* stream);
+
+/* U1Phase.kinetic_energy (group/u1/pytorch/group.py:164-165): ke[nb] = 0.5 sum v^2 */
+int l2b_u1_kinetic(const void* v, void* ke, int nb, int xdim, int dtype, void* stream);
+/* U1Phase.compat_proj (group.py:130-131): ((x + pi) mod 2 pi) - pi, n elements */
+int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* Metropolis-Hastings accept / reject mix (dynamics.py:632-702,1065-1087)   */
+/* ------------------------------------------------------------------------ */
+/* out[b, :] = accept[b] ? prop[b, :] : init[b, :] for `nfields` field pairs of
+ * `row_bytes[k]` bytes per chain; accept[nb] float32 0/1 = (acc > u).        */
+int l2b_accept_mix(const void* const* host_init, const void* const* host_prop, void* const* host_out,
+                   const size_t* host_row_bytes, int nfields, const float* accept, int nb,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2B_H */

@@ -1,0 +1,68 @@
+"""Builds `l2hmc_b200/libl2b.so` (the C-ABI CUDA library, include/l2b.h) in-tree
+with nvcc for sm_100a.  No torch headers are involved: the library's interface
+is plain pointers and sizes, and Python talks to it through ctypes
+(`l2hmc_b200/_lib.py`)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / 'csrc'
+LIB = PKG / 'libl2b.so'
+SOURCES = ['l2b_capi.cu', 'l2b_su3.cu', 'l2b_u1.cu']
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+    '-std=c++17', '-Xcompiler', '-fPIC',
+]
+
+
+def _nvcc() -> str:
+    exe = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(exe):
+        raise RuntimeError('nvcc not found: cannot build libl2b.so')
+    return exe
+
+
+def _stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    deps = list(CSRC.glob('*.cu')) + list(CSRC.glob('*.cuh')) + [PKG.parent / 'include' / 'l2b.h']
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not _stale():
+        return LIB
+    nvcc = _nvcc()
+    objdir = PKG / 'build'
+    objdir.mkdir(exist_ok=True)
+
+    def compile_one(src: str) -> Path:
+        obj = objdir / (src + '.o')
+        cmd = [nvcc, *NVCC_FLAGS, '-c', str(CSRC / src), '-o', str(obj)]
+        if verbose:
+            cmd[1:1] = ['-Xptxas', '-v']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {src}:\n{r.stdout}\n{r.stderr}')
+        if verbose:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, '-shared', '-o', str(LIB), *map(str, objs)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f'link failed:\n{r.stdout}\n{r.stderr}')
+    return LIB
+
+
+if __name__ == '__main__':
+    import sys
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,120 @@
+"""ctypes binding of libl2b.so (include/l2b.h).
+
+The CUDA library is the product; there is NO CPU fallback.  Importing this
+module where the library has not been built, or calling into it without a CUDA
+device, raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_size_t, c_uint64, c_void_p, POINTER
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / 'libl2b.so'
+
+L2B_F32, L2B_F64 = 0, 1
+
+
+class L2BError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not LIB_PATH.exists():
+        if os.environ.get('L2B_AUTOBUILD', '1') == '1':
+            from . import _build
+            _build.build()
+        if not LIB_PATH.exists():
+            raise L2BError(
+                f'{LIB_PATH} is missing: build it with `python -m l2hmc_b200._build` '
+                '(or __graft_entry__.build()); there is no CPU fallback')
+    return ctypes.CDLL(str(LIB_PATH))
+
+
+_lib = _load()
+
+_P = c_void_p
+_DIMS = POINTER(c_int)
+# name -> argtypes (restype is int unless listed in _RES)
+_SIGS = {
+    'l2b_su3_aos_to_soa': [_P, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_soa_to_aos': [_P, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_wilson_loops': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_plaq_sums': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_force': [_P, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_exp': [_P, c_double, _P, c_size_t, c_int, _P],
+    'l2b_su3_update_gauge': [_P, _P, c_double, _P, c_int, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_project': [_P, _P, _P, c_size_t, c_int, _P],
+    'l2b_su3_to_vec': [_P, _P, c_size_t, c_int, _P],
+    'l2b_su3_from_vec': [_P, _P, c_size_t, c_int, _P],
+    'l2b_su3_tah': [_P, _P, c_size_t, c_int, _P],
+    'l2b_su3_kinetic': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_check': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_rand_momentum': [c_uint64, c_uint64, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
+    'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_observables': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_force': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_xupdate': [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_kinetic': [_P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_compat_proj': [_P, _P, c_size_t, c_int, _P],
+    'l2b_accept_mix': [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_size_t), c_int, _P, c_int, _P],
+}
+_RES = {
+    'l2b_last_error': ([], c_char_p),
+    'l2b_version': ([], c_int),
+    'l2b_launch_count': ([], c_uint64),
+    'l2b_su3_ws_bytes': ([c_int, _DIMS, c_int], c_size_t),
+    'l2b_u1_ws_bytes': ([c_int, c_int, c_int, c_int], c_size_t),
+}
+
+EXPORTS = sorted(list(_SIGS) + list(_RES))
+
+for _name, _args in _SIGS.items():
+    _f = getattr(_lib, _name)
+    _f.argtypes = _args
+    _f.restype = c_int
+for _name, (_args, _res) in _RES.items():
+    _f = getattr(_lib, _name)
+    _f.argtypes = _args
+    _f.restype = _res
+
+
+def last_error() -> str:
+    return (_lib.l2b_last_error() or b'').decode()
+
+
+def version() -> int:
+    return int(_lib.l2b_version())
+
+
+def launch_count() -> int:
+    return int(_lib.l2b_launch_count())
+
+
+def dims4(shape) -> ctypes.Array:
+    assert len(shape) == 4
+    return (c_int * 4)(*[int(s) for s in shape])
+
+
+def su3_ws_bytes(nb: int, shape) -> int:
+    n = int(_lib.l2b_su3_ws_bytes(int(nb), dims4(shape), L2B_F64))
+    if n == 0:
+        raise L2BError(f'l2b_su3_ws_bytes: {last_error()}')
+    return n
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point; raise L2BError with the library's
+    message on a non-zero return (the reference's error style is Python
+    exceptions/asserts, dynamics.py:1268, configs.py:482)."""
+    rc = getattr(_lib, name)(*args)
+    if rc != 0:
+        raise L2BError(f'{name} failed (rc={rc}): {last_error()}')

@@ -1,0 +1,841 @@
+// l2b_su3.cu -- sm_100a kernels + C ABI for the 4-D SU(3) leapfrog hot path.
+//
+// Kernel inventory (DESIGN.md has the roofline of each):
+//   k_aos_to_soa / k_soa_to_aos   boundary layout <-> planar layout (+ |P|^2 partials)
+//   k_force                       staples -> (beta/3) TAH(U A), fused momentum kick,
+//                                 fused Wilson-action and kinetic-energy partial sums
+//   k_drift                       U <- exp(eps P) U  (Cayley-Hamilton exponential)
+//   k_plaq                        plaquette traces / per-chain sums
+//   k_update_gauge, k_project, k_vupdate, ... link-local ops on the boundary layout,
+//                                 staged through shared memory so that global traffic is
+//                                 contiguous 128-bit accesses while each thread keeps a
+//                                 whole 3x3 matrix in registers
+//   k_reduce_affine               deterministic second reduction stage
+//
+// Reference functions each entry point replaces are listed in include/l2b.h.
+#include "l2b_common.cuh"
+#include "l2b_su3_site.cuh"
+
+namespace l2b {
+namespace {
+
+using T = double;
+using C = double2;
+constexpr int NTL = 128;       // threads (= links) per block of the link-local kernels
+constexpr int FORCE_TS = 32;   // sites per block of k_force (block = FORCE_TS x 4 directions)
+
+// ---------------------------------------------------------------------------
+// shared-memory staging of the interleaved (AoS) layout
+// ---------------------------------------------------------------------------
+template <int NT, typename E>
+__device__ __forceinline__ void stage_in(E* sm, const E* __restrict__ g, size_t first_item, int nitems, int width) {
+  const E* src = g + first_item * width;
+  const int n = nitems * width;
+  for (int k = threadIdx.x; k < n; k += NT) sm[k] = __ldg(src + k);
+}
+template <int NT, typename E>
+__device__ __forceinline__ void stage_out(E* __restrict__ g, const E* sm, size_t first_item, int nitems, int width) {
+  E* dst = g + first_item * width;
+  const int n = nitems * width;
+  for (int k = threadIdx.x; k < n; k += NT) dst[k] = sm[k];
+}
+__device__ __forceinline__ void sm_get(Mat3<T>& m, const C* sm, int i) {
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { const C v = sm[i * 9 + e]; m.re[e] = v.x; m.im[e] = v.y; }
+}
+__device__ __forceinline__ void sm_put(C* sm, int i, const Mat3<T>& m) {
+#pragma unroll
+  for (int e = 0; e < 9; ++e) sm[i * 9 + e] = make_double2(m.re[e], m.im[e]);
+}
+// load this thread's matrix out of a contiguous run of `n` AoS matrices
+template <int NT>
+__device__ __forceinline__ void block_load_mat(Mat3<T>& m, C* sm, const C* g, size_t first, int n) {
+  stage_in<NT>(sm, g, first, n, 9);
+  __syncthreads();
+  if ((int)threadIdx.x < n) sm_get(m, sm, threadIdx.x);
+  __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ void block_store_mat(C* g, C* sm, const Mat3<T>& m, size_t first, int n) {
+  if ((int)threadIdx.x < n) sm_put(sm, threadIdx.x, m);
+  __syncthreads();
+  stage_out<NT>(g, sm, first, n, 9);
+  __syncthreads();
+}
+template <int NT>
+__device__ __forceinline__ void block_load_real9(T r[9], T* sm, const T* g, size_t first, int n) {
+  if (g == nullptr) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) r[e] = T(0);
+    return;                                  // uniform across the block
+  }
+  stage_in<NT>(sm, g, first, n, 9);
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) r[e] = sm[threadIdx.x * 9 + e];
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------
+template <bool WITH_NORM2>
+__global__ void __launch_bounds__(NTL) k_aos_to_soa(const C* __restrict__ aos, C* __restrict__ soa, int V,
+                                                    double* __restrict__ part) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const int plane = blockIdx.y;            // b * 4 + mu
+  const int site0 = blockIdx.x * NTL;
+  const int n = min(NTL, V - site0);
+  stage_in<NTL>(sm, aos, (size_t)plane * V + site0, n, 9);
+  __syncthreads();
+  double acc = 0.0;
+  if ((int)threadIdx.x < n) {
+    C* out = soa + (size_t)plane * 9 * V + site0 + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const C v = sm[threadIdx.x * 9 + e];
+      out[(size_t)e * V] = v;
+      if (WITH_NORM2) { acc = fma(v.x, v.x, acc); acc = fma(v.y, v.y, acc); }
+    }
+  }
+  if (WITH_NORM2) {
+    // per link (|P|_F^2 - 8), as the reference sums it (group.py:125-126)
+    if ((int)threadIdx.x < n) acc -= 8.0;
+    acc = block_sum<NTL>(acc, red, threadIdx.x);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(NTL) k_soa_to_aos(const C* __restrict__ soa, C* __restrict__ aos, int V) {
+  __shared__ C sm[NTL * 9];
+  const int plane = blockIdx.y;
+  const int site0 = blockIdx.x * NTL;
+  const int n = min(NTL, V - site0);
+  if ((int)threadIdx.x < n) {
+    const C* in = soa + (size_t)plane * 9 * V + site0 + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) sm[threadIdx.x * 9 + e] = __ldg(in + (size_t)e * V);
+  }
+  __syncthreads();
+  stage_out<NTL>(aos, sm, (size_t)plane * V + site0, n, 9);
+}
+
+// ---------------------------------------------------------------------------
+// force (+ kick) on the planar layout.  Block = FORCE_TS consecutive sites x 4
+// directions: the four warps that share a site neighbourhood run together so the
+// 18 neighbour matrices of a link are mostly served by L1.
+// ---------------------------------------------------------------------------
+template <int TS, bool KICK>
+__global__ void __launch_bounds__(TS * 4) k_force(const C* __restrict__ U, C* __restrict__ P, Lat lat, double coef,
+                                                  double* __restrict__ part) {
+  __shared__ double red[TS * 4 / 32];
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  const int tid = threadIdx.y * TS + threadIdx.x;
+  double retr = 0.0, p2 = 0.0;
+  if (site < lat.V) {
+    Mat3<T> g, f;
+    link_times_staples<T, C>(g, U, lat, b, mu, site);
+    retr = re_trace(g);
+    project_tah(f, g);
+    C* pp = soa_plane(P, lat, b, mu) + site;
+    const size_t V = lat.V;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      C v;
+      if (KICK) {
+        v = pp[e * V];
+        v.x = fma(-coef, f.re[e], v.x);
+        v.y = fma(-coef, f.im[e], v.y);
+        p2 = fma(v.x, v.x, p2);
+        p2 = fma(v.y, v.y, p2);
+      } else {
+        v.x = coef * f.re[e];
+        v.y = coef * f.im[e];
+      }
+      pp[e * V] = v;
+    }
+    if (KICK) p2 -= 8.0;   // per link (|P|_F^2 - 8), group.py:125-126
+  }
+  if (part != nullptr) {
+    retr = block_sum<TS * 4>(retr, red, tid);
+    p2 = block_sum<TS * 4>(p2, red, tid);
+    if (tid == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = retr;
+      o[1] = p2;
+    }
+  }
+}
+
+// U <- exp(eps P) U on the planar layout
+__global__ void __launch_bounds__(128, 4) k_drift(C* __restrict__ U, const C* __restrict__ P, int V, double eps) {
+  const int plane = blockIdx.y;
+  const int site = blockIdx.x * 128 + threadIdx.x;
+  if (site >= V) return;
+  const C* pp = P + (size_t)plane * 9 * V;
+  C* up = U + (size_t)plane * 9 * V;
+  Mat3<T> p, ex, u, r;
+  soa_load(p, pp, V, site);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { p.re[e] *= eps; p.im[e] *= eps; }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { const C v = up[(size_t)e * V + site]; u.re[e] = v.x; u.im[e] = v.y; }
+  mat_exp(ex, p);
+  mat_mul<false, false, false>(r, ex, u);
+  soa_store(up, V, site, r);
+}
+
+// plaquette traces: per-chain partial sums and (optionally) the full wloops tensor
+template <bool WRITE_LOOPS>
+__global__ void __launch_bounds__(128) k_plaq(const C* __restrict__ U, Lat lat, double* __restrict__ part,
+                                              C* __restrict__ wloops, int nb) {
+  __shared__ double red[4];
+  const int b = blockIdx.y;
+  const int site = blockIdx.x * 128 + threadIdx.x;
+  double sr = 0.0, si = 0.0;
+  if (site < lat.V) {
+    T tr[6], ti[6];
+    site_plaquette_traces<T, C>(tr, ti, U, lat, b, site);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      sr += tr[p];
+      si += ti[p];
+      if (WRITE_LOOPS) wloops[((size_t)p * nb + b) * lat.V + site] = make_double2(tr[p], ti[p]);
+    }
+  }
+  if (part != nullptr) {
+    sr = block_sum<128>(sr, red, threadIdx.x);
+    si = block_sum<128>(si, red, threadIdx.x);
+    if (threadIdx.x == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = sr;
+      o[1] = si;
+    }
+  }
+}
+
+// out[b*out_stride + out_off] = scale * sum_j part[(b*nblk + j)*ncomp + comp] + shift
+__global__ void __launch_bounds__(256) k_reduce_affine(const double* __restrict__ part, int nblk, int ncomp, int comp,
+                                                       double scale, double shift, double* __restrict__ out,
+                                                       int out_stride, int out_off) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < nblk; j += 256) acc += part[((size_t)b * nblk + j) * ncomp + comp];
+  acc = block_sum<256>(acc, red, threadIdx.x);
+  if (threadIdx.x == 0) out[(size_t)b * out_stride + out_off] = fma(scale, acc, shift);
+}
+
+// ---------------------------------------------------------------------------
+// link-local kernels on the boundary (AoS) layout.  grid.x covers `n_per_row`
+// matrices of one row (a chain, or the whole array when rows == 1), grid.y = rows.
+// ---------------------------------------------------------------------------
+enum UnaryOp { OP_EXP = 0, OP_TAH = 1, OP_PROJECT = 2, OP_TOVEC = 3 };
+
+template <int OP>
+__global__ void __launch_bounds__(NTL) k_unary(const C* __restrict__ x, C* __restrict__ out, T* __restrict__ vec8,
+                                               size_t nmat, double scale) {
+  __shared__ C sm[NTL * 9];
+  const size_t first = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, nmat - first);
+  Mat3<T> m, r;
+  block_load_mat<NTL>(m, sm, x, first, n);
+  const bool live = (int)threadIdx.x < n;
+  if (live) {
+    if (OP == OP_EXP) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { m.re[e] *= scale; m.im[e] *= scale; }
+      mat_exp(r, m);
+    } else if (OP == OP_TAH) {
+      project_tah(r, m);
+    } else if (OP == OP_PROJECT) {
+      project_su(r, m);
+    } else {
+      r = m;
+    }
+    if (vec8 != nullptr) {
+      T v[8];
+      su3_to_vec(v, r);
+      double2* o = reinterpret_cast<double2*>(vec8 + (first + threadIdx.x) * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    }
+  }
+  if (out != nullptr) block_store_mat<NTL>(out, sm, r, first, n);
+}
+
+__global__ void __launch_bounds__(NTL) k_from_vec(const T* __restrict__ vec8, C* __restrict__ out, size_t nmat) {
+  __shared__ C sm[NTL * 9];
+  const size_t first = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, nmat - first);
+  Mat3<T> m;
+  if ((int)threadIdx.x < n) {
+    T v[8];
+    const double2* in = reinterpret_cast<const double2*>(vec8 + (first + threadIdx.x) * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double2 w = __ldg(in + k); v[2 * k] = w.x; v[2 * k + 1] = w.y; }
+    vec_to_su3(m, v);
+  }
+  block_store_mat<NTL>(out, sm, m, first, n);
+}
+
+// x_out = m*x + exp(eps p) ((1-m)*x)   (mask == nullptr: x_out = exp(eps p) x)
+__global__ void __launch_bounds__(NTL) k_update_gauge(const C* __restrict__ x, const C* __restrict__ p, double eps,
+                                                      const float* __restrict__ mask, int mask_complement,
+                                                      C* __restrict__ out, size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;               // link index inside the chain
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> X, Pm, E, R;
+  block_load_mat<NTL>(Pm, sm, p, row0 + l0, n);
+  block_load_mat<NTL>(X, sm, x, row0 + l0, n);
+  if ((int)threadIdx.x < n) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { Pm.re[e] *= eps; Pm.im[e] *= eps; }
+    mat_exp(E, Pm);
+    if (mask == nullptr) {
+      mat_mul<false, false, false>(R, E, X);
+    } else {
+      Mat3<T> Xm, Xb;
+      const float* mk = mask + (l0 + threadIdx.x) * 9;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        float m = __ldg(mk + e);
+        if (mask_complement) m = 1.0f - m;
+        const T md = (T)m, mb = (T)(1.0f - m);
+        Xm.re[e] = md * X.re[e]; Xm.im[e] = md * X.im[e];
+        Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+      }
+      R = Xm;
+      mat_mul<false, false, true>(R, E, Xb);
+    }
+  }
+  block_store_mat<NTL>(out, sm, R, row0 + l0, n);
+}
+
+// L2HMC momentum update epilogue (see l2b.h)
+__global__ void __launch_bounds__(NTL) k_vupdate(const C* __restrict__ v, const C* __restrict__ f,
+                                                 const T* __restrict__ s, const T* __restrict__ t,
+                                                 const T* __restrict__ q, double eps, int sign, C* __restrict__ out,
+                                                 double* __restrict__ part, size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> Vm, Fm, R;
+  T sv[9], tv[9], qv[9];
+  block_load_mat<NTL>(Vm, sm, v, row0 + l0, n);
+  block_load_mat<NTL>(Fm, sm, f, row0 + l0, n);
+  T* smr = reinterpret_cast<T*>(sm);
+  block_load_real9<NTL>(sv, smr, s, row0 + l0, n);
+  block_load_real9<NTL>(tv, smr, t, row0 + l0, n);
+  block_load_real9<NTL>(qv, smr, q, row0 + l0, n);
+  double ld = 0.0;
+  if ((int)threadIdx.x < n) {
+    const T sg = (T)sign;
+    const T he = T(0.5) * eps;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const T logjac = sg * eps * sv[e] / T(2);
+      ld += logjac;
+      const T es = exp(logjac);
+      const T eq = exp(eps * qv[e]);
+      const T fr = fma(Fm.re[e], eq, tv[e]);     // t is real: it only shifts the real part
+      const T fi = Fm.im[e] * eq;
+      if (sign > 0) {
+        R.re[e] = es * Vm.re[e] - he * fr;
+        R.im[e] = es * Vm.im[e] - he * fi;
+      } else {
+        R.re[e] = es * (Vm.re[e] + he * fr);
+        R.im[e] = es * (Vm.im[e] + he * fi);
+      }
+    }
+  }
+  block_store_mat<NTL>(out, sm, R, row0 + l0, n);
+  if (part != nullptr) {
+    ld = block_sum<NTL>(ld, red, threadIdx.x);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = ld;
+  }
+}
+
+// sum |p|^2 over a chain row of `row_len` complex numbers (layout agnostic)
+__global__ void __launch_bounds__(256) k_norm2_rows(const C* __restrict__ p, size_t row_len, double* __restrict__ part) {
+  __shared__ double red[8];
+  const C* row = p + (size_t)blockIdx.y * row_len;
+  double acc = 0.0;
+  for (size_t k = (size_t)blockIdx.x * 256 + threadIdx.x; k < row_len; k += (size_t)gridDim.x * 256) {
+    const C v = __ldg(row + k);
+    acc += fma(v.x, v.x, fma(v.y, v.y, -8.0 / 9.0));   // 9 entries per link share the -8
+  }
+  acc = block_sum<256>(acc, red, threadIdx.x);
+  if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// checkSU partials: (sum d, max d) per block
+__global__ void __launch_bounds__(NTL) k_check(const C* __restrict__ x, double* __restrict__ part,
+                                               size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> X;
+  block_load_mat<NTL>(X, sm, x, row0 + l0, n);
+  double d = 0.0;
+  if ((int)threadIdx.x < n) d = check_su_dev(X);
+  const double dsum = block_sum<NTL>(d, red, threadIdx.x);
+  const double dmax = block_max<NTL>(d, red, threadIdx.x);
+  if (threadIdx.x == 0) {
+    double* o = part + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    o[0] = dsum;
+    o[1] = dmax;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_check_final(const double* __restrict__ part, int nblk, double nlinks,
+                                                     double* __restrict__ avg, double* __restrict__ mx) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  double s = 0.0, m = 0.0;
+  for (int j = threadIdx.x; j < nblk; j += 256) {
+    s += part[((size_t)b * nblk + j) * 2];
+    m = max(m, part[((size_t)b * nblk + j) * 2 + 1]);
+  }
+  s = block_sum<256>(s, red, threadIdx.x);
+  m = block_max<256>(m, red, threadIdx.x);
+  if (threadIdx.x == 0) {
+    const double c = 2.0 * (3 * 3 + 1);
+    avg[b] = sqrt(s / nlinks / c);
+    mx[b] = sqrt(m / c);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 Gaussian momenta
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// two 32-bit words -> uniform double in (0, 1)
+__device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
+  const unsigned long long z = ((unsigned long long)a << 32) | b;
+  return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t offset, C* __restrict__ p,
+                                                       double* __restrict__ part, size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> m;
+  double acc = 0.0;
+  if ((int)threadIdx.x < n) {
+    const uint64_t link = row0 + l0 + threadIdx.x;
+    T nrm[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t c[4] = {(uint32_t)link, (uint32_t)(link >> 32), (uint32_t)(offset * 4 + k), (uint32_t)((offset * 4 + k) >> 32)};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const double u1 = u01(c[0], c[1]), u2 = u01(c[2], c[3]);
+      const double r = sqrt(-2.0 * log(u1));
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      nrm[2 * k] = r * cs;
+      nrm[2 * k + 1] = r * sn;
+    }
+    tah_from_normals(m, nrm);
+    acc = norm2(m) - 8.0;
+  }
+  block_store_mat<NTL>(p, sm, m, row0 + l0, n);
+  if (part != nullptr) {
+    acc = block_sum<NTL>(acc, red, threadIdx.x);
+    if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------
+struct Geo {
+  Lat lat;
+  int nb;
+  size_t links_per_chain;   // 4 V
+  size_t field_elems;       // nb * 4 * V * 9 complex numbers
+  int nblk_force;           // blocks per chain of k_force
+  int nblk_link;            // blocks per chain of link-local kernels
+  int nblk_conv;            // blocks per (chain, mu) plane of the converters
+  int nblk_plaq;
+  size_t part_elems;        // doubles reserved for partials
+};
+
+int make_geo(Geo& g, int nb, const int dims[4], int dtype) {
+  L2B_REQUIRE(dims != nullptr, L2B_ERR_INVALID, "dims is NULL");
+  L2B_REQUIRE(nb > 0 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0 && dims[3] > 0, L2B_ERR_INVALID,
+              "non-positive size: nb=%d dims=%d,%d,%d,%d", nb, dims[0], dims[1], dims[2], dims[3]);
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only (got dtype=%d)", dtype);
+  const long long V = (long long)dims[0] * dims[1] * dims[2] * dims[3];
+  L2B_REQUIRE(V * 9 < (1ll << 31), L2B_ERR_UNSUPPORTED, "lattice volume %lld too large for 32-bit site index", V);
+  L2B_REQUIRE(nb * 4 <= 65535, L2B_ERR_UNSUPPORTED, "nb=%d exceeds grid.y limit (16383 chains per call)", nb);
+  g.lat = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  g.nb = nb;
+  g.links_per_chain = (size_t)4 * V;
+  g.field_elems = (size_t)nb * 4 * V * 9;
+  g.nblk_force = (int)((V + FORCE_TS - 1) / FORCE_TS);
+  g.nblk_link = (int)((4 * V + NTL - 1) / NTL);
+  g.nblk_conv = (int)((V + NTL - 1) / NTL);
+  g.nblk_plaq = (int)((V + 127) / 128);
+  size_t per_chain = (size_t)g.nblk_force * 2;
+  if ((size_t)g.nblk_link * 2 > per_chain) per_chain = (size_t)g.nblk_link * 2;
+  if ((size_t)g.nblk_conv * 4 > per_chain) per_chain = (size_t)g.nblk_conv * 4;
+  g.part_elems = per_chain * nb;
+  return L2B_OK;
+}
+
+size_t ws_bytes_of(const Geo& g) {
+  return 2 * align_up(g.field_elems * sizeof(C), 256) + align_up(g.part_elems * sizeof(double), 256);
+}
+
+struct Ws {
+  C* f0;
+  C* f1;
+  double* part;
+};
+
+int carve(Ws& w, const Geo& g, void* ws, size_t ws_bytes) {
+  L2B_REQUIRE(ws != nullptr, L2B_ERR_INVALID, "workspace is NULL");
+  L2B_REQUIRE(((uintptr_t)ws & 255) == 0, L2B_ERR_INVALID, "workspace must be 256-byte aligned");
+  L2B_REQUIRE(ws_bytes >= ws_bytes_of(g), L2B_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, ws_bytes_of(g));
+  char* p = (char*)ws;
+  w.f0 = (C*)p; p += align_up(g.field_elems * sizeof(C), 256);
+  w.f1 = (C*)p; p += align_up(g.field_elems * sizeof(C), 256);
+  w.part = (double*)p;
+  return L2B_OK;
+}
+
+int launch_a2s(const Geo& g, const C* aos, C* soa, double* part, cudaStream_t st) {
+  dim3 grid(g.nblk_conv, g.nb * 4);
+  if (part) k_aos_to_soa<true><<<grid, NTL, 0, st>>>(aos, soa, g.lat.V, part);
+  else k_aos_to_soa<false><<<grid, NTL, 0, st>>>(aos, soa, g.lat.V, nullptr);
+  L2B_LAUNCHED("k_aos_to_soa");
+  return L2B_OK;
+}
+int launch_s2a(const Geo& g, const C* soa, C* aos, cudaStream_t st) {
+  dim3 grid(g.nblk_conv, g.nb * 4);
+  k_soa_to_aos<<<grid, NTL, 0, st>>>(soa, aos, g.lat.V);
+  L2B_LAUNCHED("k_soa_to_aos");
+  return L2B_OK;
+}
+int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double* part, cudaStream_t st) {
+  dim3 grid(g.nblk_force, g.nb), block(FORCE_TS, 4);
+  if (kick) k_force<FORCE_TS, true><<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
+  else k_force<FORCE_TS, false><<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
+  L2B_LAUNCHED("k_force");
+  return L2B_OK;
+}
+int launch_reduce(const double* part, int nblk, int ncomp, int comp, double scale, double shift, double* out,
+                  int out_stride, int out_off, int nb, cudaStream_t st) {
+  k_reduce_affine<<<nb, 256, 0, st>>>(part, nblk, ncomp, comp, scale, shift, out, out_stride, out_off);
+  L2B_LAUNCHED("k_reduce_affine");
+  return L2B_OK;
+}
+
+#define L2B_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != L2B_OK) return rc__; \
+  } while (0)
+
+}  // namespace
+}  // namespace l2b
+
+using namespace l2b;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+size_t l2b_su3_ws_bytes(int nb, const int dims[4], int dtype) {
+  Geo g;
+  if (make_geo(g, nb, dims, dtype) != L2B_OK) return 0;
+  return ws_bytes_of(g);
+}
+
+int l2b_su3_aos_to_soa(const void* x_aos, void* x_soa, int nb, const int dims[4], int dtype, void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_aos && x_soa, L2B_ERR_INVALID, "null field pointer");
+  return launch_a2s(g, (const C*)x_aos, (C*)x_soa, nullptr, (cudaStream_t)stream);
+}
+
+int l2b_su3_soa_to_aos(const void* x_soa, void* x_aos, int nb, const int dims[4], int dtype, void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_aos && x_soa, L2B_ERR_INVALID, "null field pointer");
+  return launch_s2a(g, (const C*)x_soa, (C*)x_aos, (cudaStream_t)stream);
+}
+
+int l2b_su3_wilson_loops(const void* x, void* wloops, int nb, const int dims[4], int dtype, void* ws,
+                         size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && wloops, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  k_plaq<true><<<dim3(g.nblk_plaq, nb), 128, 0, st>>>(w.f0, g.lat, nullptr, (C*)wloops, nb);
+  L2B_LAUNCHED("k_plaq");
+  return L2B_OK;
+}
+
+int l2b_su3_plaq_sums(const void* x, double* sums, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes,
+                      void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && sums, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  k_plaq<false><<<dim3(g.nblk_plaq, nb), 128, 0, st>>>(w.f0, g.lat, w.part, nullptr, nb);
+  L2B_LAUNCHED("k_plaq");
+  L2B_TRY(launch_reduce(w.part, g.nblk_plaq, 2, 0, 1.0, 0.0, sums, 2, 0, nb, st));
+  L2B_TRY(launch_reduce(w.part, g.nblk_plaq, 2, 1, 1.0, 0.0, sums, 2, 1, nb, st));
+  return L2B_OK;
+}
+
+int l2b_su3_force(const void* x, double beta, void* force, double* plaq_sum_or_null, int nb, const int dims[4],
+                  int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && force, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  L2B_TRY(launch_force(g, w.f0, w.f1, false, beta / 3.0, plaq_sum_or_null ? w.part : nullptr, st));
+  if (plaq_sum_or_null)  // sum_links Re tr(U A) counts every plaquette four times
+    L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, 0.25, 0.0, plaq_sum_or_null, 1, 0, nb, st));
+  return launch_s2a(g, w.f1, (C*)force, st);
+}
+
+int l2b_su3_exp(const void* p, double scale, void* out, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(p && out, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_unary<OP_EXP><<<nblk, NTL, 0, (cudaStream_t)stream>>>((const C*)p, (C*)out, nullptr, nmat, scale);
+  L2B_LAUNCHED("k_unary<exp>");
+  return L2B_OK;
+}
+
+int l2b_su3_tah(const void* x, void* out, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && out, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_unary<OP_TAH><<<nblk, NTL, 0, (cudaStream_t)stream>>>((const C*)x, (C*)out, nullptr, nmat, 1.0);
+  L2B_LAUNCHED("k_unary<tah>");
+  return L2B_OK;
+}
+
+int l2b_su3_project(const void* x, void* x_proj_or_null, void* vec8_or_null, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && (x_proj_or_null || vec8_or_null), L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_unary<OP_PROJECT><<<nblk, NTL, 0, (cudaStream_t)stream>>>((const C*)x, (C*)x_proj_or_null, (T*)vec8_or_null, nmat, 1.0);
+  L2B_LAUNCHED("k_unary<project>");
+  return L2B_OK;
+}
+
+int l2b_su3_to_vec(const void* x, void* vec8, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && vec8, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_unary<OP_TOVEC><<<nblk, NTL, 0, (cudaStream_t)stream>>>((const C*)x, nullptr, (T*)vec8, nmat, 1.0);
+  L2B_LAUNCHED("k_unary<tovec>");
+  return L2B_OK;
+}
+
+int l2b_su3_from_vec(const void* vec8, void* x, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && vec8, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_from_vec<<<nblk, NTL, 0, (cudaStream_t)stream>>>((const T*)vec8, (C*)x, nmat);
+  L2B_LAUNCHED("k_from_vec");
+  return L2B_OK;
+}
+
+int l2b_su3_update_gauge(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+                         void* x_out, int nb, const int dims[4], int dtype, void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x && p && x_out, L2B_ERR_INVALID, "null pointer");
+  k_update_gauge<<<dim3(g.nblk_link, nb), NTL, 0, (cudaStream_t)stream>>>((const C*)x, (const C*)p, eps, mask,
+                                                                          mask_complement, (C*)x_out,
+                                                                          g.links_per_chain);
+  L2B_LAUNCHED("k_update_gauge");
+  return L2B_OK;
+}
+
+int l2b_su3_kinetic(const void* p, double* ke, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes,
+                    void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(p && ke, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t row = g.links_per_chain * 9;
+  int nblk = (int)((row + 256 * 8 - 1) / (256 * 8));
+  if (nblk > g.nblk_link) nblk = g.nblk_link;
+  if (nblk < 1) nblk = 1;
+  k_norm2_rows<<<dim3(nblk, nb), 256, 0, st>>>((const C*)p, row, w.part);
+  L2B_LAUNCHED("k_norm2_rows");
+  return launch_reduce(w.part, nblk, 1, 0, 0.5, 0.0, ke, 1, 0, nb, st);
+}
+
+int l2b_su3_check(const void* x, double* avg, double* mx, int nb, const int dims[4], int dtype, void* ws,
+                  size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && avg && mx, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_check<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, w.part, g.links_per_chain);
+  L2B_LAUNCHED("k_check");
+  k_check_final<<<nb, 256, 0, st>>>(w.part, g.nblk_link, (double)g.links_per_chain, avg, mx);
+  L2B_LAUNCHED("k_check_final");
+  return L2B_OK;
+}
+
+int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or_null, int nb, const int dims[4],
+                          int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(p, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  if (ke_or_null) {
+    L2B_TRY(carve(w, g, ws, ws_bytes));
+    part = w.part;
+  }
+  k_rand_momentum<<<dim3(g.nblk_link, nb), NTL, 0, st>>>(seed, offset, (C*)p, part, g.links_per_chain);
+  L2B_LAUNCHED("k_rand_momentum");
+  if (ke_or_null)
+    L2B_TRY(launch_reduce(part, g.nblk_link, 1, 0, 0.5, 0.0, ke_or_null, 1, 0, nb, st));
+  return L2B_OK;
+}
+
+int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                    int sign, void* v_out, double* logdet, int nb, const int dims[4], int dtype, void* ws,
+                    size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(v && force && v_out, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  if (logdet) {
+    L2B_TRY(carve(w, g, ws, ws_bytes));
+    part = w.part;
+  }
+  k_vupdate<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)v, (const C*)force, (const T*)s, (const T*)t,
+                                                   (const T*)q, eps, sign, (C*)v_out, part, g.links_per_chain);
+  L2B_LAUNCHED("k_vupdate");
+  if (logdet) L2B_TRY(launch_reduce(part, g.nblk_link, 1, 0, 1.0, 0.0, logdet, 1, 0, nb, st));
+  return L2B_OK;
+}
+
+int l2b_su3_force_kick_planar(const void* u_planar, void* p_planar, double beta, double eps_kick,
+                              double* sums_or_null, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes,
+                              void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(u_planar && p_planar, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  if (sums_or_null) {
+    L2B_TRY(carve(w, g, ws, ws_bytes));
+    part = w.part;
+  }
+  L2B_TRY(launch_force(g, (const C*)u_planar, (C*)p_planar, true, eps_kick * beta / 3.0, part, st));
+  if (sums_or_null) {
+    L2B_TRY(launch_reduce(part, g.nblk_force, 2, 0, 0.25, 0.0, sums_or_null, 2, 0, nb, st));
+    L2B_TRY(launch_reduce(part, g.nblk_force, 2, 1, 1.0, 0.0, sums_or_null, 2, 1, nb, st));
+  }
+  return L2B_OK;
+}
+
+int l2b_su3_drift_planar(void* u_planar, const void* p_planar, double eps, int nb, const int dims[4], int dtype,
+                         void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(u_planar && p_planar, L2B_ERR_INVALID, "null pointer");
+  k_drift<<<dim3((g.lat.V + 127) / 128, nb * 4), 128, 0, (cudaStream_t)stream>>>((C*)u_planar, (const C*)p_planar,
+                                                                                 g.lat.V, eps);
+  L2B_LAUNCHED("k_drift");
+  return L2B_OK;
+}
+
+int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps, int nlf, void* x_prop,
+                           void* v_prop, double* energies, int nb, const int dims[4], int dtype, void* ws,
+                           size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && v && x_prop && v_prop && energies, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nlf >= 1, L2B_ERR_INVALID, "nlf must be >= 1 (got %d)", nlf);
+  cudaStream_t st = (cudaStream_t)stream;
+  C* U = w.f0;
+  C* P = w.f1;
+  const double b3 = beta / 3.0;
+  const double ke_shift = 0.0;  // the -8 per link is already inside the partials
+  // in: boundary layout -> planar; KE0 rides on the momentum conversion
+  L2B_TRY(launch_a2s(g, (const C*)x, U, nullptr, st));
+  L2B_TRY(launch_a2s(g, (const C*)v, P, w.part, st));
+  L2B_TRY(launch_reduce(w.part, g.nblk_conv * 4, 1, 0, 0.5, ke_shift, energies, 4, 0, nb, st));
+  // first half kick; S0 rides on the force evaluation
+  L2B_TRY(launch_force(g, U, P, true, 0.5 * eps * b3, w.part, st));
+  L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 1, nb, st));
+  const dim3 dgrid((g.lat.V + 127) / 128, nb * 4);
+  for (int k = 1; k <= nlf; ++k) {
+    k_drift<<<dgrid, 128, 0, st>>>(U, P, g.lat.V, eps);
+    L2B_LAUNCHED("k_drift");
+    const bool last = (k == nlf);
+    L2B_TRY(launch_force(g, U, P, true, (last ? 0.5 : 1.0) * eps * b3, last ? w.part : nullptr, st));
+  }
+  L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 1, 0.5, ke_shift, energies, 4, 2, nb, st));
+  L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 3, nb, st));
+  L2B_TRY(launch_s2a(g, U, (C*)x_prop, st));
+  L2B_TRY(launch_s2a(g, P, (C*)v_prop, st));
+  return L2B_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// l2b_su3_math.cuh -- per-link 3x3 complex arithmetic for the SU(3) hot path.
+//
+// Everything here is a register-resident, fully unrolled __host__ __device__
+// inline so that (a) the CUDA kernels keep whole matrices in registers and the
+// complex multiply-adds compile to back-to-back DFMA, and (b) the very same
+// arithmetic can be compiled for the host by tests/hostemu to be diffed against
+// the numpy oracle without a GPU.
+//
+// Reference semantics followed (paths relative to /root/reference/src/l2hmc):
+//   mul / adjoint / trace      group/su3/pytorch/group.py:55-75
+//   projectTAH                 group/su3/pytorch/group.py:92-103
+//   exp / update_gauge         group/su3/pytorch/group.py:45-50,88-90 (torch.matrix_exp)
+//   projectSU / eigs3x3 / ...  group/su3/pytorch/utils.py:227-346
+//   su3_to_vec / vec_to_su3    group/su3/pytorch/utils.py:394-445
+//   randTAH3 (layout of the 8 normals)  group/su3/pytorch/utils.py:171-195
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define L2B_HD __host__ __device__ __forceinline__
+#define L2B_UNROLL _Pragma("unroll")
+#else
+#define L2B_HD inline
+#define L2B_UNROLL
+#endif
+
+namespace l2b {
+
+// 3x3 complex matrix, row-major element e = 3*i + j, split re/im so that every
+// scalar lands in its own register.
+template <typename T>
+struct Mat3 {
+  T re[9];
+  T im[9];
+};
+
+template <typename T>
+L2B_HD void mat_zero(Mat3<T>& a) {
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) { a.re[e] = T(0); a.im[e] = T(0); }
+}
+
+template <typename T>
+L2B_HD void mat_identity(Mat3<T>& a) {
+  mat_zero(a);
+  a.re[0] = a.re[4] = a.re[8] = T(1);
+}
+
+// C (+)= op(A) * op(B),  op = identity or conjugate transpose.
+template <bool ADJ_A, bool ADJ_B, bool ACC, typename T>
+L2B_HD void mat_mul(Mat3<T>& c, const Mat3<T>& a, const Mat3<T>& b) {
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      T sr = ACC ? c.re[3 * i + j] : T(0);
+      T si = ACC ? c.im[3 * i + j] : T(0);
+      L2B_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        const int ea = ADJ_A ? (3 * k + i) : (3 * i + k);
+        const int eb = ADJ_B ? (3 * j + k) : (3 * k + j);
+        const T ar = a.re[ea];
+        const T ai = ADJ_A ? -a.im[ea] : a.im[ea];
+        const T br = b.re[eb];
+        const T bi = ADJ_B ? -b.im[eb] : b.im[eb];
+        sr = fma(ar, br, sr);
+        sr = fma(-ai, bi, sr);
+        si = fma(ar, bi, si);
+        si = fma(ai, br, si);
+      }
+      c.re[3 * i + j] = sr;
+      c.im[3 * i + j] = si;
+    }
+  }
+}
+
+// tr(A * B^+) = sum_ij A_ij conj(B_ij)
+template <typename T>
+L2B_HD void trace_mul_adj(const Mat3<T>& a, const Mat3<T>& b, T& tr_re, T& tr_im) {
+  T sr = T(0), si = T(0);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    sr = fma(a.re[e], b.re[e], sr);
+    sr = fma(a.im[e], b.im[e], sr);
+    si = fma(a.im[e], b.re[e], si);
+    si = fma(-a.re[e], b.im[e], si);
+  }
+  tr_re = sr;
+  tr_im = si;
+}
+
+template <typename T>
+L2B_HD T re_trace(const Mat3<T>& a) { return a.re[0] + a.re[4] + a.re[8]; }
+
+template <typename T>
+L2B_HD T norm2(const Mat3<T>& a) {
+  T s = T(0);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) { s = fma(a.re[e], a.re[e], s); s = fma(a.im[e], a.im[e], s); }
+  return s;
+}
+
+// R = (X - X^+)/2 - tr(.)/3       (group.py:92-103)
+template <typename T>
+L2B_HD void project_tah(Mat3<T>& r, const Mat3<T>& x) {
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      r.re[3 * i + j] = T(0.5) * (x.re[3 * i + j] - x.re[3 * j + i]);
+      r.im[3 * i + j] = T(0.5) * (x.im[3 * i + j] + x.im[3 * j + i]);
+    }
+  }
+  // the diagonal of (X - X^+)/2 is purely imaginary
+  const T d = (r.im[0] + r.im[4] + r.im[8]) / T(3);
+  r.im[0] -= d; r.im[4] -= d; r.im[8] -= d;
+}
+
+template <typename T>
+L2B_HD void cmul_(T ar, T ai, T br, T bi, T& cr, T& ci) {
+  cr = ar * br - ai * bi;
+  ci = ar * bi + ai * br;
+}
+
+template <typename T>
+L2B_HD void det3(const Mat3<T>& a, T& dr, T& di) {
+  // cofactor expansion along the first row, complex
+#define cm cmul_<T>
+  T m0r, m0i, m1r, m1i, t0r, t0i, t1r, t1i;
+  // c0 = a11 a22 - a12 a21
+  cm(a.re[4], a.im[4], a.re[8], a.im[8], t0r, t0i);
+  cm(a.re[5], a.im[5], a.re[7], a.im[7], t1r, t1i);
+  m0r = t0r - t1r; m0i = t0i - t1i;
+  cm(a.re[0], a.im[0], m0r, m0i, m1r, m1i);
+  dr = m1r; di = m1i;
+  // c1 = a10 a22 - a12 a20
+  cm(a.re[3], a.im[3], a.re[8], a.im[8], t0r, t0i);
+  cm(a.re[5], a.im[5], a.re[6], a.im[6], t1r, t1i);
+  m0r = t0r - t1r; m0i = t0i - t1i;
+  cm(a.re[1], a.im[1], m0r, m0i, m1r, m1i);
+  dr -= m1r; di -= m1i;
+  // c2 = a10 a21 - a11 a20
+  cm(a.re[3], a.im[3], a.re[7], a.im[7], t0r, t0i);
+  cm(a.re[4], a.im[4], a.re[6], a.im[6], t1r, t1i);
+  m0r = t0r - t1r; m0i = t0i - t1i;
+  cm(a.re[2], a.im[2], m0r, m0i, m1r, m1i);
+  dr += m1r; di += m1i;
+#undef cm
+}
+
+// ---------------------------------------------------------------------------
+// exp(A) for an arbitrary complex 3x3 A (torch.matrix_exp in the reference).
+// Cayley-Hamilton: A^3 = t A^2 - c A + d, so A^n = a_n + b_n A + c_n A^2 with
+//   (a, b, c)_{n+1} = (d c_n, a_n - c c_n, b_n + t c_n),
+// i.e. the Taylor series is summed on three complex scalars instead of on
+// matrices (2 matrix products in total instead of ~18).  |c_n| <= C(n,2) rho^(n-2),
+// so with ||A||_F <= 1 after scaling by 2^-s, 20 terms truncate below 1e-16;
+// the scaling is undone by s squarings.
+// ---------------------------------------------------------------------------
+template <typename T>
+L2B_HD void mat_exp(Mat3<T>& out, const Mat3<T>& ain) {
+  Mat3<T> a = ain;
+  const T n2 = norm2(a);
+  int s = 0;
+  if (n2 > T(1)) {
+    // s = ceil(log2(||A||_F)) = ceil(log2(n2) / 2)
+    int ex;
+    const T fr = frexp(n2, &ex);         // n2 = fr * 2^ex, fr in [0.5, 1)
+    (void)fr;
+    s = (ex + 1) / 2;                    // 2^(2s) >= n2
+    if (s > 60) s = 60;
+    const T sc = ldexp(T(1), -s);
+    L2B_UNROLL
+    for (int e = 0; e < 9; ++e) { a.re[e] *= sc; a.im[e] *= sc; }
+  }
+  Mat3<T> a2;
+  mat_mul<false, false, false>(a2, a, a);
+  // characteristic polynomial coefficients
+  const T tr = a.re[0] + a.re[4] + a.re[8], ti = a.im[0] + a.im[4] + a.im[8];
+  const T t2r = a2.re[0] + a2.re[4] + a2.re[8], t2i = a2.im[0] + a2.im[4] + a2.im[8];
+  // c = (t^2 - tr A^2) / 2
+  const T cr = T(0.5) * (tr * tr - ti * ti - t2r), ci = T(0.5) * (T(2) * tr * ti - t2i);
+  T dr, di;
+  det3(a, dr, di);
+  // running (a_n, b_n, c_n) and their 1/n!-weighted sums
+  T anr = T(0), ani = T(0), bnr = T(0), bni = T(0), cnr = T(1), cni = T(0);  // n = 2
+  T sar = T(1), sai = T(0), sbr = T(1), sbi = T(0), scr = T(0.5), sci = T(0);
+  T inv_fact = T(0.5);
+  L2B_UNROLL
+  for (int n = 3; n <= 20; ++n) {
+    // (a, b, c)_{n} from (a, b, c)_{n-1}
+    const T nar = dr * cnr - di * cni, nai = dr * cni + di * cnr;
+    const T nbr = anr - (cr * cnr - ci * cni), nbi = ani - (cr * cni + ci * cnr);
+    const T ncr = bnr + (tr * cnr - ti * cni), nci = bni + (tr * cni + ti * cnr);
+    anr = nar; ani = nai; bnr = nbr; bni = nbi; cnr = ncr; cni = nci;
+    inv_fact = inv_fact / T(n);
+    sar = fma(inv_fact, anr, sar); sai = fma(inv_fact, ani, sai);
+    sbr = fma(inv_fact, bnr, sbr); sbi = fma(inv_fact, bni, sbi);
+    scr = fma(inv_fact, cnr, scr); sci = fma(inv_fact, cni, sci);
+  }
+  // out = sa + sb A + sc A^2
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    T r = sbr * a.re[e] - sbi * a.im[e];
+    T i = sbr * a.im[e] + sbi * a.re[e];
+    r = fma(scr, a2.re[e], r); r = fma(-sci, a2.im[e], r);
+    i = fma(scr, a2.im[e], i); i = fma(sci, a2.re[e], i);
+    out.re[e] = r; out.im[e] = i;
+  }
+  out.re[0] += sar; out.im[0] += sai;
+  out.re[4] += sar; out.im[4] += sai;
+  out.re[8] += sar; out.im[8] += sai;
+  for (int k = 0; k < s; ++k) {
+    Mat3<T> tmp;
+    mat_mul<false, false, false>(tmp, out, out);
+    out = tmp;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// projectSU  (utils.py:227-346), clamps included
+// ---------------------------------------------------------------------------
+template <typename T>
+L2B_HD void eigs3x3(T tr, T p2, T det, T& e0, T& e1, T& e2) {
+  const T third = T(1) / T(3);
+  const T tr3 = third * tr;
+  const T p23 = third * p2;
+  const T tr32 = tr3 * tr3;
+  const T q = fabs(T(0.5) * (p23 - tr32));
+  const T r = T(0.25) * tr3 * (T(5) * tr32 - p2) - T(0.5) * det;
+  const T sq = sqrt(q);
+  const T sq3 = q * sq;
+  T isq3 = T(1) / sq3;
+  isq3 = fmin(T(3e38), fmax(T(-3e38), isq3));
+  T rsq3 = r * isq3;
+  rsq3 = fmin(T(1), fmax(T(-1), rsq3));
+  const T lim = T(1) - T(1e-12);
+  rsq3 = fmin(lim, fmax(-lim, rsq3));
+  const T t = third * acos(rsq3);
+  const T st = sin(t), ct = cos(t);
+  const T sqc = sq * ct;
+  const T sqs = T(1.7320508075688772935) * sq * st;
+  const T ll = tr3 + sqc;
+  e0 = tr3 - T(2) * sqc;
+  e1 = ll + sqs;
+  e2 = ll - sqs;
+}
+
+template <typename T>
+L2B_HD void rsqrt_phm3_coeffs(T tr, T p2, T det, T& c0, T& c1, T& c2) {
+  T e0, e1, e2;
+  eigs3x3(tr, p2, det, e0, e1, e2);
+  const T se0 = sqrt(fabs(e0)), se1 = sqrt(fabs(e1)), se2 = sqrt(fabs(e2));
+  const T u = se0 + se1 + se2;
+  const T w = se0 * se1 * se2;
+  const T d = w * (se0 + se1) * (se0 + se2) * (se1 + se2);
+  const T di = T(1) / d;
+  c0 = di * (w * u * u + e0 * se0 * (e1 + e2) + e1 * se1 * (e0 + e2) + e2 * se2 * (e0 + e1));
+  c1 = -(tr * u + w) * di;
+  c2 = u * di;
+}
+
+template <typename T>
+L2B_HD void project_su(Mat3<T>& y, const Mat3<T>& x) {
+  Mat3<T> t, t2, r, m;
+  mat_mul<true, false, false>(t, x, x);        // X^+ X
+  mat_mul<false, false, false>(t2, t, t);
+  const T tr = re_trace(t);
+  const T p2 = re_trace(t2);
+  T dr, di;
+  det3(t, dr, di);
+  T c0, c1, c2;
+  rsqrt_phm3_coeffs(tr, p2, dr, c0, c1, c2);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    r.re[e] = fma(c1, t.re[e], c2 * t2.re[e]);
+    r.im[e] = fma(c1, t.im[e], c2 * t2.im[e]);
+  }
+  r.re[0] += c0; r.re[4] += c0; r.re[8] += c0;
+  mat_mul<false, false, false>(m, x, r);       // projectU
+  det3(m, dr, di);
+  const T p = -atan2(di, dr) / T(3);
+  const T cp = cos(p), sp = sin(p);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    y.re[e] = m.re[e] * cp - m.im[e] * sp;
+    y.im[e] = m.re[e] * sp + m.im[e] * cp;
+  }
+}
+
+// checkSU summand: ||X^+X - 1||_F^2 + |det X - 1|^2   (utils.py:376-391)
+template <typename T>
+L2B_HD T check_su_dev(const Mat3<T>& x) {
+  Mat3<T> t;
+  mat_mul<true, false, false>(t, x, x);
+  t.re[0] -= T(1); t.re[4] -= T(1); t.re[8] -= T(1);
+  T dr, di;
+  det3(x, dr, di);
+  dr -= T(1);
+  return norm2(t) + dr * dr + di * di;
+}
+
+// su3_to_vec (utils.py:394-420)
+template <typename T>
+L2B_HD void su3_to_vec(T v[8], const Mat3<T>& x) {
+  v[0] = T(-2) * x.im[1];
+  v[1] = T(-2) * x.re[1];
+  v[2] = x.im[4] - x.im[0];
+  v[3] = T(-2) * x.im[2];
+  v[4] = T(-2) * x.re[2];
+  v[5] = T(-2) * x.im[5];
+  v[6] = T(-2) * x.re[5];
+  v[7] = T(0.57735026918962576451) * (T(2) * x.im[8] - x.im[4] - x.im[0]);
+}
+
+// vec_to_su3 (utils.py:423-445)
+template <typename T>
+L2B_HD void vec_to_su3(Mat3<T>& m, const T v[8]) {
+  const T c = T(-0.5);
+  const T x01r = c * v[1], x01i = c * v[0];
+  const T x02r = c * v[4], x02i = c * v[3];
+  const T x12r = c * v[6], x12i = c * v[5];
+  const T x2i = T(0.57735026918962576451) * v[7];
+  const T x0i = c * (x2i + v[2]);
+  const T x1i = c * (x2i - v[2]);
+  m.re[0] = T(0); m.im[0] = x0i;
+  m.re[4] = T(0); m.im[4] = x1i;
+  m.re[8] = T(0); m.im[8] = x2i;
+  m.re[1] = x01r; m.im[1] = x01i;
+  m.re[2] = x02r; m.im[2] = x02i;
+  m.re[5] = x12r; m.im[5] = x12i;
+  m.re[3] = -x01r; m.im[3] = x01i;   // -conj(x01)
+  m.re[6] = -x02r; m.im[6] = x02i;
+  m.re[7] = -x12r; m.im[7] = x12i;
+}
+
+// randTAH3 with the eight N(0,1) draws explicit, in the reference's draw order
+// (r3, r8, r01, r02, r12, i01, i02, i12)   (utils.py:171-195)
+template <typename T>
+L2B_HD void tah_from_normals(Mat3<T>& m, const T n[8]) {
+  const T s2 = T(0.70710678118654752440);
+  const T s3 = T(0.57735026918962576451);
+  const T r3 = s2 * n[0];
+  const T r8 = s2 * s3 * n[1];
+  m.re[0] = T(0); m.im[0] = r8 + r3;
+  m.re[4] = T(0); m.im[4] = r8 - r3;
+  m.re[8] = T(0); m.im[8] = T(-2) * r8;
+  m.re[1] = s2 * n[2]; m.im[1] = s2 * n[5];
+  m.re[3] = -m.re[1];  m.im[3] = m.im[1];
+  m.re[2] = s2 * n[3]; m.im[2] = s2 * n[6];
+  m.re[6] = -m.re[2];  m.im[6] = m.im[2];
+  m.re[5] = s2 * n[4]; m.im[5] = s2 * n[7];
+  m.re[7] = -m.re[5];  m.im[7] = m.im[5];
+}
+
+}  // namespace l2b

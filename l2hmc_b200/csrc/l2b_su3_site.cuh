@@ -1,0 +1,185 @@
+// l2b_su3_site.cuh -- lattice geometry, the internal planar (SoA) link layout
+// and the per-link / per-site stencil bodies of the SU(3) kernels.
+//
+// Boundary layout (what callers hand in; reference configs.py:501-507):
+//     x[b, mu, t, x, y, z, i, j]  complex, interleaved re/im  ("AoS", 144 B/link in c128)
+// Internal layout used by every stencil kernel ("SoA"):
+//     U[b][mu][e][site]  one complex<T> per entry, e = 3*i + j, site = ((t*X + x)*Y + y)*Z + z
+// so a warp that owns 32 consecutive sites reads each matrix entry with ONE fully
+// coalesced 128-bit load per lane, and a neighbour in +-z is the same row shifted by
+// 16 B.  The conversion happens once per trajectory, not per leapfrog step.
+//
+// The bodies are __host__ __device__ so tests/hostemu can run them on the CPU.
+#pragma once
+#include "l2b_su3_math.cuh"
+
+namespace l2b {
+
+#if defined(__CUDACC__)
+template <typename T> struct cplx_of;
+template <> struct cplx_of<double> { using type = double2; };
+template <> struct cplx_of<float> { using type = float2; };
+#else
+template <typename T> struct cplx_host { T x, y; };
+template <typename T> struct cplx_of { using type = cplx_host<T>; };
+#endif
+
+struct Lat {
+  int L[4];        // T, X, Y, Z
+  int stride[4];   // site stride of each direction
+  int V;
+};
+
+L2B_HD Lat make_lat(int T, int X, int Y, int Z) {
+  Lat l;
+  l.L[0] = T; l.L[1] = X; l.L[2] = Y; l.L[3] = Z;
+  l.stride[3] = 1; l.stride[2] = Z; l.stride[1] = Y * Z; l.stride[0] = X * Y * Z;
+  l.V = T * X * Y * Z;
+  return l;
+}
+
+L2B_HD void site_coords(const Lat& l, int site, int c[4]) {
+  c[3] = site % l.L[3]; site /= l.L[3];
+  c[2] = site % l.L[2]; site /= l.L[2];
+  c[1] = site % l.L[1]; site /= l.L[1];
+  c[0] = site;
+}
+
+// site index of n + mu_hat / n - mu_hat (periodic)
+L2B_HD int site_fwd(const Lat& l, int site, const int c[4], int mu) {
+  return (c[mu] == l.L[mu] - 1) ? site - (l.L[mu] - 1) * l.stride[mu] : site + l.stride[mu];
+}
+L2B_HD int site_bwd(const Lat& l, int site, const int c[4], int mu) {
+  return (c[mu] == 0) ? site + (l.L[mu] - 1) * l.stride[mu] : site - l.stride[mu];
+}
+
+#if defined(__CUDA_ARCH__)
+#define L2B_LDG(p) __ldg(p)
+#else
+#define L2B_LDG(p) (*(p))
+#endif
+
+// plane pointer of (chain b, direction mu): 9 rows of V complex numbers
+template <typename C>
+L2B_HD const C* soa_plane(const C* f, const Lat& l, int b, int mu) {
+  return f + ((size_t)b * 4 + mu) * 9 * (size_t)l.V;
+}
+template <typename C>
+L2B_HD C* soa_plane(C* f, const Lat& l, int b, int mu) {
+  return f + ((size_t)b * 4 + mu) * 9 * (size_t)l.V;
+}
+
+template <typename T, typename C>
+L2B_HD void soa_load(Mat3<T>& m, const C* plane, int V, int site) {
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    const C v = L2B_LDG(plane + (size_t)e * V + site);
+    m.re[e] = v.x; m.im[e] = v.y;
+  }
+}
+
+template <typename T, typename C>
+L2B_HD void soa_store(C* plane, int V, int site, const Mat3<T>& m) {
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    C v; v.x = m.re[e]; v.y = m.im[e];
+    plane[(size_t)e * V + site] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// G = U_mu(n) * A_mu(n),   A = sum of the six staples around link (mu, n):
+//   A_mu(n) = sum_{nu != mu} [ U_nu(n+mu) U_mu(n+nu)^+ U_nu(n)^+
+//                            + U_nu(n+mu-nu)^+ U_mu(n-nu)^+ U_nu(n-nu) ]
+// Then  force = (beta/3) TAH(G)  (== projectTAH(dS/dU U^+), reference
+// lattice/su3/pytorch/lattice.py:299-308, which gets it by autograd) and
+// sum_{mu,n} Re tr G = 4 * sum_plaquettes Re tr P  (every plaquette is seen from
+// each of its four links), which gives the Wilson action for free.
+// ---------------------------------------------------------------------------
+L2B_HD int sel4(int a0, int a1, int a2, int a3, int i) {
+  // register-only replacement for a[i] with a runtime i (no local-memory array)
+  return (i == 0) ? a0 : (i == 1) ? a1 : (i == 2) ? a2 : a3;
+}
+
+template <typename T, typename C>
+L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int mu, int site) {
+  const int V = l.V;
+  // coordinates, and for every direction d: site offset of a forward / backward hop
+  int r = site;
+  const int c3 = r % l.L[3]; r /= l.L[3];
+  const int c2 = r % l.L[2]; r /= l.L[2];
+  const int c1 = r % l.L[1]; r /= l.L[1];
+  const int c0 = r;
+  const int f0 = (c0 == l.L[0] - 1) ? -(l.L[0] - 1) * l.stride[0] : l.stride[0];
+  const int f1 = (c1 == l.L[1] - 1) ? -(l.L[1] - 1) * l.stride[1] : l.stride[1];
+  const int f2 = (c2 == l.L[2] - 1) ? -(l.L[2] - 1) * l.stride[2] : l.stride[2];
+  const int f3 = (c3 == l.L[3] - 1) ? -(l.L[3] - 1) : 1;
+  const int b0 = (c0 == 0) ? (l.L[0] - 1) * l.stride[0] : -l.stride[0];
+  const int b1 = (c1 == 0) ? (l.L[1] - 1) * l.stride[1] : -l.stride[1];
+  const int b2 = (c2 == 0) ? (l.L[2] - 1) * l.stride[2] : -l.stride[2];
+  const int b3 = (c3 == 0) ? (l.L[3] - 1) : -1;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int n_pmu = site + sel4(f0, f1, f2, f3, mu);
+  Mat3<T> a, x, y, m;
+  mat_zero(a);
+  L2B_UNROLL
+  for (int k = 1; k < 4; ++k) {
+    const int nu = (mu + k) & 3;
+    const C* pnu = chain + (size_t)nu * plane_sz;
+    const int fnu = sel4(f0, f1, f2, f3, nu);
+    const int bnu = sel4(b0, b1, b2, b3, nu);
+    const int n_pnu = site + fnu;
+    const int n_mnu = site + bnu;
+    const int n_pmu_mnu = n_pmu + bnu;           // the mu hop does not change the nu coordinate
+    // forward staple
+    soa_load(x, pnu, V, n_pmu);                  // U_nu(n+mu)
+    soa_load(y, pmu, V, n_pnu);                  // U_mu(n+nu)
+    mat_mul<false, true, false>(m, x, y);        // U_nu(n+mu) U_mu(n+nu)^+
+    soa_load(x, pnu, V, site);                   // U_nu(n)
+    mat_mul<false, true, true>(a, m, x);         // a += m U_nu(n)^+
+    // backward staple
+    soa_load(x, pnu, V, n_pmu_mnu);              // U_nu(n+mu-nu)
+    soa_load(y, pmu, V, n_mnu);                  // U_mu(n-nu)
+    mat_mul<true, true, false>(m, x, y);         // U_nu(n+mu-nu)^+ U_mu(n-nu)^+
+    soa_load(x, pnu, V, n_mnu);                  // U_nu(n-nu)
+    mat_mul<false, false, true>(a, m, x);        // a += m U_nu(n-nu)
+  }
+  soa_load(x, pmu, V, site);
+  mat_mul<false, false, false>(g, x, a);
+}
+
+// ---------------------------------------------------------------------------
+// Plaquette traces at one site, the reference's six planes in ITS order
+// (u = 1..3, v < u):  tr[ U_u(n) U_v(n+u) (U_v(n) U_u(n+v))^+ ]
+// (lattice/su3/pytorch/lattice.py:157-199).  tr_re/tr_im[p], p = 0..5.
+// ---------------------------------------------------------------------------
+template <typename T, typename C>
+L2B_HD void site_plaquette_traces(T tr_re[6], T tr_im[6], const C* U, const Lat& l, int b, int site) {
+  int c[4];
+  site_coords(l, site, c);
+  const int V = l.V;
+  int p = 0;
+  L2B_UNROLL
+  for (int u = 1; u < 4; ++u) {
+    L2B_UNROLL
+    for (int v = 0; v < 3; ++v) {
+      if (v < u) {
+        const C* pu = soa_plane(U, l, b, u);
+        const C* pv = soa_plane(U, l, b, v);
+        Mat3<T> a, bb, yuv, yvu;
+        soa_load(a, pu, V, site);
+        soa_load(bb, pv, V, site_fwd(l, site, c, u));
+        mat_mul<false, false, false>(yuv, a, bb);
+        soa_load(a, pv, V, site);
+        soa_load(bb, pu, V, site_fwd(l, site, c, v));
+        mat_mul<false, false, false>(yvu, a, bb);
+        trace_mul_adj(yuv, yvu, tr_re[p], tr_im[p]);
+        ++p;
+      }
+    }
+  }
+}
+
+}  // namespace l2b

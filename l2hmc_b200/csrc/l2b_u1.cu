@@ -1,0 +1,426 @@
+// l2b_u1.cu -- sm_100a kernels + C ABI for the 2-D U(1) leapfrog hot path.
+//
+// x[b, mu, t, x] real angles (mu = 0, 1), plaquette angle
+//   w(t,x) = x0(t,x) + x1(t+1,x) - x0(t,x+1) - x1(t,x)
+// (reference lattice/u1/pytorch/lattice.py:154-159; dims=1 is T, dims=2 is X).
+//
+// The HMC trajectory kernel keeps one chain's links, momenta and sin(w) in
+// shared memory for the WHOLE trajectory (one thread block per chain), so HBM
+// sees each field once on the way in and once on the way out regardless of the
+// number of leapfrog steps.
+#include <math.h>
+
+#include "l2b_common.cuh"
+
+namespace l2b {
+namespace {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static __device__ __forceinline__ float sin_(float a) { return sinf(a); }
+  static __device__ __forceinline__ float cos_(float a) { return cosf(a); }
+  static __device__ __forceinline__ float tan_(float a) { return tanf(a); }
+  static __device__ __forceinline__ float atan_(float a) { return atanf(a); }
+  static __device__ __forceinline__ float exp_(float a) { return expf(a); }
+  static __device__ __forceinline__ float log_(float a) { return logf(a); }
+  static __device__ __forceinline__ float floor_(float a) { return floorf(a); }
+  static __device__ __forceinline__ float fmod_(float a, float b) { return fmodf(a, b); }
+};
+template <> struct Num<double> {
+  static __device__ __forceinline__ double sin_(double a) { return sin(a); }
+  static __device__ __forceinline__ double cos_(double a) { return cos(a); }
+  static __device__ __forceinline__ double tan_(double a) { return tan(a); }
+  static __device__ __forceinline__ double atan_(double a) { return atan(a); }
+  static __device__ __forceinline__ double exp_(double a) { return exp(a); }
+  static __device__ __forceinline__ double log_(double a) { return log(a); }
+  static __device__ __forceinline__ double floor_(double a) { return floor(a); }
+  static __device__ __forceinline__ double fmod_(double a, double b) { return fmod(a, b); }
+};
+
+// ((x + pi) mod 2 pi) - pi with Python-style modulo (group/u1/pytorch/group.py:130-131)
+template <typename T>
+__device__ __forceinline__ T wrap_pi(T x) {
+  const T pi = (T)kPi, tp = (T)kTwoPi;
+  T r = Num<T>::fmod_(x + pi, tp);
+  if (r < T(0)) r += tp;
+  return r - pi;
+}
+// x - 2 pi floor((x + pi) / 2 pi)   (lattice/u1/pytorch/lattice.py:45-47)
+template <typename T>
+__device__ __forceinline__ T project_angle(T x) {
+  const T pi = (T)kPi, tp = (T)kTwoPi;
+  return x - tp * Num<T>::floor_((x + pi) / tp);
+}
+
+template <typename T>
+__device__ __forceinline__ T plaq_angle(const T* __restrict__ x0, const T* __restrict__ x1, int t, int xx, int Tt, int X) {
+  const int tp = (t + 1 == Tt) ? 0 : t + 1;
+  const int xp = (xx + 1 == X) ? 0 : xx + 1;
+  return x0[t * X + xx] + x1[tp * X + xx] - x0[t * X + xp] - x1[t * X + xx];
+}
+
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_wloops(const T* __restrict__ x, T* __restrict__ w, int Tt, int X) {
+  const int N = Tt * X;
+  const T* x0 = x + (size_t)blockIdx.y * 2 * N;
+  const T* x1 = x0 + N;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < N) w[(size_t)blockIdx.y * N + i] = plaq_angle(x0, x1, i / X, i % X, Tt, X);
+}
+
+// obs[b] = (action, plaq, sinQ, intQ); one block per chain, fixed-order reduction
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_obs(const T* __restrict__ x, T beta, T* __restrict__ obs, int Tt, int X) {
+  __shared__ double red[8];
+  const int N = Tt * X;
+  const T* x0 = x + (size_t)blockIdx.x * 2 * N;
+  const T* x1 = x0 + N;
+  double sc = 0.0, ss = 0.0, sq = 0.0;
+  for (int i = threadIdx.x; i < N; i += 256) {
+    const T w = plaq_angle(x0, x1, i / X, i % X, Tt, X);
+    sc += (double)(T(1) - Num<T>::cos_(w));
+    ss += (double)Num<T>::sin_(w);
+    sq += (double)project_angle(w);
+  }
+  sc = block_sum<256>(sc, red, threadIdx.x);
+  ss = block_sum<256>(ss, red, threadIdx.x);
+  sq = block_sum<256>(sq, red, threadIdx.x);
+  if (threadIdx.x == 0) {
+    T* o = obs + (size_t)blockIdx.x * 4;
+    o[0] = (T)((double)beta * sc);
+    o[1] = (T)(1.0 - sc / N);
+    o[2] = (T)(ss / kTwoPi);
+    o[3] = (T)(sq / kTwoPi);
+  }
+}
+
+// F0 = beta (sin w(t,x) - sin w(t,x-1)),  F1 = beta (-sin w(t,x) + sin w(t-1,x))
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_force(const T* __restrict__ x, T beta, T* __restrict__ f, int Tt, int X) {
+  const int N = Tt * X;
+  const T* x0 = x + (size_t)blockIdx.y * 2 * N;
+  const T* x1 = x0 + N;
+  T* f0 = f + (size_t)blockIdx.y * 2 * N;
+  T* f1 = f0 + N;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const int t = i / X, xx = i % X;
+  const int tm = (t == 0) ? Tt - 1 : t - 1;
+  const int xm = (xx == 0) ? X - 1 : xx - 1;
+  const T s = Num<T>::sin_(plaq_angle(x0, x1, t, xx, Tt, X));
+  const T sxm = Num<T>::sin_(plaq_angle(x0, x1, t, xm, Tt, X));
+  const T stm = Num<T>::sin_(plaq_angle(x0, x1, tm, xx, Tt, X));
+  f0[i] = beta * (s - sxm);
+  f1[i] = beta * (-s + stm);
+}
+
+// ---------------------------------------------------------------------------
+// whole-trajectory HMC, one block per chain, state resident in shared memory
+// ---------------------------------------------------------------------------
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) k_u1_hmc(const T* __restrict__ x, const T* __restrict__ v, T beta, T eps, int nlf,
+                                               T* __restrict__ xo, T* __restrict__ vo, T* __restrict__ energies,
+                                               int Tt, int X) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double red[NT / 32];
+  const int N = Tt * X;
+  T* sx = reinterpret_cast<T*>(smraw);   // [2N] links
+  T* sv = sx + 2 * N;                    // [2N] momenta
+  T* sw = sv + 2 * N;                    // [N]  sin(w)
+  const size_t row = (size_t)blockIdx.x * 2 * N;
+  const int tid = threadIdx.x;
+  double ke = 0.0;
+  for (int i = tid; i < 2 * N; i += NT) {
+    sx[i] = x[row + i];
+    const T p = v[row + i];
+    sv[i] = p;
+    ke += (double)p * (double)p;
+  }
+  __syncthreads();
+  ke = block_sum<NT>(ke, red, tid);
+  if (tid == 0) energies[(size_t)blockIdx.x * 4 + 0] = (T)(0.5 * ke);
+
+  for (int k = 0; k <= nlf; ++k) {
+    // sin(w) at the current links; the action rides along on the first and last pass
+    const bool want_s = (k == 0) || (k == nlf);
+    double sc = 0.0;
+    for (int i = tid; i < N; i += NT) {
+      const T w = plaq_angle(sx, sx + N, i / X, i % X, Tt, X);
+      sw[i] = Num<T>::sin_(w);
+      if (want_s) sc += (double)(T(1) - Num<T>::cos_(w));
+    }
+    __syncthreads();
+    if (want_s) {
+      sc = block_sum<NT>(sc, red, tid);
+      if (tid == 0) energies[(size_t)blockIdx.x * 4 + (k == 0 ? 1 : 3)] = (T)((double)beta * sc);
+    }
+    // kick (half at both ends, merged full kicks in between), then drift
+    const T c = ((k == 0 || k == nlf) ? T(0.5) : T(1)) * eps;
+    for (int i = tid; i < N; i += NT) {
+      const int t = i / X, xx = i % X;
+      const int tm = (t == 0) ? Tt - 1 : t - 1;
+      const int xm = (xx == 0) ? X - 1 : xx - 1;
+      const T s = sw[i];
+      const T f0 = beta * (s - sw[t * X + xm]);
+      const T f1 = beta * (-s + sw[tm * X + xx]);
+      const T v0 = sv[i] - c * f0;
+      const T v1 = sv[N + i] - c * f1;
+      sv[i] = v0;
+      sv[N + i] = v1;
+      if (k < nlf) {
+        sx[i] += eps * v0;
+        sx[N + i] += eps * v1;
+      }
+    }
+    __syncthreads();
+  }
+  ke = 0.0;
+  for (int i = tid; i < 2 * N; i += NT) {
+    xo[row + i] = sx[i];
+    const T p = sv[i];
+    vo[row + i] = p;
+    ke += (double)p * (double)p;
+  }
+  ke = block_sum<NT>(ke, red, tid);
+  if (tid == 0) energies[(size_t)blockIdx.x * 4 + 2] = (T)(0.5 * ke);
+}
+
+// ---------------------------------------------------------------------------
+// L2HMC element-wise updates on real fields; one block per chain
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_vupdate(const T* __restrict__ v, const T* __restrict__ f,
+                                                    const T* __restrict__ s, const T* __restrict__ t,
+                                                    const T* __restrict__ q, T eps, int sign, T* __restrict__ out,
+                                                    T* __restrict__ logdet, int xdim) {
+  __shared__ double red[8];
+  const size_t row = (size_t)blockIdx.x * xdim;
+  double ld = 0.0;
+  const T half_eps = T(0.5) * eps;
+  for (int i = threadIdx.x; i < xdim; i += 256) {
+    const T si = s ? s[row + i] : T(0), ti = t ? t[row + i] : T(0), qi = q ? q[row + i] : T(0);
+    const T logjac = (T)sign * eps * si / T(2);
+    ld += (double)logjac;
+    const T es = Num<T>::exp_(logjac);
+    const T eq = Num<T>::exp_(eps * qi);
+    const T fn = f[row + i] * eq + ti;
+    out[row + i] = (sign > 0) ? (es * v[row + i] - half_eps * fn) : (es * (v[row + i] + half_eps * fn));
+  }
+  if (logdet != nullptr) {
+    ld = block_sum<256>(ld, red, threadIdx.x);
+    if (threadIdx.x == 0) logdet[blockIdx.x] = (T)ld;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_xupdate(const T* __restrict__ x, const T* __restrict__ v,
+                                                    const T* __restrict__ s, const T* __restrict__ t,
+                                                    const T* __restrict__ q, const float* __restrict__ mask, T eps,
+                                                    int sign, int use_ncp, T* __restrict__ out,
+                                                    T* __restrict__ logdet, int xdim) {
+  __shared__ double red[8];
+  const size_t row = (size_t)blockIdx.x * xdim;
+  double ld = 0.0;
+  for (int i = threadIdx.x; i < xdim; i += 256) {
+    const T m = (T)mask[i], mb = T(1) - m;
+    const T xi = x[row + i], vi = v[row + i];
+    const T si = ((T)sign * eps) * (s ? s[row + i] : T(0));
+    const T qi = eps * (q ? q[row + i] : T(0));
+    const T ti = t ? t[row + i] : T(0);
+    const T es = Num<T>::exp_(si), eq = Num<T>::exp_(qi);
+    const T tr = eps * (vi * eq + ti);
+    T xn, lj;
+    if (use_ncp) {
+      const T hx = xi / T(2);
+      const T x1 = T(2) * Num<T>::atan_(Num<T>::tan_(hx) * es);
+      xn = (sign > 0) ? (x1 + tr) : (x1 - es * tr);
+      const T ct = Num<T>::cos_(hx), st = es * Num<T>::sin_(hx);
+      lj = Num<T>::log_(es / (ct * ct + st * st));
+    } else {
+      xn = (sign > 0) ? (xi * es + tr) : (es * (xi - tr));
+      lj = si;
+    }
+    ld += (double)(mb * lj);
+    out[row + i] = wrap_pi(m * xi + mb * xn);
+  }
+  if (logdet != nullptr) {
+    ld = block_sum<256>(ld, red, threadIdx.x);
+    if (threadIdx.x == 0) logdet[blockIdx.x] = (T)ld;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_kinetic(const T* __restrict__ v, T* __restrict__ ke, int xdim) {
+  __shared__ double red[8];
+  const size_t row = (size_t)blockIdx.x * xdim;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < xdim; i += 256) { const double p = (double)v[row + i]; acc += p * p; }
+  acc = block_sum<256>(acc, red, threadIdx.x);
+  if (threadIdx.x == 0) ke[blockIdx.x] = (T)(0.5 * acc);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_wrap(const T* __restrict__ x, T* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = wrap_pi(x[i]);
+}
+
+int check_u1(int nb, int Tt, int X, int dtype) {
+  L2B_REQUIRE(nb > 0 && Tt > 0 && X > 0, L2B_ERR_INVALID, "non-positive size: nb=%d T=%d X=%d", nb, Tt, X);
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE((long long)Tt * X < (1ll << 28), L2B_ERR_UNSUPPORTED, "lattice too large");
+  return L2B_OK;
+}
+
+size_t hmc_smem_bytes(int Tt, int X, int dtype) {
+  return (size_t)5 * Tt * X * (dtype == L2B_F64 ? 8 : 4);
+}
+
+template <typename T, int NT>
+int launch_hmc(const void* x, const void* v, double beta, double eps, int nlf, void* xo, void* vo, void* en, int nb,
+               int Tt, int X, size_t smem, cudaStream_t st) {
+  L2B_CUDA(cudaFuncSetAttribute(k_u1_hmc<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_u1_hmc<T, NT><<<nb, NT, smem, st>>>((const T*)x, (const T*)v, (T)beta, (T)eps, nlf, (T*)xo, (T*)vo, (T*)en, Tt, X);
+  L2B_LAUNCHED("k_u1_hmc");
+  return L2B_OK;
+}
+
+template <typename T>
+int dispatch_hmc(const void* x, const void* v, double beta, double eps, int nlf, void* xo, void* vo, void* en,
+                 int nb, int Tt, int X, size_t smem, cudaStream_t st) {
+  const int N = Tt * X;
+  if (N >= 2048) return launch_hmc<T, 512>(x, v, beta, eps, nlf, xo, vo, en, nb, Tt, X, smem, st);
+  if (N >= 512) return launch_hmc<T, 256>(x, v, beta, eps, nlf, xo, vo, en, nb, Tt, X, smem, st);
+  return launch_hmc<T, 128>(x, v, beta, eps, nlf, xo, vo, en, nb, Tt, X, smem, st);
+}
+
+#define L2B_DISPATCH_T(dtype, CALL_F32, CALL_F64) \
+  do {                                            \
+    if ((dtype) == L2B_F32) { CALL_F32; }         \
+    else { CALL_F64; }                            \
+  } while (0)
+
+}  // namespace
+}  // namespace l2b
+
+using namespace l2b;
+
+extern "C" {
+
+size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype) {
+  (void)nb; (void)T; (void)X; (void)dtype;
+  return 0;  // every U(1) reduction is one block per chain: no scratch needed
+}
+
+int l2b_u1_wilson_loops(const void* x, void* w, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && w, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((T * X + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_wloops<float><<<grid, 256, 0, st>>>((const float*)x, (float*)w, T, X)),
+                 (k_u1_wloops<double><<<grid, 256, 0, st>>>((const double*)x, (double*)w, T, X)));
+  L2B_LAUNCHED("k_u1_wloops");
+  return L2B_OK;
+}
+
+int l2b_u1_observables(const void* x, double beta, void* obs, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && obs, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_obs<float><<<nb, 256, 0, st>>>((const float*)x, (float)beta, (float*)obs, T, X)),
+                 (k_u1_obs<double><<<nb, 256, 0, st>>>((const double*)x, beta, (double*)obs, T, X)));
+  L2B_LAUNCHED("k_u1_obs");
+  return L2B_OK;
+}
+
+int l2b_u1_force(const void* x, double beta, void* force, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && force, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((T * X + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_force<float><<<grid, 256, 0, st>>>((const float*)x, (float)beta, (float*)force, T, X)),
+                 (k_u1_force<double><<<grid, 256, 0, st>>>((const double*)x, beta, (double*)force, T, X)));
+  L2B_LAUNCHED("k_u1_force");
+  return L2B_OK;
+}
+
+int l2b_u1_hmc_trajectory(const void* x, const void* v, double beta, double eps, int nlf, void* x_prop,
+                          void* v_prop, void* energies, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && v && x_prop && v_prop && energies, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nlf >= 1, L2B_ERR_INVALID, "nlf must be >= 1 (got %d)", nlf);
+  const size_t smem = hmc_smem_bytes(T, X, dtype);
+  L2B_REQUIRE(smem <= 227 * 1024, L2B_ERR_UNSUPPORTED,
+              "U(1) %dx%d chain state (%zu B) does not fit one SM's shared memory", T, X, smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == L2B_F32) return dispatch_hmc<float>(x, v, beta, eps, nlf, x_prop, v_prop, energies, nb, T, X, smem, st);
+  return dispatch_hmc<double>(x, v, beta, eps, nlf, x_prop, v_prop, energies, nb, T, X, smem, st);
+}
+
+int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                   int sign, void* v_out, void* logdet, int nb, int xdim, int dtype, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(v && force && v_out, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype,
+                 (k_u1_vupdate<float><<<nb, 256, 0, st>>>((const float*)v, (const float*)force, (const float*)s,
+                                                          (const float*)t, (const float*)q, (float)eps, sign,
+                                                          (float*)v_out, (float*)logdet, xdim)),
+                 (k_u1_vupdate<double><<<nb, 256, 0, st>>>((const double*)v, (const double*)force, (const double*)s,
+                                                           (const double*)t, (const double*)q, eps, sign,
+                                                           (double*)v_out, (double*)logdet, xdim)));
+  L2B_LAUNCHED("k_u1_vupdate");
+  return L2B_OK;
+}
+
+int l2b_u1_xupdate(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
+                   double eps, int sign, int use_ncp, void* x_out, void* logdet, int nb, int xdim, int dtype,
+                   void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(x && v && mask && x_out, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype,
+                 (k_u1_xupdate<float><<<nb, 256, 0, st>>>((const float*)x, (const float*)v, (const float*)s,
+                                                          (const float*)t, (const float*)q, mask, (float)eps, sign,
+                                                          use_ncp, (float*)x_out, (float*)logdet, xdim)),
+                 (k_u1_xupdate<double><<<nb, 256, 0, st>>>((const double*)x, (const double*)v, (const double*)s,
+                                                           (const double*)t, (const double*)q, mask, eps, sign,
+                                                           use_ncp, (double*)x_out, (double*)logdet, xdim)));
+  L2B_LAUNCHED("k_u1_xupdate");
+  return L2B_OK;
+}
+
+int l2b_u1_kinetic(const void* v, void* ke, int nb, int xdim, int dtype, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(v && ke, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_kinetic<float><<<nb, 256, 0, st>>>((const float*)v, (float*)ke, xdim)),
+                 (k_u1_kinetic<double><<<nb, 256, 0, st>>>((const double*)v, (double*)ke, xdim)));
+  L2B_LAUNCHED("k_u1_kinetic");
+  return L2B_OK;
+}
+
+int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(x && out, L2B_ERR_INVALID, "null pointer");
+  if (n == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((n + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_wrap<float><<<nblk, 256, 0, st>>>((const float*)x, (float*)out, n)),
+                 (k_u1_wrap<double><<<nblk, 256, 0, st>>>((const double*)x, (double*)out, n)));
+  L2B_LAUNCHED("k_u1_wrap");
+  return L2B_OK;
+}
+
+}  // extern "C"

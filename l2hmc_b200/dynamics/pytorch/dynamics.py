@@ -1,0 +1,561 @@
+"""`Dynamics`: the generalised leapfrog integrator + Metropolis-Hastings step,
+same public surface as the reference's
+`dynamics/pytorch/dynamics.py:113-1535`, with the per-step work done by the
+sm_100a kernels of libl2b:
+
+  plain HMC  (`apply_transition_hmc` / `transition_kernel_hmc`, :632-658,:915-954)
+      one call of `l2b_{su3,u1}_hmc_trajectory` (whole trajectory; energies for
+      the accept probability come fused with the first / last force pass);
+  L2HMC      (`forward` -> `apply_transition_fb` / `transition_kernel_fb`, :956-1029)
+      force, projectSU+su3_to_vec, v-update epilogue, masked x-update and the
+      Hamiltonians are libl2b kernels; the xnet/vnet dense layers are torch.nn.
+
+Reference quirks kept on purpose: eps -> eps/(1+eps) in
+L2HMC only; element-wise float32 masks built with numpy's RNG; SU(3) x-update
+`m*x + exp(eps v) @ ((1-m)*x)` with logdet 0 and no xnet call; vnet inputs go
+through projectSU; `acc_mask` float32; HMC `nleapfrog` doubles when
+`merge_directions`; x_out returned flattened.
+
+Gradient flow (training, BASELINE cfg 5) is not wired through the kernels yet:
+calling the L2HMC path with autograd enabled and trainable parameters raises.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from math import pi as PI
+from pathlib import Path
+from typing import Callable, Optional, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import configs as cfgs
+from ... import ops
+from ...group.su3.pytorch.group import SU3
+from ...group.u1.pytorch.group import U1Phase
+from ...lattice.su3.pytorch.lattice import LatticeSU3
+from ...lattice.u1.pytorch.lattice import LatticeU1
+from ...network.pytorch.network import NetworkFactory, dummy_network
+
+TWO_PI = 2. * PI
+Shape = Union[tuple, list]
+Tensor = torch.Tensor
+
+
+@dataclass
+class State:
+    x: Tensor
+    v: Tensor
+    beta: Tensor
+
+    def __post_init__(self):
+        self.nb = self.x.shape[0]
+        self.xshape = self.x.shape
+
+    def flatten(self) -> 'State':
+        return State(x=self.x.flatten(1), v=self.v.flatten(1), beta=self.beta)
+
+    def to_numpy(self):
+        return {'x': self.x.detach().cpu().numpy(), 'v': self.v.detach().cpu().numpy(),
+                'beta': torch.as_tensor(self.beta).detach().cpu().numpy()}
+
+
+@dataclass
+class MonteCarloStates:
+    init: State
+    proposed: State
+    out: State
+
+
+def sigmoid(x: Tensor) -> Tensor:
+    return 1. / (1. + torch.exp(-x))
+
+
+def _fbeta(beta) -> float:
+    return float(beta.detach()) if isinstance(beta, torch.Tensor) else float(beta)
+
+
+class Dynamics(nn.Module):
+    def __init__(self, potential_fn: Callable, config: cfgs.DynamicsConfig,
+                 network_factory: Optional[NetworkFactory] = None):
+        super().__init__()
+        if not torch.cuda.is_available():
+            raise ops.L2BError('l2hmc_b200.Dynamics needs a CUDA device (no CPU fallback)')
+        self.config = config
+        self.xdim = self.config.xdim
+        self.xshape = self.config.xshape
+        self.potential_fn = potential_fn
+        self.nlf = self.config.nleapfrog
+        self.device = self._device = torch.device('cuda', torch.cuda.current_device())
+        self._su3 = self.config.group.upper() == 'SU3'
+        if self._su3:
+            self.g = SU3()
+            self.lattice = LatticeSU3(self.config.nchains, self.config.latvolume)
+        else:
+            self.g = U1Phase()
+            self.lattice = LatticeU1(self.config.nchains, self.config.latvolume)
+        self.network_factory = network_factory
+        if network_factory is not None:
+            self._networks_built = True
+            self.networks = self._build_networks(network_factory)
+            # registered twice, like the reference (dynamics.py:140-144): the
+            # state_dict carries both `networks.xnet.*` and `xnet.*`
+            self.xnet = self.networks['xnet']
+            self.vnet = self.networks['vnet']
+        else:
+            self._networks_built = False
+            self.xnet = dummy_network
+            self.vnet = dummy_network
+            self.networks = {'xnet': self.xnet, 'vnet': self.vnet}
+        self.masks = [m.to(self.device) for m in self._build_masks()]
+        self._dtype = torch.get_default_dtype()
+        rg = (not self.config.eps_fixed)
+        self.xeps = nn.ParameterList([
+            nn.Parameter(torch.tensor(float(self.config.eps)), requires_grad=rg)
+            for _ in range(self.config.nleapfrog)])
+        self.veps = nn.ParameterList([
+            nn.Parameter(torch.tensor(float(self.config.eps)), requires_grad=rg)
+            for _ in range(self.config.nleapfrog)])
+        self.to(self.device)
+
+    # ------------------------------------------------------------------ build
+    def _build_networks(self, network_factory: NetworkFactory) -> nn.ModuleDict:
+        split = self.config.use_split_xnets
+        n = self.nlf if self.config.use_separate_networks else 1
+        return network_factory.build_networks(n, split, group=self.g)
+
+    def _build_masks(self):
+        """nlf random half-masks over the xdim ELEMENTS, numpy RNG
+        (dynamics.py:1101-1110)"""
+        masks = []
+        for _ in range(self.config.nleapfrog):
+            idx = np.random.permutation(np.arange(self.xdim))[:self.xdim // 2]
+            mask = np.zeros((self.xdim,), dtype=np.float32)
+            mask[idx] = 1.
+            masks.append(torch.from_numpy(mask[None, :]))
+        return masks
+
+    def get_models(self) -> dict:
+        if self.config.use_separate_networks:
+            xnet, vnet = {}, {}
+            for lf in range(self.config.nleapfrog):
+                vnet[str(lf)] = self._get_vnet(lf)
+                if self.config.use_split_xnets:
+                    xnet[str(lf)] = {'0': self._get_xnet(lf, first=True), '1': self._get_xnet(lf, first=False)}
+                else:
+                    xnet[str(lf)] = self._get_xnet(lf, first=True)
+        else:
+            vnet = self._get_vnet(0)
+            if self.config.use_split_xnets:
+                xnet = {'0': self._get_xnet(0, first=True), '1': self._get_xnet(0, first=False)}
+            else:
+                xnet = self._get_xnet(0, first=True)
+        return {'xnet': xnet, 'vnet': vnet}
+
+    def init_weights(self, method='xavier_uniform', **kwargs):
+        """dynamics.py:333-424 (the methods the configs use)"""
+        fn = {'zeros': nn.init.zeros_, 'zero': nn.init.zeros_, 'xavier_uniform': nn.init.xavier_uniform_,
+              'xavier_normal': nn.init.xavier_normal_, 'kaiming_normal': nn.init.kaiming_normal_,
+              'kaiming_uniform': nn.init.kaiming_uniform_}.get(method)
+        if fn is None:
+            raise ValueError(f'unknown init method {method!r}')
+        with torch.no_grad():
+            for m in self.modules():
+                if isinstance(m, (nn.Linear, nn.Conv2d)):
+                    fn(m.weight)
+                    if method in ('zeros', 'zero') and m.bias is not None:
+                        nn.init.zeros_(m.bias)
+
+    # ---------------------------------------------------------- save / load
+    def save(self, outdir: os.PathLike) -> None:
+        netdir = Path(outdir).joinpath('networks')
+        netdir.mkdir(exist_ok=True, parents=True)
+        self.save_eps(outdir=netdir)
+        torch.save(self.state_dict(), netdir.joinpath('dynamics.pt').as_posix())
+
+    def save_eps(self, outdir: os.PathLike) -> None:
+        """same file placement as the reference (dynamics.py:544-557, which nests
+        a second `networks/` when called from `save`)"""
+        netdir = Path(outdir).joinpath('networks')
+        netdir.mkdir(exist_ok=True, parents=True)
+        xeps = np.array([i.detach().cpu().numpy() for i in self.xeps])
+        veps = np.array([i.detach().cpu().numpy() for i in self.veps])
+        np.save(netdir.joinpath('xeps.npy'), xeps)
+        np.save(netdir.joinpath('veps.npy'), veps)
+        np.savetxt(netdir.joinpath('xeps.txt').as_posix(), xeps)
+        np.savetxt(netdir.joinpath('veps.txt').as_posix(), veps)
+
+    def load(self, outdir: os.PathLike) -> None:
+        netdir = Path(outdir).joinpath('networks')
+        self.load_state_dict(torch.load(netdir.joinpath('dynamics.pt'), map_location=self.device))
+
+    def assign_eps(self, eps) -> None:
+        n = self.config.nleapfrog
+        if isinstance(eps, dict):
+            xe, ve = eps['xeps'], eps['veps']
+        elif isinstance(eps, tuple):
+            xe = {str(i): eps[0] for i in range(n)}
+            ve = {str(i): eps[1] for i in range(n)}
+        elif isinstance(eps, float):
+            xe = {str(i): eps for i in range(n)}
+            ve = {str(i): eps for i in range(n)}
+        else:
+            raise TypeError
+        rg = (not self.config.eps_fixed)
+        self.xeps = nn.ParameterList(
+            [nn.Parameter(torch.as_tensor(float(xe[str(i)])), requires_grad=rg) for i in range(n)]).to(self.device)
+        self.veps = nn.ParameterList(
+            [nn.Parameter(torch.as_tensor(float(ve[str(i)])), requires_grad=rg) for i in range(n)]).to(self.device)
+
+    # ------------------------------------------------------------ transitions
+    def forward(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, dict]:
+        x, beta = inputs
+        x = x.to(self._device)
+        inputs = (x, beta)
+        return self.apply_transition_fb(inputs) if self.config.merge_directions else self.apply_transition(inputs)
+
+    def flatten(self, x: Tensor) -> Tensor:
+        return x.reshape(x.shape[0], -1)
+
+    def unflatten(self, x: Tensor) -> Tensor:
+        return x.reshape(x.shape[0], *self.xshape[1:])
+
+    def _mix(self, data: dict, sumlogdet_key: bool) -> tuple[Tensor, dict]:
+        """accept/reject: out = ma*proposed + mr*init (dynamics.py:632-702) as a
+        bit-exact per-chain select in one kernel"""
+        ma_, _ = self._get_accept_masks(data['metrics']['acc'])
+        init, prop = data['init'], data['proposed']
+        xout, vout = ops.accept_mix(ma_, [(init.x, prop.x), (init.v, prop.v)])
+        state_out = State(x=xout, v=vout, beta=init.beta)
+        mc_states = MonteCarloStates(init=init, proposed=prop, out=state_out)
+        if sumlogdet_key:
+            data['metrics'].update({'beta': init.beta, 'acc_mask': ma_,
+                                    'sumlogdet': ma_ * data['metrics']['sumlogdet'], 'mc_states': mc_states})
+        else:
+            data['metrics'].update({'acc_mask': ma_, 'mc_states': mc_states})
+        return xout, data['metrics']
+
+    def apply_transition_hmc(self, inputs: tuple[Tensor, Tensor], eps: Optional[float] = None,
+                             nleapfrog: Optional[int] = None) -> tuple[Tensor, dict]:
+        data = self.generate_proposal_hmc(inputs, eps=eps, nleapfrog=nleapfrog)
+        return self._mix(data, sumlogdet_key=False)
+
+    def apply_transition_fb(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, dict]:
+        data = self.generate_proposal_fb(inputs)
+        return self._mix(data, sumlogdet_key=True)
+
+    def apply_transition(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, dict]:
+        forward = bool(torch.rand(1) > 0.5)
+        data = self.generate_proposal(inputs, forward=forward)
+        return self._mix(data, sumlogdet_key=True)
+
+    def random_state(self, beta: float) -> State:
+        x = self.g.random(list(self.xshape))
+        v = self.g.random_momentum(list(self.xshape))
+        return State(x=x, v=v, beta=torch.tensor(beta).to(self.device))
+
+    def test_reversibility(self) -> dict:
+        state = self.random_state(beta=1.)
+        state_fwd, _ = self.transition_kernel(state, forward=True)
+        state_, _ = self.transition_kernel(state_fwd, forward=False)
+        dx = (self.flatten(state.x) - self.flatten(state_.x)).abs()
+        dv = (self.flatten(state.v) - self.flatten(state_.v)).abs()
+        return {'dx': dx.detach().cpu().numpy(), 'dv': dv.detach().cpu().numpy()}
+
+    def _momentum(self, x: Tensor) -> Tensor:
+        return self.g.random_momentum([x.shape[0], *self.xshape[1:]])
+
+    def generate_proposal_hmc(self, inputs, eps: Optional[float] = None, nleapfrog: Optional[int] = None) -> dict:
+        x, beta = inputs
+        x = x.to(self._device)
+        init = State(x=x, v=self._momentum(x), beta=beta)
+        proposed, metrics = self.transition_kernel_hmc(init, eps=eps, nleapfrog=nleapfrog)
+        return {'init': init, 'proposed': proposed, 'metrics': metrics}
+
+    def generate_proposal_fb(self, inputs) -> dict:
+        x, beta = inputs
+        init = State(x=x, v=self._momentum(x), beta=beta)
+        proposed, metrics = self.transition_kernel_fb(State(init.x, init.v, beta))
+        return {'init': init, 'proposed': proposed, 'metrics': metrics}
+
+    def generate_proposal(self, inputs, forward: bool) -> dict:
+        x, beta = inputs
+        init = State(x=x, v=self._momentum(x), beta=beta)
+        proposed, metrics = self.transition_kernel(init, forward)
+        return {'init': init, 'proposed': proposed, 'metrics': metrics}
+
+    # ------------------------------------------------------------ metrics
+    def get_metrics(self, state: State, logdet: Tensor, step: Optional[int] = None,
+                    extras: Optional[dict] = None) -> dict:
+        energy = self.hamiltonian(state)
+        metrics = {'energy': energy, 'logprob': energy - logdet, 'logdet': logdet}
+        if extras is not None:
+            metrics.update(extras)
+        if step is not None:
+            metrics.update({'xeps': self.xeps[step], 'veps': self.veps[step]})
+        return metrics
+
+    def update_history(self, metrics: dict, history: dict):
+        for key, val in metrics.items():
+            history.setdefault(key, []).append(val)
+        return history
+
+    @staticmethod
+    def _stack_history(history: dict) -> dict:
+        for key, val in history.items():
+            if isinstance(val, list) and isinstance(val[0], Tensor):
+                history[key] = torch.stack(val)
+        return history
+
+    def _zeros(self, nb: int) -> Tensor:
+        return torch.zeros(nb, device=self.device)
+
+    # ------------------------------------------------------------ plain HMC
+    def leapfrog_hmc(self, state: State, eps: Optional[float] = None) -> State:
+        """one step with two un-merged half kicks (dynamics.py:900-913); used by
+        the verbose path -- the fused trajectory kernel is the fast path"""
+        eps = self.config.eps if eps is None else eps
+        beta = _fbeta(state.beta)
+        if self._su3:
+            x, v = self.unflatten(state.x), self.unflatten(state.v)
+            v1, _ = ops.su3_vupdate(v, ops.su3_force(x, beta), None, None, None, eps, +1)
+            xp = ops.su3_update_gauge(x, v1, eps)
+            v2, _ = ops.su3_vupdate(v1, ops.su3_force(xp, beta), None, None, None, eps, +1)
+            return State(x=xp, v=v2, beta=state.beta)
+        x_ = state.x.reshape_as(state.v)
+        shape = self.config.latvolume
+        v1, _ = ops.u1_vupdate(state.v, ops.u1_force(x_, beta, shape), None, None, None, eps, +1)
+        xp = x_ + eps * v1
+        v2, _ = ops.u1_vupdate(v1, ops.u1_force(xp, beta, shape), None, None, None, eps, +1)
+        return State(x=xp, v=v2, beta=state.beta)
+
+    def transition_kernel_hmc(self, state: State, eps: Optional[float] = None,
+                              nleapfrog: Optional[int] = None) -> tuple[State, dict]:
+        nb = state.x.shape[0]
+        sumlogdet = self._zeros(nb)
+        eps = self.config.eps_hmc if eps is None else eps
+        nlf = self.config.nleapfrog if not self.config.merge_directions else 2 * self.config.nleapfrog
+        if eps is None:
+            eps = 1. / nlf
+        nleapfrog = nlf if nleapfrog is None else nleapfrog
+        beta = _fbeta(state.beta)
+        if self.config.verbose:
+            state_ = State(x=state.x, v=state.v, beta=state.beta)
+            history = self.update_history(self.get_metrics(state_, sumlogdet), {})
+            for _ in range(nleapfrog):
+                state_ = self.leapfrog_hmc(state_, eps=eps)
+                history = self.update_history(self.get_metrics(state_, sumlogdet), history)
+            acc = self.compute_accept_prob(state, state_, sumlogdet)
+            history.update({'acc': acc, 'sumlogdet': sumlogdet})
+            return state_, self._stack_history(history)
+        if self._su3:
+            xp, vp, en = ops.su3_hmc_trajectory(self.unflatten(state.x), self.unflatten(state.v), beta, eps, nleapfrog)
+        else:
+            xp, vp, en = ops.u1_hmc_trajectory(state.x, state.v, beta, eps, nleapfrog, shape=self.config.latvolume)
+            xp, vp = xp.reshape_as(state.v), vp.reshape_as(state.v)
+        dh = (en[:, 0] + en[:, 1]) - (en[:, 2] + en[:, 3]) + sumlogdet
+        acc = torch.exp(torch.minimum(dh, torch.zeros_like(dh)))
+        return State(x=xp, v=vp, beta=state.beta), {'acc': acc, 'sumlogdet': sumlogdet}
+
+    # --------------------------------------------------------------- L2HMC
+    def _check_inference_only(self) -> None:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                'L2HMC through libl2b is inference-only in this round: wrap the call in '
+                'torch.no_grad() (training path = SURVEY.md cfg 5, not built yet)')
+
+    def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
+        self._check_inference_only()
+        nb = state.x.shape[0]
+        sumlogdet = self._zeros(nb)
+        sldf, sldb = torch.zeros_like(sumlogdet), torch.zeros_like(sumlogdet)
+        state_ = State(x=state.x, v=state.v, beta=state.beta)
+        history: dict = {}
+        verbose = self.config.verbose
+        if verbose:
+            extras = {'sldf': sldf, 'sldb': sldb, 'sld': sumlogdet}
+            history = self.update_history(self.get_metrics(state_, sumlogdet, step=0, extras=extras), history)
+        for step in range(self.config.nleapfrog):
+            state_, logdet = self._forward_lf(step, state_)
+            sumlogdet = sumlogdet + logdet
+            if verbose:
+                sldf = sldf + logdet
+                extras = {'sldf': sldf, 'sldb': sldb, 'sld': sumlogdet}
+                history = self.update_history(self.get_metrics(state_, sumlogdet, step=step, extras=extras), history)
+        state_ = State(state_.x, -state_.v, state_.beta)
+        for step in range(self.config.nleapfrog):
+            state_, logdet = self._backward_lf(step, state_)
+            sumlogdet = sumlogdet + logdet
+            if verbose:
+                sldb = sldb + logdet
+                extras = {'sldf': torch.zeros_like(sldb), 'sldb': sldb, 'sld': sumlogdet}
+                history = self.update_history(
+                    self.get_metrics(state_, sumlogdet, step=(self.config.nleapfrog - step - 1), extras=extras),
+                    history)
+        acc = self.compute_accept_prob(state, state_, sumlogdet)
+        history.update({'acc': acc, 'sumlogdet': sumlogdet})
+        return state_, (self._stack_history(history) if verbose else history)
+
+    def transition_kernel(self, state: State, forward: bool) -> tuple[State, dict]:
+        self._check_inference_only()
+        lf_fn = self._forward_lf if forward else self._backward_lf
+        sinit = State(x=state.x, v=state.v, beta=state.beta)
+        sumlogdet = self._zeros(state.x.shape[0])
+        history: dict = {}
+        if self.config.verbose:
+            history = self.update_history(self.get_metrics(state, sumlogdet), history)
+        for step in range(self.config.nleapfrog):
+            state, logdet = lf_fn(step, state)
+            sumlogdet = sumlogdet + logdet
+            if self.config.verbose:
+                history = self.update_history(self.get_metrics(state, sumlogdet, step=step), history)
+        # NB: the reference passes the states swapped here (dynamics.py:1053-1057)
+        acc = self.compute_accept_prob(state_init=state, state_prop=sinit, sumlogdet=sumlogdet)
+        history.update({'acc': acc, 'sumlogdet': sumlogdet})
+        return state, (self._stack_history(history) if self.config.verbose else history)
+
+    def compute_accept_prob(self, state_init: State, state_prop: State, sumlogdet: Tensor) -> Tensor:
+        """exp(min(H0 - H1 + sumlogdet, 0))   (dynamics.py:1065-1079)"""
+        dh = self.hamiltonian(state_init) - self.hamiltonian(state_prop) + sumlogdet
+        return torch.exp(torch.minimum(dh, torch.zeros_like(dh)))
+
+    @staticmethod
+    def _get_accept_masks(px: Tensor) -> tuple[Tensor, Tensor]:
+        acc = (px > torch.rand_like(px)).to(torch.float)
+        return acc, torch.ones_like(acc) - acc
+
+    @staticmethod
+    def _get_direction_masks(batch_size: int) -> tuple[Tensor, Tensor]:
+        fwd = (torch.rand(batch_size) > 0.5).to(torch.float)
+        return fwd, torch.ones_like(fwd) - fwd
+
+    def _get_mask(self, step: int) -> tuple[Tensor, Tensor]:
+        m = self.masks[step]
+        return m, torch.ones_like(m) - m
+
+    def _get_vnet(self, step: int):
+        if not self._networks_built:
+            return self.vnet
+        if self.config.use_separate_networks:
+            return self.vnet.get_submodule(str(step))
+        return self.vnet
+
+    def _get_xnet(self, step: int, first: bool = False):
+        if not self._networks_built:
+            return self.xnet
+        if self.config.use_separate_networks:
+            xnet = self.xnet.get_submodule(str(step))
+            if self.config.use_split_xnets:
+                return xnet.get_submodule('first') if first else xnet.get_submodule('second')
+            return xnet
+        return self.xnet
+
+    def group_to_vec(self, x: Tensor) -> Tensor:
+        return self.g.group_to_vec(self.unflatten(x))
+
+    def vec_to_group(self, x: Tensor) -> Tensor:
+        x = self.unflatten(x)
+        if self._su3:
+            return self.g.vec_to_group(x)
+        return torch.complex(x[..., 0], x[..., 1])
+
+    def _call_vnet(self, step: int, inputs: tuple[Tensor, Tensor]):
+        """(x, force) -> (s, t, q); SU(3) inputs are su3_to_vec(projectSU(.)) of
+        BOTH x and the force (dynamics.py:1142-1159)"""
+        x, force = inputs
+        if self._su3:
+            if not self._networks_built:
+                return None, None, None       # dummy network: zeros -> plain kick
+            vnet = self._get_vnet(step)
+            dt = next(vnet.parameters()).dtype      # nets live in torch's default dtype
+            return vnet((self.group_to_vec(x).to(dt), self.group_to_vec(force).to(dt)))
+        vnet = self._get_vnet(step)
+        return vnet((x, force))
+
+    def _call_xnet(self, step: int, inputs: tuple[Tensor, Tensor], first: bool = False):
+        x, v = inputs
+        xnet = self._get_xnet(step, first)
+        if not self._su3:
+            x = self.g.group_to_vec(x)
+        else:
+            x = torch.stack([x.real, x.imag], 1)
+            v = torch.stack([v.real, v.imag], 1)
+        return xnet((x, v))
+
+    def _eps(self, p: Tensor) -> float:
+        """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394)"""
+        return float(sigmoid(p.detach().log()))
+
+    def _forward_lf(self, step: int, state: State) -> tuple[State, Tensor]:
+        m, mb = self._get_mask(step)
+        state, logdet = self._update_v_fwd(step, state)
+        sumlogdet = logdet
+        state, logdet = self._update_x_fwd(step, state, m, first=True)
+        sumlogdet = sumlogdet + logdet
+        state, logdet = self._update_x_fwd(step, state, mb, first=False)
+        sumlogdet = sumlogdet + logdet
+        state, logdet = self._update_v_fwd(step, state)
+        return state, sumlogdet + logdet
+
+    def _backward_lf(self, step: int, state: State) -> tuple[State, Tensor]:
+        step_r = self.config.nleapfrog - step - 1
+        m, mb = self._get_mask(step_r)
+        state, logdet = self._update_v_bwd(step_r, state)
+        sumlogdet = logdet
+        state, logdet = self._update_x_bwd(step_r, state, mb, first=False)
+        sumlogdet = sumlogdet + logdet
+        state, logdet = self._update_x_bwd(step_r, state, m, first=True)
+        sumlogdet = sumlogdet + logdet
+        state, logdet = self._update_v_bwd(step_r, state)
+        return state, sumlogdet + logdet
+
+    def _update_v(self, step: int, state: State, sign: int) -> tuple[State, Tensor]:
+        """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel"""
+        force = self.grad_potential(state.x, state.beta)
+        eps = self._eps(self.veps[step])
+        s, t, q = self._call_vnet(step, (state.x, force))
+        if self._su3:
+            v, logdet = ops.su3_vupdate(self.unflatten(state.v), self.unflatten(force), s, t, q, eps, sign)
+        else:
+            v, logdet = ops.u1_vupdate(state.v, force, s, t, q, eps, sign)
+        return State(state.x, v, state.beta), logdet
+
+    def _update_v_fwd(self, step: int, state: State) -> tuple[State, Tensor]:
+        return self._update_v(step, state, +1)
+
+    def _update_v_bwd(self, step: int, state: State) -> tuple[State, Tensor]:
+        return self._update_v(step, state, -1)
+
+    def _update_x(self, step: int, state: State, m: Tensor, first: bool, sign: int) -> tuple[State, Tensor]:
+        """dynamics.py:1386-1477"""
+        eps = self._eps(self.xeps[step])
+        x = self.unflatten(state.x)
+        if self._su3:
+            # x' = m*x + exp(+-eps v) @ ((1-m)*x); xnet is never called, logdet = 0
+            xn = ops.su3_update_gauge(x, self.unflatten(state.v), sign * eps, mask=m)
+            return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
+        xm_init = self.unflatten(m) * x
+        s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)
+        xn, logdet = ops.u1_xupdate(x, state.v, s, t, q, m, eps, sign, self.config.use_ncp)
+        return State(x=xn, v=state.v, beta=state.beta), logdet
+
+    def _update_x_fwd(self, step: int, state: State, m: Tensor, first: bool) -> tuple[State, Tensor]:
+        return self._update_x(step, state, m, first, +1)
+
+    def _update_x_bwd(self, step: int, state: State, m: Tensor, first: bool) -> tuple[State, Tensor]:
+        return self._update_x(step, state, m, first, -1)
+
+    # ------------------------------------------------------------ energies
+    def hamiltonian(self, state: State) -> Tensor:
+        return self.kinetic_energy(state.v) + self.potential_energy(state.x, state.beta)
+
+    def kinetic_energy(self, v: Tensor) -> Tensor:
+        return self.g.kinetic_energy(self.unflatten(v) if self._su3 else v)
+
+    def potential_energy(self, x: Tensor, beta: Tensor):
+        return self.potential_fn(x, beta)
+
+    def grad_potential(self, x: Tensor, beta: Tensor) -> Tensor:
+        return self.lattice.grad_action(x, beta)

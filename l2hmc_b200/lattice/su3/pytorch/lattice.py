@@ -1,0 +1,146 @@
+"""`LatticeSU3` with the reference's method surface
+(`lattice/su3/pytorch/lattice.py:41-349`), backed by the stencil kernels of
+libl2b: plaquette traces / per-chain sums (`l2b_su3_wilson_loops`,
+`l2b_su3_plaq_sums`) and the analytic staple force (`l2b_su3_force`) in place of
+the reference's autograd-of-the-action.
+
+`x`: `[nb, 4, T, X, Y, Z, 3, 3]` complex128 on CUDA (or flattened `[nb, -1]`).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ....configs import Charges
+from ....group.su3.pytorch.group import SU3
+from ....lattice.lattice import Lattice
+from .... import ops
+
+Tensor = torch.Tensor
+
+
+def _f(beta) -> float:
+    return float(beta.detach()) if isinstance(beta, torch.Tensor) else float(beta)
+
+
+class LatticeSU3(Lattice):
+    """4D lattice with SU(3) links."""
+    dim = 4
+
+    def __init__(self, nchains: int, shape: list[int], c1: float = 0.0) -> None:
+        assert len(shape) == 4
+        self.g = SU3()
+        self.nt, self.nx, self.ny, self.nz = shape
+        self.c1 = c1
+        if c1 != 0.0:
+            raise NotImplementedError(
+                'rectangle (DBW2, c1 != 0) term: SURVEY.md section 8 f-4, not built yet; '
+                'every shipped config uses c1 = 0 (configs.py:658)')
+        super().__init__(group=self.g, nchains=nchains, shape=list(shape))
+
+    def _field(self, x: Tensor) -> Tensor:
+        if x.dim() != 8:
+            x = x.reshape(x.shape[0], *self._shape[1:])
+        return x
+
+    def coeffs(self, beta) -> dict:
+        b = _f(beta)
+        return {'plaq': b * (1.0 - 8.0 * self.c1), 'rect': b * self.c1}
+
+    # -- observables ---------------------------------------------------------
+    def _sums(self, x: Tensor) -> Tensor:
+        """[nb, 2] = (sum Re tr P, sum Im tr P) in one pass over the links"""
+        return ops.su3_plaq_sums(self._field(x.detach()))
+
+    def wilson_loops(self, x: Tensor) -> Tensor:
+        """ps[6, nb, T, X, Y, Z]   (lattice.py:157-199,242-244)"""
+        return ops.su3_wilson_loops(self._field(x.detach()))
+
+    def _wilson_loops(self, x: Tensor, needs_rect: bool = False) -> tuple[Tensor, Tensor]:
+        assert not needs_rect, 'rectangles: SURVEY section 8 f-4'
+        ps = self.wilson_loops(x)
+        return ps, torch.zeros((12, *ps.shape[1:]), dtype=ps.dtype, device=ps.device)
+
+    def action(self, x: Tensor, beta) -> Tensor:
+        """S = -(beta/3) sum Re tr P   (lattice.py:252-269)"""
+        return self._sums(x)[:, 0] * (-_f(beta) / 3.0)
+
+    def _action(self, wloops, beta) -> Tensor:
+        """NB: the reference's `_action` has no minus sign (lattice.py:271-285)"""
+        ps = wloops[0] if isinstance(wloops, (tuple, list)) else wloops
+        psum = ps.real.sum(tuple(range(2, ps.dim()))).sum(0)
+        return self.coeffs(beta)['plaq'] * psum / 3.0
+
+    def _plaquettes(self, x: Tensor) -> Tensor:
+        return self._sums(x)[:, 0] / (6 * 3 * self.volume)
+
+    def _plaqs(self, wloops: Tensor) -> Tensor:
+        psum = wloops.real.sum(tuple(range(2, wloops.dim()))).sum(0)
+        return psum / (6 * 3 * self.volume)
+
+    def plaqs(self, x: Optional[Tensor] = None, wloops: Optional[Tensor] = None) -> Tensor:
+        if wloops is None:
+            assert x is not None
+            return self._plaquettes(x)
+        return self._plaqs(wloops)
+
+    def _charges(self, wloops: Tensor) -> Charges:
+        qsum = wloops.imag.sum(tuple(range(2, wloops.dim()))).sum(0)
+        return Charges(intQ=qsum / (32 * (np.pi ** 2)), sinQ=qsum / (6 * 3 * self.volume))
+
+    def _int_charges(self, wloops: Tensor) -> Tensor:
+        return self._charges(wloops).intQ
+
+    def _sin_charges(self, wloops: Tensor) -> Tensor:
+        return self._charges(wloops).sinQ
+
+    def charges(self, x: Optional[Tensor] = None, wloops: Optional[Tensor] = None) -> Charges:
+        if wloops is not None:
+            return self._charges(wloops)
+        q = self._sums(x)[:, 1]
+        return Charges(intQ=q / (32 * (np.pi ** 2)), sinQ=q / (6 * 3 * self.volume))
+
+    def int_charges(self, x: Optional[Tensor] = None, wloops: Optional[Tensor] = None) -> Tensor:
+        return self.charges(x, wloops).intQ
+
+    def sin_charges(self, x: Optional[Tensor] = None, wloops: Optional[Tensor] = None) -> Tensor:
+        return self.charges(x, wloops).sinQ
+
+    # -- energies / force ----------------------------------------------------
+    def kinetic_energy(self, v: Tensor) -> Tensor:
+        return self.g.kinetic_energy(self._field(v))
+
+    def grad_action(self, x: Tensor, beta) -> Tensor:
+        """(beta/3) TAH(U A), analytic; equals the reference's
+        projectTAH(autograd(S) @ x^+) (lattice.py:299-308).  Like the reference
+        (no create_graph) the result is a constant w.r.t. later backprop."""
+        return ops.su3_force(self._field(x.detach()), _f(beta))
+
+    def action_with_grad(self, x: Tensor, beta) -> tuple[Tensor, Tensor]:
+        """one force pass yields both (lattice.py:287-297)"""
+        f, ps = ops.su3_force(self._field(x.detach()), _f(beta), want_plaq_sum=True)
+        return ps * (-_f(beta) / 3.0), f
+
+    def calc_metrics(self, x: Tensor, beta=None, xinit: Optional[Tensor] = None) -> dict:
+        """lattice.py:310-349"""
+        sums = self._sums(x)
+        V18 = 6 * 3 * self.volume
+        plaqs = sums[:, 0] / V18
+        intQ, sinQ = sums[:, 1] / (32 * np.pi ** 2), sums[:, 1] / V18
+        metrics = {'plaqs': plaqs, 'sinQ': sinQ, 'intQ': intQ}
+        if beta is not None:
+            s, dsdx = self.action_with_grad(x, beta)
+            metrics.update({'action': s, 'dsdx': dsdx})
+            if xinit is not None:
+                s_, dsdx_ = self.action_with_grad(xinit, beta)
+                metrics.update({'daction': (s - s_).abs(), 'dsdx': (dsdx - dsdx_).abs()})
+        if xinit is not None:
+            sums_ = self._sums(xinit)
+            metrics.update({
+                'dplaqs': (plaqs - sums_[:, 0] / V18).abs(),
+                'dQint': (intQ - sums_[:, 1] / (32 * np.pi ** 2)).abs(),
+                'dQsin': (sinQ - sums_[:, 1] / V18).abs(),
+            })
+        return metrics

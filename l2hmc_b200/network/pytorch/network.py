@@ -1,0 +1,286 @@
+"""xnet / vnet `LeapfrogLayer`s with the reference's module tree and parameter
+names (`network/pytorch/network.py:151-801`, `network/factory.py:21-71`), so a
+reference `state_dict` loads unchanged:
+
+    input_layer.{conv_stack.layers.<i>, xlayer, vlayer}, hidden_layers.<i>,
+    scale.{coeff, layer}, transf.{coeff, layer}, transl, batch_norm
+
+    z = act(W_x flat(conv?(x)) + W_v flat(v));  z = act(W_i z) ...
+    s = a_s e^{c_s} tanh(W_s z),  t = a_t W_t z,  q = a_q e^{c_q} tanh(W_q z)
+
+The dense / conv layers run on cuBLAS / cuDNN through torch.nn (library GEMMs);
+everything the integrator does with (s, t, q) afterwards is in libl2b's fused
+epilogue kernels (`l2b_su3_vupdate`, `l2b_u1_vupdate`, `l2b_u1_xupdate`).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ...configs import ConvolutionConfig, InputSpec, NetWeight, NetWeights, NetworkConfig
+
+Tensor = torch.Tensor
+
+
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError('l2hmc_b200 needs a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def activation_fn(name: str) -> nn.Module:
+    """fresh module per network (reference shares global inplace instances,
+    network.py:40-46; the arithmetic is identical)"""
+    fns = {
+        'elu': lambda: nn.ELU(inplace=True),
+        'tanh': lambda: nn.Tanh(),
+        'relu': lambda: nn.ReLU(inplace=True),
+        'swish': lambda: nn.SiLU(),
+        'leaky_relu': lambda: nn.LeakyReLU(inplace=True),
+    }
+    if name not in fns:
+        raise ValueError(f'unknown activation {name!r}')
+    return fns[name]()
+
+
+def flatten(x: Tensor) -> Tensor:
+    return x.reshape(x.shape[0], -1)
+
+
+def dummy_network(inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor]:
+    """network.py:69-77"""
+    x, _ = inputs
+    return torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
+
+
+class PeriodicPadding(nn.Module):
+    """wraps `size` on BOTH sides of the last two axes (network.py:151-172)"""
+
+    def __init__(self, size: int):
+        super().__init__()
+        self.size = size
+
+    def forward(self, x: Tensor) -> Tensor:
+        assert len(x.shape) >= 3, 'Expected len(x.shape) >= 3'
+        x = torch.cat([x[:, :, -self.size:, :], x, x[:, :, 0:self.size, :]], 2)
+        return torch.cat([x[:, :, :, -self.size:], x, x[:, :, :, 0:self.size]], 3)
+
+
+class ScaledTanh(nn.Module):
+    """exp(coeff) * tanh(W x + b)   (network.py:175-206)"""
+
+    def __init__(self, in_features: int, out_features: int) -> None:
+        super().__init__()
+        self.coeff = nn.Parameter(torch.zeros(1, out_features))
+        self.layer = nn.Linear(in_features=in_features, out_features=out_features)
+
+    def forward(self, x):
+        return self.coeff.exp() * torch.tanh(self.layer(x))
+
+
+class ConvStack(nn.Module):
+    """network.py:240-346; same `layers` ordering so indices (hence state_dict
+    keys) match."""
+
+    def __init__(self, xshape: Sequence[int], conv_config: ConvolutionConfig, activation_fn: Any,
+                 use_batch_norm: bool = False) -> None:
+        super().__init__()
+        if len(xshape) == 3:
+            d, nt, nx = xshape[0], xshape[1], xshape[2]
+        elif len(xshape) == 4:
+            _, d, nt, nx = xshape
+        elif len(xshape) == 8:
+            d = xshape[1]
+            nt, nx = xshape[2], xshape[3]
+        else:
+            raise ValueError(f'Invalid value for xshape: {xshape}')
+        self.d, self.nt, self.nx = d, nt, nx
+        self.xshape = xshape
+        self.xdim = int(np.prod(xshape[1:]))
+        self.activation_fn = activation_fn
+        self.layers = nn.ModuleList()
+        filters = list(conv_config.filters or [])
+        sizes = list(conv_config.sizes or [])
+        if len(filters) > 0 and len(filters) == len(sizes):
+            self.layers.append(PeriodicPadding(sizes[0] - 1))
+            self.layers.append(nn.LazyConv2d(filters[0], sizes[0]))
+            for idx, (f, n) in enumerate(zip(filters[1:], sizes[1:])):
+                self.layers.append(PeriodicPadding(n - 1))
+                self.layers.append(nn.LazyConv2d(f, n))
+                if (idx + 1) % 2 == 0:
+                    p = 2 if conv_config.pool is None else conv_config.pool[idx]
+                    self.layers.append(nn.MaxPool2d(p))
+                self.layers.append(self.activation_fn)
+        self.layers.append(nn.Flatten())
+        if use_batch_norm:
+            self.layers.append(nn.LazyBatchNorm1d())
+        self.layers.append(nn.LazyLinear(self.xdim))
+        self.layers.append(self.activation_fn)
+
+    def forward(self, x: Tensor) -> Tensor:
+        if tuple(x.shape) != tuple(self.xshape):
+            try:
+                x = x.reshape(x.shape[0], self.d + 2, self.nt, self.nx)
+            except (ValueError, RuntimeError):
+                x = x.reshape((x.shape[0], *self.xshape[1:]))
+        for layer in self.layers:
+            x = layer(x)
+        return x
+
+
+class InputLayer(nn.Module):
+    """network.py:349-451"""
+
+    def __init__(self, xshape: Sequence[int], network_config: NetworkConfig, activation_fn: Callable,
+                 conv_config: Optional[ConvolutionConfig] = None) -> None:
+        super().__init__()
+        self.xshape = xshape
+        self.activation_fn = activation_fn
+        conv_stack: nn.Module = nn.Identity()
+        if conv_config is not None and conv_config.filters is not None and len(conv_config.filters) > 0:
+            conv_stack = ConvStack(xshape=xshape, conv_config=conv_config, activation_fn=activation_fn)
+        self.conv_stack = conv_stack
+        self.xlayer = nn.LazyLinear(network_config.units[0])
+        self.vlayer = nn.LazyLinear(network_config.units[0])
+
+    def forward(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
+        x, v = inputs
+        x = self.conv_stack(x)
+        v = self.vlayer(flatten(v))
+        x = self.xlayer(flatten(x))
+        return self.activation_fn(x + v)
+
+
+class LeapfrogLayer(nn.Module):
+    """network.py:454-551"""
+
+    def __init__(self, xshape: Sequence[int], network_config: NetworkConfig,
+                 input_shapes: Optional[dict] = None, net_weight: Optional[NetWeight] = None,
+                 conv_config: Optional[ConvolutionConfig] = None, name: Optional[str] = None):
+        super().__init__()
+        self.xshape = xshape
+        self.nw = NetWeight(1., 1., 1.) if net_weight is None else net_weight
+        self.net_config = network_config
+        self.name = name if name is not None else 'network'
+        self.xdim = int(np.prod(xshape[1:]))
+        act = network_config.activation_fn
+        self.activation_fn = activation_fn(act) if isinstance(act, str) else act
+        self.input_layer = InputLayer(xshape=xshape, network_config=network_config,
+                                      activation_fn=self.activation_fn, conv_config=conv_config)
+        self.units = list(network_config.units)
+        self.hidden_layers = nn.ModuleList(
+            [nn.Linear(self.units[i], u) for i, u in enumerate(self.units[1:])])
+        self.scale = ScaledTanh(self.units[-1], self.xdim)
+        self.transf = ScaledTanh(self.units[-1], self.xdim)
+        self.transl = nn.Linear(self.units[-1], self.xdim)
+        self.dropout = nn.Dropout(network_config.dropout_prob)
+        if network_config.use_batch_norm:
+            self.batch_norm = nn.BatchNorm1d(self.units[-1])
+
+    def set_net_weight(self, net_weight: NetWeight):
+        self.nw = net_weight
+
+    def forward(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor]:
+        z = self.input_layer(inputs)
+        for layer in self.hidden_layers:
+            z = self.activation_fn(layer(z))
+        if self.net_config.dropout_prob > 0:
+            z = self.dropout(z)
+        if self.net_config.use_batch_norm:
+            z = self.batch_norm(z)
+        s = self.nw.s * self.scale(z)
+        t = self.nw.t * self.transl(z)
+        q = self.nw.q * self.transf(z)
+        return s, t, q
+
+
+def get_and_call_network(xshape: Sequence[int], *, network_config: NetworkConfig, is_xnet: bool, group,
+                         input_shapes=None, net_weight=None, conv_config=None, name=None) -> LeapfrogLayer:
+    """Build a LeapfrogLayer on the GPU and materialise its lazy layers with one
+    dummy call, as the reference does (network.py:572-631); only the SHAPES of
+    the dummy inputs matter."""
+    dev = _device()
+    net = LeapfrogLayer(xshape=xshape, network_config=network_config, input_shapes=input_shapes,
+                        net_weight=net_weight, conv_config=conv_config, name=name).to(dev)
+    nb = 2
+    dt = torch.get_default_dtype()
+    gname = getattr(group, '_name', None)
+    if gname == 'SU3':
+        lat = tuple(xshape[1:6])                       # (4, T, X, Y, Z)
+        if is_xnet:                                    # cat(real, imag) on dim 1 (network.py:614-616)
+            x = torch.zeros((nb, 2 * lat[0], *lat[1:], 3, 3), dtype=dt, device=dev)
+            v = torch.zeros_like(x)
+        else:                                          # group_to_vec -> 8 reals per link
+            x = torch.zeros((nb, *lat, 8), dtype=dt, device=dev)
+            v = torch.zeros_like(x)
+    else:
+        d, T, X = xshape[1], xshape[2], xshape[3]
+        x = torch.zeros((nb, 2 * d if is_xnet else d, T, X), dtype=dt, device=dev)
+        v = torch.zeros((nb, d * T * X), dtype=dt, device=dev)
+    was_training = net.training
+    net.eval()                                          # keep BatchNorm statistics untouched
+    with torch.no_grad():
+        _ = net((x, v))
+    net.train(was_training)
+    return net
+
+
+class NetworkFactory:
+    """network/factory.py:21-71 + network.py:634-801"""
+
+    def __init__(self, input_spec: InputSpec, network_config: NetworkConfig,
+                 conv_config: Optional[ConvolutionConfig] = None, net_weights: Optional[NetWeights] = None,
+                 build_unused_su3_xnet: bool = True):
+        if net_weights is None:
+            net_weights = NetWeights(x=NetWeight(1., 1., 1.), v=NetWeight(1., 1., 1.))
+        self.nw = net_weights
+        self.input_spec = input_spec
+        self.network_config = network_config
+        self.conv_config = conv_config
+        # The SU(3) x-update never calls xnet (dynamics.py:1420-1425) but the
+        # reference still builds it; keep it by default so state_dicts match.
+        self.build_unused_su3_xnet = build_unused_su3_xnet
+        self.config = {'net_weights': self.nw, 'input_spec': self.input_spec, 'network_config': self.network_config}
+
+    def get_build_configs(self):
+        return {
+            'xnet': {'net_weight': self.nw.x, 'xshape': self.input_spec.xshape,
+                     'input_shapes': self.input_spec.xnet, 'network_config': self.network_config,
+                     'conv_config': self.conv_config},
+            'vnet': {'net_weight': self.nw.v, 'xshape': self.input_spec.xshape,
+                     'input_shapes': self.input_spec.vnet, 'network_config': self.network_config},
+        }
+
+    def build_xnet(self, group, name: Optional[str] = None) -> nn.Module:
+        if getattr(group, '_name', None) == 'SU3' and not self.build_unused_su3_xnet:
+            return nn.Identity()
+        return get_and_call_network(
+            xshape=self.input_spec.xshape, network_config=self.network_config, is_xnet=True, group=group,
+            input_shapes=self.input_spec.xnet, net_weight=self.nw.x, conv_config=self.conv_config,
+            name='xnet' if name is None else f'xnet/{name}')
+
+    def build_vnet(self, group, name: Optional[str] = None) -> LeapfrogLayer:
+        return get_and_call_network(
+            xshape=self.input_spec.xshape, network_config=self.network_config, is_xnet=False, group=group,
+            input_shapes=self.input_spec.vnet, net_weight=self.nw.v, conv_config=self.conv_config,
+            name='vnet' if name is None else f'vnet/{name}')
+
+    def build_networks(self, n: int, split_xnets: bool, group) -> nn.ModuleDict:
+        assert n >= 1, 'Must build at least one network'
+        if n == 1:
+            return nn.ModuleDict({'xnet': self.build_xnet(group=group), 'vnet': self.build_vnet(group=group)})
+        vnet, xnet = nn.ModuleDict(), nn.ModuleDict()
+        for lf in range(n):
+            vnet[f'{lf}'] = self.build_vnet(group=group, name=f'{lf}')
+            if split_xnets:
+                xnet[f'{lf}'] = nn.ModuleDict({
+                    'first': self.build_xnet(group=group, name=f'{lf}/first'),
+                    'second': self.build_xnet(group=group, name=f'{lf}/second'),
+                })
+            else:
+                xnet[f'{lf}'] = self.build_xnet(group=group, name=f'{lf}')
+        return nn.ModuleDict({'xnet': xnet, 'vnet': vnet})

@@ -1,0 +1,392 @@
+"""Tensor-level entry points over the C ABI (include/l2b.h).
+
+Every function here takes/returns CUDA `torch.Tensor`s, hands raw device
+pointers + the current CUDA stream to libl2b through ctypes and allocates the
+outputs/workspace the library asks for.  torch is used for device memory and
+streams only; no arithmetic of the hot path happens in torch here, and there is
+no CPU path: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_size_t, c_void_p
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import L2B_F32, L2B_F64, L2BError, call, dims4
+
+Tensor = torch.Tensor
+
+_WS: dict = {}
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> c_void_p:
+    return c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L2BError(
+                'l2hmc_b200 runs on CUDA tensors only (got a CPU tensor); '
+                'there is no CPU fallback')
+
+
+def _workspace(nbytes: int, device: torch.device) -> Tensor:
+    """Grow-only scratch buffer per device.  Calls are stream-ordered on the
+    current stream, so one buffer per device is safe for a single-stream caller
+    (the reference is single-threaded on the default stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+def free_workspaces() -> None:
+    _WS.clear()
+
+
+# ---------------------------------------------------------------------------
+# SU(3)
+# ---------------------------------------------------------------------------
+def _su3_field(x: Tensor, shape: Optional[Sequence[int]] = None) -> tuple[Tensor, int, list[int]]:
+    """-> (contiguous complex128 [nb,4,T,X,Y,Z,3,3], nb, [T,X,Y,Z])"""
+    _need_cuda(x)
+    if x.dtype != torch.complex128:
+        raise L2BError(f'SU(3) fields must be complex128 (got {x.dtype})')
+    if x.dim() != 8:
+        if shape is None:
+            raise L2BError(f'SU(3) field of shape {tuple(x.shape)} needs an explicit lattice shape')
+        x = x.reshape(x.shape[0], 4, *shape, 3, 3)
+    if tuple(x.shape[-2:]) != (3, 3) or x.shape[1] != 4:
+        raise L2BError(f'bad SU(3) field shape {tuple(x.shape)}')
+    return x.contiguous(), int(x.shape[0]), [int(s) for s in x.shape[2:6]]
+
+
+def _su3_ws(nb: int, dims: Sequence[int], device) -> tuple[Tensor, int]:
+    n = _lib.su3_ws_bytes(nb, dims)
+    return _workspace(n, device), n
+
+
+def su3_wilson_loops(x: Tensor) -> Tensor:
+    x, nb, dims = _su3_field(x)
+    out = torch.empty((6, nb, *dims), dtype=torch.complex128, device=x.device)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_wilson_loops', _ptr(x), _ptr(out), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return out
+
+
+def su3_plaq_sums(x: Tensor) -> Tensor:
+    """[nb, 2] = (sum Re tr P, sum Im tr P)"""
+    x, nb, dims = _su3_field(x)
+    out = torch.empty((nb, 2), dtype=torch.float64, device=x.device)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_plaq_sums', _ptr(x), _ptr(out), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return out
+
+
+def su3_force(x: Tensor, beta: float, want_plaq_sum: bool = False):
+    x, nb, dims = _su3_field(x)
+    f = torch.empty_like(x)
+    ps = torch.empty(nb, dtype=torch.float64, device=x.device) if want_plaq_sum else None
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_force', _ptr(x), float(beta), _ptr(f), _ptr(ps), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return (f, ps) if want_plaq_sum else f
+
+
+def _mats(x: Tensor) -> tuple[Tensor, int]:
+    _need_cuda(x)
+    if x.dtype != torch.complex128 or tuple(x.shape[-2:]) != (3, 3):
+        raise L2BError(f'expected [..., 3, 3] complex128 (got {tuple(x.shape)} {x.dtype})')
+    x = x.contiguous()
+    return x, x.numel() // 9
+
+
+def su3_exp(p: Tensor, scale: float = 1.0) -> Tensor:
+    p, n = _mats(p)
+    out = torch.empty_like(p)
+    call('l2b_su3_exp', _ptr(p), float(scale), _ptr(out), n, L2B_F64, _stream())
+    return out
+
+
+def su3_tah(x: Tensor) -> Tensor:
+    x, n = _mats(x)
+    out = torch.empty_like(x)
+    call('l2b_su3_tah', _ptr(x), _ptr(out), n, L2B_F64, _stream())
+    return out
+
+
+def su3_project(x: Tensor, want_matrix: bool = True, want_vec: bool = False):
+    x, n = _mats(x)
+    m = torch.empty_like(x) if want_matrix else None
+    v = torch.empty((*x.shape[:-2], 8), dtype=torch.float64, device=x.device) if want_vec else None
+    call('l2b_su3_project', _ptr(x), _ptr(m), _ptr(v), n, L2B_F64, _stream())
+    if want_matrix and want_vec:
+        return m, v
+    return m if want_matrix else v
+
+
+def su3_to_vec(x: Tensor) -> Tensor:
+    x, n = _mats(x)
+    v = torch.empty((*x.shape[:-2], 8), dtype=torch.float64, device=x.device)
+    call('l2b_su3_to_vec', _ptr(x), _ptr(v), n, L2B_F64, _stream())
+    return v
+
+
+def su3_from_vec(v: Tensor) -> Tensor:
+    _need_cuda(v)
+    if v.dtype != torch.float64 or v.shape[-1] != 8:
+        raise L2BError(f'expected [..., 8] float64 (got {tuple(v.shape)} {v.dtype})')
+    v = v.contiguous()
+    x = torch.empty((*v.shape[:-1], 3, 3), dtype=torch.complex128, device=v.device)
+    call('l2b_su3_from_vec', _ptr(v), _ptr(x), v.numel() // 8, L2B_F64, _stream())
+    return x
+
+
+def su3_update_gauge(x: Tensor, p: Tensor, eps: float = 1.0, mask: Optional[Tensor] = None,
+                     mask_complement: bool = False) -> Tensor:
+    x, nb, dims = _su3_field(x)
+    p, nbp, _ = _su3_field(p, dims)
+    if p.shape != x.shape:
+        raise L2BError(f'x {tuple(x.shape)} and p {tuple(p.shape)} differ')
+    if mask is not None:
+        _need_cuda(mask)
+        mask = mask.to(torch.float32).contiguous()
+        if mask.numel() != x[0].numel():
+            raise L2BError(f'mask has {mask.numel()} entries, expected {x[0].numel()}')
+    out = torch.empty_like(x)
+    call('l2b_su3_update_gauge', _ptr(x), _ptr(p), float(eps), _ptr(mask), int(mask_complement), _ptr(out), nb,
+         dims4(dims), L2B_F64, _stream())
+    return out
+
+
+def su3_kinetic(p: Tensor) -> Tensor:
+    p, nb, dims = _su3_field(p)
+    ke = torch.empty(nb, dtype=torch.float64, device=p.device)
+    ws, n = _su3_ws(nb, dims, p.device)
+    call('l2b_su3_kinetic', _ptr(p), _ptr(ke), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return ke
+
+
+def su3_check(x: Tensor) -> tuple[Tensor, Tensor]:
+    x, nb, dims = _su3_field(x)
+    avg = torch.empty(nb, dtype=torch.float64, device=x.device)
+    mx = torch.empty_like(avg)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_check', _ptr(x), _ptr(avg), _ptr(mx), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return avg, mx
+
+
+def su3_rand_momentum(nb: int, dims: Sequence[int], seed: int, offset: int, device, want_ke: bool = False):
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise L2BError('su3_rand_momentum needs a CUDA device')
+    p = torch.empty((nb, 4, *dims, 3, 3), dtype=torch.complex128, device=device)
+    ke = torch.empty(nb, dtype=torch.float64, device=device) if want_ke else None
+    ws, n = _su3_ws(nb, dims, device)
+    with torch.cuda.device(device):
+        call('l2b_su3_rand_momentum', int(seed) & (2**64 - 1), int(offset), _ptr(p), _ptr(ke), nb, dims4(dims),
+             L2B_F64, _ptr(ws), n, _stream())
+    return (p, ke) if want_ke else p
+
+
+def su3_vupdate(v: Tensor, force: Tensor, s: Optional[Tensor], t: Optional[Tensor], q: Optional[Tensor],
+                eps: float, sign: int) -> tuple[Tensor, Tensor]:
+    v, nb, dims = _su3_field(v)
+    force, _, _ = _su3_field(force, dims)
+    xdim = v[0].numel()
+
+    def real(a):
+        if a is None:
+            return None
+        _need_cuda(a)
+        a = a.to(torch.float64).contiguous()
+        if a.numel() != nb * xdim:
+            raise L2BError(f's/t/q must have {nb * xdim} entries (got {a.numel()})')
+        return a
+    s, t, q = real(s), real(t), real(q)
+    out = torch.empty_like(v)
+    logdet = torch.empty(nb, dtype=torch.float64, device=v.device)
+    ws, n = _su3_ws(nb, dims, v.device)
+    call('l2b_su3_vupdate', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(out),
+         _ptr(logdet), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return out, logdet
+
+
+def su3_hmc_trajectory(x: Tensor, v: Tensor, beta: float, eps: float, nlf: int):
+    """-> (x_prop, v_prop, energies[nb, 4] = (KE0, S0, KE1, S1))"""
+    x, nb, dims = _su3_field(x)
+    v, _, _ = _su3_field(v, dims)
+    if v.shape != x.shape:
+        raise L2BError(f'x {tuple(x.shape)} and v {tuple(v.shape)} differ')
+    xo = torch.empty_like(x)
+    vo = torch.empty_like(v)
+    en = torch.empty((nb, 4), dtype=torch.float64, device=x.device)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_hmc_trajectory', _ptr(x), _ptr(v), float(beta), float(eps), int(nlf), _ptr(xo), _ptr(vo),
+         _ptr(en), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return xo, vo, en
+
+
+def su3_aos_to_soa(x: Tensor) -> Tensor:
+    x, nb, dims = _su3_field(x)
+    out = torch.empty_like(x)
+    call('l2b_su3_aos_to_soa', _ptr(x), _ptr(out), nb, dims4(dims), L2B_F64, _stream())
+    return out
+
+
+def su3_soa_to_aos(x: Tensor) -> Tensor:
+    x, nb, dims = _su3_field(x)
+    out = torch.empty_like(x)
+    call('l2b_su3_soa_to_aos', _ptr(x), _ptr(out), nb, dims4(dims), L2B_F64, _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# U(1)
+# ---------------------------------------------------------------------------
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L2B_F32
+    if t.dtype == torch.float64:
+        return L2B_F64
+    raise L2BError(f'U(1) fields must be float32/float64 (got {t.dtype})')
+
+
+def _u1_field(x: Tensor, shape: Optional[Sequence[int]] = None) -> tuple[Tensor, int, int, int]:
+    _need_cuda(x)
+    if x.dim() != 4:
+        if shape is None:
+            raise L2BError(f'U(1) field of shape {tuple(x.shape)} needs an explicit lattice shape')
+        x = x.reshape(x.shape[0], 2, *shape)
+    if x.shape[1] != 2:
+        raise L2BError(f'bad U(1) field shape {tuple(x.shape)}')
+    _dt(x)
+    return x.contiguous(), int(x.shape[0]), int(x.shape[2]), int(x.shape[3])
+
+
+def u1_wilson_loops(x: Tensor, shape=None) -> Tensor:
+    x, nb, T, X = _u1_field(x, shape)
+    w = torch.empty((nb, T, X), dtype=x.dtype, device=x.device)
+    call('l2b_u1_wilson_loops', _ptr(x), _ptr(w), nb, T, X, _dt(x), _stream())
+    return w
+
+
+def u1_observables(x: Tensor, beta: float, shape=None) -> Tensor:
+    """[nb, 4] = (action, plaq, sinQ, intQ)"""
+    x, nb, T, X = _u1_field(x, shape)
+    obs = torch.empty((nb, 4), dtype=x.dtype, device=x.device)
+    call('l2b_u1_observables', _ptr(x), float(beta), _ptr(obs), nb, T, X, _dt(x), _stream())
+    return obs
+
+
+def u1_force(x: Tensor, beta: float, shape=None) -> Tensor:
+    x, nb, T, X = _u1_field(x, shape)
+    f = torch.empty_like(x)
+    call('l2b_u1_force', _ptr(x), float(beta), _ptr(f), nb, T, X, _dt(x), _stream())
+    return f
+
+
+def u1_hmc_trajectory(x: Tensor, v: Tensor, beta: float, eps: float, nlf: int, shape=None):
+    x, nb, T, X = _u1_field(x, shape)
+    v, _, _, _ = _u1_field(v, (T, X))
+    if v.dtype != x.dtype:
+        raise L2BError('x and v dtypes differ')
+    xo, vo = torch.empty_like(x), torch.empty_like(v)
+    en = torch.empty((nb, 4), dtype=x.dtype, device=x.device)
+    call('l2b_u1_hmc_trajectory', _ptr(x), _ptr(v), float(beta), float(eps), int(nlf), _ptr(xo), _ptr(vo), _ptr(en),
+         nb, T, X, _dt(x), _stream())
+    return xo, vo, en
+
+
+def _rows(a: Optional[Tensor], nb: int, like: Tensor) -> Optional[Tensor]:
+    if a is None:
+        return None
+    _need_cuda(a)
+    return a.to(like.dtype).reshape(nb, -1).contiguous()
+
+
+def u1_vupdate(v: Tensor, force: Tensor, s, t, q, eps: float, sign: int) -> tuple[Tensor, Tensor]:
+    _need_cuda(v, force)
+    nb = v.shape[0]
+    v2 = v.reshape(nb, -1).contiguous()
+    f2 = force.to(v.dtype).reshape(nb, -1).contiguous()
+    xdim = v2.shape[1]
+    s, t, q = _rows(s, nb, v2), _rows(t, nb, v2), _rows(q, nb, v2)
+    out = torch.empty_like(v2)
+    logdet = torch.empty(nb, dtype=v.dtype, device=v.device)
+    call('l2b_u1_vupdate', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(out),
+         _ptr(logdet), nb, xdim, _dt(v2), _stream())
+    return out.reshape(v.shape), logdet
+
+
+def u1_xupdate(x: Tensor, v: Tensor, s, t, q, mask: Tensor, eps: float, sign: int, use_ncp: bool):
+    _need_cuda(x, v, mask)
+    nb = x.shape[0]
+    x2 = x.reshape(nb, -1).contiguous()
+    v2 = v.to(x.dtype).reshape(nb, -1).contiguous()
+    xdim = x2.shape[1]
+    s, t, q = _rows(s, nb, x2), _rows(t, nb, x2), _rows(q, nb, x2)
+    mask = mask.to(torch.float32).reshape(-1).contiguous()
+    if mask.numel() != xdim:
+        raise L2BError(f'mask has {mask.numel()} entries, expected {xdim}')
+    out = torch.empty_like(x2)
+    logdet = torch.empty(nb, dtype=x.dtype, device=x.device)
+    call('l2b_u1_xupdate', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), float(eps), int(sign),
+         int(bool(use_ncp)), _ptr(out), _ptr(logdet), nb, xdim, _dt(x2), _stream())
+    return out.reshape(x.shape), logdet
+
+
+def u1_kinetic(v: Tensor) -> Tensor:
+    _need_cuda(v)
+    nb = v.shape[0]
+    v2 = v.reshape(nb, -1).contiguous()
+    ke = torch.empty(nb, dtype=v.dtype, device=v.device)
+    call('l2b_u1_kinetic', _ptr(v2), _ptr(ke), nb, v2.shape[1], _dt(v2), _stream())
+    return ke
+
+
+def u1_compat_proj(x: Tensor) -> Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    call('l2b_u1_compat_proj', _ptr(x), _ptr(out), x.numel(), _dt(x), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------
+# accept / reject
+# ---------------------------------------------------------------------------
+def accept_mix(accept: Tensor, pairs: Sequence[tuple[Tensor, Tensor]]) -> list[Tensor]:
+    """out_k[b] = accept[b] ? prop_k[b] : init_k[b] for every (init_k, prop_k).
+    accept: [nb] float32 0/1 (dynamics.py:1081-1087).  Outputs are [nb, -1]."""
+    _need_cuda(accept)
+    accept = accept.to(torch.float32).contiguous()
+    nb = accept.numel()
+    n = len(pairs)
+    inits, props, outs = [], [], []
+    for a, b in pairs:
+        _need_cuda(a, b)
+        a = a.reshape(nb, -1).contiguous()
+        b = b.to(a.dtype).reshape(nb, -1).contiguous()
+        if a.shape != b.shape:
+            raise L2BError(f'init {tuple(a.shape)} and proposed {tuple(b.shape)} differ')
+        inits.append(a)
+        props.append(b)
+        outs.append(torch.empty_like(a))
+    arr = c_void_p * n
+    pi = arr(*[a.data_ptr() for a in inits])
+    pp = arr(*[b.data_ptr() for b in props])
+    po = arr(*[o.data_ptr() for o in outs])
+    rb = (c_size_t * n)(*[a.shape[1] * a.element_size() for a in inits])
+    call('l2b_accept_mix', ctypes.cast(pi, ctypes.POINTER(c_void_p)), ctypes.cast(pp, ctypes.POINTER(c_void_p)),
+         ctypes.cast(po, ctypes.POINTER(c_void_p)), rb, n, _ptr(accept), nb, _stream())
+    return outs

@@ -95,6 +95,17 @@ def su3_goldens(ref, torch):
         out[f'{k}_acc'] = _np(met['acc'])
         out[f'{k}_h0'] = _np(dyn.hamiltonian(st))
         out[f'{k}_h1'] = _np(dyn.hamiltonian(sp))
+    # warm start (plaquette ~0.8 > equilibrium) so that 0 < acc < 1 is exercised
+    cold = torch.eye(3, dtype=torch.complex128).expand(*lat._shape).contiguous()
+    xw = g.update_gauge(cold, 0.2 * lat.random_momentum())
+    vw = lat.random_momentum()
+    out['xw'], out['vw'] = _np(xw), _np(vw)
+    stw = ref.State(x=xw, v=vw, beta=b)
+    spw, metw = dyn.transition_kernel_hmc(stw, eps=0.05, nleapfrog=4)
+    out['hmcw_eps'], out['hmcw_nlf'] = 0.05, 4
+    out['hmcw_x'], out['hmcw_v'] = _np(spw.x), _np(spw.v)
+    out['hmcw_acc'] = _np(metw['acc'])
+    out['hmcw_h0'], out['hmcw_h1'] = _np(dyn.hamiltonian(stw)), _np(dyn.hamiltonian(spw))
     np.savez_compressed(GOLD / 'su3_f64.npz', **out)
 
     # ---- L2HMC forward sweep on a smaller lattice, vnet units [8] ---------

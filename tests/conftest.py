@@ -1,0 +1,35 @@
+"""pytest configuration: registers the `gpu` marker and puts the repo root on
+sys.path.  `-m "not gpu"` runs here on CPU (oracle vs golden vectors, host
+logic, host-emulated kernel bodies, C-ABI symbol check); `-m gpu` are the
+parity tests proper and call the CUDA path through the C ABI on a B200."""
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason='no CUDA device in this container')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+    return ROOT / 'tests' / 'golden'

@@ -1,0 +1,134 @@
+"""GPU tier (-m gpu): the CUDA U(1) path through the C ABI against the golden
+vectors of the reference (fp32 and fp64) and the numpy oracle.
+
+Tolerances: fp64 1e-12; fp32 1e-5 (north star), applied relative to the
+magnitude of per-chain sums.  "Bit-exact integer topological charge" is checked
+as round(intQ) equality (intQ itself is a float sum of wrapped angles / 2 pi,
+SURVEY 7.3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import u1 as ou1, dynamics as od
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def maxdiff(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - np.asarray(b, dtype=np.float64))))
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from l2hmc_b200 import ops as _ops
+    return _ops
+
+
+@pytest.mark.parametrize('tag,tol', [('f64', 1e-12), ('f32', 1e-5)])
+def test_u1_lattice_ops(ops, golden_dir, tag, tol):
+    gu = np.load(golden_dir / f'u1_{tag}.npz')
+    x, beta = dev(gu['x']), float(gu['beta'])
+    assert maxdiff(host(ops.u1_wilson_loops(x)), gu['wloops']) <= tol
+    obs = host(ops.u1_observables(x, beta))
+    assert obs.dtype == gu['x'].dtype
+    assert np.allclose(obs[:, 0], gu['action'], rtol=tol)
+    assert maxdiff(obs[:, 1], gu['plaqs']) <= tol
+    assert maxdiff(obs[:, 2], gu['sinQ']) <= tol
+    assert maxdiff(obs[:, 3], gu['intQ']) <= tol
+    assert np.array_equal(np.round(obs[:, 3]), np.round(gu['intQ'])), 'integer topological charge must match exactly'
+    assert maxdiff(host(ops.u1_force(x, beta)), gu['force']) <= 10 * tol
+    assert maxdiff(host(ops.u1_compat_proj(3.0 * x)), gu['compat']) <= 10 * tol
+    assert np.allclose(host(ops.u1_kinetic(dev(gu['v']))), ou1.kinetic_energy(gu['v']), rtol=tol)
+
+
+@pytest.mark.parametrize('tag,tol', [('f64', 1e-12), ('f32', 1e-5)])
+def test_u1_hmc_trajectory_vs_reference_golden(ops, golden_dir, tag, tol):
+    gu = np.load(golden_dir / f'u1_{tag}.npz')
+    shape = [int(s) for s in gu['shape']]
+    x, v, beta = dev(gu['x']), dev(gu['v']), float(gu['beta'])
+    xo, vo, en = ops.u1_hmc_trajectory(x, v, beta, 0.1, 5, shape=shape)
+    assert maxdiff(host(xo).reshape(3, -1), gu['hmc_x']) <= 10 * tol
+    assert maxdiff(host(vo).reshape(3, -1), gu['hmc_v']) <= 10 * tol
+    en = host(en).astype(np.float64)
+    h0, h1 = en[:, 0] + en[:, 1], en[:, 2] + en[:, 3]
+    assert np.allclose(h0, gu['hmc_h0'], rtol=tol) and np.allclose(h1, gu['hmc_h1'], rtol=tol)
+    acc = np.exp(np.minimum(h0 - h1, 0))
+    assert maxdiff(acc, gu['hmc_acc']) <= tol * max(1.0, float(np.abs(gu['hmc_h0']).max()))
+
+
+@pytest.mark.parametrize('tag,tol', [('f64', 1e-12), ('f32', 1e-5)])
+def test_u1_l2hmc_elementwise_updates(ops, golden_dir, tag, tol):
+    """x/v update kernels fed with the (s, t, q) the oracle's networks produce"""
+    gu = np.load(golden_dir / f'u1_{tag}.npz')
+    shape = [int(s) for s in gu['shape']]
+    pre = 'dense/'
+    sd = {k[len(pre) + 3:]: gu[k] for k in gu.files if k.startswith(pre + 'sd/')}
+    spec = od.L2HMCSpec(group='U1', xshape=(3, 2, *shape), nleapfrog=2, xeps=list(gu[pre + 'xeps']),
+                        veps=list(gu[pre + 'veps']), masks=list(gu[pre + 'masks']), state_dict=sd,
+                        activation='leaky_relu', use_batch_norm=True)
+    x, v, beta = gu['x'], gu[pre + 'v'], float(gu['beta'])
+    dt = x.dtype.type
+    m = spec.masks[0]
+    for step, first, sign, kx, kl, mask in ((0, True, +1, 'xfwd_x', 'xfwd_logdet', m),
+                                            (1, False, -1, 'xbwd_x', 'xbwd_logdet', m)):
+        eps = od._sig_log(spec.xeps[step], x.dtype)
+        s, t, q = od.call_xnet(spec, step, m.reshape(1, 2, *shape) * x, v, first)
+        xo, ld = ops.u1_xupdate(dev(x), dev(v), dev(s), dev(t), dev(q), dev(mask), float(eps), sign, True)
+        assert maxdiff(host(xo), gu[pre + kx]) <= 20 * tol
+        assert maxdiff(host(ld), gu[pre + kl]) <= 20 * tol
+    f = ou1.grad_action(x, beta)
+    s, t, q = od.call_vnet(spec, 0, x, f)
+    eps = od._sig_log(spec.veps[0], x.dtype)
+    vo, ld = ops.u1_vupdate(dev(v), dev(f), dev(s), dev(t), dev(q), float(eps), +1)
+    assert maxdiff(host(vo), gu[pre + 'vfwd_v']) <= 20 * tol
+    assert maxdiff(host(ld), gu[pre + 'vfwd_logdet']) <= 20 * tol
+    # non-NCP affine update vs the oracle
+    spec.use_ncp = False
+    st = od.State(x, v, beta)
+    for sign, fwd in ((+1, True), (-1, False)):
+        s2, ld2 = od.update_x(spec, 0, st, m, True, fwd)
+        sn, tn, qn = od.call_xnet(spec, 0, m.reshape(1, 2, *shape) * x, v, True)
+        eps = od._sig_log(spec.xeps[0], x.dtype)
+        xo, ld = ops.u1_xupdate(dev(x), dev(v), dev(sn), dev(tn), dev(qn), dev(m), float(eps), sign, False)
+        assert maxdiff(host(xo), s2.x) <= 20 * tol and maxdiff(host(ld), ld2) <= 20 * tol
+
+
+@pytest.mark.parametrize('T,X,nb,dtype', [(2, 2, 1, np.float64), (16, 16, 128, np.float32), (7, 5, 3, np.float64),
+                                          (64, 64, 16, np.float32), (64, 64, 4, np.float64)])
+def test_u1_vs_oracle_shapes(ops, T, X, nb, dtype):
+    rng = np.random.default_rng(T * X + nb)
+    x = rng.uniform(-np.pi, np.pi, (nb, 2, T, X)).astype(dtype)
+    v = rng.standard_normal((nb, 2 * T * X)).astype(dtype)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    beta, eps, nlf = 4.0, 0.05, 10
+    s, acc = od.transition_kernel_hmc(od.U1Ops, od.State(x, v, beta), eps, nlf)
+    xo, vo, en = ops.u1_hmc_trajectory(dev(x), dev(v), beta, eps, nlf, shape=[T, X])
+    assert maxdiff(host(xo).reshape(nb, -1), s.x) <= 20 * tol
+    assert maxdiff(host(vo).reshape(nb, -1), s.v) <= 20 * tol
+    en = host(en).astype(np.float64)
+    h0 = (ou1.kinetic_energy(v) + ou1.action(x, beta)).astype(np.float64)
+    assert np.allclose(en[:, 0] + en[:, 1], h0, rtol=10 * tol)
+    obs = host(ops.u1_observables(dev(x), beta))
+    assert np.array_equal(np.round(obs[:, 3]), np.round(ou1.int_charges(x.astype(np.float64))))
+
+
+def test_u1_reversibility_full_size(ops):
+    """BASELINE cfg 2 shape (64x64, 4096 chains, fp32): run forward, flip v, run back"""
+    nb, T, X = 4096, 64, 64
+    torch.manual_seed(1)
+    x = (torch.rand(nb, 2, T, X, device=DEV) * 2 - 1) * np.pi
+    v = torch.randn(nb, 2, T, X, device=DEV)
+    x1, v1, en = ops.u1_hmc_trajectory(x, v, 4.0, 0.1, 10)
+    x2, v2, _ = ops.u1_hmc_trajectory(x1, -v1, 4.0, 0.1, 10)
+    assert float((x2 - x).abs().max()) < 5e-4     # fp32 round-off over 20 steps of O(10) angles
+    assert float((v2 + v).abs().max()) < 5e-4
+    assert torch.isfinite(en).all()

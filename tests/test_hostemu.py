@@ -1,0 +1,110 @@
+"""CPU tier: the __host__ __device__ bodies of the CUDA kernels
+(l2hmc_b200/csrc/l2b_su3_math.cuh, l2b_su3_site.cuh), compiled for the host by
+tests/hostemu, agree with the golden vectors of the reference.  This checks the
+kernels' arithmetic and lattice index math without a GPU; launch geometry,
+shared-memory staging and reductions are covered by the `-m gpu` tier."""
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import su3 as osu3
+
+HERE = Path(__file__).resolve().parent / 'hostemu'
+P = ctypes.c_void_p
+
+
+@pytest.fixture(scope='module')
+def emu():
+    so = HERE / 'libhostemu.so'
+    src = HERE / 'hostemu.cpp'
+    deps = [src] + list((HERE.parents[1] / 'l2hmc_b200' / 'csrc').glob('*.cuh'))
+    if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in deps):
+        subprocess.check_call(['g++', '-O2', '-std=c++17', '-shared', '-fPIC', '-o', str(so), str(src)])
+    return ctypes.CDLL(str(so))
+
+
+@pytest.fixture(scope='module')
+def g(golden_dir):
+    return np.load(golden_dir / 'su3_f64.npz')
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(P)
+
+
+def maxdiff(a, b):
+    return float(np.max(np.abs(a - b)))
+
+
+def unary(emu, mode, a, scale=1.0, vec=False):
+    a = np.ascontiguousarray(a)
+    out = np.empty_like(a)
+    v8 = np.empty(a.shape[:-2] + (8,)) if vec else None
+    emu.emu_unary(ctypes.c_int(mode), ptr(a), ctypes.c_double(scale), ptr(out), ptr(v8), ctypes.c_size_t(a.size // 9))
+    return (out, v8) if vec else out
+
+
+def test_link_local_math(emu, g):
+    assert maxdiff(unary(emu, 0, g['v'], 0.25), g['expv']) < 1e-14
+    assert maxdiff(unary(emu, 0, g['y'], 1.0), g['expy']) < 1e-11 * np.abs(g['expy']).max()
+    assert maxdiff(unary(emu, 1, g['y']), g['tah_y']) < 1e-15
+    assert maxdiff(unary(emu, 2, g['y']), g['projsu_y']) < 1e-10
+    _, vx = unary(emu, 2, g['x'], vec=True)
+    assert maxdiff(vx, g['vec_x']) < 1e-13
+    m = np.empty_like(g['x'])
+    emu.emu_from_vec(ptr(np.ascontiguousarray(g['vec_x'])), ptr(m), ctypes.c_size_t(m.size // 9))
+    assert maxdiff(m, g['vec2su3']) < 1e-15
+    rng = np.random.default_rng(0)
+    n8 = rng.standard_normal((64, 8))
+    t = np.empty((64, 3, 3), dtype=np.complex128)
+    emu.emu_tah_from_normals(ptr(n8), ptr(t), ctypes.c_size_t(64))
+    assert maxdiff(t, osu3.tah_from_normals(n8)) == 0.0
+    y = np.ascontiguousarray(g['y'])
+    d = np.empty(y.shape[:-2])
+    emu.emu_check(ptr(y), ptr(d), ctypes.c_size_t(y.size // 9))
+    nb = y.shape[0]
+    assert np.allclose(np.sqrt(d.reshape(nb, -1).mean(1) / 20), g['checksu_avg'], rtol=1e-13)
+
+
+def test_exp_large_norm_uses_scaling(emu):
+    rng = np.random.default_rng(3)
+    a = (rng.standard_normal((32, 3, 3)) + 1j * rng.standard_normal((32, 3, 3))) * 6.0
+    ref = osu3.expm(a)
+    out = unary(emu, 0, a)
+    assert np.max(np.abs(out - ref) / np.abs(ref).max()) < 1e-11
+
+
+def test_stencil_bodies(emu, g):
+    x = np.ascontiguousarray(g['x'])
+    nb, beta = x.shape[0], float(g['beta'])
+    dims = (ctypes.c_int * 4)(*[int(s) for s in g['shape']])
+    f = np.empty_like(x)
+    retr = np.empty(nb)
+    emu.emu_force(ptr(x), ctypes.c_double(beta), ptr(f), ptr(retr), ctypes.c_int(nb), dims)
+    assert maxdiff(f, g['force']) < 1e-13
+    assert np.allclose(-beta / 3 * retr / 4, g['action'], rtol=1e-12, atol=1e-12)
+    wl = np.empty((6, nb) + x.shape[2:6], dtype=np.complex128)
+    emu.emu_wloops(ptr(x), ptr(wl), ctypes.c_int(nb), dims)
+    assert maxdiff(wl, g['wloops']) < 1e-13
+
+
+@pytest.mark.parametrize('key,xk,vk', [('hmc1', 'x', 'v'), ('hmc4', 'x', 'v'), ('hmcw', 'xw', 'vw')])
+def test_trajectory_kernel_sequence(emu, g, key, xk, vk):
+    """merged kicks == the reference's two half kicks, to rounding"""
+    x, v = np.ascontiguousarray(g[xk]), np.ascontiguousarray(g[vk])
+    nb, beta = x.shape[0], float(g['beta'])
+    nlf = int(g['hmcw_nlf']) if key == 'hmcw' else int(key[3:])
+    dims = (ctypes.c_int * 4)(*[int(s) for s in g['shape']])
+    xo, vo, en = np.empty_like(x), np.empty_like(x), np.empty((nb, 4))
+    emu.emu_hmc(ptr(x), ptr(v), ctypes.c_double(beta), ctypes.c_double(float(g[f'{key}_eps'])), ctypes.c_int(nlf),
+                ptr(xo), ptr(vo), ptr(en), ctypes.c_int(nb), dims)
+    assert maxdiff(xo, g[f'{key}_x']) < 1e-13
+    assert maxdiff(vo, g[f'{key}_v']) < 1e-13
+    h0, h1 = en[:, 0] + en[:, 1], en[:, 2] + en[:, 3]
+    assert np.allclose(h0, g[f'{key}_h0'], rtol=1e-12, atol=1e-11)
+    assert np.allclose(h1, g[f'{key}_h1'], rtol=1e-12, atol=1e-11)
+    acc = np.exp(np.minimum(h0 - h1, 0.0))
+    assert maxdiff(acc, g[f'{key}_acc']) < 1e-11
