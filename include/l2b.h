@@ -48,6 +48,9 @@ int l2b_version(void);
 /* number of kernel launches issued by this library on behalf of the calling
  * process since load (bench.py reports it as gpu_launches) */
 uint64_t l2b_launch_count(void);
+/* tuning knobs (process-wide): "su3_force_variant" = launch geometry of the force
+ * kernel, see kForceVariants in csrc/l2b_su3.cu */
+int l2b_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------ */
 /* SU(3)                                                                     */

@@ -57,6 +57,7 @@ _SIGS = {
     'l2b_su3_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
+    'l2b_set_option': [c_char_p, c_int],
     'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_observables': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_force': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
@@ -93,6 +94,10 @@ def last_error() -> str:
 
 def version() -> int:
     return int(_lib.l2b_version())
+
+
+def set_option(key: str, value: int) -> None:
+    call('l2b_set_option', key.encode(), int(value))
 
 
 def launch_count() -> int:

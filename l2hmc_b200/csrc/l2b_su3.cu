@@ -13,6 +13,8 @@
 //   k_reduce_affine               deterministic second reduction stage
 //
 // Reference functions each entry point replaces are listed in include/l2b.h.
+#include <string.h>
+
 #include "l2b_common.cuh"
 #include "l2b_su3_site.cuh"
 
@@ -22,7 +24,6 @@ namespace {
 using T = double;
 using C = double2;
 constexpr int NTL = 128;       // threads (= links) per block of the link-local kernels
-constexpr int FORCE_TS = 32;   // sites per block of k_force (block = FORCE_TS x 4 directions)
 
 // ---------------------------------------------------------------------------
 // shared-memory staging of the interleaved (AoS) layout
@@ -126,10 +127,11 @@ __global__ void __launch_bounds__(NTL) k_soa_to_aos(const C* __restrict__ soa, C
 // ---------------------------------------------------------------------------
 // force (+ kick) on the planar layout.  Block = FORCE_TS consecutive sites x 4
 // directions: the four warps that share a site neighbourhood run together so the
-// 18 neighbour matrices of a link are mostly served by L1.
+// 18 neighbour matrices of a link are mostly served by L1.  (TS = 16 packs two
+// directions into one warp.)
 // ---------------------------------------------------------------------------
-template <int TS, bool KICK>
-__global__ void __launch_bounds__(TS * 4) k_force(const C* __restrict__ U, C* __restrict__ P, Lat lat, double coef,
+template <int TS, int MINB, bool KICK>
+__global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U, C* __restrict__ P, Lat lat, double coef,
                                                   double* __restrict__ part) {
   __shared__ double red[TS * 4 / 32];
   const int b = blockIdx.y;
@@ -473,7 +475,29 @@ __global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t o
 // ---------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------
+// launch geometries of k_force: (sites per block, min resident blocks per SM ->
+// register cap).  Selected with l2b_set_option("su3_force_variant", i); the
+// default is the one measured fastest on B200 (profiles/).
+using ForceFn = void (*)(const C*, C*, Lat, double, double*);
+struct ForceVariant {
+  int ts;
+  ForceFn kick, nokick;
+};
+#define L2B_FV(TS, MINB) {TS, k_force<TS, MINB, true>, k_force<TS, MINB, false>}
+const ForceVariant kForceVariants[] = {
+    L2B_FV(32, 1),   // 0: 128 threads, uncapped registers
+    L2B_FV(32, 3),   // 1: <= 168 registers, 12 warps / SM
+    L2B_FV(32, 4),   // 2: <= 128 registers, 16 warps / SM
+    L2B_FV(64, 2),   // 3: 256 threads, <= 128 registers
+    L2B_FV(32, 5),   // 4: <= 96 registers (spills), 20 warps / SM
+    L2B_FV(64, 1),   // 5: 256 threads, uncapped
+    L2B_FV(16, 8),   // 6: 64 threads (2 directions per warp), <= 128 registers
+};
+constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
+int g_force_variant = 2;
+
 struct Geo {
+  int force_variant;
   Lat lat;
   int nb;
   size_t links_per_chain;   // 4 V
@@ -497,7 +521,9 @@ int make_geo(Geo& g, int nb, const int dims[4], int dtype) {
   g.nb = nb;
   g.links_per_chain = (size_t)4 * V;
   g.field_elems = (size_t)nb * 4 * V * 9;
-  g.nblk_force = (int)((V + FORCE_TS - 1) / FORCE_TS);
+  g.force_variant = g_force_variant;
+  const int fts = kForceVariants[g.force_variant].ts;
+  g.nblk_force = (int)((V + fts - 1) / fts);
   g.nblk_link = (int)((4 * V + NTL - 1) / NTL);
   g.nblk_conv = (int)((V + NTL - 1) / NTL);
   g.nblk_plaq = (int)((V + 127) / 128);
@@ -543,9 +569,9 @@ int launch_s2a(const Geo& g, const C* soa, C* aos, cudaStream_t st) {
   return L2B_OK;
 }
 int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double* part, cudaStream_t st) {
-  dim3 grid(g.nblk_force, g.nb), block(FORCE_TS, 4);
-  if (kick) k_force<FORCE_TS, true><<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
-  else k_force<FORCE_TS, false><<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
+  const ForceVariant& fv = kForceVariants[g.force_variant];
+  dim3 grid(g.nblk_force, g.nb), block(fv.ts, 4);
+  (kick ? fv.kick : fv.nokick)<<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
   L2B_LAUNCHED("k_force");
   return L2B_OK;
 }
@@ -571,6 +597,18 @@ using namespace l2b;
 // C ABI
 // ===========================================================================
 extern "C" {
+
+int l2b_set_option(const char* key, int value) {
+  L2B_REQUIRE(key != nullptr, L2B_ERR_INVALID, "null key");
+  if (strcmp(key, "su3_force_variant") == 0) {
+    L2B_REQUIRE(value >= 0 && value < kNumForceVariants, L2B_ERR_INVALID, "su3_force_variant must be in [0, %d)",
+                kNumForceVariants);
+    g_force_variant = value;
+    return L2B_OK;
+  }
+  set_error("unknown option '%s'", key);
+  return L2B_ERR_INVALID;
+}
 
 size_t l2b_su3_ws_bytes(int nb, const int dims[4], int dtype) {
   Geo g;

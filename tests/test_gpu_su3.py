@@ -186,7 +186,7 @@ def test_rand_momentum_distribution(ops):
     n2 = (np.abs(pn) ** 2).sum((-1, -2))
     assert abs(n2.mean() - 8.0) < 0.05, '<|P|_F^2> = 8 (group.py:125-126 convention)'
     vec = osu3.su3_to_vec(pn)
-    assert abs(vec.mean()) < 0.01 and abs(vec.var() - 1.0) < 0.01, 'the 8 components are N(0,1)'
+    assert abs(vec.mean()) < 0.01 and abs(vec.var() - 2.0) < 0.02, 'X^a = -2 tr[T^a X] are N(0, 2): tr T^aT^b = -1/2'
     assert np.allclose(host(ke), osu3.kinetic_energy(pn), rtol=1e-12, atol=1e-10)
     p2 = ops.su3_rand_momentum(nb, shape, seed=1234, offset=0, device=DEV)
     p3 = ops.su3_rand_momentum(nb, shape, seed=1234, offset=1, device=DEV)
