@@ -24,6 +24,7 @@ namespace {
 using T = double;
 using C = double2;
 constexpr int NTL = 128;       // threads (= links) per block of the link-local kernels
+constexpr int PF_AHEAD_SITES = 16384;  // ~ (148 SMs x 3 blocks x 32 sites) + margin
 
 // ---------------------------------------------------------------------------
 // shared-memory staging of the interleaved (AoS) layout
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(NTL) k_soa_to_aos(const C* __restrict__ soa, C
 // 18 neighbour matrices of a link are mostly served by L1.  (TS = 16 packs two
 // directions into one warp.)
 // ---------------------------------------------------------------------------
-template <int TS, int MINB, bool KICK>
+template <int TS, int MINB, bool KICK, int PF>
 __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U, C* __restrict__ P, Lat lat, double coef,
                                                   double* __restrict__ part) {
   __shared__ double red[TS * 4 / 32];
@@ -141,7 +142,16 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
   double retr = 0.0, p2 = 0.0;
   if (site < lat.V) {
     Mat3<T> g, f;
-    link_times_staples<T, C>(g, U, lat, b, mu, site);
+    if (PF == 2) {
+      // pull this direction's own links / momenta of a block far enough ahead into L2,
+      // so that by the time that block runs its first-touch loads hit L2 instead of HBM
+      const int ahead = site + PF_AHEAD_SITES;
+      if (ahead < lat.V) {
+        soa_prefetch<2>(soa_plane(U, lat, b, mu), lat.V, ahead);
+        if (KICK) soa_prefetch<2>(soa_plane((const C*)P, lat, b, mu), lat.V, ahead);
+      }
+    }
+    link_times_staples<T, C, (PF == 1 ? 1 : 0)>(g, U, lat, b, mu, site);
     retr = re_trace(g);
     project_tah(f, g);
     C* pp = soa_plane(P, lat, b, mu) + site;
@@ -483,7 +493,8 @@ struct ForceVariant {
   int ts;
   ForceFn kick, nokick;
 };
-#define L2B_FV(TS, MINB) {TS, k_force<TS, MINB, true>, k_force<TS, MINB, false>}
+#define L2B_FV(TS, MINB) {TS, k_force<TS, MINB, true, 0>, k_force<TS, MINB, false, 0>}
+#define L2B_FVP(TS, MINB, PF) {TS, k_force<TS, MINB, true, PF>, k_force<TS, MINB, false, PF>}
 const ForceVariant kForceVariants[] = {
     L2B_FV(32, 1),   // 0: 128 threads, uncapped registers
     L2B_FV(32, 3),   // 1: <= 168 registers, 12 warps / SM
@@ -492,9 +503,13 @@ const ForceVariant kForceVariants[] = {
     L2B_FV(32, 5),   // 4: <= 96 registers (spills), 20 warps / SM
     L2B_FV(64, 1),   // 5: 256 threads, uncapped
     L2B_FV(16, 8),   // 6: 64 threads (2 directions per warp), <= 128 registers
+    L2B_FVP(32, 3, 1),  // 7: variant 1 + L1 prefetch of the next direction's operands
+    L2B_FVP(32, 3, 2),  // 8: variant 1 + L2 look-ahead prefetch of own links/momenta
+    L2B_FVP(32, 4, 1),  // 9: variant 2 + L1 prefetch
+    L2B_FVP(32, 4, 2),  // 10: variant 2 + L2 look-ahead
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
-int g_force_variant = 2;
+int g_force_variant = 1;
 
 struct Geo {
   int force_variant;

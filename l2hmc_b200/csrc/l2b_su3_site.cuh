@@ -96,12 +96,31 @@ L2B_HD void soa_store(C* plane, int V, int site, const Mat3<T>& m) {
 // sum_{mu,n} Re tr G = 4 * sum_plaquettes Re tr P  (every plaquette is seen from
 // each of its four links), which gives the Wilson action for free.
 // ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define L2B_PREFETCH_L1(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define L2B_PREFETCH_L2(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#else
+#define L2B_PREFETCH_L1(p) ((void)(p))
+#define L2B_PREFETCH_L2(p) ((void)(p))
+#endif
+
+template <int LEVEL, typename C>
+L2B_HD void soa_prefetch(const C* plane, int V, int site) {
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    if (LEVEL == 1) L2B_PREFETCH_L1(plane + (size_t)e * V + site);
+    else L2B_PREFETCH_L2(plane + (size_t)e * V + site);
+  }
+}
+
 L2B_HD int sel4(int a0, int a1, int a2, int a3, int i) {
   // register-only replacement for a[i] with a runtime i (no local-memory array)
   return (i == 0) ? a0 : (i == 1) ? a1 : (i == 2) ? a2 : a3;
 }
 
-template <typename T, typename C>
+// PF = 1: while the staples of direction k are being multiplied, prefetch (to L1)
+// the six matrices of direction k+1 -- latency hiding that costs no registers.
+template <typename T, typename C, int PF = 0>
 L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int mu, int site) {
   const int V = l.V;
   // coordinates, and for every direction d: site offset of a forward / backward hop
@@ -133,6 +152,17 @@ L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int 
     const int n_pnu = site + fnu;
     const int n_mnu = site + bnu;
     const int n_pmu_mnu = n_pmu + bnu;           // the mu hop does not change the nu coordinate
+    if (PF == 1 && k < 3) {
+      const int nu2 = (mu + k + 1) & 3;
+      const C* pnu2 = chain + (size_t)nu2 * plane_sz;
+      const int f2n = sel4(f0, f1, f2, f3, nu2), b2n = sel4(b0, b1, b2, b3, nu2);
+      soa_prefetch<1>(pnu2, V, n_pmu);
+      soa_prefetch<1>(pmu, V, site + f2n);
+      soa_prefetch<1>(pnu2, V, site);
+      soa_prefetch<1>(pnu2, V, n_pmu + b2n);
+      soa_prefetch<1>(pmu, V, site + b2n);
+      soa_prefetch<1>(pnu2, V, site + b2n);
+    }
     // forward staple
     soa_load(x, pnu, V, n_pmu);                  // U_nu(n+mu)
     soa_load(y, pmu, V, n_pnu);                  // U_mu(n+nu)

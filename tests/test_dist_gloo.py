@@ -1,0 +1,70 @@
+"""CPU tier: world_size-2 `gloo` test of the N>1 host logic (chain sharding,
+observable gather, flat gradient all-reduce).  No GPU kernels are involved."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from l2hmc_b200 import dist as l2d
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (1, 7, 64, 512, 513):
+        for world in (1, 2, 3, 8):
+            spans = [l2d.shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        l2d.shard_bounds(8, 2, 2)
+    assert l2d.rank_seed(9992, 1, 1) == 9992 * 4
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, nchains, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = l2d.init('gloo')
+    assert (r, w) == (rank, world)
+    full = torch.arange(nchains * 3, dtype=torch.float64).reshape(nchains, 3)
+    mine = l2d.shard_chains(full, rank, world)
+    # "observable" computed shard-locally, gathered back in global chain order
+    got = l2d.gather_chains(mine.sum(1), nchains)
+    ok_gather = torch.equal(got, full.sum(1))
+    # gradient all-reduce: mean over ranks, unused parameter skipped
+    a = torch.nn.Parameter(torch.zeros(5))
+    b = torch.nn.Parameter(torch.zeros(2, 2))
+    unused = torch.nn.Parameter(torch.zeros(3))
+    a.grad = torch.full((5,), float(rank + 1))
+    b.grad = torch.full((2, 2), float(10 * (rank + 1)))
+    n = l2d.allreduce_mean_grads([a, unused, b])
+    mean = sum(range(1, world + 1)) / world
+    ok_grad = (n == 9 and torch.allclose(a.grad, torch.full((5,), mean))
+               and torch.allclose(b.grad, torch.full((2, 2), 10 * mean)) and unused.grad is None)
+    q.put((rank, bool(ok_gather), bool(ok_grad)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('nchains', [8, 7])
+def test_world2_gloo(nchains):
+    world, port = 2, _free_port()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nchains, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, True), (1, True, True)]
