@@ -114,16 +114,18 @@ class ClockSampler:
 # ---------------------------------------------------------------------------
 # reference / cpu_baseline arm
 # ---------------------------------------------------------------------------
-def reference_sample(workload: str):
-    """bounded sample of the workload for the CPU arm: same lattice, dtype and
-    integrator, fewer chains and leapfrog steps (cost is linear in both)."""
+def reference_sample(workload: str, nsteps: int):
+    """bounded sample of the workload for the CPU arm: same lattice, dtype,
+    step size and integrator, fewer chains (cost is linear in chains) and, when
+    many steps are requested, fewer leapfrog steps per trajectory, so that the
+    whole run is ~80 chain-leapfrog-steps of 16^4 (~2 min on 8 cores)."""
     group, lattice, nb, nlf, dtype, beta = WORKLOADS[workload]
     if group == 'SU3':
         v = 1
         for s in lattice:
             v *= s
         nb_s = max(1, min(nb, 65536 // v))         # 16^4 -> 1 chain, 8^4 -> 16 chains
-        nlf_s = 2
+        nlf_s = max(1, min(nlf, 80 // max(1, nsteps)))
     else:
         nb_s, nlf_s = min(nb, 512), nlf
     return group, lattice, nb_s, nlf_s, dtype, beta
@@ -135,7 +137,8 @@ def run_reference_steps(workload: str, steps: int, warmup: int):
     Falls back to the numpy oracle port when oracle/_ref did not travel."""
     import numpy as np
     import torch
-    group, lattice, nb, nlf, dtype, beta = reference_sample(workload)
+    group, lattice, nb, nlf, dtype, beta = reference_sample(workload, steps + warmup)
+    assert not torch.cuda.is_available(), 'the CPU arm must not see a GPU (the reference moves itself to CUDA)'
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     eps = 1.0 / WORKLOADS[workload][3]
@@ -190,6 +193,9 @@ def main_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    # The reference moves itself to CUDA whenever torch sees a device
+    # (l2hmc/__init__.py:45-51, dynamics.py:194-200); this arm times its CPU path.
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''
     base, ms = run_reference_steps(args.workload, args.steps, args.warmup)
     group, lattice, nb, nlf, dtype, beta = WORKLOADS[args.workload]
     line = {
@@ -324,7 +330,7 @@ def main_ours(args):
     if rank == 0:
         cpu_base = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu_base, _ = run_reference_steps(args.workload, 3, 1)
+            cpu_base = cpu_baseline_subprocess(args.workload)
         gb = 864.0 if su3 else 24.0
         line = {
             'metric': METRIC, 'value': value, 'unit': 'link-updates/s', 'n_gpus': world, 'steps': args.steps,
@@ -346,6 +352,21 @@ def main_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_subprocess(workload: str):
+    """the reference's CPU path, in a child process that cannot see the GPU"""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1')
+    for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS'):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--workload', workload,
+                            '--steps', '1', '--warmup', '1'], env=env, capture_output=True, text=True, timeout=900)
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1]
+        return json.loads(line)['cpu_baseline']
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU result
+        return {'value': None, 'unit': 'link-updates/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                'sample': f'failed: {type(e).__name__}: {e}'}
 
 
 def su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, steps, peak, peak_kind, ms_traj):
