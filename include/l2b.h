@@ -49,7 +49,8 @@ int l2b_version(void);
  * process since load (bench.py reports it as gpu_launches) */
 uint64_t l2b_launch_count(void);
 /* tuning knobs (process-wide): "su3_force_variant" = launch geometry of the force
- * kernel, see kForceVariants in csrc/l2b_su3.cu */
+ * kernel, see kForceVariants in csrc/l2b_su3.cu; "su3_fuse_drift" = 0/1, run the drift as its
+ * own kernel (6 transfers per step) or fused into the force kernel (4) */
 int l2b_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------ */
@@ -148,6 +149,13 @@ int l2b_su3_force_kick_planar(const void* u_planar, void* p_planar, double beta,
                               size_t ws_bytes, void* stream);
 int l2b_su3_drift_planar(void* u_planar, const void* p_planar, double eps, int nb, const int dims[4],
                          int dtype, void* stream);
+/* one whole leapfrog step in ONE kernel (what l2b_su3_hmc_trajectory runs):
+ *   P <- P - eps_kick (beta/3) TAH(U A);   u_out <- exp(eps_drift P) u_in
+ * u_out must not alias u_in (other links still read their old neighbours):
+ * 4 field transfers per step instead of 6.  sums_or_null as above.            */
+int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, void* u_out_planar, double beta,
+                                    double eps_kick, double eps_drift, double* sums_or_null, int nb,
+                                    const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* U(1), x[nb, 2, T, X] real angles                                          */

@@ -56,6 +56,7 @@ _SIGS = {
     'l2b_su3_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
     'l2b_set_option': [c_char_p, c_int],
     'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],

@@ -13,6 +13,7 @@
 //   k_reduce_affine               deterministic second reduction stage
 //
 // Reference functions each entry point replaces are listed in include/l2b.h.
+#include <stdlib.h>
 #include <string.h>
 
 #include "l2b_common.cuh"
@@ -131,13 +132,35 @@ __global__ void __launch_bounds__(NTL) k_soa_to_aos(const C* __restrict__ soa, C
 // 18 neighbour matrices of a link are mostly served by L1.  (TS = 16 packs two
 // directions into one warp.)
 // ---------------------------------------------------------------------------
-template <int TS, int MINB, bool KICK, int PF>
+// Brick tiling: the TS sites of a block form a compact 4-D brick ((1,2,2,8) for 32 sites,
+// (2,2,2,8) for 64) instead of TS consecutive sites (two or four z-rows).  Each z-run of 8
+// sites is still one aligned 128-byte segment per matrix entry, so coalescing is unchanged,
+// but the brick's surface is smaller: the distinct neighbour matrices a block has to pull
+// from L2 drop from 6.4 per link to 5.5 (32 sites) / 4.3 (64 sites).
+template <int TS>
+__device__ __forceinline__ int brick_site(const Lat& lat, int blk, int tx) {
+  constexpr int BT = (TS == 64) ? 2 : 1;
+  const int nz = lat.L[3] >> 3, ny = lat.L[2] >> 1, nx = lat.L[1] >> 1;
+  int r = blk;
+  const int iz = r % nz; r /= nz;
+  const int iy = r % ny; r /= ny;
+  const int ix = r % nx; r /= nx;
+  const int it = r;
+  const int z = (iz << 3) + (tx & 7);
+  const int y = (iy << 1) + ((tx >> 3) & 1);
+  const int x = (ix << 1) + ((tx >> 4) & 1);
+  const int t = it * BT + ((TS == 64) ? (tx >> 5) : 0);
+  return ((t * lat.L[1] + x) * lat.L[2] + y) * lat.L[3] + z;
+}
+
+template <int TS, int MINB, bool KICK, int PF, bool DRIFT, bool BRICK = false>
 __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U, C* __restrict__ P, Lat lat, double coef,
-                                                  double* __restrict__ part) {
+                                                  double* __restrict__ part, C* __restrict__ Uout,
+                                                  double eps_drift) {
   __shared__ double red[TS * 4 / 32];
   const int b = blockIdx.y;
   const int mu = threadIdx.y;
-  const int site = blockIdx.x * TS + threadIdx.x;
+  const int site = BRICK ? brick_site<TS>(lat, blockIdx.x, threadIdx.x) : blockIdx.x * TS + threadIdx.x;
   const int tid = threadIdx.y * TS + threadIdx.x;
   double retr = 0.0, p2 = 0.0;
   if (site < lat.V) {
@@ -160,7 +183,156 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
     for (int e = 0; e < 9; ++e) {
       C v;
       if (KICK) {
-        v = pp[e * V];
+        v = __ldcs(pp + e * V);          // momenta are touched once per launch: keep them out of
+        v.x = fma(-coef, f.re[e], v.x);  // the way of the link matrices in L1/L2 (evict-first)
+        v.y = fma(-coef, f.im[e], v.y);
+        p2 = fma(v.x, v.x, p2);
+        p2 = fma(v.y, v.y, p2);
+      } else {
+        v.x = coef * f.re[e];
+        v.y = coef * f.im[e];
+      }
+      __stcs(pp + e * V, v);
+      if (DRIFT) { f.re[e] = eps_drift * v.x; f.im[e] = eps_drift * v.y; }   // f <- eps * P_new
+    }
+    if (KICK) p2 -= 8.0;   // per link (|P|_F^2 - 8), group.py:125-126
+    if (DRIFT) {
+      // fused drift into the OTHER link buffer: U'(mu,n) = exp(eps P_new) U(mu,n).  Neighbours of
+      // other threads keep reading the old links from `U`, so no grid-wide sync is needed and a
+      // leapfrog step costs 4 field transfers (r U, r P, w P, w U') instead of 6.
+      Mat3<T> ex, w, un;
+      soa_load(w, soa_plane(U, lat, b, mu), lat.V, site);
+      mat_exp(ex, f);
+      mat_mul<false, false, false>(un, ex, w);
+      soa_store(soa_plane(Uout, lat, b, mu), lat.V, site, un);
+    }
+  }
+  if (part != nullptr) {
+    retr = block_sum<TS * 4>(retr, red, tid);
+    p2 = block_sum<TS * 4>(p2, red, tid);
+    if (tid == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = retr;
+      o[1] = p2;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// k_force_async: same arithmetic as k_force, but the 18 neighbour matrices of a
+// link travel global -> shared memory with cp.async (LDGSTS) through a per-thread
+// ring of R slots, issued R-1 operands ahead of their use.  In-flight loads then
+// live in the otherwise idle shared memory instead of in registers, which is what
+// caps k_force (its stalls are ~65 % long-scoreboard at 12 warps/SM).  Every
+// thread copies exactly the 16-byte words it will read itself, so cp.async
+// wait_group is the only synchronisation needed; slot layout [slot][e][thread]
+// keeps both the asynchronous writes and the LDS.128 reads conflict free.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <int R, int MINB, bool KICK>
+__global__ void __launch_bounds__(128, MINB) k_force_async(const C* __restrict__ U, C* __restrict__ P, Lat lat,
+                                                           double coef, double* __restrict__ part, C*, double) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ double red[4];
+  C* ring = reinterpret_cast<C*>(smraw);          // [R][9][128]
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  int site = blockIdx.x * 32 + threadIdx.x;
+  const bool live = site < lat.V;
+  if (!live) site = lat.V - 1;                    // keep the pipeline uniform; results discarded
+  const int V = lat.V;
+  int r = site;
+  const int c3 = r % lat.L[3]; r /= lat.L[3];
+  const int c2 = r % lat.L[2]; r /= lat.L[2];
+  const int c1 = r % lat.L[1]; r /= lat.L[1];
+  const int c0 = r;
+  const int f0 = (c0 == lat.L[0] - 1) ? -(lat.L[0] - 1) * lat.stride[0] : lat.stride[0];
+  const int f1 = (c1 == lat.L[1] - 1) ? -(lat.L[1] - 1) * lat.stride[1] : lat.stride[1];
+  const int f2 = (c2 == lat.L[2] - 1) ? -(lat.L[2] - 1) * lat.stride[2] : lat.stride[2];
+  const int f3 = (c3 == lat.L[3] - 1) ? -(lat.L[3] - 1) : 1;
+  const int b0 = (c0 == 0) ? (lat.L[0] - 1) * lat.stride[0] : -lat.stride[0];
+  const int b1 = (c1 == 0) ? (lat.L[1] - 1) * lat.stride[1] : -lat.stride[1];
+  const int b2 = (c2 == 0) ? (lat.L[2] - 1) * lat.stride[2] : -lat.stride[2];
+  const int b3 = (c3 == 0) ? (lat.L[3] - 1) : -1;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int n_pmu = site + sel4(f0, f1, f2, f3, mu);
+
+  // operand j = 6*(k-1) + w, k = 1..3 (nu = mu + k), w: 0 X1=U_nu(n+mu) 1 Y1=U_mu(n+nu) 2 Z1=U_nu(n)
+  //                                                     3 X2=U_nu(n+mu-nu) 4 Y2=U_mu(n-nu) 5 Z2=U_nu(n-nu); j = 18: U_mu(n)
+  auto issue = [&](int j) {
+    const C* src;
+    if (j >= 18) {
+      src = pmu + site;
+    } else {
+      const int k = j / 6 + 1, w = j % 6;
+      const int nu = (mu + k) & 3;
+      const C* pnu = chain + (size_t)nu * plane_sz;
+      const int fnu = sel4(f0, f1, f2, f3, nu), bnu = sel4(b0, b1, b2, b3, nu);
+      src = (w == 0) ? pnu + n_pmu : (w == 1) ? pmu + site + fnu : (w == 2) ? pnu + site
+          : (w == 3) ? pnu + n_pmu + bnu : (w == 4) ? pmu + site + bnu : pnu + site + bnu;
+    }
+    C* dst = ring + ((size_t)(j % R) * 9) * 128 + tid;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) cp_async16(dst + e * 128, src + (size_t)e * V);
+  };
+  auto take = [&](Mat3<T>& m, int j) {
+    const C* src = ring + ((size_t)(j % R) * 9) * 128 + tid;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { const C v = src[e * 128]; m.re[e] = v.x; m.im[e] = v.y; }
+  };
+
+#pragma unroll
+  for (int j = 0; j < R - 1; ++j) { issue(j); cp_async_commit(); }
+  Mat3<T> a, x, y, m;
+  mat_zero(a);
+#pragma unroll
+  for (int j = 0; j < 19; ++j) {
+    if (j + R - 1 < 19) issue(j + R - 1);
+    cp_async_commit();                           // one group per step (possibly empty) keeps the count uniform
+    cp_async_wait<R - 1>();                      // operand j has landed
+    const int w = j % 6;
+    if (j == 18) {
+      take(x, j);
+    } else if (w == 0 || w == 3) {
+      take(x, j);
+    } else if (w == 1) {
+      take(y, j);
+      mat_mul<false, true, false>(m, x, y);      // U_nu(n+mu) U_mu(n+nu)^+
+    } else if (w == 4) {
+      take(y, j);
+      mat_mul<true, true, false>(m, x, y);       // U_nu(n+mu-nu)^+ U_mu(n-nu)^+
+    } else if (w == 2) {
+      take(x, j);
+      mat_mul<false, true, true>(a, m, x);       // += m U_nu(n)^+
+    } else {
+      take(x, j);
+      mat_mul<false, false, true>(a, m, x);      // += m U_nu(n-nu)
+    }
+  }
+  Mat3<T> g, f;
+  mat_mul<false, false, false>(g, x, a);
+  double retr = 0.0, p2 = 0.0;
+  if (live) {
+    retr = re_trace(g);
+    project_tah(f, g);
+    C* pp = soa_plane(P, lat, b, mu) + site;
+    const size_t Vs = lat.V;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      C v;
+      if (KICK) {
+        v = pp[e * Vs];
         v.x = fma(-coef, f.re[e], v.x);
         v.y = fma(-coef, f.im[e], v.y);
         p2 = fma(v.x, v.x, p2);
@@ -169,13 +341,13 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
         v.x = coef * f.re[e];
         v.y = coef * f.im[e];
       }
-      pp[e * V] = v;
+      pp[e * Vs] = v;
     }
-    if (KICK) p2 -= 8.0;   // per link (|P|_F^2 - 8), group.py:125-126
+    if (KICK) p2 -= 8.0;
   }
   if (part != nullptr) {
-    retr = block_sum<TS * 4>(retr, red, tid);
-    p2 = block_sum<TS * 4>(p2, red, tid);
+    retr = block_sum<128>(retr, red, tid);
+    p2 = block_sum<128>(p2, red, tid);
     if (tid == 0) {
       double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
       o[0] = retr;
@@ -488,13 +660,21 @@ __global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t o
 // launch geometries of k_force: (sites per block, min resident blocks per SM ->
 // register cap).  Selected with l2b_set_option("su3_force_variant", i); the
 // default is the one measured fastest on B200 (profiles/).
-using ForceFn = void (*)(const C*, C*, Lat, double, double*);
+using ForceFn = void (*)(const C*, C*, Lat, double, double*, C*, double);
 struct ForceVariant {
   int ts;
   ForceFn kick, nokick;
+  int smem;   // dynamic shared memory (cp.async operand ring), 0 for the register-only kernel
+  ForceFn kick_drift;   // kick + fused drift into the second link buffer (nullptr: not available)
+  int brick_fallback;   // >= 0: brick-tiled variant; use this linear variant when the lattice does not tile
 };
-#define L2B_FV(TS, MINB) {TS, k_force<TS, MINB, true, 0>, k_force<TS, MINB, false, 0>}
-#define L2B_FVP(TS, MINB, PF) {TS, k_force<TS, MINB, true, PF>, k_force<TS, MINB, false, PF>}
+#define L2B_FV(TS, MINB) L2B_FVP(TS, MINB, 0)
+#define L2B_FVP(TS, MINB, PF) \
+  {TS, k_force<TS, MINB, true, PF, false>, k_force<TS, MINB, false, PF, false>, 0, k_force<TS, MINB, true, PF, true>, -1}
+#define L2B_FVA(R, MINB) {32, k_force_async<R, MINB, true>, k_force_async<R, MINB, false>, R * 9 * 128 * 16, nullptr, -1}
+#define L2B_FVB(TS, MINB, PF, FALLBACK)                                                              \
+  {TS, k_force<TS, MINB, true, PF, false, true>, k_force<TS, MINB, false, PF, false, true>, 0,       \
+   k_force<TS, MINB, true, PF, true, true>, FALLBACK}
 const ForceVariant kForceVariants[] = {
     L2B_FV(32, 1),   // 0: 128 threads, uncapped registers
     L2B_FV(32, 3),   // 1: <= 168 registers, 12 warps / SM
@@ -507,9 +687,21 @@ const ForceVariant kForceVariants[] = {
     L2B_FVP(32, 3, 2),  // 8: variant 1 + L2 look-ahead prefetch of own links/momenta
     L2B_FVP(32, 4, 1),  // 9: variant 2 + L1 prefetch
     L2B_FVP(32, 4, 2),  // 10: variant 2 + L2 look-ahead
+    L2B_FVA(4, 3),      // 11: cp.async ring of 4 operands, 12 warps / SM (216 KB smem / SM)
+    L2B_FVA(3, 4),      // 12: ring of 3, 16 warps / SM
+    L2B_FVA(6, 2),      // 13: ring of 6, 8 warps / SM
+    L2B_FVA(3, 3),      // 14: ring of 3, 12 warps / SM
+    L2B_FVA(2, 4),      // 15: ring of 2, 16 warps / SM
+    L2B_FVB(32, 3, 0, 1),   // 16: brick (1,2,2,8), <= 168 registers
+    L2B_FVB(32, 4, 0, 2),   // 17: brick (1,2,2,8), <= 128 registers
+    L2B_FVB(64, 1, 0, 1),   // 18: brick (2,2,2,8), 256 threads, uncapped registers
+    L2B_FVB(64, 2, 0, 2),   // 19: brick (2,2,2,8), 256 threads, <= 128 registers
+    L2B_FVB(32, 3, 2, 8),   // 20: brick (1,2,2,8) + L2 look-ahead
+    L2B_FVB(64, 2, 2, 10),  // 21: brick (2,2,2,8) + L2 look-ahead
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
-int g_force_variant = 1;
+int g_force_variant = 8;
+int g_fuse_drift = 1;
 
 struct Geo {
   int force_variant;
@@ -536,7 +728,16 @@ int make_geo(Geo& g, int nb, const int dims[4], int dtype) {
   g.nb = nb;
   g.links_per_chain = (size_t)4 * V;
   g.field_elems = (size_t)nb * 4 * V * 9;
+  if (const char* ev = getenv("L2B_SU3_FORCE_VARIANT")) {
+    const int v = atoi(ev);
+    if (v >= 0 && v < kNumForceVariants) g_force_variant = v;
+  }
   g.force_variant = g_force_variant;
+  {
+    const ForceVariant& fv0 = kForceVariants[g.force_variant];
+    const bool tiles = (dims[3] % 8 == 0) && (dims[2] % 2 == 0) && (dims[1] % 2 == 0) && (fv0.ts != 64 || dims[0] % 2 == 0);
+    if (fv0.brick_fallback >= 0 && !tiles) g.force_variant = fv0.brick_fallback;
+  }
   const int fts = kForceVariants[g.force_variant].ts;
   g.nblk_force = (int)((V + fts - 1) / fts);
   g.nblk_link = (int)((4 * V + NTL - 1) / NTL);
@@ -550,12 +751,13 @@ int make_geo(Geo& g, int nb, const int dims[4], int dtype) {
 }
 
 size_t ws_bytes_of(const Geo& g) {
-  return 2 * align_up(g.field_elems * sizeof(C), 256) + align_up(g.part_elems * sizeof(double), 256);
+  return 3 * align_up(g.field_elems * sizeof(C), 256) + align_up(g.part_elems * sizeof(double), 256);
 }
 
 struct Ws {
   C* f0;
   C* f1;
+  C* f2;
   double* part;
 };
 
@@ -566,6 +768,7 @@ int carve(Ws& w, const Geo& g, void* ws, size_t ws_bytes) {
   char* p = (char*)ws;
   w.f0 = (C*)p; p += align_up(g.field_elems * sizeof(C), 256);
   w.f1 = (C*)p; p += align_up(g.field_elems * sizeof(C), 256);
+  w.f2 = (C*)p; p += align_up(g.field_elems * sizeof(C), 256);
   w.part = (double*)p;
   return L2B_OK;
 }
@@ -583,10 +786,15 @@ int launch_s2a(const Geo& g, const C* soa, C* aos, cudaStream_t st) {
   L2B_LAUNCHED("k_soa_to_aos");
   return L2B_OK;
 }
-int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double* part, cudaStream_t st) {
+int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double* part, cudaStream_t st,
+                 C* Uout = nullptr, double eps_drift = 0.0) {
   const ForceVariant& fv = kForceVariants[g.force_variant];
   dim3 grid(g.nblk_force, g.nb), block(fv.ts, 4);
-  (kick ? fv.kick : fv.nokick)<<<grid, block, 0, st>>>(U, P, g.lat, coef, part);
+  ForceFn fn = Uout ? fv.kick_drift : (kick ? fv.kick : fv.nokick);
+  L2B_REQUIRE(fn != nullptr, L2B_ERR_UNSUPPORTED, "force variant %d has no fused kick+drift kernel", g.force_variant);
+  if (fv.smem > 48 * 1024)
+    L2B_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv.smem));
+  fn<<<grid, block, fv.smem, st>>>(U, P, g.lat, coef, part, Uout, eps_drift);
   L2B_LAUNCHED("k_force");
   return L2B_OK;
 }
@@ -619,6 +827,10 @@ int l2b_set_option(const char* key, int value) {
     L2B_REQUIRE(value >= 0 && value < kNumForceVariants, L2B_ERR_INVALID, "su3_force_variant must be in [0, %d)",
                 kNumForceVariants);
     g_force_variant = value;
+    return L2B_OK;
+  }
+  if (strcmp(key, "su3_fuse_drift") == 0) {
+    g_fuse_drift = value != 0;
     return L2B_OK;
   }
   set_error("unknown option '%s'", key);
@@ -845,6 +1057,29 @@ int l2b_su3_force_kick_planar(const void* u_planar, void* p_planar, double beta,
   return L2B_OK;
 }
 
+int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, void* u_out_planar, double beta,
+                                    double eps_kick, double eps_drift, double* sums_or_null, int nb,
+                                    const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(u_in_planar && p_planar && u_out_planar, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(u_in_planar != u_out_planar, L2B_ERR_INVALID, "u_out must not alias u_in");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* part = nullptr;
+  if (sums_or_null) {
+    L2B_TRY(carve(w, g, ws, ws_bytes));
+    part = w.part;
+  }
+  L2B_TRY(launch_force(g, (const C*)u_in_planar, (C*)p_planar, true, eps_kick * beta / 3.0, part, st,
+                       (C*)u_out_planar, eps_drift));
+  if (sums_or_null) {
+    L2B_TRY(launch_reduce(part, g.nblk_force, 2, 0, 0.25, 0.0, sums_or_null, 2, 0, nb, st));
+    L2B_TRY(launch_reduce(part, g.nblk_force, 2, 1, 1.0, 0.0, sums_or_null, 2, 1, nb, st));
+  }
+  return L2B_OK;
+}
+
 int l2b_su3_drift_planar(void* u_planar, const void* p_planar, double eps, int nb, const int dims[4], int dtype,
                          void* stream) {
   Geo g;
@@ -874,15 +1109,30 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
   L2B_TRY(launch_a2s(g, (const C*)x, U, nullptr, st));
   L2B_TRY(launch_a2s(g, (const C*)v, P, w.part, st));
   L2B_TRY(launch_reduce(w.part, g.nblk_conv * 4, 1, 0, 0.5, ke_shift, energies, 4, 0, nb, st));
-  // first half kick; S0 rides on the force evaluation
-  L2B_TRY(launch_force(g, U, P, true, 0.5 * eps * b3, w.part, st));
-  L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 1, nb, st));
-  const dim3 dgrid((g.lat.V + 127) / 128, nb * 4);
-  for (int k = 1; k <= nlf; ++k) {
-    k_drift<<<dgrid, 128, 0, st>>>(U, P, g.lat.V, eps);
-    L2B_LAUNCHED("k_drift");
-    const bool last = (k == nlf);
-    L2B_TRY(launch_force(g, U, P, true, (last ? 0.5 : 1.0) * eps * b3, last ? w.part : nullptr, st));
+  const bool fused = g_fuse_drift && kForceVariants[g.force_variant].kick_drift != nullptr;
+  if (fused) {
+    // kick + drift fused, links ping-pong between two planar buffers:
+    //   K(eps/2) K(eps) ... K(eps)   [nlf launches, each: P -= c F(U); U' = exp(eps P) U]   +   final half kick
+    C* Ua = U;
+    C* Ub = w.f2;
+    for (int k = 0; k < nlf; ++k) {
+      L2B_TRY(launch_force(g, Ua, P, true, (k == 0 ? 0.5 : 1.0) * eps * b3, k == 0 ? w.part : nullptr, st, Ub, eps));
+      if (k == 0) L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 1, nb, st));
+      C* t = Ua; Ua = Ub; Ub = t;
+    }
+    L2B_TRY(launch_force(g, Ua, P, true, 0.5 * eps * b3, w.part, st));
+    U = Ua;
+  } else {
+    // first half kick; S0 rides on the force evaluation
+    L2B_TRY(launch_force(g, U, P, true, 0.5 * eps * b3, w.part, st));
+    L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 1, nb, st));
+    const dim3 dgrid((g.lat.V + 127) / 128, nb * 4);
+    for (int k = 1; k <= nlf; ++k) {
+      k_drift<<<dgrid, 128, 0, st>>>(U, P, g.lat.V, eps);
+      L2B_LAUNCHED("k_drift");
+      const bool last = (k == nlf);
+      L2B_TRY(launch_force(g, U, P, true, (last ? 0.5 : 1.0) * eps * b3, last ? w.part : nullptr, st));
+    }
   }
   L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 1, 0.5, ke_shift, energies, 4, 2, nb, st));
   L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 3, nb, st));

@@ -1,4 +1,4 @@
-"""Short driver for ncu captures: 2 HMC trajectories of the bench workload
+"""Short driver for ncu captures: N HMC trajectories of the bench workload
 (SU(3) 16^4, 64 chains, N_LF 10 unless overridden).  Not a benchmark: numbers
 printed under a profiler are never reported."""
 import sys

@@ -12,7 +12,7 @@ from l2hmc_b200 import ops, _lib  # noqa: E402
 
 dev = 'cuda:0'
 cases = [(16, 64), (8, 256)]
-variants = [int(a) for a in sys.argv[1:]] or list(range(11))
+variants = [int(a) for a in sys.argv[1:]] or list(range(22))
 out = []
 for L, nb in cases:
     shape = [L] * 4
@@ -41,15 +41,22 @@ for L, nb in cases:
         b.record()
         torch.cuda.synchronize()
         ms_f = a.elapsed_time(b) / 10
-        for _ in range(2):
-            ops.su3_hmc_trajectory(x, v, 6.0, 0.1, 10)
-        a.record()
-        for _ in range(3):
-            ops.su3_hmc_trajectory(x, v, 6.0, 0.1, 10)
-        b.record()
-        torch.cuda.synchronize()
-        ms_t = a.elapsed_time(b) / 3
+        ms_t = {}
+        for fuse in (0, 1):
+            _lib.set_option('su3_fuse_drift', fuse)
+            try:
+                for _ in range(2):
+                    ops.su3_hmc_trajectory(x, v, 6.0, 0.1, 10)
+                a.record()
+                for _ in range(3):
+                    ops.su3_hmc_trajectory(x, v, 6.0, 0.1, 10)
+                b.record()
+                torch.cuda.synchronize()
+                ms_t[fuse] = a.elapsed_time(b) / 3
+            except Exception:
+                ms_t[fuse] = float('nan')
         r = dict(L=L, nb=nb, variant=var, force_ms=round(ms_f, 4), force_GBps=round(432 * links / ms_f / 1e6, 1),
-                 traj_ms=round(ms_t, 3), link_updates_per_s=round(links * 10 / ms_t * 1e3 / 1e9, 4))
+                 traj_ms=round(ms_t[0], 3), traj_fused_ms=round(ms_t[1], 3),
+                 glups_fused=round(links * 10 / ms_t[1] * 1e3 / 1e9, 4))
         print(json.dumps(r), flush=True)
         out.append(r)
