@@ -193,6 +193,24 @@ int l2b_u1_kinetic(const void* v, void* ke, int nb, int xdim, int dtype, void* s
 /* U1Phase.compat_proj (group.py:130-131): ((x + pi) mod 2 pi) - pi, n elements */
 int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stream);
 
+/* --- adjoints (L2HMC training; the reference relies on autograd for these) --- */
+/* adjoint of l2b_u1_wilson_loops: gx[nb,2,T,X] from gw[nb,T,X] */
+int l2b_u1_wilson_loops_bwd(const void* gw, void* gx, int nb, int T, int X, int dtype, void* stream);
+/* adjoint of l2b_u1_force = Hessian-vector product of the action (the reference
+ * differentiates through grad_action with create_graph=True, lattice.py:106,113-116) */
+int l2b_u1_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, int T, int X, int dtype,
+                     void* stream);
+/* adjoints of l2b_u1_vupdate / l2b_u1_xupdate: gradients w.r.t. every input
+ * (gs/gt/gq may be NULL) and geps[nb] = per-chain derivative w.r.t. eps */
+int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                       int sign, const void* gv_out, const void* glogdet, void* gv, void* gforce, void* gs, void* gt,
+                       void* gq, void* geps, int nb, int xdim, int dtype, void* stream);
+int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
+                       double eps, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
+                       void* gs, void* gt, void* gq, void* geps, int nb, int xdim, int dtype, void* stream);
+/* out[b,:] = scale[b] * in[b,:]: adjoint of action (in = force) and of kinetic energy (in = v) */
+int l2b_rowscale(const void* in, const void* scale, void* out, int nb, int xdim, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* Metropolis-Hastings accept / reject mix (dynamics.py:632-702,1065-1087)   */
 /* ------------------------------------------------------------------------ */

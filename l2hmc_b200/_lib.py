@@ -67,6 +67,11 @@ _SIGS = {
     'l2b_u1_xupdate': [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
     'l2b_u1_kinetic': [_P, _P, c_int, c_int, c_int, _P],
     'l2b_u1_compat_proj': [_P, _P, c_size_t, c_int, _P],
+    'l2b_u1_wilson_loops_bwd': [_P, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_force_bwd': [_P, c_double, _P, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_xupdate_bwd': [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_rowscale': [_P, _P, _P, c_int, c_int, c_int, _P],
     'l2b_accept_mix': [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_size_t), c_int, _P, c_int, _P],
 }
 _RES = {

@@ -269,6 +269,180 @@ __global__ void __launch_bounds__(256) k_u1_wrap(const T* __restrict__ x, T* __r
   if (i < n) out[i] = wrap_pi(x[i]);
 }
 
+// ---------------------------------------------------------------------------
+// backward kernels of the U(1) L2HMC path (training).  The reference gets these
+// from autograd (force with create_graph=True, lattice/u1/pytorch/lattice.py:102-117;
+// updates dynamics.py:1266-1297,1398-1467); here they are written out.
+// ---------------------------------------------------------------------------
+// adjoint of the plaquette-angle map: gx0 = gw(t,x) - gw(t,x-1), gx1 = gw(t-1,x) - gw(t,x)
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_wloops_bwd(const T* __restrict__ gw, T* __restrict__ gx, int Tt, int X) {
+  const int N = Tt * X;
+  const T* g = gw + (size_t)blockIdx.y * N;
+  T* g0 = gx + (size_t)blockIdx.y * 2 * N;
+  T* g1 = g0 + N;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const int t = i / X, xx = i % X;
+  const int tm = (t == 0) ? Tt - 1 : t - 1;
+  const int xm = (xx == 0) ? X - 1 : xx - 1;
+  const T c = g[i];
+  g0[i] = c - g[t * X + xm];
+  g1[i] = g[tm * X + xx] - c;
+}
+
+// d<gF, F(x)>/dx with F = beta (sin w - sin w(x-1), -sin w + sin w(t-1)):
+//   gw(a) = beta cos w(a) [gF0(a) - gF0(a+x) - gF1(a) + gF1(a+t)], then the adjoint above.
+template <typename T>
+__device__ __forceinline__ T u1_hvp_gw(const T* x0, const T* x1, const T* f0, const T* f1, T beta, int t, int xx, int Tt,
+                                       int X) {
+  const int tp = (t + 1 == Tt) ? 0 : t + 1;
+  const int xp = (xx + 1 == X) ? 0 : xx + 1;
+  const T w = x0[t * X + xx] + x1[tp * X + xx] - x0[t * X + xp] - x1[t * X + xx];
+  const T c = f0[t * X + xx] - f0[t * X + xp] - f1[t * X + xx] + f1[tp * X + xx];
+  return beta * Num<T>::cos_(w) * c;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_force_bwd(const T* __restrict__ x, T beta, const T* __restrict__ gf,
+                                                      T* __restrict__ gx, int Tt, int X) {
+  const int N = Tt * X;
+  const T* x0 = x + (size_t)blockIdx.y * 2 * N;
+  const T* x1 = x0 + N;
+  const T* f0 = gf + (size_t)blockIdx.y * 2 * N;
+  const T* f1 = f0 + N;
+  T* g0 = gx + (size_t)blockIdx.y * 2 * N;
+  T* g1 = g0 + N;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const int t = i / X, xx = i % X;
+  const int tm = (t == 0) ? Tt - 1 : t - 1;
+  const int xm = (xx == 0) ? X - 1 : xx - 1;
+  const T c = u1_hvp_gw(x0, x1, f0, f1, beta, t, xx, Tt, X);
+  g0[i] = c - u1_hvp_gw(x0, x1, f0, f1, beta, t, xm, Tt, X);
+  g1[i] = u1_hvp_gw(x0, x1, f0, f1, beta, tm, xx, Tt, X) - c;
+}
+
+// adjoint of k_u1_vupdate.  geps[b] = d/d eps of chain b (summed over chains by the caller).
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_vupdate_bwd(const T* __restrict__ v, const T* __restrict__ f,
+                                                        const T* __restrict__ s, const T* __restrict__ t,
+                                                        const T* __restrict__ q, T eps, int sign,
+                                                        const T* __restrict__ gout, const T* __restrict__ glogdet,
+                                                        T* __restrict__ gv, T* __restrict__ gf, T* __restrict__ gs,
+                                                        T* __restrict__ gt, T* __restrict__ gq, T* __restrict__ geps,
+                                                        int xdim) {
+  __shared__ double red[8];
+  const size_t row = (size_t)blockIdx.x * xdim;
+  const T gl = glogdet ? glogdet[blockIdx.x] : T(0);
+  const T sg = (T)sign, he = T(0.5) * eps;
+  double ge = 0.0;
+  for (int i = threadIdx.x; i < xdim; i += 256) {
+    const T si = s ? s[row + i] : T(0), ti = t ? t[row + i] : T(0), qi = q ? q[row + i] : T(0);
+    const T vi = v[row + i], fi = f[row + i], go = gout[row + i];
+    const T lj = sg * eps * si / T(2);
+    const T es = Num<T>::exp_(lj), eq = Num<T>::exp_(eps * qi);
+    const T fn = fi * eq + ti;
+    T g_es, g_fn;
+    if (sign > 0) {        // v' = es v - he fn
+      g_es = go * vi;
+      g_fn = -he * go;
+      ge += (double)(-T(0.5) * fn * go);
+    } else {               // v' = es (v + he fn)
+      g_es = go * (vi + he * fn);
+      g_fn = go * es * he;
+      ge += (double)(T(0.5) * fn * go * es);
+    }
+    gv[row + i] = go * es;
+    const T g_lj = g_es * es + gl;
+    ge += (double)(g_lj * sg * si / T(2));
+    const T g_eq = g_fn * fi;
+    ge += (double)(g_eq * eq * qi);
+    gf[row + i] = g_fn * eq;
+    if (gs) gs[row + i] = g_lj * sg * eps / T(2);
+    if (gt) gt[row + i] = g_fn;
+    if (gq) gq[row + i] = g_eq * eq * eps;
+  }
+  ge = block_sum<256>(ge, red, threadIdx.x);
+  if (threadIdx.x == 0) geps[blockIdx.x] = (T)ge;
+}
+
+// adjoint of k_u1_xupdate (the wrap to [-pi, pi) has unit derivative)
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_xupdate_bwd(const T* __restrict__ x, const T* __restrict__ v,
+                                                        const T* __restrict__ s, const T* __restrict__ t,
+                                                        const T* __restrict__ q, const float* __restrict__ mask, T eps,
+                                                        int sign, int use_ncp, const T* __restrict__ gout,
+                                                        const T* __restrict__ glogdet, T* __restrict__ gx,
+                                                        T* __restrict__ gv, T* __restrict__ gs, T* __restrict__ gt,
+                                                        T* __restrict__ gq, T* __restrict__ geps, int xdim) {
+  __shared__ double red[8];
+  const size_t row = (size_t)blockIdx.x * xdim;
+  const T gl = glogdet ? glogdet[blockIdx.x] : T(0);
+  const T sg = (T)sign;
+  double ge = 0.0;
+  for (int i = threadIdx.x; i < xdim; i += 256) {
+    const T m = (T)mask[i], mb = T(1) - m;
+    const T xi = x[row + i], vi = v[row + i];
+    const T s0 = s ? s[row + i] : T(0), q0 = q ? q[row + i] : T(0), ti = t ? t[row + i] : T(0);
+    const T sp = sg * eps * s0, qp = eps * q0;
+    const T es = Num<T>::exp_(sp), eq = Num<T>::exp_(qp);
+    const T u = vi * eq + ti;            // tr = eps * u
+    const T tr = eps * u;
+    const T go = gout[row + i];
+    const T g = go * mb;                 // gradient reaching the updated branch xn
+    const T glj = gl * mb;               // gradient reaching the per-element log-Jacobian
+    T g_x, g_sp, g_tr;
+    if (use_ncp) {
+      const T hx = xi / T(2);
+      const T sn = Num<T>::sin_(hx), cs = Num<T>::cos_(hx);
+      const T den = cs * cs + es * es * sn * sn;
+      const T y = Num<T>::tan_(hx) * es;
+      const T dx1_dsp = T(2) * y / (T(1) + y * y);
+      const T dlj_dsp = T(1) - T(2) * es * es * sn * sn / den;
+      const T dlj_dx = -(sn * cs * (es * es - T(1))) / den;
+      g_x = g * (es / den) + glj * dlj_dx;
+      if (sign > 0) {                    // xn = x1 + tr
+        g_sp = g * dx1_dsp + glj * dlj_dsp;
+        g_tr = g;
+      } else {                           // xn = x1 - es tr
+        g_sp = g * (dx1_dsp - es * tr) + glj * dlj_dsp;
+        g_tr = -g * es;
+      }
+    } else {
+      if (sign > 0) {                    // xn = x es + tr, lj = sp
+        g_x = g * es;
+        g_sp = g * xi * es + glj;
+        g_tr = g;
+      } else {                           // xn = es (x - tr), lj = sp
+        g_x = g * es;
+        g_sp = g * es * (xi - tr) + glj;
+        g_tr = -g * es;
+      }
+    }
+    gx[row + i] = go * m + g_x;
+    const T g_u = g_tr * eps;            // tr = eps u
+    ge += (double)(g_tr * u);
+    gv[row + i] = g_u * eq;
+    const T g_qp = g_u * vi * eq;
+    if (gt) gt[row + i] = g_u;
+    if (gq) gq[row + i] = g_qp * eps;
+    ge += (double)(g_qp * q0);
+    if (gs) gs[row + i] = g_sp * sg * eps;
+    ge += (double)(g_sp * sg * s0);
+  }
+  ge = block_sum<256>(ge, red, threadIdx.x);
+  if (threadIdx.x == 0) geps[blockIdx.x] = (T)ge;
+}
+
+// out[b, :] = scale[b] * in[b, :]   (chain-wise scaling: action / kinetic-energy adjoints)
+template <typename T>
+__global__ void __launch_bounds__(256) k_rowscale(const T* __restrict__ in, const T* __restrict__ scale,
+                                                  T* __restrict__ out, int xdim) {
+  const size_t row = (size_t)blockIdx.y * xdim;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < xdim) out[row + i] = scale[blockIdx.y] * in[row + i];
+}
+
 int check_u1(int nb, int Tt, int X, int dtype) {
   L2B_REQUIRE(nb > 0 && Tt > 0 && X > 0, L2B_ERR_INVALID, "non-positive size: nb=%d T=%d X=%d", nb, Tt, X);
   L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
@@ -420,6 +594,89 @@ int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stre
   L2B_DISPATCH_T(dtype, (k_u1_wrap<float><<<nblk, 256, 0, st>>>((const float*)x, (float*)out, n)),
                  (k_u1_wrap<double><<<nblk, 256, 0, st>>>((const double*)x, (double*)out, n)));
   L2B_LAUNCHED("k_u1_wrap");
+  return L2B_OK;
+}
+
+int l2b_u1_wilson_loops_bwd(const void* gw, void* gx, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(gw && gx, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((T * X + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_wloops_bwd<float><<<grid, 256, 0, st>>>((const float*)gw, (float*)gx, T, X)),
+                 (k_u1_wloops_bwd<double><<<grid, 256, 0, st>>>((const double*)gw, (double*)gx, T, X)));
+  L2B_LAUNCHED("k_u1_wloops_bwd");
+  return L2B_OK;
+}
+
+int l2b_u1_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, int T, int X, int dtype,
+                     void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && gforce && gx, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((T * X + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype,
+                 (k_u1_force_bwd<float><<<grid, 256, 0, st>>>((const float*)x, (float)beta, (const float*)gforce,
+                                                             (float*)gx, T, X)),
+                 (k_u1_force_bwd<double><<<grid, 256, 0, st>>>((const double*)x, beta, (const double*)gforce,
+                                                              (double*)gx, T, X)));
+  L2B_LAUNCHED("k_u1_force_bwd");
+  return L2B_OK;
+}
+
+int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                       int sign, const void* gv_out, const void* glogdet, void* gv, void* gforce, void* gs, void* gt,
+                       void* gq, void* geps, int nb, int xdim, int dtype, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(v && force && gv_out && gv && gforce && geps, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype,
+                 (k_u1_vupdate_bwd<float><<<nb, 256, 0, st>>>(
+                     (const float*)v, (const float*)force, (const float*)s, (const float*)t, (const float*)q, (float)eps,
+                     sign, (const float*)gv_out, (const float*)glogdet, (float*)gv, (float*)gforce, (float*)gs,
+                     (float*)gt, (float*)gq, (float*)geps, xdim)),
+                 (k_u1_vupdate_bwd<double><<<nb, 256, 0, st>>>(
+                     (const double*)v, (const double*)force, (const double*)s, (const double*)t, (const double*)q, eps,
+                     sign, (const double*)gv_out, (const double*)glogdet, (double*)gv, (double*)gforce, (double*)gs,
+                     (double*)gt, (double*)gq, (double*)geps, xdim)));
+  L2B_LAUNCHED("k_u1_vupdate_bwd");
+  return L2B_OK;
+}
+
+int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
+                       double eps, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
+                       void* gs, void* gt, void* gq, void* geps, int nb, int xdim, int dtype, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(x && v && mask && gx_out && gx && gv && geps, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype,
+                 (k_u1_xupdate_bwd<float><<<nb, 256, 0, st>>>(
+                     (const float*)x, (const float*)v, (const float*)s, (const float*)t, (const float*)q, mask,
+                     (float)eps, sign, use_ncp, (const float*)gx_out, (const float*)glogdet, (float*)gx, (float*)gv,
+                     (float*)gs, (float*)gt, (float*)gq, (float*)geps, xdim)),
+                 (k_u1_xupdate_bwd<double><<<nb, 256, 0, st>>>(
+                     (const double*)x, (const double*)v, (const double*)s, (const double*)t, (const double*)q, mask, eps,
+                     sign, use_ncp, (const double*)gx_out, (const double*)glogdet, (double*)gx, (double*)gv,
+                     (double*)gs, (double*)gt, (double*)gq, (double*)geps, xdim)));
+  L2B_LAUNCHED("k_u1_xupdate_bwd");
+  return L2B_OK;
+}
+
+int l2b_rowscale(const void* in, const void* scale, void* out, int nb, int xdim, int dtype, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(in && scale && out, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((xdim + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_rowscale<float><<<grid, 256, 0, st>>>((const float*)in, (const float*)scale, (float*)out, xdim)),
+                 (k_rowscale<double><<<grid, 256, 0, st>>>((const double*)in, (const double*)scale, (double*)out, xdim)));
+  L2B_LAUNCHED("k_rowscale");
   return L2B_OK;
 }
 

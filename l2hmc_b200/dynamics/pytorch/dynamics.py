@@ -16,8 +16,9 @@ L2HMC only; element-wise float32 masks built with numpy's RNG; SU(3) x-update
 through projectSU; `acc_mask` float32; HMC `nleapfrog` doubles when
 `merge_directions`; x_out returned flattened.
 
-Gradient flow (training, BASELINE cfg 5) is not wired through the kernels yet:
-calling the L2HMC path with autograd enabled and trainable parameters raises.
+Training: the U(1) L2HMC path is differentiable end to end through hand-written
+adjoint kernels (l2hmc_b200/autograd.py); the SU(3) L2HMC path is inference-only
+for now and raises if called with autograd enabled and trainable parameters.
 """
 from __future__ import annotations
 
@@ -33,6 +34,7 @@ from torch import nn
 
 from ... import configs as cfgs
 from ... import ops
+from ... import autograd as ag
 from ...group.su3.pytorch.group import SU3
 from ...group.u1.pytorch.group import U1Phase
 from ...lattice.su3.pytorch.lattice import LatticeSU3
@@ -361,10 +363,12 @@ class Dynamics(nn.Module):
 
     # --------------------------------------------------------------- L2HMC
     def _check_inference_only(self) -> None:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        """U(1) trains through hand-written adjoint kernels (l2hmc_b200/autograd.py);
+        the SU(3) adjoints (exp, projectSU) are not written yet."""
+        if self._su3 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                'L2HMC through libl2b is inference-only in this round: wrap the call in '
-                'torch.no_grad() (training path = SURVEY.md cfg 5, not built yet)')
+                'SU(3) L2HMC through libl2b is inference-only in this round: wrap the call in '
+                'torch.no_grad() (SU(3) training path = SURVEY.md cfg 5, not built yet)')
 
     def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
         self._check_inference_only()
@@ -488,6 +492,10 @@ class Dynamics(nn.Module):
         """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394)"""
         return float(sigmoid(p.detach().log()))
 
+    def _eps_t(self, p: Tensor) -> Tensor:
+        """same, as a 0-dim tensor attached to the graph (trainable step sizes)"""
+        return sigmoid(p.log())
+
     def _forward_lf(self, step: int, state: State) -> tuple[State, Tensor]:
         m, mb = self._get_mask(step)
         state, logdet = self._update_v_fwd(step, state)
@@ -519,7 +527,7 @@ class Dynamics(nn.Module):
         if self._su3:
             v, logdet = ops.su3_vupdate(self.unflatten(state.v), self.unflatten(force), s, t, q, eps, sign)
         else:
-            v, logdet = ops.u1_vupdate(state.v, force, s, t, q, eps, sign)
+            v, logdet = ag.U1VUpdate.apply(state.v, force, s, t, q, self._eps_t(self.veps[step]), sign)
         return State(state.x, v, state.beta), logdet
 
     def _update_v_fwd(self, step: int, state: State) -> tuple[State, Tensor]:
@@ -538,7 +546,8 @@ class Dynamics(nn.Module):
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
         xm_init = self.unflatten(m) * x
         s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)
-        xn, logdet = ops.u1_xupdate(x, state.v, s, t, q, m, eps, sign, self.config.use_ncp)
+        xn, logdet = ag.U1XUpdate.apply(x, state.v, s, t, q, m, self._eps_t(self.xeps[step]), sign,
+                                        bool(self.config.use_ncp))
         return State(x=xn, v=state.v, beta=state.beta), logdet
 
     def _update_x_fwd(self, step: int, state: State, m: Tensor, first: bool) -> tuple[State, Tensor]:

@@ -8,6 +8,7 @@ import torch
 
 from ....group.group import Group
 from .... import ops
+from .... import autograd as ag
 
 PI = torch.pi
 TWO_PI = 2. * torch.pi
@@ -71,7 +72,7 @@ class U1Phase(Group):
 
     def compat_proj(self, x: Tensor) -> Tensor:
         """((x + pi) mod 2 pi) - pi   (group.py:130-131)"""
-        return ops.u1_compat_proj(x)
+        return ag.U1CompatProj.apply(x)
 
     def projectTAH(self, x: Tensor) -> Tensor:
         return x
@@ -86,4 +87,4 @@ class U1Phase(Group):
         return torch.randn(*shape, device=_device()).reshape(shape[0], -1)
 
     def kinetic_energy(self, p: Tensor) -> Tensor:
-        return ops.u1_kinetic(p)
+        return ag.U1Kinetic.apply(p)

@@ -13,6 +13,7 @@ from ....configs import Charges, LatticeMetrics
 from ....group.u1.pytorch.group import U1Phase
 from ....lattice.lattice import Lattice
 from .... import ops
+from .... import autograd as ag
 
 TWOPI = 2. * PI
 Tensor = torch.Tensor
@@ -52,18 +53,24 @@ class LatticeU1(Lattice):
 
     # -- kernels ---------------------------------------------------------------
     def wilson_loops(self, x: Tensor) -> Tensor:
-        return ops.u1_wilson_loops(self._field(x.detach()))
+        """differentiable (the loss back-propagates through it, loss/pytorch/loss.py:194-197)"""
+        return ag.U1WilsonLoops.apply(x, list(self._lattice_shape))
 
     def _obs(self, x: Tensor, beta=1.0) -> Tensor:
         """[nb, 4] = (action, plaq, sinQ, intQ) in one pass"""
         return ops.u1_observables(self._field(x.detach()), _f(beta))
 
     def action(self, x: Tensor, beta) -> Tensor:
-        return self._obs(x, beta)[:, 0]
+        """differentiable: backward is the force kernel"""
+        return ag.U1Action.apply(x, _f(beta), list(self._lattice_shape))
 
     def grad_action(self, x: Tensor, beta, create_graph: bool = True) -> Tensor:
-        """analytic dS/dx (reference: autograd, lattice.py:102-117), shaped like x"""
-        return ops.u1_force(self._field(x.detach()), _f(beta)).reshape(x.shape)
+        """analytic dS/dx (reference: autograd, lattice.py:102-117), shaped like x.
+        Differentiable once more, like the reference's create_graph=True: the
+        backward is the Hessian-vector-product kernel."""
+        if not create_graph:
+            x = x.detach()
+        return ag.U1Force.apply(x, _f(beta), list(self._lattice_shape))
 
     def action_with_grad(self, x: Tensor, beta) -> tuple[Tensor, Tensor]:
         return self.action(x, beta), self.grad_action(x, beta)

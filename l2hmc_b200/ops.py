@@ -390,3 +390,72 @@ def accept_mix(accept: Tensor, pairs: Sequence[tuple[Tensor, Tensor]]) -> list[T
     call('l2b_accept_mix', ctypes.cast(pi, ctypes.POINTER(c_void_p)), ctypes.cast(pp, ctypes.POINTER(c_void_p)),
          ctypes.cast(po, ctypes.POINTER(c_void_p)), rb, n, _ptr(accept), nb, _stream())
     return outs
+
+
+# ---------------------------------------------------------------------------
+# adjoints (training path)
+# ---------------------------------------------------------------------------
+def u1_wilson_loops_bwd(gw: Tensor) -> Tensor:
+    _need_cuda(gw)
+    gw = gw.contiguous()
+    nb, T, X = gw.shape
+    gx = torch.empty((nb, 2, T, X), dtype=gw.dtype, device=gw.device)
+    call('l2b_u1_wilson_loops_bwd', _ptr(gw), _ptr(gx), nb, T, X, _dt(gw), _stream())
+    return gx
+
+
+def u1_force_bwd(x: Tensor, beta: float, gforce: Tensor, shape=None) -> Tensor:
+    x, nb, T, X = _u1_field(x, shape)
+    gforce = gforce.to(x.dtype).reshape(x.shape).contiguous()
+    gx = torch.empty_like(x)
+    call('l2b_u1_force_bwd', _ptr(x), float(beta), _ptr(gforce), _ptr(gx), nb, T, X, _dt(x), _stream())
+    return gx
+
+
+def u1_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
+    nb = v.shape[0]
+    v2 = v.reshape(nb, -1).contiguous()
+    f2 = force.to(v.dtype).reshape(nb, -1).contiguous()
+    xdim = v2.shape[1]
+    s, t, q = _rows(s, nb, v2), _rows(t, nb, v2), _rows(q, nb, v2)
+    go = gv_out.to(v.dtype).reshape(nb, -1).contiguous()
+    gl = None if glogdet is None else glogdet.to(v.dtype).contiguous()
+    gv, gf = torch.empty_like(v2), torch.empty_like(v2)
+    gs = torch.empty_like(v2) if s is not None else None
+    gt = torch.empty_like(v2) if t is not None else None
+    gq = torch.empty_like(v2) if q is not None else None
+    geps = torch.empty(nb, dtype=v.dtype, device=v.device)
+    call('l2b_u1_vupdate_bwd', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(go),
+         _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, xdim, _dt(v2), _stream())
+    return gv, gf, gs, gt, gq, geps
+
+
+def u1_xupdate_bwd(x, v, s, t, q, mask, eps: float, sign: int, use_ncp: bool, gx_out, glogdet):
+    nb = x.shape[0]
+    x2 = x.reshape(nb, -1).contiguous()
+    v2 = v.to(x.dtype).reshape(nb, -1).contiguous()
+    xdim = x2.shape[1]
+    s, t, q = _rows(s, nb, x2), _rows(t, nb, x2), _rows(q, nb, x2)
+    mask = mask.to(torch.float32).reshape(-1).contiguous()
+    go = gx_out.to(x.dtype).reshape(nb, -1).contiguous()
+    gl = None if glogdet is None else glogdet.to(x.dtype).contiguous()
+    gx, gv = torch.empty_like(x2), torch.empty_like(x2)
+    gs = torch.empty_like(x2) if s is not None else None
+    gt = torch.empty_like(x2) if t is not None else None
+    gq = torch.empty_like(x2) if q is not None else None
+    geps = torch.empty(nb, dtype=x.dtype, device=x.device)
+    call('l2b_u1_xupdate_bwd', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), float(eps), int(sign),
+         int(bool(use_ncp)), _ptr(go), _ptr(gl), _ptr(gx), _ptr(gv), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, xdim,
+         _dt(x2), _stream())
+    return gx, gv, gs, gt, gq, geps
+
+
+def rowscale(a: Tensor, scale: Tensor) -> Tensor:
+    """out[b, ...] = scale[b] * a[b, ...]   (real fields)"""
+    _need_cuda(a, scale)
+    nb = a.shape[0]
+    a2 = a.reshape(nb, -1).contiguous()
+    sc = scale.to(a.dtype).contiguous()
+    out = torch.empty_like(a2)
+    call('l2b_rowscale', _ptr(a2), _ptr(sc), _ptr(out), nb, a2.shape[1], _dt(a2), _stream())
+    return out.reshape(a.shape)

@@ -219,6 +219,21 @@ def u1_goldens(ref, torch, tag: str):
         out[pre + 'xbwd_x'], out[pre + 'xbwd_logdet'] = _np(s3.x), _np(ld3)
         s4, ld4 = dyn._update_v_fwd(0, st)
         out[pre + 'vfwd_v'], out[pre + 'vfwd_logdet'] = _np(s4.v), _np(ld4)
+        # gradients of a scalar that touches every output of the sweep (x_prop, acc,
+        # sumlogdet, wilson loops), through the reference's own autograd graph
+        sp, met = dyn.transition_kernel_fb(st)
+        xp = sp.x.flatten(1)
+        loss = ((met['acc'] * xp.cos().sum(1)).sum() + met['sumlogdet'].sum()
+                + (met['acc'] * lat.wilson_loops(sp.x).sin().sum((1, 2))).sum())
+        # named_parameters() de-duplicates the twice-registered nets and keeps the `networks.` alias
+        named = [(n[len('networks.'):] if n.startswith('networks.') else n, p)
+                 for n, p in dyn.named_parameters() if p.requires_grad]
+        grads = torch.autograd.grad(loss, [p for _, p in named] + [x], allow_unused=True)
+        out[pre + 'loss'] = _np(loss)
+        for (n, _), g_ in zip(named, grads[:-1]):
+            if g_ is not None:
+                out[pre + 'grad/' + n] = _np(g_)
+        out[pre + 'grad_x'] = _np(grads[-1])
     np.savez_compressed(GOLD / f'u1_{tag}.npz', **out)
 
 
