@@ -138,6 +138,25 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
                            void* x_prop, void* v_prop, double* energies, int nb,
                            const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/* --- adjoints (L2HMC training; the reference relies on autograd for these).  Gradients
+ * of complex fields use torch's convention G = dL/dRe + i dL/dIm for a real loss L. --- */
+/* adjoint of LatticeSU3.action: gx = coef[b] * A^+ (A = staple sum); with
+ * coef[b] = -(beta/3) * dL/dS[b] this is dL/dx through S = -(beta/3) sum Re tr P */
+int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, const int dims[4], int dtype, void* ws,
+                        size_t ws_bytes, void* stream);
+/* adjoint of l2b_su3_vupdate w.r.t. v, force, s, t, q (gforce/gs/gt/gq may be NULL) and eps
+ * (geps[nb], per chain) */
+int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                        int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
+                        void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+/* adjoint of l2b_su3_update_gauge w.r.t. x, p and eps (matrix-exponential adjoint as a Taylor
+ * series on Cayley-Hamilton coefficients; *bad_flag is set when ||eps p||_F > 3 somewhere) */
+int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+                             const void* gx_out, void* gx, void* gp, double* geps, int* bad_flag, int nb,
+                             const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+/* adjoint of l2b_su3_to_vec: gx[nmat,3,3] from gvec8[nmat,8] */
+int l2b_su3_to_vec_bwd(const void* gvec8, void* gx, size_t nmat, int dtype, void* stream);
+
 /* The two kernels of one leapfrog step on fields ALREADY in the planar layout
  * (l2b_su3_aos_to_soa), for callers that keep the state planar between steps
  * and for per-kernel timing (bench.py):

@@ -55,6 +55,10 @@ _SIGS = {
     'l2b_su3_rand_momentum': [c_uint64, c_uint64, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_action_grad': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_update_gauge_bwd': [_P, _P, c_double, _P, c_int, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_to_vec_bwd': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],

@@ -356,6 +356,172 @@ __global__ void __launch_bounds__(128, MINB) k_force_async(const C* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------
+// adjoint kernels of the SU(3) L2HMC path (training)
+// ---------------------------------------------------------------------------
+// gx(mu,n) = coef[b] * A_mu(n)^+  : adjoint of the Wilson action, dS/dU = -(beta/3) A^+
+// (the staple sum of the force kernel without the final link product), planar output
+template <int TS>
+__global__ void __launch_bounds__(TS * 4, 3) k_action_grad(const C* __restrict__ U, C* __restrict__ G, Lat lat,
+                                                           const double* __restrict__ coef) {
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  if (site >= lat.V) return;
+  Mat3<T> a, ah;
+  link_times_staples<T, C, 0, false>(a, U, lat, b, mu, site);
+  const double c = coef[b];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { ah.re[3 * i + j] = c * a.re[3 * j + i]; ah.im[3 * i + j] = -c * a.im[3 * j + i]; }
+  }
+  soa_store(soa_plane(G, lat, b, mu), lat.V, site, ah);
+}
+
+// adjoint of k_vupdate (force is a constant of the graph)
+__global__ void __launch_bounds__(NTL) k_vupdate_bwd(const C* __restrict__ v, const C* __restrict__ f,
+                                                     const T* __restrict__ s, const T* __restrict__ t,
+                                                     const T* __restrict__ q, double eps, int sign,
+                                                     const C* __restrict__ gout, const double* __restrict__ glogdet,
+                                                     C* __restrict__ gv, C* __restrict__ gf, T* __restrict__ gs,
+                                                     T* __restrict__ gt, T* __restrict__ gq, double* __restrict__ part,
+                                                     size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> Vm, Fm, Gm, R;
+  T sv[9], tv[9], qv[9];
+  block_load_mat<NTL>(Vm, sm, v, row0 + l0, n);
+  block_load_mat<NTL>(Fm, sm, f, row0 + l0, n);
+  block_load_mat<NTL>(Gm, sm, gout, row0 + l0, n);
+  T* smr = reinterpret_cast<T*>(sm);
+  block_load_real9<NTL>(sv, smr, s, row0 + l0, n);
+  block_load_real9<NTL>(tv, smr, t, row0 + l0, n);
+  block_load_real9<NTL>(qv, smr, q, row0 + l0, n);
+  const double gl = glogdet ? glogdet[blockIdx.y] : 0.0;
+  const T sg = (T)sign, he = T(0.5) * eps;
+  double ge = 0.0;
+  const bool live = (int)threadIdx.x < n;
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const T lj = sg * eps * sv[e] / T(2);
+      const T es = exp(lj), eq = exp(eps * qv[e]);
+      const T fr = fma(Fm.re[e], eq, tv[e]), fi = Fm.im[e] * eq;
+      const T a = Gm.re[e], b = Gm.im[e];
+      T g_es, g_fr, g_fi;
+      if (sign > 0) {
+        g_es = a * Vm.re[e] + b * Vm.im[e];
+        g_fr = -he * a; g_fi = -he * b;
+        ge += -T(0.5) * (fr * a + fi * b);
+      } else {
+        g_es = a * (Vm.re[e] + he * fr) + b * (Vm.im[e] + he * fi);
+        g_fr = es * he * a; g_fi = es * he * b;
+        ge += T(0.5) * es * (fr * a + fi * b);
+      }
+      R.re[e] = es * a; R.im[e] = es * b;
+      Gm.re[e] = g_fr * eq; Gm.im[e] = g_fi * eq;   // d/dF (the reference's force keeps its `@ x^+` factor attached)
+      const T g_lj = g_es * es + gl;
+      ge += g_lj * sg * sv[e] / T(2);
+      const T g_eq = g_fr * Fm.re[e] + g_fi * Fm.im[e];
+      ge += g_eq * eq * qv[e];
+      sv[e] = g_lj * sg * eps / T(2);     // reuse the registers for the outputs
+      tv[e] = g_fr;
+      qv[e] = g_eq * eq * eps;
+    }
+  }
+  block_store_mat<NTL>(gv, sm, R, row0 + l0, n);
+  if (gf != nullptr) block_store_mat<NTL>(gf, sm, Gm, row0 + l0, n);
+  // real outputs: stage 9 values per link through shared memory for contiguous stores
+  T* outs[3] = {gs, gt, gq};
+  for (int k = 0; k < 3; ++k) {
+    if (outs[k] == nullptr) continue;
+    if (live) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) smr[threadIdx.x * 9 + e] = (k == 0) ? sv[e] : (k == 1) ? tv[e] : qv[e];
+    }
+    __syncthreads();
+    stage_out<NTL>(outs[k], smr, row0 + l0, n, 9);
+    __syncthreads();
+  }
+  ge = block_sum<NTL>(ge, red, threadIdx.x);
+  if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = ge;
+}
+
+// adjoint of k_update_gauge:  R = m*X + E ((1-m)*X),  E = exp(eps P)
+//   G_X = m*G + (1-m)*(E^+ G),  G_E = G ((1-m)*X)^+,  G_P = eps * expadj(eps P; G_E),
+//   g_eps = Re sum conj(G_A) P
+__global__ void __launch_bounds__(NTL) k_update_gauge_bwd(const C* __restrict__ x, const C* __restrict__ p, double eps,
+                                                          const float* __restrict__ mask, int mask_complement,
+                                                          const C* __restrict__ gout, C* __restrict__ gx,
+                                                          C* __restrict__ gp, double* __restrict__ part,
+                                                          int* __restrict__ bad, size_t links_per_chain) {
+  __shared__ C sm[NTL * 9];
+  __shared__ double red[NTL / 32];
+  const size_t row0 = (size_t)blockIdx.y * links_per_chain;
+  const size_t l0 = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, links_per_chain - l0);
+  Mat3<T> X, Pm, G, E, Xb, GX, GE, GA;
+  block_load_mat<NTL>(Pm, sm, p, row0 + l0, n);
+  block_load_mat<NTL>(X, sm, x, row0 + l0, n);
+  block_load_mat<NTL>(G, sm, gout, row0 + l0, n);
+  double ge = 0.0;
+  if ((int)threadIdx.x < n) {
+    Mat3<T> A;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { A.re[e] = eps * Pm.re[e]; A.im[e] = eps * Pm.im[e]; }
+    mat_exp(E, A);
+    T md[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      float m = (mask == nullptr) ? 0.0f : __ldg(mask + (l0 + threadIdx.x) * 9 + e);
+      if (mask != nullptr && mask_complement) m = 1.0f - m;
+      md[e] = (T)m;
+      const T mb = (T)(1.0f - m);
+      Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+    }
+    mat_mul<true, false, false>(GX, E, G);          // E^+ G
+    mat_mul<false, true, false>(GE, G, Xb);         // G Xb^+
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const T mb = T(1) - md[e];
+      GX.re[e] = md[e] * G.re[e] + mb * GX.re[e];
+      GX.im[e] = md[e] * G.im[e] + mb * GX.im[e];
+    }
+    bool ok;
+    mat_exp_adjoint(GA, A, GE, ok);
+    if (!ok) atomicExch(bad, 1);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      ge = fma(GA.re[e], Pm.re[e], ge);
+      ge = fma(GA.im[e], Pm.im[e], ge);
+      GA.re[e] *= eps; GA.im[e] *= eps;
+    }
+  }
+  block_store_mat<NTL>(gx, sm, GX, row0 + l0, n);
+  block_store_mat<NTL>(gp, sm, GA, row0 + l0, n);
+  ge = block_sum<NTL>(ge, red, threadIdx.x);
+  if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = ge;
+}
+
+__global__ void __launch_bounds__(NTL) k_to_vec_bwd(const T* __restrict__ gvec8, C* __restrict__ gx, size_t nmat) {
+  __shared__ C sm[NTL * 9];
+  const size_t first = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, nmat - first);
+  Mat3<T> m;
+  if ((int)threadIdx.x < n) {
+    T v[8];
+    const double2* in = reinterpret_cast<const double2*>(gvec8 + (first + threadIdx.x) * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double2 w = __ldg(in + k); v[2 * k] = w.x; v[2 * k + 1] = w.y; }
+    su3_to_vec_adjoint(m, v);
+  }
+  block_store_mat<NTL>(gx, sm, m, first, n);
+}
+
 // U <- exp(eps P) U on the planar layout
 __global__ void __launch_bounds__(128, 4) k_drift(C* __restrict__ U, const C* __restrict__ P, int V, double eps) {
   const int plane = blockIdx.y;
@@ -1138,6 +1304,64 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
   L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 3, nb, st));
   L2B_TRY(launch_s2a(g, U, (C*)x_prop, st));
   L2B_TRY(launch_s2a(g, P, (C*)v_prop, st));
+  return L2B_OK;
+}
+
+int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, const int dims[4], int dtype, void* ws,
+                        size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && coef && gx, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  k_action_grad<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, w.f1, g.lat, coef);
+  L2B_LAUNCHED("k_action_grad");
+  return launch_s2a(g, w.f1, (C*)gx, st);
+}
+
+int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+                        int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
+                        void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(v && force && gv_out && gv && geps, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_vupdate_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)v, (const C*)force, (const T*)s, (const T*)t,
+                                                       (const T*)q, eps, sign, (const C*)gv_out, glogdet, (C*)gv,
+                                                       (C*)gforce, (T*)gs, (T*)gt, (T*)gq, w.part,
+                                                       g.links_per_chain);
+  L2B_LAUNCHED("k_vupdate_bwd");
+  return launch_reduce(w.part, g.nblk_link, 1, 0, 1.0, 0.0, geps, 1, 0, nb, st);
+}
+
+int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+                             const void* gx_out, void* gx, void* gp, double* geps, int* bad_flag, int nb,
+                             const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && p && gx_out && gx && gp && geps && bad_flag, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_update_gauge_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, mask, mask_complement,
+                                                            (const C*)gx_out, (C*)gx, (C*)gp, w.part, bad_flag,
+                                                            g.links_per_chain);
+  L2B_LAUNCHED("k_update_gauge_bwd");
+  return launch_reduce(w.part, g.nblk_link, 1, 0, 1.0, 0.0, geps, 1, 0, nb, st);
+}
+
+int l2b_su3_to_vec_bwd(const void* gvec8, void* gx, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(gvec8 && gx, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  k_to_vec_bwd<<<nblk, NTL, 0, (cudaStream_t)stream>>>((const T*)gvec8, (C*)gx, nmat);
+  L2B_LAUNCHED("k_to_vec_bwd");
   return L2B_OK;
 }
 

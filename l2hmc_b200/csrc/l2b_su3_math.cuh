@@ -353,4 +353,72 @@ L2B_HD void tah_from_normals(Mat3<T>& m, const T n[8]) {
   m.re[7] = -m.re[5];  m.im[7] = m.im[5];
 }
 
+// ---------------------------------------------------------------------------
+// adjoints used by the training path (torch convention for a real loss L:
+// G_Z = dL/dRe Z + i dL/dIm Z, so for Y = A B:  G_A = G_Y B^+,  G_B = A^+ G_Y)
+// ---------------------------------------------------------------------------
+
+// Adjoint of E = exp(A):  G_A = sum_{n>=1} 1/n! sum_{k<n} B^k G_E B^(n-1-k),  B = A^+.
+// With B^m = a_m + b_m B + c_m B^2 (Cayley-Hamilton, as in mat_exp) the inner sums obey
+//   D_1 = G,  D_n = B D_{n-1} + G B^{n-1} = B D_{n-1} + a G + b (G B) + c (G B^2),
+// one matrix product per Taylor term.  No scaling/squaring: 34 terms converge to
+// double precision for ||A||_F <= 3 (3^34/34! ~ 6e-23); L2HMC arguments are eps*v
+// with eps < 1, ||v||_F ~ 2.8.  `ok` is cleared when the norm is outside that range.
+template <typename T>
+L2B_HD void mat_exp_adjoint(Mat3<T>& ga, const Mat3<T>& a, const Mat3<T>& ge, bool& ok) {
+  ok = norm2(a) <= T(9);
+  Mat3<T> b, b2, gb, gb2, d, tmp;
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) { b.re[3 * i + j] = a.re[3 * j + i]; b.im[3 * i + j] = -a.im[3 * j + i]; }
+  }
+  mat_mul<false, false, false>(b2, b, b);
+  mat_mul<false, false, false>(gb, ge, b);
+  mat_mul<false, false, false>(gb2, gb, b);
+  const T tr = b.re[0] + b.re[4] + b.re[8], ti = b.im[0] + b.im[4] + b.im[8];
+  const T t2r = b2.re[0] + b2.re[4] + b2.re[8], t2i = b2.im[0] + b2.im[4] + b2.im[8];
+  const T cr = T(0.5) * (tr * tr - ti * ti - t2r), ci = T(0.5) * (T(2) * tr * ti - t2i);
+  T dr, di;
+  det3(b, dr, di);
+  // (a_m, b_m, c_m) of B^m, starting at m = 0: (1, 0, 0)
+  T amr = T(1), ami = T(0), bmr = T(0), bmi = T(0), cmr = T(0), cmi = T(0);
+  d = ge;          // D_1
+  ga = ge;         // n = 1 term, 1/1!
+  T inv_fact = T(1);
+  for (int n = 2; n <= 34; ++n) {
+    // advance B^{n-2} -> B^{n-1}
+    const T nar = dr * cmr - di * cmi, nai = dr * cmi + di * cmr;
+    const T nbr = amr - (cr * cmr - ci * cmi), nbi = ami - (cr * cmi + ci * cmr);
+    const T ncr = bmr + (tr * cmr - ti * cmi), nci = bmi + (tr * cmi + ti * cmr);
+    amr = nar; ami = nai; bmr = nbr; bmi = nbi; cmr = ncr; cmi = nci;
+    // D_n = B D_{n-1} + a G + b GB + c GB2
+    mat_mul<false, false, false>(tmp, b, d);
+    L2B_UNROLL
+    for (int e = 0; e < 9; ++e) {
+      T r = tmp.re[e], i = tmp.im[e];
+      r += amr * ge.re[e] - ami * ge.im[e];   i += amr * ge.im[e] + ami * ge.re[e];
+      r += bmr * gb.re[e] - bmi * gb.im[e];   i += bmr * gb.im[e] + bmi * gb.re[e];
+      r += cmr * gb2.re[e] - cmi * gb2.im[e]; i += cmr * gb2.im[e] + cmi * gb2.re[e];
+      d.re[e] = r; d.im[e] = i;
+    }
+    inv_fact /= T(n);
+    L2B_UNROLL
+    for (int e = 0; e < 9; ++e) { ga.re[e] = fma(inv_fact, d.re[e], ga.re[e]); ga.im[e] = fma(inv_fact, d.im[e], ga.im[e]); }
+  }
+}
+
+// adjoint of su3_to_vec (a real-linear map of the matrix entries)
+template <typename T>
+L2B_HD void su3_to_vec_adjoint(Mat3<T>& g, const T v[8]) {
+  const T s3 = T(0.57735026918962576451);
+  mat_zero(g);
+  g.re[1] = T(-2) * v[1]; g.im[1] = T(-2) * v[0];
+  g.re[2] = T(-2) * v[4]; g.im[2] = T(-2) * v[3];
+  g.re[5] = T(-2) * v[6]; g.im[5] = T(-2) * v[5];
+  g.im[0] = -v[2] - s3 * v[7];
+  g.im[4] = v[2] - s3 * v[7];
+  g.im[8] = T(2) * s3 * v[7];
+}
+
 }  // namespace l2b

@@ -120,7 +120,9 @@ L2B_HD int sel4(int a0, int a1, int a2, int a3, int i) {
 
 // PF = 1: while the staples of direction k are being multiplied, prefetch (to L1)
 // the six matrices of direction k+1 -- latency hiding that costs no registers.
-template <typename T, typename C, int PF = 0>
+// WITH_LINK = false returns the staple sum A itself (the action's adjoint is
+// dS/dU = -(beta/3) A^+), true returns G = U A.
+template <typename T, typename C, int PF = 0, bool WITH_LINK = true>
 L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int mu, int site) {
   const int V = l.V;
   // coordinates, and for every direction d: site offset of a forward / backward hop
@@ -176,8 +178,12 @@ L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int 
     soa_load(x, pnu, V, n_mnu);                  // U_nu(n-nu)
     mat_mul<false, false, true>(a, m, x);        // a += m U_nu(n-nu)
   }
-  soa_load(x, pmu, V, site);
-  mat_mul<false, false, false>(g, x, a);
+  if (WITH_LINK) {
+    soa_load(x, pmu, V, site);
+    mat_mul<false, false, false>(g, x, a);
+  } else {
+    g = a;
+  }
 }
 
 // ---------------------------------------------------------------------------

@@ -16,9 +16,11 @@ L2HMC only; element-wise float32 masks built with numpy's RNG; SU(3) x-update
 through projectSU; `acc_mask` float32; HMC `nleapfrog` doubles when
 `merge_directions`; x_out returned flattened.
 
-Training: the U(1) L2HMC path is differentiable end to end through hand-written
-adjoint kernels (l2hmc_b200/autograd.py); the SU(3) L2HMC path is inference-only
-for now and raises if called with autograd enabled and trainable parameters.
+Training: both L2HMC paths are differentiable end to end (l2hmc_b200/autograd.py):
+U(1) entirely through hand-written adjoint kernels; SU(3) through adjoint kernels for
+the action, the v-update, the masked exp(eps v) x-update (matrix-exponential adjoint),
+su3_to_vec and the kinetic energy, with projectSU and the per-site Wilson loops
+back-propagated by re-evaluating a torch restatement inside backward for now.
 """
 from __future__ import annotations
 
@@ -363,12 +365,9 @@ class Dynamics(nn.Module):
 
     # --------------------------------------------------------------- L2HMC
     def _check_inference_only(self) -> None:
-        """U(1) trains through hand-written adjoint kernels (l2hmc_b200/autograd.py);
-        the SU(3) adjoints (exp, projectSU) are not written yet."""
-        if self._su3 and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                'SU(3) L2HMC through libl2b is inference-only in this round: wrap the call in '
-                'torch.no_grad() (SU(3) training path = SURVEY.md cfg 5, not built yet)')
+        """kept for API stability: both groups are differentiable now
+        (l2hmc_b200/autograd.py)"""
+        return None
 
     def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
         self._check_inference_only()
@@ -525,7 +524,8 @@ class Dynamics(nn.Module):
         eps = self._eps(self.veps[step])
         s, t, q = self._call_vnet(step, (state.x, force))
         if self._su3:
-            v, logdet = ops.su3_vupdate(self.unflatten(state.v), self.unflatten(force), s, t, q, eps, sign)
+            v, logdet = ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), s, t, q,
+                                            self._eps_t(self.veps[step]).to(torch.float64), sign)
         else:
             v, logdet = ag.U1VUpdate.apply(state.v, force, s, t, q, self._eps_t(self.veps[step]), sign)
         return State(state.x, v, state.beta), logdet
@@ -542,7 +542,8 @@ class Dynamics(nn.Module):
         x = self.unflatten(state.x)
         if self._su3:
             # x' = m*x + exp(+-eps v) @ ((1-m)*x); xnet is never called, logdet = 0
-            xn = ops.su3_update_gauge(x, self.unflatten(state.v), sign * eps, mask=m)
+            xn = ag.SU3UpdateGauge.apply(x, self.unflatten(state.v), self._eps_t(self.xeps[step]).to(torch.float64),
+                                         m, sign)
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
         xm_init = self.unflatten(m) * x
         s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)

@@ -14,6 +14,7 @@ import torch
 
 from ....group.group import Group
 from .... import ops
+from .... import autograd as ag
 
 Tensor = torch.Tensor
 
@@ -107,18 +108,18 @@ class SU3(Group):
         return ops.su3_tah(x)
 
     def projectSU(self, x: Tensor) -> Tensor:
-        return ops.su3_project(x)
+        return ag.SU3Project.apply(x)
 
     def compat_proj(self, x: Tensor) -> Tensor:
-        return ops.su3_project(x)
+        return ag.SU3Project.apply(x)
 
     def kinetic_energy(self, p: Tensor) -> Tensor:
         """0.5 * sum(|P|_F^2 - 8)   (group.py:125-126)"""
-        return ops.su3_kinetic(p)
+        return ag.SU3Kinetic.apply(p)
 
     def group_to_vec(self, x: Tensor) -> Tensor:
         """su3_to_vec(projectSU(x)) in one kernel   (group.py:138-147)"""
-        return ops.su3_project(x, want_matrix=False, want_vec=True)
+        return ag.SU3GroupToVec.apply(x)
 
     def vec_to_group(self, x: Tensor) -> Tensor:
         """projectSU(vec_to_su3(x))   (group.py:128-136)"""

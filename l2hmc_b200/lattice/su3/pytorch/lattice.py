@@ -17,6 +17,7 @@ from ....configs import Charges
 from ....group.su3.pytorch.group import SU3
 from ....lattice.lattice import Lattice
 from .... import ops
+from .... import autograd as ag
 
 Tensor = torch.Tensor
 
@@ -55,8 +56,8 @@ class LatticeSU3(Lattice):
         return ops.su3_plaq_sums(self._field(x.detach()))
 
     def wilson_loops(self, x: Tensor) -> Tensor:
-        """ps[6, nb, T, X, Y, Z]   (lattice.py:157-199,242-244)"""
-        return ops.su3_wilson_loops(self._field(x.detach()))
+        """ps[6, nb, T, X, Y, Z]   (lattice.py:157-199,242-244); differentiable"""
+        return ag.SU3WilsonLoops.apply(self._field(x))
 
     def _wilson_loops(self, x: Tensor, needs_rect: bool = False) -> tuple[Tensor, Tensor]:
         assert not needs_rect, 'rectangles: SURVEY section 8 f-4'
@@ -64,8 +65,9 @@ class LatticeSU3(Lattice):
         return ps, torch.zeros((12, *ps.shape[1:]), dtype=ps.dtype, device=ps.device)
 
     def action(self, x: Tensor, beta) -> Tensor:
-        """S = -(beta/3) sum Re tr P   (lattice.py:252-269)"""
-        return self._sums(x)[:, 0] * (-_f(beta) / 3.0)
+        """S = -(beta/3) sum Re tr P   (lattice.py:252-269); differentiable (adjoint =
+        the staple-sum kernel)"""
+        return ag.SU3Action.apply(self._field(x), _f(beta))
 
     def _action(self, wloops, beta) -> Tensor:
         """NB: the reference's `_action` has no minus sign (lattice.py:271-285)"""
@@ -116,7 +118,7 @@ class LatticeSU3(Lattice):
         """(beta/3) TAH(U A), analytic; equals the reference's
         projectTAH(autograd(S) @ x^+) (lattice.py:299-308).  Like the reference
         (no create_graph) the result is a constant w.r.t. later backprop."""
-        return ops.su3_force(self._field(x.detach()), _f(beta))
+        return ag.SU3Force.apply(self._field(x), _f(beta))
 
     def action_with_grad(self, x: Tensor, beta) -> tuple[Tensor, Tensor]:
         """one force pass yields both (lattice.py:287-297)"""

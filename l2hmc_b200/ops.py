@@ -459,3 +459,57 @@ def rowscale(a: Tensor, scale: Tensor) -> Tensor:
     out = torch.empty_like(a2)
     call('l2b_rowscale', _ptr(a2), _ptr(sc), _ptr(out), nb, a2.shape[1], _dt(a2), _stream())
     return out.reshape(a.shape)
+
+
+def su3_action_grad(x: Tensor, coef: Tensor) -> Tensor:
+    """gx = coef[b] * A^+ (A = staple sum)"""
+    x, nb, dims = _su3_field(x)
+    coef = coef.to(torch.float64).contiguous()
+    gx = torch.empty_like(x)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_action_grad', _ptr(x), _ptr(coef), _ptr(gx), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return gx
+
+
+def su3_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
+    v, nb, dims = _su3_field(v)
+    force, _, _ = _su3_field(force, dims)
+    gv_out, _, _ = _su3_field(gv_out.to(torch.complex128), dims)
+    xdim = v[0].numel()
+
+    def real(a):
+        return None if a is None else a.to(torch.float64).reshape(nb, xdim).contiguous()
+    s, t, q = real(s), real(t), real(q)
+    gl = None if glogdet is None else glogdet.to(torch.float64).contiguous()
+    gv, gf = torch.empty_like(v), torch.empty_like(v)
+    mk = lambda ref: None if ref is None else torch.empty((nb, xdim), dtype=torch.float64, device=v.device)  # noqa: E731
+    gs, gt, gq = mk(s), mk(t), mk(q)
+    geps = torch.empty(nb, dtype=torch.float64, device=v.device)
+    ws, n = _su3_ws(nb, dims, v.device)
+    call('l2b_su3_vupdate_bwd', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(gv_out),
+         _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, dims4(dims), L2B_F64, _ptr(ws), n,
+         _stream())
+    return gv, gf, gs, gt, gq, geps
+
+
+def su3_update_gauge_bwd(x, p, eps: float, mask, mask_complement: bool, gx_out):
+    x, nb, dims = _su3_field(x)
+    p, _, _ = _su3_field(p, dims)
+    gx_out, _, _ = _su3_field(gx_out.to(torch.complex128), dims)
+    if mask is not None:
+        mask = mask.to(torch.float32).contiguous()
+    gx, gp = torch.empty_like(x), torch.empty_like(x)
+    geps = torch.empty(nb, dtype=torch.float64, device=x.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_update_gauge_bwd', _ptr(x), _ptr(p), float(eps), _ptr(mask), int(mask_complement), _ptr(gx_out),
+         _ptr(gx), _ptr(gp), _ptr(geps), _ptr(bad), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return gx, gp, geps, bad
+
+
+def su3_to_vec_bwd(gvec: Tensor) -> Tensor:
+    _need_cuda(gvec)
+    gvec = gvec.to(torch.float64).contiguous()
+    gx = torch.empty((*gvec.shape[:-1], 3, 3), dtype=torch.complex128, device=gvec.device)
+    call('l2b_su3_to_vec_bwd', _ptr(gvec), _ptr(gx), gvec.numel() // 8, L2B_F64, _stream())
+    return gx

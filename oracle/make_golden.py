@@ -152,6 +152,20 @@ def su3_goldens(ref, torch):
     sp, met = dyn.transition_kernel_fb(st)
     out['fb_x'], out['fb_v'] = _np(sp.x), _np(sp.v)
     out['fb_acc'], out['fb_sumlogdet'] = _np(met['acc']), _np(met['sumlogdet'])
+    # gradients through the reference's own autograd graph of a scalar touching
+    # x_prop, acc (both Hamiltonians), sumlogdet and the plaquette sums
+    wgt = torch.randn(*x.shape)
+    out['loss_w'] = _np(wgt)
+    loss = ((met['acc'] * (sp.x.real * wgt).flatten(1).sum(1)).sum() + met['sumlogdet'].sum()
+            + 0.01 * (met['acc'] * lat.wilson_loops(sp.x).real.sum((0, 2, 3, 4, 5))).sum())
+    named = [(n[len('networks.'):] if n.startswith('networks.') else n, p)
+             for n, p in dyn.named_parameters() if p.requires_grad]
+    grads = torch.autograd.grad(loss, [p for _, p in named] + [x], allow_unused=True)
+    out['loss'] = _np(loss)
+    for (n, _), g_ in zip(named, grads[:-1]):
+        if g_ is not None:
+            out['grad/' + n] = _np(g_)
+    out['grad_x'] = _np(grads[-1])
     np.savez_compressed(GOLD / 'su3_l2hmc_f64.npz', **out)
 
 

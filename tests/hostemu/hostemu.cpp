@@ -144,3 +144,33 @@ void emu_hmc(const C* x, const C* v, double beta, double eps, int nlf, C* xo, C*
 }
 
 }  // extern "C"
+
+// ---- adjoints --------------------------------------------------------------
+extern "C" {
+// ga = adjoint of exp at a applied to ge (n matrices)
+void emu_exp_adjoint(const C* a, const C* ge, C* ga, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    Mat3<T> A, G, R;
+    aos_get(A, a, i); aos_get(G, ge, i);
+    bool ok;
+    mat_exp_adjoint(R, A, G, ok);
+    aos_put(ga, i, R);
+  }
+}
+void emu_to_vec_adjoint(const double* gv, C* gx, size_t n) {
+  for (size_t i = 0; i < n; ++i) { Mat3<T> g; su3_to_vec_adjoint(g, gv + i * 8); aos_put(gx, i, g); }
+}
+// staple sums A_mu(n) in the boundary layout
+void emu_staples(const C* x, C* out, int nb, const int* dims) {
+  const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  std::vector<C> U;
+  to_soa(U, x, nb, l);
+  for (int b = 0; b < nb; ++b)
+    for (int mu = 0; mu < 4; ++mu)
+      for (int s = 0; s < l.V; ++s) {
+        Mat3<T> a;
+        link_times_staples<T, C, 0, false>(a, U.data(), l, b, mu, s);
+        aos_put(out, ((size_t)b * 4 + mu) * l.V + s, a);
+      }
+}
+}

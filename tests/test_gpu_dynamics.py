@@ -90,8 +90,9 @@ def test_su3_l2hmc_matches_reference(golden_dir, default_dtype):
     assert metrics['sumlogdet'].shape == (nb,)
     mc = metrics['mc_states']
     assert mc.init.x.shape == st.x.shape and mc.out.x.shape == (nb, dyn.xdim)
-    with pytest.raises(NotImplementedError, match='inference-only'):
-        dyn((st.x, st.beta))
+    # with autograd enabled the same call builds a graph (training path)
+    xout2, metrics2 = dyn((st.x, st.beta))
+    assert metrics2['acc'].requires_grad
 
 
 @pytest.mark.parametrize('tag,tol', [('f64', 1e-11), ('f32', 2e-5)])
