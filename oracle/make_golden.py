@@ -160,12 +160,15 @@ def su3_goldens(ref, torch):
             + 0.01 * (met['acc'] * lat.wilson_loops(sp.x).real.sum((0, 2, 3, 4, 5))).sum())
     named = [(n[len('networks.'):] if n.startswith('networks.') else n, p)
              for n, p in dyn.named_parameters() if p.requires_grad]
-    grads = torch.autograd.grad(loss, [p for _, p in named] + [x], allow_unused=True)
+    grads = torch.autograd.grad(loss, [p for _, p in named] + [x], allow_unused=True, retain_graph=True)
     out['loss'] = _np(loss)
     for (n, _), g_ in zip(named, grads[:-1]):
         if g_ is not None:
             out['grad/' + n] = _np(g_)
     out['grad_x'] = _np(grads[-1])
+    if ref.LatticeLoss is not None:      # conf/loss/su3.yaml: plaq 0.1 + rmse 0.1
+        lcfg = ref.cfgs.LossConfig(use_mixed_loss=False, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1)
+        out['lattice_loss'] = _np(ref.LatticeLoss(lat, lcfg)(x_init=x, x_prop=sp.x, acc=met['acc']))
     np.savez_compressed(GOLD / 'su3_l2hmc_f64.npz', **out)
 
 
@@ -248,6 +251,11 @@ def u1_goldens(ref, torch, tag: str):
             if g_ is not None:
                 out[pre + 'grad/' + n] = _np(g_)
         out[pre + 'grad_x'] = _np(grads[-1])
+        if ref.LatticeLoss is not None:  # conf/loss/default.yaml: mixed loss, charge_weight 0.01
+            lcfg = ref.cfgs.LossConfig(use_mixed_loss=True, charge_weight=0.01, rmse_weight=0.0, plaq_weight=0.0)
+            out[pre + 'lattice_loss'] = _np(ref.LatticeLoss(lat, lcfg)(x_init=x, x_prop=sp.x, acc=met['acc']))
+            lcfg2 = ref.cfgs.LossConfig(use_mixed_loss=False, charge_weight=0.05, rmse_weight=0.0, plaq_weight=0.0)
+            out[pre + 'lattice_loss2'] = _np(ref.LatticeLoss(lat, lcfg2)(x_init=x, x_prop=sp.x, acc=met['acc']))
     np.savez_compressed(GOLD / f'u1_{tag}.npz', **out)
 
 

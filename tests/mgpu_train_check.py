@@ -1,0 +1,70 @@
+"""Multi-GPU check (run under torchrun on >= 2 GPUs; not collected by pytest):
+L2HMC SU(3) train_step with chains sharded over ranks + ONE flat gradient all-reduce
+gives every rank the same parameters, equal to the single-process full-batch step.
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/mgpu_train_check.py"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from l2hmc_b200 import dist as l2d  # noqa: E402
+from test_gpu_trainer import _su3_trainer  # noqa: E402
+
+
+def main():
+    rank, world, local = l2d.init('nccl')
+    torch.cuda.set_device(local)
+    torch.set_default_dtype(torch.float64)
+    nb = 4 * world
+
+    def fresh():
+        torch.manual_seed(5)
+        np.random.seed(5)
+        return _su3_trainer(nb=nb // world)
+
+    # identical initial weights / masks on every rank (same seeds), global batch built identically
+    tr, lat = fresh()
+    torch.manual_seed(11)
+    from l2hmc_b200 import ops
+    xg = ops.su3_project(torch.complex(torch.randn(nb, 4, 4, 4, 4, 4, 3, 3, device='cuda'),
+                                       torch.randn(nb, 4, 4, 4, 4, 4, 3, 3, device='cuda')))
+    vg = ops.su3_rand_momentum(nb, [4, 4, 4, 4], 77, 0, torch.device('cuda', local))
+    beta = torch.tensor(6.0)
+
+    def grads_of(trainer, x, v):
+        trainer.dynamics.train()
+        trainer.optimizer.zero_grad(set_to_none=True)
+        from l2hmc_b200.dynamics.pytorch.dynamics import State
+        sp, met = trainer.dynamics.transition_kernel_fb(State(x, v, beta))
+        loss = trainer.loss_fn(x_init=x, x_prop=sp.x, acc=met['acc'])
+        loss.backward()
+        return loss
+
+    lo, hi = l2d.shard_bounds(nb, rank, world)
+    grads_of(tr, xg[lo:hi].contiguous(), vg[lo:hi].contiguous())
+    n = l2d.allreduce_mean_grads([p for p in tr.dynamics.parameters() if p.requires_grad])
+    sharded = torch.cat([p.grad.reshape(-1) for p in tr.dynamics.parameters() if p.grad is not None])
+    # reference: the whole batch in one process (same weights)
+    tr2, _ = fresh()
+    tr2.dynamics.config.nchains = nb
+    grads_of(tr2, xg, vg)
+    full = torch.cat([p.grad.reshape(-1) for p in tr2.dynamics.parameters() if p.grad is not None])
+    # mean over ranks of per-shard mean losses == full-batch mean loss (equal shard sizes)
+    err = float((sharded - full).abs().max() / full.abs().max())
+    gathered = [torch.empty_like(sharded) for _ in range(world)]
+    dist.all_gather(gathered, sharded)
+    same = all(torch.equal(gathered[0], g) for g in gathered)
+    if rank == 0:
+        print(f'world={world} reduced_elems={n} rel_err_vs_full_batch={err:.3e} identical_across_ranks={same}')
+    assert same and err < 1e-9, (same, err)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
