@@ -42,6 +42,7 @@ extern "C" {
 
 #define L2B_F32 0
 #define L2B_F64 1
+#define L2B_BF16 2 /* element type of net-side buffers only (vec8, s/t/q, GEMM operands) */
 
 const char* l2b_last_error(void);
 int l2b_version(void);
@@ -144,6 +145,10 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
  * coef[b] = -(beta/3) * dL/dS[b] this is dL/dx through S = -(beta/3) sum Re tr P */
 int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, const int dims[4], int dtype, void* ws,
                         size_t ws_bytes, void* stream);
+/* adjoint of l2b_su3_wilson_loops: gx from the cotangent gwloops[6, nb, T, X, Y, Z] complex of the
+ * per-site loops (the reference back-propagates lattice.py:157-199 through 18 bmm + 12 roll) */
+int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int nb, const int dims[4], int dtype,
+                             void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_vupdate w.r.t. v, force, s, t, q (gforce/gs/gt/gq may be NULL) and eps
  * (geps[nb], per chain) */
 int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
@@ -156,6 +161,16 @@ int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const flo
                              const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_to_vec: gx[nmat,3,3] from gvec8[nmat,8] */
 int l2b_su3_to_vec_bwd(const void* gvec8, void* gx, size_t nmat, int dtype, void* stream);
+
+/* group_to_vec = su3_to_vec(projectSU(x)) (dynamics.py:1154-1156, group.py:138-147) with the
+ * 8 reals per link written directly in the vnet's element type `vec_dtype`
+ * (L2B_F64 / L2B_F32 / L2B_BF16): no separate cast pass in front of the input GEMM */
+int l2b_su3_project_vec(const void* x, void* vec8, int vec_dtype, size_t nmat, int dtype, void* stream);
+/* adjoint of projectSU (cotangent gmat[nmat,3,3]) and/or of group_to_vec (cotangent
+ * gvec8[nmat,8] of type vec_dtype); the reference differentiates utils.py:227-346 with autograd,
+ * here the closed form: polar factor + 3x3 Sylvester solve (csrc/l2b_su3_math.cuh) */
+int l2b_su3_project_bwd(const void* x, const void* gmat_or_null, const void* gvec8_or_null, int vec_dtype, void* gx,
+                        size_t nmat, int dtype, void* stream);
 
 /* The two kernels of one leapfrog step on fields ALREADY in the planar layout
  * (l2b_su3_aos_to_soa), for callers that keep the state planar between steps

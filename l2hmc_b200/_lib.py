@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / 'libl2b.so'
 
-L2B_F32, L2B_F64 = 0, 1
+L2B_F32, L2B_F64, L2B_BF16 = 0, 1, 2
 
 
 class L2BError(RuntimeError):
@@ -59,6 +59,9 @@ _SIGS = {
     'l2b_su3_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_update_gauge_bwd': [_P, _P, c_double, _P, c_int, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_to_vec_bwd': [_P, _P, c_size_t, c_int, _P],
+    'l2b_su3_wilson_loops_bwd': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_project_vec': [_P, _P, c_int, c_size_t, c_int, _P],
+    'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],

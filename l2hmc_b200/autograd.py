@@ -17,6 +17,20 @@ from . import ops
 Tensor = torch.Tensor
 
 
+_BAD_FLAGS: list = []
+
+
+def check_exp_adjoint_flags() -> None:
+    """raise if any matrix-exponential adjoint of the last backward pass saw ||eps p||_F > 3
+    (one device read for the whole pass instead of a sync per x-update)"""
+    if not _BAD_FLAGS:
+        return
+    bad = int(torch.stack([b.reshape(()) for b in _BAD_FLAGS]).sum())
+    _BAD_FLAGS.clear()
+    if bad != 0:
+        raise ops.L2BError('matrix-exponential adjoint: ||eps p||_F > 3 (outside the series\' validated range)')
+
+
 def _eps_grad(geps_per_chain: Tensor, eps: Tensor):
     return geps_per_chain.sum().to(eps.dtype).reshape(eps.shape)
 
@@ -97,40 +111,43 @@ class U1VUpdate(torch.autograd.Function):
     """(v', logdet) = vupdate(v, F, s, t, q; eps, sign)   (dynamics.py:1266-1297)"""
 
     @staticmethod
-    def forward(ctx, v, force, s, t, q, eps, sign):
+    def forward(ctx, v, force, s, t, q, eps, sign, eps_value=None):
         ctx.save_for_backward(v, force, s, t, q, eps)
         ctx.sign = sign
-        out, logdet = ops.u1_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), float(eps), sign)
+        ctx.eps_value = float(eps) if eps_value is None else eps_value   # host copy: no sync per update
+        out, logdet = ops.u1_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), ctx.eps_value, sign)
         return out, logdet
 
     @staticmethod
     def backward(ctx, gout, glogdet):
         v, force, s, t, q, eps = ctx.saved_tensors
-        gv, gf, gs, gt, gq, geps = ops.u1_vupdate_bwd(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), float(eps),
-                                                      ctx.sign, gout, glogdet)
+        gv, gf, gs, gt, gq, geps = ops.u1_vupdate_bwd(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q),
+                                                      ctx.eps_value, ctx.sign, gout, glogdet)
         rs = lambda g, ref: None if (g is None or ref is None) else g.reshape(ref.shape).to(ref.dtype)  # noqa: E731
         return (gv.reshape(v.shape), gf.reshape(force.shape).to(force.dtype), rs(gs, s), rs(gt, t), rs(gq, q),
-                _eps_grad(geps, eps), None)
+                _eps_grad(geps, eps), None, None)
 
 
 class U1XUpdate(torch.autograd.Function):
     """(x', logdet) = xupdate(x, v, s, t, q; mask, eps, sign, use_ncp)   (dynamics.py:1398-1467)"""
 
     @staticmethod
-    def forward(ctx, x, v, s, t, q, mask, eps, sign, use_ncp):
+    def forward(ctx, x, v, s, t, q, mask, eps, sign, use_ncp, eps_value=None):
         ctx.save_for_backward(x, v, s, t, q, mask, eps)
         ctx.sign, ctx.use_ncp = sign, use_ncp
-        out, logdet = ops.u1_xupdate(x.detach(), v.detach(), _opt(s), _opt(t), _opt(q), mask, float(eps), sign, use_ncp)
+        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        out, logdet = ops.u1_xupdate(x.detach(), v.detach(), _opt(s), _opt(t), _opt(q), mask, ctx.eps_value, sign,
+                                     use_ncp)
         return out, logdet
 
     @staticmethod
     def backward(ctx, gout, glogdet):
         x, v, s, t, q, mask, eps = ctx.saved_tensors
-        gx, gv, gs, gt, gq, geps = ops.u1_xupdate_bwd(x.detach(), v.detach(), _opt(s), _opt(t), _opt(q), mask, float(eps),
-                                                      ctx.sign, ctx.use_ncp, gout, glogdet)
+        gx, gv, gs, gt, gq, geps = ops.u1_xupdate_bwd(x.detach(), v.detach(), _opt(s), _opt(t), _opt(q), mask,
+                                                      ctx.eps_value, ctx.sign, ctx.use_ncp, gout, glogdet)
         rs = lambda g, ref: None if (g is None or ref is None) else g.reshape(ref.shape).to(ref.dtype)  # noqa: E731
         return (gx.reshape(x.shape), gv.reshape(v.shape).to(v.dtype), rs(gs, s), rs(gt, t), rs(gq, q), None,
-                _eps_grad(geps, eps), None, None)
+                _eps_grad(geps, eps), None, None, None)
 
 
 # ---------------------------------------------------------------------------
@@ -139,65 +156,8 @@ class U1XUpdate(torch.autograd.Function):
 # its explicit `@ x^+` factor (dsdx itself is not part of the graph: no
 # create_graph, lattice/su3/pytorch/lattice.py:306).
 #
-# Two adjoints are not hand-written yet and are obtained by re-evaluating a
-# differentiable torch restatement INSIDE backward (GPU ATen ops, no CPU path):
-# projectSU (closed-form eigen/acos formula) and the per-site Wilson loops.
+# Every adjoint is a hand-written kernel (include/l2b.h, "adjoints").
 # ---------------------------------------------------------------------------
-def _project_su_torch(x: Tensor) -> Tensor:
-    """differentiable restatement of projectSU (group/su3/pytorch/utils.py:227-346)
-    used only to back-propagate through l2b_su3_project"""
-    eye = torch.eye(3, dtype=x.dtype, device=x.device)
-    t = x.mH @ x
-    t2 = t @ t
-    tr = torch.diagonal(t, dim1=-2, dim2=-1).sum(-1).real
-    p2 = torch.diagonal(t2, dim1=-2, dim2=-1).sum(-1).real
-    det = torch.linalg.det(t).real
-    tr3 = tr / 3.0
-    tr32 = tr3 * tr3
-    q = (0.5 * (p2 / 3.0 - tr32)).abs()
-    r = 0.25 * tr3 * (5.0 * tr32 - p2) - 0.5 * det
-    sq = q.sqrt()
-    isq3 = (1.0 / (q * sq)).clamp(-3e38, 3e38)
-    rsq3 = (r * isq3).clamp(-1.0, 1.0).clamp(-1.0 + 1e-12, 1.0 - 1e-12)
-    th = torch.acos(rsq3) / 3.0
-    sqc = sq * th.cos()
-    sqs = (3.0 ** 0.5) * sq * th.sin()
-    ll = tr3 + sqc
-    e0, e1, e2 = tr3 - 2.0 * sqc, ll + sqs, ll - sqs
-    s0, s1, s2 = e0.abs().sqrt(), e1.abs().sqrt(), e2.abs().sqrt()
-    u = s0 + s1 + s2
-    w = s0 * s1 * s2
-    di = 1.0 / (w * (s0 + s1) * (s0 + s2) * (s1 + s2))
-    c0 = di * (w * u * u + e0 * s0 * (e1 + e2) + e1 * s1 * (e0 + e2) + e2 * s2 * (e0 + e1))
-    c1 = -(tr * u + w) * di
-    c2 = u * di
-    rs = c0[..., None, None] * eye + c1[..., None, None] * t + c2[..., None, None] * t2
-    m = x @ rs
-    d = torch.linalg.det(m)
-    ph = -torch.atan2(d.imag, d.real) / 3.0
-    return m * torch.complex(ph.cos(), ph.sin())[..., None, None]
-
-
-def _wilson_loops_torch(x: Tensor) -> Tensor:
-    """differentiable restatement of LatticeSU3._wilson_loops (lattice.py:157-199)"""
-    ps = []
-    for u in range(1, 4):
-        for v in range(0, u):
-            xu, xv = x[:, u], x[:, v]
-            yuv = xu @ xv.roll(-1, dims=u + 1)
-            yvu = xv @ xu.roll(-1, dims=v + 1)
-            ps.append(torch.diagonal(yuv @ yvu.adjoint(), dim1=-2, dim2=-1).sum(-1))
-    return torch.stack(ps)
-
-
-def _vjp(fn, x: Tensor, g: Tensor) -> Tensor:
-    with torch.enable_grad():
-        xr = x.detach().requires_grad_(True)
-        y = fn(xr)
-        gx, = torch.autograd.grad(y, xr, grad_outputs=g.to(y.dtype))
-    return gx
-
-
 class SU3Project(torch.autograd.Function):
     """projectSU (compat_proj)"""
 
@@ -209,22 +169,23 @@ class SU3Project(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, = ctx.saved_tensors
-        return _vjp(_project_su_torch, x, g)
+        return ops.su3_project_bwd(x.detach(), gmat=g).reshape(x.shape)
 
 
 class SU3GroupToVec(torch.autograd.Function):
-    """su3_to_vec(projectSU(x)) in one kernel (vnet input packing, dynamics.py:1154-1156)"""
+    """su3_to_vec(projectSU(x)) in one kernel (vnet input packing, dynamics.py:1154-1156),
+    written in `dtype` (the nets' element type) so no cast pass precedes the input GEMM;
+    backward is the closed-form adjoint kernel (l2b_su3_project_bwd)"""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, dtype=torch.float64):
         ctx.save_for_backward(x)
-        return ops.su3_project(x.detach(), want_matrix=False, want_vec=True)
+        return ops.su3_project_vec(x.detach(), dtype)
 
     @staticmethod
     def backward(ctx, gvec):
         x, = ctx.saved_tensors
-        gy = ops.su3_to_vec_bwd(gvec)                 # adjoint of the linear vec8 map (kernel)
-        return _vjp(_project_su_torch, x, gy)         # adjoint of projectSU (torch restatement)
+        return ops.su3_project_bwd(x.detach(), gvec=gvec).reshape(x.shape), None
 
 
 class SU3WilsonLoops(torch.autograd.Function):
@@ -236,7 +197,7 @@ class SU3WilsonLoops(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, = ctx.saved_tensors
-        return _vjp(_wilson_loops_torch, x, g)
+        return ops.su3_wilson_loops_bwd(x.detach(), g).reshape(x.shape)
 
 
 class SU3Action(torch.autograd.Function):
@@ -293,34 +254,37 @@ class SU3VUpdate(torch.autograd.Function):
     """(v', logdet) = vupdate(v, F, s, t, q; eps, sign) on complex v   (dynamics.py:1266-1297)"""
 
     @staticmethod
-    def forward(ctx, v, force, s, t, q, eps, sign):
+    def forward(ctx, v, force, s, t, q, eps, sign, eps_value=None):
         ctx.save_for_backward(v, force, s, t, q, eps)
         ctx.sign = sign
-        return ops.su3_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), float(eps), sign)
+        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        return ops.su3_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), ctx.eps_value, sign)
 
     @staticmethod
     def backward(ctx, gout, glogdet):
         v, force, s, t, q, eps = ctx.saved_tensors
         gv, gf, gs, gt, gq, geps = ops.su3_vupdate_bwd(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q),
-                                                       float(eps), ctx.sign, gout, glogdet)
+                                                       ctx.eps_value, ctx.sign, gout, glogdet)
         rs = lambda g, ref: None if (g is None or ref is None) else g.reshape(ref.shape).to(ref.dtype)  # noqa: E731
         return (gv.reshape(v.shape), gf.reshape(force.shape), rs(gs, s), rs(gt, t), rs(gq, q), _eps_grad(geps, eps),
-                None)
+                None, None)
 
 
 class SU3UpdateGauge(torch.autograd.Function):
     """x' = m*x + exp(sign eps p) ((1-m)*x)   (dynamics.py:1420-1425,1468-1474)"""
 
     @staticmethod
-    def forward(ctx, x, p, eps, mask, sign):
+    def forward(ctx, x, p, eps, mask, sign, eps_value=None):
         ctx.save_for_backward(x, p, eps, mask)
         ctx.sign = sign
-        return ops.su3_update_gauge(x.detach(), p.detach(), sign * float(eps), mask=mask)
+        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        return ops.su3_update_gauge(x.detach(), p.detach(), sign * ctx.eps_value, mask=mask)
 
     @staticmethod
     def backward(ctx, g):
         x, p, eps, mask = ctx.saved_tensors
-        gx, gp, geps, bad = ops.su3_update_gauge_bwd(x.detach(), p.detach(), ctx.sign * float(eps), mask, False, g)
-        if int(bad) != 0:
-            raise ops.L2BError('matrix-exponential adjoint: ||eps p||_F > 3 (outside the series\' validated range)')
-        return gx.reshape(x.shape), gp.reshape(p.shape), _eps_grad(geps, eps) * ctx.sign, None, None
+        gx, gp, geps, bad = ops.su3_update_gauge_bwd(x.detach(), p.detach(), ctx.sign * ctx.eps_value, mask, False, g)
+        _BAD_FLAGS.append(bad)        # checked once per backward pass (check_exp_adjoint_flags), not per link update
+        if len(_BAD_FLAGS) > 1024:    # callers that never check: bound the list
+            check_exp_adjoint_flags()
+        return gx.reshape(x.shape), gp.reshape(p.shape), _eps_grad(geps, eps) * ctx.sign, None, None, None

@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include "l2b_common.cuh"
 #include "l2b_su3_site.cuh"
 
@@ -379,6 +381,19 @@ __global__ void __launch_bounds__(TS * 4, 3) k_action_grad(const C* __restrict__
   soa_store(soa_plane(G, lat, b, mu), lat.V, site, ah);
 }
 
+// adjoint of k_plaq<WRITE_LOOPS>: gx(mu,n) from the cotangent of the per-site loops
+template <int TS>
+__global__ void __launch_bounds__(TS * 4, 3) k_wloops_bwd(const C* __restrict__ U, const C* __restrict__ gw,
+                                                          C* __restrict__ G, Lat lat, int nb) {
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  if (site >= lat.V) return;
+  Mat3<T> g;
+  wloops_adjoint_link<T, C>(g, U, gw, lat, nb, b, mu, site);
+  soa_store(soa_plane(G, lat, b, mu), lat.V, site, g);
+}
+
 // adjoint of k_vupdate (force is a constant of the graph)
 __global__ void __launch_bounds__(NTL) k_vupdate_bwd(const C* __restrict__ v, const C* __restrict__ f,
                                                      const T* __restrict__ s, const T* __restrict__ t,
@@ -520,6 +535,89 @@ __global__ void __launch_bounds__(NTL) k_to_vec_bwd(const T* __restrict__ gvec8,
     su3_to_vec_adjoint(m, v);
   }
   block_store_mat<NTL>(gx, sm, m, first, n);
+}
+
+// 8 reals per link in the element type of the nets (vnet input packing): f64 / f32 / bf16
+template <typename V> struct Vec8IO;
+template <> struct Vec8IO<double> {
+  static __device__ __forceinline__ void store(double* o, const T v[8]) {
+    double2* d = reinterpret_cast<double2*>(o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) d[k] = make_double2(v[2 * k], v[2 * k + 1]);
+  }
+  static __device__ __forceinline__ void load(T v[8], const double* i) {
+    const double2* d = reinterpret_cast<const double2*>(i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const double2 w = __ldg(d + k); v[2 * k] = w.x; v[2 * k + 1] = w.y; }
+  }
+};
+template <> struct Vec8IO<float> {
+  static __device__ __forceinline__ void store(float* o, const T v[8]) {
+    float4* d = reinterpret_cast<float4*>(o);
+    d[0] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+    d[1] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+  }
+  static __device__ __forceinline__ void load(T v[8], const float* i) {
+    const float4* d = reinterpret_cast<const float4*>(i);
+    const float4 a = __ldg(d), b = __ldg(d + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <> struct Vec8IO<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* o, const T v[8]) {
+    __align__(16) __nv_bfloat162 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn((float)v[2 * k], (float)v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+  }
+  static __device__ __forceinline__ void load(T v[8], const __nv_bfloat16* i) {
+    __align__(16) __nv_bfloat162 h[4];
+    *reinterpret_cast<uint4*>(h) = __ldg(reinterpret_cast<const uint4*>(i));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); v[2 * k] = f.x; v[2 * k + 1] = f.y; }
+  }
+};
+
+// vec8 = su3_to_vec(projectSU(x)) written straight in the nets' element type
+template <typename V>
+__global__ void __launch_bounds__(NTL) k_project_vec(const C* __restrict__ x, V* __restrict__ vec8, size_t nmat) {
+  __shared__ C sm[NTL * 9];
+  const size_t first = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, nmat - first);
+  Mat3<T> m, r;
+  block_load_mat<NTL>(m, sm, x, first, n);
+  if ((int)threadIdx.x < n) {
+    project_su(r, m);
+    T v[8];
+    su3_to_vec(v, r);
+    Vec8IO<V>::store(vec8 + (first + threadIdx.x) * 8, v);
+  }
+}
+
+// adjoint of y = projectSU(x) (cotangent gmat) and/or vec8 = su3_to_vec(projectSU(x))
+// (cotangent gvec8): closed form, project_su_adjoint in l2b_su3_math.cuh
+template <typename V>
+__global__ void __launch_bounds__(NTL) k_project_bwd(const C* __restrict__ x, const C* __restrict__ gmat,
+                                                     const V* __restrict__ gvec8, C* __restrict__ gx, size_t nmat) {
+  __shared__ C sm[NTL * 9];
+  const size_t first = (size_t)blockIdx.x * NTL;
+  const int n = (int)min((size_t)NTL, nmat - first);
+  Mat3<T> m, g, r;
+  block_load_mat<NTL>(m, sm, x, first, n);
+  if (gmat != nullptr) block_load_mat<NTL>(g, sm, gmat, first, n);
+  else mat_zero(g);
+  if ((int)threadIdx.x < n) {
+    if (gvec8 != nullptr) {
+      T v[8];
+      Vec8IO<V>::load(v, gvec8 + (first + threadIdx.x) * 8);
+      Mat3<T> gv;
+      su3_to_vec_adjoint(gv, v);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { g.re[e] += gv.re[e]; g.im[e] += gv.im[e]; }
+    }
+    project_su_adjoint(r, m, g);
+  }
+  block_store_mat<NTL>(gx, sm, r, first, n);
 }
 
 // U <- exp(eps P) U on the planar layout
@@ -1321,6 +1419,20 @@ int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, con
   return launch_s2a(g, w.f1, (C*)gx, st);
 }
 
+int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int nb, const int dims[4], int dtype,
+                             void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && gwloops && gx, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  k_wloops_bwd<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, (const C*)gwloops, w.f1, g.lat, nb);
+  L2B_LAUNCHED("k_wloops_bwd");
+  return launch_s2a(g, w.f1, (C*)gx, st);
+}
+
 int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
                         int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
                         void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
@@ -1362,6 +1474,36 @@ int l2b_su3_to_vec_bwd(const void* gvec8, void* gx, size_t nmat, int dtype, void
   const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
   k_to_vec_bwd<<<nblk, NTL, 0, (cudaStream_t)stream>>>((const T*)gvec8, (C*)gx, nmat);
   L2B_LAUNCHED("k_to_vec_bwd");
+  return L2B_OK;
+}
+
+int l2b_su3_project_vec(const void* x, void* vec8, int vec_dtype, size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && vec8, L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_dtype == L2B_F64) k_project_vec<double><<<nblk, NTL, 0, st>>>((const C*)x, (double*)vec8, nmat);
+  else if (vec_dtype == L2B_F32) k_project_vec<float><<<nblk, NTL, 0, st>>>((const C*)x, (float*)vec8, nmat);
+  else if (vec_dtype == L2B_BF16) k_project_vec<__nv_bfloat16><<<nblk, NTL, 0, st>>>((const C*)x, (__nv_bfloat16*)vec8, nmat);
+  else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "vec_dtype must be L2B_F64, L2B_F32 or L2B_BF16");
+  L2B_LAUNCHED("k_project_vec");
+  return L2B_OK;
+}
+
+int l2b_su3_project_bwd(const void* x, const void* gmat_or_null, const void* gvec8_or_null, int vec_dtype, void* gx,
+                        size_t nmat, int dtype, void* stream) {
+  L2B_REQUIRE(dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "SU(3) kernels implement L2B_F64 only");
+  L2B_REQUIRE(x && gx && (gmat_or_null || gvec8_or_null), L2B_ERR_INVALID, "null pointer");
+  if (nmat == 0) return L2B_OK;
+  const unsigned nblk = (unsigned)((nmat + NTL - 1) / NTL);
+  cudaStream_t st = (cudaStream_t)stream;
+  const C* gm = (const C*)gmat_or_null;
+  if (vec_dtype == L2B_F64) k_project_bwd<double><<<nblk, NTL, 0, st>>>((const C*)x, gm, (const double*)gvec8_or_null, (C*)gx, nmat);
+  else if (vec_dtype == L2B_F32) k_project_bwd<float><<<nblk, NTL, 0, st>>>((const C*)x, gm, (const float*)gvec8_or_null, (C*)gx, nmat);
+  else if (vec_dtype == L2B_BF16) k_project_bwd<__nv_bfloat16><<<nblk, NTL, 0, st>>>((const C*)x, gm, (const __nv_bfloat16*)gvec8_or_null, (C*)gx, nmat);
+  else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "vec_dtype must be L2B_F64, L2B_F32 or L2B_BF16");
+  L2B_LAUNCHED("k_project_bwd");
   return L2B_OK;
 }
 

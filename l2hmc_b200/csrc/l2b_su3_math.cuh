@@ -420,5 +420,105 @@ L2B_HD void su3_to_vec_adjoint(Mat3<T>& g, const T v[8]) {
   g.im[4] = v[2] - s3 * v[7];
   g.im[8] = T(2) * s3 * v[7];
 }
+// inverse of a complex 3x3 matrix by cofactors (used on the Hermitian positive
+// definite I1 H^2 + I3 of the polar-factor adjoint below)
+template <typename T>
+L2B_HD void mat_inv3(Mat3<T>& inv, const Mat3<T>& a) {
+  T dr, di;
+  det3(a, dr, di);
+  const T dn = T(1) / (dr * dr + di * di);
+  const T ir = dr * dn, ii = -di * dn;          // 1 / det
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      // cofactor C_ji (transpose): rows != j, cols != i, cyclic order keeps the sign
+      const int r0 = (j + 1) % 3, r1 = (j + 2) % 3, c0 = (i + 1) % 3, c1 = (i + 2) % 3;
+      T pr, pi, qr, qi;
+      cmul_<T>(a.re[3 * r0 + c0], a.im[3 * r0 + c0], a.re[3 * r1 + c1], a.im[3 * r1 + c1], pr, pi);
+      cmul_<T>(a.re[3 * r0 + c1], a.im[3 * r0 + c1], a.re[3 * r1 + c0], a.im[3 * r1 + c0], qr, qi);
+      const T mr = pr - qr, mi = pi - qi;
+      inv.re[3 * i + j] = mr * ir - mi * ii;
+      inv.im[3 * i + j] = mr * ii + mi * ir;
+    }
+  }
+}
+
+// Adjoint of Y = projectSU(X)  (utils.py:227-346 differentiated by the reference's
+// autograd; here analytically).  With X = M H the polar decomposition (M unitary,
+// H = (X^+X)^{1/2}) and Y = M e^{-i phi/3}, phi = arg det M:
+//   G_M = G_Y conj(c) + i kappa M,  c = e^{-i phi/3},  kappa = Im(c tr(G_Y^+ M)) / 3
+//   dM  = M Omega,  H Omega + Omega H = M^+ dX - dX^+ M   (Omega anti-Hermitian)
+//   =>  G_X = M Z,  H Z + Z H = Cm := M^+ G_M - G_M^+ M.
+// The 3x3 Sylvester equation is solved in closed form: for eigenvalues x, y of H,
+//   1/(x+y) = [x^2 - xy + y^2 + I1 (y - x) + I2] / p(y),  p(H) = 2 (I1 H^2 + I3),
+// (I1, I2, I3 the invariants of H), hence
+//   Z = [Cm H^2 - H Cm H + H^2 Cm + I1 (Cm H - H Cm) + I2 Cm] (2 (I1 H^2 + I3))^{-1}.
+// Exact wherever the forward's clamps are inactive (H positive definite).
+template <typename T>
+L2B_HD void project_su_adjoint(Mat3<T>& gx, const Mat3<T>& x, const Mat3<T>& gy) {
+  Mat3<T> t, t2, r, m;
+  mat_mul<true, false, false>(t, x, x);
+  mat_mul<false, false, false>(t2, t, t);
+  T dr, di;
+  det3(t, dr, di);
+  T c0, c1, c2;
+  rsqrt_phm3_coeffs(re_trace(t), re_trace(t2), dr, c0, c1, c2);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    r.re[e] = fma(c1, t.re[e], c2 * t2.re[e]);
+    r.im[e] = fma(c1, t.im[e], c2 * t2.im[e]);
+  }
+  r.re[0] += c0; r.re[4] += c0; r.re[8] += c0;
+  mat_mul<false, false, false>(m, x, r);
+  det3(m, dr, di);
+  const T p = -atan2(di, dr) / T(3);
+  const T cp = cos(p), sp = sin(p);             // c = cp + i sp
+  // tr(G_Y^+ M) = sum conj(gy) m  = conj(tr(M G_Y^+))
+  T ur, ui;
+  trace_mul_adj(m, gy, ur, ui);
+  const T kappa = (cp * ui + sp * ur) / T(3);
+  Mat3<T> gm;
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    gm.re[e] = gy.re[e] * cp + gy.im[e] * sp - kappa * m.im[e];
+    gm.im[e] = gy.im[e] * cp - gy.re[e] * sp + kappa * m.re[e];
+  }
+  Mat3<T> g, cm, h, h2, ch, hc, num, tmp;
+  mat_mul<true, false, false>(g, m, gm);        // M^+ G_M
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      cm.re[3 * i + j] = g.re[3 * i + j] - g.re[3 * j + i];
+      cm.im[3 * i + j] = g.im[3 * i + j] + g.im[3 * j + i];
+    }
+  }
+  mat_mul<true, false, false>(h, x, m);         // H = X^+ M
+  mat_mul<false, false, false>(h2, h, h);
+  const T i1 = re_trace(h);
+  const T i2 = T(0.5) * (i1 * i1 - re_trace(h2));
+  det3(h, dr, di);
+  const T i3 = dr;
+  mat_mul<false, false, false>(ch, cm, h);
+  mat_mul<false, false, false>(hc, h, cm);
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    num.re[e] = fma(i1, ch.re[e] - hc.re[e], i2 * cm.re[e]);
+    num.im[e] = fma(i1, ch.im[e] - hc.im[e], i2 * cm.im[e]);
+  }
+  mat_mul<false, false, true>(num, ch, h);      // + Cm H^2
+  mat_mul<false, false, true>(num, h, hc);      // + H^2 Cm
+  mat_mul<false, false, false>(tmp, h, ch);     // H Cm H
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    num.re[e] -= tmp.re[e]; num.im[e] -= tmp.im[e];
+    tmp.re[e] = T(2) * i1 * h2.re[e]; tmp.im[e] = T(2) * i1 * h2.im[e];
+  }
+  tmp.re[0] += T(2) * i3; tmp.re[4] += T(2) * i3; tmp.re[8] += T(2) * i3;
+  mat_inv3(h2, tmp);                            // h2 <- (2 (I1 H^2 + I3))^{-1}
+  mat_mul<false, false, false>(tmp, num, h2);   // Z
+  mat_mul<false, false, false>(gx, m, tmp);
+}
 
 }  // namespace l2b

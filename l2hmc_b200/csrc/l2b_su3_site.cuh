@@ -217,5 +217,80 @@ L2B_HD void site_plaquette_traces(T tr_re[6], T tr_im[6], const C* U, const Lat&
     }
   }
 }
+// ---------------------------------------------------------------------------
+// Adjoint of the per-site Wilson loops w_p(n) = tr[U_u(n) U_v(n+u) U_u(n+v)^+ U_v(n)^+]
+// (p = plane (u, v), u > v, reference order) for a cotangent gw[p][b][n] (torch
+// convention dL/dRe w + i dL/dIm w).  Link (mu, n) sits in six plaquettes, two per other
+// direction nu, and with S_f / S_b the forward / backward staples of link_times_staples
+//   G_mu(n) = sum_nu [ c_f S_f^+ + c_b S_b^+ ],
+//   mu > nu: c_f = gw_p(n),       c_b = conj(gw_p(n - nu))
+//   mu < nu: c_f = conj(gw_p(n)), c_b = gw_p(n - nu),        p = plane(max, min).
+// (a real, site-independent gw gives back coef * A^+, the action's adjoint.)
+// ---------------------------------------------------------------------------
+template <typename T, typename C>
+L2B_HD void wloops_adjoint_link(Mat3<T>& g, const C* U, const C* gw, const Lat& l, int nb, int b, int mu, int site) {
+  const int V = l.V;
+  int r = site;
+  const int c3 = r % l.L[3]; r /= l.L[3];
+  const int c2 = r % l.L[2]; r /= l.L[2];
+  const int c1 = r % l.L[1]; r /= l.L[1];
+  const int c0 = r;
+  const int f0 = (c0 == l.L[0] - 1) ? -(l.L[0] - 1) * l.stride[0] : l.stride[0];
+  const int f1 = (c1 == l.L[1] - 1) ? -(l.L[1] - 1) * l.stride[1] : l.stride[1];
+  const int f2 = (c2 == l.L[2] - 1) ? -(l.L[2] - 1) * l.stride[2] : l.stride[2];
+  const int f3 = (c3 == l.L[3] - 1) ? -(l.L[3] - 1) : 1;
+  const int b0 = (c0 == 0) ? (l.L[0] - 1) * l.stride[0] : -l.stride[0];
+  const int b1 = (c1 == 0) ? (l.L[1] - 1) * l.stride[1] : -l.stride[1];
+  const int b2 = (c2 == 0) ? (l.L[2] - 1) * l.stride[2] : -l.stride[2];
+  const int b3 = (c3 == 0) ? (l.L[3] - 1) : -1;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int n_pmu = site + sel4(f0, f1, f2, f3, mu);
+  Mat3<T> a, x, y, m, st;
+  mat_zero(a);                       // a = sum conj(c) S, so that G = a^+
+  L2B_UNROLL
+  for (int k = 1; k < 4; ++k) {
+    const int nu = (mu + k) & 3;
+    const C* pnu = chain + (size_t)nu * plane_sz;
+    const int fnu = sel4(f0, f1, f2, f3, nu);
+    const int bnu = sel4(b0, b1, b2, b3, nu);
+    const int n_pnu = site + fnu;
+    const int n_mnu = site + bnu;
+    const int n_pmu_mnu = n_pmu + bnu;
+    const int hi = mu > nu ? mu : nu, lo = mu > nu ? nu : mu;
+    const int p = hi * (hi - 1) / 2 + lo;
+    const C* gwp = gw + ((size_t)p * nb + b) * V;
+    const C wf = L2B_LDG(gwp + site), wb = L2B_LDG(gwp + n_mnu);
+    // conj(c_f), conj(c_b)
+    const T cfr = wf.x, cfi = (mu > nu) ? -wf.y : wf.y;
+    const T cbr = wb.x, cbi = (mu > nu) ? wb.y : -wb.y;
+    soa_load(x, pnu, V, n_pmu);
+    soa_load(y, pmu, V, n_pnu);
+    mat_mul<false, true, false>(m, x, y);
+    soa_load(x, pnu, V, site);
+    mat_mul<false, true, false>(st, m, x);          // S_f
+    L2B_UNROLL
+    for (int e = 0; e < 9; ++e) {
+      a.re[e] += cfr * st.re[e] - cfi * st.im[e];
+      a.im[e] += cfr * st.im[e] + cfi * st.re[e];
+    }
+    soa_load(x, pnu, V, n_pmu_mnu);
+    soa_load(y, pmu, V, n_mnu);
+    mat_mul<true, true, false>(m, x, y);
+    soa_load(x, pnu, V, n_mnu);
+    mat_mul<false, false, false>(st, m, x);         // S_b
+    L2B_UNROLL
+    for (int e = 0; e < 9; ++e) {
+      a.re[e] += cbr * st.re[e] - cbi * st.im[e];
+      a.im[e] += cbr * st.im[e] + cbi * st.re[e];
+    }
+  }
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) { g.re[3 * i + j] = a.re[3 * j + i]; g.im[3 * i + j] = -a.im[3 * j + i]; }
+  }
+}
 
 }  // namespace l2b

@@ -455,7 +455,9 @@ class Dynamics(nn.Module):
             return xnet
         return self.xnet
 
-    def group_to_vec(self, x: Tensor) -> Tensor:
+    def group_to_vec(self, x: Tensor, dtype: Optional[torch.dtype] = None) -> Tensor:
+        if self._su3 and dtype is not None:
+            return self.g.group_to_vec(self.unflatten(x), dtype)
         return self.g.group_to_vec(self.unflatten(x))
 
     def vec_to_group(self, x: Tensor) -> Tensor:
@@ -473,7 +475,9 @@ class Dynamics(nn.Module):
                 return None, None, None       # dummy network: zeros -> plain kick
             vnet = self._get_vnet(step)
             dt = next(vnet.parameters()).dtype      # nets live in torch's default dtype
-            return vnet((self.group_to_vec(x).to(dt), self.group_to_vec(force).to(dt)))
+            if torch.is_autocast_enabled('cuda'):   # cfg 5: bf16 nets; the kernel writes bf16 directly
+                dt = torch.get_autocast_dtype('cuda')
+            return vnet((self.group_to_vec(x, dt), self.group_to_vec(force, dt)))
         vnet = self._get_vnet(step)
         return vnet((x, force))
 
@@ -488,7 +492,19 @@ class Dynamics(nn.Module):
         return xnet((x, v))
 
     def _eps(self, p: Tensor) -> float:
-        """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394)"""
+        """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394) as a host
+        float for the kernels' by-value argument.  All 2*nlf step sizes are read back with ONE
+        device->host copy and cached until a parameter changes (optimizer step / assign_eps),
+        instead of a synchronising float() in every link and momentum update."""
+        params = list(self.xeps) + list(self.veps)
+        key = tuple((id(q), q._version) for q in params)
+        cache = getattr(self, '_eps_cache', None)
+        if cache is None or cache[0] != key:
+            vals = sigmoid(torch.stack([q.detach().reshape(()) for q in params]).log()).tolist()
+            cache = (key, {id(q): v for q, v in zip(params, vals)})
+            self._eps_cache = cache
+        if id(p) in cache[1]:
+            return cache[1][id(p)]
         return float(sigmoid(p.detach().log()))
 
     def _eps_t(self, p: Tensor) -> Tensor:
@@ -525,9 +541,9 @@ class Dynamics(nn.Module):
         s, t, q = self._call_vnet(step, (state.x, force))
         if self._su3:
             v, logdet = ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), s, t, q,
-                                            self._eps_t(self.veps[step]).to(torch.float64), sign)
+                                            self._eps_t(self.veps[step]).to(torch.float64), sign, eps)
         else:
-            v, logdet = ag.U1VUpdate.apply(state.v, force, s, t, q, self._eps_t(self.veps[step]), sign)
+            v, logdet = ag.U1VUpdate.apply(state.v, force, s, t, q, self._eps_t(self.veps[step]), sign, eps)
         return State(state.x, v, state.beta), logdet
 
     def _update_v_fwd(self, step: int, state: State) -> tuple[State, Tensor]:
@@ -543,12 +559,12 @@ class Dynamics(nn.Module):
         if self._su3:
             # x' = m*x + exp(+-eps v) @ ((1-m)*x); xnet is never called, logdet = 0
             xn = ag.SU3UpdateGauge.apply(x, self.unflatten(state.v), self._eps_t(self.xeps[step]).to(torch.float64),
-                                         m, sign)
+                                         m, sign, eps)
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
         xm_init = self.unflatten(m) * x
         s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)
         xn, logdet = ag.U1XUpdate.apply(x, state.v, s, t, q, m, self._eps_t(self.xeps[step]), sign,
-                                        bool(self.config.use_ncp))
+                                        bool(self.config.use_ncp), eps)
         return State(x=xn, v=state.v, beta=state.beta), logdet
 
     def _update_x_fwd(self, step: int, state: State, m: Tensor, first: bool) -> tuple[State, Tensor]:

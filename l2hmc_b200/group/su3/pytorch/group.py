@@ -117,9 +117,10 @@ class SU3(Group):
         """0.5 * sum(|P|_F^2 - 8)   (group.py:125-126)"""
         return ag.SU3Kinetic.apply(p)
 
-    def group_to_vec(self, x: Tensor) -> Tensor:
-        """su3_to_vec(projectSU(x)) in one kernel   (group.py:138-147)"""
-        return ag.SU3GroupToVec.apply(x)
+    def group_to_vec(self, x: Tensor, dtype: torch.dtype = torch.float64) -> Tensor:
+        """su3_to_vec(projectSU(x)) in one kernel   (group.py:138-147); `dtype` lets the
+        caller receive the 8 reals per link directly in the nets' element type"""
+        return ag.SU3GroupToVec.apply(x, dtype)
 
     def vec_to_group(self, x: Tensor) -> Tensor:
         """projectSU(vec_to_su3(x))   (group.py:128-136)"""

@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import L2B_F32, L2B_F64, L2BError, call, dims4
+from ._lib import L2B_BF16, L2B_F32, L2B_F64, L2BError, call, dims4
 
 Tensor = torch.Tensor
 
@@ -132,6 +132,42 @@ def su3_project(x: Tensor, want_matrix: bool = True, want_vec: bool = False):
     if want_matrix and want_vec:
         return m, v
     return m if want_matrix else v
+
+
+_NET_DT = {torch.float64: L2B_F64, torch.float32: L2B_F32, torch.bfloat16: L2B_BF16}
+
+
+def _net_dt(dtype: torch.dtype) -> int:
+    if dtype not in _NET_DT:
+        raise L2BError(f'net-side buffers must be float64 / float32 / bfloat16 (got {dtype})')
+    return _NET_DT[dtype]
+
+
+def su3_project_vec(x: Tensor, dtype: torch.dtype = torch.float64) -> Tensor:
+    """group_to_vec = su3_to_vec(projectSU(x)) written in the nets' element type"""
+    x, n = _mats(x)
+    v = torch.empty((*x.shape[:-2], 8), dtype=dtype, device=x.device)
+    call('l2b_su3_project_vec', _ptr(x), _ptr(v), _net_dt(dtype), n, L2B_F64, _stream())
+    return v
+
+
+def su3_project_bwd(x: Tensor, gmat: Optional[Tensor] = None, gvec: Optional[Tensor] = None) -> Tensor:
+    """adjoint of projectSU (gmat) and/or of group_to_vec (gvec), closed form"""
+    x, n = _mats(x)
+    vdt = L2B_F64
+    if gmat is not None:
+        gmat, ng = _mats(gmat.to(torch.complex128))
+        if ng != n:
+            raise L2BError('gmat and x differ in size')
+    if gvec is not None:
+        _need_cuda(gvec)
+        vdt = _net_dt(gvec.dtype)
+        gvec = gvec.contiguous()
+        if gvec.numel() != 8 * n:
+            raise L2BError(f'gvec must have {8 * n} entries (got {gvec.numel()})')
+    gx = torch.empty_like(x)
+    call('l2b_su3_project_bwd', _ptr(x), _ptr(gmat), _ptr(gvec), vdt, _ptr(gx), n, L2B_F64, _stream())
+    return gx
 
 
 def su3_to_vec(x: Tensor) -> Tensor:
@@ -468,6 +504,19 @@ def su3_action_grad(x: Tensor, coef: Tensor) -> Tensor:
     gx = torch.empty_like(x)
     ws, n = _su3_ws(nb, dims, x.device)
     call('l2b_su3_action_grad', _ptr(x), _ptr(coef), _ptr(gx), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
+    return gx
+
+
+def su3_wilson_loops_bwd(x: Tensor, gw: Tensor) -> Tensor:
+    """adjoint of su3_wilson_loops: gw [6, nb, T, X, Y, Z] complex -> gx like x"""
+    x, nb, dims = _su3_field(x)
+    _need_cuda(gw)
+    gw = gw.to(torch.complex128).contiguous()
+    if tuple(gw.shape) != (6, nb, *dims):
+        raise L2BError(f'gw must be {(6, nb, *dims)} (got {tuple(gw.shape)})')
+    gx = torch.empty_like(x)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_wilson_loops_bwd', _ptr(x), _ptr(gw), _ptr(gx), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
     return gx
 
 

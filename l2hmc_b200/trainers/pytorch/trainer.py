@@ -12,6 +12,7 @@ from typing import Optional
 
 import torch
 
+from ... import autograd as ag
 from ... import dist as l2dist
 from ...configs import LossConfig
 from ...dynamics.pytorch.dynamics import Dynamics
@@ -74,6 +75,7 @@ class Trainer:
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
         loss.backward()
+        ag.check_exp_adjoint_flags()      # one device read per step (matrix-exp adjoint range check)
         # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks;
         # parameters without a gradient (the unused SU(3) xnet) are not communicated.
         l2dist.allreduce_mean_grads(self.optimizer.param_groups[0]['params'], self.grad_bucket_dtype)

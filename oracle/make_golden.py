@@ -172,6 +172,34 @@ def su3_goldens(ref, torch):
     np.savez_compressed(GOLD / 'su3_l2hmc_f64.npz', **out)
 
 
+def su3_adjoint_goldens(ref, torch):
+    """vector-Jacobian products the reference's autograd gives for the per-link maps
+    projectSU / group_to_vec (utils.py:227-346,394-420) and for `wilson_loops`
+    (lattice.py:157-199): what the hand-written adjoint kernels must reproduce."""
+    assert torch.get_default_dtype() == torch.float64
+    torch.manual_seed(424242)
+    g = ref.LatticeSU3(1, [2, 2, 2, 2]).g
+    n = 48
+    xg = torch.complex(torch.randn(n, 3, 3), torch.randn(n, 3, 3))               # generic
+    xs = g.projectSU(torch.complex(torch.randn(n, 3, 3), torch.randn(n, 3, 3)))
+    xs = xs + 1e-3 * torch.complex(torch.randn(n, 3, 3), torch.randn(n, 3, 3))   # near SU(3)
+    xa = g.projectTAH(torch.complex(torch.randn(n, 3, 3), torch.randn(n, 3, 3)))  # a force
+    x = torch.cat([xg, xs, xa]).detach().requires_grad_(True)
+    gmat = torch.complex(torch.randn(3 * n, 3, 3), torch.randn(3 * n, 3, 3))
+    gvec = torch.randn(3 * n, 8)
+    gx_mat, = torch.autograd.grad(g.projectSU(x), x, grad_outputs=gmat)
+    gx_vec, = torch.autograd.grad(g.group_to_vec(x), x, grad_outputs=gvec)
+    out = dict(x=_np(x), gmat=_np(gmat), gvec=_np(gvec), gx_mat=_np(gx_mat), gx_vec=_np(gx_vec))
+    shape, nb = [4, 3, 2, 5], 2
+    lat = ref.LatticeSU3(nb, shape)
+    u = lat.random().detach().requires_grad_(True)
+    w = lat.wilson_loops(u)
+    gw = torch.complex(torch.randn(*w.shape), torch.randn(*w.shape))
+    gu, = torch.autograd.grad(w, u, grad_outputs=gw)
+    out.update(wl_shape=np.array(shape), wl_x=_np(u), wl_gw=_np(gw), wl_gx=_np(gu))
+    np.savez_compressed(GOLD / 'su3_adjoint_f64.npz', **out)
+
+
 def u1_goldens(ref, torch, tag: str):
     shape, nb, beta, nlf = [8, 6], 3, 4.0, 2
     lat = ref.LatticeU1(nb, shape)
@@ -266,13 +294,15 @@ def main():
     if len(sys.argv) < 2:
         make_ref.build()
         GOLD.mkdir(parents=True, exist_ok=True)
-        for tag in ('f64', 'f32'):
+        for tag in ('f64', 'f32', 'adjoint'):
             subprocess.check_call([sys.executable, __file__, tag])
         for f in sorted(GOLD.glob('*.npz')):
             print(f'{f.name:24s} {f.stat().st_size / 1024:8.1f} KiB')
         return
     tag = sys.argv[1]
     torch.set_num_threads(4)
+    if tag == 'adjoint':       # python oracle/make_golden.py adjoint  (adds one file, leaves the others)
+        return su3_adjoint_goldens(load_reference(torch.float64), torch)
     ref = load_reference(torch.float64 if tag == 'f64' else torch.float32)
     if tag == 'f64':
         su3_goldens(ref, torch)

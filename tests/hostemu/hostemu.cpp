@@ -48,6 +48,31 @@ void emu_unary(int mode, const C* x, double scale, C* out, double* vec8, size_t 
     if (vec8) su3_to_vec(vec8 + i * 8, r);
   }
 }
+// adjoint of su3_to_vec(projectSU(x)) (gvec8 given) or of projectSU(x) (gmat given)
+void emu_project_bwd(const C* x, const C* gmat, const double* gvec8, C* gx, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    Mat3<T> m, g, r;
+    aos_get(m, x, i);
+    if (gvec8) su3_to_vec_adjoint(g, gvec8 + i * 8); else mat_zero(g);
+    if (gmat) { Mat3<T> a; aos_get(a, gmat, i); for (int e = 0; e < 9; ++e) { g.re[e] += a.re[e]; g.im[e] += a.im[e]; } }
+    project_su_adjoint(r, m, g);
+    aos_put(gx, i, r);
+  }
+}
+// adjoint of the per-site Wilson loops (k_wloops_bwd): x, gx AoS; gw [6][nb][V]
+void emu_wloops_bwd(const C* x, const C* gw, C* gx, int nb, const int* dims) {
+  const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  std::vector<C> soa, out((size_t)nb * 4 * 9 * l.V);
+  to_soa(soa, x, nb, l);
+  for (int b = 0; b < nb; ++b)
+    for (int mu = 0; mu < 4; ++mu)
+      for (int s = 0; s < l.V; ++s) {
+        Mat3<T> g;
+        wloops_adjoint_link<T, C>(g, soa.data(), gw, l, nb, b, mu, s);
+        soa_store(soa_plane(out.data(), l, b, mu), l.V, s, g);
+      }
+  to_aos(gx, out, nb, l);
+}
 void emu_from_vec(const double* vec8, C* out, size_t n) {
   for (size_t i = 0; i < n; ++i) { Mat3<T> m; vec_to_su3(m, vec8 + i * 8); aos_put(out, i, m); }
 }

@@ -259,3 +259,42 @@ def test_su3_adjoint_kernels_vs_finite_differences():
             num = (val(1e-6) - val(-1e-6)) / 2e-6
             gi = g.reshape(-1)[idx]
             assert abs(num - float(gi.real if dirn == 1.0 else gi.imag)) <= 2e-6 * max(1.0, abs(num))
+
+
+def test_su3_project_adjoint_matches_reference_autograd(golden_dir):
+    """l2b_su3_project_bwd (closed-form adjoint of projectSU / group_to_vec) against the
+    VJPs the reference's autograd gives (tests/golden/su3_adjoint_f64.npz)"""
+    from l2hmc_b200 import ops
+    ga = np.load(golden_dir / 'su3_adjoint_f64.npz')
+    x = dev(ga['x'])
+    n = x.shape[0]
+
+    def relerr(got, want):
+        want = dev(want)
+        scale = want.abs().reshape(n, -1).amax(1).clamp(min=1.0)
+        return ((got - want).abs().reshape(n, -1).amax(1) / scale)
+    e1 = relerr(ops.su3_project_bwd(x, gmat=dev(ga['gmat'])), ga['gx_mat'])
+    e2 = relerr(ops.su3_project_bwd(x, gvec=dev(ga['gvec'])), ga['gx_vec'])
+    assert float(e1.max()) < 1e-8 and float(e2.max()) < 1e-8
+    assert float(e1.median()) < 1e-12 and float(e2.median()) < 1e-12
+    # both cotangents at once == sum (the map is linear in the cotangent)
+    both = ops.su3_project_bwd(x, gmat=dev(ga['gmat']), gvec=dev(ga['gvec']))
+    assert float(relerr(both, ga['gx_mat'] + ga['gx_vec']).max()) < 1e-8
+    # typed vec8 outputs / cotangents: f32 and bf16 round-trip of the same numbers
+    v64 = ops.su3_project_vec(x, torch.float64)
+    assert torch.equal(v64, ops.su3_project(x, want_matrix=False, want_vec=True))
+    for dt, tol in ((torch.float32, 1e-6), (torch.bfloat16, 1e-2)):
+        vd = ops.su3_project_vec(x, dt)
+        assert vd.dtype == dt and float((vd.double() - v64).abs().max()) <= tol * float(v64.abs().max())
+        gv = dev(ga['gvec']).to(dt)
+        a = ops.su3_project_bwd(x, gvec=gv)
+        b = ops.su3_project_bwd(x, gvec=gv.double())
+        assert float((a - b).abs().max()) == 0.0
+
+
+def test_su3_wilson_loops_adjoint_matches_reference_autograd(golden_dir):
+    from l2hmc_b200 import ops
+    ga = np.load(golden_dir / 'su3_adjoint_f64.npz')
+    got = ops.su3_wilson_loops_bwd(dev(ga['wl_x']), dev(ga['wl_gw']))
+    want = dev(ga['wl_gx'])
+    assert float((got - want).abs().max()) < 1e-13 * max(1.0, float(want.abs().max()))

@@ -108,3 +108,31 @@ def test_trajectory_kernel_sequence(emu, g, key, xk, vk):
     assert np.allclose(h1, g[f'{key}_h1'], rtol=1e-12, atol=1e-11)
     acc = np.exp(np.minimum(h0 - h1, 0.0))
     assert maxdiff(acc, g[f'{key}_acc']) < 1e-11
+
+
+def test_project_su_adjoint_matches_reference_autograd(emu, golden_dir):
+    """closed-form adjoint of projectSU / group_to_vec (polar factor + Sylvester solve,
+    l2b_su3_math.cuh project_su_adjoint) == the reference's autograd VJPs"""
+    ga = np.load(golden_dir / 'su3_adjoint_f64.npz')
+    x = np.ascontiguousarray(ga['x'])
+    n = x.shape[0]
+    for gmat, gvec, want in ((ga['gmat'], None, ga['gx_mat']), (None, ga['gvec'], ga['gx_vec'])):
+        gx = np.empty_like(x)
+        emu.emu_project_bwd(ptr(x), ptr(None if gmat is None else np.ascontiguousarray(gmat)),
+                            ptr(None if gvec is None else np.ascontiguousarray(gvec)), ptr(gx), ctypes.c_size_t(n))
+        # the map is ill conditioned for the anti-Hermitian block (|g| up to 1e3): relative per link
+        scale = np.maximum(1.0, np.abs(want).reshape(n, -1).max(1))
+        err = np.abs(gx - want).reshape(n, -1).max(1) / scale
+        assert err.max() < 1e-8, err.max()
+        assert np.median(err) < 1e-12
+
+
+def test_wilson_loops_adjoint_matches_reference_autograd(emu, golden_dir):
+    """weighted-staple adjoint of the per-site Wilson loops (wloops_adjoint_link) == the
+    reference's autograd through lattice.py:157-199"""
+    ga = np.load(golden_dir / 'su3_adjoint_f64.npz')
+    x, gw, want = (np.ascontiguousarray(ga[k]) for k in ('wl_x', 'wl_gw', 'wl_gx'))
+    dims = (ctypes.c_int * 4)(*[int(v) for v in ga['wl_shape']])
+    gx = np.empty_like(x)
+    emu.emu_wloops_bwd(ptr(x), ptr(gw), ptr(gx), ctypes.c_int(x.shape[0]), dims)
+    assert maxdiff(gx, want) < 1e-13 * max(1.0, np.abs(want).max())
