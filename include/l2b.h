@@ -145,6 +145,11 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
  * coef[b] = -(beta/3) * dL/dS[b] this is dL/dx through S = -(beta/3) sum Re tr P */
 int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, const int dims[4], int dtype, void* ws,
                         size_t ws_bytes, void* stream);
+/* adjoint of l2b_su3_force with the reference's graph semantics (lattice.py:299-308: dsdx =
+ * autograd(S) is a constant, only the explicit `@ x.adjoint()` is attached):
+ * gx = TAH(gforce)^+ dsdx,  dsdx = -(beta/3) A^+ */
+int l2b_su3_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, const int dims[4], int dtype,
+                      void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_wilson_loops: gx from the cotangent gwloops[6, nb, T, X, Y, Z] complex of the
  * per-site loops (the reference back-propagates lattice.py:157-199 through 18 bmm + 12 roll) */
 int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int nb, const int dims[4], int dtype,

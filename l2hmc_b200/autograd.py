@@ -230,11 +230,8 @@ class SU3Force(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gf):
-        x, = ctx.saved_tensors
-        gy = ops.su3_tah(gf.contiguous())                       # TAH is self-adjoint
-        ones = torch.ones(x.shape[0], dtype=torch.float64, device=x.device)
-        dsdx = ops.su3_action_grad(x.detach(), ones * (-ctx.beta / 3.0))
-        return (gy.mH @ dsdx).reshape(x.shape), None
+        x, = ctx.saved_tensors                                  # TAH is self-adjoint
+        return ops.su3_force_bwd(x.detach(), ctx.beta, gf.contiguous()).reshape(x.shape), None
 
 
 class SU3Kinetic(torch.autograd.Function):

@@ -363,20 +363,30 @@ __global__ void __launch_bounds__(128, MINB) k_force_async(const C* __restrict__
 // ---------------------------------------------------------------------------
 // gx(mu,n) = coef[b] * A_mu(n)^+  : adjoint of the Wilson action, dS/dU = -(beta/3) A^+
 // (the staple sum of the force kernel without the final link product), planar output
+// With GF != nullptr (adjoint of the force at fixed dsdx):
+//   gx(mu,n) = TAH(GF(mu,n))^+ * (scale * A_mu(n)^+),  scale = -(beta/3)
 template <int TS>
 __global__ void __launch_bounds__(TS * 4, 3) k_action_grad(const C* __restrict__ U, C* __restrict__ G, Lat lat,
-                                                           const double* __restrict__ coef) {
+                                                           const double* __restrict__ coef, double scale,
+                                                           const C* __restrict__ GF) {
   const int b = blockIdx.y;
   const int mu = threadIdx.y;
   const int site = blockIdx.x * TS + threadIdx.x;
   if (site >= lat.V) return;
   Mat3<T> a, ah;
   link_times_staples<T, C, 0, false>(a, U, lat, b, mu, site);
-  const double c = coef[b];
+  const double c = coef ? coef[b] : scale;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) { ah.re[3 * i + j] = c * a.re[3 * j + i]; ah.im[3 * i + j] = -c * a.im[3 * j + i]; }
+  }
+  if (GF != nullptr) {
+    Mat3<T> gf, th;
+    soa_load(gf, soa_plane(GF, lat, b, mu), lat.V, site);
+    project_tah(th, gf);
+    mat_mul<true, false, false>(a, th, ah);
+    ah = a;
   }
   soa_store(soa_plane(G, lat, b, mu), lat.V, site, ah);
 }
@@ -1414,8 +1424,23 @@ int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, con
   L2B_REQUIRE(x && coef && gx, L2B_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
-  k_action_grad<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, w.f1, g.lat, coef);
+  k_action_grad<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, w.f1, g.lat, coef, 0.0, nullptr);
   L2B_LAUNCHED("k_action_grad");
+  return launch_s2a(g, w.f1, (C*)gx, st);
+}
+
+int l2b_su3_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, const int dims[4], int dtype,
+                      void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && gforce && gx, L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  L2B_TRY(launch_a2s(g, (const C*)gforce, w.f2, nullptr, st));
+  k_action_grad<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, w.f1, g.lat, nullptr, -beta / 3.0, w.f2);
+  L2B_LAUNCHED("k_action_grad<force_bwd>");
   return launch_s2a(g, w.f1, (C*)gx, st);
 }
 

@@ -507,6 +507,17 @@ def su3_action_grad(x: Tensor, coef: Tensor) -> Tensor:
     return gx
 
 
+def su3_force_bwd(x: Tensor, beta: float, gforce: Tensor) -> Tensor:
+    """gx = TAH(gforce)^+ dsdx with dsdx = -(beta/3) A^+ (one stencil kernel)"""
+    x, nb, dims = _su3_field(x)
+    gforce, _, _ = _su3_field(gforce.to(torch.complex128), dims)
+    gx = torch.empty_like(x)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_force_bwd', _ptr(x), float(beta), _ptr(gforce), _ptr(gx), nb, dims4(dims), L2B_F64, _ptr(ws), n,
+         _stream())
+    return gx
+
+
 def su3_wilson_loops_bwd(x: Tensor, gw: Tensor) -> Tensor:
     """adjoint of su3_wilson_loops: gw [6, nb, T, X, Y, Z] complex -> gx like x"""
     x, nb, dims = _su3_field(x)
