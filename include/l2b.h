@@ -197,6 +197,30 @@ int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, voi
                                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */
+/* ------------------------------------------------------------------------ */
+/* The three heads of the vnet LeapfrogLayer (network/pytorch/network.py:536-548:
+ *   s = nw.s e^{c_s} tanh(W_s z + b_s), t = nw.t (W_t z + b_t), q = nw.q e^{c_q} tanh(W_q z + b_q),
+ * each [nb, xdim]) and Dynamics._update_v_fwd/_bwd (dynamics.py:1266-1297) that consumes them,
+ * as ONE kernel: bf16 tcgen05.mma with fp32 accumulators in TMEM, weights streamed by TMA bulk
+ * copies from a pre-packed bf16 image, epilogue straight out of TMEM.  s, t, q never reach HBM. */
+/* bytes of the packed image / of the logdet workspace */
+size_t l2b_vnet_heads_packed_bytes(int xdim, int hidden);
+size_t l2b_vnet_heads_ws_bytes(int nb, int xdim);
+/* W_s, W_t, W_q: [xdim, hidden] row-major (nn.Linear.weight) of w_dtype (L2B_F32/F64/BF16) ->
+ * bf16 UMMA tile image (also the fp32 -> bf16 cast autocast would do); redo when weights change */
+int l2b_vnet_pack_heads(const void* w_s, const void* w_t, const void* w_q, int w_dtype, void* packed, int xdim,
+                        int hidden, void* stream);
+/* z: bf16 [nb, hidden] (output of the hidden stack); bias_*: f32 [xdim]; scale_s = nw.s e^{c_s},
+ * scale_q = nw.q e^{c_q}: f32 [xdim]; scale_t = nw.t; v, force, v_out: complex128 [nb, xdim];
+ * logdet[nb] (NULL: skip); stq_or_null: f32 [3, nb, xdim] dump of (s, t, q) for the backward pass
+ * and for tests.  hidden % 8 == 0 and hidden <= 256, else L2B_ERR_UNSUPPORTED. */
+int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                          const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                          const void* v, const void* force, double eps, int sign, void* v_out, double* logdet,
+                          float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* U(1), x[nb, 2, T, X] real angles                                          */
 /* ------------------------------------------------------------------------ */
 size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype);

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_int, c_size_t, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p, POINTER
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -67,6 +67,9 @@ _SIGS = {
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
     'l2b_set_option': [c_char_p, c_int],
+    'l2b_vnet_pack_heads': [_P, _P, _P, c_int, _P, c_int, c_int, _P],
+    'l2b_su3_heads_vupdate': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, c_int, _P, _P, _P, c_int, c_int,
+                              c_int, _P, c_size_t, _P],
     'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_observables': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_force': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
@@ -88,6 +91,8 @@ _RES = {
     'l2b_launch_count': ([], c_uint64),
     'l2b_su3_ws_bytes': ([c_int, _DIMS, c_int], c_size_t),
     'l2b_u1_ws_bytes': ([c_int, c_int, c_int, c_int], c_size_t),
+    'l2b_vnet_heads_packed_bytes': ([c_int, c_int], c_size_t),
+    'l2b_vnet_heads_ws_bytes': ([c_int, c_int], c_size_t),
 }
 
 EXPORTS = sorted(list(_SIGS) + list(_RES))

@@ -267,6 +267,42 @@ class SU3VUpdate(torch.autograd.Function):
                 None, None)
 
 
+class SU3HeadsVUpdate(torch.autograd.Function):
+    """(v', logdet) = vupdate(v, F, heads(z); eps, sign) with the three head GEMMs on the
+    tensor cores and s, t, q kept on chip (l2b_su3_heads_vupdate, csrc/l2b_vnet.cu).
+    backward re-materialises s, t, q with torch (library GEMMs, same autocast state as the
+    forward), runs the hand-written v-update adjoint on them and back-propagates the three
+    cotangents through that small graph -- the activations are never stored."""
+
+    @staticmethod
+    def forward(ctx, z, v, force, eps, sign, eps_value, net, *head_params):
+        ctx.save_for_backward(z, v, force, eps, *head_params)
+        ctx.sign, ctx.net = sign, net
+        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        ctx.autocast = (torch.is_autocast_enabled('cuda'), torch.get_autocast_dtype('cuda'))
+        out, logdet = ops.su3_heads_vupdate(z.detach(), net.heads_pack(), v.detach(), force.detach(), ctx.eps_value,
+                                            sign)
+        return out, logdet
+
+    @staticmethod
+    def backward(ctx, gout, glogdet):
+        z, v, force, eps = ctx.saved_tensors[:4]
+        net = ctx.net
+        with torch.enable_grad(), torch.autocast('cuda', enabled=ctx.autocast[0], dtype=ctx.autocast[1]):
+            zr = z.detach().requires_grad_(True)
+            s, t, q = net.heads(zr)
+        gv, gf, gs, gt, gq, geps = ops.su3_vupdate_bwd(v.detach(), force.detach(), s.detach(), t.detach(), q.detach(),
+                                                       ctx.eps_value, ctx.sign, gout, glogdet)
+        params = [p for p in net.head_params() if p.requires_grad]
+        grads = torch.autograd.grad([s, t, q], [zr] + params,
+                                    [gs.reshape(s.shape).to(s.dtype), gt.reshape(t.shape).to(t.dtype),
+                                     gq.reshape(q.shape).to(q.dtype)], allow_unused=True)
+        it = iter(grads[1:])
+        gparams = tuple(next(it) if p.requires_grad else None for p in net.head_params())
+        return (grads[0], gv.reshape(v.shape), gf.reshape(force.shape), _eps_grad(geps, eps), None, None, None,
+                *gparams)
+
+
 class SU3UpdateGauge(torch.autograd.Function):
     """x' = m*x + exp(sign eps p) ((1-m)*x)   (dynamics.py:1420-1425,1468-1474)"""
 

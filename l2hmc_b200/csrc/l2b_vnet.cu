@@ -1,0 +1,400 @@
+// l2b_vnet.cu -- tensor-core side of the L2HMC momentum update (sm_100a, tcgen05).
+//
+// k_heads_vupdate fuses the three output heads of the vnet `LeapfrogLayer`
+// (reference network/pytorch/network.py:536-548: scale / transl / transf) with
+// the momentum-update epilogue that consumes them (dynamics.py:1266-1297):
+//
+//   s = a_s tanh(W_s z + b_s),  t = a_t (W_t z + b_t),  q = a_q tanh(W_q z + b_q)      [nb, xdim] each
+//   fwd: v' = e^{eps s/2} v - eps/2 (F e^{eps q} + t)     logdet = sum  eps s/2
+//   bwd: v' = e^{-eps s/2} (v + eps/2 (F e^{eps q} + t))  logdet = sum -eps s/2
+//
+// so that s, t, q (3 x nb x xdim numbers) never exist in HBM: the only field-sized
+// traffic is v (r), F (r), v' (w) plus the bf16 weights.
+//
+// GEMM shape: the xdim outputs are the UMMA M axis (128 per CTA), the chains are the
+// UMMA N axis (64 per CTA), K = hidden units.  One CTA = one (128-column, 64-chain) tile:
+//   * the z tile (B operand, all of K) is written to shared memory in the canonical
+//     no-swizzle K-major core-matrix layout by the CTA's threads;
+//   * the weight tile (A operand) streams in with 1-D TMA bulk copies
+//     (cp.async.bulk ... mbarrier::complete_tx) from a PRE-PACKED bf16 image whose 16 KB
+//     stages are byte-for-byte the shared-memory layout (packed once per optimizer step
+//     by k_pack_heads, which is also the fp32 -> bf16 cast);
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, M128 N64 K16) into three
+//     fp32 accumulators in TMEM (3 x 64 columns), tcgen05.commit recycles the stages;
+//   * the epilogue reads TMEM with tcgen05.ld (lane = xdim column, column = chain), so the
+//     v / F / v' accesses of a warp are 512 contiguous bytes per chain.
+// Two CTAs are resident per SM (98 KB smem, 256 TMEM columns each): one CTA's HBM-bound
+// epilogue overlaps the other's weight streaming and MMAs.
+#include <cuda_bf16.h>
+
+#include "l2b_common.cuh"
+
+namespace l2b {
+namespace {
+
+constexpr int BM = 128;                       // xdim columns per tile (UMMA M)
+constexpr int BN = 64;                        // chains per tile (UMMA N)
+constexpr int KC = 64;                        // K per pipeline stage
+constexpr int NST = 4;                        // weight stages in flight
+constexpr int A_STAGE_BYTES = BM * KC * 2;    // 16 KB
+constexpr int KMAX = 256;                     // largest (padded) hidden size with z resident
+constexpr int TMEM_COLS = 256;                // 3 x BN = 192 accumulator columns, power of two
+constexpr int NTH = 128;
+
+struct Smem {
+  alignas(128) unsigned char a[NST][A_STAGE_BYTES];     // weight ring
+  alignas(128) unsigned char b[BN * KMAX * 2];          // z tile, [kcore][chain][8]
+  alignas(8) unsigned long long full[NST];
+  unsigned long long empty[NST];
+  unsigned long long accum;
+  float ld[NTH / 32][BN];                               // logdet partials per warp
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// shared-memory matrix descriptor, no swizzle, K-major canonical layout:
+// core matrix = 8 rows x 16 B contiguous; LBO = byte step between core matrices along K,
+// SBO = byte step between 8-row groups along M/N; bits 46-47 = 1 (sm_100 descriptor version)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = BN
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// ---------------------------------------------------------------------------
+// weight packing: W_h[xdim, H] (nn.Linear layout, f64 / f32 / bf16) -> bf16 image
+//   packed[tile][head][kcore][row 0..127][8],  kcore < KP/8,  zero padded rows / columns
+// one thread per 16-byte chunk
+// ---------------------------------------------------------------------------
+template <typename W>
+__device__ __forceinline__ float w_load(const W* p) { return (float)*p; }
+template <>
+__device__ __forceinline__ float w_load<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename W>
+__global__ void __launch_bounds__(256) k_pack_heads(const W* __restrict__ w0, const W* __restrict__ w1,
+                                                    const W* __restrict__ w2, uint4* __restrict__ packed, int xdim,
+                                                    int H, int KP, size_t nchunks) {
+  const size_t id = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (id >= nchunks) return;
+  const int r = (int)(id % BM);
+  size_t rest = id / BM;
+  const int kcore = (int)(rest % (KP / 8));
+  rest /= (KP / 8);
+  const int head = (int)(rest % 3);
+  const size_t tile = rest / 3;
+  const size_t row = tile * BM + r;
+  const W* w = head == 0 ? w0 : (head == 1 ? w1 : w2);
+  __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kcore * 8 + e;
+    h[e] = __float2bfloat16((row < (size_t)xdim && k < H) ? w_load(w + row * H + k) : 0.0f);
+  }
+  packed[id] = *reinterpret_cast<const uint4*>(h);
+}
+
+// ---------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------
+struct HeadsArgs {
+  const __nv_bfloat16* z;       // [nb, H]
+  const unsigned char* packed;  // k_pack_heads image
+  const float* bias[3];         // [xdim] each
+  const float* scale_s;         // [xdim]  nw.s * exp(coeff_s)
+  const float* scale_q;         // [xdim]  nw.q * exp(coeff_q)
+  float scale_t;                // nw.t
+  const double2* v;             // [nb, xdim] complex128
+  const double2* f;
+  double2* out;
+  double* part;                 // [nb, ntiles] logdet partials (may be null)
+  float* stq;                   // optional [3, nb, xdim] fp32 dump of (s, t, q)
+  double eps;
+  int sign, nb, xdim, H, KP, ntiles;
+};
+
+__global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nct = (a.nb + BN - 1) / BN;
+  const int tile = blockIdx.x / nct;          // chain tiles of one column tile are adjacent:
+  const int chain0 = (blockIdx.x % nct) * BN;  // they run together and share the weights in L2
+  const int NKC = a.KP / KC;
+  const int total = 3 * NKC;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
+    mbar_init(smem_u32(&sm.accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
+                 "n"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // z tile -> canonical K-major image [kcore][chain][8 bf16]; chains >= nb and k >= H are zero
+  {
+    const int nchunk = BN * (a.KP / 8);
+    uint4* bimg = reinterpret_cast<uint4*>(sm.b);
+    for (int idx = tid; idx < nchunk; idx += NTH) {
+      const int c = idx % BN, i = idx / BN;
+      const int b = chain0 + c;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (b < a.nb && i * 8 < a.H) val = __ldg(reinterpret_cast<const uint4*>(a.z + (size_t)b * a.H + i * 8));
+      bimg[idx] = val;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  if (tid == 0) {
+    // ---- TMA producer + MMA issuer (one thread) ------------------------------------------
+    const unsigned char* wsrc = a.packed + (size_t)tile * total * A_STAGE_BYTES;
+    const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
+    const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;   // K step of each image; 8-row groups are adjacent
+    for (int s = 0; s < NST && s < total; ++s) {
+      mbar_expect_tx(smem_u32(&sm.full[s]), A_STAGE_BYTES);
+      bulk_g2s(a_base + s * A_STAGE_BYTES, wsrc + (size_t)s * A_STAGE_BYTES, A_STAGE_BYTES, smem_u32(&sm.full[s]));
+    }
+    for (int s = 0; s < total; ++s) {
+      const int slot = s % NST;
+      const uint32_t ph = (uint32_t)(s / NST) & 1u;
+      mbar_wait(smem_u32(&sm.full[slot]), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int head = s / NKC, kc = s % NKC;
+#pragma unroll
+      for (int kk = 0; kk < KC / 16; ++kk) {
+        const uint64_t ad = umma_desc(a_base + slot * A_STAGE_BYTES + (2 * kk) * (BM * 16), a_lbo, sbo);
+        const uint64_t bd = umma_desc(b_base + (2 * (kc * (KC / 16) + kk)) * (BN * 16), b_lbo, sbo);
+        umma_f16(tmem + head * BN, ad, bd, kIdesc, (kc | kk) != 0 ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&sm.empty[slot]));         // arrives when these MMAs have read the stage
+      if (s + NST < total) {
+        mbar_wait(smem_u32(&sm.empty[slot]), ph);
+        mbar_expect_tx(smem_u32(&sm.full[slot]), A_STAGE_BYTES);
+        bulk_g2s(a_base + slot * A_STAGE_BYTES, wsrc + (size_t)(s + NST) * A_STAGE_BYTES, A_STAGE_BYTES,
+                 smem_u32(&sm.full[slot]));
+      }
+    }
+    umma_commit(smem_u32(&sm.accum));                  // all three accumulators complete
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM lane = xdim column, TMEM column = chain -----------------------------
+  mbar_wait(smem_u32(&sm.accum), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const size_t j = (size_t)tile * BM + tid;
+  const bool col_ok = j < (size_t)a.xdim;
+  const float bs = col_ok ? __ldg(a.bias[0] + j) : 0.f, bt = col_ok ? __ldg(a.bias[1] + j) : 0.f,
+              bq = col_ok ? __ldg(a.bias[2] + j) : 0.f;
+  const float as = col_ok ? __ldg(a.scale_s + j) : 0.f, aq = col_ok ? __ldg(a.scale_q + j) : 0.f, at = a.scale_t;
+  const float epsf = (float)a.eps, hs = 0.5f * (float)a.sign * epsf;
+  const double he = 0.5 * a.eps;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    if (chain0 + c0 >= a.nb) {                          // uniform: nothing left in this tile
+      for (int c = 0; c < 16; ++c) if (lane == 0) sm.ld[warp][c0 + c] = 0.f;
+      continue;
+    }
+    uint32_t rs[16], rt[16], rq[16];
+    tmem_ld16(trow + 0 * BN + c0, rs);
+    tmem_ld16(trow + 1 * BN + c0, rt);
+    tmem_ld16(trow + 2 * BN + c0, rq);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    float lj[16];
+    double2 vv[16], ff[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int b = chain0 + c0 + c;
+      const bool ok = col_ok && b < a.nb;
+      vv[c] = ok ? __ldg(a.v + (size_t)b * a.xdim + j) : make_double2(0., 0.);
+      ff[c] = ok ? __ldg(a.f + (size_t)b * a.xdim + j) : make_double2(0., 0.);
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const int b = chain0 + c0 + c;
+      const bool ok = col_ok && b < a.nb;
+      const float s = as * tanhf(__uint_as_float(rs[c]) + bs);
+      const float t = at * (__uint_as_float(rt[c]) + bt);
+      const float q = aq * tanhf(__uint_as_float(rq[c]) + bq);
+      const float logjac = hs * s;                      // sign * eps * s / 2
+      lj[c] = ok ? logjac : 0.f;
+      const double es = (double)expf(logjac), eq = (double)expf(epsf * q);
+      const double fr = fma(ff[c].x, eq, (double)t), fi = ff[c].y * eq;
+      double2 o;
+      if (a.sign > 0) { o.x = es * vv[c].x - he * fr; o.y = es * vv[c].y - he * fi; }
+      else { o.x = es * (vv[c].x + he * fr); o.y = es * (vv[c].y + he * fi); }
+      if (ok) {
+        a.out[(size_t)b * a.xdim + j] = o;
+        if (a.stq != nullptr) {
+          const size_t plane = (size_t)a.nb * a.xdim, at_ = (size_t)b * a.xdim + j;
+          a.stq[at_] = s; a.stq[plane + at_] = t; a.stq[2 * plane + at_] = q;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float x = lj[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0) sm.ld[warp][c0 + c] = x;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (a.part != nullptr && tid < BN && chain0 + tid < a.nb) {
+    const double x = (double)sm.ld[0][tid] + (double)sm.ld[1][tid] + (double)sm.ld[2][tid] + (double)sm.ld[3][tid];
+    a.part[(size_t)(chain0 + tid) * a.ntiles + tile] = x;
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// fixed-order sum of the per-tile partials: out[b] = sum_tile part[b][tile]
+__global__ void __launch_bounds__(256) k_sum_rows(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double red[8];
+  const double* row = part + (size_t)blockIdx.x * n;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) s += row[k];
+  s = block_sum<256>(s, red, threadIdx.x);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+}  // namespace
+}  // namespace l2b
+
+using namespace l2b;
+
+extern "C" {
+
+size_t l2b_vnet_heads_packed_bytes(int xdim, int hidden) {
+  if (xdim <= 0 || hidden <= 0) return 0;
+  const size_t ntiles = ((size_t)xdim + BM - 1) / BM;
+  const size_t KP = ((size_t)hidden + KC - 1) / KC * KC;
+  return ntiles * 3 * KP * BM * 2;
+}
+
+size_t l2b_vnet_heads_ws_bytes(int nb, int xdim) {
+  if (xdim <= 0 || nb <= 0) return 0;
+  const size_t ntiles = ((size_t)xdim + BM - 1) / BM;
+  return align_up((size_t)nb * ntiles * sizeof(double), 256);
+}
+
+int l2b_vnet_pack_heads(const void* w_s, const void* w_t, const void* w_q, int w_dtype, void* packed, int xdim,
+                        int hidden, void* stream) {
+  L2B_REQUIRE(w_s && w_t && w_q && packed, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(xdim > 0 && hidden > 0, L2B_ERR_INVALID, "xdim and hidden must be positive");
+  L2B_REQUIRE(((uintptr_t)packed & 15) == 0, L2B_ERR_INVALID, "packed image must be 16-byte aligned");
+  const int KP = (hidden + KC - 1) / KC * KC;
+  const size_t nchunks = l2b_vnet_heads_packed_bytes(xdim, hidden) / 16;
+  const unsigned nblk = (unsigned)((nchunks + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w_dtype == L2B_F32)
+    k_pack_heads<float><<<nblk, 256, 0, st>>>((const float*)w_s, (const float*)w_t, (const float*)w_q, (uint4*)packed, xdim, hidden, KP, nchunks);
+  else if (w_dtype == L2B_F64)
+    k_pack_heads<double><<<nblk, 256, 0, st>>>((const double*)w_s, (const double*)w_t, (const double*)w_q, (uint4*)packed, xdim, hidden, KP, nchunks);
+  else if (w_dtype == L2B_BF16)
+    k_pack_heads<__nv_bfloat16><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)w_s, (const __nv_bfloat16*)w_t, (const __nv_bfloat16*)w_q, (uint4*)packed, xdim, hidden, KP, nchunks);
+  else
+    L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "w_dtype must be L2B_F32, L2B_F64 or L2B_BF16");
+  L2B_LAUNCHED("k_pack_heads");
+  return L2B_OK;
+}
+
+int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                          const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                          const void* v, const void* force, double eps, int sign, void* v_out, double* logdet,
+                          float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(z && packed && bias_s && bias_t && bias_q && scale_s && scale_q && v && force && v_out,
+              L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "nb and xdim must be positive");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  L2B_REQUIRE(hidden > 0 && hidden % 8 == 0 && hidden <= KMAX, L2B_ERR_UNSUPPORTED,
+              "fused heads kernel needs hidden %% 8 == 0 and hidden <= %d (got %d)", KMAX, hidden);
+  L2B_REQUIRE((((uintptr_t)z | (uintptr_t)packed | (uintptr_t)v | (uintptr_t)force | (uintptr_t)v_out) & 15) == 0,
+              L2B_ERR_INVALID, "z, packed, v, force, v_out must be 16-byte aligned");
+  HeadsArgs a;
+  a.z = (const __nv_bfloat16*)z;
+  a.packed = (const unsigned char*)packed;
+  a.bias[0] = bias_s; a.bias[1] = bias_t; a.bias[2] = bias_q;
+  a.scale_s = scale_s; a.scale_q = scale_q; a.scale_t = scale_t;
+  a.v = (const double2*)v; a.f = (const double2*)force; a.out = (double2*)v_out;
+  a.stq = stq_or_null;
+  a.eps = eps; a.sign = sign; a.nb = nb; a.xdim = xdim; a.H = hidden;
+  a.KP = (hidden + KC - 1) / KC * KC;
+  a.ntiles = (xdim + BM - 1) / BM;
+  a.part = nullptr;
+  if (logdet) {
+    L2B_REQUIRE(ws != nullptr && ws_bytes >= l2b_vnet_heads_ws_bytes(nb, xdim), L2B_ERR_WORKSPACE,
+                "workspace too small for the logdet partials");
+    a.part = (double*)ws;
+  }
+  const int nct = (nb + BN - 1) / BN;
+  const size_t nblk = (size_t)a.ntiles * nct;
+  L2B_REQUIRE(nblk < (1ull << 31), L2B_ERR_UNSUPPORTED, "grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_CUDA(cudaFuncSetAttribute((const void*)k_heads_vupdate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(Smem)));
+  k_heads_vupdate<<<(unsigned)nblk, NTH, sizeof(Smem), st>>>(a);
+  L2B_LAUNCHED("k_heads_vupdate");
+  if (logdet) {
+    k_sum_rows<<<nb, 256, 0, st>>>(a.part, a.ntiles, logdet);
+    L2B_LAUNCHED("k_sum_rows");
+  }
+  return L2B_OK;
+}
+
+}  // extern "C"

@@ -534,10 +534,31 @@ class Dynamics(nn.Module):
         state, logdet = self._update_v_bwd(step_r, state)
         return state, sumlogdet + logdet
 
+    def _fused_heads(self, vnet) -> bool:
+        """SU(3) v-update with the vnet heads on the tensor cores (bf16 tcgen05, fp32
+        accumulate) fused with the update itself.  `tensor_core_heads`: 'auto' (default) =
+        whenever the nets already run in bf16 (autocast, BASELINE cfg 5), 'always', 'never'."""
+        mode = getattr(self, 'tensor_core_heads', 'auto')
+        if mode == 'never' or not (self._su3 and self._networks_built):
+            return False
+        if not ops.heads_supported(vnet.units[-1]):
+            return False
+        if mode == 'always':
+            return True
+        return torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
+
     def _update_v(self, step: int, state: State, sign: int) -> tuple[State, Tensor]:
         """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel"""
         force = self.grad_potential(state.x, state.beta)
         eps = self._eps(self.veps[step])
+        if self._su3 and self._networks_built and self._fused_heads(self._get_vnet(step)):
+            vnet = self._get_vnet(step)
+            dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
+            z = vnet.hidden((self.group_to_vec(state.x, dt), self.group_to_vec(force, dt)))
+            v, logdet = ag.SU3HeadsVUpdate.apply(z, self.unflatten(state.v), self.unflatten(force),
+                                                 self._eps_t(self.veps[step]).to(torch.float64), sign, eps, vnet,
+                                                 *vnet.head_params())
+            return State(state.x, v, state.beta), logdet
         s, t, q = self._call_vnet(step, (state.x, force))
         if self._su3:
             v, logdet = ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), s, t, q,

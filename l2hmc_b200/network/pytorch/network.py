@@ -184,7 +184,8 @@ class LeapfrogLayer(nn.Module):
     def set_net_weight(self, net_weight: NetWeight):
         self.nw = net_weight
 
-    def forward(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor]:
+    def hidden(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
+        """everything in front of the three output heads (network.py:536-545)"""
         z = self.input_layer(inputs)
         for layer in self.hidden_layers:
             z = self.activation_fn(layer(z))
@@ -192,10 +193,38 @@ class LeapfrogLayer(nn.Module):
             z = self.dropout(z)
         if self.net_config.use_batch_norm:
             z = self.batch_norm(z)
+        return z
+
+    def heads(self, z: Tensor) -> tuple[Tensor, Tensor, Tensor]:
+        """network.py:546-548"""
         s = self.nw.s * self.scale(z)
         t = self.nw.t * self.transl(z)
         q = self.nw.q * self.transf(z)
         return s, t, q
+
+    def forward(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor]:
+        return self.heads(self.hidden(inputs))
+
+    def head_params(self) -> tuple[Tensor, ...]:
+        return (self.scale.layer.weight, self.scale.layer.bias, self.scale.coeff,
+                self.transl.weight, self.transl.bias,
+                self.transf.layer.weight, self.transf.layer.bias, self.transf.coeff)
+
+    def heads_pack(self):
+        """bf16 UMMA tile image of the three head matrices + epilogue constants for the fused
+        tcgen05 kernel (ops.su3_heads_vupdate); rebuilt only when a head parameter or the net
+        weights changed (optimizer step, load_state_dict, set_net_weight)"""
+        from ... import ops
+        ps = self.head_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q)
+        cached = getattr(self, '_heads_pack', None)
+        if cached is None or cached[0] != key:
+            ws, bs, cs, wt, bt, wq, bq, cq = ps
+            with torch.no_grad():
+                pack = ops.vnet_pack_heads(ws, wt, wq, bs, bt, bq, cs, cq, self.nw.s, self.nw.t, self.nw.q)
+            cached = (key, pack)
+            self._heads_pack = cached
+        return cached[1]
 
 
 def get_and_call_network(xshape: Sequence[int], *, network_config: NetworkConfig, is_xnet: bool, group,

@@ -573,3 +573,67 @@ def su3_to_vec_bwd(gvec: Tensor) -> Tensor:
     gx = torch.empty((*gvec.shape[:-1], 3, 3), dtype=torch.complex128, device=gvec.device)
     call('l2b_su3_to_vec_bwd', _ptr(gvec), _ptr(gx), gvec.numel() // 8, L2B_F64, _stream())
     return gx
+
+
+# ---------------------------------------------------------------------------
+# vnet output heads on the tensor cores, fused with the momentum update
+# ---------------------------------------------------------------------------
+class HeadsPack:
+    """bf16 UMMA tile image of (W_s, W_t, W_q) plus the per-column epilogue constants
+    (include/l2b.h, l2b_vnet_pack_heads)"""
+    __slots__ = ('packed', 'bias', 'scale_s', 'scale_q', 'scale_t', 'xdim', 'hidden')
+
+    def __init__(self, packed, bias, scale_s, scale_q, scale_t, xdim, hidden):
+        self.packed, self.bias, self.scale_s, self.scale_q = packed, bias, scale_s, scale_q
+        self.scale_t, self.xdim, self.hidden = float(scale_t), int(xdim), int(hidden)
+
+
+def heads_supported(hidden: int) -> bool:
+    return hidden % 8 == 0 and 0 < hidden <= 256
+
+
+def vnet_pack_heads(w_s: Tensor, w_t: Tensor, w_q: Tensor, b_s: Tensor, b_t: Tensor, b_q: Tensor,
+                    coeff_s: Tensor, coeff_q: Tensor, nw_s: float = 1.0, nw_t: float = 1.0,
+                    nw_q: float = 1.0) -> HeadsPack:
+    """weights [xdim, hidden] as nn.Linear stores them; coeff_* are ScaledTanh.coeff [1, xdim]"""
+    _need_cuda(w_s, w_t, w_q)
+    xdim, hidden = int(w_s.shape[0]), int(w_s.shape[1])
+    if w_t.shape != w_s.shape or w_q.shape != w_s.shape or w_t.dtype != w_s.dtype or w_q.dtype != w_s.dtype:
+        raise L2BError('head weights must share shape and dtype')
+    ws_, wt_, wq_ = (w.detach().contiguous() for w in (w_s, w_t, w_q))
+    nbytes = int(_lib._lib.l2b_vnet_heads_packed_bytes(xdim, hidden))
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w_s.device)
+    call('l2b_vnet_pack_heads', _ptr(ws_), _ptr(wt_), _ptr(wq_), _net_dt(w_s.dtype), _ptr(packed), xdim, hidden,
+         _stream())
+    f32 = lambda a: a.detach().to(torch.float32).reshape(-1).contiguous()  # noqa: E731
+    bias = torch.stack([f32(b_s), f32(b_t), f32(b_q)]).contiguous()
+    scale_s = (float(nw_s) * f32(coeff_s).exp()).contiguous()
+    scale_q = (float(nw_q) * f32(coeff_q).exp()).contiguous()
+    return HeadsPack(packed, bias, scale_s, scale_q, nw_t, xdim, hidden)
+
+
+def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps: float, sign: int,
+                      want_stq: bool = False):
+    """(v', logdet[, stq]) with s, t, q = heads(z) never materialised (unless want_stq:
+    f32 [3, nb, xdim])"""
+    _need_cuda(z, v, force)
+    if z.dtype != torch.bfloat16:
+        z = z.to(torch.bfloat16)
+    z = z.contiguous()
+    nb = int(z.shape[0])
+    if int(z.shape[1]) != pack.hidden:
+        raise L2BError(f'z has {z.shape[1]} features, the packed heads expect {pack.hidden}')
+    if v.dtype != torch.complex128 or force.dtype != torch.complex128:
+        raise L2BError('v and force must be complex128')
+    v, force = v.contiguous(), force.contiguous()
+    if v.numel() != nb * pack.xdim or force.numel() != nb * pack.xdim:
+        raise L2BError(f'v / force must have {nb * pack.xdim} complex entries')
+    out = torch.empty_like(v)
+    logdet = torch.empty(nb, dtype=torch.float64, device=v.device)
+    stq = torch.empty((3, nb, pack.xdim), dtype=torch.float32, device=v.device) if want_stq else None
+    nws = int(_lib._lib.l2b_vnet_heads_ws_bytes(nb, pack.xdim))
+    ws = _workspace(nws, v.device)
+    call('l2b_su3_heads_vupdate', _ptr(z), _ptr(pack.packed), _ptr(pack.bias[0]), _ptr(pack.bias[1]),
+         _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), float(eps),
+         int(sign), _ptr(out), _ptr(logdet), _ptr(stq), nb, pack.xdim, pack.hidden, _ptr(ws), nws, _stream())
+    return (out, logdet, stq) if want_stq else (out, logdet)

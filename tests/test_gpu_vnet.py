@@ -1,0 +1,164 @@
+"""GPU tier (-m gpu): the tcgen05 heads GEMM fused with the momentum update
+(l2b_su3_heads_vupdate) against a float64 torch evaluation of the same bf16-rounded
+operands (network.py:536-548 + dynamics.py:1266-1297)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _case(nb, xdim, hidden, seed, wdtype=torch.float32):
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)  # noqa: E731
+    w = [(r(xdim, hidden) / hidden ** 0.5).to(wdtype).to(DEV) for _ in range(3)]
+    b = [(0.1 * r(xdim)).to(wdtype).to(DEV) for _ in range(3)]
+    cs, cq = (0.1 * r(1, xdim)).to(wdtype).to(DEV), (0.1 * r(1, xdim)).to(wdtype).to(DEV)
+    z = torch.tanh(r(nb, hidden)).to(torch.bfloat16).to(DEV)
+    v = torch.complex(r(nb, xdim), r(nb, xdim)).to(DEV)
+    f = torch.complex(r(nb, xdim), r(nb, xdim)).to(DEV)
+    return w, b, cs, cq, z, v, f
+
+
+def _reference(w, b, cs, cq, nw, z, v, f, eps, sign):
+    """float64 evaluation with the operands rounded to bf16 exactly as the kernel sees them"""
+    zz = z.double()
+    wr = [x.to(torch.bfloat16).double() for x in w]
+    s = nw[0] * cs.double().exp() * torch.tanh(zz @ wr[0].T + b[0].double())
+    t = nw[1] * (zz @ wr[1].T + b[1].double())
+    q = nw[2] * cq.double().exp() * torch.tanh(zz @ wr[2].T + b[2].double())
+    lj = sign * eps * s / 2
+    if sign > 0:
+        out = lj.exp() * v - 0.5 * eps * (f * (eps * q).exp() + t)
+    else:
+        out = lj.exp() * (v + 0.5 * eps * (f * (eps * q).exp() + t))
+    return out, lj.sum(1), torch.stack([s, t, q])
+
+
+@pytest.mark.parametrize('nb,xdim,hidden', [(64, 1152, 256), (5, 256, 64), (70, 4320, 128), (130, 1000 * 9, 40)])
+@pytest.mark.parametrize('sign', [+1, -1])
+def test_heads_vupdate_matches_float64_reference(nb, xdim, hidden, sign):
+    from l2hmc_b200 import ops
+    w, b, cs, cq, z, v, f = _case(nb, xdim, hidden, seed=nb + hidden)
+    nw = (0.7, 1.3, 0.9)
+    pack = ops.vnet_pack_heads(w[0], w[1], w[2], b[0], b[1], b[2], cs, cq, *nw)
+    eps = 0.11
+    out, logdet, stq = ops.su3_heads_vupdate(z, pack, v, f, eps, sign, want_stq=True)
+    want, wld, wstq = _reference(w, b, cs, cq, nw, z, v, f, eps, sign)
+    # fp32 accumulation / tanhf / expf on bf16 operands: 1e-5 relative (BASELINE north-star fp32 tolerance)
+    assert float((stq.double() - wstq).abs().max()) < 2e-5 * max(1.0, float(wstq.abs().max()))
+    assert float((out - want).abs().max()) < 1e-5 * max(1.0, float(want.abs().max()))
+    assert float((logdet - wld).abs().max()) < 1e-5 * max(1.0, float(wld.abs().max()))
+    out2, logdet2 = ops.su3_heads_vupdate(z, pack, v, f, eps, sign)
+    assert torch.equal(out2, out) and torch.equal(logdet2, logdet), 'bit-reproducible, with or without the s/t/q dump'
+
+
+def test_heads_unsupported_hidden_raises():
+    from l2hmc_b200 import ops
+    w, b, cs, cq, z, v, f = _case(4, 128, 260, seed=1)
+    pack = ops.vnet_pack_heads(w[0], w[1], w[2], b[0], b[1], b[2], cs, cq)
+    with pytest.raises(ops.L2BError):
+        ops.su3_heads_vupdate(z, pack, v, f, 0.1, 1)
+
+
+def _vnet(xshape, units, seed):
+    from l2hmc_b200.configs import NetworkConfig, NetWeight
+    from l2hmc_b200.network.pytorch.network import LeapfrogLayer
+    torch.manual_seed(seed)
+    net = LeapfrogLayer(xshape=xshape, network_config=NetworkConfig(units=list(units), activation_fn='tanh',
+                                                                    dropout_prob=0.0, use_batch_norm=False),
+                        net_weight=NetWeight(0.8, 1.1, 0.9)).to(DEV)
+    V = int(np.prod(xshape[2:6]))
+    with torch.no_grad():
+        net((torch.zeros(2, 4 * V * 8, device=DEV), torch.zeros(2, 4 * V * 8, device=DEV)))   # materialise lazy layers
+        for p in net.parameters():                      # bf16-representable parameters: the fused and the
+            p.copy_(p.to(torch.bfloat16).to(p.dtype))   # unfused path then see identical operands
+        net.scale.coeff.normal_(0, 0.1)
+        net.transf.coeff.normal_(0, 0.1)
+    return net
+
+
+@pytest.mark.parametrize('sign', [+1, -1])
+def test_fused_heads_function_matches_unfused_path_and_gradients(sign):
+    """SU3HeadsVUpdate (tcgen05 heads + epilogue, recompute backward) against
+    LeapfrogLayer.heads + SU3VUpdate on bf16-representable operands: values and every gradient"""
+    from l2hmc_b200 import autograd as ag
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        nb, shape, hidden = 6, (2, 4, 2, 3), 64
+        xshape = (nb, 4, *shape, 3, 3)
+        xdim = 4 * int(np.prod(shape)) * 9
+        net = _vnet(xshape, (hidden,), seed=5)
+        g = torch.Generator(device='cpu').manual_seed(9)
+        z0 = torch.tanh(torch.randn(nb, hidden, generator=g)).to(torch.bfloat16).float().to(DEV)
+        v0 = torch.complex(torch.randn(nb, xdim, generator=g, dtype=torch.float64),
+                           torch.randn(nb, xdim, generator=g, dtype=torch.float64)).to(DEV)
+        f0 = torch.complex(torch.randn(nb, xdim, generator=g, dtype=torch.float64),
+                           torch.randn(nb, xdim, generator=g, dtype=torch.float64)).to(DEV)
+        wv = torch.complex(torch.randn(nb, xdim, generator=g, dtype=torch.float64),
+                           torch.randn(nb, xdim, generator=g, dtype=torch.float64)).to(DEV)
+        wl = torch.randn(nb, generator=g, dtype=torch.float64).to(DEV)
+        params = [p for p in net.head_params()]
+
+        def run(fused):
+            z = z0.clone().requires_grad_(True)
+            v = v0.clone().requires_grad_(True)
+            f = f0.clone().requires_grad_(True)
+            eps = torch.tensor(0.13, dtype=torch.float64, device=DEV, requires_grad=True)
+            if fused:
+                out, ld = ag.SU3HeadsVUpdate.apply(z, v, f, eps, sign, None, net, *params)
+            else:
+                s, t, q = net.heads(z)
+                out, ld = ag.SU3VUpdate.apply(v.reshape(nb, 4, *shape, 3, 3), f.reshape(nb, 4, *shape, 3, 3), s, t, q,
+                                              eps, sign)
+                out = out.reshape(nb, xdim)
+            loss = (out * wv.conj()).real.sum() + (ld * wl).sum()
+            grads = torch.autograd.grad(loss, [z, v, f, eps] + params)
+            return out.detach(), ld.detach(), grads
+        o1, l1, g1 = run(True)
+        o0, l0, g0 = run(False)
+        assert float((o1 - o0).abs().max()) < 1e-5 * max(1.0, float(o0.abs().max()))
+        assert float((l1 - l0).abs().max()) < 1e-5 * max(1.0, float(l0.abs().max()))
+        for a, b in zip(g1, g0):
+            assert a.shape == b.shape and a.dtype == b.dtype
+            assert float((a - b).abs().max()) < 2e-5 * max(1.0, float(b.abs().max()))
+    finally:
+        torch.set_default_dtype(old)
+
+
+def test_dynamics_uses_tensor_core_heads_under_bf16_autocast():
+    """BASELINE cfg 5 path: under bf16 autocast the SU(3) v-update runs k_heads_vupdate; the
+    sweep agrees with the unfused bf16 path to bf16 accuracy and the train step yields finite grads"""
+    from test_gpu_trainer import _su3_trainer
+    from l2hmc_b200 import _lib
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        torch.manual_seed(1)
+        np.random.seed(1)
+        tr, lat = _su3_trainer(nb=4, units=(32,), autocast=torch.bfloat16)
+        dyn = tr.dynamics
+        x = lat.random().to(torch.complex128)
+        v = lat.random_momentum()
+        beta = torch.tensor(6.0)
+        from l2hmc_b200.dynamics.pytorch.dynamics import State
+        outs = {}
+        for mode in ('never', 'auto'):
+            dyn.tensor_core_heads = mode
+            n0 = _lib.launch_count()
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                st, met = dyn.transition_kernel_fb(State(x, v, beta))
+            outs[mode] = (st.x, st.v, met['sumlogdet'], _lib.launch_count() - n0)
+        assert float((outs['auto'][1] - outs['never'][1]).abs().max()) < 5e-2 * float(outs['never'][1].abs().max())
+        assert float((outs['auto'][0] - outs['never'][0]).abs().max()) < 5e-2
+        assert outs['auto'][3] != outs['never'][3], 'the fused kernel replaces k_vupdate launches'
+        dyn.tensor_core_heads = 'auto'
+        xo, m = tr.train_step((x, beta))
+        assert torch.isfinite(m['loss'])
+        gr = {n: p.grad for n, p in dyn.named_parameters() if p.grad is not None}
+        assert any('vnet.scale.layer.weight' in n for n in gr) and any('veps' in n for n in gr)
+        assert all(torch.isfinite(t).all() for t in gr.values())
+    finally:
+        torch.set_default_dtype(old)
