@@ -23,8 +23,10 @@
 //     fp32 accumulators in TMEM (3 x 64 columns), tcgen05.commit recycles the stages;
 //   * the epilogue reads TMEM with tcgen05.ld (lane = xdim column, column = chain), so the
 //     v / F / v' accesses of a warp are 512 contiguous bytes per chain.
-// Two CTAs are resident per SM (98 KB smem, 256 TMEM columns each): one CTA's HBM-bound
-// epilogue overlaps the other's weight streaming and MMAs.
+// (Measured negative: a cp.async.bulk.prefetch.L2 of the tile's v / F rows at kernel start made the
+// kernel 14 % slower -- the epilogue's own 16 loads in flight per thread already cover the latency.)
+// Two CTAs of 8 warps are resident per SM (~107 KB smem, 256 TMEM columns each): one CTA's
+// HBM-bound epilogue overlaps the other's weight streaming and MMAs.
 #include <cuda_bf16.h>
 
 #include "l2b_common.cuh"
@@ -39,7 +41,8 @@ constexpr int NST = 4;                        // weight stages in flight
 constexpr int A_STAGE_BYTES = BM * KC * 2;    // 16 KB
 constexpr int KMAX = 256;                     // largest (padded) hidden size with z resident
 constexpr int TMEM_COLS = 256;                // 3 x BN = 192 accumulator columns, power of two
-constexpr int NTH = 128;
+constexpr int NTH = 256;                       // 8 warps: 1 TMA/MMA thread, all 8 warps in the epilogue
+constexpr int CH = 8;                          // chains per epilogue chunk
 
 struct Smem {
   alignas(128) unsigned char a[NST][A_STAGE_BYTES];     // weight ring
@@ -47,7 +50,8 @@ struct Smem {
   alignas(8) unsigned long long full[NST];
   unsigned long long empty[NST];
   unsigned long long accum;
-  float ld[NTH / 32][BN];                               // logdet partials per warp
+  float lj[NTH / 32][CH * 33];                          // per-warp log-Jacobian staging (padded rows)
+  float ld[NTH / 32][32];                               // logdet partials: [warp][chain of its half]
   uint32_t tmem_base;
 };
 
@@ -60,6 +64,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // bounded spin: a protocol bug traps (CUDA error) instead of hanging the GPU
+template <int SLEEP_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
   for (uint32_t spin = 0; !ok; ++spin) {
@@ -70,7 +75,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!ok && spin > (1u << 26)) __trap();
+    if (!ok) {
+      if (SLEEP_NS > 0) __nanosleep(SLEEP_NS);          // waiting epilogue warps stay off the issue ports
+      if (spin > (1u << 24)) __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -99,13 +107,28 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
+// tanh(x) = 1 - 2 / (1 + e^{2x}) on the SFU (ex2.approx + rcp.approx): absolute error ~2e-7, which is
+// what the epilogue needs (s, q enter through eps*s/2 and eps*q); saturates correctly for large |x|
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = ex2_approx(2.885390081777927f * x);   // e^{2x}; inf -> rcp = 0 -> 1, 0 -> -1
+  return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
+}
+__device__ __forceinline__ float exp_fast(float x) { return ex2_approx(1.4426950408889634f * x); }
 
 // ---------------------------------------------------------------------------
 // weight packing: W_h[xdim, H] (nn.Linear layout, f64 / f32 / bf16) -> bf16 image
@@ -159,6 +182,76 @@ struct HeadsArgs {
   int sign, nb, xdim, H, KP, ntiles;
 };
 
+// FULL: interior tile (all 64 chains and 128 columns valid, no s/t/q dump): no per-element predicates
+template <bool FWD, bool FULL>
+__device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t tmem, int tile, int chain0, int warp,
+                                         int lane) {
+  const int quarter = warp & 3, half = warp >> 2;
+  const size_t j = (size_t)tile * BM + quarter * 32 + lane;
+  const bool col_ok = FULL || j < (size_t)a.xdim;
+  const float bs = col_ok ? __ldg(a.bias[0] + j) : 0.f, bt = col_ok ? __ldg(a.bias[1] + j) : 0.f,
+              bq = col_ok ? __ldg(a.bias[2] + j) : 0.f;
+  const float as = col_ok ? __ldg(a.scale_s + j) : 0.f, aq = col_ok ? __ldg(a.scale_q + j) : 0.f, at = a.scale_t;
+  const float epsf = (float)a.eps, hs = (FWD ? 0.5f : -0.5f) * epsf;
+  const double he = 0.5 * a.eps;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+  float* ljw = sm.lj[warp];
+  const size_t xd = (size_t)a.xdim;
+#pragma unroll 1
+  for (int ck = 0; ck < 4; ++ck) {
+    const int c0 = half * 32 + ck * CH;
+    if (!FULL && chain0 + c0 >= a.nb) break;            // warp-uniform: nothing left for this warp
+    uint32_t rs[CH], rt[CH], rq[CH];
+    tmem_ld8(trow + 0 * BN + c0, rs);
+    tmem_ld8(trow + 1 * BN + c0, rt);
+    tmem_ld8(trow + 2 * BN + c0, rq);
+    const size_t base = (size_t)(chain0 + c0) * xd + j;
+    const double2* pv = a.v + base;
+    const double2* pf = a.f + base;
+    double2* po = a.out + base;
+    double2 vv[CH], ff[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const bool ok = FULL || (col_ok && chain0 + c0 + c < a.nb);
+      vv[c] = ok ? __ldg(pv + c * xd) : make_double2(0., 0.);
+      ff[c] = ok ? __ldg(pf + c * xd) : make_double2(0., 0.);
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const bool ok = FULL || (col_ok && chain0 + c0 + c < a.nb);
+      const float s = as * tanh_fast(__uint_as_float(rs[c]) + bs);
+      const float t = at * (__uint_as_float(rt[c]) + bt);
+      const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
+      const float logjac = hs * s;                      // sign * eps * s / 2
+      ljw[c * 33 + lane] = ok ? logjac : 0.f;
+      const double es = (double)exp_fast(logjac), eq = (double)exp_fast(epsf * q);
+      const double fr = fma(ff[c].x, eq, (double)t), fi = ff[c].y * eq;
+      double2 o;
+      if (FWD) { o.x = fma(es, vv[c].x, -he * fr); o.y = fma(es, vv[c].y, -he * fi); }
+      else { o.x = es * fma(he, fr, vv[c].x); o.y = es * fma(he, fi, vv[c].y); }
+      if (ok) {
+        po[c * xd] = o;
+        if (!FULL && a.stq != nullptr) {
+          const size_t plane = (size_t)a.nb * xd, at_ = base + c * xd;
+          a.stq[at_] = s; a.stq[plane + at_] = t; a.stq[2 * plane + at_] = q;
+        }
+      }
+    }
+    __syncwarp();
+    {                                                   // fixed-order sum over the warp's 32 columns:
+      const int c = lane & 7, part = lane >> 3;         // lane (c, part) adds columns 8 part .. +7 of chain c
+      float x = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x += ljw[c * 33 + part * 8 + k];
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      if (lane < CH) sm.ld[warp][ck * CH + lane] = x;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -169,6 +262,7 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   const int NKC = a.KP / KC;
   const int total = 3 * NKC;
 
+  sm.ld[warp][lane] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
     mbar_init(smem_u32(&sm.accum), 1);
@@ -232,69 +326,26 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   __syncwarp();
 
   // ---- epilogue: TMEM lane = xdim column, TMEM column = chain -----------------------------
-  mbar_wait(smem_u32(&sm.accum), 0);
+  // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (the hardware's lane quarter of a warp)
+  // and owns the chains [32 (w / 4), +32) of the tile, 8 chains at a time.
+  mbar_wait<128>(smem_u32(&sm.accum), 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const size_t j = (size_t)tile * BM + tid;
-  const bool col_ok = j < (size_t)a.xdim;
-  const float bs = col_ok ? __ldg(a.bias[0] + j) : 0.f, bt = col_ok ? __ldg(a.bias[1] + j) : 0.f,
-              bq = col_ok ? __ldg(a.bias[2] + j) : 0.f;
-  const float as = col_ok ? __ldg(a.scale_s + j) : 0.f, aq = col_ok ? __ldg(a.scale_q + j) : 0.f, at = a.scale_t;
-  const float epsf = (float)a.eps, hs = 0.5f * (float)a.sign * epsf;
-  const double he = 0.5 * a.eps;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    if (chain0 + c0 >= a.nb) {                          // uniform: nothing left in this tile
-      for (int c = 0; c < 16; ++c) if (lane == 0) sm.ld[warp][c0 + c] = 0.f;
-      continue;
-    }
-    uint32_t rs[16], rt[16], rq[16];
-    tmem_ld16(trow + 0 * BN + c0, rs);
-    tmem_ld16(trow + 1 * BN + c0, rt);
-    tmem_ld16(trow + 2 * BN + c0, rq);
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    float lj[16];
-    double2 vv[16], ff[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int b = chain0 + c0 + c;
-      const bool ok = col_ok && b < a.nb;
-      vv[c] = ok ? __ldg(a.v + (size_t)b * a.xdim + j) : make_double2(0., 0.);
-      ff[c] = ok ? __ldg(a.f + (size_t)b * a.xdim + j) : make_double2(0., 0.);
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int b = chain0 + c0 + c;
-      const bool ok = col_ok && b < a.nb;
-      const float s = as * tanhf(__uint_as_float(rs[c]) + bs);
-      const float t = at * (__uint_as_float(rt[c]) + bt);
-      const float q = aq * tanhf(__uint_as_float(rq[c]) + bq);
-      const float logjac = hs * s;                      // sign * eps * s / 2
-      lj[c] = ok ? logjac : 0.f;
-      const double es = (double)expf(logjac), eq = (double)expf(epsf * q);
-      const double fr = fma(ff[c].x, eq, (double)t), fi = ff[c].y * eq;
-      double2 o;
-      if (a.sign > 0) { o.x = es * vv[c].x - he * fr; o.y = es * vv[c].y - he * fi; }
-      else { o.x = es * (vv[c].x + he * fr); o.y = es * (vv[c].y + he * fi); }
-      if (ok) {
-        a.out[(size_t)b * a.xdim + j] = o;
-        if (a.stq != nullptr) {
-          const size_t plane = (size_t)a.nb * a.xdim, at_ = (size_t)b * a.xdim + j;
-          a.stq[at_] = s; a.stq[plane + at_] = t; a.stq[2 * plane + at_] = q;
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      float x = lj[c];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if (lane == 0) sm.ld[warp][c0 + c] = x;
+  {
+    const bool full = (chain0 + BN <= a.nb) && ((size_t)(tile + 1) * BM <= (size_t)a.xdim) && a.stq == nullptr;
+    if (full) {
+      if (a.sign > 0) epilogue<true, true>(a, sm, tmem, tile, chain0, warp, lane);
+      else epilogue<false, true>(a, sm, tmem, tile, chain0, warp, lane);
+    } else {
+      if (a.sign > 0) epilogue<true, false>(a, sm, tmem, tile, chain0, warp, lane);
+      else epilogue<false, false>(a, sm, tmem, tile, chain0, warp, lane);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (a.part != nullptr && tid < BN && chain0 + tid < a.nb) {
-    const double x = (double)sm.ld[0][tid] + (double)sm.ld[1][tid] + (double)sm.ld[2][tid] + (double)sm.ld[3][tid];
+    const int h = tid >> 5, c = tid & 31;
+    const double x = (double)sm.ld[4 * h + 0][c] + (double)sm.ld[4 * h + 1][c] + (double)sm.ld[4 * h + 2][c] +
+                     (double)sm.ld[4 * h + 3][c];
     a.part[(size_t)(chain0 + tid) * a.ntiles + tile] = x;
   }
   if (warp == 0) {

@@ -38,11 +38,17 @@ def main(rep):
             if k in hdr:
                 i = hdr.index(k)
                 print(f'| {label} (`{k}`) | {r[i]} {units[i]} |')
+        for i, k in enumerate(hdr):      # whatever tensor-pipe counters this ncu version exposes
+            if 'pipe_tensor' in k and ('pct_of_peak_sustained_active' in k or 'cycles_active.avg' in k) and r[i] not in ('', '0'):
+                print(f'| tensor pipe (`{k}`) | {r[i]} {units[i]} |')
         try:
-            rd = float(r[hdr.index('dram__bytes_read.sum')])
-            wr = float(r[hdr.index('dram__bytes_write.sum')])
-            u = units[hdr.index('dram__bytes_read.sum')]
-            print(f'| **DRAM traffic (read+write)** | {rd + wr:.3f} {u} |')
+            mult = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+            ird, iwr = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
+            tot = float(r[ird]) * mult[units[ird]] + float(r[iwr]) * mult[units[iwr]]
+            print(f'| **DRAM traffic (read+write)** | {tot / 1e9:.3f} Gbyte |')
+            dur = float(r[hdr.index('gpu__time_duration.sum')]) * {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}[
+                units[hdr.index('gpu__time_duration.sum')]]
+            print(f'| **DRAM GB/s over the launch** | {tot / dur / 1e9:.1f} |')
         except Exception:
             pass
         print()

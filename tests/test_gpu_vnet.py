@@ -107,8 +107,10 @@ def test_fused_heads_function_matches_unfused_path_and_gradients(sign):
             v = v0.clone().requires_grad_(True)
             f = f0.clone().requires_grad_(True)
             eps = torch.tensor(0.13, dtype=torch.float64, device=DEV, requires_grad=True)
-            if fused:
-                out, ld = ag.SU3HeadsVUpdate.apply(z, v, f, eps, sign, None, net, *params)
+            if fused:      # fields in their lattice shape, as Dynamics passes them (the adjoint kernel needs it)
+                out, ld = ag.SU3HeadsVUpdate.apply(z, v.reshape(nb, 4, *shape, 3, 3), f.reshape(nb, 4, *shape, 3, 3),
+                                                   eps, sign, None, net, *params)
+                out = out.reshape(nb, xdim)
             else:
                 s, t, q = net.heads(z)
                 out, ld = ag.SU3VUpdate.apply(v.reshape(nb, 4, *shape, 3, 3), f.reshape(nb, 4, *shape, 3, 3), s, t, q,
