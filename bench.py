@@ -43,6 +43,15 @@ WORKLOADS = {
     'u1_64x64_nb4096_nlf10_f32': ('U1', [64, 64], 4096, 10, 'f32', 4.0),
     'u1_16x16_nb128_nlf8_f32': ('U1', [16, 16], 128, 8, 'f32', 4.0),
 }
+# L2HMC workloads (BASELINE cfg 3 secondary / cfg 5): a "step" is one Trainer.eval_step
+# (Dynamics.forward, 2*N_LF leapfrog layers) or one Trainer.train_step (forward + loss +
+# backward + gradient all-reduce over the ranks + Adam); bf16 vnet (autocast), fp64 lattice,
+# network.units = [256] (conf/network/su3.yaml), N_LF = 4 (conf/su3test.yaml).
+L2HMC_WORKLOADS = {
+    # name: (mode, lattice, chains per GPU, N_LF, hidden units, beta)
+    'su3_8x8x8x8_nb256_l2hmc_eval_bf16': ('eval', [8, 8, 8, 8], 256, 4, 256, 6.0),
+    'su3_8x8x8x8_nb32_l2hmc_train_bf16': ('train', [8, 8, 8, 8], 32, 4, 256, 6.0),
+}
 DEFAULT_WORKLOAD = 'su3_16x16x16x16_nb64_nlf10_c128'
 METRIC = 'link-updates/sec (chains*V*d*Nlf/s)'
 SEED = 9992  # conf/config.yaml:11
@@ -376,6 +385,151 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+def main_l2hmc(args):
+    """SU(3) L2HMC eval / training step through the public Trainer API (secondary workloads)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU; there is no CPU fallback'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from l2hmc_b200 import _lib, ops
+    from l2hmc_b200.configs import (DynamicsConfig, LossConfig, NetWeight, NetWeights, NetworkConfig,
+                                    get_input_spec)
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    from l2hmc_b200.trainers.pytorch.trainer import Trainer
+    mode, lattice, nb, nlf, units, beta = L2HMC_WORKLOADS[args.workload]
+    torch.manual_seed(SEED)            # identical initial weights on every rank (DDP broadcasts rank 0's)
+    np.random.seed(SEED)
+    torch.set_default_dtype(torch.float32)
+    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=0.01, eps_hmc=0.01,
+                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                         network_config=NetworkConfig(units=[units], activation_fn='tanh', dropout_prob=0.0,
+                                                      use_batch_norm=False),
+                         conv_config=None, net_weights=NetWeights(x=NetWeight(0., 1., 1.), v=NetWeight(1., 1., 1.)),
+                         build_unused_su3_xnet=False)
+    lat = LatticeSU3(nb, lattice)
+    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+    tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
+                 clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16)
+    torch.manual_seed(SEED + 1 + rank)   # per-rank chains
+    x = lat.random().to(torch.complex128)
+    bt = torch.tensor(beta)
+    V = 1
+    for s_ in lattice:
+        V *= s_
+    units_rank = nb * 4 * V * 2 * nlf     # link-updates per step per GPU (nlf forward + nlf backward layers)
+
+    def step(xin):
+        if mode == 'eval':
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                return tr.eval_step((xin, bt))
+        return tr.train_step((xin, bt))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(x)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xo, met = step(x)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / args.steps
+    value = world * units_rank / (ms * 1e-3)
+    assert torch.isfinite(met['loss']), 'non-finite loss'
+    # e2e: links from pinned host memory every step, loss read back to the host
+    xh = x.cpu().pin_memory()
+    loss_h = torch.empty((), dtype=met['loss'].dtype).pin_memory()
+    xin = torch.empty_like(x)
+    n_e2e = max(2, min(args.steps, 5))
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(n_e2e):
+        xin.copy_(xh, non_blocking=True)
+        xo, met = step(xin)
+        loss_h.copy_(met['loss'], non_blocking=True)
+    e3.record()
+    barrier()
+    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_val = world * units_rank * n_e2e / (float(t2) * 1e-3)
+    # roofline of the tensor-core kernel of this path: k_heads_vupdate, timed alone with CUDA events
+    peak, peak_kind = peaks()
+    vnet = dyn._get_vnet(0)
+    pack = vnet.heads_pack()
+    xdim = pack.xdim
+    z = torch.tanh(torch.randn(nb, units, device=dev)).to(torch.bfloat16)
+    vv = lat.random_momentum().reshape(nb, xdim)
+    ff = lat.random_momentum().reshape(nb, xdim)
+    for _ in range(3):
+        ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
+    evs = []
+    for _ in range(10):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record()
+        ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
+        b_.record()
+        evs.append((a_, b_))
+    torch.cuda.synchronize()
+    ms_k = statistics.mean(a_.elapsed_time(b_) for a_, b_ in evs)
+    algo = 3.0 * 16 * nb * xdim + 3.0 * 2 * xdim * units          # v r, F r, v' w (complex128) + bf16 weights once
+    ach = algo / (ms_k * 1e-3) / 1e9
+    flops = 2.0 * 3 * nb * xdim * units
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'link-updates/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64 lattice + bf16 nets (fp32 accumulate)', 'data': 'synthetic',
+            'config': {'workload': args.workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
+                       'global_chains': nb * world, 'nleapfrog': nlf, 'units': [units], 'beta': beta, 'step': mode,
+                       'start': 'hot (g.random), random-init weights',
+                       'parallelism': (f'chains sharded over {world} GPU(s); '
+                                       + ('one flat bf16 NCCL all-reduce of the NN gradients per step' if mode == 'train'
+                                          else 'no collective')),
+                       'l2_policy': 'fields + weights (~1 GB) exceed L2; no flush'},
+            'roofline': {'bound': 'hbm', 'kernel': 'k_heads_vupdate (tcgen05 heads GEMM + momentum update)',
+                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind,
+                         'traffic': None, 'algorithmic_bytes_per_launch': algo, 'avg_launch_ms': ms_k,
+                         'tensor_tflops': flops / (ms_k * 1e-3) / 1e12,
+                         'note': 'algorithmic bytes = v, F read + v\' written (complex128) + the bf16 head weights once; '
+                                 'the GEMM is 0.2 % of the bf16 tensor peak by construction (HBM-bound op)'},
+            'cpu_baseline': None,
+            'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': x.numel() * x.element_size(),
+                    'd2h_bytes_per_step': loss_h.element_size(), 'steps': n_e2e,
+                    'api': f'Trainer.{mode}_step((x_host_pinned -> device, beta))'},
+            'gpu_launches': launches, 'clocks': clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline_subprocess(workload: str):
     """the reference's CPU path, in a child process that cannot see the GPU"""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES='', RANK='0', WORLD_SIZE='1')
@@ -448,13 +602,19 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--workload', choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument('--workload', choices=sorted(WORKLOADS) + sorted(L2HMC_WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':
+        if args.workload in L2HMC_WORKLOADS:
+            if int(os.environ.get('RANK', '0')) == 0:
+                print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference arm covers the HMC workloads only'}))
+            return
         main_reference(args)
+    elif args.workload in L2HMC_WORKLOADS:
+        main_l2hmc(args)
     else:
         main_ours(args)
 
