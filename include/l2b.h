@@ -23,6 +23,10 @@
  *    SU(3) precision the reference configures, conf/experiment/su3.yaml) and
  *    return L2B_ERR_UNSUPPORTED otherwise.
  *  - per-chain reductions are deterministic (fixed-order two-stage sums).
+ *  - step sizes: every L2HMC update takes `double eps, const <real>* eps_dev`.  With eps_dev ==
+ *    NULL the step size is `eps`; otherwise the kernel reads it from device memory as
+ *    eps * (*eps_dev) (eps is then a host-side multiplier, +-1 in practice), so a trainable step
+ *    size never has to visit the host and whole steps can be captured in CUDA graphs.
  */
 #ifndef L2B_H
 #define L2B_H
@@ -94,7 +98,7 @@ int l2b_su3_exp(const void* p, double scale, void* out, size_t nmat, int dtype, 
  *                   element-wise and shared by all chains (dynamics.py:1101-1110);
  *                   if mask_complement != 0 the roles of m and 1-m are swapped.
  * x_out may alias x.                                                          */
-int l2b_su3_update_gauge(const void* x, const void* p, double eps, const float* mask,
+int l2b_su3_update_gauge(const void* x, const void* p, double eps, const double* eps_dev, const float* mask,
                          int mask_complement, void* x_out, int nb, const int dims[4], int dtype,
                          void* stream);
 
@@ -116,9 +120,11 @@ int l2b_su3_check(const void* x, double* avg, double* max, int nb, const int dim
                   void* ws, size_t ws_bytes, void* stream);
 /* SU3.random_momentum / randTAH3 (utils.py:171-195): Gaussian traceless
  * anti-Hermitian momenta, <|P|_F^2> = 8, from a counter-based Philox4x32-10
- * stream keyed by (seed, offset, link index); ke_or_null[nb] as l2b_su3_kinetic. */
-int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or_null, int nb,
-                          const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+ * stream keyed by (seed, offset, link index); ke_or_null[nb] as l2b_su3_kinetic.
+ * offset_dev_or_null: device-resident call counter added to `offset` and incremented by
+ * one after the draw, so that a CUDA-graph replay of this call draws fresh momenta. */
+int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, uint64_t* offset_dev_or_null, void* p, double* ke_or_null,
+                          int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* Dynamics._update_v_fwd / _update_v_bwd epilogue (dynamics.py:1266-1297) on
  * complex v, force with REAL s, t, q of shape [nb, 4*V*9] (network outputs):
@@ -126,7 +132,7 @@ int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or
  *   backward (sign=-1): v' = exp(-eps s/2) (v + eps/2 (F exp(eps q) + t)), logdet = -sum eps s/2
  * s/t/q may be NULL (treated as 0, i.e. a plain HMC half kick). v_out may alias v. */
 int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q,
-                    double eps, int sign, void* v_out, double* logdet, int nb, const int dims[4],
+                    double eps, const double* eps_dev, int sign, void* v_out, double* logdet, int nb, const int dims[4],
                     int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* Dynamics.transition_kernel_hmc (dynamics.py:900-954) for SU(3): nlf leapfrog
@@ -156,12 +162,12 @@ int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int n
                              void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_vupdate w.r.t. v, force, s, t, q (gforce/gs/gt/gq may be NULL) and eps
  * (geps[nb], per chain) */
-int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const double* eps_dev,
                         int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
                         void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_update_gauge w.r.t. x, p and eps (matrix-exponential adjoint as a Taylor
  * series on Cayley-Hamilton coefficients; *bad_flag is set when ||eps p||_F > 3 somewhere) */
-int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const double* eps_dev, const float* mask, int mask_complement,
                              const void* gx_out, void* gx, void* gp, double* geps, int* bad_flag, int nb,
                              const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_to_vec: gx[nmat,3,3] from gvec8[nmat,8] */
@@ -217,8 +223,8 @@ int l2b_vnet_pack_heads(const void* w_s, const void* w_t, const void* w_q, int w
  * and for tests.  hidden % 8 == 0 and hidden <= 256, else L2B_ERR_UNSUPPORTED. */
 int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
                           const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
-                          const void* v, const void* force, double eps, int sign, void* v_out, double* logdet,
-                          float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream);
+                          const void* v, const void* force, double eps, const double* eps_dev, int sign, void* v_out,
+                          double* logdet, float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* U(1), x[nb, 2, T, X] real angles                                          */
@@ -242,13 +248,13 @@ int l2b_u1_hmc_trajectory(const void* x, const void* v, double beta, double eps,
                           int dtype, void* stream);
 /* Dynamics._update_v_{fwd,bwd} epilogue for real fields (dynamics.py:1266-1297) */
 int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q,
-                   double eps, int sign, void* v_out, void* logdet, int nb, int xdim, int dtype,
+                   double eps, const void* eps_dev, int sign, void* v_out, void* logdet, int nb, int xdim, int dtype,
                    void* stream);
 /* Dynamics._update_x_{fwd,bwd} for U(1) (dynamics.py:1398-1419,1443-1467),
  * use_ncp selects the non-compact-projection update; m = mask[xdim] float32.
  * x_out is wrapped to [-pi, pi) like g.compat_proj.                           */
 int l2b_u1_xupdate(const void* x, const void* v, const void* s, const void* t, const void* q,
-                   const float* mask, double eps, int sign, int use_ncp, void* x_out, void* logdet,
+                   const float* mask, double eps, const void* eps_dev, int sign, int use_ncp, void* x_out, void* logdet,
                    int nb, int xdim, int dtype, void* stream);
 
 /* U1Phase.kinetic_energy (group/u1/pytorch/group.py:164-165): ke[nb] = 0.5 sum v^2 */
@@ -265,11 +271,11 @@ int l2b_u1_force_bwd(const void* x, double beta, const void* gforce, void* gx, i
                      void* stream);
 /* adjoints of l2b_u1_vupdate / l2b_u1_xupdate: gradients w.r.t. every input
  * (gs/gt/gq may be NULL) and geps[nb] = per-chain derivative w.r.t. eps */
-int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const void* eps_dev,
                        int sign, const void* gv_out, const void* glogdet, void* gv, void* gforce, void* gs, void* gt,
                        void* gq, void* geps, int nb, int xdim, int dtype, void* stream);
 int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
-                       double eps, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
+                       double eps, const void* eps_dev, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
                        void* gs, void* gt, void* gq, void* geps, int nb, int xdim, int dtype, void* stream);
 /* out[b,:] = scale[b] * in[b,:]: adjoint of action (in = force) and of kinetic energy (in = v) */
 int l2b_rowscale(const void* in, const void* scale, void* out, int nb, int xdim, int dtype, void* stream);

@@ -45,19 +45,19 @@ _SIGS = {
     'l2b_su3_plaq_sums': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force': [_P, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_exp': [_P, c_double, _P, c_size_t, c_int, _P],
-    'l2b_su3_update_gauge': [_P, _P, c_double, _P, c_int, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_update_gauge': [_P, _P, c_double, _P, _P, c_int, _P, c_int, _DIMS, c_int, _P],
     'l2b_su3_project': [_P, _P, _P, c_size_t, c_int, _P],
     'l2b_su3_to_vec': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_from_vec': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_tah': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_kinetic': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_check': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
-    'l2b_su3_rand_momentum': [c_uint64, c_uint64, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
-    'l2b_su3_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_rand_momentum': [c_uint64, c_uint64, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_vupdate': [_P, _P, _P, _P, _P, c_double, _P, c_int, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_action_grad': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
-    'l2b_su3_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
-    'l2b_su3_update_gauge_bwd': [_P, _P, c_double, _P, c_int, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_update_gauge_bwd': [_P, _P, c_double, _P, _P, c_int, _P, _P, _P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_to_vec_bwd': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_wilson_loops_bwd': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_bwd': [_P, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
@@ -68,20 +68,20 @@ _SIGS = {
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
     'l2b_set_option': [c_char_p, c_int],
     'l2b_vnet_pack_heads': [_P, _P, _P, c_int, _P, c_int, c_int, _P],
-    'l2b_su3_heads_vupdate': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, c_int, _P, _P, _P, c_int, c_int,
+    'l2b_su3_heads_vupdate': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, _P, c_int, _P, _P, _P, c_int, c_int,
                               c_int, _P, c_size_t, _P],
     'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_observables': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_force': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
-    'l2b_u1_vupdate': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, c_int, c_int, c_int, _P],
-    'l2b_u1_xupdate': [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_vupdate': [_P, _P, _P, _P, _P, c_double, _P, c_int, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_xupdate': [_P, _P, _P, _P, _P, _P, c_double, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P],
     'l2b_u1_kinetic': [_P, _P, c_int, c_int, c_int, _P],
     'l2b_u1_compat_proj': [_P, _P, c_size_t, c_int, _P],
     'l2b_u1_wilson_loops_bwd': [_P, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_force_bwd': [_P, c_double, _P, _P, c_int, c_int, c_int, c_int, _P],
-    'l2b_u1_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
-    'l2b_u1_xupdate_bwd': [_P, _P, _P, _P, _P, _P, c_double, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_vupdate_bwd': [_P, _P, _P, _P, _P, c_double, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
+    'l2b_u1_xupdate_bwd': [_P, _P, _P, _P, _P, _P, c_double, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     'l2b_rowscale': [_P, _P, _P, c_int, c_int, c_int, _P],
     'l2b_accept_mix': [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_size_t), c_int, _P, c_int, _P],
 }

@@ -114,7 +114,7 @@ class U1VUpdate(torch.autograd.Function):
     def forward(ctx, v, force, s, t, q, eps, sign, eps_value=None):
         ctx.save_for_backward(v, force, s, t, q, eps)
         ctx.sign = sign
-        ctx.eps_value = float(eps) if eps_value is None else eps_value   # host copy: no sync per update
+        ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         out, logdet = ops.u1_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), ctx.eps_value, sign)
         return out, logdet
 
@@ -135,7 +135,7 @@ class U1XUpdate(torch.autograd.Function):
     def forward(ctx, x, v, s, t, q, mask, eps, sign, use_ncp, eps_value=None):
         ctx.save_for_backward(x, v, s, t, q, mask, eps)
         ctx.sign, ctx.use_ncp = sign, use_ncp
-        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         out, logdet = ops.u1_xupdate(x.detach(), v.detach(), _opt(s), _opt(t), _opt(q), mask, ctx.eps_value, sign,
                                      use_ncp)
         return out, logdet
@@ -254,7 +254,7 @@ class SU3VUpdate(torch.autograd.Function):
     def forward(ctx, v, force, s, t, q, eps, sign, eps_value=None):
         ctx.save_for_backward(v, force, s, t, q, eps)
         ctx.sign = sign
-        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         return ops.su3_vupdate(v.detach(), force.detach(), _opt(s), _opt(t), _opt(q), ctx.eps_value, sign)
 
     @staticmethod
@@ -278,7 +278,7 @@ class SU3HeadsVUpdate(torch.autograd.Function):
     def forward(ctx, z, v, force, eps, sign, eps_value, net, *head_params):
         ctx.save_for_backward(z, v, force, eps, *head_params)
         ctx.sign, ctx.net = sign, net
-        ctx.eps_value = float(eps) if eps_value is None else eps_value
+        ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         ctx.autocast = (torch.is_autocast_enabled('cuda'), torch.get_autocast_dtype('cuda'))
         out, logdet = ops.su3_heads_vupdate(z.detach(), net.heads_pack(), v.detach(), force.detach(), ctx.eps_value,
                                             sign)
@@ -310,13 +310,14 @@ class SU3UpdateGauge(torch.autograd.Function):
     def forward(ctx, x, p, eps, mask, sign, eps_value=None):
         ctx.save_for_backward(x, p, eps, mask)
         ctx.sign = sign
-        ctx.eps_value = float(eps) if eps_value is None else eps_value
-        return ops.su3_update_gauge(x.detach(), p.detach(), sign * ctx.eps_value, mask=mask)
+        ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
+        return ops.su3_update_gauge(x.detach(), p.detach(), ctx.eps_value, mask=mask, eps_mult=float(sign))
 
     @staticmethod
     def backward(ctx, g):
         x, p, eps, mask = ctx.saved_tensors
-        gx, gp, geps, bad = ops.su3_update_gauge_bwd(x.detach(), p.detach(), ctx.sign * ctx.eps_value, mask, False, g)
+        gx, gp, geps, bad = ops.su3_update_gauge_bwd(x.detach(), p.detach(), ctx.eps_value, mask, False, g,
+                                                     eps_mult=float(ctx.sign))
         _BAD_FLAGS.append(bad)        # checked once per backward pass (check_exp_adjoint_flags), not per link update
         if len(_BAD_FLAGS) > 1024:    # callers that never check: bound the list
             check_exp_adjoint_flags()

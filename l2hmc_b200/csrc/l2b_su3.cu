@@ -407,11 +407,12 @@ __global__ void __launch_bounds__(TS * 4, 3) k_wloops_bwd(const C* __restrict__ 
 // adjoint of k_vupdate (force is a constant of the graph)
 __global__ void __launch_bounds__(NTL) k_vupdate_bwd(const C* __restrict__ v, const C* __restrict__ f,
                                                      const T* __restrict__ s, const T* __restrict__ t,
-                                                     const T* __restrict__ q, double eps, int sign,
+                                                     const T* __restrict__ q, double eps_in, const double* __restrict__ eps_dev, int sign,
                                                      const C* __restrict__ gout, const double* __restrict__ glogdet,
                                                      C* __restrict__ gv, C* __restrict__ gf, T* __restrict__ gs,
                                                      T* __restrict__ gt, T* __restrict__ gq, double* __restrict__ part,
                                                      size_t links_per_chain) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ C sm[NTL * 9];
   __shared__ double red[NTL / 32];
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
@@ -479,11 +480,12 @@ __global__ void __launch_bounds__(NTL) k_vupdate_bwd(const C* __restrict__ v, co
 // adjoint of k_update_gauge:  R = m*X + E ((1-m)*X),  E = exp(eps P)
 //   G_X = m*G + (1-m)*(E^+ G),  G_E = G ((1-m)*X)^+,  G_P = eps * expadj(eps P; G_E),
 //   g_eps = Re sum conj(G_A) P
-__global__ void __launch_bounds__(NTL) k_update_gauge_bwd(const C* __restrict__ x, const C* __restrict__ p, double eps,
+__global__ void __launch_bounds__(NTL) k_update_gauge_bwd(const C* __restrict__ x, const C* __restrict__ p, double eps_in, const double* __restrict__ eps_dev,
                                                           const float* __restrict__ mask, int mask_complement,
                                                           const C* __restrict__ gout, C* __restrict__ gx,
                                                           C* __restrict__ gp, double* __restrict__ part,
                                                           int* __restrict__ bad, size_t links_per_chain) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ C sm[NTL * 9];
   __shared__ double red[NTL / 32];
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
@@ -743,9 +745,10 @@ __global__ void __launch_bounds__(NTL) k_from_vec(const T* __restrict__ vec8, C*
 }
 
 // x_out = m*x + exp(eps p) ((1-m)*x)   (mask == nullptr: x_out = exp(eps p) x)
-__global__ void __launch_bounds__(NTL) k_update_gauge(const C* __restrict__ x, const C* __restrict__ p, double eps,
+__global__ void __launch_bounds__(NTL) k_update_gauge(const C* __restrict__ x, const C* __restrict__ p, double eps_in, const double* __restrict__ eps_dev,
                                                       const float* __restrict__ mask, int mask_complement,
                                                       C* __restrict__ out, size_t links_per_chain) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ C sm[NTL * 9];
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
   const size_t l0 = (size_t)blockIdx.x * NTL;               // link index inside the chain
@@ -780,8 +783,9 @@ __global__ void __launch_bounds__(NTL) k_update_gauge(const C* __restrict__ x, c
 // L2HMC momentum update epilogue (see l2b.h)
 __global__ void __launch_bounds__(NTL) k_vupdate(const C* __restrict__ v, const C* __restrict__ f,
                                                  const T* __restrict__ s, const T* __restrict__ t,
-                                                 const T* __restrict__ q, double eps, int sign, C* __restrict__ out,
+                                                 const T* __restrict__ q, double eps_in, const double* __restrict__ eps_dev, int sign, C* __restrict__ out,
                                                  double* __restrict__ part, size_t links_per_chain) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ C sm[NTL * 9];
   __shared__ double red[NTL / 32];
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
@@ -895,8 +899,15 @@ __device__ __forceinline__ double u01(uint32_t a, uint32_t b) {
   return ((double)(z >> 11) + 0.5) * (1.0 / 9007199254740992.0);
 }
 
-__global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t offset, C* __restrict__ p,
-                                                       double* __restrict__ part, size_t links_per_chain) {
+__global__ void k_u64_add(unsigned long long* p, unsigned long long inc) { *p += inc; }
+
+__global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t offset_in,
+                                                       const unsigned long long* __restrict__ offset_dev,
+                                                       C* __restrict__ p, double* __restrict__ part,
+                                                       size_t links_per_chain) {
+  // Philox stream offset: by value, plus a device-resident call counter when given (so that a
+  // CUDA-graph replay draws fresh momenta: the counter is bumped by k_u64_add after this kernel)
+  const uint64_t offset = offset_in + (offset_dev ? (uint64_t)offset_dev[0] : 0ull);
   __shared__ C sm[NTL * 9];
   __shared__ double red[NTL / 32];
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
@@ -1226,12 +1237,12 @@ int l2b_su3_from_vec(const void* vec8, void* x, size_t nmat, int dtype, void* st
   return L2B_OK;
 }
 
-int l2b_su3_update_gauge(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+int l2b_su3_update_gauge(const void* x, const void* p, double eps, const double* eps_dev, const float* mask, int mask_complement,
                          void* x_out, int nb, const int dims[4], int dtype, void* stream) {
   Geo g;
   L2B_TRY(make_geo(g, nb, dims, dtype));
   L2B_REQUIRE(x && p && x_out, L2B_ERR_INVALID, "null pointer");
-  k_update_gauge<<<dim3(g.nblk_link, nb), NTL, 0, (cudaStream_t)stream>>>((const C*)x, (const C*)p, eps, mask,
+  k_update_gauge<<<dim3(g.nblk_link, nb), NTL, 0, (cudaStream_t)stream>>>((const C*)x, (const C*)p, eps, eps_dev, mask,
                                                                           mask_complement, (C*)x_out,
                                                                           g.links_per_chain);
   L2B_LAUNCHED("k_update_gauge");
@@ -1270,8 +1281,8 @@ int l2b_su3_check(const void* x, double* avg, double* mx, int nb, const int dims
   return L2B_OK;
 }
 
-int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or_null, int nb, const int dims[4],
-                          int dtype, void* ws, size_t ws_bytes, void* stream) {
+int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, uint64_t* offset_dev_or_null, void* p, double* ke_or_null,
+                          int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
   Geo g;
   Ws w;
   L2B_TRY(make_geo(g, nb, dims, dtype));
@@ -1282,14 +1293,19 @@ int l2b_su3_rand_momentum(uint64_t seed, uint64_t offset, void* p, double* ke_or
     L2B_TRY(carve(w, g, ws, ws_bytes));
     part = w.part;
   }
-  k_rand_momentum<<<dim3(g.nblk_link, nb), NTL, 0, st>>>(seed, offset, (C*)p, part, g.links_per_chain);
+  k_rand_momentum<<<dim3(g.nblk_link, nb), NTL, 0, st>>>(seed, offset, (const unsigned long long*)offset_dev_or_null,
+                                                         (C*)p, part, g.links_per_chain);
   L2B_LAUNCHED("k_rand_momentum");
+  if (offset_dev_or_null) {
+    k_u64_add<<<1, 1, 0, st>>>((unsigned long long*)offset_dev_or_null, 1ull);
+    L2B_LAUNCHED("k_u64_add");
+  }
   if (ke_or_null)
     L2B_TRY(launch_reduce(part, g.nblk_link, 1, 0, 0.5, 0.0, ke_or_null, 1, 0, nb, st));
   return L2B_OK;
 }
 
-int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const double* eps_dev,
                     int sign, void* v_out, double* logdet, int nb, const int dims[4], int dtype, void* ws,
                     size_t ws_bytes, void* stream) {
   Geo g;
@@ -1304,7 +1320,7 @@ int l2b_su3_vupdate(const void* v, const void* force, const void* s, const void*
     part = w.part;
   }
   k_vupdate<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)v, (const C*)force, (const T*)s, (const T*)t,
-                                                   (const T*)q, eps, sign, (C*)v_out, part, g.links_per_chain);
+                                                   (const T*)q, eps, eps_dev, sign, (C*)v_out, part, g.links_per_chain);
   L2B_LAUNCHED("k_vupdate");
   if (logdet) L2B_TRY(launch_reduce(part, g.nblk_link, 1, 0, 1.0, 0.0, logdet, 1, 0, nb, st));
   return L2B_OK;
@@ -1458,7 +1474,7 @@ int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int n
   return launch_s2a(g, w.f1, (C*)gx, st);
 }
 
-int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const double* eps_dev,
                         int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
                         void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
   Geo g;
@@ -1469,14 +1485,14 @@ int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const v
   L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
   cudaStream_t st = (cudaStream_t)stream;
   k_vupdate_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)v, (const C*)force, (const T*)s, (const T*)t,
-                                                       (const T*)q, eps, sign, (const C*)gv_out, glogdet, (C*)gv,
+                                                       (const T*)q, eps, eps_dev, sign, (const C*)gv_out, glogdet, (C*)gv,
                                                        (C*)gforce, (T*)gs, (T*)gt, (T*)gq, w.part,
                                                        g.links_per_chain);
   L2B_LAUNCHED("k_vupdate_bwd");
   return launch_reduce(w.part, g.nblk_link, 1, 0, 1.0, 0.0, geps, 1, 0, nb, st);
 }
 
-int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const float* mask, int mask_complement,
+int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const double* eps_dev, const float* mask, int mask_complement,
                              const void* gx_out, void* gx, void* gp, double* geps, int* bad_flag, int nb,
                              const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
   Geo g;
@@ -1485,7 +1501,7 @@ int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const flo
   L2B_TRY(carve(w, g, ws, ws_bytes));
   L2B_REQUIRE(x && p && gx_out && gx && gp && geps && bad_flag, L2B_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  k_update_gauge_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, mask, mask_complement,
+  k_update_gauge_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, eps_dev, mask, mask_complement,
                                                             (const C*)gx_out, (C*)gx, (C*)gp, w.part, bad_flag,
                                                             g.links_per_chain);
   L2B_LAUNCHED("k_update_gauge_bwd");

@@ -195,8 +195,9 @@ __global__ void __launch_bounds__(NT) k_u1_hmc(const T* __restrict__ x, const T*
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_vupdate(const T* __restrict__ v, const T* __restrict__ f,
                                                     const T* __restrict__ s, const T* __restrict__ t,
-                                                    const T* __restrict__ q, T eps, int sign, T* __restrict__ out,
+                                                    const T* __restrict__ q, T eps_in, const T* __restrict__ eps_dev, int sign, T* __restrict__ out,
                                                     T* __restrict__ logdet, int xdim) {
+  const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ double red[8];
   const size_t row = (size_t)blockIdx.x * xdim;
   double ld = 0.0;
@@ -219,9 +220,10 @@ __global__ void __launch_bounds__(256) k_u1_vupdate(const T* __restrict__ v, con
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_xupdate(const T* __restrict__ x, const T* __restrict__ v,
                                                     const T* __restrict__ s, const T* __restrict__ t,
-                                                    const T* __restrict__ q, const float* __restrict__ mask, T eps,
+                                                    const T* __restrict__ q, const float* __restrict__ mask, T eps_in, const T* __restrict__ eps_dev,
                                                     int sign, int use_ncp, T* __restrict__ out,
                                                     T* __restrict__ logdet, int xdim) {
+  const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ double red[8];
   const size_t row = (size_t)blockIdx.x * xdim;
   double ld = 0.0;
@@ -326,11 +328,12 @@ __global__ void __launch_bounds__(256) k_u1_force_bwd(const T* __restrict__ x, T
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_vupdate_bwd(const T* __restrict__ v, const T* __restrict__ f,
                                                         const T* __restrict__ s, const T* __restrict__ t,
-                                                        const T* __restrict__ q, T eps, int sign,
+                                                        const T* __restrict__ q, T eps_in, const T* __restrict__ eps_dev, int sign,
                                                         const T* __restrict__ gout, const T* __restrict__ glogdet,
                                                         T* __restrict__ gv, T* __restrict__ gf, T* __restrict__ gs,
                                                         T* __restrict__ gt, T* __restrict__ gq, T* __restrict__ geps,
                                                         int xdim) {
+  const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ double red[8];
   const size_t row = (size_t)blockIdx.x * xdim;
   const T gl = glogdet ? glogdet[blockIdx.x] : T(0);
@@ -370,11 +373,12 @@ __global__ void __launch_bounds__(256) k_u1_vupdate_bwd(const T* __restrict__ v,
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_xupdate_bwd(const T* __restrict__ x, const T* __restrict__ v,
                                                         const T* __restrict__ s, const T* __restrict__ t,
-                                                        const T* __restrict__ q, const float* __restrict__ mask, T eps,
+                                                        const T* __restrict__ q, const float* __restrict__ mask, T eps_in, const T* __restrict__ eps_dev,
                                                         int sign, int use_ncp, const T* __restrict__ gout,
                                                         const T* __restrict__ glogdet, T* __restrict__ gx,
                                                         T* __restrict__ gv, T* __restrict__ gs, T* __restrict__ gt,
                                                         T* __restrict__ gq, T* __restrict__ geps, int xdim) {
+  const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;   // device-resident step size (CUDA graphs)
   __shared__ double red[8];
   const size_t row = (size_t)blockIdx.x * xdim;
   const T gl = glogdet ? glogdet[blockIdx.x] : T(0);
@@ -537,7 +541,7 @@ int l2b_u1_hmc_trajectory(const void* x, const void* v, double beta, double eps,
   return dispatch_hmc<double>(x, v, beta, eps, nlf, x_prop, v_prop, energies, nb, T, X, smem, st);
 }
 
-int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const void* eps_dev,
                    int sign, void* v_out, void* logdet, int nb, int xdim, int dtype, void* stream) {
   L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
   L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
@@ -546,17 +550,17 @@ int l2b_u1_vupdate(const void* v, const void* force, const void* s, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   L2B_DISPATCH_T(dtype,
                  (k_u1_vupdate<float><<<nb, 256, 0, st>>>((const float*)v, (const float*)force, (const float*)s,
-                                                          (const float*)t, (const float*)q, (float)eps, sign,
+                                                          (const float*)t, (const float*)q, (float)eps, (const float*)eps_dev, sign,
                                                           (float*)v_out, (float*)logdet, xdim)),
                  (k_u1_vupdate<double><<<nb, 256, 0, st>>>((const double*)v, (const double*)force, (const double*)s,
-                                                           (const double*)t, (const double*)q, eps, sign,
+                                                           (const double*)t, (const double*)q, eps, (const double*)eps_dev, sign,
                                                            (double*)v_out, (double*)logdet, xdim)));
   L2B_LAUNCHED("k_u1_vupdate");
   return L2B_OK;
 }
 
 int l2b_u1_xupdate(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
-                   double eps, int sign, int use_ncp, void* x_out, void* logdet, int nb, int xdim, int dtype,
+                   double eps, const void* eps_dev, int sign, int use_ncp, void* x_out, void* logdet, int nb, int xdim, int dtype,
                    void* stream) {
   L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
   L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
@@ -565,10 +569,10 @@ int l2b_u1_xupdate(const void* x, const void* v, const void* s, const void* t, c
   cudaStream_t st = (cudaStream_t)stream;
   L2B_DISPATCH_T(dtype,
                  (k_u1_xupdate<float><<<nb, 256, 0, st>>>((const float*)x, (const float*)v, (const float*)s,
-                                                          (const float*)t, (const float*)q, mask, (float)eps, sign,
+                                                          (const float*)t, (const float*)q, mask, (float)eps, (const float*)eps_dev, sign,
                                                           use_ncp, (float*)x_out, (float*)logdet, xdim)),
                  (k_u1_xupdate<double><<<nb, 256, 0, st>>>((const double*)x, (const double*)v, (const double*)s,
-                                                           (const double*)t, (const double*)q, mask, eps, sign,
+                                                           (const double*)t, (const double*)q, mask, eps, (const double*)eps_dev, sign,
                                                            use_ncp, (double*)x_out, (double*)logdet, xdim)));
   L2B_LAUNCHED("k_u1_xupdate");
   return L2B_OK;
@@ -625,7 +629,7 @@ int l2b_u1_force_bwd(const void* x, double beta, const void* gforce, void* gx, i
   return L2B_OK;
 }
 
-int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps,
+int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const void* eps_dev,
                        int sign, const void* gv_out, const void* glogdet, void* gv, void* gforce, void* gs, void* gt,
                        void* gq, void* geps, int nb, int xdim, int dtype, void* stream) {
   L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
@@ -635,11 +639,11 @@ int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const vo
   cudaStream_t st = (cudaStream_t)stream;
   L2B_DISPATCH_T(dtype,
                  (k_u1_vupdate_bwd<float><<<nb, 256, 0, st>>>(
-                     (const float*)v, (const float*)force, (const float*)s, (const float*)t, (const float*)q, (float)eps,
+                     (const float*)v, (const float*)force, (const float*)s, (const float*)t, (const float*)q, (float)eps, (const float*)eps_dev,
                      sign, (const float*)gv_out, (const float*)glogdet, (float*)gv, (float*)gforce, (float*)gs,
                      (float*)gt, (float*)gq, (float*)geps, xdim)),
                  (k_u1_vupdate_bwd<double><<<nb, 256, 0, st>>>(
-                     (const double*)v, (const double*)force, (const double*)s, (const double*)t, (const double*)q, eps,
+                     (const double*)v, (const double*)force, (const double*)s, (const double*)t, (const double*)q, eps, (const double*)eps_dev,
                      sign, (const double*)gv_out, (const double*)glogdet, (double*)gv, (double*)gforce, (double*)gs,
                      (double*)gt, (double*)gq, (double*)geps, xdim)));
   L2B_LAUNCHED("k_u1_vupdate_bwd");
@@ -647,7 +651,7 @@ int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const vo
 }
 
 int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
-                       double eps, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
+                       double eps, const void* eps_dev, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
                        void* gs, void* gt, void* gq, void* geps, int nb, int xdim, int dtype, void* stream) {
   L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
   L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
@@ -657,10 +661,10 @@ int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* 
   L2B_DISPATCH_T(dtype,
                  (k_u1_xupdate_bwd<float><<<nb, 256, 0, st>>>(
                      (const float*)x, (const float*)v, (const float*)s, (const float*)t, (const float*)q, mask,
-                     (float)eps, sign, use_ncp, (const float*)gx_out, (const float*)glogdet, (float*)gx, (float*)gv,
+                     (float)eps, (const float*)eps_dev, sign, use_ncp, (const float*)gx_out, (const float*)glogdet, (float*)gx, (float*)gv,
                      (float*)gs, (float*)gt, (float*)gq, (float*)geps, xdim)),
                  (k_u1_xupdate_bwd<double><<<nb, 256, 0, st>>>(
-                     (const double*)x, (const double*)v, (const double*)s, (const double*)t, (const double*)q, mask, eps,
+                     (const double*)x, (const double*)v, (const double*)s, (const double*)t, (const double*)q, mask, eps, (const double*)eps_dev,
                      sign, use_ncp, (const double*)gx_out, (const double*)glogdet, (double*)gx, (double*)gv,
                      (double*)gs, (double*)gt, (double*)gq, (double*)geps, xdim)));
   L2B_LAUNCHED("k_u1_xupdate_bwd");

@@ -178,7 +178,8 @@ struct HeadsArgs {
   double2* out;
   double* part;                 // [nb, ntiles] logdet partials (may be null)
   float* stq;                   // optional [3, nb, xdim] fp32 dump of (s, t, q)
-  double eps;
+  double eps;                   // multiplies *eps_dev when that is given
+  const double* eps_dev;        // device-resident step size (CUDA graphs) or null
   int sign, nb, xdim, H, KP, ntiles;
 };
 
@@ -192,8 +193,9 @@ __device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t 
   const float bs = col_ok ? __ldg(a.bias[0] + j) : 0.f, bt = col_ok ? __ldg(a.bias[1] + j) : 0.f,
               bq = col_ok ? __ldg(a.bias[2] + j) : 0.f;
   const float as = col_ok ? __ldg(a.scale_s + j) : 0.f, aq = col_ok ? __ldg(a.scale_q + j) : 0.f, at = a.scale_t;
-  const float epsf = (float)a.eps, hs = (FWD ? 0.5f : -0.5f) * epsf;
-  const double he = 0.5 * a.eps;
+  const double epsd = a.eps_dev ? a.eps * a.eps_dev[0] : a.eps;
+  const float epsf = (float)epsd, hs = (FWD ? 0.5f : -0.5f) * epsf;
+  const double he = 0.5 * epsd;
   const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
   float* ljw = sm.lj[warp];
   const size_t xd = (size_t)a.xdim;
@@ -407,7 +409,8 @@ int l2b_vnet_pack_heads(const void* w_s, const void* w_t, const void* w_q, int w
 
 int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
                           const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
-                          const void* v, const void* force, double eps, int sign, void* v_out, double* logdet,
+                          const void* v, const void* force, double eps, const double* eps_dev, int sign, void* v_out,
+                          double* logdet,
                           float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream) {
   L2B_REQUIRE(z && packed && bias_s && bias_t && bias_q && scale_s && scale_q && v && force && v_out,
               L2B_ERR_INVALID, "null pointer");
@@ -424,7 +427,7 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
   a.scale_s = scale_s; a.scale_q = scale_q; a.scale_t = scale_t;
   a.v = (const double2*)v; a.f = (const double2*)force; a.out = (double2*)v_out;
   a.stq = stq_or_null;
-  a.eps = eps; a.sign = sign; a.nb = nb; a.xdim = xdim; a.H = hidden;
+  a.eps = eps; a.eps_dev = eps_dev; a.sign = sign; a.nb = nb; a.xdim = xdim; a.H = hidden;
   a.KP = (hidden + KC - 1) / KC * KC;
   a.ntiles = (xdim + BM - 1) / BM;
   a.part = nullptr;

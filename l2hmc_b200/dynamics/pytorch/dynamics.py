@@ -493,9 +493,9 @@ class Dynamics(nn.Module):
 
     def _eps(self, p: Tensor) -> float:
         """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394) as a host
-        float for the kernels' by-value argument.  All 2*nlf step sizes are read back with ONE
-        device->host copy and cached until a parameter changes (optimizer step / assign_eps),
-        instead of a synchronising float() in every link and momentum update."""
+        float (logging / callers that want a number).  The update kernels do NOT use this: they
+        read the 0-dim device tensor `_eps_t(p)` directly (include/l2b.h, `eps_dev`).  All 2*nlf
+        step sizes are read back with ONE device->host copy and cached until a parameter changes."""
         params = list(self.xeps) + list(self.veps)
         key = tuple((id(q), q._version) for q in params)
         cache = getattr(self, '_eps_cache', None)
@@ -550,7 +550,7 @@ class Dynamics(nn.Module):
     def _update_v(self, step: int, state: State, sign: int) -> tuple[State, Tensor]:
         """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel"""
         force = self.grad_potential(state.x, state.beta)
-        eps = self._eps(self.veps[step])
+        eps = None      # the kernels read the step size from the device tensor (no host round trip)
         if self._su3 and self._networks_built and self._fused_heads(self._get_vnet(step)):
             vnet = self._get_vnet(step)
             dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
@@ -575,7 +575,7 @@ class Dynamics(nn.Module):
 
     def _update_x(self, step: int, state: State, m: Tensor, first: bool, sign: int) -> tuple[State, Tensor]:
         """dynamics.py:1386-1477"""
-        eps = self._eps(self.xeps[step])
+        eps = None      # device-resident step size, as in _update_v
         x = self.unflatten(state.x)
         if self._su3:
             # x' = m*x + exp(+-eps v) @ ((1-m)*x); xnet is never called, logdet = 0

@@ -87,7 +87,25 @@ def randTAH3(shape: Sequence[int], device=None) -> Tensor:
         pad = (-n) % 4
         p = ops.su3_rand_momentum(1, [1, 1, 1, (n + pad) // 4], torch.initial_seed(), next(_RNG_CALLS), device)
         return p.reshape(-1, 3, 3)[:n].reshape(*shape, 3, 3)
+    if torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the host call counter would be frozen into the graph:
+        # use a device-resident counter in a disjoint offset range (bit 62 set) instead
+        return ops.su3_rand_momentum(nb, dims, torch.initial_seed(), (1 << 62) + (next(_RNG_CALLS) << 32), device,
+                                     offset_dev=_graph_counter(device))
     return ops.su3_rand_momentum(nb, dims, torch.initial_seed(), next(_RNG_CALLS), device)
+
+
+_GRAPH_COUNTERS: dict = {}
+
+
+def _graph_counter(device) -> Tensor:
+    """one int64 device scalar per device, allocated OUTSIDE any capture (first use warms it up)"""
+    key = torch.device(device).index
+    if key not in _GRAPH_COUNTERS:
+        if torch.cuda.is_current_stream_capturing():
+            raise ops.L2BError('run one SU(3) step eagerly before capturing (the RNG counter is not allocated yet)')
+        _GRAPH_COUNTERS[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _GRAPH_COUNTERS[key]
 
 
 class SU3(Group):

@@ -26,6 +26,15 @@ class LatticeLoss:
         if not isinstance(lattice, (LatticeU1, LatticeSU3)):
             raise ValueError(f'Unexpected lattice: {lattice}')
         self.g = lattice.g
+        self._dev_weights: dict = {}
+
+    def _w(self, w: Tensor, like: Tensor) -> Tensor:
+        """loss weight on `like`'s device, copied once (an H2D copy per call would synchronise and
+        cannot be captured in a CUDA graph)"""
+        key = (id(w), like.device)
+        if key not in self._dev_weights:
+            self._dev_weights[key] = w.to(like.device)
+        return self._dev_weights[key]
 
     def __call__(self, x_init: Tensor, x_prop: Tensor, acc: Tensor) -> Tensor:
         return self.calc_loss(x_init=x_init, x_prop=x_prop, acc=acc)
@@ -40,8 +49,8 @@ class LatticeLoss:
         ploss = acc * (p2 - p1) ** 2
         if use_mixed_loss:
             ploss = ploss + 1e-4
-            return self.mixed_loss(ploss, self.plaq_weight.to(ploss.device)).mean()
-        return (-ploss / self.plaq_weight.to(ploss.device)).mean()
+            return self.mixed_loss(ploss, self._w(self.plaq_weight, ploss)).mean()
+        return (-ploss / self._w(self.plaq_weight, ploss)).mean()
 
     def _charge_loss(self, w1: Tensor, w2: Tensor, acc: Tensor, use_mixed_loss: Optional[bool] = None) -> Tensor:
         q1 = self.lattice._sin_charges(wloops=w1)
@@ -50,8 +59,8 @@ class LatticeLoss:
         use_mixed = self.config.use_mixed_loss if use_mixed_loss is None else use_mixed_loss
         if use_mixed:
             qloss = qloss + 1e-4
-            return self.mixed_loss(qloss, self.charge_weight.to(qloss.device)).mean()
-        return (-qloss / self.charge_weight.to(qloss.device)).mean()
+            return self.mixed_loss(qloss, self._w(self.charge_weight, qloss)).mean()
+        return (-qloss / self._w(self.charge_weight, qloss)).mean()
 
     def lattice_metrics(self, xinit: Tensor, xout: Optional[Tensor] = None) -> dict[str, Tensor]:
         metrics = self.lattice.calc_metrics(x=xinit)
@@ -77,8 +86,8 @@ class LatticeLoss:
         use_mixed = self.config.use_mixed_loss if use_mixed_loss is None else use_mixed_loss
         if use_mixed:
             rmse_loss = rmse_loss + 1e-4
-            return self.mixed_loss(rmse_loss, self.rmse_weight.to(rmse_loss.device)).mean()
-        return (-rmse_loss / self.rmse_weight.to(rmse_loss.device)).mean()
+            return self.mixed_loss(rmse_loss, self._w(self.rmse_weight, rmse_loss)).mean()
+        return (-rmse_loss / self._w(self.rmse_weight, rmse_loss)).mean()
 
     def general_loss(self, x_init, x_prop, acc, plaq_weight=None, charge_weight=None, use_mixed_loss=None):
         wl_init = self.lattice.wilson_loops(x=x_init)
@@ -97,7 +106,7 @@ class LatticeLoss:
         x_prop = x_prop.reshape(x_init.shape)
         wl_init = self.lattice.wilson_loops(x=x_init)
         wl_prop = self.lattice.wilson_loops(x=x_prop)
-        zero = torch.tensor(0., dtype=acc.dtype, device=acc.device)
+        zero = acc.new_zeros(())
         rmse = self.rmse_loss(x_init, x_prop, acc) if self.rmse_weight > 0 else zero
         plaq = self._plaq_loss(wl_init, wl_prop, acc) if self.plaq_weight > 0 else zero
         charge = self._charge_loss(wl_init, wl_prop, acc) if self.charge_weight > 0 else zero

@@ -218,7 +218,10 @@ class LeapfrogLayer(nn.Module):
         ps = self.head_params()
         key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q)
         cached = getattr(self, '_heads_pack', None)
-        if cached is None or cached[0] != key:
+        # a training step captured in a CUDA graph changes the weights on every replay without
+        # Python running: the pack kernel must then be part of the graph
+        repack = torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()
+        if cached is None or cached[0] != key or repack:
             ws, bs, cs, wt, bt, wq, bq, cq = ps
             with torch.no_grad():
                 pack = ops.vnet_pack_heads(ws, wt, wq, bs, bt, bq, cs, cq, self.nw.s, self.nw.t, self.nw.q)

@@ -50,6 +50,20 @@ def _workspace(nbytes: int, device: torch.device) -> Tensor:
     return ws
 
 
+def _eps_args(eps, dtype: torch.dtype, mult: float = 1.0):
+    """Step size for the L2HMC update kernels: a Python number goes by value; a 0-dim CUDA tensor
+    (the trainable `xeps`/`veps` after sigmoid(log(.))) stays on the device and the kernel reads
+    eps = mult * (*ptr), so nothing synchronises and the call can be captured in a CUDA graph.
+    -> (by-value double, device pointer, keep-alive)"""
+    if isinstance(eps, Tensor):
+        e = eps.detach()
+        if e.is_cuda:
+            e = e.to(dtype).reshape(1).contiguous()
+            return float(mult), c_void_p(e.data_ptr()), e
+        return float(mult) * float(e), c_void_p(0), None
+    return float(mult) * float(eps), c_void_p(0), None
+
+
 def free_workspaces() -> None:
     _WS.clear()
 
@@ -187,8 +201,9 @@ def su3_from_vec(v: Tensor) -> Tensor:
     return x
 
 
-def su3_update_gauge(x: Tensor, p: Tensor, eps: float = 1.0, mask: Optional[Tensor] = None,
-                     mask_complement: bool = False) -> Tensor:
+def su3_update_gauge(x: Tensor, p: Tensor, eps=1.0, mask: Optional[Tensor] = None,
+                     mask_complement: bool = False, eps_mult: float = 1.0) -> Tensor:
+    """x' = m*x + exp(eps_mult * eps * p) ((1-m)*x); eps: number or 0-dim CUDA tensor"""
     x, nb, dims = _su3_field(x)
     p, nbp, _ = _su3_field(p, dims)
     if p.shape != x.shape:
@@ -199,7 +214,8 @@ def su3_update_gauge(x: Tensor, p: Tensor, eps: float = 1.0, mask: Optional[Tens
         if mask.numel() != x[0].numel():
             raise L2BError(f'mask has {mask.numel()} entries, expected {x[0].numel()}')
     out = torch.empty_like(x)
-    call('l2b_su3_update_gauge', _ptr(x), _ptr(p), float(eps), _ptr(mask), int(mask_complement), _ptr(out), nb,
+    ev, ep, _keep = _eps_args(eps, torch.float64, eps_mult)
+    call('l2b_su3_update_gauge', _ptr(x), _ptr(p), ev, ep, _ptr(mask), int(mask_complement), _ptr(out), nb,
          dims4(dims), L2B_F64, _stream())
     return out
 
@@ -221,7 +237,10 @@ def su3_check(x: Tensor) -> tuple[Tensor, Tensor]:
     return avg, mx
 
 
-def su3_rand_momentum(nb: int, dims: Sequence[int], seed: int, offset: int, device, want_ke: bool = False):
+def su3_rand_momentum(nb: int, dims: Sequence[int], seed: int, offset: int, device, want_ke: bool = False,
+                      offset_dev: Optional[Tensor] = None):
+    """offset_dev: optional int64 CUDA scalar added to `offset` and bumped by one after the draw
+    (CUDA-graph replays then draw fresh momenta)"""
     device = torch.device(device)
     if device.type != 'cuda':
         raise L2BError('su3_rand_momentum needs a CUDA device')
@@ -229,13 +248,14 @@ def su3_rand_momentum(nb: int, dims: Sequence[int], seed: int, offset: int, devi
     ke = torch.empty(nb, dtype=torch.float64, device=device) if want_ke else None
     ws, n = _su3_ws(nb, dims, device)
     with torch.cuda.device(device):
-        call('l2b_su3_rand_momentum', int(seed) & (2**64 - 1), int(offset), _ptr(p), _ptr(ke), nb, dims4(dims),
+        call('l2b_su3_rand_momentum', int(seed) & (2**64 - 1), int(offset), _ptr(offset_dev), _ptr(p), _ptr(ke), nb,
+             dims4(dims),
              L2B_F64, _ptr(ws), n, _stream())
     return (p, ke) if want_ke else p
 
 
 def su3_vupdate(v: Tensor, force: Tensor, s: Optional[Tensor], t: Optional[Tensor], q: Optional[Tensor],
-                eps: float, sign: int) -> tuple[Tensor, Tensor]:
+                eps, sign: int) -> tuple[Tensor, Tensor]:
     v, nb, dims = _su3_field(v)
     force, _, _ = _su3_field(force, dims)
     xdim = v[0].numel()
@@ -252,7 +272,8 @@ def su3_vupdate(v: Tensor, force: Tensor, s: Optional[Tensor], t: Optional[Tenso
     out = torch.empty_like(v)
     logdet = torch.empty(nb, dtype=torch.float64, device=v.device)
     ws, n = _su3_ws(nb, dims, v.device)
-    call('l2b_su3_vupdate', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(out),
+    ev, ep, _keep = _eps_args(eps, torch.float64)
+    call('l2b_su3_vupdate', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), ev, ep, int(sign), _ptr(out),
          _ptr(logdet), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
     return out, logdet
 
@@ -350,7 +371,7 @@ def _rows(a: Optional[Tensor], nb: int, like: Tensor) -> Optional[Tensor]:
     return a.to(like.dtype).reshape(nb, -1).contiguous()
 
 
-def u1_vupdate(v: Tensor, force: Tensor, s, t, q, eps: float, sign: int) -> tuple[Tensor, Tensor]:
+def u1_vupdate(v: Tensor, force: Tensor, s, t, q, eps, sign: int) -> tuple[Tensor, Tensor]:
     _need_cuda(v, force)
     nb = v.shape[0]
     v2 = v.reshape(nb, -1).contiguous()
@@ -359,12 +380,13 @@ def u1_vupdate(v: Tensor, force: Tensor, s, t, q, eps: float, sign: int) -> tupl
     s, t, q = _rows(s, nb, v2), _rows(t, nb, v2), _rows(q, nb, v2)
     out = torch.empty_like(v2)
     logdet = torch.empty(nb, dtype=v.dtype, device=v.device)
-    call('l2b_u1_vupdate', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(out),
+    ev, ep, _keep = _eps_args(eps, v2.dtype)
+    call('l2b_u1_vupdate', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), ev, ep, int(sign), _ptr(out),
          _ptr(logdet), nb, xdim, _dt(v2), _stream())
     return out.reshape(v.shape), logdet
 
 
-def u1_xupdate(x: Tensor, v: Tensor, s, t, q, mask: Tensor, eps: float, sign: int, use_ncp: bool):
+def u1_xupdate(x: Tensor, v: Tensor, s, t, q, mask: Tensor, eps, sign: int, use_ncp: bool):
     _need_cuda(x, v, mask)
     nb = x.shape[0]
     x2 = x.reshape(nb, -1).contiguous()
@@ -376,7 +398,8 @@ def u1_xupdate(x: Tensor, v: Tensor, s, t, q, mask: Tensor, eps: float, sign: in
         raise L2BError(f'mask has {mask.numel()} entries, expected {xdim}')
     out = torch.empty_like(x2)
     logdet = torch.empty(nb, dtype=x.dtype, device=x.device)
-    call('l2b_u1_xupdate', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), float(eps), int(sign),
+    ev, ep, _keep = _eps_args(eps, x2.dtype)
+    call('l2b_u1_xupdate', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), ev, ep, int(sign),
          int(bool(use_ncp)), _ptr(out), _ptr(logdet), nb, xdim, _dt(x2), _stream())
     return out.reshape(x.shape), logdet
 
@@ -448,7 +471,7 @@ def u1_force_bwd(x: Tensor, beta: float, gforce: Tensor, shape=None) -> Tensor:
     return gx
 
 
-def u1_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
+def u1_vupdate_bwd(v, force, s, t, q, eps, sign: int, gv_out, glogdet):
     nb = v.shape[0]
     v2 = v.reshape(nb, -1).contiguous()
     f2 = force.to(v.dtype).reshape(nb, -1).contiguous()
@@ -461,12 +484,13 @@ def u1_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
     gt = torch.empty_like(v2) if t is not None else None
     gq = torch.empty_like(v2) if q is not None else None
     geps = torch.empty(nb, dtype=v.dtype, device=v.device)
-    call('l2b_u1_vupdate_bwd', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(go),
+    ev, ep, _keep = _eps_args(eps, v2.dtype)
+    call('l2b_u1_vupdate_bwd', _ptr(v2), _ptr(f2), _ptr(s), _ptr(t), _ptr(q), ev, ep, int(sign), _ptr(go),
          _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, xdim, _dt(v2), _stream())
     return gv, gf, gs, gt, gq, geps
 
 
-def u1_xupdate_bwd(x, v, s, t, q, mask, eps: float, sign: int, use_ncp: bool, gx_out, glogdet):
+def u1_xupdate_bwd(x, v, s, t, q, mask, eps, sign: int, use_ncp: bool, gx_out, glogdet):
     nb = x.shape[0]
     x2 = x.reshape(nb, -1).contiguous()
     v2 = v.to(x.dtype).reshape(nb, -1).contiguous()
@@ -480,7 +504,8 @@ def u1_xupdate_bwd(x, v, s, t, q, mask, eps: float, sign: int, use_ncp: bool, gx
     gt = torch.empty_like(x2) if t is not None else None
     gq = torch.empty_like(x2) if q is not None else None
     geps = torch.empty(nb, dtype=x.dtype, device=x.device)
-    call('l2b_u1_xupdate_bwd', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), float(eps), int(sign),
+    ev, ep, _keep = _eps_args(eps, x2.dtype)
+    call('l2b_u1_xupdate_bwd', _ptr(x2), _ptr(v2), _ptr(s), _ptr(t), _ptr(q), _ptr(mask), ev, ep, int(sign),
          int(bool(use_ncp)), _ptr(go), _ptr(gl), _ptr(gx), _ptr(gv), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, xdim,
          _dt(x2), _stream())
     return gx, gv, gs, gt, gq, geps
@@ -531,7 +556,7 @@ def su3_wilson_loops_bwd(x: Tensor, gw: Tensor) -> Tensor:
     return gx
 
 
-def su3_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
+def su3_vupdate_bwd(v, force, s, t, q, eps, sign: int, gv_out, glogdet):
     v, nb, dims = _su3_field(v)
     force, _, _ = _su3_field(force, dims)
     gv_out, _, _ = _su3_field(gv_out.to(torch.complex128), dims)
@@ -546,13 +571,14 @@ def su3_vupdate_bwd(v, force, s, t, q, eps: float, sign: int, gv_out, glogdet):
     gs, gt, gq = mk(s), mk(t), mk(q)
     geps = torch.empty(nb, dtype=torch.float64, device=v.device)
     ws, n = _su3_ws(nb, dims, v.device)
-    call('l2b_su3_vupdate_bwd', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), float(eps), int(sign), _ptr(gv_out),
+    ev, ep, _keep = _eps_args(eps, torch.float64)
+    call('l2b_su3_vupdate_bwd', _ptr(v), _ptr(force), _ptr(s), _ptr(t), _ptr(q), ev, ep, int(sign), _ptr(gv_out),
          _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gs), _ptr(gt), _ptr(gq), _ptr(geps), nb, dims4(dims), L2B_F64, _ptr(ws), n,
          _stream())
     return gv, gf, gs, gt, gq, geps
 
 
-def su3_update_gauge_bwd(x, p, eps: float, mask, mask_complement: bool, gx_out):
+def su3_update_gauge_bwd(x, p, eps, mask, mask_complement: bool, gx_out, eps_mult: float = 1.0):
     x, nb, dims = _su3_field(x)
     p, _, _ = _su3_field(p, dims)
     gx_out, _, _ = _su3_field(gx_out.to(torch.complex128), dims)
@@ -562,7 +588,8 @@ def su3_update_gauge_bwd(x, p, eps: float, mask, mask_complement: bool, gx_out):
     geps = torch.empty(nb, dtype=torch.float64, device=x.device)
     bad = torch.zeros(1, dtype=torch.int32, device=x.device)
     ws, n = _su3_ws(nb, dims, x.device)
-    call('l2b_su3_update_gauge_bwd', _ptr(x), _ptr(p), float(eps), _ptr(mask), int(mask_complement), _ptr(gx_out),
+    ev, ep, _keep = _eps_args(eps, torch.float64, eps_mult)
+    call('l2b_su3_update_gauge_bwd', _ptr(x), _ptr(p), ev, ep, _ptr(mask), int(mask_complement), _ptr(gx_out),
          _ptr(gx), _ptr(gp), _ptr(geps), _ptr(bad), nb, dims4(dims), L2B_F64, _ptr(ws), n, _stream())
     return gx, gp, geps, bad
 
@@ -612,7 +639,7 @@ def vnet_pack_heads(w_s: Tensor, w_t: Tensor, w_q: Tensor, b_s: Tensor, b_t: Ten
     return HeadsPack(packed, bias, scale_s, scale_q, nw_t, xdim, hidden)
 
 
-def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps: float, sign: int,
+def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps, sign: int,
                       want_stq: bool = False):
     """(v', logdet[, stq]) with s, t, q = heads(z) never materialised (unless want_stq:
     f32 [3, nb, xdim])"""
@@ -633,7 +660,8 @@ def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps:
     stq = torch.empty((3, nb, pack.xdim), dtype=torch.float32, device=v.device) if want_stq else None
     nws = int(_lib._lib.l2b_vnet_heads_ws_bytes(nb, pack.xdim))
     ws = _workspace(nws, v.device)
+    ev, ep, _keep = _eps_args(eps, torch.float64)
     call('l2b_su3_heads_vupdate', _ptr(z), _ptr(pack.packed), _ptr(pack.bias[0]), _ptr(pack.bias[1]),
-         _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), float(eps),
+         _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), ev, ep,
          int(sign), _ptr(out), _ptr(logdet), _ptr(stq), nb, pack.xdim, pack.hidden, _ptr(ws), nws, _stream())
     return (out, logdet, stq) if want_stq else (out, logdet)

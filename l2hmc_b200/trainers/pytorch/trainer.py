@@ -24,16 +24,66 @@ Tensor = torch.Tensor
 class Trainer:
     def __init__(self, dynamics: Dynamics, loss_config: Optional[LossConfig] = None, lr: float = 1e-3,
                  clip_val: float = 0.0, autocast_dtype: Optional[torch.dtype] = None,
-                 grad_bucket_dtype: Optional[torch.dtype] = None):
+                 grad_bucket_dtype: Optional[torch.dtype] = None, cuda_graphs: bool = False):
+        """cuda_graphs: capture each step function (one graph per input shape / beta / step
+        arguments) on first use and replay it afterwards -- the whole step, including backward
+        and Adam for `train_step`, becomes ONE graph launch.  Step sizes and the
+        SU(3) momentum RNG counter live on the device, so replays stay correct while parameters
+        train.  Needs `merge_directions` (the default) and a single process for `train_step`."""
         self.dynamics = dynamics
         self.lattice = dynamics.lattice
         self.g = dynamics.g
         self.loss_fn = LatticeLoss(self.lattice, loss_config or LossConfig())
         params = [p for p in dynamics.parameters() if p.requires_grad]
-        self.optimizer = torch.optim.Adam(params, lr=lr)
+        self.cuda_graphs = bool(cuda_graphs)
+        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=self.cuda_graphs)
         self.clip_val = clip_val
         self.autocast_dtype = autocast_dtype
         self.grad_bucket_dtype = grad_bucket_dtype
+        self._graphs: dict = {}
+        self._eager = False            # True while warming up / capturing: step functions run their eager body
+
+    # ------------------------------------------------------------ CUDA graphs
+    def _weights_version(self) -> int:
+        return sum(p._version for p in self.dynamics.parameters())
+
+    def _graphed(self, key, fn, x: Tensor, train: bool = False):
+        """run `fn(static_x) -> (x_out, metrics)` through a CUDA graph keyed by `key`"""
+        ent = self._graphs.get(key)
+        if ent is None:
+            if not self.dynamics.config.merge_directions:
+                raise RuntimeError('cuda_graphs needs merge_directions=True (the direction coin is drawn on the host)')
+            static_x = x.detach().clone()
+            if getattr(self.g, '_name', None) == 'SU3':
+                from ...group.su3.pytorch import group as su3group
+                su3group._graph_counter(static_x.device)
+            self._eager = True
+            try:
+                side = torch.cuda.Stream(device=static_x.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):           # warm-up off the capture: lazy allocations, workspaces
+                    for _ in range(3):                  # (for train_step these are three ordinary training steps)
+                        fn(static_x)
+                torch.cuda.current_stream().wait_stream(side)
+                ag._BAD_FLAGS.clear()
+                if train:
+                    self.optimizer.zero_grad(set_to_none=True)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out = fn(static_x)
+            finally:
+                self._eager = False
+            flags = list(ag._BAD_FLAGS)                 # matrix-exp adjoint range flags: static, re-read per replay
+            ag._BAD_FLAGS.clear()
+            ent = (graph, static_x, out, flags)
+            self._graphs[key] = ent
+        graph, static_x, out, flags = ent
+        static_x.copy_(x)
+        graph.replay()
+        if flags and int(torch.stack([f.reshape(()) for f in flags]).sum()) != 0:
+            raise ag.ops.L2BError('matrix-exponential adjoint: ||eps p||_F > 3 (outside the series\' validated range)')
+        xo, metrics = out
+        return xo.clone(), {k: (v.clone() if isinstance(v, Tensor) else v) for k, v in metrics.items()}
 
     def _x(self, x: Tensor) -> Tensor:
         return self.g.compat_proj(x.reshape(x.shape[0], *self.dynamics.xshape[1:]))
@@ -41,6 +91,11 @@ class Trainer:
     @torch.no_grad()
     def hmc_step(self, inputs, eps: Optional[float] = None, nleapfrog: Optional[int] = None):
         """trainer.py:904-929"""
+        if self.cuda_graphs and not self._eager:
+            xi, beta = inputs
+            xi = xi.to(self.dynamics.device)
+            key = ('hmc', tuple(xi.shape), xi.dtype, float(beta), eps, nleapfrog)
+            return self._graphed(key, lambda xs: self.hmc_step((xs, float(beta)), eps=eps, nleapfrog=nleapfrog), xi)
         xi, beta = inputs
         xi = self._x(xi.to(self.dynamics.device))
         xo, metrics = self.dynamics.apply_transition_hmc((xi, beta), eps=eps, nleapfrog=nleapfrog)
@@ -52,6 +107,12 @@ class Trainer:
     @torch.no_grad()
     def eval_step(self, inputs):
         """trainer.py:931-956"""
+        if self.cuda_graphs and not self._eager:
+            xi, beta = inputs
+            xi = xi.to(self.dynamics.device)
+            key = ('eval', tuple(xi.shape), xi.dtype, float(beta), self._weights_version(),
+                   torch.is_autocast_enabled('cuda'))
+            return self._graphed(key, lambda xs: self.eval_step((xs, float(beta))), xi)
         self.dynamics.eval()
         xi, beta = inputs
         xi = self._x(xi.to(self.dynamics.device))
@@ -62,11 +123,21 @@ class Trainer:
 
     def train_step(self, inputs):
         """forward, loss, backward, (all-reduce), clip, Adam   (trainer.py:1266-1367)"""
+        if self.cuda_graphs and not self._eager:
+            if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size() > 1:
+                raise RuntimeError('cuda_graphs for train_step is single-process for now (all-reduce not captured)')
+            xi, beta = inputs
+            xi = xi.to(self.dynamics.device)
+            key = ('train', tuple(xi.shape), xi.dtype, float(beta))
+            return self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
         self.dynamics.train()
         xi, beta = inputs
         with torch.no_grad():
             xi = self._x(xi.to(self.dynamics.device))
-        self.optimizer.zero_grad(set_to_none=True)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:       # in a captured step the gradients are static buffers the replay overwrites
+            self.optimizer.zero_grad(set_to_none=True)
         if self.autocast_dtype is not None:
             with torch.autocast('cuda', dtype=self.autocast_dtype):
                 xo, metrics = self.dynamics((xi, beta))
@@ -75,7 +146,8 @@ class Trainer:
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
         loss.backward()
-        ag.check_exp_adjoint_flags()      # one device read per step (matrix-exp adjoint range check)
+        if not capturing:
+            ag.check_exp_adjoint_flags()  # one device read per step (matrix-exp adjoint range check)
         # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks;
         # parameters without a gradient (the unused SU(3) xnet) are not communicated.
         l2dist.allreduce_mean_grads(self.optimizer.param_groups[0]['params'], self.grad_bucket_dtype)
