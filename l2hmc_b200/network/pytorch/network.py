@@ -220,7 +220,7 @@ class LeapfrogLayer(nn.Module):
         cached = getattr(self, '_heads_pack', None)
         # a training step captured in a CUDA graph changes the weights on every replay without
         # Python running: the pack kernel must then be part of the graph
-        repack = torch.cuda.is_current_stream_capturing() and torch.is_grad_enabled()
+        repack = torch.cuda.is_current_stream_capturing() and self.training and any(p.requires_grad for p in ps)
         if cached is None or cached[0] != key or repack:
             ws, bs, cs, wt, bt, wq, bq, cq = ps
             with torch.no_grad():

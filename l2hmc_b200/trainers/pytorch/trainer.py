@@ -44,6 +44,11 @@ class Trainer:
         self._eager = False            # True while warming up / capturing: step functions run their eager body
 
     # ------------------------------------------------------------ CUDA graphs
+    def _canon(self, x: Tensor) -> Tensor:
+        """on the device, in the lattice shape (the flattened x_out of the previous step maps to the same graph)"""
+        x = x.to(self.dynamics.device)
+        return x.reshape(x.shape[0], *self.dynamics.xshape[1:])
+
     def _weights_version(self) -> int:
         return sum(p._version for p in self.dynamics.parameters())
 
@@ -93,7 +98,7 @@ class Trainer:
         """trainer.py:904-929"""
         if self.cuda_graphs and not self._eager:
             xi, beta = inputs
-            xi = xi.to(self.dynamics.device)
+            xi = self._canon(xi)
             key = ('hmc', tuple(xi.shape), xi.dtype, float(beta), eps, nleapfrog)
             return self._graphed(key, lambda xs: self.hmc_step((xs, float(beta)), eps=eps, nleapfrog=nleapfrog), xi)
         xi, beta = inputs
@@ -109,7 +114,7 @@ class Trainer:
         """trainer.py:931-956"""
         if self.cuda_graphs and not self._eager:
             xi, beta = inputs
-            xi = xi.to(self.dynamics.device)
+            xi = self._canon(xi)
             key = ('eval', tuple(xi.shape), xi.dtype, float(beta), self._weights_version(),
                    torch.is_autocast_enabled('cuda'))
             return self._graphed(key, lambda xs: self.eval_step((xs, float(beta))), xi)
@@ -128,7 +133,7 @@ class Trainer:
                     and torch.distributed.get_world_size() > 1:
                 raise RuntimeError('cuda_graphs for train_step is single-process for now (all-reduce not captured)')
             xi, beta = inputs
-            xi = xi.to(self.dynamics.device)
+            xi = self._canon(xi)
             key = ('train', tuple(xi.shape), xi.dtype, float(beta))
             return self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
         self.dynamics.train()

@@ -42,7 +42,7 @@ fac = NetworkFactory(input_spec=get_input_spec(cfg),
 lat = LatticeSU3(nb, shape)
 dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
 tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
-             clip_val=1.0, autocast_dtype=torch.bfloat16)
+             clip_val=1.0, autocast_dtype=torch.bfloat16, cuda_graphs='--graph' in sys.argv)
 x = lat.random().to(torch.complex128)
 beta = torch.tensor(6.0)
 
@@ -54,7 +54,7 @@ def step():
     return tr.train_step((x, beta))
 
 
-for _ in range(2):
+for _ in range(5 if '--graph' in sys.argv else 2):
     step()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
