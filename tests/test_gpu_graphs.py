@@ -160,9 +160,11 @@ def test_su3_l2hmc_train_step_graphed_with_tensor_core_heads(f32_default):
     assert not torch.equal(w0, dyn.vnet.scale.layer.weight) and not torch.equal(e0, dyn.veps[0])
     _, mx = lat.g.checkSU(tr._x(xo))
     assert float(mx.max()) < 1e-10
-    # the packed bf16 image inside the graph follows the weights: an eager evaluation of the heads with the
-    # CURRENT weights agrees with what the graph's own pack buffer now holds
+    # the packed bf16 image inside the graph follows the weights: a replay re-packs the weights it STARTS from
     from l2hmc_b200 import ops
-    fresh = ops.vnet_pack_heads(*[dyn.vnet.head_params()[i] for i in (0, 3, 5, 1, 4, 6, 2, 7)], dyn.vnet.nw.s,
-                                dyn.vnet.nw.t, dyn.vnet.nw.q)
-    assert torch.equal(fresh.packed, dyn.vnet._heads_pack[1].packed), 're-packed on the last replay'
+    before = [p.detach().clone() for p in dyn.vnet.head_params()]
+    tr.train_step((xo, beta))
+    fresh = ops.vnet_pack_heads(*[before[i] for i in (0, 3, 5, 1, 4, 6, 2, 7)], dyn.vnet.nw.s, dyn.vnet.nw.t,
+                                dyn.vnet.nw.q)
+    assert torch.equal(fresh.packed, dyn.vnet._heads_pack[1].packed), 're-packed inside the replay'
+    assert not torch.equal(before[0], dyn.vnet.head_params()[0]), 'and Adam moved the weights afterwards'
