@@ -195,6 +195,18 @@ class Dynamics(nn.Module):
         netdir = Path(outdir).joinpath('networks')
         self.load_state_dict(torch.load(netdir.joinpath('dynamics.pt'), map_location=self.device))
 
+    def load_eps(self, outdir: os.PathLike) -> dict:
+        """dynamics.py:566-582"""
+        netdir = Path(outdir).joinpath('networks')
+        xe = torch.from_numpy(np.load(netdir.joinpath('xeps.npy')))
+        ve = torch.from_numpy(np.load(netdir.joinpath('veps.npy')))
+        n = self.config.nleapfrog
+        return {'xeps': {str(lf): xe[lf] for lf in range(n)}, 'veps': {str(lf): ve[lf] for lf in range(n)}}
+
+    def restore_eps(self, outdir: os.PathLike) -> None:
+        """dynamics.py:584-586 (note the reference's nested `networks/networks` placement, kept by save_eps)"""
+        self.assign_eps(self.load_eps(Path(outdir).joinpath('networks')))
+
     def assign_eps(self, eps) -> None:
         n = self.config.nleapfrog
         if isinstance(eps, dict):
@@ -254,6 +266,32 @@ class Dynamics(nn.Module):
         forward = bool(torch.rand(1) > 0.5)
         data = self.generate_proposal(inputs, forward=forward)
         return self._mix(data, sumlogdet_key=True)
+
+    def apply_transition_both(self, inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, dict]:
+        """forward AND backward proposals, a per-chain direction coin, then accept/reject
+        (dynamics.py:744-803).  The mixes are per-chain selects done by `k_accept_mix`."""
+        x, beta = inputs
+        fwd = self.generate_proposal(inputs, forward=True)
+        bwd = self.generate_proposal(inputs, forward=False)
+        mf_, mb_ = self._get_direction_masks(batch_size=x.shape[0])
+        mf_, mb_ = mf_.to(self.device), mb_.to(self.device)
+        v_init, xp, vp = ops.accept_mix(mf_, [(bwd['init'].v, fwd['init'].v), (bwd['proposed'].x, fwd['proposed'].x),
+                                              (bwd['proposed'].v, fwd['proposed'].v)])
+        mfwd, mbwd = fwd['metrics'], bwd['metrics']
+        logdetp = mf_ * mfwd['sumlogdet'] + mb_ * mbwd['sumlogdet']
+        acc = mf_ * mfwd['acc'] + mb_ * mbwd['acc']
+        ma_, mr_ = self._get_accept_masks(acc)
+        x_out, v_out = ops.accept_mix(ma_, [(x, xp), (v_init, vp)])
+        state_init = State(x=x, v=v_init, beta=beta)
+        state_prop = State(x=xp, v=vp, beta=beta)
+        state_out = State(x=x_out, v=v_out, beta=beta)
+        metrics = {}
+        for (key, vf), (_, vb) in zip(mfwd.items(), mbwd.items()):
+            if isinstance(vf, Tensor) and vf.dim() >= 1 and vf.shape[-1] == ma_.shape[0]:
+                metrics[key] = ma_ * (mf_ * vf + mb_ * vb)
+        metrics.update({'acc': acc, 'acc_mask': ma_, 'sumlogdet': ma_ * logdetp,
+                        'mc_states': MonteCarloStates(init=state_init, proposed=state_prop, out=state_out)})
+        return x_out, metrics
 
     def random_state(self, beta: float) -> State:
         x = self.g.random(list(self.xshape))
@@ -491,6 +529,39 @@ class Dynamics(nn.Module):
             v = torch.stack([v.real, v.imag], 1)
         return xnet((x, v))
 
+    def _stack_as_xy(self, x: Tensor) -> Tensor:
+        """[cos(x), sin(x)] on a new last axis (dynamics.py:1137-1140)"""
+        return torch.stack([x.cos(), x.sin()], dim=-1).to(self.device)
+
+    @staticmethod
+    def complexify(x: Tensor, dim: int = 1) -> Tensor:
+        """dynamics.py:1501-1535"""
+        assert len(x.shape) >= 2 and x.shape[dim] == 2
+        if dim != 1:
+            xr, xi = x.transpose(0, dim)
+            return torch.complex(xr.transpose(0, dim - 1), xi.transpose(0, dim - 1))
+        return torch.complex(x[:, 0], x[:, 1])
+
+    # plain-HMC half updates with the TRAINABLE step sizes (dynamics.py:1244-1264)
+    def _update_v_fwd_hmc(self, step: int, state: State) -> Tensor:
+        return self._update_v(step, state, +1, hmc=True)[0].v
+
+    def _update_v_bwd_hmc(self, step: int, state: State) -> Tensor:
+        return self._update_v(step, state, -1, hmc=True)[0].v
+
+    def _update_x_fwd_hmc(self, step: int, state: State) -> Tensor:
+        return self._update_x_hmc(step, state, +1)
+
+    def _update_x_bwd_hmc(self, step: int, state: State) -> Tensor:
+        return self._update_x_hmc(step, state, -1)
+
+    def _update_x_hmc(self, step: int, state: State, sign: int) -> Tensor:
+        eps_t = self._eps_t(self.xeps[step])
+        if self._su3:
+            return ag.SU3UpdateGauge.apply(self.unflatten(state.x), self.unflatten(state.v), eps_t.to(torch.float64),
+                                           None, sign, None)
+        return self.g.update_gauge(state.x.reshape_as(state.v), (sign * eps_t) * state.v)
+
     def _eps(self, p: Tensor) -> float:
         """sigmoid(log(eps)) == eps / (1 + eps)   (dynamics.py:82-83,1270,1394) as a host
         float (logging / callers that want a number).  The update kernels do NOT use this: they
@@ -547,10 +618,19 @@ class Dynamics(nn.Module):
             return True
         return torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
 
-    def _update_v(self, step: int, state: State, sign: int) -> tuple[State, Tensor]:
-        """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel"""
+    def _update_v(self, step: int, state: State, sign: int, hmc: bool = False) -> tuple[State, Tensor]:
+        """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel (hmc=True: no
+        networks, the plain half kick v -+ eps/2 F of dynamics.py:1244-1254)"""
         force = self.grad_potential(state.x, state.beta)
         eps = None      # the kernels read the step size from the device tensor (no host round trip)
+        if hmc:
+            if self._su3:
+                return State(state.x, ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), None, None,
+                                                          None, self._eps_t(self.veps[step]).to(torch.float64), sign,
+                                                          eps)[0], state.beta), self._zeros(state.x.shape[0])
+            f = force.reshape_as(state.v)
+            return State(state.x, ag.U1VUpdate.apply(state.v, f, None, None, None, self._eps_t(self.veps[step]), sign,
+                                                     eps)[0], state.beta), self._zeros(state.x.shape[0])
         if self._su3 and self._networks_built and self._fused_heads(self._get_vnet(step)):
             vnet = self._get_vnet(step)
             dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype

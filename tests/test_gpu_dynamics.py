@@ -177,3 +177,57 @@ def test_hmc_public_api_contract(golden_dir, default_dtype):
     assert maxdiff(host(m['dsdx']), g['force']) < 1e-12
     assert maxdiff(host(lat.g.group_to_vec(dev(g['x']))), g['vec_x']) < 1e-12
     assert maxdiff(host(lat.g.update_gauge(dev(g['x']), 0.1 * dev(g['v']))), g['upd']) < 1e-12
+
+
+def test_hmc_half_updates_and_apply_transition_both(default_dtype):
+    """the remaining public Dynamics methods of the reference (dynamics.py:744-803,1244-1264)"""
+    from l2hmc_b200 import ops
+    from l2hmc_b200.configs import DynamicsConfig, NetworkConfig, get_input_spec
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    default_dtype(torch.float64)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    # U(1)
+    nb, shape = 5, [6, 4]
+    cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=2, eps=0.2, verbose=False,
+                         merge_directions=False)
+    fac = NetworkFactory(input_spec=get_input_spec(cfg), network_config=NetworkConfig(units=[8], activation_fn='tanh',
+                         dropout_prob=0.0, use_batch_norm=False), conv_config=None, net_weights=None)
+    lat = LatticeU1(nb, shape)
+    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+    x, v, beta = lat.random(), lat.g.random_momentum([nb, 2, *shape]), torch.tensor(2.5)
+    st = State(x, v, beta)
+    e = float(torch.sigmoid(dyn.veps[1].log()))
+    f = lat.grad_action(x, beta).reshape(nb, -1)
+    assert float((dyn._update_v_fwd_hmc(1, st) - (v - 0.5 * e * f)).abs().max()) < 1e-13
+    assert float((dyn._update_v_bwd_hmc(1, st) - (v + 0.5 * e * f)).abs().max()) < 1e-13
+    ex = float(torch.sigmoid(dyn.xeps[0].log()))
+    assert float((dyn._update_x_fwd_hmc(0, st) - (x.reshape(nb, -1) + ex * v)).abs().max()) < 1e-13
+    assert float((dyn._update_x_bwd_hmc(0, st) - (x.reshape(nb, -1) - ex * v)).abs().max()) < 1e-13
+    with torch.no_grad():
+        xo, m = dyn.apply_transition_both((x, beta))
+    ms = m['mc_states']
+    assert xo.shape == (nb, 2 * 24) and m['acc'].shape == (nb,) and set(m['acc_mask'].tolist()) <= {0.0, 1.0}
+    for b in range(nb):      # per chain: out is the proposal iff accepted
+        want = ms.proposed.x[b] if float(m['acc_mask'][b]) == 1.0 else x[b].reshape(-1)
+        assert torch.equal(xo[b], want.reshape(-1))
+    z = torch.randn(3, 2, 4, device=DEV)
+    assert torch.equal(Dynamics.complexify(z), torch.complex(z[:, 0], z[:, 1]))
+    assert dyn._stack_as_xy(x).shape == (*x.shape, 2)
+    # SU(3)
+    nb, shape = 2, [2, 2, 2, 4]
+    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=1, eps=0.1, verbose=False,
+                         use_split_xnets=False, use_separate_networks=False)
+    lat3 = LatticeSU3(nb, shape)
+    dyn3 = Dynamics(potential_fn=lat3.action, config=cfg, network_factory=None)
+    x3, v3 = lat3.random(), lat3.random_momentum()
+    st3 = State(x3, v3, torch.tensor(5.5))
+    e3 = float(torch.sigmoid(dyn3.xeps[0].log()))
+    assert float((dyn3._update_x_fwd_hmc(0, st3) - ops.su3_update_gauge(x3, v3, e3)).abs().max()) < 1e-14
+    assert float((dyn3._update_x_bwd_hmc(0, st3) - ops.su3_update_gauge(x3, v3, -e3)).abs().max()) < 1e-14
+    ev = float(torch.sigmoid(dyn3.veps[0].log()))
+    f3 = lat3.grad_action(x3, torch.tensor(5.5))
+    assert float((dyn3._update_v_fwd_hmc(0, st3) - (v3 - 0.5 * ev * f3)).abs().max()) < 1e-13
