@@ -362,9 +362,9 @@ class Dynamics(nn.Module):
         beta = _fbeta(state.beta)
         if self._su3:
             x, v = self.unflatten(state.x), self.unflatten(state.v)
-            v1, _ = ops.su3_vupdate(v, ops.su3_force(x, beta), None, None, None, eps, +1)
+            v1, _ = ops.su3_vupdate(v, self.grad_potential(x, state.beta).detach(), None, None, None, eps, +1)
             xp = ops.su3_update_gauge(x, v1, eps)
-            v2, _ = ops.su3_vupdate(v1, ops.su3_force(xp, beta), None, None, None, eps, +1)
+            v2, _ = ops.su3_vupdate(v1, self.grad_potential(xp, state.beta).detach(), None, None, None, eps, +1)
             return State(x=xp, v=v2, beta=state.beta)
         x_ = state.x.reshape_as(state.v)
         shape = self.config.latvolume
@@ -383,6 +383,12 @@ class Dynamics(nn.Module):
             eps = 1. / nlf
         nleapfrog = nlf if nleapfrog is None else nleapfrog
         beta = _fbeta(state.beta)
+        if self._su3 and getattr(self.lattice, 'c1', 0.0) != 0.0 and not self.config.verbose:
+            # rectangle action: the fused trajectory kernel integrates the plain Wilson force only
+            state_ = State(x=state.x, v=state.v, beta=state.beta)
+            for _ in range(nleapfrog):
+                state_ = self.leapfrog_hmc(state_, eps=eps)
+            return state_, {'acc': self.compute_accept_prob(state, state_, sumlogdet), 'sumlogdet': sumlogdet}
         if self.config.verbose:
             state_ = State(x=state.x, v=state.v, beta=state.beta)
             history = self.update_history(self.get_metrics(state_, sumlogdet), {})

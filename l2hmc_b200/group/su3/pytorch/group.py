@@ -74,6 +74,61 @@ def norm2(x: Tensor, axis: Sequence[int] = (-2, -1), exclude: Optional[Sequence[
     return n.sum([i for i in range(len(n.shape)) if i not in exclude])
 
 
+def eyeOf(x: Tensor) -> Tensor:
+    """broadcastable real identity (utils.py:134-141)"""
+    eye = torch.zeros([1] * (x.dim() - 2) + [*x.shape[-2:]], device=x.device)
+    eye[-2:] = torch.eye(x.shape[-1], device=x.device)
+    return eye
+
+
+def checkU(x: Tensor) -> tuple[Tensor, Tensor]:
+    """average / maximum deviation of X^+X from 1 (utils.py:362-374); a diagnostic, plain torch"""
+    nc = x.shape[-1]
+    d = norm2(x.mH @ x - eyeOf(x)).flatten(1)
+    c = 2 * (nc * nc + 1)
+    return (d.mean(-1) / c).sqrt(), (d.max(-1)[0] / c).sqrt()
+
+
+def rsqrtPHM3f(tr: Tensor, p2: Tensor, det: Tensor) -> tuple[Tensor, Tensor, Tensor]:
+    """coefficients of X^{-1/2} = c0 + c1 X + c2 X^2 for positive Hermitian 3x3 X from its
+    invariants (utils.py:227-317, clamps included) -- the same closed form `k_unary<PROJECT>` uses
+    per link; this torch version serves callers outside the integrator"""
+    tr3, p23 = tr / 3.0, p2 / 3.0
+    tr32 = tr3 * tr3
+    q = (0.5 * (p23 - tr32)).abs()
+    r = 0.25 * tr3 * (5.0 * tr32 - p2) - 0.5 * det
+    sq = q.sqrt()
+    isq3 = (1.0 / (q * sq)).clamp(-3e38, 3e38)
+    rsq3 = (r * isq3).clamp(-1.0, 1.0).clamp(-1.0 + 1e-12, 1.0 - 1e-12)
+    t = torch.acos(rsq3) / 3.0
+    sqc, sqs = sq * t.cos(), (3.0 ** 0.5) * sq * t.sin()
+    ll = tr3 + sqc
+    e0, e1, e2 = tr3 - 2.0 * sqc, ll + sqs, ll - sqs
+    s0, s1, s2 = e0.abs().sqrt(), e1.abs().sqrt(), e2.abs().sqrt()
+    u, w = s0 + s1 + s2, s0 * s1 * s2
+    di = 1.0 / (w * (s0 + s1) * (s0 + s2) * (s1 + s2))
+    c0 = di * (w * u * u + e0 * s0 * (e1 + e2) + e1 * s1 * (e0 + e2) + e2 * s2 * (e0 + e1))
+    return c0, -(tr * u + w) * di, u * di
+
+
+def rsqrtPHM3(x: Tensor) -> Tensor:
+    """X^{-1/2} of a positive Hermitian 3x3 (utils.py:320-330)"""
+    tr = torch.diagonal(x, dim1=-2, dim2=-1).sum(-1).real
+    x2 = x @ x
+    p2 = torch.diagonal(x2, dim1=-2, dim2=-1).sum(-1).real
+    c0, c1, c2 = (c[..., None, None].to(x.dtype) for c in rsqrtPHM3f(tr, p2, torch.linalg.det(x).real))
+    return c0 * torch.eye(3, dtype=x.dtype, device=x.device) + c1 * x + c2 * x2
+
+
+def projectU(x: Tensor) -> Tensor:
+    """X (X^+X)^{-1/2}: the unitary polar factor without the determinant phase (utils.py:333-338).
+    projectSU(X) = projectU(X) e^{-i arg det / 3} and arg det projectU(X) = arg det X, so the
+    kernel's projectSU is re-phased instead of repeating the eigen-solve in torch."""
+    y = ops.su3_project(x)
+    ph = torch.angle(torch.linalg.det(x)) / 3.0
+    return y * torch.polar(torch.ones_like(ph), ph)[..., None, None]
+
+
 def randTAH3(shape: Sequence[int], device=None) -> Tensor:
     """utils.py:171-195; `shape` is the batch shape [nb, 4, T, X, Y, Z]"""
     shape = tuple(int(s) for s in shape)
@@ -154,6 +209,25 @@ class SU3(Group):
     def random_momentum(self, shape: Sequence[int]) -> Tensor:
         """randTAH3(shape[:-2])   (group.py:121-123)"""
         return randTAH3(list(shape)[:-2])
+
+    def checkU(self, x: Tensor) -> tuple[Tensor, Tensor]:
+        return checkU(x)
+
+    def projectU(self, x: Tensor) -> Tensor:
+        return projectU(x)
+
+    def rsqrtPHM3(self, x: Tensor) -> Tensor:
+        return rsqrtPHM3(x)
+
+    def rsqrtPHM3f(self, tr: Tensor, p2: Tensor, det: Tensor):
+        return rsqrtPHM3f(tr, p2, det)
+
+    def diff_trace(self, x: Tensor) -> Tensor:
+        """a TODO stub in the reference too (group.py:80-86)"""
+        return x
+
+    def diff2trace(self, x: Tensor) -> Tensor:
+        return x
 
     def checkSU(self, x: Tensor) -> tuple[Tensor, Tensor]:
         return checkSU(x)

@@ -21,6 +21,24 @@ def _device() -> torch.device:
     return torch.device('cuda', torch.cuda.current_device())
 
 
+def rand_unif(shape: Sequence[int], a: float, b: float, requires_grad: bool = True) -> Tensor:
+    """x ~ U(a, b) (group.py:23-41), on the CUDA device"""
+    rand = (a - b) * torch.rand(tuple(shape), device=_device()) + b
+    return rand.clone().detach().requires_grad_(requires_grad)
+
+
+def random_angle(shape: Sequence[int], requires_grad: bool = True) -> Tensor:
+    """group.py:44-47"""
+    return rand_unif(shape, -PI, PI, requires_grad=requires_grad)
+
+
+def eyeOf(x: Tensor) -> Tensor:
+    """group.py:50-57"""
+    eye = torch.zeros([1] * (x.dim() - 1) + [*x.shape[-1:]], device=x.device)
+    eye[-1:] = torch.eye(x.shape[-1], device=x.device)
+    return eye
+
+
 class U1Phase(Group):
     def __init__(self) -> None:
         super().__init__(dim=2, shape=[1], dtype=torch.get_default_dtype())
@@ -69,6 +87,10 @@ class U1Phase(Group):
 
     def diff2trace(self, x: Tensor) -> Tensor:
         return -torch.cos(x)
+
+    def floormod(self, x, y) -> Tensor:
+        """group.py:134-135"""
+        return x - torch.floor_divide(x, y) * y
 
     def compat_proj(self, x: Tensor) -> Tensor:
         """((x + pi) mod 2 pi) - pi   (group.py:130-131)"""

@@ -34,11 +34,7 @@ class LatticeSU3(Lattice):
         assert len(shape) == 4
         self.g = SU3()
         self.nt, self.nx, self.ny, self.nz = shape
-        self.c1 = c1
-        if c1 != 0.0:
-            raise NotImplementedError(
-                'rectangle (DBW2, c1 != 0) term: SURVEY.md section 8 f-4, not built yet; '
-                'every shipped config uses c1 = 0 (configs.py:658)')
+        self.c1 = float(c1)      # c1 != 0 (DBW2 / rectangle term): plaquette part on the kernels, rectangle
         super().__init__(group=self.g, nchains=nchains, shape=list(shape))
 
     def _field(self, x: Tensor) -> Tensor:
@@ -59,21 +55,54 @@ class LatticeSU3(Lattice):
         """ps[6, nb, T, X, Y, Z]   (lattice.py:157-199,242-244); differentiable"""
         return ag.SU3WilsonLoops.apply(self._field(x))
 
+    def _rect_traces(self, x: Tensor) -> Tensor:
+        """traces of the 2x1 and 1x2 rectangles, rs[12, nb, T, X, Y, Z], exactly the reference's
+        sequence of products and rolls (lattice.py:96-112,180-196).  The rectangle (c1 != 0) term
+        is off in every shipped config, so it runs as ATen ops on the GPU (differentiable by
+        torch), not as a hand-written kernel."""
+        x = self._field(x)
+        rs = []
+        tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)  # noqa: E731
+        for u in range(1, 4):
+            for v in range(0, u):
+                xu, xv = x[:, u], x[:, v]
+                yuv = xu @ xv.roll(-1, dims=u + 1)
+                yvu = xv @ xu.roll(-1, dims=v + 1)
+                yu, yv = xu.roll(-1, dims=v + 1), xv.roll(-1, dims=u + 1)
+                uu, ur = xv.mH @ yuv, xu.mH @ yvu
+                ul, ud = yuv @ yu.mH, yvu @ yv.mH
+                rs.append(tr(ur @ ul.roll(-1, dims=u + 1).mH))
+                rs.append(tr(uu @ ud.roll(-1, dims=v + 1).mH))
+        return torch.stack(rs)
+
+    def _rect_action(self, x: Tensor, beta) -> Tensor:
+        """-(beta c1 / 3) sum Re tr R"""
+        rs = self._rect_traces(x)
+        return rs.real.sum(tuple(range(2, rs.dim()))).sum(0) * (-self.coeffs(beta)['rect'] / 3.0)
+
     def _wilson_loops(self, x: Tensor, needs_rect: bool = False) -> tuple[Tensor, Tensor]:
-        assert not needs_rect, 'rectangles: SURVEY section 8 f-4'
         ps = self.wilson_loops(x)
+        if needs_rect:
+            return ps, self._rect_traces(x)
         return ps, torch.zeros((12, *ps.shape[1:]), dtype=ps.dtype, device=ps.device)
 
     def action(self, x: Tensor, beta) -> Tensor:
-        """S = -(beta/3) sum Re tr P   (lattice.py:252-269); differentiable (adjoint =
-        the staple-sum kernel)"""
-        return ag.SU3Action.apply(self._field(x), _f(beta))
+        """S = -(beta (1 - 8 c1) / 3) sum Re tr P - (beta c1 / 3) sum Re tr R   (lattice.py:252-269);
+        differentiable (plaquette part: adjoint = the staple-sum kernel)"""
+        s = ag.SU3Action.apply(self._field(x), self.coeffs(beta)['plaq'])
+        if self.c1 != 0.0:
+            s = s + self._rect_action(x, beta)
+        return s
 
     def _action(self, wloops, beta) -> Tensor:
         """NB: the reference's `_action` has no minus sign (lattice.py:271-285)"""
         ps = wloops[0] if isinstance(wloops, (tuple, list)) else wloops
         psum = ps.real.sum(tuple(range(2, ps.dim()))).sum(0)
-        return self.coeffs(beta)['plaq'] * psum / 3.0
+        act = self.coeffs(beta)['plaq'] * psum
+        if self.c1 != 0.0 and isinstance(wloops, (tuple, list)):
+            rs = wloops[1]
+            act = act + self.coeffs(beta)['rect'] * rs.real.sum(tuple(range(2, rs.dim()))).sum(0)
+        return act / 3.0
 
     def _plaquettes(self, x: Tensor) -> Tensor:
         return self._sums(x)[:, 0] / (6 * 3 * self.volume)
@@ -118,10 +147,26 @@ class LatticeSU3(Lattice):
         """(beta/3) TAH(U A), analytic; equals the reference's
         projectTAH(autograd(S) @ x^+) (lattice.py:299-308).  Like the reference
         (no create_graph) the result is a constant w.r.t. later backprop."""
-        return ag.SU3Force.apply(self._field(x), _f(beta))
+        f = ag.SU3Force.apply(self._field(x), self.coeffs(beta)['plaq'])
+        if self.c1 != 0.0:
+            f = f + self._rect_force(self._field(x), beta)
+        return f
+
+    def _rect_force(self, x: Tensor, beta) -> Tensor:
+        """projectTAH(dS_rect/dx @ x^+) with dS_rect/dx from ATen autograd, detached like the
+        reference's `dsdx` (lattice.py:299-308); the explicit `@ x^+` stays differentiable"""
+        with torch.enable_grad():
+            xr = x.detach().requires_grad_(True)
+            dsdx, = torch.autograd.grad(self._rect_action(xr, beta).sum(), xr)
+        y = dsdx.detach() @ x.mH
+        a = 0.5 * (y - y.mH)
+        return a - torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)[..., None, None] / 3.0 * torch.eye(
+            3, dtype=a.dtype, device=a.device)
 
     def action_with_grad(self, x: Tensor, beta) -> tuple[Tensor, Tensor]:
         """one force pass yields both (lattice.py:287-297)"""
+        if self.c1 != 0.0:
+            return self.action(x, beta).detach(), self.grad_action(x, beta).detach()
         f, ps = ops.su3_force(self._field(x.detach()), _f(beta), want_plaq_sum=True)
         return ps * (-_f(beta) / 3.0), f
 

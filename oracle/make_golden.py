@@ -198,6 +198,20 @@ def su3_adjoint_goldens(ref, torch):
     gu, = torch.autograd.grad(w, u, grad_outputs=gw)
     out.update(wl_shape=np.array(shape), wl_x=_np(u), wl_gw=_np(gw), wl_gx=_np(gu))
     np.savez_compressed(GOLD / 'su3_adjoint_f64.npz', **out)
+    # ---- rectangle (c1 != 0, DBW2 value) action: loops, action, force, one HMC trajectory ----
+    shape, nb, beta, c1 = [2, 4, 3, 2], 2, 5.7, -0.331
+    lat = ref.LatticeSU3(nb, shape, c1=c1)
+    xr = lat.random().detach()
+    vr = lat.random_momentum()
+    b = torch.tensor(beta)
+    ps, rs = lat._wilson_loops(xr, needs_rect=True)
+    cfg = ref.DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=2, eps=0.05, eps_hmc=0.05,
+                             verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    dyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+    sp, met = dyn.transition_kernel_hmc(ref.State(x=xr, v=vr, beta=b), eps=0.05, nleapfrog=3)
+    np.savez_compressed(GOLD / 'su3_c1_f64.npz', shape=np.array(shape), beta=beta, c1=c1, x=_np(xr), v=_np(vr),
+                        rects=_np(rs), action=_np(lat.action(xr, b)), force=_np(lat.grad_action(xr.clone(), b)),
+                        hmc_x=_np(sp.x), hmc_v=_np(sp.v), hmc_acc=_np(met['acc']))
 
 
 def u1_goldens(ref, torch, tag: str):

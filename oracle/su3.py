@@ -289,11 +289,31 @@ def plaq_sums(x):
     return psr, psi
 
 
+def rect_traces(x):
+    """traces of the 2x1 / 1x2 rectangles, rs[12, nb, T, X, Y, Z] (`_wilson_loops` with
+    needs_rect, lattice.py:180-196)"""
+    rs = []
+    for u in range(1, 4):
+        for v in range(0, u):
+            xu, xv = x[:, u], x[:, v]
+            yuv = xu @ _shift(xv, u)
+            yvu = xv @ _shift(xu, v)
+            yu, yv = _shift(xu, v), _shift(xv, u)
+            uu, ur = adj(xv) @ yuv, adj(xu) @ yvu
+            ul, ud = yuv @ adj(yu), yvu @ adj(yv)
+            rs.append(trace(ur @ adj(_shift(ul, u))))
+            rs.append(trace(uu @ adj(_shift(ud, v))))
+    return np.stack(rs)
+
+
 def action(x, beta, c1: float = 0.0):
-    """lattice.py:252-269 (plaquette part; c1 == 0 is the only configured case)"""
-    assert c1 == 0.0, 'rectangle term is SURVEY section 8 f-4 (not built yet)'
+    """lattice.py:252-269: -(beta (1 - 8 c1) / 3) sum Re tr P - (beta c1 / 3) sum Re tr R"""
     psr, _ = plaq_sums(x)
-    return beta * (1.0 - 8.0 * c1) * psr * (-1.0 / 3.0)
+    s = beta * (1.0 - 8.0 * c1) * psr
+    if c1 != 0.0:
+        rs = rect_traces(x)
+        s = s + beta * c1 * rs.real.reshape(12, x.shape[0], -1).sum(2).sum(0)
+    return s * (-1.0 / 3.0)
 
 
 def volume_of(x):

@@ -223,3 +223,33 @@ def test_accept_mix_is_bit_exact_select(ops, g):
     st0, st1 = od.State(g['x'], g['v'], 0), od.State(g['hmc4_x'], g['hmc4_v'], 0)
     wx, wv, _ = od.accept_mix(np.array([0.9, 0.1]), np.array([0.5, 0.5]), st0, st1)
     assert np.array_equal(host(xo), wx) and np.array_equal(host(vo), wv)
+
+
+def test_rectangle_action_c1_matches_reference(golden_dir):
+    """LatticeSU3(c1 != 0): plaquette part on the kernels + rectangle part as ATen ops; loops,
+    action, force and a plain-HMC trajectory against the reference's own c1 = -0.331 run"""
+    from l2hmc_b200.configs import DynamicsConfig
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        g = np.load(golden_dir / 'su3_c1_f64.npz')
+        shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
+        lat = LatticeSU3(nb, shape, c1=c1)
+        x, v = dev(g['x']), dev(g['v'])
+        b = torch.tensor(beta)
+        ps, rs = lat._wilson_loops(x, needs_rect=True)
+        assert maxdiff(host(rs), g['rects']) < 1e-13
+        assert np.all(np.abs(host(lat.action(x, b)) - g['action']) <= 1e-12 * np.abs(g['action']))
+        assert maxdiff(host(lat.grad_action(x, b)), g['force']) < 1e-12
+        cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=2, eps=0.05, eps_hmc=0.05,
+                             verbose=False, use_split_xnets=False, use_separate_networks=False)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+        with torch.no_grad():
+            sp, met = dyn.transition_kernel_hmc(State(x, v, b), eps=0.05, nleapfrog=3)
+        assert maxdiff(host(sp.x).reshape(g['hmc_x'].shape), g['hmc_x']) < 1e-12
+        assert maxdiff(host(sp.v).reshape(g['hmc_v'].shape), g['hmc_v']) < 1e-12
+        assert maxdiff(host(met['acc']), g['hmc_acc']) < 1e-10
+    finally:
+        torch.set_default_dtype(old)

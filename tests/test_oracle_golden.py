@@ -135,3 +135,11 @@ def test_u1(golden_dir, tag, tol):
         assert maxdiff(s3.x, gu[pre + 'xbwd_x']) <= 10 * tol and maxdiff(ld3, gu[pre + 'xbwd_logdet']) <= 10 * tol
         s4, ld4 = od.update_v(spec, 0, st, True)
         assert maxdiff(s4.v, gu[pre + 'vfwd_v']) <= 10 * tol and maxdiff(ld4, gu[pre + 'vfwd_logdet']) <= 10 * tol
+
+
+def test_su3_rectangle_action_oracle_matches_reference(golden_dir):
+    """c1 != 0 (DBW2 rectangle term, lattice.py:96-112,180-196,252-269)"""
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    assert maxdiff(osu3.rect_traces(g['x']), g['rects']) < 1e-13
+    got = osu3.action(g['x'], float(g['beta']), float(g['c1']))
+    assert np.all(np.abs(got - g['action']) <= 1e-12 * np.abs(g['action']))
