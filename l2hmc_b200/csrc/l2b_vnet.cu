@@ -112,6 +112,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t r[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
 // tanh(x) = 1 - 2 / (1 + e^{2x}) on the SFU (ex2.approx + rcp.approx): absolute error ~2e-7, which is
 // what the epilogue needs (s, q enter through eps*s/2 and eps*q); saturates correctly for large |x|
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -254,6 +259,76 @@ __device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t 
   }
 }
 
+// Interior tiles: software-pipelined epilogue.  4 chains per chunk, the v / F loads of chunk k+1 are in
+// flight while chunk k is computed, and chunk 0's loads are issued BEFORE waiting for the accumulators, so
+// the epilogue's first DRAM latency hides under the weight streaming + MMAs of the same CTA.
+template <bool FWD>
+__device__ __forceinline__ void epilogue_full(const HeadsArgs& a, Smem& sm, uint32_t tmem, int tile, int chain0,
+                                              int warp, int lane) {
+  constexpr int C4 = 4, NCK = 32 / C4;
+  const int quarter = warp & 3, half = warp >> 2;
+  const size_t j = (size_t)tile * BM + quarter * 32 + lane;
+  const size_t xd = (size_t)a.xdim;
+  const size_t base0 = (size_t)(chain0 + half * 32) * xd + j;
+  const double2* __restrict__ pv = a.v + base0;
+  const double2* __restrict__ pf = a.f + base0;
+  double2* __restrict__ po = a.out + base0;
+  double2 vv[2][C4], ff[2][C4];
+#pragma unroll
+  for (int c = 0; c < C4; ++c) { vv[0][c] = __ldg(pv + c * xd); ff[0][c] = __ldg(pf + c * xd); }
+  const float bs = __ldg(a.bias[0] + j), bt = __ldg(a.bias[1] + j), bq = __ldg(a.bias[2] + j);
+  const float as = __ldg(a.scale_s + j), aq = __ldg(a.scale_q + j), at = a.scale_t;
+  const double epsd = a.eps_dev ? a.eps * a.eps_dev[0] : a.eps;
+  const float epsf = (float)epsd, hs = (FWD ? 0.5f : -0.5f) * epsf;
+  const double he = 0.5 * epsd;
+  const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 32;
+  float* ljw = sm.lj[warp];
+  mbar_wait<64>(smem_u32(&sm.accum), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+  for (int ck = 0; ck < NCK; ++ck) {
+    const int cur = ck & 1, nxt = cur ^ 1;
+    if (ck + 1 < NCK) {
+#pragma unroll
+      for (int c = 0; c < C4; ++c) {
+        vv[nxt][c] = __ldg(pv + ((ck + 1) * C4 + c) * xd);
+        ff[nxt][c] = __ldg(pf + ((ck + 1) * C4 + c) * xd);
+      }
+    }
+    uint32_t rs[C4], rt[C4], rq[C4];
+    tmem_ld4(trow + 0 * BN + ck * C4, rs);
+    tmem_ld4(trow + 1 * BN + ck * C4, rt);
+    tmem_ld4(trow + 2 * BN + ck * C4, rq);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < C4; ++c) {
+      const float s = as * tanh_fast(__uint_as_float(rs[c]) + bs);
+      const float t = at * (__uint_as_float(rt[c]) + bt);
+      const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
+      const float logjac = hs * s;
+      ljw[c * 33 + lane] = logjac;
+      const double es = (double)exp_fast(logjac), eq = (double)exp_fast(epsf * q);
+      const double fr = fma(ff[cur][c].x, eq, (double)t), fi = ff[cur][c].y * eq;
+      double2 o;
+      if (FWD) { o.x = fma(es, vv[cur][c].x, -he * fr); o.y = fma(es, vv[cur][c].y, -he * fi); }
+      else { o.x = es * fma(he, fr, vv[cur][c].x); o.y = es * fma(he, fi, vv[cur][c].y); }
+      po[(ck * C4 + c) * xd] = o;
+    }
+    __syncwarp();
+    {                                                   // fixed-order sum over the warp's 32 columns
+      const int c = lane & 3, part = lane >> 2;         // lane (c, part) adds columns 4 part .. +3 of chain c
+      float x = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x += ljw[c * 33 + part * 4 + k];
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      if (lane < C4) sm.ld[warp][ck * C4 + lane] = x;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -269,6 +344,13 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
     for (int s = 0; s < NST; ++s) { mbar_init(smem_u32(&sm.full[s]), 1); mbar_init(smem_u32(&sm.empty[s]), 1); }
     mbar_init(smem_u32(&sm.accum), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first ring fill goes out NOW: the weights' DRAM latency overlaps the TMEM allocation and the z tile load
+    const unsigned char* wsrc0 = a.packed + (size_t)tile * total * A_STAGE_BYTES;
+    for (int s = 0; s < NST && s < total; ++s) {
+      mbar_expect_tx(smem_u32(&sm.full[s]), A_STAGE_BYTES);
+      bulk_g2s(smem_u32(sm.a) + s * A_STAGE_BYTES, wsrc0 + (size_t)s * A_STAGE_BYTES, A_STAGE_BYTES,
+               smem_u32(&sm.full[s]));
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)),
@@ -299,10 +381,6 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
     const unsigned char* wsrc = a.packed + (size_t)tile * total * A_STAGE_BYTES;
     const uint32_t a_base = smem_u32(sm.a), b_base = smem_u32(sm.b);
     const uint32_t a_lbo = BM * 16, b_lbo = BN * 16, sbo = 128;   // K step of each image; 8-row groups are adjacent
-    for (int s = 0; s < NST && s < total; ++s) {
-      mbar_expect_tx(smem_u32(&sm.full[s]), A_STAGE_BYTES);
-      bulk_g2s(a_base + s * A_STAGE_BYTES, wsrc + (size_t)s * A_STAGE_BYTES, A_STAGE_BYTES, smem_u32(&sm.full[s]));
-    }
     for (int s = 0; s < total; ++s) {
       const int slot = s % NST;
       const uint32_t ph = (uint32_t)(s / NST) & 1u;
@@ -330,14 +408,14 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   // ---- epilogue: TMEM lane = xdim column, TMEM column = chain -----------------------------
   // 8 warps: warp w reads TMEM lanes 32 (w % 4) .. +31 (the hardware's lane quarter of a warp)
   // and owns the chains [32 (w / 4), +32) of the tile, 8 chains at a time.
-  mbar_wait<128>(smem_u32(&sm.accum), 0);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   {
     const bool full = (chain0 + BN <= a.nb) && ((size_t)(tile + 1) * BM <= (size_t)a.xdim) && a.stq == nullptr;
-    if (full) {
-      if (a.sign > 0) epilogue<true, true>(a, sm, tmem, tile, chain0, warp, lane);
-      else epilogue<false, true>(a, sm, tmem, tile, chain0, warp, lane);
+    if (full) {                                         // (waits for the accumulators inside, after its first loads)
+      if (a.sign > 0) epilogue_full<true>(a, sm, tmem, tile, chain0, warp, lane);
+      else epilogue_full<false>(a, sm, tmem, tile, chain0, warp, lane);
     } else {
+      mbar_wait<128>(smem_u32(&sm.accum), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (a.sign > 0) epilogue<true, false>(a, sm, tmem, tile, chain0, warp, lane);
       else epilogue<false, false>(a, sm, tmem, tile, chain0, warp, lane);
     }
