@@ -202,6 +202,18 @@ int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, voi
                                     double eps_kick, double eps_drift, double* sums_or_null, int nb,
                                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/* L2HMC sweep with the state kept in the planar layout (no conversion around the stencil kernels):
+ * force without kick, group_to_vec (vec8 in [b][mu][site][8] order, as the AoS version) and the masked
+ * link update; the mask is the [xdim] element mask permuted to [4][9][V].  The heads kernel
+ * l2b_su3_heads_vupdate is layout-agnostic: pack the head weights with their rows permuted the same way. */
+int l2b_su3_force_planar(const void* u_planar, double beta, void* f_planar, int nb, const int dims[4], int dtype,
+                         void* stream);
+int l2b_su3_project_vec_planar(const void* x_planar, void* vec8, int vec_dtype, int nb, const int dims[4], int dtype,
+                               void* stream);
+int l2b_su3_update_gauge_planar(const void* x_planar, const void* p_planar, double eps, const double* eps_dev,
+                                const float* mask_planar, int mask_complement, void* x_out_planar, int nb,
+                                const int dims[4], int dtype, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */
 /* ------------------------------------------------------------------------ */

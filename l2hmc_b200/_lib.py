@@ -61,6 +61,9 @@ _SIGS = {
     'l2b_su3_to_vec_bwd': [_P, _P, c_size_t, c_int, _P],
     'l2b_su3_wilson_loops_bwd': [_P, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_bwd': [_P, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_force_planar': [_P, c_double, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_project_vec_planar': [_P, _P, c_int, c_int, _DIMS, c_int, _P],
+    'l2b_su3_update_gauge_planar': [_P, _P, c_double, _P, _P, c_int, _P, c_int, _DIMS, c_int, _P],
     'l2b_su3_project_vec': [_P, _P, c_int, c_size_t, c_int, _P],
     'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],

@@ -632,6 +632,58 @@ __global__ void __launch_bounds__(NTL) k_project_bwd(const C* __restrict__ x, co
   block_store_mat<NTL>(gx, sm, r, first, n);
 }
 
+// ---------------------------------------------------------------------------
+// planar (internal layout) variants of the link-local L2HMC kernels: with the state kept planar
+// through a whole L2HMC sweep no layout conversion surrounds the stencil kernels.  One thread per
+// link, grid (ceil(V / NTL), nb * 4); every access is a coalesced 128-bit load / store.
+// ---------------------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(NTL) k_project_vec_planar(const C* __restrict__ x, V* __restrict__ vec8, int Vs) {
+  const int site = blockIdx.x * NTL + threadIdx.x;
+  if (site >= Vs) return;
+  const size_t plane = blockIdx.y;                        // b * 4 + mu
+  Mat3<T> m, r;
+  soa_load(m, x + plane * 9 * (size_t)Vs, Vs, site);
+  project_su(r, m);
+  T v[8];
+  su3_to_vec(v, r);
+  Vec8IO<V>::store(vec8 + (plane * Vs + site) * 8, v);    // [b][mu][site][8]: the order the vnet input expects
+}
+
+// x' = m*x + exp(eps p) ((1-m)*x), planar x, p, x'; mask planar [4][9][V] float (nullptr: x' = exp(eps p) x)
+__global__ void __launch_bounds__(NTL) k_update_gauge_planar(const C* __restrict__ x, const C* __restrict__ p,
+                                                             double eps_in, const double* __restrict__ eps_dev,
+                                                             const float* __restrict__ mask, int mask_complement,
+                                                             C* __restrict__ out, int Vs) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
+  const int site = blockIdx.x * NTL + threadIdx.x;
+  if (site >= Vs) return;
+  const size_t plane = blockIdx.y;
+  const int mu = (int)(plane & 3);
+  Mat3<T> X, Pm, E, R;
+  soa_load(Pm, p + plane * 9 * (size_t)Vs, Vs, site);
+  soa_load(X, x + plane * 9 * (size_t)Vs, Vs, site);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { Pm.re[e] *= eps; Pm.im[e] *= eps; }
+  mat_exp(E, Pm);
+  if (mask == nullptr) {
+    mat_mul<false, false, false>(R, E, X);
+  } else {
+    Mat3<T> Xb;
+    const float* mk = mask + (size_t)mu * 9 * Vs + site;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      float m = __ldg(mk + (size_t)e * Vs);
+      if (mask_complement) m = 1.0f - m;
+      const T md = (T)m, mb = (T)(1.0f - m);
+      R.re[e] = md * X.re[e]; R.im[e] = md * X.im[e];
+      Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+    }
+    mat_mul<false, false, true>(R, E, Xb);
+  }
+  soa_store(out + plane * 9 * (size_t)Vs, Vs, site, R);
+}
+
 // U <- exp(eps P) U on the planar layout
 __global__ void __launch_bounds__(128, 4) k_drift(C* __restrict__ U, const C* __restrict__ P, int V, double eps) {
   const int plane = blockIdx.y;
@@ -1545,6 +1597,43 @@ int l2b_su3_project_bwd(const void* x, const void* gmat_or_null, const void* gve
   else if (vec_dtype == L2B_BF16) k_project_bwd<__nv_bfloat16><<<nblk, NTL, 0, st>>>((const C*)x, gm, (const __nv_bfloat16*)gvec8_or_null, (C*)gx, nmat);
   else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "vec_dtype must be L2B_F64, L2B_F32 or L2B_BF16");
   L2B_LAUNCHED("k_project_bwd");
+  return L2B_OK;
+}
+
+int l2b_su3_force_planar(const void* u_planar, double beta, void* f_planar, int nb, const int dims[4], int dtype,
+                         void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(u_planar && f_planar, L2B_ERR_INVALID, "null pointer");
+  return launch_force(g, (const C*)u_planar, (C*)f_planar, false, beta / 3.0, nullptr, (cudaStream_t)stream);
+}
+
+int l2b_su3_project_vec_planar(const void* x_planar, void* vec8, int vec_dtype, int nb, const int dims[4], int dtype,
+                               void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_planar && vec8, L2B_ERR_INVALID, "null pointer");
+  const dim3 grid((g.lat.V + NTL - 1) / NTL, nb * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_dtype == L2B_F64) k_project_vec_planar<double><<<grid, NTL, 0, st>>>((const C*)x_planar, (double*)vec8, g.lat.V);
+  else if (vec_dtype == L2B_F32) k_project_vec_planar<float><<<grid, NTL, 0, st>>>((const C*)x_planar, (float*)vec8, g.lat.V);
+  else if (vec_dtype == L2B_BF16) k_project_vec_planar<__nv_bfloat16><<<grid, NTL, 0, st>>>((const C*)x_planar, (__nv_bfloat16*)vec8, g.lat.V);
+  else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "vec_dtype must be L2B_F64, L2B_F32 or L2B_BF16");
+  L2B_LAUNCHED("k_project_vec_planar");
+  return L2B_OK;
+}
+
+int l2b_su3_update_gauge_planar(const void* x_planar, const void* p_planar, double eps, const double* eps_dev,
+                                const float* mask_planar, int mask_complement, void* x_out_planar, int nb,
+                                const int dims[4], int dtype, void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_planar && p_planar && x_out_planar, L2B_ERR_INVALID, "null pointer");
+  const dim3 grid((g.lat.V + NTL - 1) / NTL, nb * 4);
+  k_update_gauge_planar<<<grid, NTL, 0, (cudaStream_t)stream>>>((const C*)x_planar, (const C*)p_planar, eps, eps_dev,
+                                                                mask_planar, mask_complement, (C*)x_out_planar,
+                                                                g.lat.V);
+  L2B_LAUNCHED("k_update_gauge_planar");
   return L2B_OK;
 }
 

@@ -413,8 +413,76 @@ class Dynamics(nn.Module):
         (l2hmc_b200/autograd.py)"""
         return None
 
+    # ---------------------------------------------- planar inference sweep (SU(3))
+    def _planar_ok(self) -> bool:
+        """L2HMC sweep with x, v kept in the kernels' planar layout: inference only (the adjoint
+        kernels work on the boundary layout), tensor-core heads, plain Wilson action"""
+        if not (self._su3 and self._networks_built) or torch.is_grad_enabled() or self.config.verbose:
+            return False
+        if getattr(self, 'planar_sweep', 'auto') == 'never' or getattr(self.lattice, 'c1', 0.0) != 0.0:
+            return False
+        return all(self._fused_heads(self._get_vnet(k)) for k in range(self.config.nleapfrog))
+
+    def _planar_consts(self):
+        c = getattr(self, '_planar_cache', None)
+        if c is None:
+            V = int(np.prod(self.config.latvolume))
+            dev = self.masks[0].device
+            # planar position (mu, e, site) <- boundary position (mu, site, e)
+            perm = torch.arange(4 * V * 9, device=dev).reshape(4, V, 9).permute(0, 2, 1).reshape(-1).contiguous()
+            masks = [m.reshape(-1).index_select(0, perm).contiguous() for m in self.masks]
+            c = (perm, masks)
+            self._planar_cache = c
+        return c
+
+    def _transition_kernel_fb_planar(self, state: State) -> tuple[State, dict]:
+        """transition_kernel_fb (dynamics.py:956-1029) with the state planar between the two layout
+        conversions at its ends; same kernels' arithmetic per link as the boundary-layout path"""
+        nb = state.x.shape[0]
+        perm, pmasks = self._planar_consts()
+        beta = _fbeta(state.beta)
+        xs = ops.su3_aos_to_soa(self.unflatten(state.x))
+        vs = ops.su3_aos_to_soa(self.unflatten(state.v))
+        sumlogdet = torch.zeros(nb, dtype=torch.float64, device=xs.device)
+        nlf = self.config.nleapfrog
+
+        def v_update(step, vs_, sign):
+            vnet = self._get_vnet(step)
+            dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
+            f = ops.su3_force_planar(xs, beta)
+            z = vnet.hidden((ops.su3_project_vec_planar(xs, dt), ops.su3_project_vec_planar(f, dt)))
+            return ops.su3_heads_vupdate(z, vnet.heads_pack(perm), vs_.reshape(nb, -1), f.reshape(nb, -1),
+                                         self._eps_t(self.veps[step]).to(torch.float64), sign)
+
+        def x_update(step, xs_, vs_, complement, sign):
+            return ops.su3_update_gauge_planar(xs_, vs_.reshape(xs_.shape), self._eps_t(self.xeps[step]).to(torch.float64),
+                                               pmasks[step], complement, eps_mult=float(sign))
+        for step in range(nlf):                     # _forward_lf
+            vs, ld = v_update(step, vs, +1)
+            sumlogdet = sumlogdet + ld
+            xs = x_update(step, xs, vs, False, +1)
+            xs = x_update(step, xs, vs, True, +1)
+            vs, ld = v_update(step, vs, +1)
+            sumlogdet = sumlogdet + ld
+        vs = -vs
+        for step in range(nlf):                     # _backward_lf
+            r = nlf - step - 1
+            vs, ld = v_update(r, vs, -1)
+            sumlogdet = sumlogdet + ld
+            xs = x_update(r, xs, vs, True, -1)
+            xs = x_update(r, xs, vs, False, -1)
+            vs, ld = v_update(r, vs, -1)
+            sumlogdet = sumlogdet + ld
+        xo = ops.su3_soa_to_aos(xs)
+        vo = ops.su3_soa_to_aos(vs.reshape(xs.shape))
+        out = State(x=xo, v=vo, beta=state.beta)
+        acc = self.compute_accept_prob(state, out, sumlogdet)
+        return out, {'acc': acc, 'sumlogdet': sumlogdet}
+
     def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
         self._check_inference_only()
+        if self._planar_ok():
+            return self._transition_kernel_fb_planar(state)
         nb = state.x.shape[0]
         sumlogdet = self._zeros(nb)
         sldf, sldb = torch.zeros_like(sumlogdet), torch.zeros_like(sumlogdet)

@@ -210,13 +210,26 @@ class LeapfrogLayer(nn.Module):
                 self.transl.weight, self.transl.bias,
                 self.transf.layer.weight, self.transf.layer.bias, self.transf.coeff)
 
-    def heads_pack(self):
+    def heads_pack(self, perm: Optional[Tensor] = None):
         """bf16 UMMA tile image of the three head matrices + epilogue constants for the fused
         tcgen05 kernel (ops.su3_heads_vupdate); rebuilt only when a head parameter or the net
-        weights changed (optimizer step, load_state_dict, set_net_weight)"""
+        weights changed (optimizer step, load_state_dict, set_net_weight).  `perm` (a LongTensor
+        over the xdim outputs) packs the rows in another output order -- the planar field layout --
+        so that the kernel writes that layout directly; cached separately."""
         from ... import ops
         ps = self.head_params()
         key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q)
+        if perm is not None:
+            cached = getattr(self, '_heads_pack_perm', None)
+            if cached is None or cached[0] != key or cached[2] is not perm:
+                ws, bs, cs, wt, bt, wq, bq, cq = ps
+                with torch.no_grad():
+                    sel = lambda a, d: a.detach().index_select(d, perm)  # noqa: E731
+                    pack = ops.vnet_pack_heads(sel(ws, 0), sel(wt, 0), sel(wq, 0), sel(bs, 0), sel(bt, 0), sel(bq, 0),
+                                               sel(cs, 1), sel(cq, 1), self.nw.s, self.nw.t, self.nw.q)
+                cached = (key, pack, perm)
+                self._heads_pack_perm = cached
+            return cached[1]
         cached = getattr(self, '_heads_pack', None)
         # a training step captured in a CUDA graph changes the weights on every replay without
         # Python running: the pack kernel must then be part of the graph

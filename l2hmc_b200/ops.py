@@ -307,6 +307,38 @@ def su3_soa_to_aos(x: Tensor) -> Tensor:
     return out
 
 
+# ---- planar-state variants (L2HMC inference sweep without layout conversions) ----
+def su3_force_planar(x_planar: Tensor, beta: float) -> Tensor:
+    x, nb, dims = _su3_field(x_planar)
+    f = torch.empty_like(x)
+    call('l2b_su3_force_planar', _ptr(x), float(beta), _ptr(f), nb, dims4(dims), L2B_F64, _stream())
+    return f
+
+
+def su3_project_vec_planar(x_planar: Tensor, dtype: torch.dtype = torch.float64) -> Tensor:
+    """vec8 [nb, 4, T, X, Y, Z, 8] (same order as su3_project_vec) from a planar field"""
+    x, nb, dims = _su3_field(x_planar)
+    v = torch.empty((nb, 4, *dims, 8), dtype=dtype, device=x.device)
+    call('l2b_su3_project_vec_planar', _ptr(x), _ptr(v), _net_dt(dtype), nb, dims4(dims), L2B_F64, _stream())
+    return v
+
+
+def su3_update_gauge_planar(x_planar: Tensor, p_planar: Tensor, eps=1.0, mask_planar: Optional[Tensor] = None,
+                            mask_complement: bool = False, eps_mult: float = 1.0) -> Tensor:
+    x, nb, dims = _su3_field(x_planar)
+    p, _, _ = _su3_field(p_planar, dims)
+    if mask_planar is not None:
+        _need_cuda(mask_planar)
+        mask_planar = mask_planar.to(torch.float32).contiguous()
+        if mask_planar.numel() != x[0].numel():
+            raise L2BError(f'mask has {mask_planar.numel()} entries, expected {x[0].numel()}')
+    out = torch.empty_like(x)
+    ev, ep, _keep = _eps_args(eps, torch.float64, eps_mult)
+    call('l2b_su3_update_gauge_planar', _ptr(x), _ptr(p), ev, ep, _ptr(mask_planar), int(mask_complement), _ptr(out),
+         nb, dims4(dims), L2B_F64, _stream())
+    return out
+
+
 # ---------------------------------------------------------------------------
 # U(1)
 # ---------------------------------------------------------------------------

@@ -169,3 +169,37 @@ def test_dynamics_uses_tensor_core_heads_under_bf16_autocast():
         assert all(torch.isfinite(t).all() for t in gr.values())
     finally:
         torch.set_default_dtype(old)
+
+
+def test_planar_inference_sweep_matches_boundary_layout_sweep():
+    """Dynamics.transition_kernel_fb with the state kept planar (no layout conversion around the stencil
+    kernels, head weights packed with permuted rows) == the boundary-layout sweep, link for link"""
+    from test_gpu_trainer import _su3_trainer
+    from l2hmc_b200.dynamics.pytorch.dynamics import State
+    from l2hmc_b200 import _lib
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        torch.manual_seed(4)
+        np.random.seed(4)
+        tr, lat = _su3_trainer(nb=3, shape=(4, 2, 4, 6), units=(32,), nlf=2, autocast=torch.bfloat16)
+        dyn = tr.dynamics
+        dyn.eval()
+        x = lat.random().to(torch.complex128)
+        v = lat.random_momentum()
+        beta = torch.tensor(5.9)
+        res = {}
+        for mode in ('never', 'auto'):
+            dyn.planar_sweep = mode
+            n0 = _lib.launch_count()
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                st, met = dyn.transition_kernel_fb(State(x, v, beta))
+            res[mode] = (st.x.reshape(x.shape), st.v.reshape(x.shape), met['sumlogdet'], met['acc'],
+                         _lib.launch_count() - n0)
+        a, b = res['never'], res['auto']
+        assert b[4] < a[4], 'fewer launches: no conversions around the force'
+        assert float((a[0] - b[0]).abs().max()) < 1e-13 and float((a[1] - b[1]).abs().max()) < 1e-12
+        assert float((a[2] - b[2]).abs().max()) < 1e-5 * max(1.0, float(a[2].abs().max()))
+        assert float((a[3] - b[3]).abs().max()) < 1e-5
+    finally:
+        torch.set_default_dtype(old)
