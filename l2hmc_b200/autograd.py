@@ -267,40 +267,89 @@ class SU3VUpdate(torch.autograd.Function):
                 None, None)
 
 
+# While True (Trainer.train_step sets it around loss.backward()), the weight / bias gradients of the
+# vnet heads are not formed in every SU3HeadsVUpdate.backward: the pre-activation cotangents and z of all
+# the v-updates that share a network are stashed and ONE dW = cat(G)^T cat(z) per head is formed when the
+# backward pass ends (autograd engine callback) -- instead of 2*N_LF*2 GEMMs each followed by a bf16->fp32
+# cast and an accumulation into a 75 MB .grad (8^4: ~38 GB of traffic per training step saved).
+DEFER_HEAD_GRADS = False
+
+
+def _flush_head_grads(net) -> None:
+    pend = net._pending_head_grads
+    net._pending_head_grads = None
+    if not pend:
+        return
+    ws, bs, cs, wt, bt, wq, bq, cq = net.head_params()
+    z = torch.cat([p[3] for p in pend])
+
+    def acc(param, g):
+        if param.requires_grad:
+            g = g.to(param.dtype).reshape(param.shape)
+            param.grad = g if param.grad is None else param.grad + g
+    for k, (w, b_) in enumerate(((ws, bs), (wt, bt), (wq, bq))):
+        g = torch.cat([p[k] for p in pend])              # [n_updates * nb, xdim] pre-activation cotangents
+        acc(w, g.t() @ z)
+        acc(b_, g.sum(0, dtype=torch.float32))
+    acc(cs, torch.stack([p[4] for p in pend]).sum(0))
+    acc(cq, torch.stack([p[5] for p in pend]).sum(0))
+
+
 class SU3HeadsVUpdate(torch.autograd.Function):
     """(v', logdet) = vupdate(v, F, heads(z); eps, sign) with the three head GEMMs on the
     tensor cores and s, t, q kept on chip (l2b_su3_heads_vupdate, csrc/l2b_vnet.cu).
-    backward re-materialises s, t, q with torch (library GEMMs, same autocast state as the
-    forward), runs the hand-written v-update adjoint on them and back-propagates the three
-    cotangents through that small graph -- the activations are never stored."""
+    When a gradient is needed the kernel also writes (s, t, q) once (fp32) for the backward pass:
+    the hand-written v-update adjoint gives their cotangents, the tanh / scale derivatives are a few
+    element-wise ops, and the three small GEMMs of the Linear backward run on cuBLAS (dz now, dW either
+    now or, under DEFER_HEAD_GRADS, once per backward pass for all the v-updates sharing the net)."""
 
     @staticmethod
     def forward(ctx, z, v, force, eps, sign, eps_value, net, *head_params):
-        ctx.save_for_backward(z, v, force, eps, *head_params)
         ctx.sign, ctx.net = sign, net
         ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         ctx.autocast = (torch.is_autocast_enabled('cuda'), torch.get_autocast_dtype('cuda'))
-        out, logdet = ops.su3_heads_vupdate(z.detach(), net.heads_pack(), v.detach(), force.detach(), ctx.eps_value,
-                                            sign)
-        return out, logdet
+        need = any(ctx.needs_input_grad)
+        res = ops.su3_heads_vupdate(z.detach(), net.heads_pack(), v.detach(), force.detach(), ctx.eps_value, sign,
+                                    want_stq=need)
+        ctx.save_for_backward(z, v, force, eps, res[2] if need else None, *head_params)
+        return res[0], res[1]
 
     @staticmethod
     def backward(ctx, gout, glogdet):
-        z, v, force, eps = ctx.saved_tensors[:4]
+        z, v, force, eps, stq = ctx.saved_tensors[:5]
+        ws, bs, cs, wt, bt, wq, bq, cq = ctx.saved_tensors[5:]
         net = ctx.net
-        with torch.enable_grad(), torch.autocast('cuda', enabled=ctx.autocast[0], dtype=ctx.autocast[1]):
-            zr = z.detach().requires_grad_(True)
-            s, t, q = net.heads(zr)
-        gv, gf, gs, gt, gq, geps = ops.su3_vupdate_bwd(v.detach(), force.detach(), s.detach(), t.detach(), q.detach(),
-                                                       ctx.eps_value, ctx.sign, gout, glogdet)
-        params = [p for p in net.head_params() if p.requires_grad]
-        grads = torch.autograd.grad([s, t, q], [zr] + params,
-                                    [gs.reshape(s.shape).to(s.dtype), gt.reshape(t.shape).to(t.dtype),
-                                     gq.reshape(q.shape).to(q.dtype)], allow_unused=True)
-        it = iter(grads[1:])
-        gparams = tuple(next(it) if p.requires_grad else None for p in net.head_params())
-        return (grads[0], gv.reshape(v.shape), gf.reshape(force.shape), _eps_grad(geps, eps), None, None, None,
-                *gparams)
+        nb, xdim = stq.shape[1], stq.shape[2]
+        s, t, q = stq[0], stq[1], stq[2]
+        gv, gf, gs, gt, gq, geps = ops.su3_vupdate_bwd(v.detach(), force.detach(), s, t, q, ctx.eps_value, ctx.sign,
+                                                       gout, glogdet)
+        gs, gt, gq = (g.reshape(nb, xdim).to(torch.float32) for g in (gs, gt, gq))
+        # s = a_s tanh(pre_s), a_s = nw.s e^{c_s}:  ds/dpre = a_s (1 - tanh^2),  ds/dc_s = s   (same for q)
+        a_s = float(net.nw.s) * cs.detach().to(torch.float32).exp()
+        a_q = float(net.nw.q) * cq.detach().to(torch.float32).exp()
+        th_s = torch.where(a_s != 0, s / a_s, torch.zeros_like(s))
+        th_q = torch.where(a_q != 0, q / a_q, torch.zeros_like(q))
+        cdt = ctx.autocast[1] if ctx.autocast[0] else ws.dtype        # the dtype the reference's Linear backward runs in
+        gp = ((gs * a_s * (1.0 - th_s * th_s)).to(cdt), (gt * float(net.nw.t)).to(cdt),
+              (gq * a_q * (1.0 - th_q * th_q)).to(cdt))
+        gcs, gcq = (gs * s).sum(0, keepdim=True), (gq * q).sum(0, keepdim=True)
+        wc = net.head_weights_as(cdt)
+        gz = (gp[0] @ wc[0] + gp[1] @ wc[1] + gp[2] @ wc[2]).to(z.dtype)
+        zc = z.detach().to(cdt)
+        if DEFER_HEAD_GRADS:
+            if getattr(net, '_pending_head_grads', None) is None:
+                net._pending_head_grads = []
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_head_grads(net))
+            net._pending_head_grads.append((gp[0], gp[1], gp[2], zc, gcs, gcq))
+            gparams = (None,) * 8
+        else:
+            need = ctx.needs_input_grad[7:]
+            gw = [(g.t() @ zc).to(w.dtype) if nd else None for g, w, nd in zip(gp, (ws, wt, wq), (need[0], need[3], need[5]))]
+            gb = [g.sum(0, dtype=torch.float32).to(b_.dtype) if nd else None
+                  for g, b_, nd in zip(gp, (bs, bt, bq), (need[1], need[4], need[6]))]
+            gparams = (gw[0], gb[0], gcs.to(cs.dtype) if need[2] else None, gw[1], gb[1], gw[2], gb[2],
+                       gcq.to(cq.dtype) if need[7] else None)
+        return (gz, gv.reshape(v.shape), gf.reshape(force.shape), _eps_grad(geps, eps), None, None, None, *gparams)
 
 
 class SU3UpdateGauge(torch.autograd.Function):

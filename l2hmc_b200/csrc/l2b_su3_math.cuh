@@ -366,8 +366,8 @@ L2B_HD void tah_from_normals(Mat3<T>& m, const T n[8]) {
 // Adjoint of E = exp(A):  G_A = sum_{n>=1} 1/n! sum_{k<n} B^k G_E B^(n-1-k),  B = A^+.
 // With B^m = a_m + b_m B + c_m B^2 (Cayley-Hamilton, as in mat_exp) the inner sums obey
 //   D_1 = G,  D_n = B D_{n-1} + G B^{n-1} = B D_{n-1} + a G + b (G B) + c (G B^2),
-// one matrix product per Taylor term.  No scaling/squaring: 34 terms converge to
-// double precision for ||A||_F <= 3 (3^34/34! ~ 6e-23); L2HMC arguments are eps*v
+// one matrix product per Taylor term.  No scaling/squaring: at most 34 terms (3^34/34! ~ 6e-23
+// at ||A||_F = 3), fewer at the small norms of a leapfrog step (11 at ||A||_F <= 0.1); L2HMC arguments are eps*v
 // with eps < 1, ||v||_F ~ 2.8.  `ok` is cleared when the norm is outside that range.
 template <typename T>
 L2B_HD void mat_exp_adjoint(Mat3<T>& ga, const Mat3<T>& a, const Mat3<T>& ge, bool& ok) {
@@ -391,7 +391,11 @@ L2B_HD void mat_exp_adjoint(Mat3<T>& ga, const Mat3<T>& a, const Mat3<T>& ge, bo
   d = ge;          // D_1
   ga = ge;         // n = 1 term, 1/1!
   T inv_fact = T(1);
-  for (int n = 2; n <= 34; ++n) {
+  // terms needed at this norm: the n-th term is bounded by rho^(n-1) / (n-1)!  (rho = ||A||_F <= 3)
+  const T n2a = norm2(a);
+  const int nterms = (n2a <= T(0.01)) ? 11 : (n2a <= T(0.09)) ? 14 : (n2a <= T(0.25)) ? 17
+                     : (n2a <= T(1)) ? 21 : (n2a <= T(4)) ? 28 : 34;
+  for (int n = 2; n <= nterms; ++n) {
     // advance B^{n-2} -> B^{n-1}
     const T nar = dr * cmr - di * cmi, nai = dr * cmi + di * cmr;
     const T nbr = amr - (cr * cmr - ci * cmi), nbi = ami - (cr * cmi + ci * cmr);

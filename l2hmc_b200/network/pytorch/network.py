@@ -210,6 +210,18 @@ class LeapfrogLayer(nn.Module):
                 self.transl.weight, self.transl.bias,
                 self.transf.layer.weight, self.transf.layer.bias, self.transf.coeff)
 
+    def head_weights_as(self, dtype: torch.dtype) -> tuple[Tensor, Tensor, Tensor]:
+        """(W_s, W_t, W_q) in `dtype` for the Linear backward (dz = g W), cast once per weight version"""
+        ws, _, _, wt, _, wq, _, _ = self.head_params()
+        if ws.dtype == dtype:
+            return ws.detach(), wt.detach(), wq.detach()
+        key = (dtype, ws._version, wt._version, wq._version, ws.data_ptr())
+        cached = getattr(self, '_head_weights_cast', None)
+        if cached is None or cached[0] != key or torch.cuda.is_current_stream_capturing():
+            cached = (key, tuple(w.detach().to(dtype) for w in (ws, wt, wq)))
+            self._head_weights_cast = cached
+        return cached[1]
+
     def heads_pack(self, perm: Optional[Tensor] = None):
         """bf16 UMMA tile image of the three head matrices + epilogue constants for the fused
         tcgen05 kernel (ops.su3_heads_vupdate); rebuilt only when a head parameter or the net

@@ -150,7 +150,11 @@ class Trainer:
             xo, metrics = self.dynamics((xi, beta))
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
-        loss.backward()
+        ag.DEFER_HEAD_GRADS = True        # one dW GEMM per vnet head per step instead of one per v-update
+        try:
+            loss.backward()
+        finally:
+            ag.DEFER_HEAD_GRADS = False
         if not capturing:
             ag.check_exp_adjoint_flags()  # one device read per step (matrix-exp adjoint range check)
         # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks;

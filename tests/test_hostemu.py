@@ -136,3 +136,19 @@ def test_wilson_loops_adjoint_matches_reference_autograd(emu, golden_dir):
     gx = np.empty_like(x)
     emu.emu_wloops_bwd(ptr(x), ptr(gw), ptr(gx), ctypes.c_int(x.shape[0]), dims)
     assert maxdiff(gx, want) < 1e-13 * max(1.0, np.abs(want).max())
+
+
+def test_exp_adjoint_matches_torch_autograd_at_all_norms(emu):
+    """mat_exp_adjoint (Taylor adjoint on Cayley-Hamilton coefficients, term count chosen from the
+    norm) against torch's autograd of matrix_exp, at the thresholds of the term-count table"""
+    import torch
+    rng = np.random.default_rng(3)
+    for rho in (0.03, 0.0999, 0.1001, 0.2999, 0.3001, 0.4999, 0.5001, 0.999, 1.001, 1.999, 2.001, 2.95):
+        a = rng.standard_normal((40, 3, 3)) + 1j * rng.standard_normal((40, 3, 3))
+        a = np.ascontiguousarray(a / np.linalg.norm(a, axis=(1, 2), keepdims=True) * rho)
+        g = np.ascontiguousarray(rng.standard_normal((40, 3, 3)) + 1j * rng.standard_normal((40, 3, 3)))
+        ga = np.empty_like(a)
+        emu.emu_exp_adjoint(ptr(a), ptr(g), ptr(ga), ctypes.c_size_t(40))
+        at = torch.from_numpy(a).requires_grad_(True)
+        want, = torch.autograd.grad(torch.linalg.matrix_exp(at), at, grad_outputs=torch.from_numpy(g))
+        assert maxdiff(ga, want.numpy()) < 2e-14 * max(1.0, np.abs(want.numpy()).max()), rho
