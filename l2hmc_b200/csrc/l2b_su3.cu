@@ -1039,6 +1039,7 @@ const ForceVariant kForceVariants[] = {
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
 int g_force_variant = 8;
 int g_fuse_drift = 1;
+int g_force_carveout = -1;   // -1: driver default; 0..100: preferred shared-memory carve-out in percent
 
 struct Geo {
   int force_variant;
@@ -1131,6 +1132,8 @@ int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double*
   L2B_REQUIRE(fn != nullptr, L2B_ERR_UNSUPPORTED, "force variant %d has no fused kick+drift kernel", g.force_variant);
   if (fv.smem > 48 * 1024)
     L2B_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, fv.smem));
+  if (g_force_carveout >= 0)   // register-only variants: give the whole unified cache to L1 (neighbour reuse)
+    L2B_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, g_force_carveout));
   fn<<<grid, block, fv.smem, st>>>(U, P, g.lat, coef, part, Uout, eps_drift);
   L2B_LAUNCHED("k_force");
   return L2B_OK;
@@ -1164,6 +1167,11 @@ int l2b_set_option(const char* key, int value) {
     L2B_REQUIRE(value >= 0 && value < kNumForceVariants, L2B_ERR_INVALID, "su3_force_variant must be in [0, %d)",
                 kNumForceVariants);
     g_force_variant = value;
+    return L2B_OK;
+  }
+  if (strcmp(key, "su3_force_carveout") == 0) {
+    L2B_REQUIRE(value >= -1 && value <= 100, L2B_ERR_INVALID, "su3_force_carveout must be in [-1, 100]");
+    g_force_carveout = value;
     return L2B_OK;
   }
   if (strcmp(key, "su3_fuse_drift") == 0) {
