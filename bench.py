@@ -198,6 +198,66 @@ def run_reference_steps(workload: str, steps: int, warmup: int):
             'sample': sample}, dt_s / steps * 1e3
 
 
+def run_reference_l2hmc(workload: str, steps: int, warmup: int):
+    """The reference's own SU(3) L2HMC step on the host cores (unmodified modules under
+    oracle/_ref): `Dynamics.forward` for the eval workload, forward + LatticeLoss + backward + Adam for
+    the training workload; same lattice, N_LF, network config and step size, 2 chains (the cost is
+    linear in chains; the 180 M-parameter vnet is built in full), float64 nets: the reference's SU(3)
+    path only runs with float64 as torch's default dtype (conf/experiment/su3*.yaml: precision float64)."""
+    import numpy as np
+    import torch
+    mode, lattice, nb, nlf, units, beta = L2HMC_WORKLOADS[workload]
+    assert not torch.cuda.is_available(), 'the CPU arm must not see a GPU'
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None, 'oracle/_ref did not travel to this box'
+    ref = ref_shim.load_reference(torch.float64)     # the reference's SU(3) path needs float64 as default dtype
+    nb_s = 2
+    torch.manual_seed(SEED)
+    np.random.seed(SEED)
+    V = 1
+    for s_ in lattice:
+        V *= s_
+    cfg = ref.DynamicsConfig(nchains=nb_s, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=0.01, eps_hmc=0.01,
+                             verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    ispec = ref.InputSpec(xshape=cfg.xshape, xnet={'x': [4 * V * 8], 'v': [4 * V * 8]},
+                          vnet={'x': [4 * V * 8], 'v': [4 * V * 8]})
+    ncfg = ref.NetworkConfig(units=[units], activation_fn='tanh', dropout_prob=0.0, use_batch_norm=False)
+    nw = ref.NetWeights(x=ref.NetWeight(0., 1., 1.), v=ref.NetWeight(1., 1., 1.))
+    lat = ref.LatticeSU3(nb_s, lattice)
+    fac = ref.NetworkFactory(input_spec=ispec, network_config=ncfg, conv_config=None, net_weights=nw)
+    dyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+    x = lat.random().detach()
+    b = torch.tensor(beta)
+    lcfg = ref.cfgs.LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1)
+    loss_fn = ref.LatticeLoss(lat, lcfg)
+    opt = torch.optim.Adam([p for p in dyn.parameters() if p.requires_grad], lr=1e-4)
+
+    def step():
+        if mode == 'train':
+            opt.zero_grad()
+        xo, m = dyn((x, b))
+        xp = m.pop('mc_states').proposed.x
+        loss = loss_fn(x_init=x, x_prop=xp, acc=m['acc'])
+        if mode == 'train':
+            loss.backward()
+            opt.step()
+        return float(loss)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt_s = time.perf_counter() - t0
+    units_ = nb_s * 4 * V * 2 * nlf
+    sample = (f'SU3 {"x".join(map(str, lattice))} L2HMC {mode} step, {nb_s} chains, N_LF {nlf}, units [{units}], '
+              f'float64 nets + complex128 lattice, torch {torch.__version__} CPU, {cores} threads')
+    return {'value': units_ * steps / dt_s, 'unit': 'link-updates/s', 'cores': cores, 'kind': 'reference',
+            'sample': sample}, dt_s / steps * 1e3
+
+
 def main_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -519,7 +579,7 @@ def main_l2hmc(args):
                          'tensor_tflops': flops / (ms_k * 1e-3) / 1e12,
                          'note': 'algorithmic bytes = v, F read + v\' written (complex128) + the bf16 head weights once; '
                                  'the GEMM is 0.2 % of the bf16 tensor peak by construction (HBM-bound op)'},
-            'cpu_baseline': None,
+            'cpu_baseline': (cpu_baseline_subprocess(args.workload) if (world == 1 and not args.no_cpu_baseline) else None),
             'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': x.numel() * x.element_size(),
                     'd2h_bytes_per_step': loss_h.element_size(), 'steps': n_e2e,
                     'api': f'Trainer.{mode}_step((x_host_pinned -> device, beta))'},
@@ -612,8 +672,24 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         if args.workload in L2HMC_WORKLOADS:
-            if int(os.environ.get('RANK', '0')) == 0:
-                print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference arm covers the HMC workloads only'}))
+            if int(os.environ.get('RANK', '0')) != 0:
+                return
+            os.environ['CUDA_VISIBLE_DEVICES'] = ''
+            base, ms = run_reference_l2hmc(args.workload, max(1, min(args.steps, 2)), min(args.warmup, 1))
+            if base is None:
+                print(json.dumps({'impl': 'reference', 'unavailable': ms}))
+                return
+            mode, lattice, nb, nlf, units, beta = L2HMC_WORKLOADS[args.workload]
+            print(json.dumps({
+                'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'link-updates/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 lattice + f64 nets',
+                'data': 'synthetic',
+                'config': {'workload': args.workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
+                           'nleapfrog': nlf, 'units': [units], 'beta': beta, 'step': mode, 'sample': base['sample']},
+                'cpu_baseline': base,
+                'e2e': {'value': base['value'], 'unit': 'link-updates/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
             return
         main_reference(args)
     elif args.workload in L2HMC_WORKLOADS:
