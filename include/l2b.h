@@ -275,6 +275,19 @@ int l2b_u1_kinetic(const void* v, void* ke, int nb, int xdim, int dtype, void* s
 int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stream);
 
 /* --- adjoints (L2HMC training; the reference relies on autograd for these) --- */
+/* The three output heads of a U(1) LeapfrogLayer (network/pytorch/network.py:536-548) fused with the
+ * update that consumes them: mode 0 = Dynamics._update_v_fwd/_bwd (dynamics.py:1266-1297) on (a = v,
+ * b = force), mode 1 = _update_x_fwd/_bwd (dynamics.py:1398-1467) on (a = x, b = v, mask).  z: [nb, hidden]
+ * output of the hidden stack; w_*: [xdim, hidden] nn.Linear weights, b_*: [xdim], coeff_*: [xdim]
+ * (ScaledTanh.coeff), nw_* the NetWeight factors; all of `dtype`.  hidden <= 32 (CUDA-core kernel: the
+ * U(1) nets are 16 wide), else L2B_ERR_UNSUPPORTED.  s, t, q never reach HBM. */
+size_t l2b_u1_heads_ws_bytes(int nb, int xdim);
+int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, const void* w_t, const void* w_q,
+                        const void* b_s, const void* b_t, const void* b_q, const void* coeff_s, const void* coeff_q,
+                        double nw_s, double nw_t, double nw_q, const void* a, const void* b, const float* mask,
+                        double eps, const void* eps_dev, int sign, int use_ncp, void* out, void* logdet, int nb,
+                        int xdim, int dtype, void* ws, size_t ws_bytes, void* stream);
+
 /* adjoint of l2b_u1_wilson_loops: gx[nb,2,T,X] from gw[nb,T,X] */
 int l2b_u1_wilson_loops_bwd(const void* gw, void* gx, int nb, int T, int X, int dtype, void* stream);
 /* adjoint of l2b_u1_force = Hessian-vector product of the action (the reference

@@ -255,6 +255,164 @@ __global__ void __launch_bounds__(256) k_u1_xupdate(const T* __restrict__ x, con
   }
 }
 
+// ---------------------------------------------------------------------------
+// The three output heads of a U(1) LeapfrogLayer (network.py:536-548) fused with the update that
+// consumes them (dynamics.py:1266-1297 v-update / :1398-1467 x-update): s, t, q ([nb, xdim] each,
+// three times the size of the field) never reach HBM.  The hidden width of the U(1) nets is small
+// (conf/network/default.yaml: 16), far below a tensor-core K step worth filling, so this is a
+// CUDA-core kernel: each thread owns one output column, keeps its three weight rows (3 x HP
+// registers) and walks over a tile of chains whose hidden vectors z sit in shared memory (broadcast
+// reads); x / v / F accesses are coalesced across the columns of a warp.
+//   MODE 0: v' = vupdate(v, F; s, t, q)     MODE 1: x' = xupdate(x, v; s, t, q; mask)
+// ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T tanh_(T a);
+template <> __device__ __forceinline__ float tanh_<float>(float a) {   // 1 - 2 / (1 + e^{2a}): abs error ~2e-7
+  return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * a));
+}
+template <> __device__ __forceinline__ double tanh_<double>(double a) { return tanh(a); }
+
+// element-wise math of the fused kernel.  float: SFU intrinsics (absolute errors ~1e-7 on the arguments
+// that occur here: half-angles in [-pi/2, pi/2], exponents of O(eps)), well inside the 1e-5 fp32 budget;
+// double: the accurate library functions.
+template <typename T> struct FNum : Num<T> {
+  static __device__ __forceinline__ void sincos_(T a, T& s, T& c) { s = Num<T>::sin_(a); c = Num<T>::cos_(a); }
+  static __device__ __forceinline__ T div_(T a, T b) { return a / b; }
+};
+template <> struct FNum<float> : Num<float> {
+  static __device__ __forceinline__ float exp_(float a) { return __expf(a); }
+  static __device__ __forceinline__ float log_(float a) { return __logf(a); }
+  static __device__ __forceinline__ void sincos_(float a, float& s, float& c) { __sincosf(a, &s, &c); }
+  static __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
+};
+
+constexpr int kHeadsChains = 64;      // chains per block tile (amortises the per-thread weight-row loads)
+
+template <typename T, int HP, int MODE>
+__global__ void __launch_bounds__(256, 3) k_u1_heads_update(
+    const T* __restrict__ z, int H, const T* __restrict__ Ws, const T* __restrict__ Wt, const T* __restrict__ Wq,
+    const T* __restrict__ bs, const T* __restrict__ bt, const T* __restrict__ bq, const T* __restrict__ cs,
+    const T* __restrict__ cq, T nws, T nwt, T nwq, const T* __restrict__ a, const T* __restrict__ bfield,
+    const float* __restrict__ mask, T eps_in, const T* __restrict__ eps_dev, int sign, int use_ncp,
+    T* __restrict__ out, double* __restrict__ part, int nb, int xdim) {
+  __shared__ T zt[kHeadsChains][HP];
+  __shared__ double ldw[8][kHeadsChains];
+  const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x * 256 + tid;
+  const int b0 = blockIdx.y * kHeadsChains;
+  const int nbt = min(kHeadsChains, nb - b0);
+  for (int idx = tid; idx < kHeadsChains * HP; idx += 256) {
+    const int c = idx / HP, k = idx % HP;
+    zt[c][k] = (c < nbt && k < H) ? z[(size_t)(b0 + c) * H + k] : T(0);
+  }
+  const bool ok = j < xdim;
+  T ws[HP], wt[HP], wq[HP];
+  if (sizeof(T) == 4 && (H & 3) == 0 && ok) {            // rows are 16-byte aligned: 128-bit loads
+    const float4* r0 = reinterpret_cast<const float4*>(Ws + (size_t)j * H);
+    const float4* r1 = reinterpret_cast<const float4*>(Wt + (size_t)j * H);
+    const float4* r2 = reinterpret_cast<const float4*>(Wq + (size_t)j * H);
+#pragma unroll
+    for (int k4 = 0; k4 < HP / 4; ++k4) {
+      const bool kk = 4 * k4 < H;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 u0 = kk ? __ldg(r0 + k4) : z4, u1 = kk ? __ldg(r1 + k4) : z4, u2 = kk ? __ldg(r2 + k4) : z4;
+      ws[4 * k4] = (T)u0.x; ws[4 * k4 + 1] = (T)u0.y; ws[4 * k4 + 2] = (T)u0.z; ws[4 * k4 + 3] = (T)u0.w;
+      wt[4 * k4] = (T)u1.x; wt[4 * k4 + 1] = (T)u1.y; wt[4 * k4 + 2] = (T)u1.z; wt[4 * k4 + 3] = (T)u1.w;
+      wq[4 * k4] = (T)u2.x; wq[4 * k4 + 1] = (T)u2.y; wq[4 * k4 + 2] = (T)u2.z; wq[4 * k4 + 3] = (T)u2.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+      const bool kk = ok && k < H;
+      ws[k] = kk ? Ws[(size_t)j * H + k] : T(0);
+      wt[k] = kk ? Wt[(size_t)j * H + k] : T(0);
+      wq[k] = kk ? Wq[(size_t)j * H + k] : T(0);
+    }
+  }
+  const T b_s = ok ? bs[j] : T(0), b_t = ok ? bt[j] : T(0), b_q = ok ? bq[j] : T(0);
+  const T a_s = ok ? nws * Num<T>::exp_(cs[j]) : T(0), a_q = ok ? nwq * Num<T>::exp_(cq[j]) : T(0);
+  const T m = (MODE == 1 && ok) ? (T)mask[j] : T(0), mb = T(1) - m;
+  const T sg = (T)sign;
+  __syncthreads();
+  constexpr int G = 4;                                   // chains per group: their field loads are in flight together
+  for (int c0 = 0; c0 < nbt; c0 += G) {
+    T av[G], bv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const bool live = ok && (c0 + g < nbt);
+      const size_t at = (size_t)(b0 + c0 + g) * xdim + j;
+      av[g] = live ? a[at] : T(0);
+      bv[g] = live ? bfield[at] : T(0);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int c = c0 + g;
+      if (c >= nbt) break;                               // block-uniform
+      T sp = b_s, tp = b_t, qp = b_q;
+#pragma unroll
+      for (int k = 0; k < HP; ++k) {
+        const T zk = zt[c][k];
+        sp = fma(ws[k], zk, sp);
+        tp = fma(wt[k], zk, tp);
+        qp = fma(wq[k], zk, qp);
+      }
+      const T sv = a_s * tanh_<T>(sp), tv = nwt * tp, qv = a_q * tanh_<T>(qp);
+      const size_t at = (size_t)(b0 + c) * xdim + j;
+      T lj = T(0);
+      if (ok) {
+        if (MODE == 0) {                                 // k_u1_vupdate
+          const T logjac = sg * eps * sv / T(2);
+          const T es = FNum<T>::exp_(logjac), eq = FNum<T>::exp_(eps * qv);
+          const T fn = bv[g] * eq + tv;
+          const T he = T(0.5) * eps;
+          out[at] = (sign > 0) ? (es * av[g] - he * fn) : (es * (av[g] + he * fn));
+          lj = logjac;
+        } else {                                         // k_u1_xupdate
+          const T xi = av[g], vi = bv[g];
+          const T si = (sg * eps) * sv, qi = eps * qv;
+          const T es = FNum<T>::exp_(si), eq = FNum<T>::exp_(qi);
+          const T tr = eps * (vi * eq + tv);
+          T xn, l1;
+          if (use_ncp) {
+            T sh, ch;
+            FNum<T>::sincos_(xi / T(2), sh, ch);         // tan, cos, sin of the half angle from one sincos
+            const T x1 = T(2) * Num<T>::atan_(FNum<T>::div_(sh, ch) * es);
+            xn = (sign > 0) ? (x1 + tr) : (x1 - es * tr);
+            const T st = es * sh;
+            l1 = FNum<T>::log_(FNum<T>::div_(es, ch * ch + st * st));
+          } else {
+            xn = (sign > 0) ? (xi * es + tr) : (es * (xi - tr));
+            l1 = si;
+          }
+          lj = mb * l1;
+          out[at] = wrap_pi(m * xi + mb * xn);
+        }
+      }
+      double r = (double)lj;                             // fixed shuffle tree, then a fixed order over the 8 warps
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+      if (lane == 0) ldw[warp][c] = r;
+    }
+  }
+  __syncthreads();
+  if (part != nullptr && tid < nbt) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x += ldw[w][tid];
+    part[(size_t)(b0 + tid) * gridDim.x + blockIdx.x] = x;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_sum_rows(const double* __restrict__ part, int n, T* __restrict__ out) {
+  __shared__ double red[8];
+  const double* row = part + (size_t)blockIdx.x * n;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < n; k += 256) s += row[k];
+  s = block_sum<256>(s, red, threadIdx.x);
+  if (threadIdx.x == 0) out[blockIdx.x] = (T)s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_kinetic(const T* __restrict__ v, T* __restrict__ ke, int xdim) {
   __shared__ double red[8];
@@ -487,6 +645,28 @@ int dispatch_hmc(const void* x, const void* v, double beta, double eps, int nlf,
 
 using namespace l2b;
 
+namespace l2b {
+namespace {
+template <typename T, int MODE>
+int launch_u1_heads(int hp, dim3 grid, cudaStream_t st, const void* z, int H, const void* const w[3],
+                    const void* const b[3], const void* cs, const void* cq, const double nw[3], const void* a,
+                    const void* bf, const float* mask, double eps, const void* eps_dev, int sign, int use_ncp,
+                    void* out, double* part, int nb, int xdim) {
+#define L2B_U1H(HP)                                                                                              \
+  k_u1_heads_update<T, HP, MODE><<<grid, 256, 0, st>>>(                                                           \
+      (const T*)z, H, (const T*)w[0], (const T*)w[1], (const T*)w[2], (const T*)b[0], (const T*)b[1],             \
+      (const T*)b[2], (const T*)cs, (const T*)cq, (T)nw[0], (T)nw[1], (T)nw[2], (const T*)a, (const T*)bf, mask,   \
+      (T)eps, (const T*)eps_dev, sign, use_ncp, (T*)out, part, nb, xdim)
+  if (hp == 8) L2B_U1H(8);
+  else if (hp == 16) L2B_U1H(16);
+  else L2B_U1H(32);
+#undef L2B_U1H
+  L2B_LAUNCHED("k_u1_heads_update");
+  return L2B_OK;
+}
+}  // namespace
+}  // namespace l2b
+
 extern "C" {
 
 size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype) {
@@ -681,6 +861,54 @@ int l2b_rowscale(const void* in, const void* scale, void* out, int nb, int xdim,
   L2B_DISPATCH_T(dtype, (k_rowscale<float><<<grid, 256, 0, st>>>((const float*)in, (const float*)scale, (float*)out, xdim)),
                  (k_rowscale<double><<<grid, 256, 0, st>>>((const double*)in, (const double*)scale, (double*)out, xdim)));
   L2B_LAUNCHED("k_rowscale");
+  return L2B_OK;
+}
+
+size_t l2b_u1_heads_ws_bytes(int nb, int xdim) {
+  if (nb <= 0 || xdim <= 0) return 0;
+  return align_up((size_t)nb * ((xdim + 255) / 256) * sizeof(double), 256);
+}
+
+int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, const void* w_t, const void* w_q,
+                        const void* b_s, const void* b_t, const void* b_q, const void* coeff_s, const void* coeff_q,
+                        double nw_s, double nw_t, double nw_q, const void* a, const void* b, const float* mask,
+                        double eps, const void* eps_dev, int sign, int use_ncp, void* out, void* logdet, int nb,
+                        int xdim, int dtype, void* ws, size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(mode == 0 || mode == 1, L2B_ERR_INVALID, "mode must be 0 (v-update) or 1 (x-update)");
+  L2B_REQUIRE(hidden > 0 && hidden <= 32, L2B_ERR_UNSUPPORTED, "fused U(1) heads need hidden <= 32 (got %d)", hidden);
+  L2B_REQUIRE(z && w_s && w_t && w_q && b_s && b_t && b_q && coeff_s && coeff_q && a && b && out, L2B_ERR_INVALID,
+              "null pointer");
+  L2B_REQUIRE(mode == 0 || mask != nullptr, L2B_ERR_INVALID, "the x-update needs a mask");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  const int nblk = (xdim + 255) / 256;
+  double* part = nullptr;
+  if (logdet) {
+    L2B_REQUIRE(ws && ws_bytes >= l2b_u1_heads_ws_bytes(nb, xdim), L2B_ERR_WORKSPACE, "workspace too small");
+    part = (double*)ws;
+  }
+  const int nyb = (nb + kHeadsChains - 1) / kHeadsChains;
+  L2B_REQUIRE(nyb <= 65535, L2B_ERR_UNSUPPORTED, "too many chains for one launch");
+  const dim3 grid(nblk, nyb);
+  const int hp = hidden <= 8 ? 8 : (hidden <= 16 ? 16 : 32);
+  const void* const w[3] = {w_s, w_t, w_q};
+  const void* const bb[3] = {b_s, b_t, b_q};
+  const double nw[3] = {nw_s, nw_t, nw_q};
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (dtype == L2B_F32)
+    rc = mode == 0 ? launch_u1_heads<float, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim)
+                   : launch_u1_heads<float, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim);
+  else
+    rc = mode == 0 ? launch_u1_heads<double, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim)
+                   : launch_u1_heads<double, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim);
+  if (rc != L2B_OK) return rc;
+  if (logdet) {
+    if (dtype == L2B_F32) k_u1_sum_rows<float><<<nb, 256, 0, st>>>(part, nblk, (float*)logdet);
+    else k_u1_sum_rows<double><<<nb, 256, 0, st>>>(part, nblk, (double*)logdet);
+    L2B_LAUNCHED("k_u1_sum_rows");
+  }
   return L2B_OK;
 }
 

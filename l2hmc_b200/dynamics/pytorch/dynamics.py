@@ -692,6 +692,15 @@ class Dynamics(nn.Module):
             return True
         return torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.bfloat16
 
+    def _u1_fused(self, net, field: Tensor) -> bool:
+        """U(1) inference: the three output heads fused with the update (`l2b_u1_heads_update`);
+        `fused_u1_heads` = 'auto' (default: whenever no gradient is being recorded) | 'never'"""
+        if not self._networks_built or torch.is_grad_enabled() or torch.is_autocast_enabled('cuda'):
+            return False
+        if getattr(self, 'fused_u1_heads', 'auto') == 'never':
+            return False
+        return ops.u1_heads_supported(net.units[-1]) and net.transl.weight.dtype == field.dtype
+
     def _update_v(self, step: int, state: State, sign: int, hmc: bool = False) -> tuple[State, Tensor]:
         """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel (hmc=True: no
         networks, the plain half kick v -+ eps/2 F of dynamics.py:1244-1254)"""
@@ -712,6 +721,12 @@ class Dynamics(nn.Module):
             v, logdet = ag.SU3HeadsVUpdate.apply(z, self.unflatten(state.v), self.unflatten(force),
                                                  self._eps_t(self.veps[step]).to(torch.float64), sign, eps, vnet,
                                                  *vnet.head_params())
+            return State(state.x, v, state.beta), logdet
+        if not self._su3 and self._u1_fused(self._get_vnet(step), state.v):
+            vnet = self._get_vnet(step)          # heads + update in one kernel: s, t, q never reach HBM
+            z = vnet.hidden((state.x, force))
+            v, logdet = ops.u1_heads_update(0, z, vnet.head_params(), (vnet.nw.s, vnet.nw.t, vnet.nw.q), state.v,
+                                            force, self._eps_t(self.veps[step]), sign)
             return State(state.x, v, state.beta), logdet
         s, t, q = self._call_vnet(step, (state.x, force))
         if self._su3:
@@ -737,6 +752,13 @@ class Dynamics(nn.Module):
                                          m, sign, eps)
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
         xm_init = self.unflatten(m) * x
+        xnet = self._get_xnet(step, first)
+        if self._u1_fused(xnet, state.v):
+            z = xnet.hidden((self.g.group_to_vec(xm_init), state.v))
+            xn, logdet = ops.u1_heads_update(1, z, xnet.head_params(), (xnet.nw.s, xnet.nw.t, xnet.nw.q), x, state.v,
+                                             self._eps_t(self.xeps[step]), sign, mask=m,
+                                             use_ncp=bool(self.config.use_ncp))
+            return State(x=xn.reshape(x.shape), v=state.v, beta=state.beta), logdet
         s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)
         xn, logdet = ag.U1XUpdate.apply(x, state.v, s, t, q, m, self._eps_t(self.xeps[step]), sign,
                                         bool(self.config.use_ncp), eps)

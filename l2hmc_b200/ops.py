@@ -697,3 +697,41 @@ def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps,
          _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), ev, ep,
          int(sign), _ptr(out), _ptr(logdet), _ptr(stq), nb, pack.xdim, pack.hidden, _ptr(ws), nws, _stream())
     return (out, logdet, stq) if want_stq else (out, logdet)
+
+
+# ---------------------------------------------------------------------------
+# U(1): output heads fused with the update (CUDA-core kernel, hidden <= 32)
+# ---------------------------------------------------------------------------
+def u1_heads_supported(hidden: int) -> bool:
+    return 0 < hidden <= 32
+
+
+def u1_heads_update(mode: int, z: Tensor, head_params, nw, a: Tensor, b: Tensor, eps, sign: int,
+                    mask: Optional[Tensor] = None, use_ncp: bool = True):
+    """mode 0: (v', logdet) = vupdate(a = v, b = force); mode 1: (x', logdet) = xupdate(a = x, b = v, mask).
+    head_params = (W_s, b_s, c_s, W_t, b_t, W_q, b_q, c_q) as `LeapfrogLayer.head_params()`, nw = (s, t, q)."""
+    ws_, bs, cs, wt, bt, wq, bq, cq = (p.detach().contiguous() for p in head_params)
+    _need_cuda(z, a, b, ws_)
+    dt = a.dtype
+    nb = int(a.shape[0])
+    a2, b2 = a.reshape(nb, -1).contiguous(), b.reshape(nb, -1).to(dt).contiguous()
+    xdim, hidden = int(a2.shape[1]), int(ws_.shape[1])
+    if any(p.dtype != dt for p in (ws_, bs, cs, wt, bt, wq, bq, cq)) or tuple(ws_.shape) != (xdim, hidden):
+        raise L2BError('head parameters must have the field dtype and shape [xdim, hidden]')
+    z = z.detach().to(dt).contiguous()
+    if tuple(z.shape) != (nb, hidden):
+        raise L2BError(f'z must be [{nb}, {hidden}] (got {tuple(z.shape)})')
+    if mode == 1:
+        if mask is None:
+            raise L2BError('the x-update needs a mask')
+        mask = mask.to(torch.float32).reshape(-1).contiguous()
+    out = torch.empty_like(a2)
+    logdet = torch.empty(nb, dtype=dt, device=a.device)
+    nws = int(_lib._lib.l2b_u1_heads_ws_bytes(nb, xdim))
+    ws = _workspace(nws, a.device)
+    ev, ep, _keep = _eps_args(eps, dt)
+    call('l2b_u1_heads_update', int(mode), _ptr(z), hidden, _ptr(ws_), _ptr(wt), _ptr(wq), _ptr(bs), _ptr(bt), _ptr(bq),
+         _ptr(cs.reshape(-1)), _ptr(cq.reshape(-1)), float(nw[0]), float(nw[1]), float(nw[2]), _ptr(a2), _ptr(b2),
+         _ptr(mask), ev, ep, int(sign), int(bool(use_ncp)), _ptr(out), _ptr(logdet), nb, xdim, _dt(a2), _ptr(ws), nws,
+         _stream())
+    return out, logdet

@@ -3,6 +3,7 @@
 [8,16,32,64,128], units [16,16,16,16], dropout 0.2, batch norm, fp32):
     python profiles/prof_u1_l2hmc.py eval|train|hmc [nb] [reps] [--graph] [--table]
 Prints ms per step (CUDA events + wall).  Numbers under a profiler are never reported."""
+import os
 import sys
 import time
 from pathlib import Path
@@ -26,15 +27,18 @@ graph = '--graph' in sys.argv
 torch.manual_seed(9992)
 np.random.seed(9992)
 torch.set_default_dtype(torch.float32)
-shape = [16, 16]
+L = int(os.environ.get('L2B_U1_L', '16'))
+shape = [L, L]
+NOCONV = os.environ.get('L2B_U1_CONV', 'default') == 'none'
 cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=8, eps=0.1, eps_hmc=None, use_ncp=True,
                      verbose=False, eps_fixed=False, use_split_xnets=True, merge_directions=True,
                      use_separate_networks=True)
 fac = NetworkFactory(input_spec=get_input_spec(cfg),
                      network_config=NetworkConfig(units=[16, 16, 16, 16], activation_fn='leaky_relu', dropout_prob=0.2,
                                                   use_batch_norm=True),
-                     conv_config=ConvolutionConfig(filters=[8, 16, 32, 64, 128], sizes=[5, 3, 3, 3, 2],
-                                                   pool=[2, 2, 2, 2, 2]), net_weights=None)
+                     conv_config=None if NOCONV else ConvolutionConfig(filters=[8, 16, 32, 64, 128],
+                                                                       sizes=[5, 3, 3, 3, 2], pool=[2, 2, 2, 2, 2]),
+                     net_weights=None)
 lat = LatticeU1(nb, shape)
 dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
 kw = {'cuda_graphs': True} if graph else {}
@@ -63,8 +67,8 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 nlf_eff = 16
-print(f'{mode} U1 16x16 nb={nb} graph={graph}: {ms:.3f} ms/step (wall {1e3 * (time.perf_counter() - t0) / reps:.3f}), '
-      f'{nb * 2 * 256 * nlf_eff / (ms * 1e-3):.3e} link-updates/s, acc={float(m["acc"].mean()):.3f}, loss={float(m["loss"]):.4f}')
+print(f'{mode} U1 {L}x{L} conv={"none" if NOCONV else "default"} nb={nb} graph={graph}: {ms:.3f} ms/step (wall {1e3 * (time.perf_counter() - t0) / reps:.3f}), '
+      f'{nb * 2 * L * L * nlf_eff / (ms * 1e-3):.3e} link-updates/s, acc={float(m["acc"].mean()):.3f}, loss={float(m["loss"]):.4f}')
 if '--table' in sys.argv:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:

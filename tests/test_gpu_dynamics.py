@@ -97,7 +97,8 @@ def test_su3_l2hmc_matches_reference(golden_dir, default_dtype):
 
 @pytest.mark.parametrize('tag,tol', [('f64', 1e-11), ('f32', 2e-5)])
 @pytest.mark.parametrize('name', ['dense', 'conv'])
-def test_u1_l2hmc_matches_reference(golden_dir, default_dtype, tag, tol, name):
+@pytest.mark.parametrize('fused', ['auto', 'never'])      # heads fused with the update (l2b_u1_heads_update) or not
+def test_u1_l2hmc_matches_reference(golden_dir, default_dtype, tag, tol, name, fused):
     default_dtype(torch.float64 if tag == 'f64' else torch.float32)
     from l2hmc_b200.configs import DynamicsConfig, NetworkConfig, ConvolutionConfig, get_input_spec
     from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
@@ -120,6 +121,9 @@ def test_u1_l2hmc_matches_reference(golden_dir, default_dtype, tag, tol, name):
     assert ours == set(sd), f'state_dict key mismatch: {sorted(ours ^ set(sd))[:6]}'
     dyn.masks = [dev(m) for m in gu[pre + 'masks']]
     dyn.eval()
+    dyn.fused_u1_heads = fused
+    from l2hmc_b200 import _lib
+    n0 = _lib.launch_count()
     st = State(dev(gu['x']), dev(gu[pre + 'v']), torch.tensor(float(gu['beta'])))
     with torch.no_grad():
         m, _ = dyn._get_mask(0)
