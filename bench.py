@@ -479,7 +479,8 @@ def main_l2hmc(args):
     lat = LatticeSU3(nb, lattice)
     dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
     tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
-                 clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16)
+                 clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16,
+                 cuda_graphs=args.cuda_graphs)
     torch.manual_seed(SEED + 1 + rank)   # per-rank chains
     x = lat.random().to(torch.complex128)
     bt = torch.tensor(beta)
@@ -568,6 +569,7 @@ def main_l2hmc(args):
             'dtype': 'f64 lattice + bf16 nets (fp32 accumulate)', 'data': 'synthetic',
             'config': {'workload': args.workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'units': [units], 'beta': beta, 'step': mode,
+                       'cuda_graphs': bool(args.cuda_graphs),
                        'start': 'hot (g.random), random-init weights',
                        'parallelism': (f'chains sharded over {world} GPU(s); '
                                        + ('one flat bf16 NCCL all-reduce of the NN gradients per step' if mode == 'train'
@@ -667,6 +669,8 @@ def main():
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--workload', choices=sorted(WORKLOADS) + sorted(L2HMC_WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cuda-graphs', action='store_true',
+                    help='L2HMC workloads: run the Trainer step functions as CUDA graphs (Trainer(cuda_graphs=True))')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -74,7 +74,8 @@ class Trainer:
                 if train:
                     self.optimizer.zero_grad(set_to_none=True)
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                # thread_local: the NCCL watchdog thread may touch the CUDA runtime while we capture
+                with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                     out = fn(static_x)
             finally:
                 self._eager = False
@@ -131,7 +132,9 @@ class Trainer:
         if self.cuda_graphs and not self._eager:
             if torch.distributed.is_available() and torch.distributed.is_initialized() \
                     and torch.distributed.get_world_size() > 1:
-                raise RuntimeError('cuda_graphs for train_step is single-process for now (all-reduce not captured)')
+                # measured on 2 B200s: capturing the NCCL all-reduce works and replays, but process-group
+                # teardown then hangs; and for the GPU-bound SU(3) step graphs buy nothing (r1d profiles)
+                raise RuntimeError('cuda_graphs for train_step is single-process (the all-reduce is not captured)')
             xi, beta = inputs
             xi = self._canon(xi)
             key = ('train', tuple(xi.shape), xi.dtype, float(beta))
