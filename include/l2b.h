@@ -281,6 +281,15 @@ int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stre
  * output of the hidden stack; w_*: [xdim, hidden] nn.Linear weights, b_*: [xdim], coeff_*: [xdim]
  * (ScaledTanh.coeff), nw_* the NetWeight factors; all of `dtype`.  hidden <= 32 (CUDA-core kernel: the
  * U(1) nets are 16 wide), else L2B_ERR_UNSUPPORTED.  s, t, q never reach HBM. */
+/* Input layer of a U(1) LeapfrogLayer WITHOUT conv stack (network.py:349-451), xlayer and vlayer in one
+ * pass over the two fields: pre[nb, units] = W_x . f(x) + b_x + W_v . v + b_v, with mode 1 (xnet)
+ * f(x) = cat(cos(mask * x), sin(mask * x)) (dynamics.py:1169-1178; w_x is [units, 2 xdim]) and mode 0
+ * (vnet) f(x) = x (w_x is [units, xdim]; pass the force as v).  The caller applies the activation.
+ * units <= 16, else L2B_ERR_UNSUPPORTED. */
+size_t l2b_u1_input_ws_bytes(int nb, int xdim);
+int l2b_u1_input_layer(int mode, const void* x, const void* v, const float* mask, const void* w_x, const void* b_x,
+                       const void* w_v, const void* b_v, int units, void* pre, int nb, int xdim, int dtype, void* ws,
+                       size_t ws_bytes, void* stream);
 size_t l2b_u1_heads_ws_bytes(int nb, int xdim);
 int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, const void* w_t, const void* w_q,
                         const void* b_s, const void* b_t, const void* b_q, const void* coeff_s, const void* coeff_q,

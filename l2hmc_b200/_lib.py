@@ -87,6 +87,7 @@ _SIGS = {
     'l2b_u1_xupdate_bwd': [_P, _P, _P, _P, _P, _P, c_double, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, _P],
     'l2b_u1_heads_update': [c_int, _P, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_double, c_double, c_double, _P, _P, _P,
                             c_double, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P],
+    'l2b_u1_input_layer': [c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, _P, c_size_t, _P],
     'l2b_rowscale': [_P, _P, _P, c_int, c_int, c_int, _P],
     'l2b_accept_mix': [POINTER(_P), POINTER(_P), POINTER(_P), POINTER(c_size_t), c_int, _P, c_int, _P],
 }
@@ -99,6 +100,7 @@ _RES = {
     'l2b_vnet_heads_packed_bytes': ([c_int, c_int], c_size_t),
     'l2b_vnet_heads_ws_bytes': ([c_int, c_int], c_size_t),
     'l2b_u1_heads_ws_bytes': ([c_int, c_int], c_size_t),
+    'l2b_u1_input_ws_bytes': ([c_int, c_int], c_size_t),
 }
 
 EXPORTS = sorted(list(_SIGS) + list(_RES))

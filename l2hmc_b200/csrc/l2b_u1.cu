@@ -403,6 +403,113 @@ __global__ void __launch_bounds__(256, 3) k_u1_heads_update(
   }
 }
 
+// ---------------------------------------------------------------------------
+// Input layer of a U(1) LeapfrogLayer without conv stack (network.py:349-451), both Linears in ONE pass
+// over the two fields:   pre[b, u] = sum_j f1(x_bj) W1[u, j] + f2(x_bj) W2[u, j] + v_bj Wv[u, j]
+//   MODE 1 (xnet): f1 = cos(m_j x), f2 = sin(m_j x)   (group_to_vec of the masked links, dynamics.py:1169-1178;
+//                  W1 = W_x[:, :xdim], W2 = W_x[:, xdim:])
+//   MODE 0 (vnet): f1 = x, no f2                      (raw x and force, dynamics.py:1157-1159)
+// cuBLAS runs these as two [nb x K] x [K x 16] GEMMs at 0.75 TB/s plus a cat(cos, sin) pass; here x and v are
+// read once.  Thread = column j with its (2 or 3) x UP weights in registers, loop over a tile of chains; the
+// per-chain sums over the block's 256 columns use a reduce-scatter butterfly (16 + 16 shuffles/adds for UP = 16
+// instead of 16 x 5), per-warp partials in shared memory, fixed order -> deterministic.
+// part[colblk][b][UP]; k_u1_input_finish adds the column blocks and the two biases.
+// ---------------------------------------------------------------------------
+template <typename T> struct InTile { static constexpr int CB = sizeof(T) == 8 ? 32 : 64; };   // 32 KB of smem partials
+
+template <typename T, int UP, int MODE>
+__global__ void __launch_bounds__(256, 3) k_u1_input_layer(const T* __restrict__ x, const T* __restrict__ v,
+                                                           const float* __restrict__ mask,
+                                                           const T* __restrict__ Wx, const T* __restrict__ Wv, int U,
+                                                           T* __restrict__ part, int nb, int xdim) {
+  static_assert(UP == 16, "butterfly below is written for 16 outputs");
+  constexpr int CB = InTile<T>::CB;
+  __shared__ T wpart[8][CB][UP];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int j = blockIdx.x * 256 + tid;
+  const int b0 = blockIdx.y * CB;
+  const int nbt = min(CB, nb - b0);
+  const bool ok = j < xdim;
+  const int ldx = (MODE == 1) ? 2 * xdim : xdim;
+  T w1[UP], w2[UP], wv[UP];
+#pragma unroll
+  for (int u = 0; u < UP; ++u) {
+    const bool uu = ok && u < U;
+    w1[u] = uu ? Wx[(size_t)u * ldx + j] : T(0);
+    w2[u] = (uu && MODE == 1) ? Wx[(size_t)u * ldx + xdim + j] : T(0);
+    wv[u] = uu ? Wv[(size_t)u * xdim + j] : T(0);
+  }
+  const T m = (MODE == 1 && ok) ? (T)mask[j] : T(1);
+  constexpr int G = 4;
+  for (int c0 = 0; c0 < nbt; c0 += G) {
+    T xv[G], vv[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const bool live = ok && (c0 + g < nbt);
+      const size_t at = (size_t)(b0 + c0 + g) * xdim + j;
+      xv[g] = live ? x[at] : T(0);
+      vv[g] = live ? v[at] : T(0);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const int c = c0 + g;
+      if (c >= nbt) break;
+      T f1, f2 = T(0);
+      if (MODE == 1) FNum<T>::sincos_(m * xv[g], f2, f1);      // f1 = cos, f2 = sin
+      else f1 = xv[g];
+      if (!ok) { f1 = T(0); f2 = T(0); }                        // cos(0) = 1 must not leak from padded columns
+      T acc[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        T a = f1 * w1[u];
+        if (MODE == 1) a = fma(f2, w2[u], a);
+        acc[u] = fma(vv[g], wv[u], a);
+      }
+      // reduce-scatter over the 32 lanes: after the 4 halving steps lane l holds the partial sum of output
+      // (l >> 1) over its 16-lane... pairs; one more exchange finishes it
+#define L2B_RS_STEP(O, Hh)                                                              \
+      {                                                                                   \
+        const bool up = (lane & (O)) != 0;                                                \
+        _Pragma("unroll") for (int i = 0; i < (Hh); ++i) {                                \
+          const T send = up ? acc[i] : acc[i + (Hh)];   /* the half the partner keeps */    \
+          const T keep = up ? acc[i + (Hh)] : acc[i];                                       \
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));                         \
+        }                                                                                 \
+      }
+      L2B_RS_STEP(16, 8)
+      L2B_RS_STEP(8, 4)
+      L2B_RS_STEP(4, 2)
+      L2B_RS_STEP(2, 1)
+#undef L2B_RS_STEP
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+      if ((lane & 1) == 0) {
+        // which output this lane ended up with: bit k of u is set iff the lane kept the upper half at step k
+        const int u = ((lane & 16) ? 8 : 0) | ((lane & 8) ? 4 : 0) | ((lane & 4) ? 2 : 0) | ((lane & 2) ? 1 : 0);
+        wpart[warp][c][u] = acc[0];
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nbt * UP; idx += 256) {
+    const int c = idx / UP, u = idx % UP;
+    T s_ = T(0);
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s_ += wpart[w][c][u];
+    part[((size_t)blockIdx.x * nb + (b0 + c)) * UP + u] = s_;
+  }
+}
+
+template <typename T, int UP>
+__global__ void __launch_bounds__(256) k_u1_input_finish(const T* __restrict__ part, int ncolblk, const T* __restrict__ bx,
+                                                         const T* __restrict__ bv, int U, T* __restrict__ out, int nb) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= nb * U) return;
+  const int b = idx / U, u = idx % U;
+  T s_ = bx[u] + bv[u];
+  for (int k = 0; k < ncolblk; ++k) s_ += part[((size_t)k * nb + b) * UP + u];
+  out[idx] = s_;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_sum_rows(const double* __restrict__ part, int n, T* __restrict__ out) {
   __shared__ double red[8];
@@ -909,6 +1016,43 @@ int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, co
     else k_u1_sum_rows<double><<<nb, 256, 0, st>>>(part, nblk, (double*)logdet);
     L2B_LAUNCHED("k_u1_sum_rows");
   }
+  return L2B_OK;
+}
+
+size_t l2b_u1_input_ws_bytes(int nb, int xdim) {
+  if (nb <= 0 || xdim <= 0) return 0;
+  return align_up((size_t)((xdim + 255) / 256) * nb * 16 * sizeof(double), 256);
+}
+
+int l2b_u1_input_layer(int mode, const void* x, const void* v, const float* mask, const void* w_x, const void* b_x,
+                       const void* w_v, const void* b_v, int units, void* pre, int nb, int xdim, int dtype, void* ws,
+                       size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "non-positive size");
+  L2B_REQUIRE(dtype == L2B_F32 || dtype == L2B_F64, L2B_ERR_UNSUPPORTED, "unknown dtype %d", dtype);
+  L2B_REQUIRE(mode == 0 || mode == 1, L2B_ERR_INVALID, "mode must be 0 (vnet) or 1 (xnet)");
+  L2B_REQUIRE(units > 0 && units <= 16, L2B_ERR_UNSUPPORTED, "fused U(1) input layer needs units[0] <= 16 (got %d)", units);
+  L2B_REQUIRE(x && v && w_x && b_x && w_v && b_v && pre, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(mode == 0 || mask != nullptr, L2B_ERR_INVALID, "the xnet input needs the mask");
+  L2B_REQUIRE(ws && ws_bytes >= l2b_u1_input_ws_bytes(nb, xdim), L2B_ERR_WORKSPACE, "workspace too small");
+  const int ncolblk = (xdim + 255) / 256;
+  const int cb = dtype == L2B_F32 ? 64 : 32;
+  const int nyb = (nb + cb - 1) / cb;
+  L2B_REQUIRE(nyb <= 65535, L2B_ERR_UNSUPPORTED, "too many chains for one launch");
+  const dim3 grid(ncolblk, nyb);
+  cudaStream_t st = (cudaStream_t)stream;
+#define L2B_U1IN(T, MODE)                                                                                           \
+  k_u1_input_layer<T, 16, MODE><<<grid, 256, 0, st>>>((const T*)x, (const T*)v, mask, (const T*)w_x, (const T*)w_v,  \
+                                                       units, (T*)ws, nb, xdim)
+  if (dtype == L2B_F32) { if (mode == 1) L2B_U1IN(float, 1); else L2B_U1IN(float, 0); }
+  else { if (mode == 1) L2B_U1IN(double, 1); else L2B_U1IN(double, 0); }
+#undef L2B_U1IN
+  L2B_LAUNCHED("k_u1_input_layer");
+  const int nfin = (nb * units + 255) / 256;
+  if (dtype == L2B_F32)
+    k_u1_input_finish<float, 16><<<nfin, 256, 0, st>>>((const float*)ws, ncolblk, (const float*)b_x, (const float*)b_v, units, (float*)pre, nb);
+  else
+    k_u1_input_finish<double, 16><<<nfin, 256, 0, st>>>((const double*)ws, ncolblk, (const double*)b_x, (const double*)b_v, units, (double*)pre, nb);
+  L2B_LAUNCHED("k_u1_input_finish");
   return L2B_OK;
 }
 

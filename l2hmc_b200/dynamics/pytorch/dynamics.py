@@ -701,6 +701,18 @@ class Dynamics(nn.Module):
             return False
         return ops.u1_heads_supported(net.units[-1]) and net.transl.weight.dtype == field.dtype
 
+    def _u1_hidden(self, net, mode: int, x: Tensor, v: Tensor, m: Optional[Tensor]) -> Tensor:
+        """hidden vector z of a U(1) net; dense nets: both input Linears (with the cos / sin of the masked links
+        for the xnet) in one pass over x and v (`l2b_u1_input_layer`), else the module's own input layer"""
+        il = net.input_layer
+        if net.dense_input() and ops.u1_input_supported(net.units[0]) and il.xlayer.weight.dtype == v.dtype:
+            pre = ops.u1_input_layer(mode, x, v, il.xlayer.weight, il.xlayer.bias, il.vlayer.weight, il.vlayer.bias,
+                                     mask=m)
+            return net.hidden_from_pre(pre)
+        if mode == 1:
+            return net.hidden((self.g.group_to_vec(self.unflatten(m) * self.unflatten(x)), v))
+        return net.hidden((x, v))
+
     def _update_v(self, step: int, state: State, sign: int, hmc: bool = False) -> tuple[State, Tensor]:
         """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel (hmc=True: no
         networks, the plain half kick v -+ eps/2 F of dynamics.py:1244-1254)"""
@@ -724,7 +736,7 @@ class Dynamics(nn.Module):
             return State(state.x, v, state.beta), logdet
         if not self._su3 and self._u1_fused(self._get_vnet(step), state.v):
             vnet = self._get_vnet(step)          # heads + update in one kernel: s, t, q never reach HBM
-            z = vnet.hidden((state.x, force))
+            z = self._u1_hidden(vnet, 0, state.x, force, None)
             v, logdet = ops.u1_heads_update(0, z, vnet.head_params(), (vnet.nw.s, vnet.nw.t, vnet.nw.q), state.v,
                                             force, self._eps_t(self.veps[step]), sign)
             return State(state.x, v, state.beta), logdet
@@ -751,14 +763,14 @@ class Dynamics(nn.Module):
             xn = ag.SU3UpdateGauge.apply(x, self.unflatten(state.v), self._eps_t(self.xeps[step]).to(torch.float64),
                                          m, sign, eps)
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
-        xm_init = self.unflatten(m) * x
         xnet = self._get_xnet(step, first)
         if self._u1_fused(xnet, state.v):
-            z = xnet.hidden((self.g.group_to_vec(xm_init), state.v))
+            z = self._u1_hidden(xnet, 1, x, state.v, m)
             xn, logdet = ops.u1_heads_update(1, z, xnet.head_params(), (xnet.nw.s, xnet.nw.t, xnet.nw.q), x, state.v,
                                              self._eps_t(self.xeps[step]), sign, mask=m,
                                              use_ncp=bool(self.config.use_ncp))
             return State(x=xn.reshape(x.shape), v=state.v, beta=state.beta), logdet
+        xm_init = self.unflatten(m) * x
         s, t, q = self._call_xnet(step, (xm_init, state.v), first=first)
         xn, logdet = ag.U1XUpdate.apply(x, state.v, s, t, q, m, self._eps_t(self.xeps[step]), sign,
                                         bool(self.config.use_ncp), eps)

@@ -195,6 +195,22 @@ class LeapfrogLayer(nn.Module):
             z = self.batch_norm(z)
         return z
 
+    def hidden_from_pre(self, pre: Tensor) -> Tensor:
+        """`hidden` given the input layer's pre-activation sum W_x f(x) + b_x + W_v v + b_v (computed by
+        `ops.u1_input_layer` in one pass over the fields)"""
+        z = self.activation_fn(pre)
+        for layer in self.hidden_layers:
+            z = self.activation_fn(layer(z))
+        if self.net_config.dropout_prob > 0:
+            z = self.dropout(z)
+        if self.net_config.use_batch_norm:
+            z = self.batch_norm(z)
+        return z
+
+    def dense_input(self) -> bool:
+        """no conv stack in front of the input Linears"""
+        return isinstance(self.input_layer.conv_stack, nn.Identity)
+
     def heads(self, z: Tensor) -> tuple[Tensor, Tensor, Tensor]:
         """network.py:546-548"""
         s = self.nw.s * self.scale(z)

@@ -735,3 +735,33 @@ def u1_heads_update(mode: int, z: Tensor, head_params, nw, a: Tensor, b: Tensor,
          _ptr(mask), ev, ep, int(sign), int(bool(use_ncp)), _ptr(out), _ptr(logdet), nb, xdim, _dt(a2), _ptr(ws), nws,
          _stream())
     return out, logdet
+
+
+def u1_input_supported(units0: int) -> bool:
+    return 0 < units0 <= 16
+
+
+def u1_input_layer(mode: int, x: Tensor, v: Tensor, w_x: Tensor, b_x: Tensor, w_v: Tensor, b_v: Tensor,
+                   mask: Optional[Tensor] = None) -> Tensor:
+    """pre-activation of InputLayer without conv stack: mode 1 (xnet) W_x . cat(cos(mask x), sin(mask x)) + b_x +
+    W_v . v + b_v, mode 0 (vnet) W_x . x + b_x + W_v . v + b_v; x and v are read once.  -> [nb, units]"""
+    _need_cuda(x, v, w_x, w_v)
+    dt = x.dtype
+    nb = int(x.shape[0])
+    x2, v2 = x.reshape(nb, -1).contiguous(), v.reshape(nb, -1).to(dt).contiguous()
+    xdim, units = int(x2.shape[1]), int(w_x.shape[0])
+    w_x, b_x, w_v, b_v = (p.detach().contiguous() for p in (w_x, b_x, w_v, b_v))
+    if any(p.dtype != dt for p in (w_x, b_x, w_v, b_v)):
+        raise L2BError('input-layer parameters must have the field dtype')
+    if tuple(w_x.shape) != (units, (2 if mode == 1 else 1) * xdim) or tuple(w_v.shape) != (units, xdim):
+        raise L2BError(f'unexpected input-layer weight shapes {tuple(w_x.shape)}, {tuple(w_v.shape)}')
+    if mode == 1:
+        if mask is None:
+            raise L2BError('the xnet input needs the mask')
+        mask = mask.to(torch.float32).reshape(-1).contiguous()
+    pre = torch.empty((nb, units), dtype=dt, device=x.device)
+    nws = int(_lib._lib.l2b_u1_input_ws_bytes(nb, xdim))
+    ws = _workspace(nws, x.device)
+    call('l2b_u1_input_layer', int(mode), _ptr(x2), _ptr(v2), _ptr(mask), _ptr(w_x), _ptr(b_x), _ptr(w_v), _ptr(b_v),
+         units, _ptr(pre), nb, xdim, _dt(x2), _ptr(ws), nws, _stream())
+    return pre
