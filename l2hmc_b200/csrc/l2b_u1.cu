@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(256) k_u1_xupdate(const T* __restrict__ x, con
 // reads); x / v / F accesses are coalesced across the columns of a warp.
 //   MODE 0: v' = vupdate(v, F; s, t, q)     MODE 1: x' = xupdate(x, v; s, t, q; mask)
 // ---------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T tanh_acc(T a) { return tanh(a); }
+template <> __device__ __forceinline__ float tanh_acc<float>(float a) { return tanhf(a); }
 template <typename T> __device__ __forceinline__ T tanh_(T a);
 template <> __device__ __forceinline__ float tanh_<float>(float a) {   // 1 - 2 / (1 + e^{2a}): abs error ~2e-7
   return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * a));
@@ -356,7 +358,8 @@ __global__ void __launch_bounds__(256, 3) k_u1_heads_update(
         tp = fma(wt[k], zk, tp);
         qp = fma(wq[k], zk, qp);
       }
-      const T sv = a_s * tanh_<T>(sp), tv = nwt * tp, qv = a_q * tanh_<T>(qp);
+      // s enters the log-Jacobian linearly and is summed over the lattice: accurate tanh; q only scales v / F
+      const T sv = a_s * tanh_acc<T>(sp), tv = nwt * tp, qv = a_q * tanh_<T>(qp);
       const size_t at = (size_t)(b0 + c) * xdim + j;
       T lj = T(0);
       if (ok) {
@@ -370,16 +373,20 @@ __global__ void __launch_bounds__(256, 3) k_u1_heads_update(
         } else {                                         // k_u1_xupdate
           const T xi = av[g], vi = bv[g];
           const T si = (sg * eps) * sv, qi = eps * qv;
-          const T es = FNum<T>::exp_(si), eq = FNum<T>::exp_(qi);
+          // everything the log-Jacobian depends on (e^{s}, sin, cos) uses the accurate functions: those
+          // terms are summed over the lattice and a biased 1e-7 per element becomes 1e-2 per chain
+          // (profiles/check_u1_fused_accuracy.py); e^{q} only scales v and may come from the SFU
+          const T es = Num<T>::exp_(si), eq = FNum<T>::exp_(qi);
           const T tr = eps * (vi * eq + tv);
           T xn, l1;
           if (use_ncp) {
-            T sh, ch;
-            FNum<T>::sincos_(xi / T(2), sh, ch);         // tan, cos, sin of the half angle from one sincos
-            const T x1 = T(2) * Num<T>::atan_(FNum<T>::div_(sh, ch) * es);
+            const T hx = xi / T(2);
+            const T sh = Num<T>::sin_(hx), ch = Num<T>::cos_(hx);   // tan = sin / cos: one tanf saved
+            const T x1 = T(2) * Num<T>::atan_((sh / ch) * es);
             xn = (sign > 0) ? (x1 + tr) : (x1 - es * tr);
             const T st = es * sh;
-            l1 = FNum<T>::log_(FNum<T>::div_(es, ch * ch + st * st));
+            l1 = si - Num<T>::log_(ch * ch + st * st);   // = log(es / (..)) without the exp/log round trip; accurate log:
+                                                         // these terms are SUMMED over the lattice, a biased 3e-7 shows
           } else {
             xn = (sign > 0) ? (xi * es + tr) : (es * (xi - tr));
             l1 = si;

@@ -132,3 +132,51 @@ def test_u1_reversibility_full_size(ops):
     assert float((x2 - x).abs().max()) < 5e-4     # fp32 round-off over 20 steps of O(10) angles
     assert float((v2 + v).abs().max()) < 5e-4
     assert torch.isfinite(en).all()
+
+
+def test_fused_u1_sweep_is_as_accurate_as_the_unfused_one():
+    """fp32 L2HMC sweep with the fused input-layer / heads kernels vs the unfused fp32 path, both measured
+    against a float64 evaluation of the same nets: the log-Jacobian is a sum over the lattice, so a biased
+    1e-7 per element (SFU intrinsics in the wrong place) shows up as 1e-2 per chain -- it must not."""
+    from l2hmc_b200.configs import DynamicsConfig, NetworkConfig, get_input_spec
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    old = torch.get_default_dtype()
+    nb, shape, nlf = 16, [32, 32], 4
+
+    def build(dtype):
+        torch.set_default_dtype(dtype)
+        torch.manual_seed(1)
+        np.random.seed(1)
+        cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=nlf, eps=0.1, use_ncp=True,
+                             verbose=False, use_split_xnets=True, merge_directions=True, use_separate_networks=True)
+        fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                             network_config=NetworkConfig(units=[16, 16], activation_fn='leaky_relu', dropout_prob=0.2,
+                                                          use_batch_norm=True), conv_config=None, net_weights=None)
+        lat = LatticeU1(nb, shape)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+        dyn.eval()
+        return dyn, lat
+    try:
+        d32, lat32 = build(torch.float32)
+        d64, _ = build(torch.float64)
+        d64.load_state_dict(d32.state_dict())
+        d64.masks = [m.clone() for m in d32.masks]
+        torch.manual_seed(5)
+        x = lat32.random().float()
+        v = torch.randn(nb, 2 * 32 * 32, device=x.device, dtype=torch.float32)
+        beta = torch.tensor(4.0)
+        err = {}
+        with torch.no_grad():
+            ref, mref = d64.transition_kernel_fb(State(x.double(), v.double(), beta))
+            for mode in ('never', 'auto'):
+                d32.fused_u1_heads = mode
+                st, met = d32.transition_kernel_fb(State(x, v, beta))
+                err[mode] = (float((met['sumlogdet'].double() - mref['sumlogdet']).abs().max()),
+                             float((met['acc'].double() - mref['acc']).abs().max()),
+                             float((st.v.double().reshape(nb, -1) - ref.v.reshape(nb, -1)).abs().max()))
+        for k in range(3):
+            assert err['auto'][k] <= 3.0 * err['never'][k] + 1e-6, (k, err)
+    finally:
+        torch.set_default_dtype(old)
