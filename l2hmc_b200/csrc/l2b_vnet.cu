@@ -227,7 +227,7 @@ __device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t 
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const bool ok = FULL || (col_ok && chain0 + c0 + c < a.nb);
-      const float s = as * tanh_fast(__uint_as_float(rs[c]) + bs);
+      const float s = as * tanhf(__uint_as_float(rs[c]) + bs);   // summed into logdet over xdim elements: accurate tanh
       const float t = at * (__uint_as_float(rt[c]) + bt);
       const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
       const float logjac = hs * s;                      // sign * eps * s / 2
@@ -302,7 +302,7 @@ __device__ __forceinline__ void epilogue_full(const HeadsArgs& a, Smem& sm, uint
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int c = 0; c < C4; ++c) {
-      const float s = as * tanh_fast(__uint_as_float(rs[c]) + bs);
+      const float s = as * tanhf(__uint_as_float(rs[c]) + bs);   // summed into logdet over xdim elements: accurate tanh
       const float t = at * (__uint_as_float(rt[c]) + bt);
       const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
       const float logjac = hs * s;
