@@ -36,7 +36,8 @@ class Trainer:
         self.loss_fn = LatticeLoss(self.lattice, loss_config or LossConfig())
         params = [p for p in dynamics.parameters() if p.requires_grad]
         self.cuda_graphs = bool(cuda_graphs)
-        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=self.cuda_graphs)
+        # fused: one multi-tensor kernel over the 180 M vnet parameters instead of the foreach chain
+        self.optimizer = torch.optim.Adam(params, lr=lr, capturable=self.cuda_graphs, fused=True)
         self.clip_val = clip_val
         self.autocast_dtype = autocast_dtype
         self.grad_bucket_dtype = grad_bucket_dtype
