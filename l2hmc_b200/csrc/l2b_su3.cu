@@ -221,6 +221,67 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
 }
 
 
+// "early momentum" variants of the kick kernels.  In k_force the 9 momentum loads are issued right before
+// the kick, after ~2000 cycles of staple arithmetic, and their DRAM latency is fully exposed: 25 % of the
+// kernel's stall samples (profiles/r1d_force_stall_profile.md).  Here they are issued HOOK_AT directions
+// earlier into 18 more live doubles (the register allocator decides what to spill under the same cap).
+// Same arithmetic in the same order: results are bit-identical to k_force.
+template <int TS, int MINB, bool DRIFT, int HOOK_AT>
+__global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__ U, C* __restrict__ P, Lat lat,
+                                                           double coef, double* __restrict__ part,
+                                                           C* __restrict__ Uout, double eps_drift) {
+  __shared__ double red[TS * 4 / 32];
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  const int tid = threadIdx.y * TS + threadIdx.x;
+  double retr = 0.0, p2 = 0.0;
+  if (site < lat.V) {
+    Mat3<T> g, f;
+    const int ahead = site + PF_AHEAD_SITES;
+    if (ahead < lat.V) {
+      soa_prefetch<2>(soa_plane(U, lat, b, mu), lat.V, ahead);
+      soa_prefetch<2>(soa_plane((const C*)P, lat, b, mu), lat.V, ahead);
+    }
+    C* pp = soa_plane(P, lat, b, mu) + site;
+    const size_t V = lat.V;
+    C pv[9];
+    link_times_staples_hook<T, C, HOOK_AT>(g, U, lat, b, mu, site, [&]() {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) pv[e] = __ldcs(pp + e * V);
+    });
+    retr = re_trace(g);
+    project_tah(f, g);
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      C v = pv[e];
+      v.x = fma(-coef, f.re[e], v.x);
+      v.y = fma(-coef, f.im[e], v.y);
+      p2 = fma(v.x, v.x, p2);
+      p2 = fma(v.y, v.y, p2);
+      __stcs(pp + e * V, v);
+      if (DRIFT) { f.re[e] = eps_drift * v.x; f.im[e] = eps_drift * v.y; }
+    }
+    p2 -= 8.0;
+    if (DRIFT) {
+      Mat3<T> ex, w, un;
+      soa_load(w, soa_plane(U, lat, b, mu), lat.V, site);
+      mat_exp(ex, f);
+      mat_mul<false, false, false>(un, ex, w);
+      soa_store(soa_plane(Uout, lat, b, mu), lat.V, site, un);
+    }
+  }
+  if (part != nullptr) {
+    retr = block_sum<TS * 4>(retr, red, tid);
+    p2 = block_sum<TS * 4>(p2, red, tid);
+    if (tid == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = retr;
+      o[1] = p2;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // k_force_async: same arithmetic as k_force, but the 18 neighbour matrices of a
 // link travel global -> shared memory with cp.async (LDGSTS) through a per-thread
@@ -1035,9 +1096,14 @@ const ForceVariant kForceVariants[] = {
     L2B_FVB(64, 2, 0, 2),   // 19: brick (2,2,2,8), 256 threads, <= 128 registers
     L2B_FVB(32, 3, 2, 8),   // 20: brick (1,2,2,8) + L2 look-ahead
     L2B_FVB(64, 2, 2, 10),  // 21: brick (2,2,2,8) + L2 look-ahead
+    // early-momentum variants of variant 8 (kick kernels only; no-kick falls back to variant 8's)
+    {32, k_force_ep<32, 3, false, 3>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3>, -1},   // 22: before the last direction
+    {32, k_force_ep<32, 3, false, 2>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2>, -1},   // 23: before the 2nd direction
+    {32, k_force_ep<32, 3, false, 0>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 0>, -1},   // 24: before the staples
+    {32, k_force_ep<32, 2, false, 0>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 0>, -1},   // 25: as 24, uncapped registers (8 warps / SM)
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
-int g_force_variant = 8;
+int g_force_variant = 22;   // r1d: momentum loads issued before the last staple direction (-10 % on the 16^4 trajectory)
 int g_fuse_drift = 1;
 int g_force_carveout = -1;   // -1: driver default; 0..100: preferred shared-memory carve-out in percent
 

@@ -186,6 +186,58 @@ L2B_HD void link_times_staples(Mat3<T>& g, const C* U, const Lat& l, int b, int 
   }
 }
 
+// Same staple sum and link product as link_times_staples (identical operation order, so identical
+// bits), with a caller-supplied hook run right before staple direction HOOK_AT (1..3; 0 = before
+// the first).  The force kernel's "early momentum" variants use it to put the 9 momentum loads in
+// flight while the remaining staples are multiplied.
+template <typename T, typename C, int HOOK_AT, typename Hook>
+L2B_HD void link_times_staples_hook(Mat3<T>& g, const C* U, const Lat& l, int b, int mu, int site, Hook&& hook) {
+  const int V = l.V;
+  int r = site;
+  const int c3 = r % l.L[3]; r /= l.L[3];
+  const int c2 = r % l.L[2]; r /= l.L[2];
+  const int c1 = r % l.L[1]; r /= l.L[1];
+  const int c0 = r;
+  const int f0 = (c0 == l.L[0] - 1) ? -(l.L[0] - 1) * l.stride[0] : l.stride[0];
+  const int f1 = (c1 == l.L[1] - 1) ? -(l.L[1] - 1) * l.stride[1] : l.stride[1];
+  const int f2 = (c2 == l.L[2] - 1) ? -(l.L[2] - 1) * l.stride[2] : l.stride[2];
+  const int f3 = (c3 == l.L[3] - 1) ? -(l.L[3] - 1) : 1;
+  const int b0 = (c0 == 0) ? (l.L[0] - 1) * l.stride[0] : -l.stride[0];
+  const int b1 = (c1 == 0) ? (l.L[1] - 1) * l.stride[1] : -l.stride[1];
+  const int b2 = (c2 == 0) ? (l.L[2] - 1) * l.stride[2] : -l.stride[2];
+  const int b3 = (c3 == 0) ? (l.L[3] - 1) : -1;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int n_pmu = site + sel4(f0, f1, f2, f3, mu);
+  Mat3<T> a, x, y, m;
+  mat_zero(a);
+  if (HOOK_AT == 0) hook();
+  L2B_UNROLL
+  for (int k = 1; k < 4; ++k) {
+    if (k == HOOK_AT) hook();
+    const int nu = (mu + k) & 3;
+    const C* pnu = chain + (size_t)nu * plane_sz;
+    const int fnu = sel4(f0, f1, f2, f3, nu);
+    const int bnu = sel4(b0, b1, b2, b3, nu);
+    const int n_pnu = site + fnu;
+    const int n_mnu = site + bnu;
+    const int n_pmu_mnu = n_pmu + bnu;
+    soa_load(x, pnu, V, n_pmu);
+    soa_load(y, pmu, V, n_pnu);
+    mat_mul<false, true, false>(m, x, y);
+    soa_load(x, pnu, V, site);
+    mat_mul<false, true, true>(a, m, x);
+    soa_load(x, pnu, V, n_pmu_mnu);
+    soa_load(y, pmu, V, n_mnu);
+    mat_mul<true, true, false>(m, x, y);
+    soa_load(x, pnu, V, n_mnu);
+    mat_mul<false, false, true>(a, m, x);
+  }
+  soa_load(x, pmu, V, site);
+  mat_mul<false, false, false>(g, x, a);
+}
+
 // ---------------------------------------------------------------------------
 // Plaquette traces at one site, the reference's six planes in ITS order
 // (u = 1..3, v < u):  tr[ U_u(n) U_v(n+u) (U_v(n) U_u(n+v))^+ ]
