@@ -1101,6 +1101,9 @@ const ForceVariant kForceVariants[] = {
     {32, k_force_ep<32, 3, false, 2>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2>, -1},   // 23: before the 2nd direction
     {32, k_force_ep<32, 3, false, 0>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 0>, -1},   // 24: before the staples
     {32, k_force_ep<32, 2, false, 0>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 0>, -1},   // 25: as 24, uncapped registers (8 warps / SM)
+    {32, k_force_ep<32, 4, false, 3>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3>, -1},   // 26: as 22, <= 128 registers (16 warps / SM)
+    {32, k_force_ep<32, 2, false, 3>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 3>, -1},   // 27: as 22, uncapped registers (8 warps / SM)
+    {32, k_force_ep<32, 2, false, 2>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 2>, -1},   // 28: as 23, uncapped registers
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
 int g_force_variant = 22;   // r1d: momentum loads issued before the last staple direction (-10 % on the 16^4 trajectory)
