@@ -101,6 +101,28 @@ void emu_force(const C* x, double beta, C* force, double* retr, int nb, const in
     if (retr) retr[b] = acc;
   }
 }
+// the force through link_times_staples_hook (what the default kick kernels k_force_ep call): must be
+// bit-identical to link_times_staples; `hooks[b]` counts the hook invocations (one per link)
+void emu_force_hook(const C* x, double beta, C* force, long long* hooks, int hook_at, int nb, const int* dims) {
+  const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  std::vector<C> U;
+  to_soa(U, x, nb, l);
+  for (int b = 0; b < nb; ++b) {
+    long long n = 0;
+    for (int mu = 0; mu < 4; ++mu)
+      for (int s = 0; s < l.V; ++s) {
+        Mat3<T> g, f;
+        auto hook = [&]() { ++n; };
+        if (hook_at == 0) link_times_staples_hook<T, C, 0>(g, U.data(), l, b, mu, s, hook);
+        else if (hook_at == 2) link_times_staples_hook<T, C, 2>(g, U.data(), l, b, mu, s, hook);
+        else link_times_staples_hook<T, C, 3>(g, U.data(), l, b, mu, s, hook);
+        project_tah(f, g);
+        for (int e = 0; e < 9; ++e) { f.re[e] *= beta / 3.0; f.im[e] *= beta / 3.0; }
+        aos_put(force, ((size_t)b * 4 + mu) * l.V + s, f);
+      }
+    hooks[b] = n;
+  }
+}
 // wloops[6, nb, V] complex
 void emu_wloops(const C* x, C* wl, int nb, const int* dims) {
   const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);

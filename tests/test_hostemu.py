@@ -89,6 +89,13 @@ def test_stencil_bodies(emu, g):
     wl = np.empty((6, nb) + x.shape[2:6], dtype=np.complex128)
     emu.emu_wloops(ptr(x), ptr(wl), ctypes.c_int(nb), dims)
     assert maxdiff(wl, g['wloops']) < 1e-13
+    # the hooked variant the default kick kernels use: bit-identical, hook runs exactly once per link
+    for hook_at in (0, 2, 3):
+        fh = np.empty_like(x)
+        hooks = np.zeros(nb, dtype=np.int64)
+        emu.emu_force_hook(ptr(x), ctypes.c_double(beta), ptr(fh), ptr(hooks), ctypes.c_int(hook_at), ctypes.c_int(nb),
+                           dims)
+        assert np.array_equal(fh, f) and np.all(hooks == x[0].size // 9)
 
 
 @pytest.mark.parametrize('key,xk,vk', [('hmc1', 'x', 'v'), ('hmc4', 'x', 'v'), ('hmcw', 'xw', 'vw')])
