@@ -68,3 +68,42 @@ def test_cpu_tensors_are_rejected_not_silently_computed(lib):
         ops.su3_plaq_sums(x)
     with pytest.raises(lib.L2BError, match='no CPU fallback'):
         ops.u1_force(torch.zeros(1, 2, 4, 4), 1.0)
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/l2b.h must compile as C99 without any C++ / CUDA / torch type"""
+    import subprocess
+    src = tmp_path / 'hc.c'
+    src.write_text('#include "include/l2b.h"\nint main(void) { return l2b_version() ? 0 : 1; }\n')
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-fsyntax-only', '-I', str(ROOT), str(src)])
+
+
+def test_new_entry_points_validate_arguments_without_gpu(lib):
+    p = ctypes.c_void_p(256)
+    d = lib.dims4([4, 4, 4, 4])
+    # tcgen05 heads kernel: hidden size outside the supported range, bad sign, missing workspace for logdet
+    args = [p, p, p, p, p, p, p, 1.0, p, p, 0.1, None, 1, p, p, None, 4, 1152]
+    with pytest.raises(lib.L2BError, match='hidden'):
+        lib.call('l2b_su3_heads_vupdate', *args, 260, p, 1 << 20, None)
+    with pytest.raises(lib.L2BError, match='sign'):
+        lib.call('l2b_su3_heads_vupdate', *(args[:12] + [0] + args[13:]), 64, p, 1 << 20, None)
+    with pytest.raises(lib.L2BError, match='workspace'):
+        lib.call('l2b_su3_heads_vupdate', *args, 64, None, 0, None)
+    assert lib._lib.l2b_vnet_heads_packed_bytes(1152, 64) == 9 * 3 * 64 * 128 * 2
+    assert lib._lib.l2b_vnet_heads_packed_bytes(1000, 40) == 8 * 3 * 64 * 128 * 2      # ragged tile, K padded to 64
+    # U(1) fused kernels
+    with pytest.raises(lib.L2BError, match='hidden <= 32'):
+        lib.call('l2b_u1_heads_update', 0, p, 48, p, p, p, p, p, p, p, p, 1.0, 1.0, 1.0, p, p, None, 0.1, None, 1, 1, p, p, 4,
+                 128, lib.L2B_F32, p, 1 << 20, None)
+    with pytest.raises(lib.L2BError, match='mask'):
+        lib.call('l2b_u1_heads_update', 1, p, 16, p, p, p, p, p, p, p, p, 1.0, 1.0, 1.0, p, p, None, 0.1, None, 1, 1, p, p, 4,
+                 128, lib.L2B_F32, p, 1 << 20, None)
+    with pytest.raises(lib.L2BError, match='units'):
+        lib.call('l2b_u1_input_layer', 0, p, p, None, p, p, p, p, 24, p, 4, 128, lib.L2B_F32, p, 1 << 20, None)
+    # adjoints / planar variants
+    with pytest.raises(lib.L2BError, match='vec_dtype'):
+        lib.call('l2b_su3_project_vec', p, p, 7, 16, lib.L2B_F64, None)
+    with pytest.raises(lib.L2BError, match='null'):
+        lib.call('l2b_su3_project_bwd', p, None, None, lib.L2B_F64, p, 16, lib.L2B_F64, None)
+    with pytest.raises(lib.L2BError, match='null'):
+        lib.call('l2b_su3_update_gauge_planar', p, None, 1.0, None, None, 0, p, 2, d, lib.L2B_F64, None)
