@@ -202,6 +202,17 @@ int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, voi
                                     double eps_kick, double eps_drift, double* sums_or_null, int nb,
                                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/* adjoint of l2b_su3_heads_vupdate, element-wise part (the three small GEMMs of the Linear backward stay library
+ * calls): from (s, t, q) as dumped by the forward (stq f32 [3, nb, xdim]) and the cotangents gv_out, glogdet it
+ * writes gv, gforce (may be NULL), geps[nb], the cotangents of the heads' PRE-activations gpre [3, nb, xdim] in
+ * gpre_dtype (L2B_F32 / L2B_BF16: the dtype of the dz / dW GEMMs) and gss = gs*s, gqq = gq*q (f32 [nb, xdim])
+ * whose sums over the chains are the ScaledTanh.coeff gradients.  ws: nb * ceil(xdim/256) doubles. */
+int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq, const float* scale_s,
+                              const float* scale_q, float scale_t, double eps, const double* eps_dev, int sign,
+                              const void* gv_out, const double* glogdet, void* gv, void* gforce_or_null, void* gpre,
+                              int gpre_dtype, float* gss, float* gqq, double* geps, int nb, int xdim, void* ws,
+                              size_t ws_bytes, void* stream);
+
 /* L2HMC sweep with the state kept in the planar layout (no conversion around the stencil kernels):
  * force without kick, group_to_vec (vec8 in [b][mu][site][8] order, as the AoS version) and the masked
  * link update; the mask is the [xdim] element mask permuted to [4][9][V].  The heads kernel

@@ -299,9 +299,10 @@ class SU3HeadsVUpdate(torch.autograd.Function):
     """(v', logdet) = vupdate(v, F, heads(z); eps, sign) with the three head GEMMs on the
     tensor cores and s, t, q kept on chip (l2b_su3_heads_vupdate, csrc/l2b_vnet.cu).
     When a gradient is needed the kernel also writes (s, t, q) once (fp32) for the backward pass:
-    the hand-written v-update adjoint gives their cotangents, the tanh / scale derivatives are a few
-    element-wise ops, and the three small GEMMs of the Linear backward run on cuBLAS (dz now, dW either
-    now or, under DEFER_HEAD_GRADS, once per backward pass for all the v-updates sharing the net)."""
+    ONE element-wise adjoint kernel (l2b_su3_heads_vupdate_bwd) then yields gv, gF, d/d eps and the
+    cotangents of the heads' pre-activations in the GEMM dtype, and the three small GEMMs of the Linear
+    backward run on cuBLAS (dz now, dW either now or, under DEFER_HEAD_GRADS, once per backward pass for
+    all the v-updates sharing the net)."""
 
     @staticmethod
     def forward(ctx, z, v, force, eps, sign, eps_value, net, *head_params):
@@ -309,8 +310,9 @@ class SU3HeadsVUpdate(torch.autograd.Function):
         ctx.eps_value = eps.detach() if eps_value is None else eps_value   # 0-dim device tensor: read by the kernel
         ctx.autocast = (torch.is_autocast_enabled('cuda'), torch.get_autocast_dtype('cuda'))
         need = any(ctx.needs_input_grad)
-        res = ops.su3_heads_vupdate(z.detach(), net.heads_pack(), v.detach(), force.detach(), ctx.eps_value, sign,
-                                    want_stq=need)
+        pack = net.heads_pack()
+        res = ops.su3_heads_vupdate(z.detach(), pack, v.detach(), force.detach(), ctx.eps_value, sign, want_stq=need)
+        ctx.pack = pack
         ctx.save_for_backward(z, v, force, eps, res[2] if need else None, *head_params)
         return res[0], res[1]
 
@@ -319,20 +321,16 @@ class SU3HeadsVUpdate(torch.autograd.Function):
         z, v, force, eps, stq = ctx.saved_tensors[:5]
         ws, bs, cs, wt, bt, wq, bq, cq = ctx.saved_tensors[5:]
         net = ctx.net
-        nb, xdim = stq.shape[1], stq.shape[2]
-        s, t, q = stq[0], stq[1], stq[2]
-        gv, gf, gs, gt, gq, geps = ops.su3_vupdate_bwd(v.detach(), force.detach(), s, t, q, ctx.eps_value, ctx.sign,
-                                                       gout, glogdet)
-        gs, gt, gq = (g.reshape(nb, xdim).to(torch.float32) for g in (gs, gt, gq))
-        # s = a_s tanh(pre_s), a_s = nw.s e^{c_s}:  ds/dpre = a_s (1 - tanh^2),  ds/dc_s = s   (same for q)
-        a_s = float(net.nw.s) * cs.detach().to(torch.float32).exp()
-        a_q = float(net.nw.q) * cq.detach().to(torch.float32).exp()
-        th_s = torch.where(a_s != 0, s / a_s, torch.zeros_like(s))
-        th_q = torch.where(a_q != 0, q / a_q, torch.zeros_like(q))
         cdt = ctx.autocast[1] if ctx.autocast[0] else ws.dtype        # the dtype the reference's Linear backward runs in
-        gp = ((gs * a_s * (1.0 - th_s * th_s)).to(cdt), (gt * float(net.nw.t)).to(cdt),
-              (gq * a_q * (1.0 - th_q * th_q)).to(cdt))
-        gcs, gcq = (gs * s).sum(0, keepdim=True), (gq * q).sum(0, keepdim=True)
+        if cdt not in (torch.float32, torch.bfloat16):
+            cdt = torch.float32
+        # one element-wise kernel: gv, gF, d/d eps, the pre-activation cotangents of the three heads in the
+        # GEMM dtype, and gs*s / gq*q for the ScaledTanh.coeff gradients
+        gv, gf, gpre, gss, gqq, geps = ops.su3_heads_vupdate_bwd(v.detach(), force.detach(), stq, ctx.pack,
+                                                                 ctx.eps_value, ctx.sign, gout, glogdet, cdt,
+                                                                 want_gforce=ctx.needs_input_grad[2])
+        gp = (gpre[0], gpre[1], gpre[2])
+        gcs, gcq = gss.sum(0, keepdim=True), gqq.sum(0, keepdim=True)
         wc = net.head_weights_as(cdt)
         gz = (gp[0] @ wc[0] + gp[1] @ wc[1] + gp[2] @ wc[2]).to(z.dtype)
         zc = z.detach().to(cdt)
@@ -349,7 +347,8 @@ class SU3HeadsVUpdate(torch.autograd.Function):
                   for g, b_, nd in zip(gp, (bs, bt, bq), (need[1], need[4], need[6]))]
             gparams = (gw[0], gb[0], gcs.to(cs.dtype) if need[2] else None, gw[1], gb[1], gw[2], gb[2],
                        gcq.to(cq.dtype) if need[7] else None)
-        return (gz, gv.reshape(v.shape), gf.reshape(force.shape), _eps_grad(geps, eps), None, None, None, *gparams)
+        return (gz, gv.reshape(v.shape), None if gf is None else gf.reshape(force.shape), _eps_grad(geps, eps), None,
+                None, None, *gparams)
 
 
 class SU3UpdateGauge(torch.autograd.Function):

@@ -434,6 +434,74 @@ __global__ void __launch_bounds__(NTH, 2) k_heads_vupdate(const HeadsArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Adjoint of the fused heads + momentum update, element-wise part.  Given (s, t, q) as the forward kernel
+// dumped them and the cotangents of (v', logdet), one pass produces gv, gF, the per-chain d/d eps partials,
+// the cotangents of the three heads' PRE-activations (ready to be the A operand of the dz / dW GEMMs, in
+// the GEMM's dtype) and the products gs*s, gq*q whose column sums are the ScaledTanh.coeff gradients:
+//   s = a_s tanh(pre_s):  d/dpre_s = gs a_s (1 - (s/a_s)^2),  d/dc_s = gs s      (a_s = nw.s e^{c_s}; same for q)
+//   t = nw.t pre_t:       d/dpre_t = gt nw.t
+// Replaces k_vupdate_bwd + three fp32->fp64 conversions + ~20 element-wise torch kernels per v-update.
+// ---------------------------------------------------------------------------
+template <typename GP> __device__ __forceinline__ GP to_gp(float x);
+template <> __device__ __forceinline__ float to_gp<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 to_gp<__nv_bfloat16>(float x) { return __float2bfloat16(x); }
+
+template <typename GP>
+__global__ void __launch_bounds__(256) k_heads_vupdate_bwd(const double2* __restrict__ v, const double2* __restrict__ f,
+                                                           const float* __restrict__ stq,
+                                                           const float* __restrict__ scale_s,
+                                                           const float* __restrict__ scale_q, float scale_t,
+                                                           double eps_in, const double* __restrict__ eps_dev, int sign,
+                                                           const double2* __restrict__ gout,
+                                                           const double* __restrict__ glogdet,
+                                                           double2* __restrict__ gv, double2* __restrict__ gf,
+                                                           GP* __restrict__ gpre, float* __restrict__ gss,
+                                                           float* __restrict__ gqq, double* __restrict__ part, int nb,
+                                                           int xdim) {
+  __shared__ double red[8];
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  double ge = 0.0;
+  if (j < xdim) {
+    const size_t at = (size_t)b * xdim + j, plane = (size_t)nb * xdim;
+    const double sv = (double)stq[at], tv = (double)stq[plane + at], qv = (double)stq[2 * plane + at];
+    const double2 V = v[at], F = f[at], G = gout[at];
+    const double gl = glogdet ? glogdet[b] : 0.0;
+    const double sg = (double)sign, he = 0.5 * eps;
+    const double lj = sg * eps * sv / 2.0;
+    const double es = exp(lj), eq = exp(eps * qv);
+    const double fr = fma(F.x, eq, tv), fi = F.y * eq;
+    double g_es, g_fr, g_fi;
+    if (sign > 0) {
+      g_es = G.x * V.x + G.y * V.y;
+      g_fr = -he * G.x; g_fi = -he * G.y;
+      ge += -0.5 * (fr * G.x + fi * G.y);
+    } else {
+      g_es = G.x * (V.x + he * fr) + G.y * (V.y + he * fi);
+      g_fr = es * he * G.x; g_fi = es * he * G.y;
+      ge += 0.5 * es * (fr * G.x + fi * G.y);
+    }
+    gv[at] = make_double2(es * G.x, es * G.y);
+    if (gf != nullptr) gf[at] = make_double2(g_fr * eq, g_fi * eq);
+    const double g_lj = g_es * es + gl;
+    ge += g_lj * sg * sv / 2.0;
+    const double g_eq = g_fr * F.x + g_fi * F.y;
+    ge += g_eq * eq * qv;
+    const double gs = g_lj * sg * eps / 2.0, gt = g_fr, gq = g_eq * eq * eps;
+    const double as = (double)scale_s[j], aq = (double)scale_q[j];
+    const double ths = as != 0.0 ? sv / as : 0.0, thq = aq != 0.0 ? qv / aq : 0.0;
+    gpre[at] = to_gp<GP>((float)(gs * as * (1.0 - ths * ths)));
+    gpre[plane + at] = to_gp<GP>((float)(gt * (double)scale_t));
+    gpre[2 * plane + at] = to_gp<GP>((float)(gq * aq * (1.0 - thq * thq)));
+    gss[at] = (float)(gs * sv);
+    gqq[at] = (float)(gq * qv);
+  }
+  ge = block_sum<256>(ge, red, threadIdx.x);
+  if (threadIdx.x == 0) part[(size_t)b * gridDim.x + blockIdx.x] = ge;
+}
+
 // fixed-order sum of the per-tile partials: out[b] = sum_tile part[b][tile]
 __global__ void __launch_bounds__(256) k_sum_rows(const double* __restrict__ part, int n, double* __restrict__ out) {
   __shared__ double red[8];
@@ -526,6 +594,35 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
     k_sum_rows<<<nb, 256, 0, st>>>(a.part, a.ntiles, logdet);
     L2B_LAUNCHED("k_sum_rows");
   }
+  return L2B_OK;
+}
+
+int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq, const float* scale_s,
+                              const float* scale_q, float scale_t, double eps, const double* eps_dev, int sign,
+                              const void* gv_out, const double* glogdet, void* gv, void* gforce_or_null, void* gpre,
+                              int gpre_dtype, float* gss, float* gqq, double* geps, int nb, int xdim, void* ws,
+                              size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(v && force && stq && scale_s && scale_q && gv_out && gv && gpre && gss && gqq && geps, L2B_ERR_INVALID,
+              "null pointer");
+  L2B_REQUIRE(nb > 0 && xdim > 0 && nb <= 65535, L2B_ERR_INVALID, "nb must be in [1, 65535], xdim positive");
+  L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  const int nblk = (xdim + 255) / 256;
+  L2B_REQUIRE(ws && ws_bytes >= (size_t)nb * nblk * sizeof(double), L2B_ERR_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(nblk, nb);
+  double* part = (double*)ws;
+#define L2B_HVB(GP)                                                                                               \
+  k_heads_vupdate_bwd<GP><<<grid, 256, 0, st>>>((const double2*)v, (const double2*)force, stq, scale_s, scale_q,    \
+                                                scale_t, eps, eps_dev, sign, (const double2*)gv_out, glogdet,      \
+                                                (double2*)gv, (double2*)gforce_or_null, (GP*)gpre, gss, gqq, part, \
+                                                nb, xdim)
+  if (gpre_dtype == L2B_F32) L2B_HVB(float);
+  else if (gpre_dtype == L2B_BF16) L2B_HVB(__nv_bfloat16);
+  else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "gpre_dtype must be L2B_F32 or L2B_BF16");
+#undef L2B_HVB
+  L2B_LAUNCHED("k_heads_vupdate_bwd");
+  k_sum_rows<<<nb, 256, 0, st>>>(part, nblk, geps);
+  L2B_LAUNCHED("k_sum_rows");
   return L2B_OK;
 }
 

@@ -765,3 +765,31 @@ def u1_input_layer(mode: int, x: Tensor, v: Tensor, w_x: Tensor, b_x: Tensor, w_
     call('l2b_u1_input_layer', int(mode), _ptr(x2), _ptr(v2), _ptr(mask), _ptr(w_x), _ptr(b_x), _ptr(w_v), _ptr(b_v),
          units, _ptr(pre), nb, xdim, _dt(x2), _ptr(ws), nws, _stream())
     return pre
+
+
+def su3_heads_vupdate_bwd(v: Tensor, force: Tensor, stq: Tensor, pack: HeadsPack, eps, sign: int, gv_out: Tensor,
+                          glogdet: Optional[Tensor], gpre_dtype: torch.dtype, want_gforce: bool = True):
+    """element-wise adjoint of su3_heads_vupdate -> (gv, gforce, gpre[3, nb, xdim], gss, gqq, geps[nb])"""
+    _need_cuda(v, force, stq, gv_out)
+    nb, xdim = int(stq.shape[1]), int(stq.shape[2])
+    v2, f2 = v.contiguous(), force.contiguous()
+    go = gv_out.to(torch.complex128).contiguous()
+    if v2.numel() != nb * xdim or f2.numel() != nb * xdim or go.numel() != nb * xdim:
+        raise L2BError('v, force and gv_out must have nb * xdim complex entries')
+    stq = stq.to(torch.float32).contiguous()
+    gl = None if glogdet is None else glogdet.to(torch.float64).contiguous()
+    gv = torch.empty_like(v2)
+    gf = torch.empty_like(v2) if want_gforce else None
+    gpre = torch.empty((3, nb, xdim), dtype=gpre_dtype, device=v.device)
+    gss = torch.empty((nb, xdim), dtype=torch.float32, device=v.device)
+    gqq = torch.empty_like(gss)
+    geps = torch.empty(nb, dtype=torch.float64, device=v.device)
+    nws = nb * ((xdim + 255) // 256) * 8
+    ws = _workspace(nws, v.device)
+    if gpre_dtype not in (torch.float32, torch.bfloat16):
+        raise L2BError(f'gpre dtype must be float32 or bfloat16 (got {gpre_dtype})')
+    ev, ep, _keep = _eps_args(eps, torch.float64)
+    call('l2b_su3_heads_vupdate_bwd', _ptr(v2), _ptr(f2), _ptr(stq), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t,
+         ev, ep, int(sign), _ptr(go), _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gpre), _net_dt(gpre_dtype), _ptr(gss), _ptr(gqq),
+         _ptr(geps), nb, xdim, _ptr(ws), nws, _stream())
+    return gv, gf, gpre, gss, gqq, geps
