@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
 // kernel's stall samples (profiles/r1d_force_stall_profile.md).  Here they are issued HOOK_AT directions
 // earlier into 18 more live doubles (the register allocator decides what to spill under the same cap).
 // Same arithmetic in the same order: results are bit-identical to k_force.
-template <int TS, int MINB, bool DRIFT, int HOOK_AT>
+template <int TS, int MINB, bool DRIFT, int HOOK_AT, bool LOWREG = false>
 __global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__ U, C* __restrict__ P, Lat lat,
                                                            double coef, double* __restrict__ part,
                                                            C* __restrict__ Uout, double eps_drift) {
@@ -246,10 +246,12 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__
     C* pp = soa_plane(P, lat, b, mu) + site;
     const size_t V = lat.V;
     C pv[9];
-    link_times_staples_hook<T, C, HOOK_AT>(g, U, lat, b, mu, site, [&]() {
+    auto load_p = [&]() {
 #pragma unroll
       for (int e = 0; e < 9; ++e) pv[e] = __ldcs(pp + e * V);
-    });
+    };
+    if (LOWREG) link_times_staples_lowreg<T, C, HOOK_AT>(g, U, lat, b, mu, site, load_p);   // row-streamed operands
+    else link_times_staples_hook<T, C, HOOK_AT>(g, U, lat, b, mu, site, load_p);
     retr = re_trace(g);
     project_tah(f, g);
 #pragma unroll
@@ -1104,6 +1106,10 @@ const ForceVariant kForceVariants[] = {
     {32, k_force_ep<32, 4, false, 3>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3>, -1},   // 26: as 22, <= 128 registers (16 warps / SM)
     {32, k_force_ep<32, 2, false, 3>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 3>, -1},   // 27: as 22, uncapped registers (8 warps / SM)
     {32, k_force_ep<32, 2, false, 2>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 2>, -1},   // 28: as 23, uncapped registers
+    // row-streaming (low-register) staple products, bit-identical (tests/hostemu)
+    {32, k_force_ep<32, 3, false, 3, true>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3, true>, -1},   // 29: hook before the last direction
+    {32, k_force_ep<32, 3, false, 2, true>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2, true>, -1},   // 30: before the 2nd direction
+    {32, k_force_ep<32, 4, false, 3, true>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3, true>, -1},   // 31: as 29, <= 128 registers
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
 int g_force_variant = 22;   // r1d: momentum loads issued before the last staple direction (-10 % on the 16^4 trajectory)

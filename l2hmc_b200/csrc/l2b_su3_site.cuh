@@ -239,6 +239,131 @@ L2B_HD void link_times_staples_hook(Mat3<T>& g, const C* U, const Lat& l, int b,
 }
 
 // ---------------------------------------------------------------------------
+// Low-register form of the same staple sum: the second operand of every 3x3 product is streamed from
+// memory ROW BY ROW (3 loads at a time) instead of being held as a whole matrix, so the peak is
+// a + X + m + one row (120 registers) instead of a + X + Y + m (144).  Every output element sees the
+// same fused multiply-adds in the same order as mat_mul, so the result is bit-identical to
+// link_times_staples (tests/hostemu).  HOOK_AT / hook as in link_times_staples_hook.
+// ---------------------------------------------------------------------------
+template <typename T, typename C>
+L2B_HD void soa_load_row(T rr[3], T ri[3], const C* plane, int V, int site, int row) {
+  L2B_UNROLL
+  for (int j = 0; j < 3; ++j) {
+    const C v = L2B_LDG(plane + (size_t)(3 * row + j) * V + site);
+    rr[j] = v.x; ri[j] = v.y;
+  }
+}
+
+// m(:, k) = op(X)(: , :) . conj(Y(k, :))   for the streamed row k of Y;   ADJ_X: op = conjugate transpose
+template <bool ADJ_X, typename T>
+L2B_HD void col_from_row_adj(Mat3<T>& m, const Mat3<T>& x, const T yr[3], const T yi[3], int k) {
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    T sr = T(0), si = T(0);
+    L2B_UNROLL
+    for (int l = 0; l < 3; ++l) {
+      const int ex = ADJ_X ? (3 * l + i) : (3 * i + l);
+      const T ar = x.re[ex], ai = ADJ_X ? -x.im[ex] : x.im[ex];
+      const T br = yr[l], bi = -yi[l];
+      sr = fma(ar, br, sr);
+      sr = fma(-ai, bi, sr);
+      si = fma(ar, bi, si);
+      si = fma(ai, br, si);
+    }
+    m.re[3 * i + k] = sr;
+    m.im[3 * i + k] = si;
+  }
+}
+
+template <typename T, typename C, int HOOK_AT, typename Hook>
+L2B_HD void link_times_staples_lowreg(Mat3<T>& g, const C* U, const Lat& l, int b, int mu, int site, Hook&& hook) {
+  const int V = l.V;
+  int r = site;
+  const int c3 = r % l.L[3]; r /= l.L[3];
+  const int c2 = r % l.L[2]; r /= l.L[2];
+  const int c1 = r % l.L[1]; r /= l.L[1];
+  const int c0 = r;
+  const int f0 = (c0 == l.L[0] - 1) ? -(l.L[0] - 1) * l.stride[0] : l.stride[0];
+  const int f1 = (c1 == l.L[1] - 1) ? -(l.L[1] - 1) * l.stride[1] : l.stride[1];
+  const int f2 = (c2 == l.L[2] - 1) ? -(l.L[2] - 1) * l.stride[2] : l.stride[2];
+  const int f3 = (c3 == l.L[3] - 1) ? -(l.L[3] - 1) : 1;
+  const int b0 = (c0 == 0) ? (l.L[0] - 1) * l.stride[0] : -l.stride[0];
+  const int b1 = (c1 == 0) ? (l.L[1] - 1) * l.stride[1] : -l.stride[1];
+  const int b2 = (c2 == 0) ? (l.L[2] - 1) * l.stride[2] : -l.stride[2];
+  const int b3 = (c3 == 0) ? (l.L[3] - 1) : -1;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int n_pmu = site + sel4(f0, f1, f2, f3, mu);
+  Mat3<T> a, x, m;
+  T rr[3], ri[3];
+  mat_zero(a);
+  if (HOOK_AT == 0) hook();
+  L2B_UNROLL
+  for (int k = 1; k < 4; ++k) {
+    if (k == HOOK_AT) hook();
+    const int nu = (mu + k) & 3;
+    const C* pnu = chain + (size_t)nu * plane_sz;
+    const int fnu = sel4(f0, f1, f2, f3, nu);
+    const int bnu = sel4(b0, b1, b2, b3, nu);
+    const int n_pnu = site + fnu;
+    const int n_mnu = site + bnu;
+    const int n_pmu_mnu = n_pmu + bnu;
+    // forward staple: m = U_nu(n+mu) U_mu(n+nu)^+ ;  a += m U_nu(n)^+
+    soa_load(x, pnu, V, n_pmu);
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      soa_load_row(rr, ri, pmu, V, n_pnu, j);
+      col_from_row_adj<false>(m, x, rr, ri, j);
+    }
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {                    // a(:, j) += m . conj(Z(j, :))
+      soa_load_row(rr, ri, pnu, V, site, j);
+      L2B_UNROLL
+      for (int i = 0; i < 3; ++i) {
+        T sr = a.re[3 * i + j], si = a.im[3 * i + j];
+        L2B_UNROLL
+        for (int q = 0; q < 3; ++q) {
+          const T ar = m.re[3 * i + q], ai = m.im[3 * i + q];
+          const T br = rr[q], bi = -ri[q];
+          sr = fma(ar, br, sr);
+          sr = fma(-ai, bi, sr);
+          si = fma(ar, bi, si);
+          si = fma(ai, br, si);
+        }
+        a.re[3 * i + j] = sr; a.im[3 * i + j] = si;
+      }
+    }
+    // backward staple: m = U_nu(n+mu-nu)^+ U_mu(n-nu)^+ ;  a += m U_nu(n-nu)
+    soa_load(x, pnu, V, n_pmu_mnu);
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      soa_load_row(rr, ri, pmu, V, n_mnu, j);
+      col_from_row_adj<true>(m, x, rr, ri, j);
+    }
+    L2B_UNROLL
+    for (int q = 0; q < 3; ++q) {                    // a += m(:, q) Z(q, :), q ascending: mat_mul's order per element
+      soa_load_row(rr, ri, pnu, V, n_mnu, q);
+      L2B_UNROLL
+      for (int i = 0; i < 3; ++i) {
+        const T ar = m.re[3 * i + q], ai = m.im[3 * i + q];
+        L2B_UNROLL
+        for (int j = 0; j < 3; ++j) {
+          T sr = a.re[3 * i + j], si = a.im[3 * i + j];
+          sr = fma(ar, rr[j], sr);
+          sr = fma(-ai, ri[j], sr);
+          si = fma(ar, ri[j], si);
+          si = fma(ai, rr[j], si);
+          a.re[3 * i + j] = sr; a.im[3 * i + j] = si;
+        }
+      }
+    }
+  }
+  soa_load(x, pmu, V, site);
+  mat_mul<false, false, false>(g, x, a);
+}
+
+// ---------------------------------------------------------------------------
 // Plaquette traces at one site, the reference's six planes in ITS order
 // (u = 1..3, v < u):  tr[ U_u(n) U_v(n+u) (U_v(n) U_u(n+v))^+ ]
 // (lattice/su3/pytorch/lattice.py:157-199).  tr_re/tr_im[p], p = 0..5.

@@ -12,7 +12,7 @@ from l2hmc_b200 import ops, _lib  # noqa: E402
 
 dev = 'cuda:0'
 cases = [(16, 64), (8, 256)]
-variants = [int(a) for a in sys.argv[1:]] or list(range(29))
+variants = [int(a) for a in sys.argv[1:]] or list(range(32))
 out = []
 REF = {}
 same = None

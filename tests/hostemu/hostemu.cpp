@@ -115,7 +115,9 @@ void emu_force_hook(const C* x, double beta, C* force, long long* hooks, int hoo
         auto hook = [&]() { ++n; };
         if (hook_at == 0) link_times_staples_hook<T, C, 0>(g, U.data(), l, b, mu, s, hook);
         else if (hook_at == 2) link_times_staples_hook<T, C, 2>(g, U.data(), l, b, mu, s, hook);
-        else link_times_staples_hook<T, C, 3>(g, U.data(), l, b, mu, s, hook);
+        else if (hook_at == 3) link_times_staples_hook<T, C, 3>(g, U.data(), l, b, mu, s, hook);
+        else if (hook_at == 13) link_times_staples_lowreg<T, C, 3>(g, U.data(), l, b, mu, s, hook);
+        else link_times_staples_lowreg<T, C, 2>(g, U.data(), l, b, mu, s, hook);   // 12
         project_tah(f, g);
         for (int e = 0; e < 9; ++e) { f.re[e] *= beta / 3.0; f.im[e] *= beta / 3.0; }
         aos_put(force, ((size_t)b * 4 + mu) * l.V + s, f);

@@ -90,7 +90,7 @@ def test_stencil_bodies(emu, g):
     emu.emu_wloops(ptr(x), ptr(wl), ctypes.c_int(nb), dims)
     assert maxdiff(wl, g['wloops']) < 1e-13
     # the hooked variant the default kick kernels use: bit-identical, hook runs exactly once per link
-    for hook_at in (0, 2, 3):
+    for hook_at in (0, 2, 3, 12, 13):      # 12 / 13: the row-streaming low-register form, hook at 2 / 3
         fh = np.empty_like(x)
         hooks = np.zeros(nb, dtype=np.int64)
         emu.emu_force_hook(ptr(x), ctypes.c_double(beta), ptr(fh), ptr(hooks), ctypes.c_int(hook_at), ctypes.c_int(nb),
