@@ -62,11 +62,13 @@ int l2b_set_option(const char* key, int value);
 /* SU(3)                                                                     */
 /* ------------------------------------------------------------------------ */
 
-/* bytes of scratch needed by any SU(3) entry point for `nb` chains of a
+/* (no reference counterpart: torch allocates its temporaries implicitly)
+ * bytes of scratch needed by any SU(3) entry point for `nb` chains of a
  * T x X x Y x Z lattice (two planar field copies + reduction partials) */
 size_t l2b_su3_ws_bytes(int nb, const int dims[4], int dtype);
 
-/* reference layout <-> internal planar layout (exposed for tests/benchmarks) */
+/* reference layout [nb,4,T,X,Y,Z,3,3] (configs.py:501-507) <-> internal planar layout
+ * U[b][mu][re/im of the 9 entries][site] (exposed for tests/benchmarks) */
 int l2b_su3_aos_to_soa(const void* x_aos, void* x_soa, int nb, const int dims[4], int dtype, void* stream);
 int l2b_su3_soa_to_aos(const void* x_soa, void* x_aos, int nb, const int dims[4], int dtype, void* stream);
 
@@ -107,7 +109,7 @@ int l2b_su3_update_gauge(const void* x, const void* p, double eps, const double*
  * either output may be NULL.  vec8[nmat, 8] real.                             */
 int l2b_su3_project(const void* x, void* x_proj_or_null, void* vec8_or_null, size_t nmat, int dtype,
                     void* stream);
-/* su3_to_vec / vec_to_su3 without projection (utils.py:394-445) */
+/* su3_to_vec (utils.py:394-420) / vec_to_su3 (utils.py:423-445) without projection */
 int l2b_su3_to_vec(const void* x, void* vec8, size_t nmat, int dtype, void* stream);
 int l2b_su3_from_vec(const void* vec8, void* x, size_t nmat, int dtype, void* stream);
 /* SU3.projectTAH (group.py:92-103) */
@@ -147,7 +149,7 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
 
 /* --- adjoints (L2HMC training; the reference relies on autograd for these).  Gradients
  * of complex fields use torch's convention G = dL/dRe + i dL/dIm for a real loss L. --- */
-/* adjoint of LatticeSU3.action: gx = coef[b] * A^+ (A = staple sum); with
+/* adjoint of LatticeSU3.action (lattice.py:252-269): gx = coef[b] * A^+ (A = staple sum); with
  * coef[b] = -(beta/3) * dL/dS[b] this is dL/dx through S = -(beta/3) sum Re tr P */
 int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, const int dims[4], int dtype, void* ws,
                         size_t ws_bytes, void* stream);
@@ -160,17 +162,17 @@ int l2b_su3_force_bwd(const void* x, double beta, const void* gforce, void* gx, 
  * per-site loops (the reference back-propagates lattice.py:157-199 through 18 bmm + 12 roll) */
 int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int nb, const int dims[4], int dtype,
                              void* ws, size_t ws_bytes, void* stream);
-/* adjoint of l2b_su3_vupdate w.r.t. v, force, s, t, q (gforce/gs/gt/gq may be NULL) and eps
+/* adjoint of l2b_su3_vupdate (dynamics.py:1266-1297) w.r.t. v, force, s, t, q (gforce/gs/gt/gq may be NULL) and eps
  * (geps[nb], per chain) */
 int l2b_su3_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const double* eps_dev,
                         int sign, const void* gv_out, const double* glogdet, void* gv, void* gforce, void* gs, void* gt,
                         void* gq, double* geps, int nb, const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
-/* adjoint of l2b_su3_update_gauge w.r.t. x, p and eps (matrix-exponential adjoint as a Taylor
+/* adjoint of l2b_su3_update_gauge (group.py:45-50, dynamics.py:1420-1425,1468-1474) w.r.t. x, p and eps (matrix-exponential adjoint as a Taylor
  * series on Cayley-Hamilton coefficients; *bad_flag is set when ||eps p||_F > 3 somewhere) */
 int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const double* eps_dev, const float* mask, int mask_complement,
                              const void* gx_out, void* gx, void* gp, double* geps, int* bad_flag, int nb,
                              const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
-/* adjoint of l2b_su3_to_vec: gx[nmat,3,3] from gvec8[nmat,8] */
+/* adjoint of l2b_su3_to_vec (utils.py:394-420): gx[nmat,3,3] from gvec8[nmat,8] */
 int l2b_su3_to_vec_bwd(const void* gvec8, void* gx, size_t nmat, int dtype, void* stream);
 
 /* group_to_vec = su3_to_vec(projectSU(x)) (dynamics.py:1154-1156, group.py:138-147) with the
@@ -185,7 +187,7 @@ int l2b_su3_project_bwd(const void* x, const void* gmat_or_null, const void* gve
 
 /* The two kernels of one leapfrog step on fields ALREADY in the planar layout
  * (l2b_su3_aos_to_soa), for callers that keep the state planar between steps
- * and for per-kernel timing (bench.py):
+ * and for per-kernel timing (bench.py); together they are Dynamics.leapfrog_hmc (dynamics.py:900-913):
  *   force_kick:  P <- P - eps_kick * (beta/3) TAH(U A); sums_or_null[nb, 2] =
  *                (sum Re tr P_plaq, sum_links(|P|_F^2 - 8)) after the kick
  *   drift:       U <- exp(eps P) U                                            */
@@ -194,7 +196,7 @@ int l2b_su3_force_kick_planar(const void* u_planar, void* p_planar, double beta,
                               size_t ws_bytes, void* stream);
 int l2b_su3_drift_planar(void* u_planar, const void* p_planar, double eps, int nb, const int dims[4],
                          int dtype, void* stream);
-/* one whole leapfrog step in ONE kernel (what l2b_su3_hmc_trajectory runs):
+/* one whole leapfrog step (dynamics.py:900-913, kicks merged) in ONE kernel (what l2b_su3_hmc_trajectory runs):
  *   P <- P - eps_kick (beta/3) TAH(U A);   u_out <- exp(eps_drift P) u_in
  * u_out must not alias u_in (other links still read their old neighbours):
  * 4 field transfers per step instead of 6.  sums_or_null as above.            */
@@ -202,7 +204,7 @@ int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, voi
                                     double eps_kick, double eps_drift, double* sums_or_null, int nb,
                                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
-/* adjoint of l2b_su3_heads_vupdate, element-wise part (the three small GEMMs of the Linear backward stay library
+/* adjoint of l2b_su3_heads_vupdate (network.py:536-548 + dynamics.py:1266-1297), element-wise part (the three small GEMMs of the Linear backward stay library
  * calls): from (s, t, q) as dumped by the forward (stq f32 [3, nb, xdim]) and the cotangents gv_out, glogdet it
  * writes gv, gforce (may be NULL), geps[nb], the cotangents of the heads' PRE-activations gpre [3, nb, xdim] in
  * gpre_dtype (L2B_F32 / L2B_BF16: the dtype of the dz / dW GEMMs) and gss = gs*s, gqq = gq*q (f32 [nb, xdim])
@@ -213,7 +215,8 @@ int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq
                               int gpre_dtype, float* gss, float* gqq, double* geps, int nb, int xdim, void* ws,
                               size_t ws_bytes, void* stream);
 
-/* L2HMC sweep with the state kept in the planar layout (no conversion around the stencil kernels):
+/* L2HMC sweep (Dynamics.transition_kernel_fb, dynamics.py:956-1029) with the state kept in the planar layout
+ * (no conversion around the stencil kernels): lattice.py:299-308, group.py:138-147 and dynamics.py:1420-1425 as
  * force without kick, group_to_vec (vec8 in [b][mu][site][8] order, as the AoS version) and the masked
  * link update; the mask is the [xdim] element mask permuted to [4][9][V].  The heads kernel
  * l2b_su3_heads_vupdate is layout-agnostic: pack the head weights with their rows permuted the same way. */
@@ -252,6 +255,7 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
 /* ------------------------------------------------------------------------ */
 /* U(1), x[nb, 2, T, X] real angles                                          */
 /* ------------------------------------------------------------------------ */
+/* scratch bytes for the U(1) entry points that take `ws` (no reference counterpart) */
 size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype);
 
 /* LatticeU1.wilson_loops (lattice/u1/pytorch/lattice.py:154-159): w[nb, T, X] */
@@ -263,7 +267,7 @@ int l2b_u1_observables(const void* x, double beta, void* obs, int nb, int T, int
 /* LatticeU1.grad_action (lattice.py:102-117), analytic */
 int l2b_u1_force(const void* x, double beta, void* force, int nb, int T, int X, int dtype,
                  void* stream);
-/* Dynamics.transition_kernel_hmc for U(1): the whole trajectory of one chain
+/* Dynamics.transition_kernel_hmc + leapfrog_hmc for U(1) (dynamics.py:900-954): the whole trajectory of one chain
  * runs inside one thread block with x, v resident in shared memory.
  * energies[nb, 4] = (KE0, S0, KE1, S1) in `dtype`.                            */
 int l2b_u1_hmc_trajectory(const void* x, const void* v, double beta, double eps, int nlf,
@@ -285,13 +289,7 @@ int l2b_u1_kinetic(const void* v, void* ke, int nb, int xdim, int dtype, void* s
 /* U1Phase.compat_proj (group.py:130-131): ((x + pi) mod 2 pi) - pi, n elements */
 int l2b_u1_compat_proj(const void* x, void* out, size_t n, int dtype, void* stream);
 
-/* --- adjoints (L2HMC training; the reference relies on autograd for these) --- */
-/* The three output heads of a U(1) LeapfrogLayer (network/pytorch/network.py:536-548) fused with the
- * update that consumes them: mode 0 = Dynamics._update_v_fwd/_bwd (dynamics.py:1266-1297) on (a = v,
- * b = force), mode 1 = _update_x_fwd/_bwd (dynamics.py:1398-1467) on (a = x, b = v, mask).  z: [nb, hidden]
- * output of the hidden stack; w_*: [xdim, hidden] nn.Linear weights, b_*: [xdim], coeff_*: [xdim]
- * (ScaledTanh.coeff), nw_* the NetWeight factors; all of `dtype`.  hidden <= 32 (CUDA-core kernel: the
- * U(1) nets are 16 wide), else L2B_ERR_UNSUPPORTED.  s, t, q never reach HBM. */
+/* --- U(1) dense networks fused with the updates (inference; network/pytorch/network.py:349-551) --- */
 /* Input layer of a U(1) LeapfrogLayer WITHOUT conv stack (network.py:349-451), xlayer and vlayer in one
  * pass over the two fields: pre[nb, units] = W_x . f(x) + b_x + W_v . v + b_v, with mode 1 (xnet)
  * f(x) = cat(cos(mask * x), sin(mask * x)) (dynamics.py:1169-1178; w_x is [units, 2 xdim]) and mode 0
@@ -301,6 +299,12 @@ size_t l2b_u1_input_ws_bytes(int nb, int xdim);
 int l2b_u1_input_layer(int mode, const void* x, const void* v, const float* mask, const void* w_x, const void* b_x,
                        const void* w_v, const void* b_v, int units, void* pre, int nb, int xdim, int dtype, void* ws,
                        size_t ws_bytes, void* stream);
+/* The three output heads of a U(1) LeapfrogLayer (network/pytorch/network.py:536-548) fused with the
+ * update that consumes them: mode 0 = Dynamics._update_v_fwd/_bwd (dynamics.py:1266-1297) on (a = v,
+ * b = force), mode 1 = _update_x_fwd/_bwd (dynamics.py:1398-1467) on (a = x, b = v, mask).  z: [nb, hidden]
+ * output of the hidden stack; w_*: [xdim, hidden] nn.Linear weights, b_*: [xdim], coeff_*: [xdim]
+ * (ScaledTanh.coeff), nw_* the NetWeight factors; all of `dtype`.  hidden <= 32 (CUDA-core kernel: the
+ * U(1) nets are 16 wide), else L2B_ERR_UNSUPPORTED.  s, t, q never reach HBM. */
 size_t l2b_u1_heads_ws_bytes(int nb, int xdim);
 int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, const void* w_t, const void* w_q,
                         const void* b_s, const void* b_t, const void* b_q, const void* coeff_s, const void* coeff_q,
@@ -308,13 +312,14 @@ int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, co
                         double eps, const void* eps_dev, int sign, int use_ncp, void* out, void* logdet, int nb,
                         int xdim, int dtype, void* ws, size_t ws_bytes, void* stream);
 
-/* adjoint of l2b_u1_wilson_loops: gx[nb,2,T,X] from gw[nb,T,X] */
+/* --- adjoints (L2HMC training; the reference relies on autograd for these, trainers/pytorch/trainer.py:1284-1314) --- */
+/* adjoint of l2b_u1_wilson_loops (lattice/u1/pytorch/lattice.py:154-159): gx[nb,2,T,X] from gw[nb,T,X] */
 int l2b_u1_wilson_loops_bwd(const void* gw, void* gx, int nb, int T, int X, int dtype, void* stream);
 /* adjoint of l2b_u1_force = Hessian-vector product of the action (the reference
  * differentiates through grad_action with create_graph=True, lattice.py:106,113-116) */
 int l2b_u1_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, int T, int X, int dtype,
                      void* stream);
-/* adjoints of l2b_u1_vupdate / l2b_u1_xupdate: gradients w.r.t. every input
+/* adjoints of l2b_u1_vupdate / l2b_u1_xupdate (dynamics.py:1266-1297,1398-1467): gradients w.r.t. every input
  * (gs/gt/gq may be NULL) and geps[nb] = per-chain derivative w.r.t. eps */
 int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const void* t, const void* q, double eps, const void* eps_dev,
                        int sign, const void* gv_out, const void* glogdet, void* gv, void* gforce, void* gs, void* gt,
@@ -322,7 +327,8 @@ int l2b_u1_vupdate_bwd(const void* v, const void* force, const void* s, const vo
 int l2b_u1_xupdate_bwd(const void* x, const void* v, const void* s, const void* t, const void* q, const float* mask,
                        double eps, const void* eps_dev, int sign, int use_ncp, const void* gx_out, const void* glogdet, void* gx, void* gv,
                        void* gs, void* gt, void* gq, void* geps, int nb, int xdim, int dtype, void* stream);
-/* out[b,:] = scale[b] * in[b,:]: adjoint of action (in = force) and of kinetic energy (in = v) */
+/* out[b,:] = scale[b] * in[b,:]: adjoint of LatticeU1._action (lattice.py:80-86; in = force) and of
+ * U1Phase.kinetic_energy (group.py:164-165; in = v) */
 int l2b_rowscale(const void* in, const void* scale, void* out, int nb, int xdim, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------ */
