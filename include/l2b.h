@@ -90,6 +90,13 @@ int l2b_su3_plaq_sums(const void* x, double* sums, int nb, const int dims[4], in
 int l2b_su3_force(const void* x, double beta, void* force, double* plaq_sum_or_null, int nb,
                   const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
+/* LatticeSU3.action / grad_action of the improved action, c1 != 0 (lattice.py:96-112,180-196,252-269,
+ * 299-308; the reference builds 12 rectangle traces per site from bmm + roll and gets the force from autograd):
+ *   force_or_null = (beta/3) TAH(U [(1 - 8 c1) A + c1 R]),  R = the 18 rectangle staples of the link;
+ *   sums_or_null[nb, 2] = (sum Re tr P, sum Re tr R), so  S = -(beta/3) ((1 - 8 c1) sums[:,0] + c1 sums[:,1]). */
+int l2b_su3_force_c1(const void* x, double beta, double c1, void* force_or_null, double* sums_or_null, int nb,
+                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
+
 /* SU3.exp (group/su3/pytorch/group.py:88-90): out = matrix_exp(scale * p), n matrices */
 int l2b_su3_exp(const void* p, double scale, void* out, size_t nmat, int dtype, void* stream);
 

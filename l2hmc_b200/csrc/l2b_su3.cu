@@ -454,6 +454,40 @@ __global__ void __launch_bounds__(TS * 4, 3) k_action_grad(const C* __restrict__
   soa_store(soa_plane(G, lat, b, mu), lat.V, site, ah);
 }
 
+// Improved action (c1 != 0): force = coef * TAH(U [(1 - 8 c1) A + c1 R]) with the 18
+// rectangle staples per link (rect_staples, l2b_su3_site.cuh); per-block partials (sum Re tr(U A), sum Re tr(U R)).
+// 91 more matrix loads and 72 more products per link than the plaquette force: FP64-bound, not tuned
+// (the rectangle term is off in every shipped config of the reference).
+template <int TS>
+__global__ void __launch_bounds__(TS * 4, 2) k_force_c1(const C* __restrict__ U, C* __restrict__ F, Lat lat, double coef,
+                                                        double c1, double* __restrict__ part) {
+  __shared__ double red[TS * 4 / 32];
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  const int tid = threadIdx.y * TS + threadIdx.x;
+  double rp = 0.0, rr = 0.0;
+  if (site < lat.V) {
+    Mat3<T> g, f;
+    link_times_improved_staples<T, C>(g, rp, rr, U, lat, b, mu, site, c1);
+    if (F != nullptr) {
+      project_tah(f, g);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { f.re[e] *= coef; f.im[e] *= coef; }
+      soa_store(soa_plane(F, lat, b, mu), lat.V, site, f);
+    }
+  }
+  if (part != nullptr) {
+    rp = block_sum<TS * 4>(rp, red, tid);
+    rr = block_sum<TS * 4>(rr, red, tid);
+    if (tid == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = rp;
+      o[1] = rr;
+    }
+  }
+}
+
 // adjoint of k_plaq<WRITE_LOOPS>: gx(mu,n) from the cotangent of the per-site loops
 template <int TS>
 __global__ void __launch_bounds__(TS * 4, 3) k_wloops_bwd(const C* __restrict__ U, const C* __restrict__ gw,
@@ -1320,6 +1354,27 @@ int l2b_su3_force(const void* x, double beta, void* force, double* plaq_sum_or_n
   if (plaq_sum_or_null)  // sum_links Re tr(U A) counts every plaquette four times
     L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, 0.25, 0.0, plaq_sum_or_null, 1, 0, nb, st));
   return launch_s2a(g, w.f1, (C*)force, st);
+}
+
+int l2b_su3_force_c1(const void* x, double beta, double c1, void* force_or_null, double* sums_or_null, int nb,
+                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && (force_or_null || sums_or_null), L2B_ERR_INVALID, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (g.lat.V + 31) / 32;     // <= nblk_link, so the partials fit (make_geo)
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  k_force_c1<32><<<dim3(nblk, nb), dim3(32, 4), 0, st>>>(w.f0, force_or_null ? w.f1 : nullptr, g.lat, beta / 3.0, c1,
+                                                        sums_or_null ? w.part : nullptr);
+  L2B_LAUNCHED("k_force_c1");
+  if (sums_or_null) {   // every plaquette is seen from its 4 links, every rectangle from its 6
+    L2B_TRY(launch_reduce(w.part, nblk, 2, 0, 0.25, 0.0, sums_or_null, 2, 0, nb, st));
+    L2B_TRY(launch_reduce(w.part, nblk, 2, 1, 1.0 / 6.0, 0.0, sums_or_null, 2, 1, nb, st));
+  }
+  if (force_or_null) return launch_s2a(g, w.f1, (C*)force_or_null, st);
+  return L2B_OK;
 }
 
 int l2b_su3_exp(const void* p, double scale, void* out, size_t nmat, int dtype, void* stream) {

@@ -470,4 +470,109 @@ L2B_HD void wloops_adjoint_link(Mat3<T>& g, const C* U, const C* gw, const Lat& 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Rectangle (c1 != 0) staples.  The reference's improved action adds the traces of the 2x1 and 1x2
+// rectangles of every plane, S = -(beta/3) [ (1 - 8 c1) sum Re tr P + c1 sum Re tr R ]
+// (lattice/su3/pytorch/lattice.py:96-112,180-196,252-269), and gets the force from autograd.  Here,
+// as for the plaquette: force = (beta/3) TAH( U_mu(n) [ (1 - 8 c1) A_mu(n) + c1 R_mu(n) ] ) with
+// R_mu(n) the sum of the 18 rectangle staples of link (mu, n): for each nu != mu and each side
+// s = +-nu, the paths of five links from n+mu back to n
+//   A  (1x2, mu short):                +s +s -mu -s -s
+//   B  (2x1, link first on its side):  +mu +s -mu -mu -s
+//   C  (2x1, link second on its side): +s -mu -mu -s +mu
+// (a forward hop in d from p multiplies by U_d(p), a backward hop by U_d(p - d)^+).
+// sum_{mu,n} Re tr(U_mu(n) R_mu(n)) = 6 * sum_rectangles Re tr R (six links per rectangle).
+// Extents 1 and 2 wrap onto themselves; the displacement table handles it.
+// ---------------------------------------------------------------------------
+L2B_HD int pmod(int a, int n) {
+  a %= n;
+  return a < 0 ? a + n : a;
+}
+L2B_HD int sel5(int a0, int a1, int a2, int a3, int a4, int i) {
+  return (i == 0) ? a0 : (i == 1) ? a1 : (i == 2) ? a2 : (i == 3) ? a3 : a4;
+}
+
+template <typename T, typename C>
+L2B_HD void rect_staples(Mat3<T>& a, const C* U, const Lat& l, int b, int mu, int site) {
+  const int V = l.V;
+  int r = site;
+  const int c3 = r % l.L[3]; r /= l.L[3];
+  const int c2 = r % l.L[2]; r /= l.L[2];
+  const int c1 = r % l.L[1]; r /= l.L[1];
+  const int c0 = r;
+  const size_t plane_sz = (size_t)9 * V;
+  const C* chain = U + (size_t)b * 4 * plane_sz;
+  const C* pmu = chain + (size_t)mu * plane_sz;
+  const int cm = sel4(c0, c1, c2, c3, mu), Lm = sel4(l.L[0], l.L[1], l.L[2], l.L[3], mu);
+  const int sm = sel4(l.stride[0], l.stride[1], l.stride[2], l.stride[3], mu);
+  // site offset of a displacement of -1, 0, 1, 2 along mu (periodic)
+  const int m_m1 = (pmod(cm - 1, Lm) - cm) * sm, m_p1 = (pmod(cm + 1, Lm) - cm) * sm,
+            m_p2 = (pmod(cm + 2, Lm) - cm) * sm;
+  // hop tables: direction (1 = mu, 0 = nu) and sign (the nu signs are multiplied by the side s)
+  const int hop_mu[3][5] = {{0, 0, 1, 0, 0}, {1, 0, 1, 1, 0}, {0, 1, 1, 0, 1}};
+  const int hop_sg[3][5] = {{1, 1, -1, -1, -1}, {1, 1, -1, -1, -1}, {1, -1, -1, -1, 1}};
+  mat_zero(a);
+  L2B_UNROLL
+  for (int k = 1; k < 4; ++k) {
+    const int nu = (mu + k) & 3;
+    const C* pnu = chain + (size_t)nu * plane_sz;
+    const int cn = sel4(c0, c1, c2, c3, nu), Ln = sel4(l.L[0], l.L[1], l.L[2], l.L[3], nu);
+    const int sn = sel4(l.stride[0], l.stride[1], l.stride[2], l.stride[3], nu);
+    const int n_m2 = (pmod(cn - 2, Ln) - cn) * sn, n_m1 = (pmod(cn - 1, Ln) - cn) * sn,
+              n_p1 = (pmod(cn + 1, Ln) - cn) * sn, n_p2 = (pmod(cn + 2, Ln) - cn) * sn;
+    L2B_UNROLL
+    for (int side = 0; side < 2; ++side) {
+      const int s = side == 0 ? 1 : -1;
+      L2B_UNROLL
+      for (int shape = 0; shape < 3; ++shape) {
+        int i = 1, j = 0;          // displacement from n along mu / nu: the path starts at n + mu
+        Mat3<T> t, x, w;
+        L2B_UNROLL
+        for (int h = 0; h < 5; ++h) {
+          const bool along_mu = hop_mu[shape][h] != 0;
+          const int sg = along_mu ? hop_sg[shape][h] : hop_sg[shape][h] * s;
+          if (sg < 0) { if (along_mu) --i; else --j; }      // backward hop: the link starts one site back
+          const int at = site + sel5(0, m_m1, 0, m_p1, m_p2, i + 2) + sel5(n_m2, n_m1, 0, n_p1, n_p2, j + 2);
+          soa_load(x, along_mu ? pmu : pnu, V, at);
+          if (sg > 0) { if (along_mu) ++i; else ++j; }
+          if (h == 0) {
+            if (sg < 0) {
+              L2B_UNROLL
+              for (int e = 0; e < 9; ++e) { t.re[e] = x.re[3 * (e % 3) + e / 3]; t.im[e] = -x.im[3 * (e % 3) + e / 3]; }
+            } else {
+              t = x;
+            }
+          } else if (h < 4) {
+            if (sg < 0) mat_mul<false, true, false>(w, t, x); else mat_mul<false, false, false>(w, t, x);
+            t = w;
+          } else {
+            if (sg < 0) mat_mul<false, true, true>(a, t, x); else mat_mul<false, false, true>(a, t, x);
+          }
+        }
+      }
+    }
+  }
+}
+
+// G = U_mu(n) [ (1 - 8 c1) A_mu(n) + c1 R_mu(n) ];  retr_p = Re tr(U A) (4x the plaquette sum when
+// summed over links), retr_r = Re tr(U R) (6x the rectangle sum).
+template <typename T, typename C>
+L2B_HD void link_times_improved_staples(Mat3<T>& g, T& retr_p, T& retr_r, const C* U, const Lat& l, int b, int mu,
+                                        int site, T c1) {
+  Mat3<T> ap, ar, x, gp, gr;
+  link_times_staples<T, C, 0, false>(ap, U, l, b, mu, site);
+  rect_staples<T, C>(ar, U, l, b, mu, site);
+  soa_load(x, soa_plane(U, l, b, mu), l.V, site);
+  mat_mul<false, false, false>(gp, x, ap);
+  mat_mul<false, false, false>(gr, x, ar);
+  retr_p = re_trace(gp);
+  retr_r = re_trace(gr);
+  const T cp = T(1) - T(8) * c1;
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    g.re[e] = cp * gp.re[e] + c1 * gr.re[e];
+    g.im[e] = cp * gp.im[e] + c1 * gr.im[e];
+  }
+}
+
 }  // namespace l2b

@@ -8,6 +8,7 @@ the reference's autograd-of-the-action.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -35,6 +36,12 @@ class LatticeSU3(Lattice):
         self.g = SU3()
         self.nt, self.nx, self.ny, self.nz = shape
         self.c1 = float(c1)      # c1 != 0 (DBW2 / rectangle term): plaquette part on the kernels, rectangle
+        # `rect_kernel`: evaluate the improved action / force with the hand-written rectangle-staple kernel
+        # (l2b_su3_force_c1) wherever no autograd graph is needed (HMC, eval) instead of ATen ops.  The
+        # kernel's arithmetic is pinned on the reference's c1 goldens through the host emulation
+        # (tests/test_hostemu.py); it stays opt-in (L2B_RECT_KERNEL=1) until its launch has been run on
+        # a GPU against the same goldens (tests/test_gpu_su3.py::test_rectangle_kernel_c1_matches_reference).
+        self.rect_kernel = os.environ.get('L2B_RECT_KERNEL', '0') == '1'
         super().__init__(group=self.g, nchains=nchains, shape=list(shape))
 
     def _field(self, x: Tensor) -> Tensor:
@@ -89,6 +96,9 @@ class LatticeSU3(Lattice):
     def action(self, x: Tensor, beta) -> Tensor:
         """S = -(beta (1 - 8 c1) / 3) sum Re tr P - (beta c1 / 3) sum Re tr R   (lattice.py:252-269);
         differentiable (plaquette part: adjoint = the staple-sum kernel)"""
+        if self._use_rect_kernel(x):
+            sums = ops.su3_force_c1(self._field(x), _f(beta), self.c1, want_force=False, want_sums=True)
+            return (self.coeffs(beta)['plaq'] * sums[:, 0] + self.coeffs(beta)['rect'] * sums[:, 1]) * (-1.0 / 3.0)
         s = ag.SU3Action.apply(self._field(x), self.coeffs(beta)['plaq'])
         if self.c1 != 0.0:
             s = s + self._rect_action(x, beta)
@@ -147,10 +157,17 @@ class LatticeSU3(Lattice):
         """(beta/3) TAH(U A), analytic; equals the reference's
         projectTAH(autograd(S) @ x^+) (lattice.py:299-308).  Like the reference
         (no create_graph) the result is a constant w.r.t. later backprop."""
+        if self._use_rect_kernel(x):
+            return ops.su3_force_c1(self._field(x), _f(beta), self.c1)
         f = ag.SU3Force.apply(self._field(x), self.coeffs(beta)['plaq'])
         if self.c1 != 0.0:
             f = f + self._rect_force(self._field(x), beta)
         return f
+
+    def _use_rect_kernel(self, x: Tensor) -> bool:
+        """the rectangle kernel has no adjoint: only where nothing will be back-propagated"""
+        return (self.c1 != 0.0 and self.rect_kernel
+                and not (torch.is_grad_enabled() and (x.requires_grad or isinstance(self.c1, Tensor))))
 
     def _rect_force(self, x: Tensor, beta) -> Tensor:
         """projectTAH(dS_rect/dx @ x^+) with dS_rect/dx from ATen autograd, detached like the
@@ -165,6 +182,9 @@ class LatticeSU3(Lattice):
 
     def action_with_grad(self, x: Tensor, beta) -> tuple[Tensor, Tensor]:
         """one force pass yields both (lattice.py:287-297)"""
+        if self._use_rect_kernel(x.detach()):
+            f, sums = ops.su3_force_c1(self._field(x.detach()), _f(beta), self.c1, want_sums=True)
+            return (self.coeffs(beta)['plaq'] * sums[:, 0] + self.coeffs(beta)['rect'] * sums[:, 1]) * (-1.0 / 3.0), f
         if self.c1 != 0.0:
             return self.action(x, beta).detach(), self.grad_action(x, beta).detach()
         f, ps = ops.su3_force(self._field(x.detach()), _f(beta), want_plaq_sum=True)

@@ -116,6 +116,20 @@ def su3_force(x: Tensor, beta: float, want_plaq_sum: bool = False):
     return (f, ps) if want_plaq_sum else f
 
 
+def su3_force_c1(x: Tensor, beta: float, c1: float, want_force: bool = True, want_sums: bool = False):
+    """improved-action force and / or loop sums [nb, 2] = (sum Re tr P, sum Re tr R)
+    (lattice/su3/pytorch/lattice.py:96-112,252-269,299-308 with c1 != 0)"""
+    x, nb, dims = _su3_field(x)
+    f = torch.empty_like(x) if want_force else None
+    sums = torch.empty(nb, 2, dtype=torch.float64, device=x.device) if want_sums else None
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_force_c1', _ptr(x), float(beta), float(c1), _ptr(f), _ptr(sums), nb, dims4(dims), L2B_F64, _ptr(ws), n,
+         _stream())
+    if want_force and want_sums:
+        return f, sums
+    return f if want_force else sums
+
+
 def _mats(x: Tensor) -> tuple[Tensor, int]:
     _need_cuda(x)
     if x.dtype != torch.complex128 or tuple(x.shape[-2:]) != (3, 3):

@@ -101,6 +101,28 @@ void emu_force(const C* x, double beta, C* force, double* retr, int nb, const in
     if (retr) retr[b] = acc;
   }
 }
+// improved (c1 != 0) action: force = (beta/3) TAH(U [(1 - 8 c1) A + c1 R]); sums[b, 2] = (sum Re tr P, sum Re tr R)
+void emu_force_c1(const C* x, double beta, double c1, C* force, double* sums, int nb, const int* dims) {
+  const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  std::vector<C> U;
+  to_soa(U, x, nb, l);
+  for (int b = 0; b < nb; ++b) {
+    double sp = 0.0, sr = 0.0;
+    for (int mu = 0; mu < 4; ++mu)
+      for (int s = 0; s < l.V; ++s) {
+        Mat3<T> g, f;
+        T rp, rr;
+        link_times_improved_staples<T, C>(g, rp, rr, U.data(), l, b, mu, s, c1);
+        sp += rp;
+        sr += rr;
+        project_tah(f, g);
+        for (int e = 0; e < 9; ++e) { f.re[e] *= beta / 3.0; f.im[e] *= beta / 3.0; }
+        aos_put(force, ((size_t)b * 4 + mu) * l.V + s, f);
+      }
+    sums[2 * b] = sp / 4.0;
+    sums[2 * b + 1] = sr / 6.0;
+  }
+}
 // the force through link_times_staples_hook (what the default kick kernels k_force_ep call): must be
 // bit-identical to link_times_staples; `hooks[b]` counts the hook invocations (one per link)
 void emu_force_hook(const C* x, double beta, C* force, long long* hooks, int hook_at, int nb, const int* dims) {

@@ -91,6 +91,11 @@ def test_new_entry_points_validate_arguments_without_gpu(lib):
         lib.call('l2b_su3_heads_vupdate', *args, 64, None, 0, None)
     assert lib._lib.l2b_vnet_heads_packed_bytes(1152, 64) == 9 * 3 * 64 * 128 * 2
     assert lib._lib.l2b_vnet_heads_packed_bytes(1000, 40) == 8 * 3 * 64 * 128 * 2      # ragged tile, K padded to 64
+    # improved-action force: needs at least one output
+    with pytest.raises(lib.L2BError, match='null'):
+        lib.call('l2b_su3_force_c1', p, 6.0, -0.331, None, None, 1, d, lib.L2B_F64, p, 1 << 30, None)
+    with pytest.raises(lib.L2BError, match='workspace'):
+        lib.call('l2b_su3_force_c1', p, 6.0, -0.331, p, None, 1, d, lib.L2B_F64, p, 16, None)
     # U(1) fused kernels
     with pytest.raises(lib.L2BError, match='hidden <= 32'):
         lib.call('l2b_u1_heads_update', 0, p, 48, p, p, p, p, p, p, p, p, 1.0, 1.0, 1.0, p, p, None, 0.1, None, 1, 1, p, p, 4,

@@ -225,9 +225,11 @@ def test_accept_mix_is_bit_exact_select(ops, g):
     assert np.array_equal(host(xo), wx) and np.array_equal(host(vo), wv)
 
 
-def test_rectangle_action_c1_matches_reference(golden_dir):
-    """LatticeSU3(c1 != 0): plaquette part on the kernels + rectangle part as ATen ops; loops,
-    action, force and a plain-HMC trajectory against the reference's own c1 = -0.331 run"""
+@pytest.mark.parametrize('kernel', [False, True])
+def test_rectangle_action_c1_matches_reference(golden_dir, kernel):
+    """LatticeSU3(c1 != 0): loops, action, force and a plain-HMC trajectory against the reference's own
+    c1 = -0.331 run.  kernel=False: plaquette part on the kernels + rectangle part as ATen ops;
+    kernel=True: everything in the rectangle-staple kernel (l2b_su3_force_c1)"""
     from l2hmc_b200.configs import DynamicsConfig
     from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
     from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
@@ -237,8 +239,19 @@ def test_rectangle_action_c1_matches_reference(golden_dir):
         g = np.load(golden_dir / 'su3_c1_f64.npz')
         shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
         lat = LatticeSU3(nb, shape, c1=c1)
+        if kernel and not lat.rect_kernel:
+            pytest.skip('rectangle kernel is opt-in until its launch has been verified on a GPU: L2B_RECT_KERNEL=1')
+        lat.rect_kernel = kernel
         x, v = dev(g['x']), dev(g['v'])
         b = torch.tensor(beta)
+        if kernel:
+            from l2hmc_b200 import ops as _ops
+            sums = _ops.su3_force_c1(x, beta, c1, want_force=False, want_sums=True)
+            rs_want = g['rects'].real.reshape(12, nb, -1).sum(2).sum(0)
+            assert np.all(np.abs(host(sums)[:, 1] - rs_want) <= 1e-12 * np.abs(rs_want).max())
+            s2, f2 = lat.action_with_grad(x, b)
+            assert np.all(np.abs(host(s2) - g['action']) <= 1e-12 * np.abs(g['action']))
+            assert maxdiff(host(f2), g['force']) < 1e-12
         ps, rs = lat._wilson_loops(x, needs_rect=True)
         assert maxdiff(host(rs), g['rects']) < 1e-13
         assert np.all(np.abs(host(lat.action(x, b)) - g['action']) <= 1e-12 * np.abs(g['action']))

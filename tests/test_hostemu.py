@@ -159,3 +159,28 @@ def test_exp_adjoint_matches_torch_autograd_at_all_norms(emu):
         at = torch.from_numpy(a).requires_grad_(True)
         want, = torch.autograd.grad(torch.linalg.matrix_exp(at), at, grad_outputs=torch.from_numpy(g))
         assert maxdiff(ga, want.numpy()) < 2e-14 * max(1.0, np.abs(want.numpy()).max()), rho
+
+
+def test_rectangle_force_body_matches_reference_c1(emu, golden_dir):
+    """rect_staples / link_times_improved_staples (the c1 != 0 force kernel's body) against the
+    reference's own c1 = -0.331 run (autograd force, lattice.py:96-112,252-269,299-308) on a
+    2 x 4 x 3 x 2 lattice: extents 2 and 3 exercise the wrap of the two-site hops"""
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    x = np.ascontiguousarray(g['x'])
+    nb, beta, c1 = x.shape[0], float(g['beta']), float(g['c1'])
+    dims = (ctypes.c_int * 4)(*[int(s) for s in g['shape']])
+    f = np.empty_like(x)
+    sums = np.empty((nb, 2))
+    emu.emu_force_c1(ptr(x), ctypes.c_double(beta), ctypes.c_double(c1), ptr(f), ptr(sums), ctypes.c_int(nb), dims)
+    assert maxdiff(f, g['force']) < 1e-12 * max(1.0, np.abs(g['force']).max())
+    rs = g['rects'].real.reshape(12, nb, -1).sum(2).sum(0)
+    assert np.allclose(sums[:, 1], rs, rtol=1e-12, atol=1e-11)
+    assert np.allclose(sums[:, 0], osu3.plaq_sums(x)[0], rtol=1e-12, atol=1e-11)
+    s = -(beta / 3.0) * ((1 - 8 * c1) * sums[:, 0] + c1 * sums[:, 1])
+    assert np.allclose(s, g['action'], rtol=1e-12, atol=1e-11)
+    # c1 = 0 reduces to the plaquette force
+    f0 = np.empty_like(x)
+    emu.emu_force_c1(ptr(x), ctypes.c_double(beta), ctypes.c_double(0.0), ptr(f0), ptr(sums), ctypes.c_int(nb), dims)
+    fp = np.empty_like(x)
+    emu.emu_force(ptr(x), ctypes.c_double(beta), ptr(fp), None, ctypes.c_int(nb), dims)
+    assert maxdiff(f0, fp) < 1e-14
