@@ -37,11 +37,9 @@ class LatticeSU3(Lattice):
         self.nt, self.nx, self.ny, self.nz = shape
         self.c1 = float(c1)      # c1 != 0 (DBW2 / rectangle term): plaquette part on the kernels, rectangle
         # `rect_kernel`: evaluate the improved action / force with the hand-written rectangle-staple kernel
-        # (l2b_su3_force_c1) wherever no autograd graph is needed (HMC, eval) instead of ATen ops.  The
-        # kernel's arithmetic is pinned on the reference's c1 goldens through the host emulation
-        # (tests/test_hostemu.py); it stays opt-in (L2B_RECT_KERNEL=1) until its launch has been run on
-        # a GPU against the same goldens (tests/test_gpu_su3.py::test_rectangle_kernel_c1_matches_reference).
-        self.rect_kernel = os.environ.get('L2B_RECT_KERNEL', '0') == '1'
+        # (l2b_su3_force_c1) wherever no autograd graph is needed (HMC, eval); under autograd (training) the
+        # rectangle part runs as ATen ops.  L2B_RECT_KERNEL=0 forces the ATen path everywhere.
+        self.rect_kernel = os.environ.get('L2B_RECT_KERNEL', '1') == '1'
         super().__init__(group=self.g, nchains=nchains, shape=list(shape))
 
     def _field(self, x: Tensor) -> Tensor:

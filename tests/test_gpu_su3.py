@@ -240,7 +240,7 @@ def test_rectangle_action_c1_matches_reference(golden_dir, kernel):
         shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
         lat = LatticeSU3(nb, shape, c1=c1)
         if kernel and not lat.rect_kernel:
-            pytest.skip('rectangle kernel is opt-in until its launch has been verified on a GPU: L2B_RECT_KERNEL=1')
+            pytest.skip('rectangle kernel disabled by L2B_RECT_KERNEL=0')
         lat.rect_kernel = kernel
         x, v = dev(g['x']), dev(g['v'])
         b = torch.tensor(beta)
