@@ -446,15 +446,25 @@ class Dynamics(nn.Module):
         sumlogdet = torch.zeros(nb, dtype=torch.float64, device=xs.device)
         nlf = self.config.nleapfrog
 
+        reuse = self._reuse_force()
+        cache: dict = {}            # force and vnet inputs of the current links; emptied by every x-update
+
         def v_update(step, vs_, sign):
             vnet = self._get_vnet(step)
             dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
-            f = ops.su3_force_planar(xs, beta)
-            z = vnet.hidden((ops.su3_project_vec_planar(xs, dt), ops.su3_project_vec_planar(f, dt)))
+            if not reuse:
+                cache.clear()
+            if 'f' not in cache:
+                cache['f'] = ops.su3_force_planar(xs, beta)
+            f = cache['f']
+            if dt not in cache:
+                cache[dt] = (ops.su3_project_vec_planar(xs, dt), ops.su3_project_vec_planar(f, dt))
+            z = vnet.hidden(cache[dt])
             return ops.su3_heads_vupdate(z, vnet.heads_pack(perm), vs_.reshape(nb, -1), f.reshape(nb, -1),
                                          self._eps_t(self.veps[step]).to(torch.float64), sign)
 
         def x_update(step, xs_, vs_, complement, sign):
+            cache.clear()
             return ops.su3_update_gauge_planar(xs_, vs_.reshape(xs_.shape), self._eps_t(self.xeps[step]).to(torch.float64),
                                                pmasks[step], complement, eps_mult=float(sign))
         for step in range(nlf):                     # _forward_lf
@@ -533,6 +543,7 @@ class Dynamics(nn.Module):
 
     def compute_accept_prob(self, state_init: State, state_prop: State, sumlogdet: Tensor) -> Tensor:
         """exp(min(H0 - H1 + sumlogdet, 0))   (dynamics.py:1065-1079)"""
+        self._fcache = None          # end of a sweep: drop the force / vnet-input cache (`_force`)
         dh = self.hamiltonian(state_init) - self.hamiltonian(state_prop) + sumlogdet
         return torch.exp(torch.minimum(dh, torch.zeros_like(dh)))
 
@@ -589,7 +600,7 @@ class Dynamics(nn.Module):
             dt = next(vnet.parameters()).dtype      # nets live in torch's default dtype
             if torch.is_autocast_enabled('cuda'):   # cfg 5: bf16 nets; the kernel writes bf16 directly
                 dt = torch.get_autocast_dtype('cuda')
-            return vnet((self.group_to_vec(x, dt), self.group_to_vec(force, dt)))
+            return vnet(self._vnet_vecs(State(x, None, None), force, dt))
         vnet = self._get_vnet(step)
         return vnet((x, force))
 
@@ -679,6 +690,39 @@ class Dynamics(nn.Module):
         state, logdet = self._update_v_bwd(step_r, state)
         return state, sumlogdet + logdet
 
+    def _reuse_force(self) -> bool:
+        """Two consecutive v-updates with no x-update in between -- the second half of leapfrog layer i
+        and the first half of layer i+1, and the two around the turn-around of the forward/backward
+        sweep -- see the same links, so the force and the vnet inputs su3_to_vec(projectSU(.)) of x and
+        of the force are the same tensors.  The reference recomputes them (dynamics.py:1187-1228,
+        1266-1297); with `reuse_force = 'always'` they are computed once per distinct x (2 nlf + 1
+        instead of 4 nlf force evaluations per fb sweep; forward results bit-identical, under autograd
+        the shared tensors simply receive the sum of both cotangents).  Default 'never' until the switch
+        has been through the GPU parity tests (tests/test_gpu_dynamics.py runs both settings when
+        L2B_TEST_REUSE_FORCE=1)."""
+        return getattr(self, 'reuse_force', 'never') == 'always'
+
+    def _force(self, state: State) -> Tensor:
+        if not self._reuse_force():
+            return self.grad_potential(state.x, state.beta)
+        c = getattr(self, '_fcache', None)
+        if (c is not None and c['x'] is state.x and c['ver'] == state.x._version and c['beta'] is state.beta
+                and c['grad'] == torch.is_grad_enabled()):
+            return c['force']
+        force = self.grad_potential(state.x, state.beta)
+        self._fcache = {'x': state.x, 'ver': state.x._version, 'beta': state.beta, 'grad': torch.is_grad_enabled(),
+                        'force': force, 'vecs': {}}
+        return force
+
+    def _vnet_vecs(self, state: State, force: Tensor, dt) -> tuple[Tensor, Tensor]:
+        """(group_to_vec(x), group_to_vec(force)) in the vnet's dtype (dynamics.py:1154-1156)"""
+        c = getattr(self, '_fcache', None) if self._reuse_force() else None
+        if c is None or c['force'] is not force:
+            return self.group_to_vec(state.x, dt), self.group_to_vec(force, dt)
+        if dt not in c['vecs']:
+            c['vecs'][dt] = (self.group_to_vec(state.x, dt), self.group_to_vec(force, dt))
+        return c['vecs'][dt]
+
     def _fused_heads(self, vnet) -> bool:
         """SU(3) v-update with the vnet heads on the tensor cores (bf16 tcgen05, fp32
         accumulate) fused with the update itself.  `tensor_core_heads`: 'auto' (default) =
@@ -716,7 +760,7 @@ class Dynamics(nn.Module):
     def _update_v(self, step: int, state: State, sign: int, hmc: bool = False) -> tuple[State, Tensor]:
         """dynamics.py:1266-1297: force, vnet, then the fused epilogue kernel (hmc=True: no
         networks, the plain half kick v -+ eps/2 F of dynamics.py:1244-1254)"""
-        force = self.grad_potential(state.x, state.beta)
+        force = self._force(state)
         eps = None      # the kernels read the step size from the device tensor (no host round trip)
         if hmc:
             if self._su3:
@@ -729,7 +773,7 @@ class Dynamics(nn.Module):
         if self._su3 and self._networks_built and self._fused_heads(self._get_vnet(step)):
             vnet = self._get_vnet(step)
             dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
-            z = vnet.hidden((self.group_to_vec(state.x, dt), self.group_to_vec(force, dt)))
+            z = vnet.hidden(self._vnet_vecs(state, force, dt))
             v, logdet = ag.SU3HeadsVUpdate.apply(z, self.unflatten(state.v), self.unflatten(force),
                                                  self._eps_t(self.veps[step]).to(torch.float64), sign, eps, vnet,
                                                  *vnet.head_params())
