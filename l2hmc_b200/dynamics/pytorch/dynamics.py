@@ -16,11 +16,12 @@ L2HMC only; element-wise float32 masks built with numpy's RNG; SU(3) x-update
 through projectSU; `acc_mask` float32; HMC `nleapfrog` doubles when
 `merge_directions`; x_out returned flattened.
 
-Training: both L2HMC paths are differentiable end to end (l2hmc_b200/autograd.py):
-U(1) entirely through hand-written adjoint kernels; SU(3) through adjoint kernels for
-the action, the v-update, the masked exp(eps v) x-update (matrix-exponential adjoint),
-su3_to_vec and the kinetic energy, with projectSU and the per-site Wilson loops
-back-propagated by re-evaluating a torch restatement inside backward for now.
+Training: both L2HMC paths are differentiable end to end through hand-written adjoint
+kernels (l2hmc_b200/autograd.py): U(1) force / updates / loops; SU(3) action, force,
+v-update (also fused with the tcgen05 heads), masked exp(eps v) x-update
+(matrix-exponential adjoint), projectSU + su3_to_vec (closed-form polar-factor adjoint),
+per-site Wilson loops and the kinetic energy.  Only the dense layers in front of the
+output heads and the rectangle term of the improved action (c1 != 0) use torch autograd.
 """
 from __future__ import annotations
 

@@ -112,3 +112,22 @@ def test_new_entry_points_validate_arguments_without_gpu(lib):
         lib.call('l2b_su3_project_bwd', p, None, None, lib.L2B_F64, p, 16, lib.L2B_F64, None)
     with pytest.raises(lib.L2BError, match='null'):
         lib.call('l2b_su3_update_gauge_planar', p, None, 1.0, None, None, 0, p, 2, d, lib.L2B_F64, None)
+
+
+def test_plain_c_program_links_against_the_library(tmp_path):
+    """examples/c_abi_cold_start.c: a C99 consumer with no Python and no torch links against libl2b.so
+    (+ the CUDA runtime for its own allocations); without a GPU it reports that and exits 77, with one
+    it checks the cold-start known answers"""
+    import shutil
+    import subprocess
+    exe = tmp_path / 'cold'
+    cudalib = Path(shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc').resolve().parents[1] / 'lib64'
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Wextra', '-I', str(ROOT), str(ROOT / 'examples' / 'c_abi_cold_start.c'),
+                           '-o', str(exe), '-L', str(ROOT / 'l2hmc_b200'), '-ll2b', '-L', str(cudalib), '-lcudart',
+                           f'-Wl,-rpath,{ROOT / "l2hmc_b200"}', f'-Wl,-rpath,{cudalib}', '-lm'])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode in (0, 77), (r.returncode, r.stdout, r.stderr)
+    if r.returncode == 77:
+        assert 'no CPU fallback' in r.stderr
+    else:
+        assert '-> ok' in r.stdout
