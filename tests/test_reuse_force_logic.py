@@ -69,3 +69,98 @@ def test_reuse_hits_only_for_the_same_unmodified_links():
     other = st3.x * 3.0
     fake._vnet_vecs(State(st3.x, st.v, beta), other, torch.float32)
     assert calls['vec'] == 6
+
+
+def test_planar_sweep_schedule_with_fake_ops(monkeypatch):
+    """`_transition_kernel_fb_planar` executed on the CPU with stand-in ops (deterministic torch
+    functions that count their calls): the default schedule evaluates the force once per v-update
+    (4 nlf) and projects twice per v-update; with reuse it is once per distinct x (2 nlf + 1), and
+    both give the same state, acceptance and log-Jacobian."""
+    import l2hmc_b200.dynamics.pytorch.dynamics as dmod
+    nb, n, nlf = 3, 10, 2
+    calls = {}
+
+    def count(name):
+        calls[name] = calls.get(name, 0) + 1
+
+    class FakeOps:
+        @staticmethod
+        def su3_aos_to_soa(t):
+            return t.clone()
+
+        @staticmethod
+        def su3_soa_to_aos(t):
+            return t.clone()
+
+        @staticmethod
+        def su3_force_planar(xs, beta):
+            count('force')
+            return torch.sin(xs) * beta
+
+        @staticmethod
+        def su3_project_vec_planar(t, dt):
+            count('project')
+            return (t * 0.5).to(dt)
+
+        @staticmethod
+        def su3_heads_vupdate(z, pack, v, f, eps, sign):
+            count('vupdate')
+            return v + sign * eps * (f + z.to(v.dtype)), (z.double() * sign * eps).sum(1)
+
+        @staticmethod
+        def su3_update_gauge_planar(xs, vs, eps, mask, complement, eps_mult=1.0):
+            count('xupdate')
+            m = (1 - mask) if complement else mask
+            return xs + m * eps * eps_mult * vs
+
+    class FakeVnet:
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=torch.float64)])
+
+        def hidden(self, inputs):
+            return inputs[0] + 2.0 * inputs[1]
+
+        def heads_pack(self, perm):
+            return None
+
+    monkeypatch.setattr(dmod, 'ops', FakeOps)
+    masks = [(torch.arange(n) % 2 == k % 2).double() for k in range(nlf)]
+    fake = types.SimpleNamespace(
+        config=types.SimpleNamespace(nleapfrog=nlf), _fcache=None,
+        veps=[torch.tensor(0.05)] * nlf, xeps=[torch.tensor(0.07)] * nlf,
+        _planar_consts=lambda: (None, masks), unflatten=lambda t: t, _get_vnet=lambda step: FakeVnet(),
+        _eps_t=lambda p: p, compute_accept_prob=lambda s0, s1, sld: torch.exp(-sld.abs()))
+    fake._reuse_force = lambda: dmod.Dynamics._reuse_force(fake)
+    torch.manual_seed(0)
+    st = State(torch.randn(nb, n, dtype=torch.float64), torch.randn(nb, n, dtype=torch.float64), torch.tensor(2.0))
+    res = {}
+    for mode in ('never', 'always'):
+        fake.reuse_force = mode
+        calls.clear()
+        out, met = dmod.Dynamics._transition_kernel_fb_planar(fake, st)
+        res[mode] = (out.x, out.v, met['acc'], met['sumlogdet'], dict(calls))
+    assert res['never'][4] == {'force': 4 * nlf, 'project': 8 * nlf, 'vupdate': 4 * nlf, 'xupdate': 4 * nlf}
+    assert res['always'][4] == {'force': 2 * nlf + 1, 'project': 2 * (2 * nlf + 1), 'vupdate': 4 * nlf, 'xupdate': 4 * nlf}
+    for a, b in zip(res['never'][:4], res['always'][:4]):
+        assert torch.equal(a, b)
+
+
+def test_call_vnet_packs_projected_inputs_in_the_reference_order():
+    """`_call_vnet` for SU(3) (dynamics.py:1142-1159): vnet((group_to_vec(x), group_to_vec(force)))"""
+    fake, calls = make('never')
+    seen = {}
+
+    class Vnet:
+        def parameters(self):
+            return iter([torch.zeros(1, dtype=torch.float64)])
+
+        def __call__(self, inputs):
+            seen['inputs'] = inputs
+            return inputs[0], inputs[1], inputs[0] + inputs[1]
+    fake._su3, fake._networks_built = True, True
+    fake._get_vnet = lambda step: Vnet()
+    fake.group_to_vec = lambda x, dt: (x * 3.0).to(dt)
+    x, f = torch.randn(2, 4, dtype=torch.float64), torch.randn(2, 4, dtype=torch.float64)
+    s, t, q = Dynamics._call_vnet(fake, 0, (x, f))
+    assert torch.equal(seen['inputs'][0], x * 3.0) and torch.equal(seen['inputs'][1], f * 3.0)
+    assert torch.equal(q, (x + f) * 3.0)
