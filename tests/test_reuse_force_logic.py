@@ -163,4 +163,4 @@ def test_call_vnet_packs_projected_inputs_in_the_reference_order():
     x, f = torch.randn(2, 4, dtype=torch.float64), torch.randn(2, 4, dtype=torch.float64)
     s, t, q = Dynamics._call_vnet(fake, 0, (x, f))
     assert torch.equal(seen['inputs'][0], x * 3.0) and torch.equal(seen['inputs'][1], f * 3.0)
-    assert torch.equal(q, (x + f) * 3.0)
+    assert torch.equal(q, x * 3.0 + f * 3.0) and torch.equal(s, x * 3.0) and torch.equal(t, f * 3.0)
