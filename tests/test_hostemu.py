@@ -184,3 +184,66 @@ def test_rectangle_force_body_matches_reference_c1(emu, golden_dir):
     fp = np.empty_like(x)
     emu.emu_force(ptr(x), ctypes.c_double(beta), ptr(fp), None, ctypes.c_int(nb), dims)
     assert maxdiff(f0, fp) < 1e-14
+
+
+def _gauge_transform(x, gt):
+    """U_mu(n) -> g(n) U_mu(n) g(n + mu)^+"""
+    out = np.empty_like(x)
+    for mu in range(4):
+        out[:, mu] = gt @ x[:, mu] @ osu3.adj(np.roll(gt, -1, axis=1 + mu))
+    return out
+
+
+@pytest.mark.parametrize('c1', [0.0, -0.331])
+def test_gauge_covariance_of_the_force_bodies(emu, c1):
+    """domain property, independent of any golden: under a local gauge transformation the action is invariant
+    and the force rotates, F_mu(n) -> g(n) F_mu(n) g(n)^+; holds for the plaquette and the rectangle staples"""
+    rng = np.random.default_rng(17)
+    shape, nb, beta = (4, 3, 2, 5), 2, 5.7
+    x = np.ascontiguousarray(osu3.random_su3(rng, (nb, 4, *shape, 3, 3)))
+    gt = osu3.random_su3(rng, (nb, *shape, 3, 3))
+    xg = np.ascontiguousarray(_gauge_transform(x, gt))
+    dims = (ctypes.c_int * 4)(*shape)
+    f, fg = np.empty_like(x), np.empty_like(x)
+    s, sg = np.empty((nb, 2)), np.empty((nb, 2))
+    for xx, ff, ss in ((x, f, s), (xg, fg, sg)):
+        emu.emu_force_c1(ptr(xx), ctypes.c_double(beta), ctypes.c_double(c1), ptr(ff), ptr(ss), ctypes.c_int(nb), dims)
+    assert np.allclose(s, sg, rtol=1e-12, atol=1e-10)
+    want = np.empty_like(f)
+    for mu in range(4):
+        want[:, mu] = gt @ f[:, mu] @ osu3.adj(gt)
+    assert maxdiff(fg, want) < 1e-12 * max(1.0, np.abs(f).max())
+    # the force is traceless anti-Hermitian
+    assert maxdiff(f, -osu3.adj(f)) < 1e-13 and np.abs(osu3.trace(f)).max() < 1e-13
+
+
+def test_trajectory_body_is_reversible_and_stays_in_the_group(emu):
+    """leapfrog is time-reversible: integrating forward, flipping the momenta and integrating again returns to
+    the start (to rounding); links stay unitary with unit determinant"""
+    rng = np.random.default_rng(23)
+    shape, nb, beta, eps, nlf = (4, 2, 3, 4), 2, 6.0, 0.07, 5
+    full = (nb, 4, *shape, 3, 3)
+    x = np.ascontiguousarray(osu3.random_su3(rng, full))
+    v = np.ascontiguousarray(osu3.random_momentum(rng, full))
+    dims = (ctypes.c_int * 4)(*shape)
+    x1, v1, e1 = np.empty_like(x), np.empty_like(x), np.empty((nb, 4))
+    emu.emu_hmc(ptr(x), ptr(v), ctypes.c_double(beta), ctypes.c_double(eps), ctypes.c_int(nlf), ptr(x1), ptr(v1), ptr(e1),
+                ctypes.c_int(nb), dims)
+    vm = np.ascontiguousarray(-v1)
+    x2, v2, e2 = np.empty_like(x), np.empty_like(x), np.empty((nb, 4))
+    emu.emu_hmc(ptr(x1), ptr(vm), ctypes.c_double(beta), ctypes.c_double(eps), ctypes.c_int(nlf), ptr(x2), ptr(v2), ptr(e2),
+                ctypes.c_int(nb), dims)
+    assert maxdiff(x2, x) < 1e-12 and maxdiff(-v2, v) < 1e-12
+    assert np.allclose(e2[:, 2] + e2[:, 3], e1[:, 0] + e1[:, 1], rtol=1e-13)        # H returns to its start value
+    # (the closed-form projectSU start is unitary to ~6e-13; exp(eps P) U must not make it worse)
+    u0 = maxdiff(osu3.adj(x) @ x, np.broadcast_to(np.eye(3), x.shape))
+    assert maxdiff(osu3.adj(x1) @ x1, np.broadcast_to(np.eye(3), x1.shape)) < u0 + 1e-13
+    assert np.abs(osu3.det3(x1) - 1.0).max() < np.abs(osu3.det3(x) - 1.0).max() + 1e-13
+    # second-order integrator: halving the step at fixed trajectory length divides the energy error by ~4
+    dh = (e1[:, 2] + e1[:, 3]) - (e1[:, 0] + e1[:, 1])
+    x3, v3, e3 = np.empty_like(x), np.empty_like(x), np.empty((nb, 4))
+    emu.emu_hmc(ptr(x), ptr(v), ctypes.c_double(beta), ctypes.c_double(eps / 2), ctypes.c_int(2 * nlf), ptr(x3), ptr(v3),
+                ptr(e3), ctypes.c_int(nb), dims)
+    dh2 = (e3[:, 2] + e3[:, 3]) - (e3[:, 0] + e3[:, 1])
+    ratio = np.abs(dh2) / np.abs(dh)
+    assert np.all((ratio > 0.15) & (ratio < 0.35)), ratio
