@@ -165,6 +165,12 @@ int l2b_su3_action_grad(const void* x, const double* coef, void* gx, int nb, con
  * gx = TAH(gforce)^+ dsdx,  dsdx = -(beta/3) A^+ */
 int l2b_su3_force_bwd(const void* x, double beta, const void* gforce, void* gx, int nb, const int dims[4], int dtype,
                       void* ws, size_t ws_bytes, void* stream);
+/* adjoints of the improved action / force (c1 != 0; what autograd does through lattice.py:96-112,252-269,299-308):
+ *   gforce_or_null == NULL:  gx = coef[b] Aimp^+,  Aimp = (1 - 8 c1) A + c1 R; coef[b] = -(beta/3) dL/dS[b]
+ *   gforce_or_null != NULL:  gx = TAH(gforce)^+ (scale Aimp^+), scale = -(beta/3)  (force adjoint at fixed dsdx) */
+int l2b_su3_action_grad_c1(const void* x, const double* coef_or_null, double scale, double c1,
+                           const void* gforce_or_null, void* gx, int nb, const int dims[4], int dtype, void* ws,
+                           size_t ws_bytes, void* stream);
 /* adjoint of l2b_su3_wilson_loops: gx from the cotangent gwloops[6, nb, T, X, Y, Z] complex of the
  * per-site loops (the reference back-propagates lattice.py:157-199 through 18 bmm + 12 roll) */
 int l2b_su3_wilson_loops_bwd(const void* x, const void* gwloops, void* gx, int nb, const int dims[4], int dtype,

@@ -44,6 +44,7 @@ _SIGS = {
     'l2b_su3_wilson_loops': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_plaq_sums': [_P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force': [_P, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
+    'l2b_su3_action_grad_c1': [_P, _P, c_double, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_c1': [_P, c_double, c_double, _P, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_exp': [_P, c_double, _P, c_size_t, c_int, _P],
     'l2b_su3_update_gauge': [_P, _P, c_double, _P, _P, c_int, _P, c_int, _DIMS, c_int, _P],

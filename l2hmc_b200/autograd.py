@@ -234,6 +234,40 @@ class SU3Force(torch.autograd.Function):
         return ops.su3_force_bwd(x.detach(), ctx.beta, gf.contiguous()).reshape(x.shape), None
 
 
+class SU3ActionC1(torch.autograd.Function):
+    """improved action S[b] = -(beta/3) [(1 - 8 c1) sum Re tr P + c1 sum Re tr R]
+    (lattice/su3/pytorch/lattice.py:96-112,252-269); dS/dU = -(beta/3) [(1 - 8 c1) A + c1 R]^+"""
+
+    @staticmethod
+    def forward(ctx, x, beta, c1):
+        ctx.save_for_backward(x)
+        ctx.beta, ctx.c1 = beta, c1
+        sums = ops.su3_force_c1(x.detach(), beta, c1, want_force=False, want_sums=True)
+        return ((1.0 - 8.0 * c1) * sums[:, 0] + c1 * sums[:, 1]) * (-beta / 3.0)
+
+    @staticmethod
+    def backward(ctx, gs):
+        x, = ctx.saved_tensors
+        gx = ops.su3_action_grad_c1(x.detach(), ctx.c1, coef=gs.to(torch.float64) * (-ctx.beta / 3.0))
+        return gx.reshape(x.shape), None, None
+
+
+class SU3ForceC1(torch.autograd.Function):
+    """improved-action force, same graph semantics as SU3Force (dsdx detached, `@ x^+` attached)"""
+
+    @staticmethod
+    def forward(ctx, x, beta, c1):
+        ctx.save_for_backward(x)
+        ctx.beta, ctx.c1 = beta, c1
+        return ops.su3_force_c1(x.detach(), beta, c1)
+
+    @staticmethod
+    def backward(ctx, gf):
+        x, = ctx.saved_tensors
+        gx = ops.su3_action_grad_c1(x.detach(), ctx.c1, scale=-ctx.beta / 3.0, gforce=gf.contiguous())
+        return gx.reshape(x.shape), None, None
+
+
 class SU3Kinetic(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p):

@@ -488,6 +488,22 @@ __global__ void __launch_bounds__(TS * 4, 2) k_force_c1(const C* __restrict__ U,
   }
 }
 
+// adjoint of the improved action (GF == nullptr: gx = coef[b] Aimp^+) and of the improved force at fixed dsdx
+// (GF != nullptr: gx = TAH(GF)^+ (scale Aimp^+)); Aimp = (1 - 8 c1) A + c1 R.  c1 != 0 counterpart of k_action_grad.
+template <int TS>
+__global__ void __launch_bounds__(TS * 4, 2) k_action_grad_c1(const C* __restrict__ U, C* __restrict__ G, Lat lat,
+                                                              const double* __restrict__ coef, double scale, double c1,
+                                                              const C* __restrict__ GF) {
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site = blockIdx.x * TS + threadIdx.x;
+  if (site >= lat.V) return;
+  Mat3<T> g, gf;
+  if (GF != nullptr) soa_load(gf, soa_plane(GF, lat, b, mu), lat.V, site);
+  improved_action_adjoint_link<T, C>(g, U, GF != nullptr ? &gf : nullptr, lat, b, mu, site, coef ? coef[b] : scale, c1);
+  soa_store(soa_plane(G, lat, b, mu), lat.V, site, g);
+}
+
 // adjoint of k_plaq<WRITE_LOOPS>: gx(mu,n) from the cotangent of the per-site loops
 template <int TS>
 __global__ void __launch_bounds__(TS * 4, 3) k_wloops_bwd(const C* __restrict__ U, const C* __restrict__ gw,
@@ -1647,6 +1663,24 @@ int l2b_su3_force_bwd(const void* x, double beta, const void* gforce, void* gx, 
   L2B_TRY(launch_a2s(g, (const C*)gforce, w.f2, nullptr, st));
   k_action_grad<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(w.f0, w.f1, g.lat, nullptr, -beta / 3.0, w.f2);
   L2B_LAUNCHED("k_action_grad<force_bwd>");
+  return launch_s2a(g, w.f1, (C*)gx, st);
+}
+
+int l2b_su3_action_grad_c1(const void* x, const double* coef_or_null, double scale, double c1,
+                           const void* gforce_or_null, void* gx, int nb, const int dims[4], int dtype, void* ws,
+                           size_t ws_bytes, void* stream) {
+  Geo g;
+  Ws w;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_TRY(carve(w, g, ws, ws_bytes));
+  L2B_REQUIRE(x && gx, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(coef_or_null || gforce_or_null, L2B_ERR_INVALID, "need coef (action adjoint) or gforce (force adjoint)");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_TRY(launch_a2s(g, (const C*)x, w.f0, nullptr, st));
+  if (gforce_or_null) L2B_TRY(launch_a2s(g, (const C*)gforce_or_null, w.f2, nullptr, st));
+  k_action_grad_c1<32><<<dim3((g.lat.V + 31) / 32, nb), dim3(32, 4), 0, st>>>(
+      w.f0, w.f1, g.lat, gforce_or_null ? nullptr : coef_or_null, scale, c1, gforce_or_null ? w.f2 : nullptr);
+  L2B_LAUNCHED("k_action_grad_c1");
   return launch_s2a(g, w.f1, (C*)gx, st);
 }
 

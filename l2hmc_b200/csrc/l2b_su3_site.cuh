@@ -575,4 +575,31 @@ L2B_HD void link_times_improved_staples(Mat3<T>& g, T& retr_p, T& retr_r, const 
   }
 }
 
+// Adjoint of the improved action / force at one link (the c1 != 0 counterpart of k_action_grad):
+//   gf == nullptr:  g = c * Aimp^+,                      Aimp = (1 - 8 c1) A + c1 R
+//   gf != nullptr:  g = TAH(gf)^+ (c * Aimp^+)           (force adjoint at fixed dsdx)
+template <typename T, typename C>
+L2B_HD void improved_action_adjoint_link(Mat3<T>& g, const C* U, const Mat3<T>* gf, const Lat& l, int b, int mu,
+                                         int site, T c, T c1) {
+  Mat3<T> ap, ar, ah;
+  link_times_staples<T, C, 0, false>(ap, U, l, b, mu, site);
+  rect_staples<T, C>(ar, U, l, b, mu, site);
+  const T cp = c * (T(1) - T(8) * c1), cr = c * c1;
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      ah.re[3 * i + j] = cp * ap.re[3 * j + i] + cr * ar.re[3 * j + i];
+      ah.im[3 * i + j] = -(cp * ap.im[3 * j + i] + cr * ar.im[3 * j + i]);
+    }
+  }
+  if (gf != nullptr) {
+    Mat3<T> th;
+    project_tah(th, *gf);
+    mat_mul<true, false, false>(g, th, ah);
+  } else {
+    g = ah;
+  }
+}
+
 }  // namespace l2b

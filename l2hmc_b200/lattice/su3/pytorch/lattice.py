@@ -40,6 +40,10 @@ class LatticeSU3(Lattice):
         # (l2b_su3_force_c1) wherever no autograd graph is needed (HMC, eval); under autograd (training) the
         # rectangle part runs as ATen ops.  L2B_RECT_KERNEL=0 forces the ATen path everywhere.
         self.rect_kernel = os.environ.get('L2B_RECT_KERNEL', '1') == '1'
+        # under autograd too (adjoint kernel l2b_su3_action_grad_c1, body pinned on torch autograd by
+        # tests/test_hostemu.py); opt-in until its launch has been run on a GPU
+        # (tests/test_gpu_su3.py::test_rectangle_kernel_gradients, L2B_RECT_KERNEL_AUTOGRAD=1)
+        self.rect_kernel_autograd = os.environ.get('L2B_RECT_KERNEL_AUTOGRAD', '0') == '1'
         super().__init__(group=self.g, nchains=nchains, shape=list(shape))
 
     def _field(self, x: Tensor) -> Tensor:
@@ -97,6 +101,8 @@ class LatticeSU3(Lattice):
         if self._use_rect_kernel(x):
             sums = ops.su3_force_c1(self._field(x), _f(beta), self.c1, want_force=False, want_sums=True)
             return (self.coeffs(beta)['plaq'] * sums[:, 0] + self.coeffs(beta)['rect'] * sums[:, 1]) * (-1.0 / 3.0)
+        if self.c1 != 0.0 and self.rect_kernel and self.rect_kernel_autograd:
+            return ag.SU3ActionC1.apply(self._field(x), _f(beta), self.c1)
         s = ag.SU3Action.apply(self._field(x), self.coeffs(beta)['plaq'])
         if self.c1 != 0.0:
             s = s + self._rect_action(x, beta)
@@ -157,6 +163,8 @@ class LatticeSU3(Lattice):
         (no create_graph) the result is a constant w.r.t. later backprop."""
         if self._use_rect_kernel(x):
             return ops.su3_force_c1(self._field(x), _f(beta), self.c1)
+        if self.c1 != 0.0 and self.rect_kernel and self.rect_kernel_autograd:
+            return ag.SU3ForceC1.apply(self._field(x), _f(beta), self.c1)
         f = ag.SU3Force.apply(self._field(x), self.coeffs(beta)['plaq'])
         if self.c1 != 0.0:
             f = f + self._rect_force(self._field(x), beta)

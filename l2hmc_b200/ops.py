@@ -578,6 +578,22 @@ def su3_action_grad(x: Tensor, coef: Tensor) -> Tensor:
     return gx
 
 
+def su3_action_grad_c1(x: Tensor, c1: float, coef: Optional[Tensor] = None, scale: float = 0.0,
+                       gforce: Optional[Tensor] = None) -> Tensor:
+    """improved action (c1 != 0): gx = coef[b] Aimp^+, or with `gforce` the force adjoint
+    TAH(gforce)^+ (scale Aimp^+); Aimp = (1 - 8 c1) A + c1 R"""
+    x, nb, dims = _su3_field(x)
+    if coef is not None:
+        coef = coef.to(torch.float64).contiguous()
+    if gforce is not None:
+        gforce, _, _ = _su3_field(gforce.to(torch.complex128), dims)
+    gx = torch.empty_like(x)
+    ws, n = _su3_ws(nb, dims, x.device)
+    call('l2b_su3_action_grad_c1', _ptr(x), _ptr(coef), float(scale), float(c1), _ptr(gforce), _ptr(gx), nb, dims4(dims),
+         L2B_F64, _ptr(ws), n, _stream())
+    return gx
+
+
 def su3_force_bwd(x: Tensor, beta: float, gforce: Tensor) -> Tensor:
     """gx = TAH(gforce)^+ dsdx with dsdx = -(beta/3) A^+ (one stencil kernel)"""
     x, nb, dims = _su3_field(x)

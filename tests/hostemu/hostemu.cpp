@@ -123,6 +123,22 @@ void emu_force_c1(const C* x, double beta, double c1, C* force, double* sums, in
     sums[2 * b + 1] = sr / 6.0;
   }
 }
+// improved-action adjoints: gx = coef[b] Aimp^+ (gf == NULL) or TAH(gf)^+ (scale Aimp^+)
+void emu_action_grad_c1(const C* x, const double* coef, double scale, double c1, const C* gf, C* gx, int nb,
+                        const int* dims) {
+  const Lat l = make_lat(dims[0], dims[1], dims[2], dims[3]);
+  std::vector<C> U;
+  to_soa(U, x, nb, l);
+  for (int b = 0; b < nb; ++b)
+    for (int mu = 0; mu < 4; ++mu)
+      for (int s = 0; s < l.V; ++s) {
+        const size_t li = ((size_t)b * 4 + mu) * l.V + s;
+        Mat3<T> g, f;
+        if (gf) aos_get(f, gf, li);
+        improved_action_adjoint_link<T, C>(g, U.data(), gf ? &f : nullptr, l, b, mu, s, gf ? scale : coef[b], c1);
+        aos_put(gx, li, g);
+      }
+}
 // the force through link_times_staples_hook (what the default kick kernels k_force_ep call): must be
 // bit-identical to link_times_staples; `hooks[b]` counts the hook invocations (one per link)
 void emu_force_hook(const C* x, double beta, C* force, long long* hooks, int hook_at, int nb, const int* dims) {

@@ -266,3 +266,25 @@ def test_rectangle_action_c1_matches_reference(golden_dir, kernel):
         assert maxdiff(host(met['acc']), g['hmc_acc']) < 1e-10
     finally:
         torch.set_default_dtype(old)
+
+
+@pytest.mark.skipif(__import__('os').environ.get('L2B_RECT_KERNEL_AUTOGRAD', '0') != '1',
+                    reason='opt-in until run on a GPU: L2B_RECT_KERNEL_AUTOGRAD=1')
+def test_rectangle_kernel_gradients(golden_dir):
+    """improved action under autograd on the adjoint kernel (l2b_su3_action_grad_c1) == the ATen-op path"""
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
+    lat = LatticeSU3(nb, shape, c1=c1)
+    gs = dev(np.array([0.7, -1.3]))
+    gf = dev(np.random.default_rng(2).standard_normal(g['x'].shape) + 0j)
+    res = {}
+    for flag in (False, True):
+        lat.rect_kernel_autograd = flag
+        x = dev(g['x']).requires_grad_(True)
+        s = lat.action(x, torch.tensor(beta))
+        f = lat.grad_action(x, torch.tensor(beta))
+        gx, = torch.autograd.grad([(s * gs).sum() + (f * gf.conj()).real.sum()], x)
+        res[flag] = (host(s), host(f), host(gx))
+    for a, b in zip(res[False], res[True]):
+        assert maxdiff(a, b) < 1e-11 * max(1.0, float(np.abs(a).max()))

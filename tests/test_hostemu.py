@@ -247,3 +247,50 @@ def test_trajectory_body_is_reversible_and_stays_in_the_group(emu):
     dh2 = (e3[:, 2] + e3[:, 3]) - (e3[:, 0] + e3[:, 1])
     ratio = np.abs(dh2) / np.abs(dh)
     assert np.all((ratio > 0.15) & (ratio < 0.35)), ratio
+
+
+def test_improved_action_adjoints_match_torch_autograd(emu, golden_dir):
+    """improved_action_adjoint_link (body of k_action_grad_c1) against torch autograd through a torch
+    restatement of the reference's c1 action (plaquettes + `_rect_traces`, lattice.py:96-112,252-269) and
+    through its force projectTAH(dsdx @ x^+) with dsdx detached (lattice.py:299-308)"""
+    import torch
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
+    lat = LatticeSU3(nb, shape, c1=c1)
+    dims = (ctypes.c_int * 4)(*shape)
+
+    def action(xt):      # S = -(beta/3) [(1 - 8 c1) sum Re tr P + c1 sum Re tr R]
+        tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)  # noqa: E731
+        ps = 0.0
+        for u in range(1, 4):
+            for v in range(u):
+                xu, xv = xt[:, u], xt[:, v]
+                p = tr(xu @ xv.roll(-1, dims=u + 1) @ (xv @ xu.roll(-1, dims=v + 1)).mH)
+                ps = ps + p.real.flatten(1).sum(1)
+        return -(beta / 3.0) * (1 - 8 * c1) * ps + lat._rect_action(xt, beta)
+    x = torch.from_numpy(g['x']).requires_grad_(True)
+    s = action(x)
+    assert np.allclose(s.detach().numpy(), g['action'], rtol=1e-12)
+    rng = np.random.default_rng(4)
+    gs = rng.standard_normal(nb)
+    want, = torch.autograd.grad(s, x, grad_outputs=torch.from_numpy(gs))
+    coef = np.ascontiguousarray(gs * (-beta / 3.0))
+    xn = np.ascontiguousarray(g['x'])
+    gx = np.empty_like(xn)
+    emu.emu_action_grad_c1(ptr(xn), ptr(coef), ctypes.c_double(0.0), ctypes.c_double(c1), None, ptr(gx), ctypes.c_int(nb), dims)
+    assert maxdiff(gx, want.numpy()) < 1e-12 * max(1.0, np.abs(want.numpy()).max())
+    # force adjoint at fixed dsdx
+    dsdx, = torch.autograd.grad(action(x).sum(), x)
+    x2 = torch.from_numpy(g['x']).requires_grad_(True)
+    y = dsdx.detach() @ x2.mH
+    a = 0.5 * (y - y.mH)
+    f = a - torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)[..., None, None] / 3.0 * torch.eye(3, dtype=a.dtype)
+    assert maxdiff(f.detach().numpy(), g['force']) < 1e-12
+    gf = np.ascontiguousarray(rng.standard_normal(xn.shape) + 1j * rng.standard_normal(xn.shape))
+    want2, = torch.autograd.grad(f, x2, grad_outputs=torch.from_numpy(gf))
+    want2 = want2.resolve_conj()
+    gx2 = np.empty_like(xn)
+    emu.emu_action_grad_c1(ptr(xn), None, ctypes.c_double(-beta / 3.0), ctypes.c_double(c1), ptr(gf), ptr(gx2),
+                           ctypes.c_int(nb), dims)
+    assert maxdiff(gx2, want2.numpy()) < 1e-12 * max(1.0, np.abs(want2.numpy()).max())
