@@ -404,9 +404,26 @@ class Dynamics(nn.Module):
         else:
             xp, vp, en = ops.u1_hmc_trajectory(state.x, state.v, beta, eps, nleapfrog, shape=self.config.latvolume)
             xp, vp = xp.reshape_as(state.v), vp.reshape_as(state.v)
-        dh = (en[:, 0] + en[:, 1]) - (en[:, 2] + en[:, 3]) + sumlogdet
-        acc = torch.exp(torch.minimum(dh, torch.zeros_like(dh)))
-        return State(x=xp, v=vp, beta=state.beta), {'acc': acc, 'sumlogdet': sumlogdet}
+        prop = State(x=xp, v=vp, beta=state.beta)
+        if self._potential_is_wilson():
+            dh = (en[:, 0] + en[:, 1]) - (en[:, 2] + en[:, 3]) + sumlogdet
+            acc = torch.exp(torch.minimum(dh, torch.zeros_like(dh)))
+        else:
+            # The reference integrates with the force of its own c1 = 0 lattice (dynamics.py:134,1499) but
+            # takes the energies of the accept step from `potential_fn` (dynamics.py:1489-1491): any other
+            # potential (improved action, user callable) decides the acceptance, not the kernel's Wilson sums.
+            acc = self.compute_accept_prob(state, prop, sumlogdet)
+        return prop, {'acc': acc, 'sumlogdet': sumlogdet}
+
+    def _potential_is_wilson(self) -> bool:
+        """True when `potential_fn` is the `action` of one of our lattices with the plain Wilson / U(1)
+        plaquette action, i.e. exactly the energies the trajectory kernels return (every shipped config)"""
+        owner = getattr(self.potential_fn, '__self__', None)
+        if getattr(self.potential_fn, '__name__', '') != 'action':
+            return False
+        if isinstance(owner, LatticeSU3):
+            return self._su3 and owner.c1 == 0.0
+        return isinstance(owner, LatticeU1) and not self._su3
 
     # --------------------------------------------------------------- L2HMC
     def _check_inference_only(self) -> None:

@@ -209,9 +209,20 @@ def su3_adjoint_goldens(ref, torch):
                              verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
     dyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
     sp, met = dyn.transition_kernel_hmc(ref.State(x=xr, v=vr, beta=b), eps=0.05, nleapfrog=3)
+    # a second trajectory from a smooth start (links exp(0.2 P) near the identity) with a short trajectory, so that
+    # dH > 0 and `acc` is not trivially 1 (a hot start only relaxes: dH << 0).  NB the reference's Dynamics
+    # integrates with the force of ITS OWN lattice (c1 = 0, dynamics.py:134,1499) and takes the energies from
+    # `potential_fn` (c1 != 0)
+    x2 = torch.linalg.matrix_exp(0.2 * lat.random_momentum()).detach()
+    v2 = lat.random_momentum()
+    st2 = ref.State(x=x2, v=v2, beta=b)
+    sp2, met2 = dyn.transition_kernel_hmc(st2, eps=0.01, nleapfrog=3)
     np.savez_compressed(GOLD / 'su3_c1_f64.npz', shape=np.array(shape), beta=beta, c1=c1, x=_np(xr), v=_np(vr),
                         rects=_np(rs), action=_np(lat.action(xr, b)), force=_np(lat.grad_action(xr.clone(), b)),
-                        hmc_x=_np(sp.x), hmc_v=_np(sp.v), hmc_acc=_np(met['acc']))
+                        hmc_x=_np(sp.x), hmc_v=_np(sp.v), hmc_acc=_np(met['acc']),
+                        hmc2_x0=_np(x2), hmc2_v0=_np(v2), hmc2_x=_np(sp2.x), hmc2_v=_np(sp2.v),
+                        hmc2_acc=_np(met2['acc']), hmc2_h0=_np(dyn.hamiltonian(st2)),
+                        hmc2_h1=_np(dyn.hamiltonian(ref.State(x=sp2.x.reshape(xr.shape), v=sp2.v, beta=b))))
 
 
 def u1_goldens(ref, torch, tag: str):

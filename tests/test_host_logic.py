@@ -65,3 +65,39 @@ def test_state_containers():
     assert set(d) == {'x', 'v', 'beta'} and d['x'].shape == (2, 3, 4) and float(d['beta']) == 1.5
     mc = dmod.MonteCarloStates(init=st, proposed=fl, out=fl)
     assert mc.init is st and mc.proposed is fl
+
+
+def test_hmc_accept_probability_comes_from_potential_fn_unless_it_is_the_kernel_action(monkeypatch):
+    """transition_kernel_hmc: the trajectory kernel's own (Wilson) energies are used only when `potential_fn` is
+    the plain action of one of our lattices; an improved action (c1 != 0) or any user callable goes through
+    `hamiltonian(potential_fn)` like the reference (dynamics.py:1065-1079,1489-1491)"""
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    nb = 2
+    en = torch.tensor([[1.0, 2.0, 1.5, 2.5], [1.0, 2.0, 0.5, 1.0]], dtype=torch.float64)
+
+    class FakeOps:
+        @staticmethod
+        def su3_hmc_trajectory(x, v, beta, eps, nlf):
+            return x + 1.0, v + 1.0, en
+    monkeypatch.setattr(dmod, 'ops', FakeOps)
+
+    def run(potential_fn):
+        fake = types.SimpleNamespace(
+            config=types.SimpleNamespace(eps_hmc=0.1, nleapfrog=2, merge_directions=True, verbose=False),
+            _su3=True, lattice=types.SimpleNamespace(c1=0.0), potential_fn=potential_fn, _fcache=None,
+            _zeros=lambda n: torch.zeros(n, dtype=torch.float64), unflatten=lambda t: t)
+        fake._potential_is_wilson = lambda: Dynamics._potential_is_wilson(fake)
+        fake.hamiltonian = lambda st: st.x.sum(1) * 0.1       # stands for KE + potential_fn
+        fake.compute_accept_prob = lambda a, b, sld: Dynamics.compute_accept_prob(fake, a, b, sld)
+        st = State(torch.zeros(nb, 3, dtype=torch.float64), torch.zeros(nb, 3, dtype=torch.float64), torch.tensor(6.0))
+        prop, met = Dynamics.transition_kernel_hmc(fake, st)
+        assert torch.equal(prop.x, st.x + 1.0) and torch.equal(met['sumlogdet'], torch.zeros(nb, dtype=torch.float64))
+        return met['acc'].numpy()
+    kernel_acc = np.exp(np.minimum(np.array([3.0 - 4.0, 3.0 - 1.5]), 0.0))
+    potential_acc = np.exp(np.minimum(np.array([0.0 - 0.3, 0.0 - 0.3]), 0.0))
+    assert np.allclose(run(LatticeSU3(nb, [2, 2, 2, 2]).action), kernel_acc)
+    assert np.allclose(run(LatticeSU3(nb, [2, 2, 2, 2], c1=-0.331).action), potential_acc)
+    assert np.allclose(run(lambda x, b: x.sum()), potential_acc)
+    assert np.allclose(run(LatticeU1(nb, [4, 4]).action), potential_acc)      # a U(1) potential on an SU(3) run
+    assert np.allclose(run(LatticeSU3(nb, [2, 2, 2, 2]).kinetic_energy), potential_acc)

@@ -143,3 +143,25 @@ def test_su3_rectangle_action_oracle_matches_reference(golden_dir):
     assert maxdiff(osu3.rect_traces(g['x']), g['rects']) < 1e-13
     got = osu3.action(g['x'], float(g['beta']), float(g['c1']))
     assert np.all(np.abs(got - g['action']) <= 1e-12 * np.abs(g['action']))
+
+
+def test_su3_hmc_with_improved_action_uses_the_wilson_force(golden_dir):
+    """Reference semantics pinned: `Dynamics` integrates with the force of ITS OWN lattice, built with the
+    default c1 = 0 (dynamics.py:134,1499), while the energies of the accept step come from `potential_fn`
+    (here the c1 = -0.331 action, dynamics.py:1489-1491).  The oracle's plain-Wilson trajectory reproduces the
+    reference's proposal, and the accept probability follows from the improved action."""
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    beta, c1 = float(g['beta']), float(g['c1'])
+    x0, v0 = g['hmc2_x0'], g['hmc2_v0']
+    s, _ = od.transition_kernel_hmc(od.SU3Ops, od.State(x0, v0, beta), 0.01, 3)
+    assert maxdiff(s.x.reshape(x0.shape), g['hmc2_x'].reshape(x0.shape)) < 1e-12
+    assert maxdiff(s.v.reshape(x0.shape), g['hmc2_v'].reshape(x0.shape)) < 1e-12
+    h0 = osu3.kinetic_energy(v0) + osu3.action(x0, beta, c1)
+    h1 = osu3.kinetic_energy(s.v.reshape(x0.shape)) + osu3.action(s.x.reshape(x0.shape), beta, c1)
+    assert np.allclose(h0, g['hmc2_h0'], rtol=1e-12) and np.allclose(h1, g['hmc2_h1'], rtol=1e-12)
+    acc = np.exp(np.minimum(h0 - h1, 0.0))
+    assert np.allclose(acc, g['hmc2_acc'], rtol=1e-9) and 0 < acc.min() < 0.01 < acc.max() < 1
+    # with the Wilson energies the accept probability would be a different number
+    hw0 = osu3.kinetic_energy(v0) + osu3.action(x0, beta)
+    hw1 = osu3.kinetic_energy(s.v.reshape(x0.shape)) + osu3.action(s.x.reshape(x0.shape), beta)
+    assert not np.allclose(np.exp(np.minimum(hw0 - hw1, 0.0)), g['hmc2_acc'], rtol=1e-3)
