@@ -36,6 +36,6 @@ def test_hmc_accepts_with_the_energies_of_potential_fn(golden_dir, kernel):
         assert np.abs(xp - g['hmc2_x'].reshape(xp.shape)).max() < 1e-12
         assert np.abs(vp - g['hmc2_v'].reshape(vp.shape)).max() < 1e-12
         assert np.allclose(h0.cpu().numpy(), g['hmc2_h0'], rtol=1e-12)
-        assert np.allclose(met['acc'].cpu().numpy(), g['hmc2_acc'], rtol=1e-8)
+        assert np.allclose(met['acc'].cpu().numpy(), g['hmc2_acc'], rtol=1e-7)     # |H| ~ 4e3 at 1e-12 relative
     finally:
         torch.set_default_dtype(old)
