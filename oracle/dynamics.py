@@ -310,3 +310,99 @@ def transition_kernel_fb(spec: L2HMCSpec, s: State):
     acc = accept_prob(spec.g, State(_unflatten(spec, s.x), s.v, s.beta),
                       State(_unflatten(spec, s_.x), s_.v, s_.beta), sumlogdet)
     return s_, acc, sumlogdet
+
+
+def transition_kernel(spec: L2HMCSpec, s: State, forward: bool):
+    """dynamics.py:1031-1063, the un-merged kernel (merge_directions = False): nlf forward OR backward
+    leapfrog layers.  NB the reference passes the states to `compute_accept_prob` SWAPPED
+    (state_init = the final state, state_prop = the initial one, :1053-1057) -> (proposed, acc, sumlogdet)"""
+    nb = s.x.shape[0]
+    sumlogdet = np.zeros(nb)
+    lf = forward_lf if forward else backward_lf
+    s_ = State(s.x, s.v, s.beta)
+    for step in range(spec.nleapfrog):
+        s_, ld = lf(spec, step, s_)
+        sumlogdet = sumlogdet + ld
+    acc = accept_prob(spec.g, State(_unflatten(spec, s_.x), s_.v, s_.beta),
+                      State(_unflatten(spec, s.x), s.v, s.beta), sumlogdet)
+    return s_, acc, sumlogdet
+
+
+def _metrics(spec: L2HMCSpec, s: State, logdet, extras=None, step=None):
+    """get_metrics (dynamics.py:865-887)"""
+    energy = hamiltonian(spec.g, State(_unflatten(spec, s.x), s.v, s.beta))
+    m = {'energy': energy, 'logprob': energy - logdet, 'logdet': logdet}
+    if extras:
+        m.update(extras)
+    if step is not None:
+        m.update({'xeps': spec.xeps[step], 'veps': spec.veps[step]})
+    return m
+
+
+def _push(history: dict, metrics: dict):
+    for k, v in metrics.items():
+        history.setdefault(k, []).append(v)
+
+
+def _stacked(history: dict) -> dict:
+    return {k: (np.stack([np.asarray(e) for e in v]) if isinstance(v, list) else v) for k, v in history.items()}
+
+
+def transition_kernel_fb_verbose(spec: L2HMCSpec, s: State):
+    """transition_kernel_fb with config.verbose (dynamics.py:956-1029): the per-step metrics, recorded before the
+    first layer and after each of the 2 nlf layers -> (proposed, history with [2 nlf + 1, nb] stacks)"""
+    nb = s.x.shape[0]
+    sumlogdet, sldf, sldb = np.zeros(nb), np.zeros(nb), np.zeros(nb)
+    s_ = State(s.x, s.v, s.beta)
+    h: dict = {}
+    _push(h, _metrics(spec, s_, sumlogdet, {'sldf': sldf, 'sldb': sldb, 'sld': sumlogdet}, step=0))
+    for step in range(spec.nleapfrog):
+        s_, ld = forward_lf(spec, step, s_)
+        sumlogdet = sumlogdet + ld
+        sldf = sldf + ld
+        _push(h, _metrics(spec, s_, sumlogdet, {'sldf': sldf, 'sldb': sldb, 'sld': sumlogdet}, step=step))
+    s_ = State(s_.x, -s_.v, s_.beta)
+    for step in range(spec.nleapfrog):
+        s_, ld = backward_lf(spec, step, s_)
+        sumlogdet = sumlogdet + ld
+        sldb = sldb + ld
+        _push(h, _metrics(spec, s_, sumlogdet, {'sldf': np.zeros(nb), 'sldb': sldb, 'sld': sumlogdet},
+                          step=spec.nleapfrog - step - 1))
+    acc = accept_prob(spec.g, State(_unflatten(spec, s.x), s.v, s.beta),
+                      State(_unflatten(spec, s_.x), s_.v, s_.beta), sumlogdet)
+    h.update({'acc': acc, 'sumlogdet': sumlogdet})
+    return s_, _stacked(h)
+
+
+def transition_kernel_verbose(spec: L2HMCSpec, s: State, forward: bool):
+    """transition_kernel with config.verbose (dynamics.py:1031-1063)"""
+    nb = s.x.shape[0]
+    sumlogdet = np.zeros(nb)
+    lf = forward_lf if forward else backward_lf
+    s_ = State(s.x, s.v, s.beta)
+    h: dict = {}
+    _push(h, _metrics(spec, s_, sumlogdet))
+    for step in range(spec.nleapfrog):
+        s_, ld = lf(spec, step, s_)
+        sumlogdet = sumlogdet + ld
+        _push(h, _metrics(spec, s_, sumlogdet, step=step))
+    acc = accept_prob(spec.g, State(_unflatten(spec, s_.x), s_.v, s_.beta),
+                      State(_unflatten(spec, s.x), s.v, s.beta), sumlogdet)
+    h.update({'acc': acc, 'sumlogdet': sumlogdet})
+    return s_, _stacked(h)
+
+
+def transition_kernel_hmc_verbose(spec: L2HMCSpec, s: State, eps: float, nleapfrog: int):
+    """transition_kernel_hmc with config.verbose (dynamics.py:915-954): energies after every leapfrog step"""
+    nb = s.x.shape[0]
+    zeros = np.zeros(nb, dtype=s.v.real.dtype)
+    xshape = s.x.shape
+    s_ = State(s.x, s.v, s.beta)
+    h: dict = {}
+    _push(h, _metrics(spec, s_, zeros))
+    for _ in range(nleapfrog):
+        s_ = leapfrog_hmc(spec.g, s_, eps, xshape)
+        _push(h, _metrics(spec, s_, zeros))
+    acc = accept_prob(spec.g, s, State(s_.x.reshape(xshape), s_.v, s_.beta), zeros)
+    h.update({'acc': acc, 'sumlogdet': zeros})
+    return s_, _stacked(h)

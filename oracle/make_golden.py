@@ -309,6 +309,29 @@ def u1_goldens(ref, torch, tag: str):
             out[pre + 'lattice_loss'] = _np(ref.LatticeLoss(lat, lcfg)(x_init=x, x_prop=sp.x, acc=met['acc']))
             lcfg2 = ref.cfgs.LossConfig(use_mixed_loss=False, charge_weight=0.05, rmse_weight=0.0, plaq_weight=0.0)
             out[pre + 'lattice_loss2'] = _np(ref.LatticeLoss(lat, lcfg2)(x_init=x, x_prop=sp.x, acc=met['acc']))
+        if name == 'dense':
+            # the un-merged kernel (merge_directions = False: dynamics.py:1031-1063, note the swapped states in
+            # its accept probability) and the verbose per-step metrics (dynamics.py:865-898,956-1029)
+            for key, fwd in (('tkf', True), ('tkb', False)):
+                sk, mk = dyn.transition_kernel(st, forward=fwd)
+                out[f'{pre}{key}_x'], out[f'{pre}{key}_v'] = _np(sk.x), _np(sk.v)
+                out[f'{pre}{key}_acc'], out[f'{pre}{key}_sumlogdet'] = _np(mk['acc']), _np(mk['sumlogdet'])
+            cfgv = ref.DynamicsConfig(
+                nchains=nb, group='U1', latvolume=shape, nleapfrog=nlf, eps=0.1, eps_hmc=0.1, use_ncp=True,
+                verbose=True, use_split_xnets=True, use_separate_networks=True, merge_directions=True)
+            dynv = ref.Dynamics(potential_fn=lat.action, config=cfgv, network_factory=fac)
+            dynv.load_state_dict(dyn.state_dict())
+            dynv.masks = dyn.masks
+            dynv.eval()
+            for key, (sv, hv) in (('vfb', dynv.transition_kernel_fb(st)),
+                                  ('vtk', dynv.transition_kernel(st, forward=True)),
+                                  ('vhmc', dynv.transition_kernel_hmc(st, eps=0.1, nleapfrog=3))):
+                out[f'{pre}{key}_x'] = _np(sv.x)
+                for hk, hval in hv.items():
+                    if isinstance(hval, torch.Tensor):
+                        out[f'{pre}{key}/{hk}'] = _np(hval)
+                    elif isinstance(hval, list):          # xeps / veps: lists of 0-dim parameters
+                        out[f'{pre}{key}/{hk}'] = np.array([float(e) for e in hval])
     np.savez_compressed(GOLD / f'u1_{tag}.npz', **out)
 
 

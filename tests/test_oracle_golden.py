@@ -165,3 +165,35 @@ def test_su3_hmc_with_improved_action_uses_the_wilson_force(golden_dir):
     hw0 = osu3.kinetic_energy(v0) + osu3.action(x0, beta)
     hw1 = osu3.kinetic_energy(s.v.reshape(x0.shape)) + osu3.action(s.x.reshape(x0.shape), beta)
     assert not np.allclose(np.exp(np.minimum(hw0 - hw1, 0.0)), g['hmc2_acc'], rtol=1e-3)
+
+
+@pytest.mark.parametrize('tag,tol', [('f64', 1e-12), ('f32', 2e-5)])
+def test_u1_unmerged_kernel_and_verbose_histories(golden_dir, tag, tol):
+    """transition_kernel (merge_directions = False, swapped states in the accept probability) and the
+    verbose per-step metrics of all three kernels (dynamics.py:865-898,915-1063) against the reference"""
+    gu = np.load(golden_dir / f'u1_{tag}.npz')
+    pre = 'dense/'
+    sd = {k[len(pre) + 3:]: gu[k] for k in gu.files if k.startswith(pre + 'sd/')}
+    spec = od.L2HMCSpec(group='U1', xshape=(3, 2, *[int(s) for s in gu['shape']]), nleapfrog=2,
+                        xeps=list(gu[pre + 'xeps']), veps=list(gu[pre + 'veps']), masks=list(gu[pre + 'masks']),
+                        state_dict=sd, activation='leaky_relu', use_batch_norm=True)
+    st = od.State(gu['x'], gu[pre + 'v'], float(gu['beta']))
+    for key, fwd in (('tkf', True), ('tkb', False)):
+        sp, acc, sld = od.transition_kernel(spec, st, fwd)
+        assert maxdiff(sp.x.reshape(gu[f'{pre}{key}_x'].shape), gu[f'{pre}{key}_x']) <= 50 * tol
+        assert maxdiff(sp.v, gu[f'{pre}{key}_v']) <= 50 * tol
+        assert maxdiff(sld, gu[f'{pre}{key}_sumlogdet']) <= 50 * tol
+        assert maxdiff(acc, gu[f'{pre}{key}_acc']) <= 200 * tol
+    # swapped: the un-merged acc is exp(min(H_final - H_init + sld, 0)), not the usual H_init - H_final
+    usual = od.accept_prob(spec.g, st, od.State(sp.x.reshape(st.x.shape), sp.v, st.beta), sld)
+    assert maxdiff(usual, gu[pre + 'tkb_acc']) > 1e-3
+    htol = 500 * tol * max(1.0, float(np.abs(gu[pre + 'vfb/energy']).max()))
+    for key, (sp, h) in (('vfb', od.transition_kernel_fb_verbose(spec, st)),
+                         ('vtk', od.transition_kernel_verbose(spec, st, True)),
+                         ('vhmc', od.transition_kernel_hmc_verbose(spec, st, 0.1, 3))):
+        want = {k[len(pre) + len(key) + 1:]: gu[k] for k in gu.files if k.startswith(f'{pre}{key}/')}
+        assert set(want) == set(h), (key, sorted(set(want) ^ set(h)))
+        for k, w in want.items():
+            assert np.shape(h[k]) == w.shape, (key, k, np.shape(h[k]), w.shape)
+            assert maxdiff(h[k], w) <= htol, (key, k)
+        assert maxdiff(sp.x.reshape(gu[f'{pre}{key}_x'].shape), gu[f'{pre}{key}_x']) <= 50 * tol
