@@ -89,3 +89,30 @@ def test_verbose_histories_match_reference(golden_dir, tag, tol):
             assert maxdiff(host(sp.x).reshape(gu[f'{pre}{key}_x'].shape), gu[f'{pre}{key}_x']) <= 50 * tol
     finally:
         torch.set_default_dtype(old)
+
+
+def test_forward_without_merge_directions_goes_through_apply_transition(golden_dir):
+    """`Dynamics.forward` with merge_directions = False (dynamics.py:616-627,704-742): one random direction,
+    accept/reject mix, the metrics contract; every output chain is either its proposal or its input"""
+    from l2hmc_b200.dynamics.pytorch.dynamics import State  # noqa: F401
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        gu = np.load(golden_dir / 'u1_f64.npz')
+        dyn = _dynamics(gu, verbose=False)
+        dyn.config.merge_directions = False
+        x, beta = dev(gu['x']), torch.tensor(float(gu['beta']))
+        torch.manual_seed(5)
+        with torch.no_grad():
+            xout, met = dyn((x, beta))
+        nb = x.shape[0]
+        assert tuple(xout.shape) == (nb, dyn.xdim)
+        assert met['acc_mask'].dtype == torch.float32 and tuple(met['acc'].shape) == (nb,)
+        mc = met['mc_states']
+        xo, xp, xi = host(xout), host(mc.proposed.x).reshape(nb, -1), host(mc.init.x).reshape(nb, -1)
+        ma = host(met['acc_mask'])
+        for b in range(nb):
+            assert np.array_equal(xo[b], xp[b] if ma[b] == 1.0 else xi[b])
+        assert np.array_equal(host(met['sumlogdet']) != 0, (ma == 1.0) & (host(met['sumlogdet']) != 0))
+    finally:
+        torch.set_default_dtype(old)
