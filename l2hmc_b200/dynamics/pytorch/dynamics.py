@@ -78,6 +78,17 @@ def sigmoid(x: Tensor) -> Tensor:
     return 1. / (1. + torch.exp(-x))
 
 
+class Mask:
+    """m and its complement 1 - m (dynamics.py:102-110; unused by the reference's own integrator)"""
+
+    def __init__(self, m: Tensor):
+        self.m = m
+        self.mb = torch.ones_like(self.m) - self.m
+
+    def combine(self, x: Tensor, y: Tensor) -> Tensor:
+        return self.m * x + self.mb * y
+
+
 def _fbeta(beta) -> float:
     return float(beta.detach()) if isinstance(beta, torch.Tensor) else float(beta)
 

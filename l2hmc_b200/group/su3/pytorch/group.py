@@ -186,6 +186,18 @@ class SU3(Group):
     def compat_proj(self, x: Tensor) -> Tensor:
         return ag.SU3Project.apply(x)
 
+    def compat_proju(self, u: Tensor, x: Tensor) -> Tensor:
+        """group.py:149-165: solve u A = x for the FIRST matrix of the batch only (the reference indexes the
+        solution with [0] and lets the rest broadcast), then the traceless anti-Hermitian part of A.
+        Off the integrator path (nothing in the reference calls it): plain torch."""
+        n = x.shape[-1]
+        a = torch.linalg.solve(u, x)[0]
+        b = (a - a.mH) / 2.
+        tr = torch.einsum('...ii->...', b)
+        b = b - (tr / n)[..., None, None] * torch.eye(n, dtype=b.dtype, device=b.device)
+        assert torch.abs(torch.einsum('...ii->...', b).mean()) < 1e-6
+        return b
+
     def kinetic_energy(self, p: Tensor) -> Tensor:
         """0.5 * sum(|P|_F^2 - 8)   (group.py:125-126)"""
         return ag.SU3Kinetic.apply(p)

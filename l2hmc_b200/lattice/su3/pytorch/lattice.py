@@ -64,25 +64,71 @@ class LatticeSU3(Lattice):
         """ps[6, nb, T, X, Y, Z]   (lattice.py:157-199,242-244); differentiable"""
         return ag.SU3WilsonLoops.apply(self._field(x))
 
+    # -- matrix-valued loop fields: debugging / analysis API of the reference, off the integrator path ---------
+    def _link_staple_op(self, link: Tensor, staple: Tensor) -> Tensor:
+        """lattice.py:93-94"""
+        return self.g.mul(link, staple)
+
+    def _plaquette(self, x: Tensor, u: int, v: int) -> Tensor:
+        """U_u(n) U_v(n+u) U_u(n+v)^+ U_v(n)^+ as a matrix field [nb, T, X, Y, Z, 3, 3] (lattice.py:114-126)"""
+        x = self._field(x)
+        xu, xv = x[:, u], x[:, v]
+        return (xu @ xv.roll(-1, dims=u + 1)) @ (xv @ xu.roll(-1, dims=v + 1)).mH
+
+    def _trace_plaquette(self, x: Tensor, u: int, v: int) -> Tensor:
+        """lattice.py:128-130"""
+        return self.g.trace(self._plaquette(x, u, v))
+
+    def _rectangles(self, x: Tensor, u: int, v: int) -> tuple[Tensor, Tensor]:
+        """the 2x1 (two steps along u) and 1x2 rectangle matrices of plane (u, v), built from the four
+        three-link staples of the plaquette exactly as the reference does (lattice.py:96-112)"""
+        x = self._field(x)
+        xu, xv = x[:, u], x[:, v]
+        su, sv = u + 1, v + 1                           # tensor axes of the two directions
+        fwd_uv = xu @ xv.roll(-1, dims=su)              # U_u(n) U_v(n+u)
+        fwd_vu = xv @ xu.roll(-1, dims=sv)              # U_v(n) U_u(n+v)
+        open_v = xv.mH @ fwd_uv                         # U_v(n)^+ U_u(n) U_v(n+u)
+        open_u = xu.mH @ fwd_vu                         # U_u(n)^+ U_v(n) U_u(n+v)
+        cap_u = fwd_uv @ xu.roll(-1, dims=sv).mH        # U_u(n) U_v(n+u) U_u(n+v)^+
+        cap_v = fwd_vu @ xv.roll(-1, dims=su).mH        # U_v(n) U_u(n+v) U_v(n+u)^+
+        return open_u @ cap_u.roll(-1, dims=su).mH, open_v @ cap_v.roll(-1, dims=sv).mH
+
+    def _plaquette_field(self, x: Tensor, needs_rect: bool = False) -> tuple[list, list]:
+        """six plaquette matrix fields (planes u > v in the reference's order) and the twelve rectangle
+        fields, zeros unless `needs_rect` (lattice.py:132-156)"""
+        x = self._field(x)
+        plaqs, rects = [], []
+        for u in range(1, self.dim):
+            for v in range(u):
+                plaq = self._plaquette(x, u, v)
+                plaqs.append(plaq)
+                rects.extend(self._rectangles(x, u, v) if needs_rect
+                             else (torch.zeros_like(plaq), torch.zeros_like(plaq)))
+        return plaqs, rects
+
     def _rect_traces(self, x: Tensor) -> Tensor:
-        """traces of the 2x1 and 1x2 rectangles, rs[12, nb, T, X, Y, Z], exactly the reference's
-        sequence of products and rolls (lattice.py:96-112,180-196).  The rectangle (c1 != 0) term
-        is off in every shipped config, so it runs as ATen ops on the GPU (differentiable by
-        torch), not as a hand-written kernel."""
+        """traces of the 2x1 and 1x2 rectangles, rs[12, nb, T, X, Y, Z] (lattice.py:180-196), as ATen ops:
+        the differentiable form used under autograd; HMC / eval use the rectangle-staple kernel
+        (`l2b_su3_force_c1`)"""
         x = self._field(x)
         rs = []
-        tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)  # noqa: E731
         for u in range(1, 4):
             for v in range(0, u):
-                xu, xv = x[:, u], x[:, v]
-                yuv = xu @ xv.roll(-1, dims=u + 1)
-                yvu = xv @ xu.roll(-1, dims=v + 1)
-                yu, yv = xu.roll(-1, dims=v + 1), xv.roll(-1, dims=u + 1)
-                uu, ur = xv.mH @ yuv, xu.mH @ yvu
-                ul, ud = yuv @ yu.mH, yvu @ yv.mH
-                rs.append(tr(ur @ ul.roll(-1, dims=u + 1).mH))
-                rs.append(tr(uu @ ud.roll(-1, dims=v + 1).mH))
+                r21, r12 = self._rectangles(x, u, v)
+                rs.append(self.g.trace(r21))
+                rs.append(self.g.trace(r12))
         return torch.stack(rs)
+
+    def plaq_loss(self, acc: Tensor, x1: Optional[Tensor] = None, x2: Optional[Tensor] = None,
+                  wloops1: Optional[Tensor] = None, wloops2: Optional[Tensor] = None):
+        """a TODO stub in the reference (lattice.py:351-359): nothing is computed there either; the SU(3) loss
+        terms live in `LatticeLoss` (loss/pytorch/loss.py)"""
+        return None
+
+    def charge_loss(self, acc: Tensor, x1: Optional[Tensor] = None, x2: Optional[Tensor] = None,
+                    wloops1: Optional[Tensor] = None, wloops2: Optional[Tensor] = None):
+        """a TODO stub in the reference (lattice.py:361-369)"""
+        return None
 
     def _rect_action(self, x: Tensor, beta) -> Tensor:
         """-(beta c1 / 3) sum Re tr R"""

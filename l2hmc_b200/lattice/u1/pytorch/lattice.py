@@ -132,12 +132,40 @@ class LatticeU1(Lattice):
             - xv.roll(-4, dims=1) - xv.roll(-3, dims=1) - xv.roll(-2, dims=1) - xv.roll(-1, dims=1) - xv
         ).T
 
+    def _plaqs4x4(self, wloops4x4: Tensor) -> Tensor:
+        """lattice.py:205-206"""
+        return wloops4x4.cos().mean((1, 2))
+
     def plaqs4x4(self, x: Optional[Tensor] = None, wloops4x4: Optional[Tensor] = None) -> Tensor:
         if wloops4x4 is None:
             if x is None:
                 raise ValueError('One of `x` or `wloops` must be specified.')
             wloops4x4 = self.wilson_loops4x4(x)
-        return wloops4x4.cos().mean((1, 2))
+        return self._plaqs4x4(wloops4x4)
+
+    def _get_wloops(self, x: Optional[Tensor] = None) -> Tensor:
+        """lattice.py:230-236"""
+        if x is None:
+            raise ValueError('One of `x` or `wloops` must be specified.')
+        return self.wilson_loops(x)
+
+    def draw_uniform_batch(self, requires_grad: bool = True) -> Tensor:
+        """a batch of configurations uniform in (-pi, pi)   (lattice.py:67-71), on the GPU"""
+        return self.g.random(list(self._shape)).detach().requires_grad_(requires_grad)
+
+    def plaq_loss(self, acc: Tensor, x1: Optional[Tensor] = None, x2: Optional[Tensor] = None,
+                  wl1: Optional[Tensor] = None, wl2: Optional[Tensor] = None) -> Tensor:
+        """-mean_b[ acc * sum 2 (1 - cos(w2 - w1)) + 1e-4 ]   (lattice.py:278-292)"""
+        w1 = self._get_wloops(x1) if wl1 is None else wl1
+        w2 = self._get_wloops(x2) if wl2 is None else wl2
+        return -(acc * (2. * (1. - (w2 - w1).cos())).sum((1, 2)) + 1e-4).mean(0)
+
+    def charge_loss(self, acc: Tensor, x1: Optional[Tensor] = None, x2: Optional[Tensor] = None,
+                    wl1: Optional[Tensor] = None, wl2: Optional[Tensor] = None) -> Tensor:
+        """-mean_b[ acc * (sinQ2 - sinQ1)^2 + 1e-4 ]   (lattice.py:294-308)"""
+        w1 = self._get_wloops(x1) if wl1 is None else wl1
+        w2 = self._get_wloops(x2) if wl2 is None else wl2
+        return -(acc * (self._sin_charges(w2) - self._sin_charges(w1)) ** 2 + 1e-4).mean(0)
 
     def observables(self, x: Tensor) -> LatticeMetrics:
         wloops = self.wilson_loops(x)

@@ -101,3 +101,51 @@ def test_hmc_accept_probability_comes_from_potential_fn_unless_it_is_the_kernel_
     assert np.allclose(run(lambda x, b: x.sum()), potential_acc)
     assert np.allclose(run(LatticeU1(nb, [4, 4]).action), potential_acc)      # a U(1) potential on an SU(3) run
     assert np.allclose(run(LatticeSU3(nb, [2, 2, 2, 2]).kinetic_energy), potential_acc)
+
+
+def test_matrix_valued_loop_fields_of_the_su3_lattice(golden_dir):
+    """`_plaquette`, `_trace_plaquette`, `_rectangles`, `_plaquette_field` (lattice.py:93-156): torch code off the
+    integrator path, runs on the CPU; traces must reproduce the reference's loops / rectangle goldens"""
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    shape, nb = [int(s) for s in g['shape']], g['x'].shape[0]
+    lat = LatticeSU3(nb, shape, c1=float(g['c1']))
+    x = torch.from_numpy(g['x'])
+    plaqs, rects = lat._plaquette_field(x.reshape(nb, -1), needs_rect=True)
+    assert len(plaqs) == 6 and len(rects) == 12 and tuple(plaqs[0].shape) == (nb, *shape, 3, 3)
+    tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1).numpy()  # noqa: E731
+    assert np.abs(np.stack([tr(r) for r in rects]) - g['rects']).max() < 1e-13
+    from oracle import su3 as osu3
+    assert np.abs(np.stack([tr(p) for p in plaqs]) - osu3.wilson_loops(g['x'])).max() < 1e-13
+    assert np.abs(lat._trace_plaquette(x, 2, 1).numpy() - osu3.wilson_loops(g['x'])[2]).max() < 1e-13
+    _, zeros = lat._plaquette_field(x)
+    assert all(float(z.abs().max()) == 0.0 for z in zeros)
+    assert torch.equal(lat._link_staple_op(x[:, 0], x[:, 1]), x[:, 0] @ x[:, 1])
+    assert lat.plaq_loss(torch.ones(nb)) is None and lat.charge_loss(torch.ones(nb)) is None   # TODO stubs upstream
+    m = dmod.Mask(torch.tensor([1.0, 0.0, 1.0]))
+    assert torch.equal(m.combine(torch.tensor([1.0, 2.0, 3.0]), torch.tensor([7.0, 8.0, 9.0])), torch.tensor([1.0, 8.0, 3.0]))
+
+
+def test_u1_lattice_loss_helpers_and_compat_proju():
+    """LatticeU1.plaq_loss / charge_loss / _plaqs4x4 with explicit Wilson loops (lattice.py:205-206,278-308) and
+    SU3.compat_proju (group.py:149-165): closed forms, CPU"""
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from l2hmc_b200.group.su3.pytorch.group import SU3
+    lat = LatticeU1(2, [4, 4])
+    rng = np.random.default_rng(1)
+    w1, w2 = torch.from_numpy(rng.uniform(-3, 3, (2, 4, 4))), torch.from_numpy(rng.uniform(-3, 3, (2, 4, 4)))
+    acc = torch.tensor([0.25, 1.0], dtype=torch.float64)
+    want = -np.mean(acc.numpy() * (2 * (1 - np.cos((w2 - w1).numpy()))).sum((1, 2)) + 1e-4)
+    assert float(lat.plaq_loss(acc, wl1=w1, wl2=w2)) == pytest.approx(want, rel=1e-14)
+    q1, q2 = np.sin(w1.numpy()).sum((1, 2)) / (2 * np.pi), np.sin(w2.numpy()).sum((1, 2)) / (2 * np.pi)
+    assert float(lat.charge_loss(acc, wl1=w1, wl2=w2)) == pytest.approx(-np.mean(acc.numpy() * (q2 - q1) ** 2 + 1e-4), rel=1e-13)
+    assert np.allclose(lat._plaqs4x4(w1).numpy(), np.cos(w1.numpy()).mean((1, 2)))
+    with pytest.raises(ValueError):
+        lat._get_wloops(None)
+    u = torch.from_numpy(rng.standard_normal((3, 3, 3)) + 1j * rng.standard_normal((3, 3, 3)))
+    xm = torch.from_numpy(rng.standard_normal((3, 3, 3)) + 1j * rng.standard_normal((3, 3, 3)))
+    b = SU3().compat_proju(u, xm)
+    a0 = np.linalg.solve(u.numpy()[0], xm.numpy()[0])
+    b0 = (a0 - a0.conj().T) / 2
+    b0 = b0 - np.trace(b0) / 3 * np.eye(3)
+    assert np.abs(b.numpy() - b0).max() < 1e-13 and abs(np.trace(b.numpy())) < 1e-13
