@@ -74,6 +74,21 @@ class MonteCarloStates:
     out: State
 
 
+def rand_unif(shape: Shape, a: float, b: float, requires_grad: bool) -> Tensor:
+    """uniform samples between a and b (dynamics.py:86-94)"""
+    return ((a - b) * torch.rand(tuple(shape)) + b).detach().requires_grad_(requires_grad)
+
+
+def random_angle(shape: Shape, requires_grad: bool = True) -> Tensor:
+    """angles uniform in (-pi, pi)   (dynamics.py:97-99)"""
+    return rand_unif(shape, -PI, PI, requires_grad=requires_grad)
+
+
+def to_u1(x: Tensor) -> Tensor:
+    """wrap to [-pi, pi)   (dynamics.py:77-79)"""
+    return ((x + PI) % TWO_PI) - PI
+
+
 def sigmoid(x: Tensor) -> Tensor:
     return 1. / (1. + torch.exp(-x))
 

@@ -23,6 +23,16 @@ from .... import autograd as ag
 Tensor = torch.Tensor
 
 
+def pbc(tup, shape) -> list:
+    """site coordinates wrapped into the lattice (lattice.py:33-34)"""
+    return np.mod(tup, shape).tolist()
+
+
+def mat_adj(mat):
+    """conjugate transpose of a single matrix (lattice.py:37-38)"""
+    return mat.conj().T
+
+
 def _f(beta) -> float:
     return float(beta.detach()) if isinstance(beta, torch.Tensor) else float(beta)
 

@@ -51,6 +51,60 @@ def flatten(x: Tensor) -> Tensor:
     return x.reshape(x.shape[0], -1)
 
 
+def nested_children(m: nn.Module) -> dict:
+    """module tree as nested dicts, leaves keyed by their class name (network.py:49-57)"""
+    children = dict(m.named_children())
+    if not children:
+        return {m._get_name(): m}
+    return {name: nested_children(child) for name, child in children.items()}
+
+
+def xy_repr(x: Tensor) -> Tensor:
+    """angles -> (cos, sin) stacked on a new axis 1 (network.py:65-66)"""
+    return torch.stack((torch.cos(x), torch.sin(x)), dim=1)
+
+
+def init_all(model: nn.Module, init_func: Callable, *params, **kwargs) -> None:
+    """apply `init_func(p, *params, **kwargs)` to every parameter (network.py:80-90)"""
+    for p in model.parameters():
+        init_func(p, *params, **kwargs)
+
+
+def init_all_by_shape(model: nn.Module, init_funcs: dict) -> None:
+    """per-parameter initialiser chosen by the parameter's rank, `init_funcs[str(rank)]`, falling back to
+    `init_funcs['default']` (network.py:93-118)"""
+    assert 'default' in init_funcs, 'init_funcs must have `default` entry'
+    for p in model.parameters():
+        init_funcs.get(str(p.dim()), init_funcs['default'])(p)
+
+
+def init_weights(m: nn.Module, method: str = 'xavier_uniform') -> None:
+    """`module.apply`-style initialiser of the `nn.Linear` weights (network.py:121-141)"""
+    if not isinstance(m, nn.Linear):
+        return
+    if method == 'zeros':
+        nn.init.zeros_(m.weight)
+        nn.init.zeros_(m.bias)
+        return
+    fn = getattr(nn.init, method if method.endswith('_') else method + '_', None)
+    if callable(fn):
+        fn(m.weight)
+
+
+def zero_weights(m: nn.Module) -> None:
+    """network.py:144-148"""
+    if isinstance(m, nn.Linear):
+        nn.init.zeros_(m.weight.data)
+        if m.bias is not None:
+            nn.init.zeros_(m.bias.data)
+
+
+def calc_output_size(hw: tuple[int, int], kernel_size, stride: int = 1, pad: int = 0, dilation: int = 1) -> tuple[int, int]:
+    """spatial size after a convolution / pooling window (network.py:209-237)"""
+    k = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    return tuple((n + 2 * pad - dilation * (kk - 1) - 1) // stride + 1 for n, kk in zip(hw, k))
+
+
 def dummy_network(inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor]:
     """network.py:69-77"""
     x, _ = inputs
@@ -269,6 +323,14 @@ class LeapfrogLayer(nn.Module):
             cached = (key, pack)
             self._heads_pack = cached
         return cached[1]
+
+
+def get_network(xshape: Sequence[int], network_config: NetworkConfig, input_shapes: Optional[dict] = None,
+                net_weight: Optional[NetWeight] = None, conv_config: Optional[ConvolutionConfig] = None,
+                name: Optional[str] = None) -> LeapfrogLayer:
+    """a LeapfrogLayer with its lazy layers still unmaterialised (network.py:554-569)"""
+    return LeapfrogLayer(xshape=xshape, network_config=network_config, input_shapes=input_shapes,
+                         net_weight=net_weight, conv_config=conv_config, name=name)
 
 
 def get_and_call_network(xshape: Sequence[int], *, network_config: NetworkConfig, is_xnet: bool, group,

@@ -121,3 +121,38 @@ def test_unknown_activation_and_factory_without_gpu():
                                                             use_batch_norm=False))
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         fac.build_networks(1, False, group=None)
+
+
+def test_module_level_helpers():
+    """network.py:49-148,209-237,554-569 and dynamics.py:77-99, lattice.py:33-38: the small free functions"""
+    from l2hmc_b200.dynamics.pytorch import dynamics as d
+    from l2hmc_b200.lattice.su3.pytorch import lattice as ls
+    lin = torch.nn.Linear(3, 2)
+    seq = torch.nn.Sequential(lin, torch.nn.Sequential(torch.nn.Tanh()))
+    tree = net.nested_children(seq)
+    assert set(tree) == {'0', '1'} and tree['0'] == {'Linear': lin} and list(tree['1']['0']) == ['Tanh']
+    net.zero_weights(lin)
+    assert float(lin.weight.detach().abs().max()) == 0 and float(lin.bias.detach().abs().max()) == 0
+    net.init_weights(lin, 'xavier_normal')
+    assert float(lin.weight.detach().abs().max()) > 0
+    net.init_weights(lin, 'zeros')
+    assert float(lin.weight.detach().abs().max()) == 0
+    net.init_all(seq, torch.nn.init.constant_, 0.5)
+    assert all(bool((p == 0.5).all()) for p in seq.parameters())
+    net.init_all_by_shape(seq, {'default': lambda p: torch.nn.init.constant_(p, 1.0),
+                                '2': lambda p: torch.nn.init.constant_(p, 2.0)})
+    assert bool((lin.weight == 2.0).all()) and bool((lin.bias == 1.0).all())
+    assert net.calc_output_size((16, 16), 5) == (12, 12) and net.calc_output_size((24, 24), 2, stride=2) == (12, 12)
+    assert net.calc_output_size((15, 9), (3, 2), stride=2, pad=1) == (8, 5)
+    x = torch.tensor([[0.0, np.pi / 2]])
+    assert torch.allclose(net.xy_repr(x), torch.tensor([[[1.0, 0.0], [0.0, 1.0]]]), atol=1e-7)
+    layer = net.get_network((2, 2, 4, 4), c.NetworkConfig(units=[4], activation_fn='relu', dropout_prob=0.0,
+                                                          use_batch_norm=False))
+    assert isinstance(layer, net.LeapfrogLayer) and layer.xdim == 32
+    a = d.random_angle((100,), requires_grad=True)
+    assert a.requires_grad and float(a.abs().max()) <= np.pi
+    assert torch.allclose(d.to_u1(torch.tensor([3 * np.pi / 2, -3 * np.pi / 2, 0.3])),
+                          torch.tensor([-np.pi / 2, np.pi / 2, 0.3]), atol=1e-6)
+    assert ls.pbc((4, -1, 2, 7), (4, 4, 4, 4)) == [0, 3, 2, 3]
+    m = np.array([[1 + 2j, 3], [4j, 5]])
+    assert np.array_equal(ls.mat_adj(m), m.conj().T)
