@@ -48,6 +48,25 @@ class BaseConfig:
     def __getitem__(self, key):
         return getattr(self, key)
 
+    def to_json(self) -> str:
+        """configs.py:157-158"""
+        import json
+        return json.dumps(self.__dict__)
+
+    def to_dict(self) -> dict:
+        """configs.py:166-167"""
+        from copy import deepcopy
+        return deepcopy(self.__dict__)
+
+
+def list_to_str(x: list) -> str:
+    """dash-joined list, floats with one decimal (configs.py:133-139)"""
+    if isinstance(x[0], int):
+        return '-'.join(str(int(i)) for i in x)
+    if isinstance(x[0], float):
+        return '-'.join(f'{i:2.1f}' for i in x)
+    return '-'.join(str(i) for i in x)
+
 
 @dataclass
 class NetWeight(BaseConfig):
@@ -98,6 +117,19 @@ class ConvolutionConfig(BaseConfig):
         assert len(self.filters) == len(self.sizes)
         assert len(self.filters) == len(self.pool)
 
+    def to_str(self) -> str:
+        """directory-name fragment `conv-<filters>_<sizes>_<pool>` (configs.py:416-434)"""
+        if self.filters is None:
+            return 'conv-None'
+        if len(self.filters) == 0:
+            return ''
+        parts = [list_to_str(list(self.filters))]
+        if self.sizes is not None:
+            parts.append(list_to_str(list(self.sizes)))
+        if self.pool is not None:
+            parts.append(list_to_str(list(self.pool)))
+        return 'conv-' + '_'.join(parts)
+
 
 @dataclass
 class NetworkConfig(BaseConfig):
@@ -105,6 +137,11 @@ class NetworkConfig(BaseConfig):
     activation_fn: str
     dropout_prob: float
     use_batch_norm: bool = True
+
+    def to_str(self) -> str:
+        """`net-<units>_dp-<p>_bn-<flag>` (configs.py:444-448)"""
+        units = '-'.join(str(int(u)) for u in self.units)
+        return f'net-{units}_dp-{self.dropout_prob:2.1f}_bn-{self.use_batch_norm}'
 
 
 @dataclass
@@ -159,12 +196,21 @@ class LossConfig(BaseConfig):
     plaq_weight: float = 0.0
     aux_weight: float = 0.0
 
+    def to_str(self) -> str:
+        """configs.py:531-538"""
+        return '_'.join([f'qw-{self.charge_weight:2.1f}', f'pw-{self.plaq_weight:2.1f}', f'rw-{self.rmse_weight:2.1f}',
+                         f'aw-{self.aux_weight:2.1f}', f'mixed-{self.use_mixed_loss}'])
+
 
 @dataclass
 class InputSpec(BaseConfig):
     xshape: Sequence[int]
     xnet: Optional[Dict[str, Any]] = None
     vnet: Optional[Dict[str, Any]] = None
+
+    def to_str(self) -> str:
+        """configs.py:547-548"""
+        return '-'.join(str(i) for i in self.xshape)
 
     def __post_init__(self):
         if len(self.xshape) == 2:

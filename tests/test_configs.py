@@ -36,3 +36,16 @@ def test_u1_defaults():
     assert list(conv.sizes) == [2, 2] and list(conv.pool) == [2, 2]
     spec = c.get_input_spec(dyn)
     assert spec.xnet == {'x': [512, 2], 'v': [512]}
+
+
+def test_to_str_fragments():
+    """configs.py:133-139,294-305,416-448,531-548: the strings the reference builds its output directories from"""
+    assert c.NetworkConfig(units=[16, 16], activation_fn='relu', dropout_prob=0.2).to_str() == 'net-16-16_dp-0.2_bn-True'
+    assert c.ConvolutionConfig(filters=[8, 16], sizes=[5, 3], pool=[2, 2]).to_str() == 'conv-8-16_5-3_2-2'
+    assert c.ConvolutionConfig().to_str() == 'conv-None' and c.ConvolutionConfig(filters=[]).to_str() == ''
+    assert c.LossConfig(use_mixed_loss=True, charge_weight=0.01).to_str() == 'qw-0.0_pw-0.0_rw-0.0_aw-0.0_mixed-True'
+    assert c.InputSpec(xshape=(8, 2, 16, 16)).to_str() == '8-2-16-16'
+    assert c.NetWeights(x=c.NetWeight(0., 1., 1.), v=c.NetWeight(1., 1., 1.)).to_str() == 'nwx-s0.0t1.0q1.0-nwv-s1.0t1.0q1.0'
+    assert c.list_to_str([0.5, 1.0]) == '0.5-1.0' and c.list_to_str(['a', 'b']) == 'a-b'
+    assert c.NetWeight(1., 2., 3.).to_dict() == {'s': 1., 't': 2., 'q': 3.}
+    assert '"units": [4]' in c.NetworkConfig(units=[4], activation_fn='relu', dropout_prob=0.0).to_json()
