@@ -86,3 +86,81 @@ def test_periodic_padding_and_conv_stack_shapes_match_reference(ref):
         assert torch.allclose(a, b.to(a.dtype), rtol=1e-12, atol=1e-12)
     pad = rnet.PeriodicPadding(2)
     assert torch.equal(net.PeriodicPadding(2)(x), pad(x))
+
+
+def test_pure_torch_group_and_lattice_methods_match_reference(ref):
+    """the methods of our mirrors that involve no kernel (they act on Wilson loops / angles already computed) must
+    return what the reference's own methods return on the same tensors"""
+    import importlib
+    from l2hmc_b200.group.u1.pytorch.group import U1Phase
+    from l2hmc_b200.group.su3.pytorch import group as g3
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1, plaq_exact, area_law, project_angle
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    rgu1 = importlib.import_module('l2hmc.group.u1.pytorch.group')
+    rlu1 = importlib.import_module('l2hmc.lattice.u1.pytorch.lattice')
+    ru3 = importlib.import_module('l2hmc.group.su3.pytorch.utils')
+    torch.manual_seed(1)
+    same = lambda a, b, tol=1e-13: float((a - b).abs().max()) <= tol * max(1.0, float(b.abs().max()))  # noqa: E731
+    # ---- U(1) group
+    ours, theirs = U1Phase(), rgu1.U1Phase()
+    x, p = 3.0 * torch.randn(3, 2, 4, 6), torch.randn(3, 2, 4, 6)
+    for name, args in (('update_gauge', (x, p)), ('group_to_vec', (x,)), ('adjoint', (x,)), ('trace', (x,)),
+                       ('diff_trace', (x,)), ('diff2trace', (x,)), ('exp', (x,)), ('mul', (x, p)),
+                       ('phase_to_coords', (x,)), ('floormod', (x, 2.0))):
+        if hasattr(theirs, name):
+            assert same(getattr(ours, name)(*args), getattr(theirs, name)(*args)), name
+    assert same(ours.mul(x, p, adjoint_a=True), theirs.mul(x, p, adjoint_a=True))
+    assert same(ours.mul(x, p, adjoint_b=True), theirs.mul(x, p, adjoint_b=True))
+    v = ours.group_to_vec(x)
+    assert same(ours.vec_to_group(v), theirs.vec_to_group(v))
+    c2 = torch.randn(5, 2)
+    assert same(ours.coords_to_phase(c2), theirs.coords_to_phase(c2))
+    # ---- U(1) lattice: everything downstream of the Wilson loops
+    lo, lr = LatticeU1(3, [4, 6]), rlu1.LatticeU1(3, [4, 6])
+    w = lr.wilson_loops(x)
+    w2 = lr.wilson_loops(x + 0.3 * p)
+    beta = torch.tensor(2.5)
+    for name, args in (('_action', (w, beta)), ('_plaqs', (w,)), ('_sin_charges', (w,)), ('_int_charges', (w,)),
+                       ('_plaqs4x4', (lr.wilson_loops4x4(x),))):
+        assert same(getattr(lo, name)(*args), getattr(lr, name)(*args)), name
+    assert same(lo.wilson_loops4x4(x), lr.wilson_loops4x4(x))
+    assert same(lo.plaqs4x4(x=x), lr.plaqs4x4(x=x))
+    acc = torch.rand(3)
+    assert same(lo.plaq_loss(acc, wl1=w, wl2=w2), lr.plaq_loss(acc, wl1=w, wl2=w2))
+    assert same(lo.charge_loss(acc, wl1=w, wl2=w2), lr.charge_loss(acc, wl1=w, wl2=w2))
+    assert same(lo.plaqs(wloops=w), lr.plaqs(wloops=w)) and same(lo.sin_charges(wloops=w), lr.sin_charges(wloops=w))
+    assert same(lo.int_charges(wloops=w), lr.int_charges(wloops=w))
+    ch_o, ch_r = lo.charges(wloops=w), lr.charges(wloops=w)
+    assert same(ch_o.intQ, ch_r.intQ) and same(ch_o.sinQ, ch_r.sinQ)
+    for b in (0.5, 2.0, 6.0):
+        assert same(torch.as_tensor(plaq_exact(b)), torch.as_tensor(rlu1.plaq_exact(torch.tensor(b))))
+        assert same(torch.as_tensor(area_law(b, 4)), torch.as_tensor(rlu1.area_law(torch.tensor(b), 4)))
+    assert same(project_angle(x), rlu1.project_angle(x))
+    # ---- SU(3): torch-only helpers
+    a = torch.complex(torch.randn(6, 3, 3), torch.randn(6, 3, 3))
+    h = a @ a.mH + 0.5 * torch.eye(3)
+    assert same(g3.norm2(a), ru3.norm2(a)) and same(g3.norm2(a, axis=[-1]), ru3.norm2(a, axis=[-1]))
+    tr, p2, det = (torch.diagonal(h, dim1=-2, dim2=-1).sum(-1).real, torch.diagonal(h @ h, dim1=-2, dim2=-1).sum(-1).real,
+                   torch.linalg.det(h).real)
+    for o, r in zip(g3.rsqrtPHM3f(tr, p2, det), ru3.rsqrtPHM3f(tr, p2, det)):
+        assert same(o, r, 1e-12)
+    assert same(g3.rsqrtPHM3(h), ru3.rsqrtPHM3(h), 1e-11)
+    for o, r in zip(g3.checkU(a[None]), ru3.checkU(a[None])):
+        assert same(o, r, 1e-12)
+    from l2hmc_b200.group.su3.pytorch import utils as u3
+    for o, r in zip(u3.eigs3x3(tr, p2, det), ru3.eigs3x3(tr, p2, det)):
+        assert same(o, r, 1e-12)
+    assert same(u3.expm(0.3 * a), ru3.expm(0.3 * a)) and same(u3.cmax(a, h), ru3.cmax(a, h))
+    for o, r in zip(u3.charpoly3x3(a), ru3.charpoly3x3(a)):
+        assert same(o, r, 1e-12)
+    # ---- SU(3) lattice: downstream of the loops
+    lo3 = LatticeSU3(2, [2, 2, 2, 4])
+    rl3 = importlib.import_module('l2hmc.lattice.su3.pytorch.lattice').LatticeSU3(2, [2, 2, 2, 4])
+    wl = torch.complex(torch.randn(6, 2, 2, 2, 2, 4), torch.randn(6, 2, 2, 2, 2, 4))
+    for name in ('_plaqs', '_int_charges', '_sin_charges'):
+        assert same(getattr(lo3, name)(wl), getattr(rl3, name)(wl)), name
+    assert same(lo3._action(wl, torch.tensor(6.0)), rl3._action((wl, torch.zeros(12, *wl.shape[1:])), torch.tensor(6.0)))
+    co, cr = lo3._charges(wl), rl3._charges(wl)
+    assert same(co.intQ, cr.intQ) and same(co.sinQ, cr.sinQ)
+    for k, val in lo3.coeffs(torch.tensor(6.0)).items():
+        assert abs(val - float(rl3.coeffs(torch.tensor(6.0))[k])) < 1e-15
