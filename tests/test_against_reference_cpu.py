@@ -164,3 +164,40 @@ def test_pure_torch_group_and_lattice_methods_match_reference(ref):
     assert same(co.intQ, cr.intQ) and same(co.sinQ, cr.sinQ)
     for k, val in lo3.coeffs(torch.tensor(6.0)).items():
         assert abs(val - float(rl3.coeffs(torch.tensor(6.0))[k])) < 1e-15
+
+
+@pytest.mark.parametrize('group', ['U1', 'SU3'])
+def test_lattice_loss_matches_reference_given_the_same_wilson_loops(ref, group):
+    """LatticeLoss (loss/pytorch/loss.py:50-210) on top of the reference's CPU Wilson loops: every loss term and
+    their weighted sum, mixed and plain, must equal the reference's LatticeLoss"""
+    import importlib
+    from l2hmc_b200 import configs as c
+    from l2hmc_b200.loss.pytorch.loss import LatticeLoss
+    torch.manual_seed(3)
+    if group == 'U1':
+        from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1 as Ours
+        rlat = importlib.import_module('l2hmc.lattice.u1.pytorch.lattice').LatticeU1(3, [4, 6])
+        olat = Ours(3, [4, 6])
+        x0, x1 = 3.0 * torch.randn(3, 2, 4, 6), 3.0 * torch.randn(3, 2, 4, 6)
+    else:
+        from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3 as Ours
+        rlat = importlib.import_module('l2hmc.lattice.su3.pytorch.lattice').LatticeSU3(3, [2, 2, 2, 4])
+        olat = Ours(3, [2, 2, 2, 4])
+        x0, x1 = rlat.random().detach(), rlat.random().detach()
+    olat.wilson_loops = rlat.wilson_loops              # the kernel's job; here the reference's own CPU loops
+    acc = torch.rand(3)
+    # (upstream's rmse_loss takes `.imag` of the difference and so only runs for complex fields, loss.py:139)
+    for mixed, qw, pw, rw in itertools.product([True, False], [0.0, 0.01], [0.0, 0.1], [0.0, 0.1] if group == 'SU3' else [0.0]):
+        kw = dict(use_mixed_loss=mixed, charge_weight=qw, plaq_weight=pw, rmse_weight=rw)
+        ours, theirs = LatticeLoss(olat, c.LossConfig(**kw)), ref.LatticeLoss(rlat, ref.cfgs.LossConfig(**kw))
+        got, want = ours(x_init=x0, x_prop=x1, acc=acc), theirs(x_init=x0, x_prop=x1, acc=acc)
+        assert float((got - want).abs()) <= 1e-12 * max(1.0, float(want.abs())), kw
+        if pw > 0:
+            assert torch.allclose(ours.plaq_loss(x0, x1, acc), theirs.plaq_loss(x0, x1, acc), rtol=1e-12)
+        if qw > 0:
+            assert torch.allclose(ours.charge_loss(x0, x1, acc), theirs.charge_loss(x0, x1, acc), rtol=1e-12)
+        if rw > 0:
+            assert torch.allclose(ours.rmse_loss(x0, x1, acc), theirs.rmse_loss(x0, x1, acc), rtol=1e-12)
+        if pw > 0 or qw > 0:
+            a, b = ours.general_loss(x0, x1, acc), theirs.general_loss(x0, x1, acc)
+            assert torch.allclose(torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64), rtol=1e-6)
