@@ -145,3 +145,35 @@ def test_forward_contract(golden_dir, emulated, dtype_of, merge):
     assert tuple(xo2.shape) == (nb, dyn.xdim) and met2['acc_mask'].dtype == torch.float32
     xo_hmc, met_h = dyn.apply_transition_hmc((x, beta), eps=0.1, nleapfrog=3)
     assert tuple(xo_hmc.shape) == (nb, dyn.xdim) and 'sumlogdet' in met_h
+
+
+def test_trainer_eval_and_hmc_steps(golden_dir, emulated, dtype_of):
+    """Trainer.hmc_step / eval_step (trainers/pytorch/trainer.py:904-956): `compat_proj` at the top of the step
+    (appendix B trap 9), the loss on (x_init, proposed x, acc), x_out detached and flattened"""
+    from l2hmc_b200.configs import LossConfig
+    from l2hmc_b200.loss.pytorch.loss import LatticeLoss
+    from l2hmc_b200.trainers.pytorch.trainer import Trainer
+    dtype_of('f64')
+    gu = np.load(golden_dir / 'u1_f64.npz')
+    dyn = _dynamics(gu, 'dense', verbose=False)
+    lcfg = LossConfig(use_mixed_loss=True, charge_weight=0.01)
+    tr = Trainer(dyn, loss_config=lcfg)
+    x = torch.from_numpy(gu['x']) * 3.0                  # outside [-pi, pi): the step must wrap it first
+    beta = torch.tensor(float(gu['beta']))
+    for wraps, step in ((True, tr.eval_step), (False, lambda inp: tr.hmc_step(inp, eps=0.1, nleapfrog=3))):
+        torch.manual_seed(11)
+        xo, met = step((x, beta))
+        assert tuple(xo.shape) == (3, dyn.xdim) and not xo.requires_grad
+        # the L2HMC x-update wraps its output; plain HMC drifts x + eps v without wrapping, like the reference
+        assert (float(xo.abs().max()) <= np.pi) or not wraps
+        assert float(xo.abs().max()) < np.pi + 3.0           # but it started from the WRAPPED input (|3 x| reaches 9)
+        assert 'mc_states' not in met and met['acc_mask'].dtype == torch.float32
+        assert torch.isfinite(met['loss']) and met['loss'].dim() == 0
+    # the loss is LatticeLoss of the wrapped input, the proposal and acc
+    torch.manual_seed(11)
+    xi = dyn.g.compat_proj(x)
+    xo2, m2 = dyn((xi, beta))
+    want = LatticeLoss(dyn.lattice, lcfg)(x_init=xi, x_prop=m2['mc_states'].proposed.x, acc=m2['acc'])
+    torch.manual_seed(11)
+    _, met = tr.eval_step((x, beta))
+    assert float((met['loss'] - want).abs()) < 1e-12
