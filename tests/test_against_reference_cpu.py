@@ -209,3 +209,65 @@ def test_lattice_loss_matches_reference_given_the_same_wilson_loops(ref, group):
         if pw > 0 or qw > 0:
             a, b = ours.general_loss(x0, x1, acc), theirs.general_loss(x0, x1, acc)
             assert torch.allclose(torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64), rtol=1e-6)
+
+
+@pytest.mark.parametrize('merge', [True, False])
+def test_public_transitions_match_the_reference_under_the_same_seed(ref, monkeypatch, merge):
+    """`Dynamics.forward` (merged and un-merged) and `apply_transition_hmc` of our mirror,
+    run on the CPU with the U(1) kernels replaced by stand-ins (tests/cpu_emulation.py), against the reference's
+    own Dynamics with the same weights, masks and torch seed: momenta, direction coins and accept draws are
+    consumed in the same order, so the outputs agree chain by chain"""
+    from tests.cpu_emulation import u1_host_logic_on_cpu
+    from l2hmc_b200 import configs as c
+    shape, nb, nlf = [6, 4], 5, 2
+    kw = dict(nchains=nb, group='U1', latvolume=shape, nleapfrog=nlf, eps=0.1, eps_hmc=0.1, use_ncp=True,
+              verbose=False, use_split_xnets=True, use_separate_networks=True, merge_directions=merge)
+    ncfg = dict(units=[8, 6], activation_fn='relu', dropout_prob=0.0, use_batch_norm=False)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    rcfg = ref.DynamicsConfig(**kw)
+    rlat = ref.LatticeU1(nb, shape)
+    xdim = rcfg.xdim
+    rfac = ref.NetworkFactory(input_spec=ref.InputSpec(xshape=rcfg.xshape, xnet={'x': [xdim, 2], 'v': [xdim]},
+                                                       vnet={'x': [xdim], 'v': [xdim]}),
+                              network_config=ref.NetworkConfig(**ncfg), conv_config=None, net_weights=None)
+    rdyn = ref.Dynamics(potential_fn=rlat.action, config=rcfg, network_factory=rfac)
+    for p in rdyn.parameters():                      # the reference zero-initialises the ScaledTanh coefficients
+        if p.dim() == 2 and p.shape[0] == 1:
+            torch.nn.init.normal_(p, std=0.3)
+    rdyn.eval()
+    x = rlat.random().detach()
+    beta = torch.tensor(2.0)
+    with u1_host_logic_on_cpu(monkeypatch):
+        from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+        from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+        from l2hmc_b200.network.pytorch.network import NetworkFactory
+        ocfg = c.DynamicsConfig(**kw)
+        fac = NetworkFactory(input_spec=c.get_input_spec(ocfg), network_config=c.NetworkConfig(**ncfg),
+                             conv_config=None, net_weights=None)
+        odyn = Dynamics(potential_fn=LatticeU1(nb, shape).action, config=ocfg, network_factory=fac)
+        res = odyn.load_state_dict(rdyn.state_dict(), strict=True)       # incl. the duplicated `networks.` aliases
+        assert not res.missing_keys and not res.unexpected_keys
+        odyn.masks = [m.clone() for m in rdyn.masks]
+        odyn.eval()
+        calls = (('forward', lambda d: d((x, beta))),
+                 ('hmc', lambda d: d.apply_transition_hmc((x, beta), eps=0.1, nleapfrog=3)))
+        # (`apply_transition_both` cannot be compared: upstream's `_get_direction_masks` subtracts bool tensors and
+        # raises on current torch, dynamics.py:1089-1094; ours is covered by the contract tests)
+        with pytest.raises(RuntimeError):
+            rdyn.apply_transition_both((x, beta))
+        for name, call in calls:
+            for seed in (1, 2, 3):
+                torch.manual_seed(seed)
+                xo_r, m_r = call(rdyn)               # the reference needs autograd for its U(1) force: no no_grad
+                torch.manual_seed(seed)
+                with torch.no_grad():
+                    xo_o, m_o = call(odyn)
+                assert torch.equal(m_o['acc_mask'], m_r['acc_mask'].detach()), (name, seed)
+                assert float((xo_o - xo_r.detach().reshape(xo_o.shape)).abs().max()) < 1e-10, (name, seed)
+                assert float((m_o['acc'] - m_r['acc'].detach()).abs().max()) < 1e-10, (name, seed)
+                assert float((m_o['sumlogdet'] - m_r['sumlogdet'].detach()).abs().max()) < 1e-10, (name, seed)
+                for part in ('init', 'proposed', 'out'):
+                    so, sr = getattr(m_o['mc_states'], part), getattr(m_r['mc_states'], part)
+                    assert float((so.x.reshape(nb, -1) - sr.x.detach().reshape(nb, -1)).abs().max()) < 1e-10, (name, part)
+                    assert float((so.v.reshape(nb, -1) - sr.v.detach().reshape(nb, -1)).abs().max()) < 1e-10, (name, part)
