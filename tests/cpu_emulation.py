@@ -140,6 +140,132 @@ class _TorchProxy:
         return getattr(torch, name)
 
 
+# ---------------------------------------------------------------------------
+# SU(3): thin torch <-> numpy wrappers around the oracle (oracle/su3.py, oracle/dynamics.py)
+# ---------------------------------------------------------------------------
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _full(x, dims=None):
+    return x if x.dim() == 8 else x.reshape(x.shape[0], 4, *dims, 3, 3)
+
+
+def su3_plaq_sums(x):
+    from oracle import su3 as o
+    re, im = o.plaq_sums(_np(x))
+    return torch.stack([torch.from_numpy(re), torch.from_numpy(im)], 1)
+
+
+def su3_wilson_loops(x):
+    from oracle import su3 as o
+    return torch.from_numpy(o.wilson_loops(_np(x)))
+
+
+def su3_force(x, beta, want_plaq_sum=False):
+    from oracle import su3 as o
+    f = torch.from_numpy(o.grad_action(_np(x), float(beta)))
+    return (f, su3_plaq_sums(x)[:, 0]) if want_plaq_sum else f
+
+
+def su3_force_c1(x, beta, c1, want_force=True, want_sums=False):
+    """improved action: the force through torch autograd of the torch restatement of the reference's loops"""
+    from oracle import su3 as o
+    xn = _np(x)
+    sums = torch.stack([torch.from_numpy(o.plaq_sums(xn)[0]),
+                        torch.from_numpy(o.rect_traces(xn).real.reshape(12, xn.shape[0], -1).sum(2).sum(0))], 1)
+    if not want_force:
+        return sums
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    lat = LatticeSU3(xn.shape[0], list(xn.shape[2:6]), c1=c1)
+    lat.rect_kernel = False
+    with torch.enable_grad():
+        xr = x.detach().clone().requires_grad_(True)
+        tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)  # noqa: E731
+        ps = 0.0
+        for u in range(1, 4):
+            for v in range(u):
+                ps = ps + tr(lat._plaquette(xr, u, v)).real.flatten(1).sum(1)
+        act = -(beta / 3.0) * (1 - 8 * c1) * ps + lat._rect_action(xr, beta)
+        dsdx, = torch.autograd.grad(act.sum(), xr)
+    y = dsdx @ x.mH
+    a = 0.5 * (y - y.mH)
+    f = a - torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)[..., None, None] / 3.0 * torch.eye(3, dtype=a.dtype)
+    return (f, sums) if want_sums else f
+
+
+def su3_project(x, want_matrix=True, want_vec=False):
+    from oracle import su3 as o
+    m = o.projectSU(_np(x))
+    mt, vt = torch.from_numpy(m), torch.from_numpy(o.su3_to_vec(m))
+    if want_matrix and want_vec:
+        return mt, vt
+    return mt if want_matrix else vt
+
+
+def su3_project_vec(x, dtype=torch.float64):
+    from oracle import su3 as o
+    return torch.from_numpy(o.group_to_vec(_np(x))).to(dtype)
+
+
+def su3_kinetic(p):
+    from oracle import su3 as o
+    return torch.from_numpy(o.kinetic_energy(_np(p)))
+
+
+def su3_update_gauge(x, p, eps=1.0, mask=None, mask_complement=False, eps_mult=1.0):
+    from oracle import su3 as o
+    e = float(eps) * float(eps_mult)
+    xn, pn = _np(x), _np(p).reshape(x.shape)
+    if mask is None:
+        return torch.from_numpy(o.update_gauge(xn, e * pn))
+    m = _np(mask).astype(xn.real.dtype).reshape(1, *xn.shape[1:])
+    if mask_complement:
+        m = 1.0 - m
+    return torch.from_numpy(m * xn + o.update_gauge((1.0 - m) * xn, e * pn))
+
+
+def su3_vupdate(v, force, s, t, q, eps, sign):
+    nb = v.shape[0]
+    e = float(eps)
+    vv, ff = v.reshape(nb, -1), force.reshape(nb, -1)
+    z = torch.zeros(vv.shape, dtype=torch.float64)
+    s, t, q = (z if a is None else a.to(torch.float64).reshape(nb, -1) for a in (s, t, q))
+    kick = 0.5 * e * (ff * torch.exp(e * q) + t)
+    if sign > 0:
+        out, logdet = torch.exp(0.5 * e * s) * vv - kick, (0.5 * e * s).sum(1)
+    else:
+        out, logdet = torch.exp(-0.5 * e * s) * (vv + kick), -(0.5 * e * s).sum(1)
+    return out.reshape(v.shape), logdet
+
+
+def su3_hmc_trajectory(x, v, beta, eps, nlf):
+    from oracle import su3 as o, dynamics as od
+    xn, vn = _np(x), _np(v).reshape(x.shape)
+    sp, _ = od.transition_kernel_hmc(od.SU3Ops, od.State(xn, vn, float(beta)), float(eps), int(nlf))
+    en = torch.from_numpy(__import__('numpy').stack([o.kinetic_energy(vn), o.action(xn, float(beta)),
+                                                     o.kinetic_energy(sp.v), o.action(sp.x, float(beta))], 1))
+    return torch.from_numpy(sp.x), torch.from_numpy(sp.v), en
+
+
+@contextlib.contextmanager
+def su3_host_logic_on_cpu(monkeypatch):
+    """as u1_host_logic_on_cpu, for the boundary-layout (unfused, no-grad) SU(3) path"""
+    from l2hmc_b200 import ops
+    from l2hmc_b200.dynamics.pytorch import dynamics as dmod
+    from l2hmc_b200.network.pytorch import network as net
+    from l2hmc_b200.group.su3.pytorch import group as g3
+    for name in ('su3_plaq_sums', 'su3_wilson_loops', 'su3_force', 'su3_force_c1', 'su3_project', 'su3_project_vec',
+                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'accept_mix'):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(ops, 'heads_supported', lambda hidden: False)         # tcgen05 heads: GPU tier only
+    cpu = lambda: torch.device('cpu')  # noqa: E731
+    monkeypatch.setattr(net, '_device', cpu)
+    monkeypatch.setattr(g3, '_device', cpu)
+    monkeypatch.setattr(dmod, 'torch', _TorchProxy())
+    yield
+
+
 @contextlib.contextmanager
 def u1_host_logic_on_cpu(monkeypatch):
     """patch l2hmc_b200 so that a U(1) `Dynamics` can be built and stepped on the CPU with the stand-ins above"""

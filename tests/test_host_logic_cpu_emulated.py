@@ -177,3 +177,82 @@ def test_trainer_eval_and_hmc_steps(golden_dir, emulated, dtype_of):
     torch.manual_seed(11)
     _, met = tr.eval_step((x, beta))
     assert float((met['loss'] - want).abs()) < 1e-12
+
+
+@pytest.fixture()
+def emulated_su3(monkeypatch):
+    from tests.cpu_emulation import su3_host_logic_on_cpu
+    with su3_host_logic_on_cpu(monkeypatch):
+        yield
+
+
+def test_su3_l2hmc_sweep_host_logic(golden_dir, emulated_su3, dtype_of):
+    """the boundary-layout SU(3) sweep (vnet on su3_to_vec(projectSU(.)) of x and of the force, masked exp(eps v)
+    x-update, logdet from s only) against the reference golden, kernels replaced by oracle-backed stand-ins"""
+    from l2hmc_b200.configs import DynamicsConfig, NetworkConfig, NetWeights, NetWeight, get_input_spec
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    dtype_of('f64')
+    gl = np.load(golden_dir / 'su3_l2hmc_f64.npz')
+    shape, nb, nlf = [int(s) for s in gl['shape']], 2, int(gl['nlf'])
+    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=nlf, eps=0.05, eps_hmc=0.1,
+                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                         network_config=NetworkConfig(units=[8], activation_fn='tanh', dropout_prob=0.0, use_batch_norm=False),
+                         conv_config=None, net_weights=NetWeights(x=NetWeight(0., 1., 1.), v=NetWeight(1., 1., 1.)))
+    dyn = Dynamics(potential_fn=LatticeSU3(nb, shape).action, config=cfg, network_factory=fac)
+    sd = {k[3:]: torch.from_numpy(gl[k]) for k in gl.files if k.startswith('sd/')}
+    res = dyn.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys
+    dyn.masks = [torch.from_numpy(m) for m in gl['masks']]
+    dyn.eval()
+    st = State(torch.from_numpy(gl['x']), torch.from_numpy(gl['v']), torch.tensor(float(gl['beta'])))
+    with torch.no_grad():
+        s1, ld = dyn._update_v_fwd(0, st)
+        assert maxdiff(np.abs(host(s1.v) - gl['vfwd_v']), 0) < 1e-8 and maxdiff(host(ld), gl['vfwd_logdet']) < 1e-8
+        m, _ = dyn._get_mask(0)
+        s2, ld2 = dyn._update_x_fwd(0, st, m, first=True)
+        assert np.abs(host(s2.x) - gl['xfwd_x']).max() < 1e-12 and float(ld2.abs().max()) == 0
+        sp, met = dyn.transition_kernel_fb(st)
+    assert np.abs(host(sp.x) - gl['fb_x']).max() < 1e-8 and np.abs(host(sp.v) - gl['fb_v']).max() < 1e-8
+    assert maxdiff(host(met['acc']), gl['fb_acc']) < 1e-8 and maxdiff(host(met['sumlogdet']), gl['fb_sumlogdet']) < 1e-8
+
+
+@pytest.mark.parametrize('kernel', [True, False])
+def test_su3_hmc_with_improved_action_host_logic(golden_dir, emulated_su3, dtype_of, kernel):
+    """plain HMC with potential_fn = improved action: trajectory from the Wilson force, acceptance from
+    potential_fn (the `_potential_is_wilson` branch), both with the rectangle kernel routed in and with ATen ops"""
+    from l2hmc_b200.configs import DynamicsConfig
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    dtype_of('f64')
+    g = np.load(golden_dir / 'su3_c1_f64.npz')
+    shape, nb, beta, c1 = [int(s) for s in g['shape']], g['x'].shape[0], float(g['beta']), float(g['c1'])
+    lat = LatticeSU3(nb, shape, c1=c1)
+    lat.rect_kernel = kernel
+    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=2, eps=0.05, eps_hmc=0.05,
+                         verbose=False, use_split_xnets=False, use_separate_networks=False)
+    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+    assert not dyn._potential_is_wilson()
+    st = State(torch.from_numpy(g['hmc2_x0']), torch.from_numpy(g['hmc2_v0']), torch.tensor(beta))
+    with torch.no_grad():
+        sp, met = dyn.transition_kernel_hmc(st, eps=0.01, nleapfrog=3)
+        h0 = dyn.hamiltonian(st)
+    assert np.abs(host(sp.x).reshape(g['hmc2_x0'].shape) - g['hmc2_x'].reshape(g['hmc2_x0'].shape)).max() < 1e-12
+    assert np.abs(host(sp.v).reshape(g['hmc2_x0'].shape) - g['hmc2_v'].reshape(g['hmc2_x0'].shape)).max() < 1e-12
+    assert np.allclose(host(h0), g['hmc2_h0'], rtol=1e-12)
+    assert np.allclose(host(met['acc']), g['hmc2_acc'], rtol=1e-7)
+    # and the plain Wilson potential takes the kernel's own energies
+    dyn_w = Dynamics(potential_fn=LatticeSU3(nb, shape).action, config=cfg, network_factory=None)
+    assert dyn_w._potential_is_wilson()
+    with torch.no_grad():
+        sp_w, met_w = dyn_w.transition_kernel_hmc(st, eps=0.01, nleapfrog=3)
+    assert torch.equal(sp_w.x, sp.x) and not np.allclose(host(met_w['acc']), g['hmc2_acc'], rtol=1e-3)
+    # lattice-level c1 API through the same routing
+    x = torch.from_numpy(g['x'])
+    with torch.no_grad():
+        assert np.allclose(host(lat.action(x, torch.tensor(beta))), g['action'], rtol=1e-12)
+        assert np.abs(host(lat.grad_action(x, torch.tensor(beta))) - g['force']).max() < 1e-12
+        s2, f2 = lat.action_with_grad(x, torch.tensor(beta))
+        assert np.allclose(host(s2), g['action'], rtol=1e-12) and np.abs(host(f2) - g['force']).max() < 1e-12
