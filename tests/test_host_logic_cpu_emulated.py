@@ -256,3 +256,49 @@ def test_su3_hmc_with_improved_action_host_logic(golden_dir, emulated_su3, dtype
         assert np.abs(host(lat.grad_action(x, torch.tensor(beta))) - g['force']).max() < 1e-12
         s2, f2 = lat.action_with_grad(x, torch.tensor(beta))
         assert np.allclose(host(s2), g['action'], rtol=1e-12) and np.abs(host(f2) - g['force']).max() < 1e-12
+
+
+def test_su3_force_reuse_gives_identical_sweep_with_fewer_force_evaluations(golden_dir, emulated_su3, dtype_of):
+    """`reuse_force = 'always'` on the boundary-layout sweep: same proposal, acceptance and log-Jacobian bit for
+    bit, 2 nlf + 1 instead of 4 nlf force evaluations and projections per sweep"""
+    from l2hmc_b200 import ops
+    from l2hmc_b200.configs import DynamicsConfig, NetworkConfig, NetWeights, NetWeight, get_input_spec
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    dtype_of('f64')
+    gl = np.load(golden_dir / 'su3_l2hmc_f64.npz')
+    shape, nb, nlf = [int(s) for s in gl['shape']], 2, int(gl['nlf'])
+    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=nlf, eps=0.05, eps_hmc=0.1,
+                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+    fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                         network_config=NetworkConfig(units=[8], activation_fn='tanh', dropout_prob=0.0, use_batch_norm=False),
+                         conv_config=None, net_weights=NetWeights(x=NetWeight(0., 1., 1.), v=NetWeight(1., 1., 1.)))
+    dyn = Dynamics(potential_fn=LatticeSU3(nb, shape).action, config=cfg, network_factory=fac)
+    dyn.load_state_dict({k[3:]: torch.from_numpy(gl[k]) for k in gl.files if k.startswith('sd/')}, strict=False)
+    dyn.masks = [torch.from_numpy(m) for m in gl['masks']]
+    dyn.eval()
+    st = State(torch.from_numpy(gl['x']), torch.from_numpy(gl['v']), torch.tensor(float(gl['beta'])))
+    counts = {'force': 0, 'vec': 0}
+    force, vec = ops.su3_force, ops.su3_project_vec
+
+    def counting_force(*a, **k):
+        counts['force'] += 1
+        return force(*a, **k)
+
+    def counting_vec(*a, **k):
+        counts['vec'] += 1
+        return vec(*a, **k)
+    ops.su3_force, ops.su3_project_vec = counting_force, counting_vec       # (monkeypatch restores the originals)
+    res = {}
+    for mode in ('never', 'always'):
+        dyn.reuse_force = mode
+        counts.update(force=0, vec=0)
+        with torch.no_grad():
+            sp, met = dyn.transition_kernel_fb(st)
+        res[mode] = (sp.x, sp.v, met['acc'], met['sumlogdet'], dict(counts))
+    assert res['never'][4] == {'force': 4 * nlf, 'vec': 8 * nlf}
+    assert res['always'][4] == {'force': 2 * nlf + 1, 'vec': 2 * (2 * nlf + 1)}
+    for a, b in zip(res['never'][:4], res['always'][:4]):
+        assert torch.equal(a, b)
+    assert np.abs(host(res['always'][0]) - gl['fb_x']).max() < 1e-8
