@@ -302,3 +302,29 @@ def test_su3_force_reuse_gives_identical_sweep_with_fewer_force_evaluations(gold
     for a, b in zip(res['never'][:4], res['always'][:4]):
         assert torch.equal(a, b)
     assert np.abs(host(res['always'][0]) - gl['fb_x']).max() < 1e-8
+
+
+def test_the_late_gpu_tests_themselves_run_clean_on_the_emulation(golden_dir, monkeypatch):
+    """The GPU test files added after the round's last GPU run (tests/test_gpu_zz_*.py) are executed here, body for
+    body, on the CPU stand-ins (their DEV constant pointed at the CPU), so that a slip in the TEST code cannot be
+    what fails on the GPU box"""
+    from tests.cpu_emulation import su3_host_logic_on_cpu
+    import tests.test_gpu_zz_unmerged_and_verbose as zu
+    import tests.test_gpu_zz_improved_action_acc as zi
+    monkeypatch.setattr(zu, 'DEV', 'cpu')
+    monkeypatch.setattr(zi, 'DEV', 'cpu')
+    old = torch.get_default_dtype()
+    try:
+        with u1_host_logic_on_cpu(monkeypatch):
+            for tag, tol in (('f64', 1e-11), ('f32', 2e-5)):
+                zu.test_unmerged_transition_kernel_matches_reference(golden_dir, tag, tol)
+                zu.test_verbose_histories_match_reference(golden_dir, tag, tol)
+            zu.test_forward_without_merge_directions_goes_through_apply_transition(golden_dir)
+        with su3_host_logic_on_cpu(monkeypatch):
+            for kernel in (True, False):
+                zi.test_hmc_accepts_with_the_energies_of_potential_fn(golden_dir, kernel)
+            import tests.test_gpu_reuse_force as zr          # opt-in on the GPU; its no-autocast body runs here
+            monkeypatch.setattr(zr, 'DEV', 'cpu')
+            zr.test_su3_fb_sweep_is_bit_identical_and_evaluates_fewer_forces(golden_dir, False)
+    finally:
+        torch.set_default_dtype(old)
