@@ -21,7 +21,9 @@ def _field(x, shape=None):
 
 
 def _e(eps, like):
-    return eps.detach().to(like.dtype) if isinstance(eps, torch.Tensor) else torch.tensor(float(eps), dtype=like.dtype)
+    if isinstance(eps, torch.Tensor):
+        return eps.to(like.dtype) if eps.requires_grad else eps.detach().to(like.dtype)
+    return torch.tensor(float(eps), dtype=like.dtype)
 
 
 def u1_wilson_loops(x, shape=None):
@@ -116,6 +118,65 @@ def accept_mix(accept, pairs):
     nb = accept.numel()
     sel = accept.reshape(nb, 1) > 0
     return [torch.where(sel, b.to(a.dtype).reshape(nb, -1), a.reshape(nb, -1)) for a, b in pairs]
+
+
+# ---- adjoints of the U(1) stand-ins: vector-Jacobian products by torch autograd of the functions above ----
+def _leaf(a):
+    return None if a is None else a.detach().clone().requires_grad_(True)
+
+
+def _vjp(outs, gouts, leaves):
+    pairs = [(o, g) for o, g in zip(outs, gouts) if g is not None]
+    live = [a for a in leaves if a is not None]
+    grads = iter(torch.autograd.grad([o for o, _ in pairs], live, grad_outputs=[g.to(o.dtype).reshape(o.shape) for o, g in pairs],
+                                     allow_unused=True))
+    res = []
+    for a in leaves:
+        if a is None:
+            res.append(None)
+        else:
+            g = next(grads)
+            res.append(torch.zeros_like(a) if g is None else g)
+    return res
+
+
+def u1_wilson_loops_bwd(gw):
+    nb, T, X = gw.shape
+    with torch.enable_grad():
+        x = torch.zeros(nb, 2, T, X, dtype=gw.dtype, requires_grad=True)
+        return _vjp([u1_wilson_loops(x)], [gw], [x])[0]
+
+
+def u1_force_bwd(x, beta, gforce, shape=None):
+    with torch.enable_grad():
+        x4 = _leaf(_field(x, shape))
+        return _vjp([u1_force(x4, beta)], [gforce.reshape(x4.shape)], [x4])[0]
+
+
+def rowscale(a, scale):
+    return a * scale.to(a.dtype).reshape(-1, *([1] * (a.dim() - 1)))
+
+
+def u1_vupdate_bwd(v, force, s, t, q, eps, sign, gv_out, glogdet):
+    nb = v.shape[0]
+    with torch.enable_grad():
+        lv, lf = _leaf(v.reshape(nb, -1)), _leaf(force.to(v.dtype).reshape(nb, -1))
+        ls, lt, lq = (_leaf(_rows(a, nb, lv)) for a in (s, t, q))
+        e = _e(eps, lv).expand(nb).clone().requires_grad_(True)          # one step size per chain -> per-chain d/d eps
+        out, logdet = u1_vupdate(lv, lf, ls, lt, lq, e[:, None], sign)
+        gv, gf, gs, gt, gq, ge = _vjp([out, logdet], [gv_out, glogdet], [lv, lf, ls, lt, lq, e])
+    return gv, gf, gs, gt, gq, ge
+
+
+def u1_xupdate_bwd(x, v, s, t, q, mask, eps, sign, use_ncp, gx_out, glogdet):
+    nb = x.shape[0]
+    with torch.enable_grad():
+        lx, lv = _leaf(x.reshape(nb, -1)), _leaf(v.to(x.dtype).reshape(nb, -1))
+        ls, lt, lq = (_leaf(_rows(a, nb, lx)) for a in (s, t, q))
+        e = _e(eps, lx).expand(nb).clone().requires_grad_(True)
+        out, logdet = u1_xupdate(lx, lv, ls, lt, lq, mask, e[:, None], sign, use_ncp)
+        gx, gv, gs, gt, gq, ge = _vjp([out, logdet], [gx_out, glogdet], [lx, lv, ls, lt, lq, e])
+    return gx, gv, gs, gt, gq, ge
 
 
 class _FakeCuda:
@@ -274,7 +335,8 @@ def u1_host_logic_on_cpu(monkeypatch):
     from l2hmc_b200.network.pytorch import network as net
     from l2hmc_b200.group.u1.pytorch import group as gu1
     for name in ('u1_wilson_loops', 'u1_observables', 'u1_force', 'u1_kinetic', 'u1_compat_proj', 'u1_vupdate',
-                 'u1_xupdate', 'u1_hmc_trajectory', 'accept_mix'):
+                 'u1_xupdate', 'u1_hmc_trajectory', 'accept_mix', 'u1_wilson_loops_bwd', 'u1_force_bwd', 'rowscale',
+                 'u1_vupdate_bwd', 'u1_xupdate_bwd'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'u1_heads_supported', lambda hidden: False)      # fused kernels: GPU tier only
     monkeypatch.setattr(ops, 'u1_input_supported', lambda units: False)

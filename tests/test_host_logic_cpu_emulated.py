@@ -328,3 +328,19 @@ def test_the_late_gpu_tests_themselves_run_clean_on_the_emulation(golden_dir, mo
             zr.test_su3_fb_sweep_is_bit_identical_and_evaluates_fewer_forces(golden_dir, False)
     finally:
         torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('tag,rtol', [('f64', 1e-9), ('f32', 5e-3)])
+@pytest.mark.parametrize('name', ['dense', 'conv'])
+def test_u1_training_gradients_through_the_autograd_wiring(golden_dir, monkeypatch, tag, rtol, name):
+    """The body of the GPU tier's gradient test (tests/test_gpu_training.py) on the CPU stand-ins (adjoints = torch
+    vjps of the stand-ins): every parameter / step-size / input gradient our `torch.autograd.Function` wiring
+    produces must equal the reference's autograd goldens"""
+    import tests.test_gpu_training as tg
+    monkeypatch.setattr(tg, 'DEV', 'cpu')
+    old = torch.get_default_dtype()
+    try:
+        with u1_host_logic_on_cpu(monkeypatch):
+            tg.test_u1_l2hmc_gradients_match_reference_autograd(golden_dir, torch.set_default_dtype, tag, rtol, name)
+    finally:
+        torch.set_default_dtype(old)
