@@ -344,4 +344,5 @@ def u1_host_logic_on_cpu(monkeypatch):
     monkeypatch.setattr(net, '_device', cpu)
     monkeypatch.setattr(gu1, '_device', cpu)
     monkeypatch.setattr(dmod, 'torch', _TorchProxy())
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)   # Trainer.train_step asks
     yield

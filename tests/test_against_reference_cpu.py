@@ -271,3 +271,65 @@ def test_public_transitions_match_the_reference_under_the_same_seed(ref, monkeyp
                     so, sr = getattr(m_o['mc_states'], part), getattr(m_r['mc_states'], part)
                     assert float((so.x.reshape(nb, -1) - sr.x.detach().reshape(nb, -1)).abs().max()) < 1e-10, (name, part)
                     assert float((so.v.reshape(nb, -1) - sr.v.detach().reshape(nb, -1)).abs().max()) < 1e-10, (name, part)
+
+
+def test_train_steps_match_the_reference_under_the_same_seed(ref, monkeypatch):
+    """`Trainer.train_step` (forward, LatticeLoss, backward through our autograd Functions, Adam) on the CPU stand-ins
+    against the same step written with the reference's Dynamics / LatticeLoss / torch autograd: after three steps
+    from the same weights, masks and seeds the losses and every parameter still agree"""
+    from tests.cpu_emulation import u1_host_logic_on_cpu
+    from l2hmc_b200 import configs as c
+    shape, nb, nlf = [6, 4], 4, 2
+    kw = dict(nchains=nb, group='U1', latvolume=shape, nleapfrog=nlf, eps=0.1, eps_hmc=0.1, use_ncp=True,
+              verbose=False, use_split_xnets=True, use_separate_networks=True, merge_directions=True)
+    ncfg = dict(units=[8, 6], activation_fn='tanh', dropout_prob=0.0, use_batch_norm=False)
+    lkw = dict(use_mixed_loss=True, charge_weight=0.01, rmse_weight=0.0, plaq_weight=0.0)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    rcfg = ref.DynamicsConfig(**kw)
+    rlat = ref.LatticeU1(nb, shape)
+    xdim = rcfg.xdim
+    rfac = ref.NetworkFactory(input_spec=ref.InputSpec(xshape=rcfg.xshape, xnet={'x': [xdim, 2], 'v': [xdim]},
+                                                       vnet={'x': [xdim], 'v': [xdim]}),
+                              network_config=ref.NetworkConfig(**ncfg), conv_config=None, net_weights=None)
+    rdyn = ref.Dynamics(potential_fn=rlat.action, config=rcfg, network_factory=rfac)
+    for p in rdyn.parameters():
+        if p.dim() == 2 and p.shape[0] == 1:
+            torch.nn.init.normal_(p, std=0.3)
+    x0 = 2.0 * rlat.random().detach()                 # beyond [-pi, pi): both steps wrap it first
+    beta = torch.tensor(2.0)
+    with u1_host_logic_on_cpu(monkeypatch):
+        from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+        from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+        from l2hmc_b200.network.pytorch.network import NetworkFactory
+        from l2hmc_b200.trainers.pytorch.trainer import Trainer
+        ocfg = c.DynamicsConfig(**kw)
+        fac = NetworkFactory(input_spec=c.get_input_spec(ocfg), network_config=c.NetworkConfig(**ncfg),
+                             conv_config=None, net_weights=None)
+        odyn = Dynamics(potential_fn=LatticeU1(nb, shape).action, config=ocfg, network_factory=fac)
+        odyn.load_state_dict(rdyn.state_dict(), strict=True)
+        odyn.masks = [m.clone() for m in rdyn.masks]
+        tr = Trainer(odyn, loss_config=c.LossConfig(**lkw), lr=1e-3)
+        rloss_fn = ref.LatticeLoss(rlat, ref.cfgs.LossConfig(**lkw))
+        ropt = torch.optim.Adam([p for p in rdyn.parameters() if p.requires_grad], lr=1e-3)
+        rdyn.train()
+        xr = xo = x0
+        for step in range(3):
+            torch.manual_seed(100 + step)
+            ropt.zero_grad()
+            xi = rlat.g.compat_proj(xr.reshape(rcfg.xshape))
+            xout_r, m_r = rdyn((xi, beta))
+            loss_r = rloss_fn(x_init=xi, x_prop=m_r.pop('mc_states').proposed.x, acc=m_r['acc'])
+            loss_r.backward()
+            ropt.step()
+            xr = xout_r.detach()
+            torch.manual_seed(100 + step)
+            xo, m_o = tr.train_step((xo, beta))
+            assert float((m_o['loss'] - loss_r.detach()).abs()) < 1e-9 * max(1.0, float(loss_r.abs())), step
+            assert float((xo - xr.reshape(xo.shape)).abs().max()) < 1e-9, step
+        ours = dict(odyn.named_parameters())
+        n = 0
+        for k, p in rdyn.named_parameters():
+            assert float((ours[k] - p).abs().max()) < 1e-8, k
+            n += 1
+        assert n > 40
