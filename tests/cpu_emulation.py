@@ -309,6 +309,15 @@ def su3_hmc_trajectory(x, v, beta, eps, nlf):
     return torch.from_numpy(sp.x), torch.from_numpy(sp.v), en
 
 
+def su3_rand_momentum(nb, dims, seed, offset, device, want_ke=False, offset_dev=None):
+    """Gaussian traceless anti-Hermitian momenta from the oracle's generator, keyed like the kernel's Philox stream"""
+    import numpy as np
+    from oracle import su3 as o
+    rng = np.random.default_rng([int(seed) & (2**63 - 1), int(offset)])
+    p = torch.from_numpy(o.random_momentum(rng, (nb, 4, *[int(d) for d in dims], 3, 3)))
+    return (p, su3_kinetic(p)) if want_ke else p
+
+
 @contextlib.contextmanager
 def su3_host_logic_on_cpu(monkeypatch):
     """as u1_host_logic_on_cpu, for the boundary-layout (unfused, no-grad) SU(3) path"""
@@ -317,13 +326,14 @@ def su3_host_logic_on_cpu(monkeypatch):
     from l2hmc_b200.network.pytorch import network as net
     from l2hmc_b200.group.su3.pytorch import group as g3
     for name in ('su3_plaq_sums', 'su3_wilson_loops', 'su3_force', 'su3_force_c1', 'su3_project', 'su3_project_vec',
-                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'accept_mix'):
+                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'accept_mix'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'heads_supported', lambda hidden: False)         # tcgen05 heads: GPU tier only
     cpu = lambda: torch.device('cpu')  # noqa: E731
     monkeypatch.setattr(net, '_device', cpu)
     monkeypatch.setattr(g3, '_device', cpu)
     monkeypatch.setattr(dmod, 'torch', _TorchProxy())
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
     yield
 
 

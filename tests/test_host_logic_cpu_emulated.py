@@ -344,3 +344,24 @@ def test_u1_training_gradients_through_the_autograd_wiring(golden_dir, monkeypat
             tg.test_u1_l2hmc_gradients_match_reference_autograd(golden_dir, torch.set_default_dtype, tag, rtol, name)
     finally:
         torch.set_default_dtype(old)
+
+
+def test_gpu_tier_bodies_that_only_need_host_logic_run_on_the_emulation(golden_dir, monkeypatch):
+    """Regression net for work done without a GPU: the bodies of the GPU tier's Dynamics / Trainer tests whose
+    kernels have stand-ins are executed here on the CPU (same assertions, same goldens)"""
+    from tests.cpu_emulation import su3_host_logic_on_cpu
+    import tests.test_gpu_dynamics as td
+    import tests.test_gpu_trainer as tt
+    for mod in (td, tt):
+        monkeypatch.setattr(mod, 'DEV', 'cpu')
+    old = torch.get_default_dtype()
+    try:
+        with u1_host_logic_on_cpu(monkeypatch):
+            for tag, tol in (('f64', 1e-11), ('f32', 2e-5)):
+                for name in ('dense', 'conv'):
+                    td.test_u1_l2hmc_matches_reference(golden_dir, torch.set_default_dtype, tag, tol, name, 'never')
+            tt.test_u1_trainer_steps(torch.set_default_dtype)
+        with su3_host_logic_on_cpu(monkeypatch):
+            td.test_su3_l2hmc_matches_reference(golden_dir, torch.set_default_dtype)
+    finally:
+        torch.set_default_dtype(old)
