@@ -365,3 +365,38 @@ def test_gpu_tier_bodies_that_only_need_host_logic_run_on_the_emulation(golden_d
             td.test_su3_l2hmc_matches_reference(golden_dir, torch.set_default_dtype)
     finally:
         torch.set_default_dtype(old)
+
+
+def test_u1_gradients_are_unchanged_by_force_reuse(golden_dir, emulated, dtype_of):
+    """training with `reuse_force = 'always'`: the shared force tensor receives the cotangents of both v-updates
+    it feeds, so every gradient equals the default's (to rounding: the sums are formed in a different order)"""
+    from l2hmc_b200.dynamics.pytorch.dynamics import State
+    dtype_of('f64')
+    gu = np.load(golden_dir / 'u1_f64.npz')
+    pre = 'dense/'
+    dyn = _dynamics(gu, 'dense', verbose=False)
+    n = {'force': 0}
+    orig = dyn.grad_potential
+
+    def counting(x, beta):
+        n['force'] += 1
+        return orig(x, beta)
+    dyn.grad_potential = counting
+    res = {}
+    for mode in ('never', 'always'):
+        dyn.reuse_force = mode
+        dyn.zero_grad(set_to_none=True)
+        n['force'] = 0
+        x = torch.from_numpy(gu['x']).requires_grad_(True)
+        st = State(x, torch.from_numpy(gu[pre + 'v']), torch.tensor(float(gu['beta'])))
+        sp, met = dyn.transition_kernel_fb(st)
+        loss = (met['acc'] * sp.x.flatten(1).cos().sum(1)).sum() + met['sumlogdet'].sum()
+        loss.backward()
+        res[mode] = (float(loss), x.grad.clone(), {k: p.grad.clone() for k, p in dyn.named_parameters() if p.grad is not None},
+                     n['force'])
+    assert res['never'][3] == 8 and res['always'][3] == 5            # 4 nlf vs 2 nlf + 1 at nlf = 2
+    assert res['never'][0] == res['always'][0]
+    assert float((res['never'][1] - res['always'][1]).abs().max()) <= 1e-12 * float(res['never'][1].abs().max())
+    assert set(res['never'][2]) == set(res['always'][2]) and len(res['never'][2]) > 40
+    for k, g0 in res['never'][2].items():
+        assert float((g0 - res['always'][2][k]).abs().max()) <= 1e-12 * max(1e-30, float(g0.abs().max())), k
