@@ -255,6 +255,40 @@ def su3_force_c1(x, beta, c1, want_force=True, want_sums=False):
     return (f, sums) if want_sums else f
 
 
+def _improved_staples_adjoint(x, c1):
+    """Aimp^+ = [(1 - 8 c1) A + c1 R]^+ from torch autograd: dS/dx = -(beta/3) Aimp^+ at beta = 3 gives -Aimp^+"""
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    lat = LatticeSU3(x.shape[0], list(x.shape[2:6]), c1=c1)
+    with torch.enable_grad():
+        xr = x.detach().clone().requires_grad_(True)
+        tr = lambda a: torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)  # noqa: E731
+        ps = 0.0
+        for u in range(1, 4):
+            for v in range(u):
+                ps = ps + tr(lat._plaquette(xr, u, v)).real.flatten(1).sum(1)
+        act = -(1 - 8 * c1) * ps + lat._rect_action(xr, 3.0)
+        g, = torch.autograd.grad(act.sum(), xr)
+    return -g
+
+
+def su3_action_grad_c1(x, c1, coef=None, scale=0.0, gforce=None):
+    ah = _improved_staples_adjoint(x, c1)
+    if gforce is None:
+        return coef.to(torch.float64).reshape(-1, *([1] * (x.dim() - 1))) * ah
+    gf = gforce.reshape(x.shape)
+    a = 0.5 * (gf - gf.mH)
+    th = a - torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)[..., None, None] / 3.0 * torch.eye(3, dtype=a.dtype)
+    return th.mH @ (scale * ah)
+
+
+def su3_action_grad(x, coef):
+    return su3_action_grad_c1(_full(x), 0.0, coef=coef)
+
+
+def su3_force_bwd(x, beta, gforce):
+    return su3_action_grad_c1(_full(x), 0.0, scale=-float(beta) / 3.0, gforce=gforce)
+
+
 def su3_project(x, want_matrix=True, want_vec=False):
     from oracle import su3 as o
     m = o.projectSU(_np(x))
@@ -326,7 +360,7 @@ def su3_host_logic_on_cpu(monkeypatch):
     from l2hmc_b200.network.pytorch import network as net
     from l2hmc_b200.group.su3.pytorch import group as g3
     for name in ('su3_plaq_sums', 'su3_wilson_loops', 'su3_force', 'su3_force_c1', 'su3_project', 'su3_project_vec',
-                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'accept_mix'):
+                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'su3_action_grad_c1', 'su3_action_grad', 'su3_force_bwd', 'accept_mix'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'heads_supported', lambda hidden: False)         # tcgen05 heads: GPU tier only
     cpu = lambda: torch.device('cpu')  # noqa: E731
