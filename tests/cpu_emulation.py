@@ -343,6 +343,83 @@ def su3_hmc_trajectory(x, v, beta, eps, nlf):
     return torch.from_numpy(sp.x), torch.from_numpy(sp.v), en
 
 
+# ---- SU(3) adjoints: vjps of DIFFERENTIABLE torch restatements (independent of the kernels' closed forms) ----
+def _t_project_su(x):
+    """projectSU in torch, smooth at unitary input: the polar factor by Newton's iteration U <- (U + U^-+)/2
+    (autograd through `inv` only; the closed-form eigen route is singular exactly where lattice links live), then
+    the determinant phase exp(-i arg det / 3)"""
+    u = x
+    for _ in range(64):
+        u = 0.5 * (u + torch.linalg.inv(u).mH)
+    ph = torch.angle(torch.linalg.det(u)) / 3.0
+    return u * torch.polar(torch.ones_like(ph), -ph)[..., None, None]
+
+
+def _t_su3_to_vec(x):
+    c = -2.0
+    x00, x01, x02, x11, x12, x22 = x[..., 0, 0], x[..., 0, 1], x[..., 0, 2], x[..., 1, 1], x[..., 1, 2], x[..., 2, 2]
+    return torch.stack([c * x01.imag, c * x01.real, x11.imag - x00.imag, c * x02.imag, c * x02.real, c * x12.imag,
+                        c * x12.real, (2.0 * x22.imag - x11.imag - x00.imag) / 3.0 ** 0.5], -1)
+
+
+def su3_project_bwd(x, gmat=None, gvec=None):
+    with torch.enable_grad():
+        lx = _leaf(x)
+        y = _t_project_su(lx)
+        outs, gs = [], []
+        if gmat is not None:
+            outs.append(y)
+            gs.append(gmat)
+        if gvec is not None:
+            outs.append(_t_su3_to_vec(y))
+            gs.append(gvec.to(torch.float64))
+        return _vjp(outs, gs, [lx])[0]
+
+
+def su3_vupdate_bwd(v, force, s, t, q, eps, sign, gv_out, glogdet):
+    nb = v.shape[0]
+    with torch.enable_grad():
+        lv, lf = _leaf(v.reshape(nb, -1)), _leaf(force.reshape(nb, -1))
+        ls, lt, lq = (None if a is None else _leaf(a.to(torch.float64).reshape(nb, -1)) for a in (s, t, q))
+        e = torch.full((nb,), float(eps), dtype=torch.float64, requires_grad=True)
+        z = torch.zeros(lv.shape, dtype=torch.float64)
+        ss, tt, qq = (z if a is None else a for a in (ls, lt, lq))
+        ee = e[:, None]
+        kick = 0.5 * ee * (lf * torch.exp(ee * qq) + tt)
+        if sign > 0:
+            out, logdet = torch.exp(0.5 * ee * ss) * lv - kick, (0.5 * ee * ss).sum(1)
+        else:
+            out, logdet = torch.exp(-0.5 * ee * ss) * (lv + kick), -(0.5 * ee * ss).sum(1)
+        gv, gf, gs, gt, gq, ge = _vjp([out, logdet], [gv_out.reshape(nb, -1), glogdet], [lv, lf, ls, lt, lq, e])
+    return gv.reshape(v.shape), gf.reshape(v.shape), gs, gt, gq, ge
+
+
+def su3_update_gauge_bwd(x, p, eps, mask, mask_complement, gx_out, eps_mult=1.0):
+    nb = x.shape[0]
+    with torch.enable_grad():
+        lx, lp = _leaf(x), _leaf(p.reshape(x.shape))
+        e = torch.full((nb,), float(eps) * float(eps_mult), dtype=torch.float64, requires_grad=True)
+        ex = torch.linalg.matrix_exp(e.reshape(nb, *([1] * (x.dim() - 1))) * lp)
+        if mask is None:
+            out = ex @ lx
+        else:
+            m = mask.to(torch.float64).reshape(1, *x.shape[1:])
+            if mask_complement:
+                m = 1.0 - m
+            out = m * lx + ex @ ((1.0 - m) * lx)
+        gx, gp, ge = _vjp([out], [gx_out.reshape(x.shape)], [lx, lp, e])
+    return gx, gp, ge, torch.zeros(1, dtype=torch.int32)
+
+
+def su3_wilson_loops_bwd(x, gw):
+    from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
+    lat = LatticeSU3(x.shape[0], list(x.shape[2:6]))
+    with torch.enable_grad():
+        lx = _leaf(x)
+        w = torch.stack([lat._trace_plaquette(lx, u, v) for u in range(1, 4) for v in range(u)])
+        return _vjp([w], [gw], [lx])[0]
+
+
 def su3_rand_momentum(nb, dims, seed, offset, device, want_ke=False, offset_dev=None):
     """Gaussian traceless anti-Hermitian momenta from the oracle's generator, keyed like the kernel's Philox stream"""
     import numpy as np
@@ -360,7 +437,8 @@ def su3_host_logic_on_cpu(monkeypatch):
     from l2hmc_b200.network.pytorch import network as net
     from l2hmc_b200.group.su3.pytorch import group as g3
     for name in ('su3_plaq_sums', 'su3_wilson_loops', 'su3_force', 'su3_force_c1', 'su3_project', 'su3_project_vec',
-                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'su3_action_grad_c1', 'su3_action_grad', 'su3_force_bwd', 'accept_mix'):
+                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'su3_action_grad_c1', 'su3_action_grad', 'su3_force_bwd', 'su3_project_bwd', 'su3_vupdate_bwd',
+                 'su3_update_gauge_bwd', 'su3_wilson_loops_bwd', 'rowscale', 'accept_mix'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'heads_supported', lambda hidden: False)         # tcgen05 heads: GPU tier only
     cpu = lambda: torch.device('cpu')  # noqa: E731

@@ -403,3 +403,18 @@ def test_u1_gradients_are_unchanged_by_force_reuse(golden_dir, emulated, dtype_o
     assert set(res['never'][2]) == set(res['always'][2]) and len(res['never'][2]) > 40
     for k, g0 in res['never'][2].items():
         assert float((g0 - res['always'][2][k]).abs().max()) <= 1e-12 * max(1e-30, float(g0.abs().max())), k
+
+
+def test_su3_training_gradients_through_the_autograd_wiring(golden_dir, monkeypatch):
+    """The SU(3) gradient-golden test of the GPU tier on the CPU: adjoint stand-ins are torch vjps of smooth
+    restatements (polar factor by Newton iteration, torch.matrix_exp), i.e. independent of the kernels' closed
+    forms; what is exercised is our autograd Function wiring against the reference's autograd goldens"""
+    from tests.cpu_emulation import su3_host_logic_on_cpu
+    import tests.test_gpu_training as tg
+    monkeypatch.setattr(tg, 'DEV', 'cpu')
+    old = torch.get_default_dtype()
+    try:
+        with su3_host_logic_on_cpu(monkeypatch):
+            tg.test_su3_l2hmc_gradients_match_reference_autograd(golden_dir, torch.set_default_dtype)
+    finally:
+        torch.set_default_dtype(old)
