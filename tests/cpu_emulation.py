@@ -303,6 +303,12 @@ def su3_project_vec(x, dtype=torch.float64):
     return torch.from_numpy(o.group_to_vec(_np(x))).to(dtype)
 
 
+def su3_check(x):
+    from oracle import su3 as o
+    avg, mx = o.checkSU(_np(x))
+    return torch.from_numpy(avg), torch.from_numpy(mx)
+
+
 def su3_kinetic(p):
     from oracle import su3 as o
     return torch.from_numpy(o.kinetic_energy(_np(p)))
@@ -437,7 +443,7 @@ def su3_host_logic_on_cpu(monkeypatch):
     from l2hmc_b200.network.pytorch import network as net
     from l2hmc_b200.group.su3.pytorch import group as g3
     for name in ('su3_plaq_sums', 'su3_wilson_loops', 'su3_force', 'su3_force_c1', 'su3_project', 'su3_project_vec',
-                 'su3_kinetic', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'su3_action_grad_c1', 'su3_action_grad', 'su3_force_bwd', 'su3_project_bwd', 'su3_vupdate_bwd',
+                 'su3_kinetic', 'su3_check', 'su3_update_gauge', 'su3_vupdate', 'su3_hmc_trajectory', 'su3_rand_momentum', 'su3_action_grad_c1', 'su3_action_grad', 'su3_force_bwd', 'su3_project_bwd', 'su3_vupdate_bwd',
                  'su3_update_gauge_bwd', 'su3_wilson_loops_bwd', 'rowscale', 'accept_mix'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'heads_supported', lambda hidden: False)         # tcgen05 heads: GPU tier only

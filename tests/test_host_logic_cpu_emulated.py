@@ -329,6 +329,7 @@ def test_the_late_gpu_tests_themselves_run_clean_on_the_emulation(golden_dir, mo
             import tests.test_gpu_reuse_force as zr          # opt-in on the GPU; its no-autocast body runs here
             monkeypatch.setattr(zr, 'DEV', 'cpu')
             zr.test_su3_fb_sweep_is_bit_identical_and_evaluates_fewer_forces(golden_dir, False)
+            zr.test_su3_gradients_with_reuse_equal_default(golden_dir)
     finally:
         torch.set_default_dtype(old)
 
@@ -366,6 +367,7 @@ def test_gpu_tier_bodies_that_only_need_host_logic_run_on_the_emulation(golden_d
             tt.test_u1_trainer_steps(torch.set_default_dtype)
         with su3_host_logic_on_cpu(monkeypatch):
             td.test_su3_l2hmc_matches_reference(golden_dir, torch.set_default_dtype)
+            tt.test_su3_trainer_steps(torch.set_default_dtype)
     finally:
         torch.set_default_dtype(old)
 
