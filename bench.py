@@ -317,6 +317,14 @@ def main_ours(args):
     lat = LatticeSU3(nb, lattice) if su3 else LatticeU1(nb, lattice)
     dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
     x = lat.random()
+    if args.thermalise > 0:
+        # hot-start links make the acos / exp arguments atypical; optionally time from a
+        # configuration relaxed by N accepted-or-rejected HMC trajectories (trainer.py:1699-1744 `warmup`)
+        with torch.no_grad():
+            for _ in range(args.thermalise):
+                xo_, _m = dyn.apply_transition_hmc((x, torch.tensor(beta)), eps=eps, nleapfrog=nlf)
+                x = xo_.reshape(x.shape)
+        x = x.contiguous()
     v = lat.random_momentum()
     field_bytes = x.numel() * x.element_size()
 
@@ -429,7 +437,8 @@ def main_ours(args):
             'vs_baseline': None, 'dtype': 'f64' if dtype == 'f64' else 'f32', 'data': 'synthetic',
             'config': {'workload': args.workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'eps': eps, 'beta': beta,
-                       'start': 'hot (g.random)', 'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
+                       'start': ('hot (g.random)' if args.thermalise <= 0 else f'thermalised ({args.thermalise} HMC trajectories from a hot start)'),
+                       'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
                        'l2_policy': f'inputs larger than L2 ({field_bytes / 2**20:.0f} MiB per field per GPU), no flush'
                        if field_bytes > 200 * 2**20 else 'working set fits L2; fields re-read every step (no flush)'},
             'hbm_model': {'bytes_per_link_update': gb, 'achieved_GBps_per_gpu': value / world * gb / 1e9,
@@ -669,6 +678,8 @@ def main():
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--workload', choices=sorted(WORKLOADS) + sorted(L2HMC_WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--thermalise', type=int, default=0,
+                    help='HMC trajectories run before timing (default 0: hot start, as the reference\'s g.random)')
     ap.add_argument('--cuda-graphs', action='store_true',
                     help='L2HMC workloads: run the Trainer step functions as CUDA graphs (Trainer(cuda_graphs=True))')
     args = ap.parse_args()
