@@ -5,8 +5,15 @@ unmodified modules copied to `oracle/_ref`) on small seeded inputs and freezes
 inputs + outputs into `tests/golden/*.npz`.  The reference ships no tests or
 golden vectors, so these files are what pins parity:
 
-  * `tests/test_oracle_golden.py`   numpy oracle  == golden   (CPU, not gpu)
-  * `tests/test_gpu_parity_*.py`    CUDA path     == golden   (-m gpu)
+  * `tests/test_oracle_golden.py`            numpy oracle == golden            (CPU)
+  * `tests/test_hostemu.py`                  kernel bodies on the host == golden (CPU)
+  * `tests/test_host_logic_cpu_emulated.py`  our Dynamics / Trainer on CPU stand-ins == golden (CPU)
+  * `tests/test_gpu_*.py`                    CUDA path == golden                 (-m gpu)
+
+Contents: lattice / group functions, HMC trajectories, the merged and un-merged L2HMC kernels, verbose per-step
+histories, LatticeLoss, parameter / input gradients from the reference's autograd, per-function VJPs, and the
+improved action (c1 != 0) incl. an HMC case whose acceptance is not trivially 1.  Seeds are fixed: regenerating
+reproduces every existing key bit for bit (checked whenever keys are added).
 
 Run here (needs /root/reference):   python oracle/make_golden.py
 It re-executes itself once per default dtype, because the reference freezes
