@@ -11,9 +11,8 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-sys.path.insert(0, str(Path(__file__).resolve().parent))
 from l2hmc_b200 import dist as l2d  # noqa: E402
-from test_gpu_trainer import _su3_trainer  # noqa: E402
+from tests._helpers import _su3_trainer  # noqa: E402
 
 
 def main():

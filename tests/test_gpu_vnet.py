@@ -138,7 +138,7 @@ def test_fused_heads_function_matches_unfused_path_and_gradients(sign):
 def test_dynamics_uses_tensor_core_heads_under_bf16_autocast():
     """BASELINE cfg 5 path: under bf16 autocast the SU(3) v-update runs k_heads_vupdate; the
     sweep agrees with the unfused bf16 path to bf16 accuracy and the train step yields finite grads"""
-    from test_gpu_trainer import _su3_trainer
+    from tests._helpers import _su3_trainer
     from l2hmc_b200 import _lib
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float32)
@@ -174,7 +174,7 @@ def test_dynamics_uses_tensor_core_heads_under_bf16_autocast():
 def test_planar_inference_sweep_matches_boundary_layout_sweep():
     """Dynamics.transition_kernel_fb with the state kept planar (no layout conversion around the stencil
     kernels, head weights packed with permuted rows) == the boundary-layout sweep, link for link"""
-    from test_gpu_trainer import _su3_trainer
+    from tests._helpers import _su3_trainer
     from l2hmc_b200.dynamics.pytorch.dynamics import State
     from l2hmc_b200 import _lib
     old = torch.get_default_dtype()
