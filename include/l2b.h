@@ -50,6 +50,13 @@ extern "C" {
 
 const char* l2b_last_error(void);
 int l2b_version(void);
+/* first 32 bits of the SHA-256 of the include/l2b.h this library was compiled against (set by the
+ * build as -DL2B_ABI_HASH=...; 0 for a build that did not pass it).  The ctypes binding compares it
+ * with the header next to it and refuses / rebuilds a stale binary: many entry points take
+ * positional pointer arguments, a mismatch would be silent memory corruption */
+uint32_t l2b_abi_hash(void);
+/* same over the header and every file under csrc/: identifies the source tree the binary was built from */
+uint32_t l2b_source_hash(void);
 /* number of kernel launches issued by this library on behalf of the calling
  * process since load (bench.py reports it as gpu_launches) */
 uint64_t l2b_launch_count(void);

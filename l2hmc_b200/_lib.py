@@ -21,16 +21,54 @@ class L2BError(RuntimeError):
     pass
 
 
+def _hashes(lib: ctypes.CDLL) -> tuple[int, int]:
+    out = []
+    for name in ('l2b_abi_hash', 'l2b_source_hash'):
+        f = getattr(lib, name, None)
+        if f is None:
+            out.append(-1)            # a binary older than these exports
+            continue
+        f.argtypes, f.restype = [], ctypes.c_uint32
+        out.append(int(f()))
+    return out[0], out[1]
+
+
 def _load() -> ctypes.CDLL:
+    """dlopen libl2b.so and make sure it is THE library of this tree: its `l2b_abi_hash()` must equal the
+    hash of include/l2b.h (the signatures below are transcribed from that header; a stale binary under new
+    positional pointer arguments would corrupt memory silently) and its `l2b_source_hash()` the hash of csrc/.
+    A mismatching or missing library is rebuilt when a compiler is there (L2B_AUTOBUILD=1, the default; one
+    builder at a time under a file lock), otherwise this raises.  There is no CPU fallback."""
+    from . import _build
+    auto = os.environ.get('L2B_AUTOBUILD', '1') == '1'
     if not LIB_PATH.exists():
-        if os.environ.get('L2B_AUTOBUILD', '1') == '1':
-            from . import _build
-            _build.build()
+        if auto:
+            _build.build(force=True)
         if not LIB_PATH.exists():
             raise L2BError(
                 f'{LIB_PATH} is missing: build it with `python -m l2hmc_b200._build` '
                 '(or __graft_entry__.build()); there is no CPU fallback')
-    return ctypes.CDLL(str(LIB_PATH))
+    lib = ctypes.CDLL(str(LIB_PATH))
+    want = (_build.abi_hash(), _build.source_hash()) if _build.HEADER.exists() else None
+    if want is None or _hashes(lib) == want:
+        return lib
+    if auto:
+        import _ctypes
+        _ctypes.dlclose(lib._handle)
+        del lib
+        try:
+            _build.build(force=True)
+        except RuntimeError as e:
+            raise L2BError(f'{LIB_PATH} does not match this source tree and could not be rebuilt: {e}') from e
+        lib = ctypes.CDLL(str(LIB_PATH))
+    got = _hashes(lib)
+    if got[0] != want[0]:
+        raise L2BError(f'{LIB_PATH} was built against a different include/l2b.h (abi hash {got[0]:#x}, header '
+                       f'{want[0]:#x}): rebuild with `python -m l2hmc_b200._build --force`')
+    if got[1] != want[1]:
+        raise L2BError(f'{LIB_PATH} was built from different sources (hash {got[1]:#x}, tree {want[1]:#x}): '
+                       'rebuild with `python -m l2hmc_b200._build --force`')
+    return lib
 
 
 _lib = _load()
@@ -98,6 +136,8 @@ _SIGS = {
 _RES = {
     'l2b_last_error': ([], c_char_p),
     'l2b_version': ([], c_int),
+    'l2b_abi_hash': ([], ctypes.c_uint32),
+    'l2b_source_hash': ([], ctypes.c_uint32),
     'l2b_launch_count': ([], c_uint64),
     'l2b_su3_ws_bytes': ([c_int, _DIMS, c_int], c_size_t),
     'l2b_u1_ws_bytes': ([c_int, c_int, c_int, c_int], c_size_t),

@@ -58,7 +58,16 @@ extern "C" {
 
 const char* l2b_last_error(void) { return g_err; }
 
-int l2b_version(void) { return 100; }
+int l2b_version(void) { return 200; }
+
+#ifndef L2B_ABI_HASH
+#define L2B_ABI_HASH 0u
+#endif
+uint32_t l2b_abi_hash(void) { return (uint32_t)L2B_ABI_HASH; }
+#ifndef L2B_SRC_HASH
+#define L2B_SRC_HASH 0u
+#endif
+uint32_t l2b_source_hash(void) { return (uint32_t)L2B_SRC_HASH; }
 
 uint64_t l2b_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -42,7 +42,7 @@ from ...group.su3.pytorch.group import SU3
 from ...group.u1.pytorch.group import U1Phase
 from ...lattice.su3.pytorch.lattice import LatticeSU3
 from ...lattice.u1.pytorch.lattice import LatticeU1
-from ...network.pytorch.network import NetworkFactory, dummy_network
+from ...network.pytorch.network import NetworkFactory, dummy_network, weights_generation
 
 TWO_PI = 2. * PI
 Shape = Union[tuple, list]
@@ -697,7 +697,7 @@ class Dynamics(nn.Module):
         read the 0-dim device tensor `_eps_t(p)` directly (include/l2b.h, `eps_dev`).  All 2*nlf
         step sizes are read back with ONE device->host copy and cached until a parameter changes."""
         params = list(self.xeps) + list(self.veps)
-        key = tuple((id(q), q._version) for q in params)
+        key = tuple((id(q), q._version) for q in params) + (weights_generation(),)
         cache = getattr(self, '_eps_cache', None)
         if cache is None or cache[0] != key:
             vals = sigmoid(torch.stack([q.detach().reshape(()) for q in params]).log()).tolist()

@@ -111,6 +111,23 @@ def dummy_network(inputs: tuple[Tensor, Tensor]) -> tuple[Tensor, Tensor, Tensor
     return torch.zeros_like(x), torch.zeros_like(x), torch.zeros_like(x)
 
 
+
+# Parameter `_version`s only move when PYTHON mutates a parameter.  A training step replayed from a CUDA graph
+# updates the weights on the device without touching them, so every cache derived from parameter values (the
+# bf16 UMMA image of the heads, cast copies, host copies of the step sizes, captured eval graphs) also keys on this
+# process-wide generation, which `Trainer.train_step` bumps once per step, eager or replayed.
+_WEIGHTS_GENERATION = [0]
+
+
+def weights_generation() -> int:
+    return _WEIGHTS_GENERATION[0]
+
+
+def bump_weights_generation() -> int:
+    _WEIGHTS_GENERATION[0] += 1
+    return _WEIGHTS_GENERATION[0]
+
+
 class PeriodicPadding(nn.Module):
     """wraps `size` on BOTH sides of the last two axes (network.py:151-172)"""
 
@@ -285,7 +302,7 @@ class LeapfrogLayer(nn.Module):
         ws, _, _, wt, _, wq, _, _ = self.head_params()
         if ws.dtype == dtype:
             return ws.detach(), wt.detach(), wq.detach()
-        key = (dtype, ws._version, wt._version, wq._version, ws.data_ptr())
+        key = (dtype, ws._version, wt._version, wq._version, ws.data_ptr(), weights_generation())
         cached = getattr(self, '_head_weights_cast', None)
         if cached is None or cached[0] != key or torch.cuda.is_current_stream_capturing():
             cached = (key, tuple(w.detach().to(dtype) for w in (ws, wt, wq)))
@@ -300,7 +317,7 @@ class LeapfrogLayer(nn.Module):
         so that the kernel writes that layout directly; cached separately."""
         from ... import ops
         ps = self.head_params()
-        key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q, weights_generation())
         if perm is not None:
             cached = getattr(self, '_heads_pack_perm', None)
             if cached is None or cached[0] != key or cached[2] is not perm:

@@ -17,6 +17,7 @@ from ... import dist as l2dist
 from ...configs import LossConfig
 from ...dynamics.pytorch.dynamics import Dynamics
 from ...loss.pytorch.loss import LatticeLoss
+from ...network.pytorch.network import bump_weights_generation, weights_generation
 
 Tensor = torch.Tensor
 
@@ -50,8 +51,10 @@ class Trainer:
         x = x.to(self.dynamics.device)
         return x.reshape(x.shape[0], *self.dynamics.xshape[1:])
 
-    def _weights_version(self) -> int:
-        return sum(p._version for p in self.dynamics.parameters())
+    def _weights_version(self) -> tuple:
+        """changes whenever the parameters may have: Python-side mutation (`_version`) or a training step,
+        eager or replayed from a graph (the generation counter `train_step` bumps)"""
+        return (sum(p._version for p in self.dynamics.parameters()), weights_generation())
 
     def _graphed(self, key, fn, x: Tensor, train: bool = False):
         """run `fn(static_x) -> (x_out, metrics)` through a CUDA graph keyed by `key`"""
@@ -83,6 +86,11 @@ class Trainer:
             flags = list(ag._BAD_FLAGS)                 # matrix-exp adjoint range flags: static, re-read per replay
             ag._BAD_FLAGS.clear()
             ent = (graph, static_x, out, flags)
+            if key[0] == 'eval':
+                # an eval graph bakes in the weights-derived caches of its capture (bf16 head image, step sizes):
+                # graphs of older weights can never be replayed again -- drop them instead of growing the pool
+                for old in [k for k in self._graphs if k[0] == 'eval' and k[1:4] == key[1:4] and k[5] == key[5] and k != key]:
+                    del self._graphs[old]
             self._graphs[key] = ent
         graph, static_x, out, flags = ent
         static_x.copy_(x)
@@ -139,7 +147,9 @@ class Trainer:
             xi, beta = inputs
             xi = self._canon(xi)
             key = ('train', tuple(xi.shape), xi.dtype, float(beta))
-            return self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
+            out = self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
+            bump_weights_generation()     # the replay moved the weights without Python touching a parameter
+            return out
         self.dynamics.train()
         xi, beta = inputs
         with torch.no_grad():
@@ -167,5 +177,6 @@ class Trainer:
         if self.clip_val > 0:
             torch.nn.utils.clip_grad_norm_(self.optimizer.param_groups[0]['params'], self.clip_val)
         self.optimizer.step()
+        bump_weights_generation()
         metrics['loss'] = loss.detach()
         return xo.detach(), metrics
