@@ -62,7 +62,9 @@ uint32_t l2b_source_hash(void);
 uint64_t l2b_launch_count(void);
 /* tuning knobs (process-wide): "su3_force_variant" = launch geometry of the force
  * kernel, see kForceVariants in csrc/l2b_su3.cu; "su3_fuse_drift" = 0/1, run the drift as its
- * own kernel (6 transfers per step) or fused into the force kernel (4) */
+ * own kernel (6 transfers per step) or fused into the force kernel (4); "su3_fuse_conversions" = 0/1,
+ * l2b_su3_hmc_trajectory converts all four fields with separate kernels, or reads / writes the momenta and
+ * x_prop in the boundary layout directly from its first / last launches (same bits) */
 int l2b_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------ */

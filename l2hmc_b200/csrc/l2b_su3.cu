@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
       // leapfrog step costs 4 field transfers (r U, r P, w P, w U') instead of 6.
       Mat3<T> ex, w, un;
       soa_load(w, soa_plane(U, lat, b, mu), lat.V, site);
-      mat_exp(ex, f);
+      mat_exp_alg(ex, f);
       mat_mul<false, false, false>(un, ex, w);
       soa_store(soa_plane(Uout, lat, b, mu), lat.V, site, un);
     }
@@ -226,29 +226,39 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force(const C* __restrict__ U,
 // kernel's stall samples (profiles/r1d_force_stall_profile.md).  Here they are issued HOOK_AT directions
 // earlier into 18 more live doubles (the register allocator decides what to spill under the same cap).
 // Same arithmetic in the same order: results are bit-identical to k_force.
-template <int TS, int MINB, bool DRIFT, int HOOK_AT, bool LOWREG = false>
-__global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__ U, C* __restrict__ P, Lat lat,
-                                                           double coef, double* __restrict__ part,
-                                                           C* __restrict__ Uout, double eps_drift) {
+// PIO / UAOS fold the trajectory's layout conversions into its first and last launches (each saves one
+// full pass over a field):
+//   PIO = 1  the momenta come from the caller's boundary-layout tensor `Paos` ([nb,4,V,3,3], 144 B per link:
+//            every thread reads its own 9 contiguous entries -- a warp reads 4.6 KB contiguous, all sectors
+//            fully used) and are written planar; the kernel also sums |P_in|^2 - 8 per link (KE of the
+//            initial state, group.py:125-126) into a third partial (partials have stride 3);
+//   PIO = 2  the momenta are read planar and written to `Paos` only (final half kick -> v_prop);
+//   UAOS     the drifted links are written planar AND to the boundary-layout tensor `Uaos` (last drift -> x_prop).
+// The arithmetic and its order are those of PIO = 0: same bits.
+template <int TS, bool DRIFT, int HOOK_AT, bool LOWREG, int PIO, bool UAOS>
+__device__ __forceinline__ void force_ep_body(const C* __restrict__ U, C* __restrict__ P, const Lat& lat, double coef,
+                                              double* __restrict__ part, C* __restrict__ Uout, double eps_drift,
+                                              C* __restrict__ Paos, C* __restrict__ Uaos) {
   __shared__ double red[TS * 4 / 32];
   const int b = blockIdx.y;
   const int mu = threadIdx.y;
   const int site = blockIdx.x * TS + threadIdx.x;
   const int tid = threadIdx.y * TS + threadIdx.x;
-  double retr = 0.0, p2 = 0.0;
+  double retr = 0.0, p2 = 0.0, p2in = 0.0;
   if (site < lat.V) {
     Mat3<T> g, f;
     const int ahead = site + PF_AHEAD_SITES;
     if (ahead < lat.V) {
       soa_prefetch<2>(soa_plane(U, lat, b, mu), lat.V, ahead);
-      soa_prefetch<2>(soa_plane((const C*)P, lat, b, mu), lat.V, ahead);
+      if (PIO != 1) soa_prefetch<2>(soa_plane((const C*)P, lat, b, mu), lat.V, ahead);
     }
     C* pp = soa_plane(P, lat, b, mu) + site;
     const size_t V = lat.V;
+    const size_t aos_link = (((size_t)b * 4 + mu) * V + site) * 9;
     C pv[9];
     auto load_p = [&]() {
 #pragma unroll
-      for (int e = 0; e < 9; ++e) pv[e] = __ldcs(pp + e * V);
+      for (int e = 0; e < 9; ++e) pv[e] = (PIO == 1) ? __ldcs(Paos + aos_link + e) : __ldcs(pp + e * V);
     };
     if (LOWREG) link_times_staples_lowreg<T, C, HOOK_AT>(g, U, lat, b, mu, site, load_p);   // row-streamed operands
     else link_times_staples_hook<T, C, HOOK_AT>(g, U, lat, b, mu, site, load_p);
@@ -257,31 +267,60 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__
 #pragma unroll
     for (int e = 0; e < 9; ++e) {
       C v = pv[e];
+      if (PIO == 1) { p2in = fma(v.x, v.x, p2in); p2in = fma(v.y, v.y, p2in); }
       v.x = fma(-coef, f.re[e], v.x);
       v.y = fma(-coef, f.im[e], v.y);
       p2 = fma(v.x, v.x, p2);
       p2 = fma(v.y, v.y, p2);
-      __stcs(pp + e * V, v);
+      if (PIO == 2) __stcs(Paos + aos_link + e, v);
+      else __stcs(pp + e * V, v);
       if (DRIFT) { f.re[e] = eps_drift * v.x; f.im[e] = eps_drift * v.y; }
     }
     p2 -= 8.0;
+    if (PIO == 1) p2in -= 8.0;
     if (DRIFT) {
       Mat3<T> ex, w, un;
       soa_load(w, soa_plane(U, lat, b, mu), lat.V, site);
-      mat_exp(ex, f);
+      mat_exp_alg(ex, f);
       mat_mul<false, false, false>(un, ex, w);
       soa_store(soa_plane(Uout, lat, b, mu), lat.V, site, un);
+      if (UAOS) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+          C v;
+          v.x = un.re[e]; v.y = un.im[e];
+          __stcs(Uaos + aos_link + e, v);
+        }
+      }
     }
   }
   if (part != nullptr) {
     retr = block_sum<TS * 4>(retr, red, tid);
     p2 = block_sum<TS * 4>(p2, red, tid);
+    if (PIO == 1) p2in = block_sum<TS * 4>(p2in, red, tid);
     if (tid == 0) {
-      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * (PIO == 1 ? 3 : 2);
       o[0] = retr;
       o[1] = p2;
+      if (PIO == 1) o[2] = p2in;
     }
   }
+}
+
+template <int TS, int MINB, bool DRIFT, int HOOK_AT, bool LOWREG = false>
+__global__ void __launch_bounds__(TS * 4, MINB) k_force_ep(const C* __restrict__ U, C* __restrict__ P, Lat lat,
+                                                           double coef, double* __restrict__ part,
+                                                           C* __restrict__ Uout, double eps_drift) {
+  force_ep_body<TS, DRIFT, HOOK_AT, LOWREG, 0, false>(U, P, lat, coef, part, Uout, eps_drift, nullptr, nullptr);
+}
+
+// first / last launches of a trajectory: momenta in or out of the boundary layout, links out to it
+template <int TS, int MINB, bool DRIFT, int HOOK_AT, int PIO, bool UAOS>
+__global__ void __launch_bounds__(TS * 4, MINB) k_force_epx(const C* __restrict__ U, C* __restrict__ P, Lat lat,
+                                                            double coef, double* __restrict__ part,
+                                                            C* __restrict__ Uout, double eps_drift,
+                                                            C* __restrict__ Paos, C* __restrict__ Uaos) {
+  force_ep_body<TS, DRIFT, HOOK_AT, false, PIO, UAOS>(U, P, lat, coef, part, Uout, eps_drift, Paos, Uaos);
 }
 
 // ---------------------------------------------------------------------------
@@ -810,7 +849,7 @@ __global__ void __launch_bounds__(128, 4) k_drift(C* __restrict__ U, const C* __
   for (int e = 0; e < 9; ++e) { p.re[e] *= eps; p.im[e] *= eps; }
 #pragma unroll
   for (int e = 0; e < 9; ++e) { const C v = up[(size_t)e * V + site]; u.re[e] = v.x; u.im[e] = v.y; }
-  mat_exp(ex, p);
+  mat_exp_alg(ex, p);
   mat_mul<false, false, false>(r, ex, u);
   soa_store(up, V, site, r);
 }
@@ -1111,13 +1150,21 @@ __global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t o
 // register cap).  Selected with l2b_set_option("su3_force_variant", i); the
 // default is the one measured fastest on B200 (profiles/).
 using ForceFn = void (*)(const C*, C*, Lat, double, double*, C*, double);
+using ForceFnX = void (*)(const C*, C*, Lat, double, double*, C*, double, C*, C*);
 struct ForceVariant {
   int ts;
   ForceFn kick, nokick;
   int smem;   // dynamic shared memory (cp.async operand ring), 0 for the register-only kernel
   ForceFn kick_drift;   // kick + fused drift into the second link buffer (nullptr: not available)
   int brick_fallback;   // >= 0: brick-tiled variant; use this linear variant when the lattice does not tile
+  // trajectory ends with the layout conversions folded in (nullptr: separate conversion kernels):
+  // [0] first step (momenta from the boundary layout), [1] last step (links also to the boundary layout),
+  // [2] first == last (N_LF = 1), [3] final half kick (momenta to the boundary layout)
+  ForceFnX ends[4];
 };
+#define L2B_ENDS(HOOK)                                                                                   \
+  {k_force_epx<32, 3, true, HOOK, 1, false>, k_force_epx<32, 3, true, HOOK, 0, true>,                      \
+   k_force_epx<32, 3, true, HOOK, 1, true>, k_force_epx<32, 3, false, HOOK, 2, false>}
 #define L2B_FV(TS, MINB) L2B_FVP(TS, MINB, 0)
 #define L2B_FVP(TS, MINB, PF) \
   {TS, k_force<TS, MINB, true, PF, false>, k_force<TS, MINB, false, PF, false>, 0, k_force<TS, MINB, true, PF, true>, -1}
@@ -1149,8 +1196,8 @@ const ForceVariant kForceVariants[] = {
     L2B_FVB(32, 3, 2, 8),   // 20: brick (1,2,2,8) + L2 look-ahead
     L2B_FVB(64, 2, 2, 10),  // 21: brick (2,2,2,8) + L2 look-ahead
     // early-momentum variants of variant 8 (kick kernels only; no-kick falls back to variant 8's)
-    {32, k_force_ep<32, 3, false, 3>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3>, -1},   // 22: before the last direction
-    {32, k_force_ep<32, 3, false, 2>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2>, -1},   // 23: before the 2nd direction
+    {32, k_force_ep<32, 3, false, 3>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3>, -1, L2B_ENDS(3)},   // 22: before the last direction
+    {32, k_force_ep<32, 3, false, 2>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2>, -1, L2B_ENDS(2)},   // 23: before the 2nd direction
     {32, k_force_ep<32, 3, false, 0>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 0>, -1},   // 24: before the staples
     {32, k_force_ep<32, 2, false, 0>, k_force<32, 2, false, 2, false>, 0, k_force_ep<32, 2, true, 0>, -1},   // 25: as 24, uncapped registers (8 warps / SM)
     {32, k_force_ep<32, 4, false, 3>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3>, -1},   // 26: as 22, <= 128 registers (16 warps / SM)
@@ -1162,6 +1209,7 @@ const ForceVariant kForceVariants[] = {
     {32, k_force_ep<32, 4, false, 3, true>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3, true>, -1},   // 31: as 29, <= 128 registers
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
+int g_fuse_conversions = 1;   // fold the momentum / output layout conversions into the trajectory's end launches
 int g_force_variant = 22;   // r1d: momentum loads issued before the last staple direction (-10 % on the 16^4 trajectory)
 int g_fuse_drift = 1;
 int g_force_carveout = -1;   // -1: driver default; 0..100: preferred shared-memory carve-out in percent
@@ -1206,7 +1254,7 @@ int make_geo(Geo& g, int nb, const int dims[4], int dtype) {
   g.nblk_link = (int)((4 * V + NTL - 1) / NTL);
   g.nblk_conv = (int)((V + NTL - 1) / NTL);
   g.nblk_plaq = (int)((V + 127) / 128);
-  size_t per_chain = (size_t)g.nblk_force * 2;
+  size_t per_chain = (size_t)g.nblk_force * 3;   // (Re tr G, |P'|^2, |P_in|^2) of the trajectory's first step
   if ((size_t)g.nblk_link * 2 > per_chain) per_chain = (size_t)g.nblk_link * 2;
   if ((size_t)g.nblk_conv * 4 > per_chain) per_chain = (size_t)g.nblk_conv * 4;
   g.part_elems = per_chain * nb;
@@ -1263,6 +1311,17 @@ int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double*
   L2B_LAUNCHED("k_force");
   return L2B_OK;
 }
+int launch_force_end(const Geo& g, int which, const C* U, C* P, double coef, double* part, cudaStream_t st, C* Uout,
+                     double eps_drift, C* Paos, C* Uaos) {
+  const ForceVariant& fv = kForceVariants[g.force_variant];
+  ForceFnX fn = fv.ends[which];
+  L2B_REQUIRE(fn != nullptr, L2B_ERR_UNSUPPORTED, "force variant %d has no fused-conversion kernels", g.force_variant);
+  if (g_force_carveout >= 0)
+    L2B_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, g_force_carveout));
+  fn<<<dim3(g.nblk_force, g.nb), dim3(fv.ts, 4), 0, st>>>(U, P, g.lat, coef, part, Uout, eps_drift, Paos, Uaos);
+  L2B_LAUNCHED("k_force_epx");
+  return L2B_OK;
+}
 int launch_reduce(const double* part, int nblk, int ncomp, int comp, double scale, double shift, double* out,
                   int out_stride, int out_off, int nb, cudaStream_t st) {
   k_reduce_affine<<<nb, 256, 0, st>>>(part, nblk, ncomp, comp, scale, shift, out, out_stride, out_off);
@@ -1301,6 +1360,10 @@ int l2b_set_option(const char* key, int value) {
   }
   if (strcmp(key, "su3_fuse_drift") == 0) {
     g_fuse_drift = value != 0;
+    return L2B_OK;
+  }
+  if (strcmp(key, "su3_fuse_conversions") == 0) {
+    g_fuse_conversions = value != 0;
     return L2B_OK;
   }
   set_error("unknown option '%s'", key);
@@ -1601,11 +1664,38 @@ int l2b_su3_hmc_trajectory(const void* x, const void* v, double beta, double eps
   C* P = w.f1;
   const double b3 = beta / 3.0;
   const double ke_shift = 0.0;  // the -8 per link is already inside the partials
+  const bool fused = g_fuse_drift && kForceVariants[g.force_variant].kick_drift != nullptr;
+  if (fused && g_fuse_conversions && kForceVariants[g.force_variant].ends[0] != nullptr) {
+    // Only the links are converted: the first step reads the momenta straight from the caller's tensor (and sums
+    // KE0), the last step writes x_prop next to its planar output, the final half kick writes v_prop.
+    // 1 conversion pass + 1 extra field write instead of 4 conversion passes (8 field transfers -> 3).
+    L2B_TRY(launch_a2s(g, (const C*)x, U, nullptr, st));
+    C* Ua = U;
+    C* Ub = w.f2;
+    for (int k = 0; k < nlf; ++k) {
+      const bool first = (k == 0), last = (k == nlf - 1);
+      const double coef = (first ? 0.5 : 1.0) * eps * b3;
+      if (first || last) {
+        L2B_TRY(launch_force_end(g, first ? (last ? 2 : 0) : 1, Ua, P, coef, first ? w.part : nullptr, st, Ub, eps,
+                                 first ? (C*)v : nullptr, last ? (C*)x_prop : nullptr));
+      } else {
+        L2B_TRY(launch_force(g, Ua, P, true, coef, nullptr, st, Ub, eps));
+      }
+      if (first) {
+        L2B_TRY(launch_reduce(w.part, g.nblk_force, 3, 2, 0.5, ke_shift, energies, 4, 0, nb, st));
+        L2B_TRY(launch_reduce(w.part, g.nblk_force, 3, 0, -b3 * 0.25, 0.0, energies, 4, 1, nb, st));
+      }
+      C* t = Ua; Ua = Ub; Ub = t;
+    }
+    L2B_TRY(launch_force_end(g, 3, Ua, P, 0.5 * eps * b3, w.part, st, nullptr, 0.0, (C*)v_prop, nullptr));
+    L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 1, 0.5, ke_shift, energies, 4, 2, nb, st));
+    L2B_TRY(launch_reduce(w.part, g.nblk_force, 2, 0, -b3 * 0.25, 0.0, energies, 4, 3, nb, st));
+    return L2B_OK;
+  }
   // in: boundary layout -> planar; KE0 rides on the momentum conversion
   L2B_TRY(launch_a2s(g, (const C*)x, U, nullptr, st));
   L2B_TRY(launch_a2s(g, (const C*)v, P, w.part, st));
   L2B_TRY(launch_reduce(w.part, g.nblk_conv * 4, 1, 0, 0.5, ke_shift, energies, 4, 0, nb, st));
-  const bool fused = g_fuse_drift && kForceVariants[g.force_variant].kick_drift != nullptr;
   if (fused) {
     // kick + drift fused, links ping-pong between two planar buffers:
     //   K(eps/2) K(eps) ... K(eps)   [nlf launches, each: P -= c F(U); U' = exp(eps P) U]   +   final half kick

@@ -223,6 +223,108 @@ L2B_HD void mat_exp(Mat3<T>& out, const Mat3<T>& ain) {
 }
 
 // ---------------------------------------------------------------------------
+// exp(A) for A in su(3) (traceless anti-Hermitian): the argument of every HMC drift,
+// U' = exp(eps P) U  (group.py:45-50 via dynamics.py:900-913), where P is a momentum
+// (randTAH3) kicked by projectTAH forces and therefore stays in the algebra.
+// Same Cayley-Hamilton series as mat_exp, specialised:  t = tr A = 0,  c = -tr(A^2)/2 =
+// ||A||_F^2 / 2 is REAL,  d = det A is purely IMAGINARY (det A = -conj(det A)), so the
+// coefficients of A^n = a_n + b_n A + c_n A^2 alternate between purely real and purely
+// imaginary:    n even: (a, b, c) = (re, i im, re),    n odd: (i im, re, i im)
+// and one Taylor term costs 2 multiply-adds + 3 accumulations instead of 16 + a division
+// (1/n! is a table).  A^2 = -A A^+ is Hermitian: 6 of its 9 entries are computed.
+// No scaling / squaring: the caller (`mat_exp_alg`) sends ||A||_F > 1 to mat_exp.
+// Differences to mat_exp are at rounding level (the neglected trace of a kicked
+// momentum is ~1e-17); the trajectory goldens are reproduced to 1e-15.
+// ---------------------------------------------------------------------------
+template <typename T>
+L2B_HD void mat_exp_tah(Mat3<T>& out, const Mat3<T>& a, T n2) {
+  // A^2 = -A A^+ : diagonal real, (j, i) = conj(i, j)
+  Mat3<T> a2;
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = i; j < 3; ++j) {
+      T sr = T(0), si = T(0);
+      L2B_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        const T ar = a.re[3 * i + k], ai = a.im[3 * i + k], br = a.re[3 * j + k], bi = a.im[3 * j + k];
+        sr = fma(-ar, br, sr);
+        sr = fma(-ai, bi, sr);
+        if (j != i) { si = fma(ar, bi, si); si = fma(-ai, br, si); }
+      }
+      a2.re[3 * i + j] = sr; a2.im[3 * i + j] = si;
+      if (j != i) { a2.re[3 * j + i] = sr; a2.im[3 * j + i] = -si; }
+    }
+  }
+  const T c = T(-0.5) * (a2.re[0] + a2.re[4] + a2.re[8]);     // = ||A||_F^2 / 2
+  T dr, dl;
+  det3(a, dr, dl);                                            // d = i dl (Re d = 0 in exact arithmetic)
+  (void)dr;
+  // 1/n!, n = 0 .. 20
+  const T inv_fact[21] = {T(1), T(1), T(0.5), T(1.0 / 6), T(1.0 / 24), T(1.0 / 120), T(1.0 / 720), T(1.0 / 5040),
+                          T(1.0 / 40320), T(1.0 / 362880), T(1.0 / 3628800), T(1.0 / 39916800), T(1.0 / 479001600),
+                          T(1.0 / 6227020800.0), T(1.0 / 87178291200.0), T(1.0 / 1307674368000.0),
+                          T(1.0 / 20922789888000.0), T(1.0 / 355687428096000.0), T(1.0 / 6402373705728000.0),
+                          T(1.0 / 121645100408832000.0), T(1.0 / 2432902008176640000.0)};
+  // running coefficients: pa, pb, pc hold the single non-zero component of a_n, b_n, c_n
+  T pa = T(0), pb = T(0), pc = T(1);                          // n = 2: (0, 0, 1), all "real" slots
+  T sar = T(1), sai = T(0), sbr = T(1), sbi = T(0), scr = T(0.5), sci = T(0);
+  const int nterms = (n2 <= T(0.01)) ? 10 : (n2 <= T(0.09)) ? 13 : (n2 <= T(0.25)) ? 16 : 20;
+  L2B_UNROLL
+  for (int n = 3; n <= 20; ++n) {
+    if (n > nterms) break;
+    T na, nb;
+    if (n & 1) {            // from even n-1 (a re, b im, c re)  ->  a = i dl c,  b = a - c c (re),  c = i b
+      na = dl * pc;
+      nb = fma(-c, pc, pa);
+    } else {                // from odd n-1 (a im, b re, c im)   ->  a = -dl c (re),  b = i (a - c c),  c = b (re)
+      na = -dl * pc;
+      nb = fma(-c, pc, pa);
+    }
+    pc = pb; pa = na; pb = nb;
+    const T w = inv_fact[n];
+    if (n & 1) { sai = fma(w, pa, sai); sbr = fma(w, pb, sbr); sci = fma(w, pc, sci); }
+    else       { sar = fma(w, pa, sar); sbi = fma(w, pb, sbi); scr = fma(w, pc, scr); }
+  }
+  // out = sa + sb A + sc A^2
+  L2B_UNROLL
+  for (int e = 0; e < 9; ++e) {
+    T r = sbr * a.re[e] - sbi * a.im[e];
+    T i = sbr * a.im[e] + sbi * a.re[e];
+    r = fma(scr, a2.re[e], r); r = fma(-sci, a2.im[e], r);
+    i = fma(scr, a2.im[e], i); i = fma(sci, a2.re[e], i);
+    out.re[e] = r; out.im[e] = i;
+  }
+  out.re[0] += sar; out.im[0] += sai;
+  out.re[4] += sar; out.im[4] += sai;
+  out.re[8] += sar; out.im[8] += sai;
+}
+
+// exp(A) for an argument that is EXPECTED to lie in su(3) (HMC drifts): the specialised series when A is
+// anti-Hermitian and traceless to 1e-14 relative and ||A||_F <= 1, the general mat_exp otherwise -- so any
+// input gets the reference's torch.matrix_exp semantics, and the expected ones get it ~2.5x cheaper.
+template <typename T>
+L2B_HD void mat_exp_alg(Mat3<T>& out, const Mat3<T>& a) {
+  const T n2 = norm2(a);
+  // || A + A^+ ||_F^2 and |tr A|^2 (the diagonal of A + A^+ is 2 Re a_ii; tr of an anti-Hermitian A is i Im tr)
+  T dev = T(0);
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    dev = fma(a.re[4 * i], a.re[4 * i], dev);
+    L2B_UNROLL
+    for (int j = i + 1; j < 3; ++j) {
+      const T er = a.re[3 * i + j] + a.re[3 * j + i], ei = a.im[3 * i + j] - a.im[3 * j + i];
+      dev = fma(er, er, dev);
+      dev = fma(ei, ei, dev);
+    }
+  }
+  const T ti = a.im[0] + a.im[4] + a.im[8];
+  dev = fma(ti, ti, dev);
+  if (dev <= T(1e-28) * n2 && n2 <= T(1)) mat_exp_tah(out, a, n2);
+  else mat_exp(out, a);
+}
+
+// ---------------------------------------------------------------------------
 // projectSU  (utils.py:227-346), clamps included
 // ---------------------------------------------------------------------------
 template <typename T>

@@ -41,6 +41,7 @@ void emu_unary(int mode, const C* x, double scale, C* out, double* vec8, size_t 
     Mat3<T> m, r;
     aos_get(m, x, i);
     if (mode == 0) { for (int e = 0; e < 9; ++e) { m.re[e] *= scale; m.im[e] *= scale; } mat_exp(r, m); }
+    else if (mode == 4) { for (int e = 0; e < 9; ++e) { m.re[e] *= scale; m.im[e] *= scale; } mat_exp_alg(r, m); }
     else if (mode == 1) project_tah(r, m);
     else if (mode == 2) project_su(r, m);
     else r = m;
@@ -219,7 +220,7 @@ void emu_hmc(const C* x, const C* v, double beta, double eps, int nlf, C* xo, C*
         soa_load(pm, P.data() + (size_t)p * 9 * l.V, l.V, s);
         for (int e = 0; e < 9; ++e) { pm.re[e] *= eps; pm.im[e] *= eps; }
         soa_load(u, U.data() + (size_t)p * 9 * l.V, l.V, s);
-        mat_exp(ex, pm);
+        mat_exp_alg(ex, pm);
         mat_mul<false, false, false>(r, ex, u);
         soa_store(U.data() + (size_t)p * 9 * l.V, l.V, s, r);
       }

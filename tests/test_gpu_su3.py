@@ -124,6 +124,29 @@ def test_hmc_trajectory_vs_reference_golden(ops, g, key, xk, vk):
     assert maxdiff(acc, g[f'{key}_acc']) < 1e-12 * scale
 
 
+@pytest.mark.parametrize('shape,nb,nlf', [([4, 4, 4, 4], 2, 1), ([4, 4, 4, 4], 3, 2), ([3, 5, 4, 7], 2, 4),
+                                          ([8, 8, 8, 8], 5, 3)])
+def test_trajectory_with_conversions_folded_in_is_bit_identical(ops, shape, nb, nlf):
+    """default: the momenta are read from / written to the boundary layout by the trajectory's first / last
+    launches and x_prop by its last drift (k_force_epx); `su3_fuse_conversions = 0`: four separate conversion
+    kernels.  Same arithmetic in the same order: links and momenta agree bit for bit; the initial kinetic
+    energy is summed over a different block partition (rounding of a sum only)."""
+    from l2hmc_b200 import _lib
+    rng = np.random.default_rng(7 * nb + nlf)
+    full = (nb, 4, *shape, 3, 3)
+    x, v = dev(osu3.random_su3(rng, full)), dev(osu3.random_momentum(rng, full))
+    try:
+        _lib.set_option('su3_fuse_conversions', 0)
+        x0, v0, e0 = ops.su3_hmc_trajectory(x, v, 5.7, 0.07, nlf)
+        _lib.set_option('su3_fuse_conversions', 1)
+        x1, v1, e1 = ops.su3_hmc_trajectory(x, v, 5.7, 0.07, nlf)
+    finally:
+        _lib.set_option('su3_fuse_conversions', 1)
+    assert torch.equal(x0, x1) and torch.equal(v0, v1)
+    assert torch.equal(e0[:, 1:], e1[:, 1:])
+    assert torch.allclose(e0[:, 0], e1[:, 0], rtol=1e-13, atol=1e-12)
+
+
 @pytest.mark.parametrize('shape,nb', [([2, 2, 2, 2], 3), ([4, 4, 4, 4], 2), ([6, 4, 2, 8], 1), ([3, 5, 4, 7], 2)])
 def test_vs_oracle_on_fresh_inputs(ops, shape, nb):
     """ragged / odd / extent-2 lattices (extent 2: forward and backward neighbour coincide)"""

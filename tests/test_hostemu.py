@@ -77,6 +77,29 @@ def test_exp_large_norm_uses_scaling(emu):
     assert np.max(np.abs(out - ref) / np.abs(ref).max()) < 1e-11
 
 
+def test_exp_specialised_to_the_algebra(emu, g):
+    """mat_exp_alg (the HMC drift's exponential): su(3) arguments take the specialised Cayley-Hamilton
+    series (real c, imaginary d, Hermitian A^2, 1/n! table), everything else falls back to mat_exp"""
+    rng = np.random.default_rng(11)
+    p = osu3.random_momentum(rng, (4096, 3, 3))              # ||P||_F^2 ~ 8
+    for scale in (1e-3, 0.02, 0.05, 0.1, 0.17, 0.3, 0.35):   # leapfrog arguments eps * P, all Taylor-order buckets
+        a = scale * p
+        ref = osu3.expm(a)
+        got = unary(emu, 4, a)
+        assert maxdiff(got, ref) < 1e-15, scale
+        assert maxdiff(got, unary(emu, 0, a)) < 1e-15        # vs the general series: rounding only
+        # unitary to rounding
+        assert maxdiff(got @ got.conj().swapaxes(-1, -2), np.broadcast_to(np.eye(3), got.shape)) < 2e-15
+    assert maxdiff(unary(emu, 4, g['v'], 0.25), g['expv']) < 1e-14
+    # not in the algebra (generic complex, Hermitian part, trace) or too large: same bits as mat_exp
+    gen = (rng.standard_normal((64, 3, 3)) + 1j * rng.standard_normal((64, 3, 3))) * 0.2
+    assert np.array_equal(unary(emu, 4, gen), unary(emu, 0, gen))
+    tr = 0.1 * p[:64] + 1e-9j * np.eye(3)
+    assert np.array_equal(unary(emu, 4, tr), unary(emu, 0, tr))
+    big = 2.0 * p[:64]
+    assert np.array_equal(unary(emu, 4, big), unary(emu, 0, big))
+
+
 def test_stencil_bodies(emu, g):
     x = np.ascontiguousarray(g['x'])
     nb, beta = x.shape[0], float(g['beta'])
