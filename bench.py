@@ -12,14 +12,25 @@ ranks share nothing on the data path (weak scaling, no collective); the only
 collectives are the timing barrier and the max-over-ranks of the elapsed time.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel (k_force: staples + TAH + kick) algorithmic bytes
-                (3 link-sized transfers = 432 B per link per launch) / its average
-                CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  roofline      dominant kernel (k_force_ep: one fused leapfrog step, staples + TAH +
+                kick + exp + link update) algorithmic bytes by SURVEY 8(d)'s streaming
+                model (6 link-sized transfers = 864 B per link-update; the kernel itself
+                moves 4 = 576 B, reported next to it) / its average CUDA-event duration,
+                against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference's own PyTorch path on this box's host cores, on a
                 bounded sample of the same workload
   e2e           same metric through the public Dynamics.apply_transition_hmc call
-                with the links in pinned HOST memory: H2D of x and D2H of the
+                with the links in pinned HOST memory: H2D of x and D2H of x_out and the
                 accept probabilities inside the timed region
+  parity        chain 0 of the timed batch against the oracle (the reference itself on
+                the CPU when oracle/_ref travelled), after the timed region
+  thermalised   the headline workload timed from a configuration relaxed by 100 HMC
+                trajectories (trainer.py:1699-1744)
+  secondary     the other BASELINE configs in the same run and process group: cfg 3
+                (SU(3) 8^4 x 256 HMC), cfg 2 (U(1) 64x64 x 4096 HMC), cfg 3/5 L2HMC eval
+                and training steps (the training step includes the NCCL all-reduce of
+                the network gradients when N > 1)
+  gpu_reference the reference's own .cuda() path on the same GPU (N = 1 only)
 """
 from __future__ import annotations
 
@@ -126,15 +137,18 @@ class ClockSampler:
 def reference_sample(workload: str, nsteps: int):
     """bounded sample of the workload for the CPU arm: same lattice, dtype,
     step size and integrator, fewer chains (cost is linear in chains) and, when
-    many steps are requested, fewer leapfrog steps per trajectory, so that the
-    whole run is ~80 chain-leapfrog-steps of 16^4 (~2 min on 8 cores)."""
+    more than 10 trajectories are requested, fewer leapfrog steps per trajectory,
+    so that the whole run is <= 100 chain-leapfrog-steps of 16^4 (~1 min on 16
+    cores).  Up to 10 trajectories the sample keeps the workload's own N_LF, so
+    the two end-point Hamiltonians weigh on the CPU number exactly as they do on
+    ours."""
     group, lattice, nb, nlf, dtype, beta = WORKLOADS[workload]
     if group == 'SU3':
         v = 1
         for s in lattice:
             v *= s
         nb_s = max(1, min(nb, 65536 // v))         # 16^4 -> 1 chain, 8^4 -> 16 chains
-        nlf_s = max(1, min(nlf, 80 // max(1, nsteps)))
+        nlf_s = max(1, min(nlf, 100 // max(1, nsteps)))   # <= 10 trajectories: the workload's own N_LF
     else:
         nb_s, nlf_s = min(nb, 512), nlf
     return group, lattice, nb_s, nlf_s, dtype, beta
@@ -284,189 +298,345 @@ def main_reference(args):
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
-def main_ours(args):
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU; there is no CPU fallback'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    from l2hmc_b200 import ops
-    from l2hmc_b200 import _lib
+class Ctx:
+    """process-wide state of the product arm: rank / world / device, the process group, lazily imported package"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.local = int(os.environ.get('LOCAL_RANK', '0'))
+        assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU; there is no CPU fallback'
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device('cuda', self.local)
+        from l2hmc_b200 import dist as l2d
+        self.cpus = l2d.bind_rank_to_cores(self.local, self.world)       # before any pinned allocation
+        if self.world > 1:
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.peak, self.peak_kind = peaks()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, ms: float) -> float:
+        t = self.torch.tensor([ms], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
+
+    def free(self):
+        import gc
+        gc.collect()
+        self.torch.cuda.empty_cache()
+
+
+def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: int = 0, roofline: bool = True,
+                 e2e: bool = True, clocks: bool = True, parity: bool = False) -> dict:
+    """ONE HMC workload: device-timed trajectories on resident inputs (`value`), the per-kernel roofline, and the
+    same metric end to end through `Dynamics.apply_transition_hmc` with host buffers (`e2e`).  Returns the pieces
+    of the JSON line; rank 0's copy is the one printed."""
+    torch = ctx.torch
+    from l2hmc_b200 import _lib, ops
     from l2hmc_b200.configs import DynamicsConfig
     from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
     from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
     from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
-
-    group, lattice, nb, nlf, dtype, beta = WORKLOADS[args.workload]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    group, lattice, nb, nlf, dtype, beta = WORKLOADS[workload]
     su3 = group == 'SU3'
     dim = 4 if su3 else 2
     eps = 1.0 / nlf                                           # configs.py:485-487
     units_rank = links_of(lattice, nb, dim) * nlf             # link-updates per trajectory per GPU
     torch.manual_seed(SEED + rank)
     tdt = torch.float64 if dtype == 'f64' else torch.float32
+    old_dt = torch.get_default_dtype()
     torch.set_default_dtype(tdt)
+    try:
+        # synthetic hot-start configuration + momenta, resident in HBM
+        cfg = DynamicsConfig(nchains=nb, group=group, latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
+                             verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+        lat = LatticeSU3(nb, lattice) if su3 else LatticeU1(nb, lattice)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+        x = lat.random()
+        acc_therm = None
+        if thermalise > 0:
+            # SURVEY 8(d): hot-start links make the acos / exp arguments atypical; time from a configuration relaxed
+            # by N accepted-or-rejected HMC trajectories (the reference's `Trainer.warmup`, trainer.py:1699-1744)
+            with torch.no_grad():
+                for _ in range(thermalise):
+                    xo_, m_ = dyn.apply_transition_hmc((x, torch.tensor(beta)), eps=eps, nleapfrog=nlf)
+                    x = xo_.reshape(x.shape)
+                acc_therm = float(m_['acc'].mean())
+            x = x.contiguous()
+        v = lat.random_momentum()
+        field_bytes = x.numel() * x.element_size()
 
-    # synthetic hot-start configuration + momenta, resident in HBM
-    cfg = DynamicsConfig(nchains=nb, group=group, latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
-                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
-    lat = LatticeSU3(nb, lattice) if su3 else LatticeU1(nb, lattice)
-    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
-    x = lat.random()
-    if args.thermalise > 0:
-        # hot-start links make the acos / exp arguments atypical; optionally time from a
-        # configuration relaxed by N accepted-or-rejected HMC trajectories (trainer.py:1699-1744 `warmup`)
-        with torch.no_grad():
-            for _ in range(args.thermalise):
-                xo_, _m = dyn.apply_transition_hmc((x, torch.tensor(beta)), eps=eps, nleapfrog=nlf)
-                x = xo_.reshape(x.shape)
-        x = x.contiguous()
-    v = lat.random_momentum()
-    field_bytes = x.numel() * x.element_size()
+        def traj():
+            if su3:
+                return ops.su3_hmc_trajectory(x, v, beta, eps, nlf)
+            return ops.u1_hmc_trajectory(x, v, beta, eps, nlf, shape=lattice)
 
-    def traj():
-        if su3:
-            return ops.su3_hmc_trajectory(x, v, beta, eps, nlf)
-        return ops.u1_hmc_trajectory(x, v, beta, eps, nlf, shape=lattice)
+        for _ in range(warmup):
+            out = traj()
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local) if (rank == 0 and clocks) else None
+        if sampler:
+            sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        e0.record()
+        for _ in range(steps):
+            out = traj()
+        e1.record()
+        ctx.barrier()
+        launches = _lib.launch_count() - l0
+        clk = sampler.stop() if sampler else None
+        ms_max = ctx.max_over_ranks(e0.elapsed_time(e1))
+        value = world * units_rank * steps / (ms_max * 1e-3)
+        en = out[2]
+        assert torch.isfinite(en).all(), 'non-finite energies'
+        gb = 864.0 if su3 else 24.0
+        res = {
+            'workload': workload, 'value': value, 'ms_per_step': ms_max / steps, 'gpu_launches': launches, 'clocks': clk,
+            'dtype': 'f64' if dtype == 'f64' else 'f32',
+            'config': {'workload': workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
+                       'global_chains': nb * world, 'nleapfrog': nlf, 'eps': eps, 'beta': beta,
+                       'start': ('hot (g.random)' if thermalise <= 0 else
+                                 f'thermalised ({thermalise} HMC trajectories from a hot start, last <acc> = {acc_therm:.3f})'),
+                       'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
+                       'l2_policy': f'inputs larger than L2 ({field_bytes / 2**20:.0f} MiB per field per GPU), no flush'
+                       if field_bytes > 200 * 2**20 else 'working set fits L2; fields re-read every step (no flush)',
+                       'host_cores_bound': ctx.cpus},
+            'hbm_model': {'bytes_per_link_update': gb, 'achieved_GBps_per_gpu': value / world * gb / 1e9,
+                          'frac_of_peak': value / world * gb / 1e9 / ctx.peak, 'peak_GBps': ctx.peak,
+                          'peak_kind': ctx.peak_kind},
+        }
+        # ---- parity of the timed batch: chain 0's proposal against the oracle, after the timed region ----------
+        if parity and su3:
+            res['parity'] = parity_of_timed_batch(ctx, x, v, out, beta, eps, nlf, lattice)
+        # ---- per-kernel CUDA-event timing of the dominant kernel ------------------------------------------------
+        if roofline:
+            if su3:
+                res['roofline'] = su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, steps, ctx.peak,
+                                                      ctx.peak_kind, ms_max / steps)
+            else:
+                # whole trajectory is ONE kernel with the state resident in shared memory:
+                # algorithmic (streaming-model) bytes vs time; real HBM traffic is 4 field passes
+                ach = 24.0 * units_rank / (ms_max / steps * 1e-3) / 1e9
+                res['roofline'] = {'bound': 'hbm', 'kernel': 'k_u1_hmc (whole trajectory on-chip)', 'achieved': ach,
+                                   'peak': ctx.peak, 'unit': 'GB/s', 'frac': ach / ctx.peak, 'peak_kind': ctx.peak_kind,
+                                   'traffic': None,
+                                   'note': 'streaming model 24 B/link-update; actual DRAM traffic is 16 B/link per TRAJECTORY'}
+        del out, en
+        # ---- e2e through the public API with host buffers ------------------------------------------------------
+        if e2e:
+            res['e2e'] = hmc_e2e(ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, tdt)
+        del x, v, dyn, lat
+        ctx.free()
+        return res
+    finally:
+        torch.set_default_dtype(old_dt)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        out = traj()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = traj()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t)
-    value = world * units_rank * args.steps / (ms_max * 1e-3)
-    en = out[2]
-    assert torch.isfinite(en).all(), 'non-finite energies'
-
-    # ---- per-kernel CUDA-event timing of the dominant kernel (k_force) ---------
-    roofline = None
-    peak, peak_kind = peaks()
-    if su3:
-        roofline = su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, args.steps, peak, peak_kind,
-                                       ms_max / args.steps)
-    else:
-        # whole trajectory is ONE kernel with the state resident in shared memory:
-        # algorithmic (streaming-model) bytes vs time; real HBM traffic is 4 field passes
-        algo = 24.0 * units_rank
-        ach = algo / (ms_max / args.steps * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'k_u1_hmc (whole trajectory on-chip)', 'achieved': ach, 'peak': peak,
-                    'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind, 'traffic': None,
-                    'note': 'streaming model 24 B/link-update; actual DRAM traffic is 16 B/link per TRAJECTORY'}
-
-    # ---- e2e through the public API with host buffers -------------------------
-    # Every step: H2D of that step's links from pinned host memory, the public
-    # Dynamics.apply_transition_hmc call, D2H of the accept probabilities.  The copy
-    # of step i+1 runs on a side stream while step i computes (two device input
-    # buffers), as a production sampler feeding independent batches would do.
+def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, tdt) -> dict:
+    """Every step: H2D of that step's links from pinned host memory, the public `Dynamics.apply_transition_hmc`
+    call, D2H of the step's results: the accept probabilities AND the new configuration x_out.  Three streams:
+    the upload of step i+1 and the download of step i-1 run while step i computes (two device input buffers, two
+    device/host output buffers), as a production sampler feeding independent batches would do."""
+    torch = ctx.torch
+    dev = ctx.dev
+    nb = x.shape[0]
     xh = x.detach().cpu().pin_memory()
+    field_bytes = x.numel() * x.element_size()
+    xo_h = [torch.empty((nb, x.numel() // nb), dtype=x.dtype).pin_memory() for _ in range(2)]
     acc_h = torch.empty(nb, dtype=torch.float64 if su3 else tdt).pin_memory()
     bt = torch.tensor(beta)
-    copy_stream = torch.cuda.Stream(device=dev)
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
     xin = [torch.empty_like(x), torch.empty_like(x)]
+    xout = [None, None]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     freed = [torch.cuda.Event(), torch.cuda.Event()]
-    main_stream = torch.cuda.current_stream(dev)
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    drained = [torch.cuda.Event(), torch.cuda.Event()]
 
     def stage(i):
         buf = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[buf])               # previous user of this buffer is done
-            xin[buf].copy_(xh, non_blocking=True)            # H2D of step i's links
-            ready[buf].record(copy_stream)
+        with torch.cuda.stream(up):
+            up.wait_event(freed[buf])                     # previous user of this input buffer is done
+            xin[buf].copy_(xh, non_blocking=True)         # H2D of step i's links
+            ready[buf].record(up)
 
-    def e2e_run(n):
+    def run(n):
         for b_ in (0, 1):
-            freed[b_].record(main_stream)
+            freed[b_].record(main)
+            drained[b_].record(down)
         stage(0)
         for i in range(n):
             if i + 1 < n:
                 stage(i + 1)
             buf = i % 2
-            main_stream.wait_event(ready[buf])
+            main.wait_event(ready[buf])
+            main.wait_event(drained[buf])                 # step i-2's x_out has left its device buffer
             xo, met = dyn.apply_transition_hmc((xin[buf], bt), eps=eps, nleapfrog=nlf)
-            freed[buf].record(main_stream)
-            acc_h.copy_(met['acc'], non_blocking=True)       # D2H of the step's result
+            xout[buf] = xo
+            freed[buf].record(main)
+            done[buf].record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(done[buf])
+                xo_h[buf].copy_(xo, non_blocking=True)    # D2H of step i's new configuration
+                acc_h.copy_(met['acc'], non_blocking=True)
+                drained[buf].record(down)
+        main.wait_stream(down)
         return xo
+
     with torch.no_grad():
-        e2e_run(max(1, min(args.warmup, 2)))
-        barrier()
+        run(max(1, min(warmup, 2)))
+        ctx.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(2, min(args.steps, 6))
+        n_e2e = max(2, min(steps, 6))
         e2.record()
-        e2e_run(n_e2e)
+        run(n_e2e)
         e3.record()
-        barrier()
-    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_val = world * units_rank * n_e2e / (float(t2) * 1e-3)
-
-    if rank == 0:
-        cpu_base = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu_base = cpu_baseline_subprocess(args.workload)
-        gb = 864.0 if su3 else 24.0
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'link-updates/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f64' if dtype == 'f64' else 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
-                       'global_chains': nb * world, 'nleapfrog': nlf, 'eps': eps, 'beta': beta,
-                       'start': ('hot (g.random)' if args.thermalise <= 0 else f'thermalised ({args.thermalise} HMC trajectories from a hot start)'),
-                       'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
-                       'l2_policy': f'inputs larger than L2 ({field_bytes / 2**20:.0f} MiB per field per GPU), no flush'
-                       if field_bytes > 200 * 2**20 else 'working set fits L2; fields re-read every step (no flush)'},
-            'hbm_model': {'bytes_per_link_update': gb, 'achieved_GBps_per_gpu': value / world * gb / 1e9,
-                          'frac_of_peak': value / world * gb / 1e9 / peak, 'peak_GBps': peak, 'peak_kind': peak_kind},
-            'roofline': roofline, 'cpu_baseline': cpu_base,
-            'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': field_bytes,
-                    'd2h_bytes_per_step': acc_h.numel() * acc_h.element_size(), 'steps': n_e2e,
-                    'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta)); H2D of step i+1 overlapped with step i on a copy stream'},
-            'gpu_launches': launches, 'clocks': clocks,
-        }
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        ctx.barrier()
+    ms = ctx.max_over_ranks(e2.elapsed_time(e3))
+    # the copy engines alone, same buffers: what the host link gives this rank while all ranks copy at once
+    ctx.barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(2):
+        xin[0].copy_(xh, non_blocking=True)
+    c1.record()
+    ctx.barrier()
+    h2d_ms = ctx.max_over_ranks(c0.elapsed_time(c1)) / 2
+    return {'value': ctx.world * units_rank * n_e2e / (ms * 1e-3), 'unit': 'link-updates/s',
+            'h2d_bytes_per_step': field_bytes, 'd2h_bytes_per_step': field_bytes + acc_h.numel() * acc_h.element_size(),
+            'steps': n_e2e, 'ms_per_step': ms / n_e2e,
+            'h2d_GBps_per_gpu_all_ranks_copying': field_bytes / (h2d_ms * 1e-3) / 1e9,
+            'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta)); H2D of step i+1 and D2H of step '
+                   'i-1 (x_out, acc) overlapped with step i on two copy streams'}
 
 
-def main_l2hmc(args):
-    """SU(3) L2HMC eval / training step through the public Trainer API (secondary workloads)."""
+def parity_of_timed_batch(ctx: Ctx, x, v, out, beta, eps, nlf, lattice) -> dict:
+    """chain 0 of the timed batch, the very tensors the timed trajectories read and wrote, against the oracle on
+    the host: the reference's own `Dynamics.transition_kernel_hmc` (oracle/_ref) when it travelled, else the
+    numpy restatement (oracle/dynamics.py).  Rank 0 only; runs after the timed region."""
+    if ctx.rank != 0:
+        return None
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    assert torch.cuda.is_available(), 'bench.py (impl=ours) needs a GPU; there is no CPU fallback'
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    torch = ctx.torch
+    x0, v0 = x[:1].cpu(), v[:1].cpu()
+    gx, gv, gen = out[0][:1].cpu().numpy(), out[1][:1].cpu().numpy(), out[2][:1].cpu().numpy()
+    t0 = time.perf_counter()
+    from oracle import ref_shim
+    if ref_shim.available():
+        kind = 'reference (oracle/_ref, CPU)'
+        ref = ref_shim.load_reference(torch.float64)
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            lat = ref.LatticeSU3(1, lattice)
+            cfg = ref.DynamicsConfig(nchains=1, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
+                                     verbose=False, use_split_xnets=False, use_separate_networks=False,
+                                     merge_directions=True)
+            rdyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None).cpu()
+            bt = torch.tensor(beta)
+            sp, met = rdyn.transition_kernel_hmc(ref.State(x=x0, v=v0, beta=bt), eps=eps, nleapfrog=nlf)
+            wx, wv = sp.x.detach().reshape(x0.shape).numpy(), sp.v.detach().reshape(v0.shape).numpy()
+            wh0 = (lat.action(x0, bt) + lat.g.kinetic_energy(v0)).detach().numpy()
+            wh1 = (lat.action(sp.x.detach().reshape(x0.shape), bt) + lat.g.kinetic_energy(sp.v.detach())).detach().numpy()
+        finally:
+            torch.set_default_dtype(old)
+    else:
+        kind = 'port (oracle/dynamics.py, numpy)'
+        from oracle import dynamics as od, su3 as osu3
+        xn, vn = x0.numpy(), v0.numpy()
+        want, _ = od.transition_kernel_hmc(od.SU3Ops, od.State(xn, vn, beta), eps, nlf)
+        wx, wv = want.x, want.v
+        wh0 = osu3.action(xn, beta) + osu3.kinetic_energy(vn)
+        wh1 = osu3.action(wx, beta) + osu3.kinetic_energy(wv)
+    gh0, gh1 = gen[:, 0] + gen[:, 1], gen[:, 2] + gen[:, 3]
+    dx, dv = float(np.abs(gx - wx).max()), float(np.abs(gv - wv).max())
+    dh = max(float(np.abs(gh0 - wh0).max() / np.abs(wh0).max()), float(np.abs(gh1 - wh1).max() / np.abs(wh1).max()))
+    dacc = float(np.abs(np.exp(np.minimum(gh0 - gh1, 0)) - np.exp(np.minimum(wh0 - wh1, 0))).max())
+    ok = dx < 1e-12 and dv < 1e-12 and dh < 1e-12 and dacc < 1e-12 * max(1.0, float(np.abs(wh0).max()))
+    return {'oracle': kind, 'chains_checked': 1, 'nleapfrog': nlf, 'max_abs_dx': dx, 'max_abs_dv': dv,
+            'max_rel_dH': dh, 'max_abs_dacc': dacc, 'tolerance': '1e-12 (links, momenta abs; H rel; acc * max(1,|H|))',
+            'ok': bool(ok), 'oracle_seconds': time.perf_counter() - t0}
+
+
+def gpu_reference_subprocess(workload: str):
+    """the reference's OWN `.cuda()` path on this GPU (profiles/time_reference_gpu.py): the like-for-like baseline
+    SURVEY 8(d) asks for -- what a user of the reference gets on the same B200 today"""
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / 'profiles' / 'time_reference_gpu.py'), workload],
+                           capture_output=True, text=True, timeout=600)
+        d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith('{')][-1])
+        return {'value': d['link_updates_per_s'], 'unit': 'link-updates/s', 'ms_per_step': d['ms_per_trajectory'],
+                'sample': f"{d['chains']} chains of the same lattice / N_LF / dtype / eps on {d['device']} (the reference "
+                          f"materialises ~40 field-sized temporaries per force evaluation; peak {d['peak_mem_GB']:.1f} GB), "
+                          'per-trajectory wall time with synchronize', 'impl': d['impl']}
+    except Exception as e:
+        return {'value': None, 'unit': 'link-updates/s', 'sample': f'failed: {type(e).__name__}: {e}'}
+
+
+def main_ours(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    head = hmc_workload(ctx, args.workload, args.steps, args.warmup, thermalise=args.thermalise,
+                        parity=not args.no_parity)
+    group, lattice, nb, nlf, dtype, beta = WORKLOADS[args.workload]
+    full = (args.workload == DEFAULT_WORKLOAD) and not args.headline_only
+    line = {
+        'metric': METRIC, 'value': head['value'], 'unit': 'link-updates/s', 'n_gpus': ctx.world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': head['dtype'], 'data': 'synthetic', 'config': head['config'],
+        'hbm_model': head['hbm_model'], 'roofline': head.get('roofline'), 'cpu_baseline': None,
+        'e2e': head.get('e2e'), 'gpu_launches': head['gpu_launches'], 'clocks': head['clocks'],
+        'parity': head.get('parity'),
+    }
+    if full:
+        # ---- thermalised start (SURVEY 8(d), trainer.py:1699-1744): same workload from a relaxed configuration ----
+        th = hmc_workload(ctx, args.workload, max(2, min(args.steps, 5)), 3, thermalise=args.thermalise_n, roofline=False,
+                          e2e=False, clocks=False)
+        line['thermalised'] = {'value': th['value'], 'ms_per_step': th['ms_per_step'], 'start': th['config']['start']}
+        # ---- the other BASELINE configs, same run, same process group ------------------------------------------------
+        sec = {}
+        for w in ('su3_8x8x8x8_nb256_nlf10_c128', 'u1_64x64_nb4096_nlf10_f32'):
+            r = hmc_workload(ctx, w, max(3, min(args.steps, 10)), 3, clocks=False)
+            sec[w] = {'value': r['value'], 'ms_per_step': r['ms_per_step'], 'unit': 'link-updates/s',
+                      'roofline_frac': r['roofline']['frac'], 'roofline_kernel': r['roofline']['kernel'],
+                      'hbm_model_frac': r['hbm_model']['frac_of_peak'], 'e2e': r['e2e']['value'],
+                      'gpu_launches': r['gpu_launches'], 'chains_per_gpu': r['config']['chains_per_gpu']}
+        for w in ('su3_8x8x8x8_nb256_l2hmc_eval_bf16', 'su3_8x8x8x8_nb32_l2hmc_train_bf16'):
+            r = l2hmc_workload(ctx, w, max(3, min(args.steps, 5)), 3, cuda_graphs=False, clocks=False)
+            sec[w] = {'value': r['value'], 'ms_per_step': r['ms_per_step'], 'unit': 'link-updates/s',
+                      'roofline_frac': r['roofline']['frac'], 'roofline_kernel': r['roofline']['kernel'],
+                      'e2e': r['e2e']['value'], 'gpu_launches': r['gpu_launches'],
+                      'chains_per_gpu': r['config']['chains_per_gpu'], 'parallelism': r['config']['parallelism'],
+                      'grad_allreduce': r.get('grad_allreduce')}
+        line['secondary'] = sec
+    if ctx.rank == 0:
+        if ctx.world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_subprocess(args.workload)
+            if full:
+                line['gpu_reference'] = gpu_reference_subprocess(args.workload)
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
+
+
+def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs: bool = False,
+                   clocks: bool = True) -> dict:
+    """SU(3) L2HMC eval / training step through the public Trainer API (BASELINE cfg 3 secondary / cfg 5)."""
+    import numpy as np
+    torch = ctx.torch
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
     from l2hmc_b200 import _lib, ops
     from l2hmc_b200.configs import (DynamicsConfig, LossConfig, NetWeight, NetWeights, NetworkConfig,
                                     get_input_spec)
@@ -474,131 +644,140 @@ def main_l2hmc(args):
     from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3
     from l2hmc_b200.network.pytorch.network import NetworkFactory
     from l2hmc_b200.trainers.pytorch.trainer import Trainer
-    mode, lattice, nb, nlf, units, beta = L2HMC_WORKLOADS[args.workload]
-    torch.manual_seed(SEED)            # identical initial weights on every rank (DDP broadcasts rank 0's)
+    mode, lattice, nb, nlf, units, beta = L2HMC_WORKLOADS[workload]
+    old_dt = torch.get_default_dtype()
+    torch.manual_seed(SEED)            # identical initial weights on every rank (Trainer also broadcasts rank 0's)
     np.random.seed(SEED)
     torch.set_default_dtype(torch.float32)
-    cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=0.01, eps_hmc=0.01,
-                         verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
-    fac = NetworkFactory(input_spec=get_input_spec(cfg),
-                         network_config=NetworkConfig(units=[units], activation_fn='tanh', dropout_prob=0.0,
-                                                      use_batch_norm=False),
-                         conv_config=None, net_weights=NetWeights(x=NetWeight(0., 1., 1.), v=NetWeight(1., 1., 1.)),
-                         build_unused_su3_xnet=False)
-    lat = LatticeSU3(nb, lattice)
-    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
-    tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
-                 clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16,
-                 cuda_graphs=args.cuda_graphs)
-    torch.manual_seed(SEED + 1 + rank)   # per-rank chains
-    x = lat.random().to(torch.complex128)
-    bt = torch.tensor(beta)
-    V = 1
-    for s_ in lattice:
-        V *= s_
-    units_rank = nb * 4 * V * 2 * nlf     # link-updates per step per GPU (nlf forward + nlf backward layers)
+    try:
+        cfg = DynamicsConfig(nchains=nb, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=0.01, eps_hmc=0.01,
+                             verbose=False, use_split_xnets=False, use_separate_networks=False, merge_directions=True)
+        fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                             network_config=NetworkConfig(units=[units], activation_fn='tanh', dropout_prob=0.0,
+                                                          use_batch_norm=False),
+                             conv_config=None, net_weights=NetWeights(x=NetWeight(0., 1., 1.), v=NetWeight(1., 1., 1.)),
+                             build_unused_su3_xnet=False)
+        lat = LatticeSU3(nb, lattice)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+        tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
+                     clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16,
+                     cuda_graphs=cuda_graphs)
+        torch.manual_seed(SEED + 1 + rank)   # per-rank chains
+        x = lat.random().to(torch.complex128)
+        bt = torch.tensor(beta)
+        V = 1
+        for s_ in lattice:
+            V *= s_
+        units_rank = nb * 4 * V * 2 * nlf     # link-updates per step per GPU (nlf forward + nlf backward layers)
 
-    def step(xin):
-        if mode == 'eval':
-            with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
-                return tr.eval_step((xin, bt))
-        return tr.train_step((xin, bt))
+        def step(xin):
+            if mode == 'eval':
+                with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+                    return tr.eval_step((xin, bt))
+            return tr.train_step((xin, bt))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+        for _ in range(warmup):
+            step(x)
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local) if (rank == 0 and clocks) else None
+        if sampler:
+            sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        e0.record()
+        for _ in range(steps):
+            xo, met = step(x)
+        e1.record()
+        ctx.barrier()
+        launches = _lib.launch_count() - l0
+        clk = sampler.stop() if sampler else None
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        value = world * units_rank / (ms * 1e-3)
+        assert torch.isfinite(met['loss']), 'non-finite loss'
+        # e2e: links from pinned host memory every step, loss read back to the host
+        xh = x.cpu().pin_memory()
+        loss_h = torch.empty((), dtype=met['loss'].dtype).pin_memory()
+        xin = torch.empty_like(x)
+        n_e2e = max(2, min(steps, 5))
+        ctx.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(n_e2e):
+            xin.copy_(xh, non_blocking=True)
+            xo, met = step(xin)
+            loss_h.copy_(met['loss'], non_blocking=True)
+        e3.record()
+        ctx.barrier()
+        e2e_val = world * units_rank * n_e2e / (ctx.max_over_ranks(e2.elapsed_time(e3)) * 1e-3)
+        # roofline of the tensor-core kernel of this path: k_heads_vupdate, timed alone with CUDA events
+        vnet = dyn._get_vnet(0)
+        pack = vnet.heads_pack()
+        xdim = pack.xdim
+        z = torch.tanh(torch.randn(nb, units, device=dev)).to(torch.bfloat16)
+        vv = lat.random_momentum().reshape(nb, xdim)
+        ff = lat.random_momentum().reshape(nb, xdim)
+        for _ in range(3):
+            ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
+        evs = []
+        for _ in range(10):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
+            b_.record()
+            evs.append((a_, b_))
         torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step(x)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    l0 = _lib.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        xo, met = step(x)
-    e1.record()
-    barrier()
-    launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t) / args.steps
-    value = world * units_rank / (ms * 1e-3)
-    assert torch.isfinite(met['loss']), 'non-finite loss'
-    # e2e: links from pinned host memory every step, loss read back to the host
-    xh = x.cpu().pin_memory()
-    loss_h = torch.empty((), dtype=met['loss'].dtype).pin_memory()
-    xin = torch.empty_like(x)
-    n_e2e = max(2, min(args.steps, 5))
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(n_e2e):
-        xin.copy_(xh, non_blocking=True)
-        xo, met = step(xin)
-        loss_h.copy_(met['loss'], non_blocking=True)
-    e3.record()
-    barrier()
-    t2 = torch.tensor([e2.elapsed_time(e3)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_val = world * units_rank * n_e2e / (float(t2) * 1e-3)
-    # roofline of the tensor-core kernel of this path: k_heads_vupdate, timed alone with CUDA events
-    peak, peak_kind = peaks()
-    vnet = dyn._get_vnet(0)
-    pack = vnet.heads_pack()
-    xdim = pack.xdim
-    z = torch.tanh(torch.randn(nb, units, device=dev)).to(torch.bfloat16)
-    vv = lat.random_momentum().reshape(nb, xdim)
-    ff = lat.random_momentum().reshape(nb, xdim)
-    for _ in range(3):
-        ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
-    evs = []
-    for _ in range(10):
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        ops.su3_heads_vupdate(z, pack, vv, ff, 0.01, 1)
-        b_.record()
-        evs.append((a_, b_))
-    torch.cuda.synchronize()
-    ms_k = statistics.mean(a_.elapsed_time(b_) for a_, b_ in evs)
-    algo = 3.0 * 16 * nb * xdim + 3.0 * 2 * xdim * units          # v r, F r, v' w (complex128) + bf16 weights once
-    ach = algo / (ms_k * 1e-3) / 1e9
-    flops = 2.0 * 3 * nb * xdim * units
-    if rank == 0:
-        line = {
-            'metric': METRIC, 'value': value, 'unit': 'link-updates/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f64 lattice + bf16 nets (fp32 accumulate)', 'data': 'synthetic',
-            'config': {'workload': args.workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
+        ms_k = statistics.mean(a_.elapsed_time(b_) for a_, b_ in evs)
+        algo = 3.0 * 16 * nb * xdim + 3.0 * 2 * xdim * units          # v r, F r, v' w (complex128) + bf16 weights once
+        ach = algo / (ms_k * 1e-3) / 1e9
+        flops = 2.0 * 3 * nb * xdim * units
+        res = {
+            'workload': workload, 'value': value, 'ms_per_step': ms, 'gpu_launches': launches, 'clocks': clk,
+            'dtype': 'f64 lattice + bf16 nets (fp32 accumulate)',
+            'config': {'workload': workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'units': [units], 'beta': beta, 'step': mode,
-                       'cuda_graphs': bool(args.cuda_graphs),
+                       'cuda_graphs': bool(cuda_graphs),
                        'start': 'hot (g.random), random-init weights',
                        'parallelism': (f'chains sharded over {world} GPU(s); '
-                                       + ('one flat bf16 NCCL all-reduce of the NN gradients per step' if mode == 'train'
+                                       + ('NN gradients averaged over the ranks in a flat bf16 bucket: NCCL all-reduce on a '
+                                          'side stream, overlapped with the tail of backward' if mode == 'train'
                                           else 'no collective')),
                        'l2_policy': 'fields + weights (~1 GB) exceed L2; no flush'},
             'roofline': {'bound': 'hbm', 'kernel': 'k_heads_vupdate (tcgen05 heads GEMM + momentum update)',
-                         'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind,
-                         'traffic': None, 'algorithmic_bytes_per_launch': algo, 'avg_launch_ms': ms_k,
-                         'tensor_tflops': flops / (ms_k * 1e-3) / 1e12,
+                         'achieved': ach, 'peak': ctx.peak, 'unit': 'GB/s', 'frac': ach / ctx.peak,
+                         'peak_kind': ctx.peak_kind, 'traffic': None, 'algorithmic_bytes_per_launch': algo,
+                         'avg_launch_ms': ms_k, 'tensor_tflops': flops / (ms_k * 1e-3) / 1e12,
                          'note': 'algorithmic bytes = v, F read + v\' written (complex128) + the bf16 head weights once; '
                                  'the GEMM is 0.2 % of the bf16 tensor peak by construction (HBM-bound op)'},
-            'cpu_baseline': (cpu_baseline_subprocess(args.workload) if (world == 1 and not args.no_cpu_baseline) else None),
             'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': x.numel() * x.element_size(),
                     'd2h_bytes_per_step': loss_h.element_size(), 'steps': n_e2e,
                     'api': f'Trainer.{mode}_step((x_host_pinned -> device, beta))'},
-            'gpu_launches': launches, 'clocks': clocks,
+            'grad_allreduce': getattr(tr, 'allreduce_info', lambda: None)() if mode == 'train' else None,
+        }
+        del tr, dyn, fac, lat, x, xin, vv, ff, pack, vnet, xo, met
+        ctx.free()
+        return res
+    finally:
+        torch.set_default_dtype(old_dt)
+
+
+def main_l2hmc(args):
+    ctx = Ctx()
+    r = l2hmc_workload(ctx, args.workload, args.steps, args.warmup, cuda_graphs=args.cuda_graphs)
+    if ctx.rank == 0:
+        line = {
+            'metric': METRIC, 'value': r['value'], 'unit': 'link-updates/s', 'n_gpus': ctx.world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': r['dtype'], 'data': 'synthetic', 'config': r['config'],
+            'roofline': r['roofline'],
+            'cpu_baseline': (cpu_baseline_subprocess(args.workload) if (ctx.world == 1 and not args.no_cpu_baseline)
+                             else None),
+            'e2e': r['e2e'], 'gpu_launches': r['gpu_launches'], 'clocks': r['clocks'],
+            'grad_allreduce': r['grad_allreduce'],
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def cpu_baseline_subprocess(workload: str):
@@ -680,6 +859,12 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--thermalise', type=int, default=0,
                     help='HMC trajectories run before timing (default 0: hot start, as the reference\'s g.random)')
+    ap.add_argument('--thermalise-n', type=int, default=100,
+                    help='trajectories of the `thermalised` entry the default run adds next to the hot-start headline')
+    ap.add_argument('--headline-only', action='store_true',
+                    help='skip the thermalised / secondary (BASELINE cfg 2, 3, 5) / gpu_reference entries')
+    ap.add_argument('--no-parity', action='store_true',
+                    help='skip the oracle check of one chain of the timed batch')
     ap.add_argument('--cuda-graphs', action='store_true',
                     help='L2HMC workloads: run the Trainer step functions as CUDA graphs (Trainer(cuda_graphs=True))')
     args = ap.parse_args()

@@ -307,6 +307,10 @@ class SU3VUpdate(torch.autograd.Function):
 # backward pass ends (autograd engine callback) -- instead of 2*N_LF*2 GEMMs each followed by a bf16->fp32
 # cast and an accumulation into a 75 MB .grad (8^4: ~38 GB of traffic per training step saved).
 DEFER_HEAD_GRADS = False
+# Multi-rank training (Trainer.train_step sets it around loss.backward()): a dist.GradBucket.  The deferred dW GEMMs
+# then write straight into the bucket's flat exchange buffer and start the all-reduce of their slice at once, so the
+# collective of one head overlaps the GEMM of the next and the rest of the backward pass.
+HEAD_GRAD_SINK = None
 
 
 def _flush_head_grads(net) -> None:
@@ -317,13 +321,23 @@ def _flush_head_grads(net) -> None:
     ws, bs, cs, wt, bt, wq, bq, cq = net.head_params()
     z = torch.cat([p[3] for p in pend])
 
+    sink = HEAD_GRAD_SINK
+
     def acc(param, g):
         if param.requires_grad:
             g = g.to(param.dtype).reshape(param.shape)
             param.grad = g if param.grad is None else param.grad + g
     for k, (w, b_) in enumerate(((ws, bs), (wt, bt), (wq, bq))):
         g = torch.cat([p[k] for p in pend])              # [n_updates * nb, xdim] pre-activation cotangents
-        acc(w, g.t() @ z)
+        if sink is not None and w.requires_grad and w.grad is None and id(w) in sink.offsets:
+            out = sink.view(w)
+            if out.dtype == g.dtype == z.dtype:
+                torch.mm(g.t(), z, out=out)              # dW lands in the exchange buffer, no cast, no copy
+            else:
+                out.copy_(g.t() @ z)
+            sink.reduce_async(w)                         # its all-reduce starts while the next head's GEMM runs
+        else:
+            acc(w, g.t() @ z)
         acc(b_, g.sum(0, dtype=torch.float32))
     acc(cs, torch.stack([p[4] for p in pend]).sum(0))
     acc(cq, torch.stack([p[5] for p in pend]).sum(0))

@@ -70,6 +70,163 @@ def gather_chains(local: Tensor, nchains: int) -> Tensor:
     return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
 
 
+def bind_rank_to_cores(local_rank: int, local_world: int) -> int:
+    """Give each rank of a node its own slice of the host cores this process may use (and, where the GPU's PCI
+    device reports a NUMA node with cores in that set, a slice of THAT node's cores), before it allocates pinned
+    host memory: first-touch then places the staging buffers next to the GPU and the ranks' copy / launch threads
+    stop migrating over each other's cores.  A single rank keeps every core.  Returns the number of cores bound."""
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+    if local_world <= 1 or len(allowed) < 2 * local_world:
+        return len(allowed)
+    cores = allowed
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        node = int(open(f'/sys/bus/pci/devices/{bdf}/numa_node').read())
+        if node >= 0:
+            lst = open(f'/sys/devices/system/node/node{node}/cpulist').read().strip()
+            on_node = set()
+            for part in lst.split(','):
+                lo, _, hi = part.partition('-')
+                on_node.update(range(int(lo), int(hi or lo) + 1))
+            near = [c for c in allowed if c in on_node]
+            if len(near) >= 2 and len(near) < len(allowed):
+                # ranks whose GPUs share this node split its cores among themselves
+                peers = []
+                for r in range(local_world):
+                    q = torch.cuda.get_device_properties(r)
+                    b2 = f'{q.pci_domain_id:04x}:{q.pci_bus_id:02x}:{q.pci_device_id:02x}.0'
+                    try:
+                        if int(open(f'/sys/bus/pci/devices/{b2}/numa_node').read()) == node:
+                            peers.append(r)
+                    except OSError:
+                        pass
+                if local_rank in peers and len(near) >= 2 * len(peers):
+                    k = len(near) // len(peers)
+                    j = peers.index(local_rank)
+                    mine = near[j * k:(j + 1) * k]
+                    os.sched_setaffinity(0, mine)
+                    return len(mine)
+    except Exception:
+        pass
+    k = len(cores) // local_world
+    mine = cores[local_rank * k:(local_rank + 1) * k]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return len(allowed)
+    return len(mine)
+
+
+def broadcast_module_state(module: torch.nn.Module, extra: Iterable[Tensor] = (), src: int = 0) -> int:
+    """What wrapping the model in DDP does at construction in the reference (trainer.py:246-255): every rank
+    starts from rank `src`'s parameters and buffers.  `extra`: further tensors that must agree across ranks (the
+    numpy-built leapfrog masks).  Returns the number of tensors broadcast (0 in a single process)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0
+    n = 0
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()) + list(extra):
+            if isinstance(t, torch.nn.parameter.UninitializedParameter):
+                continue
+            dist.broadcast(t.data if isinstance(t, torch.nn.Parameter) else t, src)
+            n += 1
+    return n
+
+
+class GradBucket:
+    """The gradient exchange of L2HMC training (the role of DDP's buckets, trainer.py:246-255): ONE flat buffer in
+    `dtype` (bf16 halves the bytes on the wire) laid out over a FIXED parameter list, so every rank reduces the same
+    elements whether or not a parameter received a gradient this step (a missing gradient counts as zero).
+
+    Producers that form a large gradient late in backward -- the deferred dW GEMMs of the vnet heads, 99.9 % of the
+    bytes -- write it straight into `view(p)` and call `reduce_async(p)`: the all-reduce of that slice runs on NCCL's
+    stream while the next head's GEMM and the remaining small gradients are still being computed.  `finish()` copies
+    in whatever is still in `.grad`, reduces the rest in as few calls as there are contiguous gaps, waits, and hands
+    every parameter its averaged gradient back in `.grad` (own dtype)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], dtype: Optional[torch.dtype] = None):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError('GradBucket needs at least one parameter')
+        self.dtype = dtype or self.params[0].dtype
+        # large tensors first: their slices are reduced individually as they land, the small rest in one call
+        order = sorted(range(len(self.params)), key=lambda i: -self.params[i].numel())
+        self.offsets: dict = {}
+        off = 0
+        for i in order:
+            p = self.params[i]
+            self.offsets[id(p)] = (off, p.numel())
+            off += (p.numel() + 7) // 8 * 8          # 16-byte aligned slices
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=self.dtype, device=self.params[0].device)
+        self._works: list = []
+        self._done: list = []                         # (offset, numel) already handed to the collective
+        self.last = {'elements': off, 'bytes': off * self.flat.element_size(), 'calls': 0, 'early_calls': 0}
+
+    def active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size() > 1
+
+    def view(self, p: torch.nn.Parameter) -> Tensor:
+        off, n = self.offsets[id(p)]
+        return self.flat[off:off + n].view(p.shape)
+
+    def begin(self) -> None:
+        self._works, self._done = [], []
+        self.flat.zero_()
+
+    def reduce_async(self, p: torch.nn.Parameter) -> None:
+        """the gradient of `p` is complete in `view(p)`: start its all-reduce now"""
+        off, n = self.offsets[id(p)]
+        self._done.append((off, n))
+        if self.active():
+            self._works.append(dist.all_reduce(self.flat[off:off + n], op=dist.ReduceOp.SUM, async_op=True))
+
+    def finish(self) -> int:
+        """returns the number of all-reduce calls of this step"""
+        done = {o for o, _ in self._done}
+        with torch.no_grad():
+            for p in self.params:
+                off, n = self.offsets[id(p)]
+                if off not in done and p.grad is not None:
+                    self.flat[off:off + n].view(p.shape).copy_(p.grad)
+        early = len(self._works)
+        if self.active():
+            # complement of the slices already reduced, as maximal contiguous runs
+            gaps, cur = [], 0
+            for off, n in sorted(self._done):
+                if off > cur:
+                    gaps.append((cur, off))
+                cur = max(cur, (off + n + 7) // 8 * 8)
+            if cur < self.numel:
+                gaps.append((cur, self.numel))
+            for lo, hi in gaps:
+                self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            for w in self._works:
+                w.wait()                              # stream-level wait: the current stream orders after NCCL's
+        scale = 1.0 / (dist.get_world_size() if self.active() else 1)
+        with torch.no_grad():
+            for p in self.params:
+                # every parameter of the bucket gets the averaged gradient (zero where no rank produced one: a
+                # decision taken per rank from `p.grad is None` could differ between ranks)
+                off, n = self.offsets[id(p)]
+                src = self.flat[off:off + n].view(p.shape)
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                if src.dtype == p.grad.dtype:
+                    torch.mul(src, scale, out=p.grad)
+                else:
+                    p.grad.copy_(src).mul_(scale)
+        self.last = {'elements': self.numel, 'bytes': self.numel * self.flat.element_size(),
+                     'calls': len(self._works), 'early_calls': early}
+        n_calls = len(self._works)
+        self._works = []
+        return n_calls
+
+
 def allreduce_mean_grads(params: Iterable[torch.nn.Parameter], bucket_dtype: Optional[torch.dtype] = None) -> int:
     """ONE all-reduce over a flat buffer of the gradients that exist (parameters
     that took no part in the step -- the dead SU(3) xnet -- are skipped, which is

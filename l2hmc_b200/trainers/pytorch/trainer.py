@@ -44,6 +44,23 @@ class Trainer:
         self.grad_bucket_dtype = grad_bucket_dtype
         self._graphs: dict = {}
         self._eager = False            # True while warming up / capturing: step functions run their eager body
+        # more than one rank: start from rank 0's weights, buffers and leapfrog masks (what wrapping the model in
+        # DDP does in the reference, trainer.py:246-255), and exchange gradients through one flat bucket over the
+        # FIXED list of trainable parameters
+        self._bucket = None
+        if l2dist.dist.is_available() and l2dist.dist.is_initialized() and l2dist.dist.get_world_size() > 1:
+            l2dist.broadcast_module_state(dynamics, extra=getattr(dynamics, 'masks', ()))
+            bump_weights_generation()      # in-place on .data: no `_version` moved
+            if hasattr(dynamics, '_planar_cache'):
+                dynamics._planar_cache = None
+            self._bucket = l2dist.GradBucket(params, grad_bucket_dtype)
+
+    def allreduce_info(self) -> Optional[dict]:
+        """size / dtype / number of collectives of the last gradient exchange (None in a single process)"""
+        if self._bucket is None:
+            return None
+        return dict(self._bucket.last, dtype=str(self._bucket.dtype).replace('torch.', ''),
+                    world=l2dist.dist.get_world_size())
 
     # ------------------------------------------------------------ CUDA graphs
     def _canon(self, x: Tensor) -> Tensor:
@@ -165,15 +182,21 @@ class Trainer:
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
         ag.DEFER_HEAD_GRADS = True        # one dW GEMM per vnet head per step instead of one per v-update
+        if self._bucket is not None:
+            self._bucket.begin()
+            ag.HEAD_GRAD_SINK = self._bucket
         try:
             loss.backward()
         finally:
             ag.DEFER_HEAD_GRADS = False
+            ag.HEAD_GRAD_SINK = None
+        # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks.  The head weights
+        # (99.9 % of the bytes) were written into the bucket by their deferred GEMMs and are already on the wire;
+        # finish() adds the small rest, waits, and leaves the averaged gradients in .grad
+        if self._bucket is not None:
+            self._bucket.finish()
         if not capturing:
             ag.check_exp_adjoint_flags()  # one device read per step (matrix-exp adjoint range check)
-        # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks;
-        # parameters without a gradient (the unused SU(3) xnet) are not communicated.
-        l2dist.allreduce_mean_grads(self.optimizer.param_groups[0]['params'], self.grad_bucket_dtype)
         if self.clip_val > 0:
             torch.nn.utils.clip_grad_norm_(self.optimizer.param_groups[0]['params'], self.clip_val)
         self.optimizer.step()

@@ -50,7 +50,40 @@ def _worker(rank, world, port, nchains, q):
     mean = sum(range(1, world + 1)) / world
     ok_grad = (n == 9 and torch.allclose(a.grad, torch.full((5,), mean))
                and torch.allclose(b.grad, torch.full((2, 2), 10 * mean)) and unused.grad is None)
-    q.put((rank, bool(ok_gather), bool(ok_grad)))
+    # GradBucket: fixed parameter list (a parameter without a gradient on this rank counts as zero), one slice
+    # reduced early (what the deferred head GEMMs do), the rest in finish(); every rank ends with the same mean
+    torch.manual_seed(3)
+    ps = [torch.nn.Parameter(torch.zeros(s_)) for s_ in ((4, 3), (7,), (), (2, 5))]
+    ok_bucket = True
+    for bdt in (None, torch.bfloat16):
+        bucket = l2d.GradBucket(ps, bdt)
+        bucket.begin()
+        for pp in ps:
+            pp.grad = None
+        big = ps[0]
+        bucket.view(big).copy_(torch.full((4, 3), float(rank + 1)))      # produced straight into the bucket
+        bucket.reduce_async(big)
+        ps[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+        ps[2].grad = torch.tensor(2.0 * (rank + 1))
+        if rank == 0:
+            ps[3].grad = torch.ones(2, 5)                               # only rank 0 has this gradient
+        ncalls = bucket.finish()
+        ok_bucket &= ncalls == 2 and bucket.last['early_calls'] == 1
+        ok_bucket &= torch.allclose(ps[0].grad, torch.full((4, 3), mean))
+        ok_bucket &= torch.allclose(ps[1].grad, torch.arange(7, dtype=torch.float32) * mean)
+        ok_bucket &= torch.allclose(ps[2].grad, torch.tensor(2.0 * mean))
+        ok_bucket &= torch.allclose(ps[3].grad, torch.full((2, 5), 1.0 / world))
+        ok_bucket &= all(pp.grad.dtype == torch.float32 for pp in ps)
+    # broadcast_module_state: rank 0's parameters, buffers and extra tensors everywhere
+    torch.manual_seed(100 + rank)
+    mod = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2))
+    mask = torch.full((1, 6), float(rank))
+    nbc = l2d.broadcast_module_state(mod, extra=[mask])
+    flat = torch.cat([t.detach().reshape(-1).float() for t in list(mod.parameters()) + list(mod.buffers())] + [mask.reshape(-1)])
+    both = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(both, flat)
+    ok_bcast = nbc == 8 and all(torch.equal(both[0], o) for o in both) and float(mask.sum()) == 0.0
+    q.put((rank, bool(ok_gather), bool(ok_grad and ok_bucket and ok_bcast)))
     dist.barrier()
     dist.destroy_process_group()
 
