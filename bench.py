@@ -524,38 +524,42 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
 
 def parity_of_timed_batch(ctx: Ctx, x, v, out, beta, eps, nlf, lattice) -> dict:
     """chain 0 of the timed batch, the very tensors the timed trajectories read and wrote, against the oracle on
-    the host: the reference's own `Dynamics.transition_kernel_hmc` (oracle/_ref) when it travelled, else the
-    numpy restatement (oracle/dynamics.py).  Rank 0 only; runs after the timed region."""
+    same inputs: the reference's own `Dynamics.transition_kernel_hmc` (oracle/_ref) when it travelled, else the
+    numpy restatement (oracle/dynamics.py) on the host.  Rank 0 only; runs after the timed region."""
     if ctx.rank != 0:
         return None
     import numpy as np
     torch = ctx.torch
-    x0, v0 = x[:1].cpu(), v[:1].cpu()
     gx, gv, gen = out[0][:1].cpu().numpy(), out[1][:1].cpu().numpy(), out[2][:1].cpu().numpy()
     t0 = time.perf_counter()
     from oracle import ref_shim
     if ref_shim.available():
-        kind = 'reference (oracle/_ref, CPU)'
+        # the reference puts its module constants on CUDA as soon as torch sees a GPU (l2hmc/__init__.py:45-51), so
+        # in this process it runs its own ATen/CUDA path (none of our kernels) on the same device
+        kind = 'reference (oracle/_ref, its own ATen path on ' + str(x.device) + ')'
         ref = ref_shim.load_reference(torch.float64)
         old = torch.get_default_dtype()
         torch.set_default_dtype(torch.float64)
         try:
+            x0, v0 = x[:1].clone(), v[:1].clone()
             lat = ref.LatticeSU3(1, lattice)
             cfg = ref.DynamicsConfig(nchains=1, group='SU3', latvolume=lattice, nleapfrog=nlf, eps=eps, eps_hmc=eps,
                                      verbose=False, use_split_xnets=False, use_separate_networks=False,
                                      merge_directions=True)
-            rdyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None).cpu()
-            bt = torch.tensor(beta)
+            rdyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+            bt = torch.tensor(beta, device=x.device)
             sp, met = rdyn.transition_kernel_hmc(ref.State(x=x0, v=v0, beta=bt), eps=eps, nleapfrog=nlf)
-            wx, wv = sp.x.detach().reshape(x0.shape).numpy(), sp.v.detach().reshape(v0.shape).numpy()
-            wh0 = (lat.action(x0, bt) + lat.g.kinetic_energy(v0)).detach().numpy()
-            wh1 = (lat.action(sp.x.detach().reshape(x0.shape), bt) + lat.g.kinetic_energy(sp.v.detach())).detach().numpy()
+            wx, wv = sp.x.detach().reshape(x0.shape).cpu().numpy(), sp.v.detach().reshape(v0.shape).cpu().numpy()
+            wh0 = (lat.action(x0, bt) + lat.g.kinetic_energy(v0)).detach().cpu().numpy()
+            wh1 = (lat.action(sp.x.detach().reshape(x0.shape), bt)
+                   + lat.g.kinetic_energy(sp.v.detach())).detach().cpu().numpy()
+            del sp, met, rdyn, lat
         finally:
             torch.set_default_dtype(old)
     else:
         kind = 'port (oracle/dynamics.py, numpy)'
         from oracle import dynamics as od, su3 as osu3
-        xn, vn = x0.numpy(), v0.numpy()
+        xn, vn = x[:1].cpu().numpy(), v[:1].cpu().numpy()
         want, _ = od.transition_kernel_hmc(od.SU3Ops, od.State(xn, vn, beta), eps, nlf)
         wx, wv = want.x, want.v
         wh0 = osu3.action(xn, beta) + osu3.kinetic_energy(vn)

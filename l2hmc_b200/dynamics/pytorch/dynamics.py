@@ -741,10 +741,10 @@ class Dynamics(nn.Module):
         of the force are the same tensors.  The reference recomputes them (dynamics.py:1187-1228,
         1266-1297); with `reuse_force = 'always'` they are computed once per distinct x (2 nlf + 1
         instead of 4 nlf force evaluations per fb sweep; forward results bit-identical, under autograd
-        the shared tensors simply receive the sum of both cotangents).  Default 'never' until the switch
-        has been through the GPU parity tests (tests/test_gpu_dynamics.py runs both settings when
-        L2B_TEST_REUSE_FORCE=1)."""
-        return getattr(self, 'reuse_force', 'never') == 'always'
+        the shared tensors simply receive the sum of both cotangents).  Default 'always' since round 2
+        (tests/test_gpu_reuse_force.py: bit-identical sweeps, force count, gradients); 'never' = recompute
+        as the reference does."""
+        return getattr(self, 'reuse_force', 'always') == 'always'
 
     def _force(self, state: State) -> Tensor:
         if not self._reuse_force():

@@ -47,13 +47,12 @@ class LatticeSU3(Lattice):
         self.nt, self.nx, self.ny, self.nz = shape
         self.c1 = float(c1)      # c1 != 0 (DBW2 / rectangle term): plaquette part on the kernels, rectangle
         # `rect_kernel`: evaluate the improved action / force with the hand-written rectangle-staple kernel
-        # (l2b_su3_force_c1) wherever no autograd graph is needed (HMC, eval); under autograd (training) the
-        # rectangle part runs as ATen ops.  L2B_RECT_KERNEL=0 forces the ATen path everywhere.
+        # (l2b_su3_force_c1); L2B_RECT_KERNEL=0 forces the ATen path everywhere.
         self.rect_kernel = os.environ.get('L2B_RECT_KERNEL', '1') == '1'
-        # under autograd too (adjoint kernel l2b_su3_action_grad_c1, body pinned on torch autograd by
-        # tests/test_hostemu.py); opt-in until its launch has been run on a GPU
-        # (tests/test_gpu_su3.py::test_rectangle_kernel_gradients, L2B_RECT_KERNEL_AUTOGRAD=1)
-        self.rect_kernel_autograd = os.environ.get('L2B_RECT_KERNEL_AUTOGRAD', '0') == '1'
+        # under autograd too (adjoint kernel l2b_su3_action_grad_c1; body pinned on torch autograd by
+        # tests/test_hostemu.py, launch by tests/test_gpu_su3.py::test_rectangle_kernel_gradients against the
+        # reference's autograd goldens).  L2B_RECT_KERNEL_AUTOGRAD=0: rectangle part as ATen ops under autograd.
+        self.rect_kernel_autograd = os.environ.get('L2B_RECT_KERNEL_AUTOGRAD', '1') == '1'
         super().__init__(group=self.g, nchains=nchains, shape=list(shape))
 
     def _field(self, x: Tensor) -> Tensor:

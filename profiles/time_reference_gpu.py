@@ -19,6 +19,12 @@ from oracle import ref_shim  # noqa: E402
 assert torch.cuda.is_available(), 'needs a GPU'
 assert ref_shim.available(), 'oracle/_ref did not travel'
 names = sys.argv[1:] or ['su3_16x16x16x16_nb64_nlf10_c128', 'su3_8x8x8x8_nb256_nlf10_c128', 'u1_64x64_nb4096_nlf10_f32']
+if len(names) > 1:
+    # the reference freezes dtype-typed constants at import (group/su3/pytorch/utils.py:28-36): one process per workload
+    import subprocess
+    for name in names:
+        subprocess.run([sys.executable, __file__, name], check=False)
+    sys.exit(0)
 for name in names:
     group, lattice, nb, nlf, dtype, beta = bench.WORKLOADS[name]
     ref = ref_shim.load_reference(torch.float64 if dtype == 'f64' else torch.float32)

@@ -4,8 +4,10 @@ The CUDA trajectory (C ABI `l2b_su3_hmc_trajectory`, and the public `Dynamics.tr
 compared on identical seeded `(x, v, beta)` with
 
 * the reference's own `Dynamics.transition_kernel_hmc` (`dynamics/pytorch/dynamics.py:915-954`, `leapfrog_hmc`
-  `:900-913`; action `lattice/su3/pytorch/lattice.py:252-269`, force by autograd `:299-308`) run on the CPU in
-  the test from the unmodified copy `oracle/_ref` (it travels with the snapshot), and
+  `:900-913`; action `lattice/su3/pytorch/lattice.py:252-269`, force by autograd `:299-308`) run in the test from
+  the unmodified copy `oracle/_ref` (it travels with the snapshot) -- on whatever device the reference picks for
+  itself: it moves its module-level constants to CUDA as soon as torch sees a GPU (`l2hmc/__init__.py:45-51`,
+  `dynamics.py:194-200`), so on the GPU box this is the reference's own ATen/CUDA path, not ours -- and
 * the numpy oracle (`oracle/dynamics.py`), which needs nothing but numpy and so also runs where `oracle/_ref`
   did not travel.
 
@@ -75,9 +77,11 @@ def test_hmc_trajectory_matches_numpy_oracle_at_baseline_size(shape, nb, nlf, ep
     wh0 = osu3.action(x, beta) + osu3.kinetic_energy(v)
     wh1 = osu3.action(want.x, beta) + osu3.kinetic_energy(want.v)
     _check((gx, gv, gh0, gh1), (want.x, want.v, wh0, wh1), 'numpy oracle')
-    # the action alone, 1e-12 relative, and the observables the reference derives from the same plaquette sums
-    assert np.allclose(en[:, 0], osu3.action(x, beta), rtol=1e-12, atol=0)
-    assert np.allclose(en[:, 2], osu3.action(want.x, beta), rtol=1e-12, atol=0)
+    # energies = (KE0, S0, KE1, S1): the Wilson action and the kinetic energy separately, 1e-12 relative
+    assert np.allclose(en[:, 1], osu3.action(x, beta), rtol=1e-12, atol=0)
+    assert np.allclose(en[:, 3], osu3.action(want.x, beta), rtol=1e-12, atol=0)
+    assert np.allclose(en[:, 0], osu3.kinetic_energy(v), rtol=1e-12, atol=0)
+    assert np.allclose(en[:, 2], osu3.kinetic_energy(want.v), rtol=1e-12, atol=0)
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason='oracle/_ref did not travel')
@@ -92,13 +96,14 @@ def test_hmc_trajectory_matches_the_reference_itself_at_baseline_size(shape, nb,
         cfg = ref.DynamicsConfig(nchains=nb, group='SU3', latvolume=shape, nleapfrog=nlf, eps=eps, eps_hmc=eps,
                                  verbose=False, use_split_xnets=False, use_separate_networks=False,
                                  merge_directions=True)
-        rdyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None).cpu()
-        xt, vt, bt = torch.from_numpy(x), torch.from_numpy(v), torch.tensor(beta)
+        rdyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+        rdev = torch.device('cuda' if torch.cuda.is_available() else 'cpu')   # l2hmc/__init__.py:45-51
+        xt, vt, bt = torch.from_numpy(x).to(rdev), torch.from_numpy(v).to(rdev), torch.tensor(beta, device=rdev)
         sp, met = rdyn.transition_kernel_hmc(ref.State(x=xt, v=vt, beta=bt), eps=eps, nleapfrog=nlf)
-        wx, wv = sp.x.detach().reshape(x.shape).numpy(), sp.v.detach().reshape(v.shape).numpy()
-        wh0 = (lat.action(xt, bt) + lat.g.kinetic_energy(vt)).detach().numpy()
-        wh1 = (lat.action(sp.x.detach().reshape(xt.shape), bt) + lat.g.kinetic_energy(sp.v.detach())).detach().numpy()
-        racc = met['acc'].detach().numpy()
+        wx, wv = host(sp.x).reshape(x.shape), host(sp.v).reshape(v.shape)
+        wh0 = host(lat.action(xt, bt) + lat.g.kinetic_energy(vt))
+        wh1 = host(lat.action(sp.x.detach().reshape(xt.shape), bt) + lat.g.kinetic_energy(sp.v.detach()))
+        racc = host(met['acc'])
 
         gx, gv, gh0, gh1, _ = _cuda_trajectory(x, v, beta, eps, nlf)
         _check((gx, gv, gh0, gh1), (wx, wv, wh0, wh1), 'reference')
@@ -120,7 +125,7 @@ def test_hmc_trajectory_matches_the_reference_itself_at_baseline_size(shape, nb,
         assert np.abs(host(mmet['acc']) - racc).max() < 1e-12 * scale
         # observables of the proposal (`calc_metrics`, lattice.py:310-349): plaquette and both charges
         for name in ('plaqs', 'sinQ', 'intQ'):
-            rm = lat.calc_metrics(sp.x.detach().reshape(xt.shape))[name].detach().numpy()
+            rm = host(lat.calc_metrics(sp.x.detach().reshape(xt.shape))[name])
             mm = host(mlat.calc_metrics(mp.x)[name])
             assert np.allclose(mm, rm, rtol=1e-12, atol=1e-13), name
     finally:

@@ -291,8 +291,6 @@ def test_rectangle_action_c1_matches_reference(golden_dir, kernel):
         torch.set_default_dtype(old)
 
 
-@pytest.mark.skipif(__import__('os').environ.get('L2B_RECT_KERNEL_AUTOGRAD', '0') != '1',
-                    reason='opt-in until run on a GPU: L2B_RECT_KERNEL_AUTOGRAD=1')
 def test_rectangle_kernel_gradients(golden_dir):
     """improved action under autograd on the adjoint kernel (l2b_su3_action_grad_c1) == the ATen-op path"""
     from l2hmc_b200.lattice.su3.pytorch.lattice import LatticeSU3

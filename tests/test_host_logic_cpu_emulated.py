@@ -323,10 +323,10 @@ def test_the_late_gpu_tests_themselves_run_clean_on_the_emulation(golden_dir, mo
         with su3_host_logic_on_cpu(monkeypatch):
             for kernel in (True, False):
                 zi.test_hmc_accepts_with_the_energies_of_potential_fn(golden_dir, kernel)
-            import tests.test_gpu_su3 as zs                  # opt-in on the GPU: improved action under autograd
+            import tests.test_gpu_su3 as zs                  # improved action under autograd
             monkeypatch.setattr(zs, 'DEV', 'cpu')
             zs.test_rectangle_kernel_gradients(golden_dir)
-            import tests.test_gpu_reuse_force as zr          # opt-in on the GPU; its no-autocast body runs here
+            import tests.test_gpu_reuse_force as zr          # its no-autocast body runs here
             monkeypatch.setattr(zr, 'DEV', 'cpu')
             zr.test_su3_fb_sweep_is_bit_identical_and_evaluates_fewer_forces(golden_dir, False)
             zr.test_su3_gradients_with_reuse_equal_default(golden_dir)

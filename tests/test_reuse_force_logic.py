@@ -1,5 +1,5 @@
 """CPU tier: host logic of the force / vnet-input reuse between consecutive v-updates
-(`Dynamics._force`, `_vnet_vecs`; opt-in, `reuse_force = 'always'`).  The methods only need
+(`Dynamics._force`, `_vnet_vecs`; `reuse_force = 'always'`, the default).  The methods only need
 `grad_potential` and `group_to_vec`, so they run here on a stand-in object with counting stubs."""
 import types
 
