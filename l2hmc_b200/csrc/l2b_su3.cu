@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "l2b_common.cuh"
@@ -321,6 +322,115 @@ __global__ void __launch_bounds__(TS * 4, MINB) k_force_epx(const C* __restrict_
                                                             C* __restrict__ Uout, double eps_drift,
                                                             C* __restrict__ Paos, C* __restrict__ Uaos) {
   force_ep_body<TS, DRIFT, HOOK_AT, false, PIO, UAOS>(U, P, lat, coef, part, Uout, eps_drift, Paos, Uaos);
+}
+
+// ---------------------------------------------------------------------------
+// k_force_tma: the fused step with the block's OWN momenta and links -- the two first-touch, DRAM-latency
+// loads of a link's update, (9 + 9) LDG.128 per thread that k_force_ep keeps in registers from the last
+// staple direction on -- brought in by the TMA instead: one elected thread issues eight
+// `cp.async.bulk.tensor.2d` (SASS UTMALDG) for the [9 entries x 32 sites] boxes of P_mu and U_mu, mu = 0..3,
+// at kernel entry; they land in shared memory ([field][mu][e][site], 36 KB) behind an mbarrier while all
+// four warps multiply staples, and are read back with conflict-free LDS.128 right before the kick.
+// The planar field is a rank-2 tensor for the TMA: inner dimension = the 2 V doubles of one (chain, mu, e)
+// row, outer = the nb * 36 rows.  Same arithmetic in the same order as k_force_ep: same bits.
+// Variant 32 (`su3_force_variant`); needs V % 32 == 0, otherwise variant 22 runs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_addr(dst)), "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(smem_addr(bar))
+      : "memory");
+}
+
+template <int MINB, bool DRIFT>
+__global__ void __launch_bounds__(128, MINB) k_force_tma(const __grid_constant__ CUtensorMap mapP,
+                                                         const __grid_constant__ CUtensorMap mapU,
+                                                         const C* __restrict__ U, C* __restrict__ P, Lat lat,
+                                                         double coef, double* __restrict__ part,
+                                                         C* __restrict__ Uout, double eps_drift) {
+  constexpr int TS = 32;
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double red[4];
+  C* tileP = reinterpret_cast<C*>(tma_smem);            // [mu][e][site]
+  C* tileU = tileP + 4 * 9 * TS;
+  const int b = blockIdx.y;
+  const int mu = threadIdx.y;
+  const int site0 = blockIdx.x * TS;
+  const int site = site0 + threadIdx.x;
+  const int tid = threadIdx.y * TS + threadIdx.x;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bar)),
+                 "r"((uint32_t)(2 * 4 * 9 * TS * sizeof(C)))
+                 : "memory");
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      tma_load_2d(tileP + m * 9 * TS, &mapP, 2 * site0, (b * 4 + m) * 9, &bar);
+      tma_load_2d(tileU + m * 9 * TS, &mapU, 2 * site0, (b * 4 + m) * 9, &bar);
+    }
+  }
+  double retr = 0.0, p2 = 0.0;
+  {
+    Mat3<T> a, g, f, w;
+    const int ahead = site + PF_AHEAD_SITES;
+    if (ahead < lat.V) soa_prefetch<2>(soa_plane(U, lat, b, mu), lat.V, ahead);   // neighbours' L2 hits live on this
+    link_times_staples<T, C, 0, false>(a, U, lat, b, mu, site);                   // A = sum of the six staples
+    // the tiles have had the whole staple phase to land
+    {
+      uint32_t ok = 0;
+      for (uint32_t spin = 0; !ok; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_addr(&bar))
+            : "memory");
+        if (!ok && spin > (1u << 24)) __trap();
+      }
+    }
+    const C* tu = tileU + (mu * 9) * TS + threadIdx.x;
+    const C* tp = tileP + (mu * 9) * TS + threadIdx.x;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) { const C v = tu[e * TS]; w.re[e] = v.x; w.im[e] = v.y; }
+    mat_mul<false, false, false>(g, w, a);
+    retr = re_trace(g);
+    project_tah(f, g);
+    C* pp = soa_plane(P, lat, b, mu) + site;
+    const size_t V = lat.V;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      C v = tp[e * TS];
+      v.x = fma(-coef, f.re[e], v.x);
+      v.y = fma(-coef, f.im[e], v.y);
+      p2 = fma(v.x, v.x, p2);
+      p2 = fma(v.y, v.y, p2);
+      __stcs(pp + e * V, v);
+      if (DRIFT) { f.re[e] = eps_drift * v.x; f.im[e] = eps_drift * v.y; }
+    }
+    p2 -= 8.0;
+    if (DRIFT) {
+      Mat3<T> ex, un;
+      mat_exp_alg(ex, f);
+      mat_mul<false, false, false>(un, ex, w);
+      soa_store(soa_plane(Uout, lat, b, mu), lat.V, site, un);
+    }
+  }
+  if (part != nullptr) {
+    retr = block_sum<128>(retr, red, tid);
+    p2 = block_sum<128>(p2, red, tid);
+    if (tid == 0) {
+      double* o = part + ((size_t)b * gridDim.x + blockIdx.x) * 2;
+      o[0] = retr;
+      o[1] = p2;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1151,6 +1261,7 @@ __global__ void __launch_bounds__(NTL) k_rand_momentum(uint64_t seed, uint64_t o
 // default is the one measured fastest on B200 (profiles/).
 using ForceFn = void (*)(const C*, C*, Lat, double, double*, C*, double);
 using ForceFnX = void (*)(const C*, C*, Lat, double, double*, C*, double, C*, C*);
+using ForceFnTma = void (*)(const CUtensorMap, const CUtensorMap, const C*, C*, Lat, double, double*, C*, double);
 struct ForceVariant {
   int ts;
   ForceFn kick, nokick;
@@ -1161,6 +1272,8 @@ struct ForceVariant {
   // [0] first step (momenta from the boundary layout), [1] last step (links also to the boundary layout),
   // [2] first == last (N_LF = 1), [3] final half kick (momenta to the boundary layout)
   ForceFnX ends[4];
+  // [0] kick, [1] kick + drift with the block's own P / U tiles staged by the TMA (nullptr: none)
+  ForceFnTma tma[2];
 };
 #define L2B_ENDS(HOOK)                                                                                   \
   {k_force_epx<32, 3, true, HOOK, 1, false>, k_force_epx<32, 3, true, HOOK, 0, true>,                      \
@@ -1207,6 +1320,12 @@ const ForceVariant kForceVariants[] = {
     {32, k_force_ep<32, 3, false, 3, true>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3, true>, -1},   // 29: hook before the last direction
     {32, k_force_ep<32, 3, false, 2, true>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 2, true>, -1},   // 30: before the 2nd direction
     {32, k_force_ep<32, 4, false, 3, true>, k_force<32, 4, false, 2, false>, 0, k_force_ep<32, 4, true, 3, true>, -1},   // 31: as 29, <= 128 registers
+    // 32: variant 22 with the block's own momenta / links staged through shared memory by the TMA (k_force_tma)
+    {32, k_force_ep<32, 3, false, 3>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3>, -1, L2B_ENDS(3),
+     {k_force_tma<3, false>, k_force_tma<3, true>}},
+    // 33: as 32, <= 128 registers (16 warps / SM)
+    {32, k_force_ep<32, 3, false, 3>, k_force<32, 3, false, 2, false>, 0, k_force_ep<32, 3, true, 3>, -1, L2B_ENDS(3),
+     {k_force_tma<4, false>, k_force_tma<4, true>}},
 };
 constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVariants[0]));
 int g_fuse_conversions = 1;   // fold the momentum / output layout conversions into the trajectory's end launches
@@ -1297,10 +1416,47 @@ int launch_s2a(const Geo& g, const C* soa, C* aos, cudaStream_t st) {
   L2B_LAUNCHED("k_soa_to_aos");
   return L2B_OK;
 }
+// rank-2 tensor map of a planar field for the TMA: inner = the 2 V doubles of one (chain, mu, e) row, outer = the
+// nb * 36 rows; box = 32 sites x 9 rows (one link tile of one direction)
+int make_plane_map(CUtensorMap* m, const void* base, const Geo& g) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    L2B_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    L2B_REQUIRE(fn != nullptr && qr == cudaDriverEntryPointSuccess, L2B_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * g.lat.V, (cuuint64_t)g.nb * 36};
+  const cuuint64_t strides[1] = {(cuuint64_t)g.lat.V * sizeof(C)};
+  const cuuint32_t box[2] = {64, 9};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  L2B_REQUIRE(rc == CUDA_SUCCESS, L2B_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)rc);
+  return L2B_OK;
+}
+
 int launch_force(const Geo& g, const C* U, C* P, bool kick, double coef, double* part, cudaStream_t st,
                  C* Uout = nullptr, double eps_drift = 0.0) {
   const ForceVariant& fv = kForceVariants[g.force_variant];
   dim3 grid(g.nblk_force, g.nb), block(fv.ts, 4);
+  if (kick && fv.tma[Uout ? 1 : 0] != nullptr && g.lat.V % 32 == 0) {
+    CUtensorMap mp, mu;
+    int rc = make_plane_map(&mp, P, g);
+    if (rc != L2B_OK) return rc;
+    rc = make_plane_map(&mu, U, g);
+    if (rc != L2B_OK) return rc;
+    ForceFnTma fn = fv.tma[Uout ? 1 : 0];
+    constexpr int smem = 2 * 4 * 9 * 32 * (int)sizeof(C);
+    fn<<<grid, block, smem, st>>>(mp, mu, U, P, g.lat, coef, part, Uout, eps_drift);
+    L2B_LAUNCHED("k_force_tma");
+    return L2B_OK;
+  }
   ForceFn fn = Uout ? fv.kick_drift : (kick ? fv.kick : fv.nokick);
   L2B_REQUIRE(fn != nullptr, L2B_ERR_UNSUPPORTED, "force variant %d has no fused kick+drift kernel", g.force_variant);
   if (fv.smem > 48 * 1024)

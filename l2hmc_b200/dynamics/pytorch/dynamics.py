@@ -410,8 +410,17 @@ class Dynamics(nn.Module):
             eps = 1. / nlf
         nleapfrog = nlf if nleapfrog is None else nleapfrog
         beta = _fbeta(state.beta)
-        if self._su3 and getattr(self.lattice, 'c1', 0.0) != 0.0 and not self.config.verbose:
-            # rectangle action: the fused trajectory kernel integrates the plain Wilson force only
+        stepwise = self._su3 and getattr(self.lattice, 'c1', 0.0) != 0.0
+        # rectangle action: the fused trajectory kernel integrates the plain Wilson force only.
+        # nleapfrog = 0: the reference's loop body never runs and the state comes back unchanged (dynamics.py:930-937).
+        stepwise = stepwise or nleapfrog <= 0
+        if not self._su3:
+            # U(1): the whole-trajectory kernel keeps x, v and sin(w) of one chain in shared memory (5 T X elements);
+            # lattices beyond 227 KB take the per-step kernels, as every size does in the reference
+            T_, X_ = self.config.latvolume
+            esize = 8 if state.x.dtype == torch.float64 else 4
+            stepwise = stepwise or 5 * T_ * X_ * esize > ops.U1_TRAJECTORY_SMEM_LIMIT
+        if stepwise and not self.config.verbose:
             state_ = State(x=state.x, v=state.v, beta=state.beta)
             for _ in range(nleapfrog):
                 state_ = self.leapfrog_hmc(state_, eps=eps)
@@ -450,12 +459,6 @@ class Dynamics(nn.Module):
         if isinstance(owner, LatticeSU3):
             return self._su3 and owner.c1 == 0.0
         return isinstance(owner, LatticeU1) and not self._su3
-
-    # --------------------------------------------------------------- L2HMC
-    def _check_inference_only(self) -> None:
-        """kept for API stability: both groups are differentiable now
-        (l2hmc_b200/autograd.py)"""
-        return None
 
     # ---------------------------------------------- planar inference sweep (SU(3))
     def _planar_ok(self) -> bool:
@@ -534,7 +537,6 @@ class Dynamics(nn.Module):
         return out, {'acc': acc, 'sumlogdet': sumlogdet}
 
     def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
-        self._check_inference_only()
         if self._planar_ok():
             return self._transition_kernel_fb_planar(state)
         nb = state.x.shape[0]
@@ -568,7 +570,6 @@ class Dynamics(nn.Module):
         return state_, (self._stack_history(history) if verbose else history)
 
     def transition_kernel(self, state: State, forward: bool) -> tuple[State, dict]:
-        self._check_inference_only()
         lf_fn = self._forward_lf if forward else self._backward_lf
         sinit = State(x=state.x, v=state.v, beta=state.beta)
         sumlogdet = self._zeros(state.x.shape[0])

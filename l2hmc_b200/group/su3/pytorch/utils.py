@@ -1,15 +1,13 @@
 """Free-function surface of the reference's `group/su3/pytorch/utils.py`, so that
 `from l2hmc.group.su3.pytorch.utils import projectSU, su3_to_vec, ...` keeps working after the import swap.
 
-The functions the integrator uses (projectSU / projectU / rsqrtPHM3 / rsqrtPHM3f / eigs3x3,
-su3_to_vec / vec_to_su3, randTAH3, norm2, eyeOf, checkSU / checkU, projectTAH) are implemented in
-`group.py` on top of the libl2b kernels and re-exported here; the small algebra helpers below are plain torch.
-Not mirrored: the reference's unused experiments (`cubic_zeros`, `su3_to_eigs`, `log3x3`, `acos_safe*`,
-`su3fabc`, `SU3Gradient`) -- nothing in the reference calls them.
+Only the functions of SURVEY section 8 a18 -- projectSU / projectU / rsqrtPHM3 / rsqrtPHM3f / eigs3x3,
+su3_to_vec / vec_to_su3, randTAH3, norm2, eyeOf, checkSU / checkU, projectTAH -- live here: implemented in `group.py`
+on top of the libl2b kernels and re-exported, plus `eigs3x3` as the free function the reference exposes.  The
+reference's other helpers in that file (`cmax`, `unit`, `charpoly3x3`, `expm`, `cubic_zeros`, `log3x3`, ...) are
+not on the hot path and are not mirrored.
 """
 from __future__ import annotations
-
-from typing import Optional, Sequence
 
 import torch
 
@@ -17,41 +15,6 @@ from .group import (checkSU, checkU, eyeOf, norm2, projectSU, projectTAH, projec
                     rsqrtPHM3f, su3_to_vec, vec_to_su3)
 
 Tensor = torch.Tensor
-eyeOf1 = eyeOf                      # utils.py:125-131: same identity, older spelling
-
-
-def cmax(x: Tensor, y: Tensor) -> Tensor:
-    """element-wise, the argument of larger magnitude (utils.py:50-52)"""
-    return torch.where(x.abs() > y.abs(), x, y)
-
-
-def unit(shape: Sequence[int], dtype: Optional[torch.dtype] = torch.complex128) -> Tensor:
-    """an identity broadcastable against a batch of `shape[-2:]` matrices (utils.py:55-62)"""
-    eye = torch.eye(int(shape[-1]), dtype=dtype)
-    return eye.reshape(*([1] * (len(shape) - 2)), *eye.shape)
-
-
-def eye_like(x: Tensor) -> Tensor:
-    """identity with x's (2-d) shape, dtype and device (utils.py:144-145)"""
-    return torch.eye(*x.shape, dtype=x.dtype, device=x.device)
-
-
-def charpoly3x3(a: Tensor) -> tuple[Tensor, Tensor, Tensor]:
-    """det(l - A) = l^3 + c3 l^2 + c2 l + c1 for a batch [n, 3, 3]; returns (c1, c2, c3) = (-det A,
-    sum of principal 2x2 minors, -tr A)   (utils.py:65-82)"""
-    tr = torch.diagonal(a, dim1=-2, dim2=-1).sum(-1)
-    tr2 = torch.diagonal(a @ a, dim1=-2, dim2=-1).sum(-1)
-    return -torch.linalg.det(a), 0.5 * (tr * tr - tr2), -tr
-
-
-def expm(m: Tensor, order: int = 12) -> Tensor:
-    """Taylor polynomial of exp(m) of degree `order` in Horner form (utils.py:148-154) -- a truncated series, not
-    `torch.matrix_exp`; the integrator itself uses SU3.exp (the Cayley-Hamilton kernel `l2b_su3_exp`)"""
-    eye = torch.eye(m.shape[-1], dtype=m.dtype, device=m.device)
-    x = eye + m / order
-    for i in range(order - 1, 0, -1):
-        x = eye + (m @ x) / i
-    return x
 
 
 def eigs3x3(tr: Tensor, p2: Tensor, det: Tensor) -> tuple[Tensor, Tensor, Tensor]:

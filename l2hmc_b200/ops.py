@@ -398,6 +398,11 @@ def u1_force(x: Tensor, beta: float, shape=None) -> Tensor:
     return f
 
 
+# shared memory one block may opt into on sm_100a: the whole-trajectory U(1) kernel needs 5 T X elements of it
+# (csrc/l2b_u1.cu hmc_smem_bytes) and returns L2B_ERR_UNSUPPORTED above; `Dynamics` takes the per-step path there
+U1_TRAJECTORY_SMEM_LIMIT = 227 * 1024
+
+
 def u1_hmc_trajectory(x: Tensor, v: Tensor, beta: float, eps: float, nlf: int, shape=None):
     x, nb, T, X = _u1_field(x, shape)
     v, _, _, _ = _u1_field(v, (T, X))

@@ -147,6 +147,30 @@ def test_trajectory_with_conversions_folded_in_is_bit_identical(ops, shape, nb, 
     assert torch.allclose(e0[:, 0], e1[:, 0], rtol=1e-13, atol=1e-12)
 
 
+@pytest.mark.parametrize('variant', [32, 33])
+@pytest.mark.parametrize('shape,nb', [([4, 4, 4, 4], 3), ([8, 8, 8, 8], 2), ([3, 5, 4, 7], 2)])
+def test_tma_staged_step_kernel_is_bit_identical(ops, shape, nb, variant):
+    """force variants 32 / 33: the block's own momenta and links arrive through `cp.async.bulk.tensor.2d` + mbarrier
+    (k_force_tma); same arithmetic as the default variant 22.  V % 32 != 0 ([3,5,4,7]) takes variant 22's kernels."""
+    from l2hmc_b200 import _lib
+    rng = np.random.default_rng(5 * nb + shape[0])
+    full = (nb, 4, *shape, 3, 3)
+    x, v = dev(osu3.random_su3(rng, full)), dev(osu3.random_momentum(rng, full))
+    res = {}
+    try:
+        for var in (22, variant):
+            _lib.set_option('su3_force_variant', var)
+            for fuse in (1, 0):      # with the conversions folded into the end launches, and with all N_LF + 1 on the variant
+                _lib.set_option('su3_fuse_conversions', fuse)
+                res[(var, fuse)] = ops.su3_hmc_trajectory(x, v, 5.7, 0.07, 4)
+    finally:
+        _lib.set_option('su3_force_variant', 22)
+        _lib.set_option('su3_fuse_conversions', 1)
+    for fuse in (1, 0):
+        for a, b in zip(res[(22, fuse)], res[(variant, fuse)]):
+            assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize('shape,nb', [([2, 2, 2, 2], 3), ([4, 4, 4, 4], 2), ([6, 4, 2, 8], 1), ([3, 5, 4, 7], 2)])
 def test_vs_oracle_on_fresh_inputs(ops, shape, nb):
     """ragged / odd / extent-2 lattices (extent 2: forward and backward neighbour coincide)"""

@@ -156,7 +156,7 @@ def test_su3_utils_module_surface():
     helpers agree with closed forms / numpy"""
     from l2hmc_b200.group.su3.pytorch import utils as u
     for name in ('projectSU', 'projectU', 'projectTAH', 'rsqrtPHM3', 'rsqrtPHM3f', 'eigs3x3', 'su3_to_vec', 'vec_to_su3',
-                 'randTAH3', 'norm2', 'eyeOf', 'eyeOf1', 'eye_like', 'checkSU', 'checkU', 'expm', 'unit', 'cmax', 'charpoly3x3'):
+                 'randTAH3', 'norm2', 'eyeOf', 'checkSU', 'checkU'):
         assert callable(getattr(u, name)), name
     rng = np.random.default_rng(9)
     a = rng.standard_normal((5, 3, 3)) + 1j * rng.standard_normal((5, 3, 3))
@@ -169,13 +169,4 @@ def test_su3_utils_module_surface():
     assert np.allclose(np.sort(e, -1), np.linalg.eigvalsh(h), rtol=1e-10)
     r = u.rsqrtPHM3(ht).numpy()                                     # X^{-1/2}: r h r = 1
     assert np.abs(r @ h @ r - np.eye(3)).max() < 1e-9
-    c1, c2, c3 = u.charpoly3x3(torch.from_numpy(a))
-    lam = np.linalg.eigvals(a)
-    assert np.allclose(c3.numpy(), -lam.sum(1)) and np.allclose(c1.numpy(), -lam.prod(1))
-    assert np.allclose(c2.numpy(), lam[:, 0] * lam[:, 1] + lam[:, 0] * lam[:, 2] + lam[:, 1] * lam[:, 2])
-    small = torch.from_numpy(0.1 * a)
-    assert (u.expm(small, order=12) - torch.linalg.matrix_exp(small)).abs().max() < 1e-13
-    assert tuple(u.unit((7, 4, 3, 3)).shape) == (1, 1, 3, 3) and tuple(u.eye_like(torch.zeros(3, 3)).shape) == (3, 3)
-    x, y = torch.tensor([1 + 1j, 0.1j]), torch.tensor([0.5 + 0j, 2.0 + 0j])
-    assert torch.equal(u.cmax(x, y), torch.tensor([1 + 1j, 2.0 + 0j]))
     assert torch.equal(u.eyeOf(ht).squeeze().real, torch.eye(3, dtype=u.eyeOf(ht).real.dtype))
