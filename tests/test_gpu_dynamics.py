@@ -235,3 +235,32 @@ def test_hmc_half_updates_and_apply_transition_both(default_dtype):
     ev = float(torch.sigmoid(dyn3.veps[0].log()))
     f3 = lat3.grad_action(x3, torch.tensor(5.5))
     assert float((dyn3._update_v_fwd_hmc(0, st3) - (v3 - 0.5 * ev * f3)).abs().max()) < 1e-13
+
+
+@pytest.mark.parametrize('tag,shape,tol', [('f64', [96, 80], 1e-11), ('f32', [128, 112], 2e-4)])
+def test_u1_hmc_beyond_one_block_of_shared_memory_and_zero_steps(default_dtype, tag, shape, tol):
+    """The whole-trajectory U(1) kernel keeps 5 T X elements of one chain in shared memory; lattices beyond 227 KB
+    (96x80 in f64, 128x112 in f32) take the per-step kernels instead of raising, and `nleapfrog=0` returns the
+    state unchanged with acc = 1 -- both as the reference behaves (dynamics.py:900-954)."""
+    from l2hmc_b200.configs import DynamicsConfig
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics, State
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from oracle import dynamics as od
+    tdt, ndt = (torch.float64, np.float64) if tag == 'f64' else (torch.float32, np.float32)
+    default_dtype(tdt)
+    nb, nlf, eps, beta = 3, 4, 0.05, 2.5
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-np.pi, np.pi, (nb, 2, *shape)).astype(ndt)
+    v = rng.standard_normal((nb, 2 * shape[0] * shape[1])).astype(ndt)
+    cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=nlf, eps=eps, eps_hmc=eps, verbose=False)
+    lat = LatticeU1(nb, shape)
+    dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+    st = State(dev(x), dev(v), torch.tensor(beta))
+    prop, met = dyn.transition_kernel_hmc(st, eps=eps, nleapfrog=nlf)
+    want, acc = od.transition_kernel_hmc(od.U1Ops, od.State(x.astype(np.float64), v.astype(np.float64), beta), eps, nlf)
+    assert maxdiff(host(prop.x).reshape(nb, -1), want.x.reshape(nb, -1)) < tol
+    assert maxdiff(host(prop.v).reshape(nb, -1), want.v.reshape(nb, -1)) < tol
+    assert maxdiff(host(met['acc']), acc) < (1e-9 if tag == 'f64' else 5e-2)
+    same, met0 = dyn.transition_kernel_hmc(st, eps=eps, nleapfrog=0)
+    assert torch.equal(same.x.reshape(nb, -1), st.x.reshape(nb, -1)) and torch.equal(same.v, st.v)
+    assert torch.equal(met0['acc'], torch.ones_like(met0['acc']))
