@@ -362,15 +362,21 @@ def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: i
         lat = LatticeSU3(nb, lattice) if su3 else LatticeU1(nb, lattice)
         dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
         x = lat.random()
-        acc_therm = None
+        acc_therm = plaq_therm = None
         if thermalise > 0:
             # hot-start links make the acos / exp arguments atypical; time from a configuration relaxed
-            # by N accepted-or-rejected HMC trajectories (the reference's `Trainer.warmup`, trainer.py:1699-1744)
+            # by N accept/reject HMC trajectories (the reference's `Trainer.warmup`, trainer.py:1699-1744).  The
+            # relaxation runs at a fifth of the workload's step size: at eps = 1 / N_LF a 16^4 lattice stops accepting
+            # after the first few trajectories and the chain would stay close to the hot start.
+            eps_t = eps / 5.0
+            accs = []
             with torch.no_grad():
                 for _ in range(thermalise):
-                    xo_, m_ = dyn.apply_transition_hmc((x, torch.tensor(beta)), eps=eps, nleapfrog=nlf)
+                    xo_, m_ = dyn.apply_transition_hmc((x, torch.tensor(beta)), eps=eps_t, nleapfrog=nlf)
                     x = xo_.reshape(x.shape)
-                acc_therm = float(m_['acc'].mean())
+                    accs.append(m_['acc_mask'].mean())
+                acc_therm = float(torch.stack(accs[-20:]).mean())
+                plaq_therm = float(lat.plaqs(x).mean())
             x = x.contiguous()
         v = lat.random_momentum()
         field_bytes = x.numel() * x.element_size()
@@ -407,7 +413,8 @@ def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: i
             'config': {'workload': workload, 'group': group, 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'eps': eps, 'beta': beta,
                        'start': ('hot (g.random)' if thermalise <= 0 else
-                                 f'thermalised ({thermalise} HMC trajectories from a hot start, last <acc> = {acc_therm:.3f})'),
+                                 f'thermalised ({thermalise} HMC trajectories at eps/5 from a hot start; accept rate over the last 20 = '
+                                 f'{acc_therm:.2f}, plaquette {plaq_therm:.4f})'),
                        'parallelism': f'chains sharded over {world} GPU(s), no data-path collective',
                        'l2_policy': f'inputs larger than L2 ({field_bytes / 2**20:.0f} MiB per field per GPU), no flush'
                        if field_bytes > 200 * 2**20 else 'working set fits L2; fields re-read every step (no flush)',

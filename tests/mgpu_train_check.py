@@ -61,6 +61,38 @@ def main():
     if rank == 0:
         print(f'world={world} reduced_elems={n} rel_err_vs_full_batch={err:.3e} identical_across_ranks={same}')
     assert same and err < 1e-9, (same, err)
+
+    # ---- the Trainer path itself: ranks built from DIFFERENT seeds must start from rank 0's weights and masks
+    # (broadcast at construction, the DDP wrap of trainer.py:246-255) and stay identical through train steps whose
+    # gradients travel through the flat bucket (bf16 nets under autocast: the deferred head GEMMs write into it and
+    # start their all-reduce early; float64 nets: everything goes through finish())
+    for autocast, bdt in ((torch.bfloat16, torch.bfloat16), (None, None)):
+        torch.set_default_dtype(torch.float32 if autocast is not None else torch.float64)
+        torch.manual_seed(100 + rank)
+        np.random.seed(100 + rank)
+        tr3, lat3 = _su3_trainer(nb=2, units=(16,), autocast=autocast)
+        tr3.grad_bucket_dtype = bdt
+        assert tr3._bucket is not None
+        if bdt is not None:
+            tr3._bucket = l2d.GradBucket(tr3._bucket.params, bdt)
+        torch.manual_seed(200 + rank)                 # different chains on every rank
+        x3 = lat3.random().to(torch.complex128)
+        before = torch.cat([p.detach().reshape(-1).double() for p in tr3.dynamics.parameters()])
+        for _ in range(2):
+            x3n, m3 = tr3.train_step((x3, beta))
+        after = torch.cat([p.detach().reshape(-1).double() for p in tr3.dynamics.parameters()]
+                          + [m.reshape(-1).double() for m in tr3.dynamics.masks])
+        allp = [torch.empty_like(after) for _ in range(world)]
+        dist.all_gather(allp, after)
+        same3 = all(torch.equal(allp[0], a) for a in allp)
+        moved = float((after[:before.numel()] - before).abs().max())
+        info = tr3.allreduce_info()
+        if rank == 0:
+            print(f'trainer path autocast={autocast}: identical_across_ranks={same3} max|dp|={moved:.3e} exchange={info}')
+        assert same3 and moved > 0 and info['calls'] >= 1 and torch.isfinite(m3['loss'])
+        if autocast is not None:
+            assert info['early_calls'] == 3, info       # the three head matrices went out from inside backward
+    torch.set_default_dtype(torch.float64)
     dist.barrier()
     dist.destroy_process_group()
 
