@@ -250,6 +250,36 @@ int l2b_su3_update_gauge_planar(const void* x_planar, const void* p_planar, doub
                                 const float* mask_planar, int mask_complement, void* x_out_planar, int nb,
                                 const int dims[4], int dtype, void* stream);
 
+/* both masked link updates of one leapfrog layer (dynamics.py:1195-1198 forward: mask m then 1 - m; :1217-1220
+ * backward: 1 - m then m -> first_complement = 1) in one pass: no momentum update separates them and they share the
+ * step size, so exp(eps p) is formed once and x, p are read once.  Same arithmetic per update as
+ * l2b_su3_update_gauge_planar applied twice. */
+int l2b_su3_update_gauge_planar_pair(const void* x_planar, const void* p_planar, double eps, const double* eps_dev,
+                                     const float* mask_planar, int first_complement, void* x_out_planar, int nb,
+                                     const int dims[4], int dtype, void* stream);
+
+/* ------------------------------------------------------------------------ */
+/* vnet INPUT layer on the tensor cores (tcgen05)                             */
+/* ------------------------------------------------------------------------ */
+/* InputLayer of the SU(3) vnet (network/pytorch/network.py:349-451; its two Linears :415-422) with its inputs
+ * as Dynamics._call_vnet builds them (dynamics.py:1142-1160):
+ *   z[b, h] = act( W_x su3_to_vec(projectSU(x))[b] + b_x + W_v su3_to_vec(projectSU(F))[b] + b_v ),  h < hidden <= 256
+ * as a split-K bf16 GEMM (K = 2 * 8 * nlinks) with fp32 accumulators in TMEM, one CTA per SM.  Both operands are
+ * streamed by TMA bulk copies from K-major core-matrix images: the weights from l2b_su3_input_pack, the activations
+ * from l2b_su3_project_vec_planar_lm, which writes vec8 "link-major" [link][chain < nb_pad][8] bf16 (one link = one
+ * K core; the caller zero-fills the buffer once so that the pad rows nb..nb_pad-1 are zero).
+ * activation: 0 identity, 1 tanh, 2 relu, 3 swish, 4 leaky_relu(0.01), 5 elu (network.py:40-46).
+ * z_bf16: [nb, hidden].  nlinks % 8 == 0, nb_pad % 16 == 0, nb <= nb_pad <= 256, else L2B_ERR_UNSUPPORTED. */
+size_t l2b_su3_input_packed_bytes(int nlinks, int hidden);
+size_t l2b_su3_input_ws_bytes(int nb_pad, int hidden);
+int l2b_su3_input_pack(const void* w_x, const void* w_v, int w_dtype, void* packed, int nlinks, int hidden,
+                       void* stream);
+int l2b_su3_project_vec_planar_lm(const void* x_planar, void* vec8_lm, int nb, int nb_pad, const int dims[4], int dtype,
+                                  void* stream);
+int l2b_su3_input_layer(const void* act_x, const void* act_f, const void* packed, const float* bias_x,
+                        const float* bias_v, int activation, void* z_bf16, int nb, int nb_pad, int nlinks, int hidden,
+                        void* ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */
 /* ------------------------------------------------------------------------ */
@@ -273,6 +303,17 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
                           const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
                           const void* v, const void* force, double eps, const double* eps_dev, int sign, void* v_out,
                           double* logdet, float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream);
+/* Two consecutive momentum updates between which the links do not move (dynamics.py:1187-1228: the second half of
+ * leapfrog layer i and the first half of layer i+1; the two around the turn-around of the forward / backward sweep,
+ * dynamics.py:1002, with v -> -v in between: negate_between) see the same (s, t, q) and the same force when the
+ * layers share one vnet (use_separate_networks = false, conf/dynamics/su3.yaml).  One pass computes
+ *   v'' = upd( [-] upd(v; eps1, sign1); eps2, sign2 ),   logdet = logdet_1 + logdet_2
+ * -- v, F and the head weights are read once instead of twice. */
+int l2b_su3_heads_vupdate_pair(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                               const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                               const void* v, const void* force, double eps1, const double* eps1_dev, int sign1,
+                               double eps2, const double* eps2_dev, int sign2, int negate_between, void* v_out,
+                               double* logdet, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* U(1), x[nb, 2, T, X] real angles                                          */

@@ -105,6 +105,12 @@ _SIGS = {
     'l2b_su3_project_vec_planar': [_P, _P, c_int, c_int, _DIMS, c_int, _P],
     'l2b_su3_update_gauge_planar': [_P, _P, c_double, _P, _P, c_int, _P, c_int, _DIMS, c_int, _P],
     'l2b_su3_project_vec': [_P, _P, c_int, c_size_t, c_int, _P],
+    'l2b_su3_project_vec_planar_lm': [_P, _P, c_int, c_int, _DIMS, c_int, _P],
+    'l2b_su3_update_gauge_planar_pair': [_P, _P, c_double, _P, _P, c_int, _P, c_int, _DIMS, c_int, _P],
+    'l2b_su3_heads_vupdate_pair': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, _P, c_int, c_double, _P, c_int,
+                                   c_int, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P],
+    'l2b_su3_input_pack': [_P, _P, c_int, _P, c_int, c_int, _P],
+    'l2b_su3_input_layer': [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
     'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
@@ -143,6 +149,8 @@ _RES = {
     'l2b_u1_ws_bytes': ([c_int, c_int, c_int, c_int], c_size_t),
     'l2b_vnet_heads_packed_bytes': ([c_int, c_int], c_size_t),
     'l2b_vnet_heads_ws_bytes': ([c_int, c_int], c_size_t),
+    'l2b_su3_input_packed_bytes': ([c_int, c_int], c_size_t),
+    'l2b_su3_input_ws_bytes': ([c_int, c_int], c_size_t),
     'l2b_u1_heads_ws_bytes': ([c_int, c_int], c_size_t),
     'l2b_u1_input_ws_bytes': ([c_int, c_int], c_size_t),
 }

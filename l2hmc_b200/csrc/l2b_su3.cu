@@ -912,6 +912,66 @@ __global__ void __launch_bounds__(NTL) k_project_vec_planar(const C* __restrict_
   Vec8IO<V>::store(vec8 + (plane * Vs + site) * 8, v);    // [b][mu][site][8]: the order the vnet input expects
 }
 
+// Both masked link updates of one leapfrog layer in one pass (dynamics.py:1195-1198 / 1217-1220: `_update_x_fwd(m)`
+// then `_update_x_fwd(1 - m)`, no momentum update in between, same step size): E = exp(eps p) is formed once,
+//   x1 = m (.) x + E ((1 - m) (.) x),     x2 = (1 - m) (.) x1 + E (m (.) x1)
+// (mask_complement = 1 swaps the roles: the backward layer applies 1 - m first).  Same arithmetic per update as
+// k_update_gauge_planar; one read of x and p and one write instead of two of each, one exponential instead of two.
+__global__ void __launch_bounds__(NTL) k_update_gauge_planar_pair(const C* __restrict__ x, const C* __restrict__ p,
+                                                                  double eps_in, const double* __restrict__ eps_dev,
+                                                                  const float* __restrict__ mask, int mask_complement,
+                                                                  C* __restrict__ out, int Vs) {
+  const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
+  const int site = blockIdx.x * NTL + threadIdx.x;
+  if (site >= Vs) return;
+  const size_t plane = blockIdx.y;
+  const int mu = (int)(plane & 3);
+  Mat3<T> X, Pm, E, R, Xb;
+  soa_load(Pm, p + plane * 9 * (size_t)Vs, Vs, site);
+  soa_load(X, x + plane * 9 * (size_t)Vs, Vs, site);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { Pm.re[e] *= eps; Pm.im[e] *= eps; }
+  mat_exp(E, Pm);
+  float mk[9];
+  const float* mp = mask + (size_t)mu * 9 * Vs + site;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    const float m = __ldg(mp + (size_t)e * Vs);
+    mk[e] = mask_complement ? 1.0f - m : m;
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const float m = pass == 0 ? mk[e] : 1.0f - mk[e];
+      const T md = (T)m, mb = (T)(1.0f - m);
+      R.re[e] = md * X.re[e]; R.im[e] = md * X.im[e];
+      Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+    }
+    mat_mul<false, false, true>(R, E, Xb);
+    X = R;
+  }
+  soa_store(out + plane * 9 * (size_t)Vs, Vs, site, X);
+}
+
+// same, written as the K-major operand image of the tensor-core input layer (k_su3_input_gemm, l2b_vnet.cu):
+// one link is one K core of 8 reals, so the image is link-major, vec8[link][chain < nbp][8] bf16 (rows >= nb stay
+// as the caller zeroed them).  A warp's 32 sites store 32 separate 16-byte pieces (stride nbp * 16 B); the 144-byte
+// reads stay coalesced, which is the side that matters.
+__global__ void __launch_bounds__(NTL) k_project_vec_planar_lm(const C* __restrict__ x, __nv_bfloat16* __restrict__ vec8,
+                                                               int Vs, int nbp) {
+  const int site = blockIdx.x * NTL + threadIdx.x;
+  if (site >= Vs) return;
+  const size_t plane = blockIdx.y;                        // b * 4 + mu
+  const int b = (int)(plane >> 2), mu = (int)(plane & 3);
+  Mat3<T> m, r;
+  soa_load(m, x + plane * 9 * (size_t)Vs, Vs, site);
+  project_su(r, m);
+  T v[8];
+  su3_to_vec(v, r);
+  Vec8IO<__nv_bfloat16>::store(vec8 + (((size_t)mu * Vs + site) * nbp + b) * 8, v);
+}
+
 // x' = m*x + exp(eps p) ((1-m)*x), planar x, p, x'; mask planar [4][9][V] float (nullptr: x' = exp(eps p) x)
 __global__ void __launch_bounds__(NTL) k_update_gauge_planar(const C* __restrict__ x, const C* __restrict__ p,
                                                              double eps_in, const double* __restrict__ eps_dev,
@@ -2038,6 +2098,34 @@ int l2b_su3_project_vec_planar(const void* x_planar, void* vec8, int vec_dtype, 
   else if (vec_dtype == L2B_BF16) k_project_vec_planar<__nv_bfloat16><<<grid, NTL, 0, st>>>((const C*)x_planar, (__nv_bfloat16*)vec8, g.lat.V);
   else L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "vec_dtype must be L2B_F64, L2B_F32 or L2B_BF16");
   L2B_LAUNCHED("k_project_vec_planar");
+  return L2B_OK;
+}
+
+int l2b_su3_update_gauge_planar_pair(const void* x_planar, const void* p_planar, double eps, const double* eps_dev,
+                                     const float* mask_planar, int first_complement, void* x_out_planar, int nb,
+                                     const int dims[4], int dtype, void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_planar && p_planar && x_out_planar && mask_planar, L2B_ERR_INVALID, "null pointer");
+  const dim3 grid((g.lat.V + NTL - 1) / NTL, nb * 4);
+  k_update_gauge_planar_pair<<<grid, NTL, 0, (cudaStream_t)stream>>>((const C*)x_planar, (const C*)p_planar, eps,
+                                                                     eps_dev, mask_planar, first_complement,
+                                                                     (C*)x_out_planar, g.lat.V);
+  L2B_LAUNCHED("k_update_gauge_planar_pair");
+  return L2B_OK;
+}
+
+int l2b_su3_project_vec_planar_lm(const void* x_planar, void* vec8_lm, int nb, int nb_pad, const int dims[4], int dtype,
+                                  void* stream) {
+  Geo g;
+  L2B_TRY(make_geo(g, nb, dims, dtype));
+  L2B_REQUIRE(x_planar && vec8_lm, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb_pad >= nb && nb_pad % 8 == 0, L2B_ERR_INVALID, "nb_pad must be a multiple of 8 >= nb");
+  L2B_REQUIRE(((uintptr_t)vec8_lm & 15) == 0, L2B_ERR_INVALID, "vec8_lm must be 16-byte aligned");
+  const dim3 grid((g.lat.V + NTL - 1) / NTL, nb * 4);
+  k_project_vec_planar_lm<<<grid, NTL, 0, (cudaStream_t)stream>>>((const C*)x_planar, (__nv_bfloat16*)vec8_lm, g.lat.V,
+                                                                  nb_pad);
+  L2B_LAUNCHED("k_project_vec_planar_lm");
   return L2B_OK;
 }
 

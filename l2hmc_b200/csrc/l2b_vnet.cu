@@ -186,7 +186,26 @@ struct HeadsArgs {
   double eps;                   // multiplies *eps_dev when that is given
   const double* eps_dev;        // device-resident step size (CUDA graphs) or null
   int sign, nb, xdim, H, KP, ntiles;
+  // pair mode (sign2 != 0): a SECOND momentum update with the same (s, t, q, F) applied to the result of the
+  // first, v'' = upd(+-upd(v; eps, sign); eps2, sign2) -- two consecutive v-updates of an L2HMC sweep between which
+  // the links do not move see the same network outputs (dynamics.py:1187-1228: second half of leapfrog layer i,
+  // first half of layer i+1; `negate` = the v -> -v of the turn-around, dynamics.py:1002).  One pass over
+  // v, F and the weights instead of two; logdet is the sum of both.
+  double eps2;
+  const double* eps2_dev;
+  int sign2, negate;
 };
+
+// one momentum update of one element (dynamics.py:1266-1297); returns the log-Jacobian term sign * eps * s / 2
+__device__ __forceinline__ float vupd(double2& v, const double2 f, float s, float t, float q, float epsf, double he,
+                                      bool fwd) {
+  const float logjac = (fwd ? 0.5f : -0.5f) * epsf * s;
+  const double es = (double)exp_fast(logjac), eq = (double)exp_fast(epsf * q);
+  const double fr = fma(f.x, eq, (double)t), fi = f.y * eq;
+  if (fwd) { v.x = fma(es, v.x, -he * fr); v.y = fma(es, v.y, -he * fi); }
+  else { v.x = es * fma(he, fr, v.x); v.y = es * fma(he, fi, v.y); }
+  return logjac;
+}
 
 // FULL: interior tile (all 64 chains and 128 columns valid, no s/t/q dump): no per-element predicates
 template <bool FWD, bool FULL>
@@ -199,8 +218,11 @@ __device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t 
               bq = col_ok ? __ldg(a.bias[2] + j) : 0.f;
   const float as = col_ok ? __ldg(a.scale_s + j) : 0.f, aq = col_ok ? __ldg(a.scale_q + j) : 0.f, at = a.scale_t;
   const double epsd = a.eps_dev ? a.eps * a.eps_dev[0] : a.eps;
-  const float epsf = (float)epsd, hs = (FWD ? 0.5f : -0.5f) * epsf;
+  const float epsf = (float)epsd;
   const double he = 0.5 * epsd;
+  const double epsd2 = a.eps2_dev ? a.eps2 * a.eps2_dev[0] : a.eps2;
+  const float epsf2 = (float)epsd2;
+  const double he2 = 0.5 * epsd2;
   const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
   float* ljw = sm.lj[warp];
   const size_t xd = (size_t)a.xdim;
@@ -230,13 +252,13 @@ __device__ __forceinline__ void epilogue(const HeadsArgs& a, Smem& sm, uint32_t 
       const float s = as * tanhf(__uint_as_float(rs[c]) + bs);   // summed into logdet over xdim elements: accurate tanh
       const float t = at * (__uint_as_float(rt[c]) + bt);
       const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
-      const float logjac = hs * s;                      // sign * eps * s / 2
+      double2 o = vv[c];
+      float logjac = vupd(o, ff[c], s, t, q, epsf, he, FWD);      // sign * eps * s / 2
+      if (a.sign2 != 0) {
+        if (a.negate) { o.x = -o.x; o.y = -o.y; }
+        logjac += vupd(o, ff[c], s, t, q, epsf2, he2, a.sign2 > 0);
+      }
       ljw[c * 33 + lane] = ok ? logjac : 0.f;
-      const double es = (double)exp_fast(logjac), eq = (double)exp_fast(epsf * q);
-      const double fr = fma(ff[c].x, eq, (double)t), fi = ff[c].y * eq;
-      double2 o;
-      if (FWD) { o.x = fma(es, vv[c].x, -he * fr); o.y = fma(es, vv[c].y, -he * fi); }
-      else { o.x = es * fma(he, fr, vv[c].x); o.y = es * fma(he, fi, vv[c].y); }
       if (ok) {
         po[c * xd] = o;
         if (!FULL && a.stq != nullptr) {
@@ -279,8 +301,11 @@ __device__ __forceinline__ void epilogue_full(const HeadsArgs& a, Smem& sm, uint
   const float bs = __ldg(a.bias[0] + j), bt = __ldg(a.bias[1] + j), bq = __ldg(a.bias[2] + j);
   const float as = __ldg(a.scale_s + j), aq = __ldg(a.scale_q + j), at = a.scale_t;
   const double epsd = a.eps_dev ? a.eps * a.eps_dev[0] : a.eps;
-  const float epsf = (float)epsd, hs = (FWD ? 0.5f : -0.5f) * epsf;
+  const float epsf = (float)epsd;
   const double he = 0.5 * epsd;
+  const double epsd2 = a.eps2_dev ? a.eps2 * a.eps2_dev[0] : a.eps2;
+  const float epsf2 = (float)epsd2;
+  const double he2 = 0.5 * epsd2;
   const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + half * 32;
   float* ljw = sm.lj[warp];
   mbar_wait<64>(smem_u32(&sm.accum), 0);
@@ -305,13 +330,13 @@ __device__ __forceinline__ void epilogue_full(const HeadsArgs& a, Smem& sm, uint
       const float s = as * tanhf(__uint_as_float(rs[c]) + bs);   // summed into logdet over xdim elements: accurate tanh
       const float t = at * (__uint_as_float(rt[c]) + bt);
       const float q = aq * tanh_fast(__uint_as_float(rq[c]) + bq);
-      const float logjac = hs * s;
+      double2 o = vv[cur][c];
+      float logjac = vupd(o, ff[cur][c], s, t, q, epsf, he, FWD);
+      if (a.sign2 != 0) {
+        if (a.negate) { o.x = -o.x; o.y = -o.y; }
+        logjac += vupd(o, ff[cur][c], s, t, q, epsf2, he2, a.sign2 > 0);
+      }
       ljw[c * 33 + lane] = logjac;
-      const double es = (double)exp_fast(logjac), eq = (double)exp_fast(epsf * q);
-      const double fr = fma(ff[cur][c].x, eq, (double)t), fi = ff[cur][c].y * eq;
-      double2 o;
-      if (FWD) { o.x = fma(es, vv[cur][c].x, -he * fr); o.y = fma(es, vv[cur][c].y, -he * fi); }
-      else { o.x = es * fma(he, fr, vv[cur][c].x); o.y = es * fma(he, fi, vv[cur][c].y); }
       po[(ck * C4 + c) * xd] = o;
     }
     __syncwarp();
@@ -512,12 +537,269 @@ __global__ void __launch_bounds__(256) k_sum_rows(const double* __restrict__ par
   if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
+// ---------------------------------------------------------------------------
+// SU(3) vnet INPUT layer on the tensor cores (reference network/pytorch/network.py:349-451 `InputLayer`, its two
+// Linears at :415-422, called from dynamics.py:1142-1160):
+//     z[b, h] = act( sum_k ax[b, k] Wx[h, k] + bx[h]  +  sum_k af[b, k] Wv[h, k] + bv[h] ),   k < 8 * 4V
+// ax = su3_to_vec(projectSU(x)), af = su3_to_vec(projectSU(F)) -- 8 reals per link.  A GEMM with tiny M (H <= 256) and
+// N (chains <= 256) and an enormous K (8^4: 131 072, twice): pure operand streaming, 268 MB for 34 GF at nb = H = 256.
+//
+// k_su3_input_gemm: split-K over one CTA per SM.  The concatenated K axis [x part | F part] is cut into chunks of 64
+// (= 8 links); a CTA owns a contiguous run of chunks and accumulates D[h, b] (UMMA M = 128 rows of h per accumulator,
+// N = the padded chain count) in TMEM over all of them.  Both operands are stored in HBM as the canonical no-swizzle
+// K-major core-matrix image of their chunks, so a pipeline stage is two contiguous 1-D bulk copies (UBLKCP):
+//   * weights: packed once per weight version by k_pack_input, [part][chunk][kcore 0..7][row h < HP][8 bf16];
+//   * activations: written in exactly this form by the producer itself, k_project_vec_planar_lm -- one link IS one
+//     K core (8 reals), so the image is simply "link-major": [link][chain < NBP][8 bf16].  vec8 never exists in the
+//     [chain][link][8] layout a library GEMM would need.
+// One thread issues the copies and the tcgen05.mma's (cta_group::1, kind::f16, M128 x N(NBP) x K16); 4 warps drain
+// the accumulators with tcgen05.ld into fp32 partials [cta][h][b].
+// k_su3_input_reduce: fixed-order sum of the partials over the CTAs (deterministic), both biases, the activation,
+// cast -> z[b][h] (bf16, the B operand of k_heads_vupdate).
+// ---------------------------------------------------------------------------
+constexpr int IL_KC = 64;             // K per chunk = 8 links
+constexpr int IL_NST = 3;             // pipeline stages
+constexpr int IL_NTH = 128;           // 4 warps: TMEM lane quarters 0..3
+
+struct InputArgs {
+  const unsigned char* wpk;           // k_pack_input image
+  const unsigned char* act[2];        // link-major activation images of the x part and the F part
+  float* part;                        // [ncta][HP][NBP] fp32
+  int nch;                            // chunks per part (= nlinks / 8)
+  int HP;                             // padded rows of the weight image: 128 or 256
+  int NBP;                            // padded chains: multiple of 16, <= 256
+  uint32_t tmem_cols;                 // power of two >= (HP / 128) * NBP, >= 32
+};
+
+__global__ void __launch_bounds__(IL_NTH, 1) k_su3_input_gemm(const InputArgs a) {
+  extern __shared__ __align__(128) unsigned char il_smem[];
+  __shared__ __align__(8) unsigned long long full[IL_NST], empty[IL_NST], accum;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t w_bytes = (uint32_t)a.HP * 128u, act_bytes = (uint32_t)a.NBP * 128u, stage_bytes = w_bytes + act_bytes;
+  const long long total = 2ll * a.nch;
+  const long long c0 = (long long)blockIdx.x * total / gridDim.x, c1 = (long long)(blockIdx.x + 1) * total / gridDim.x;
+  const int n = (int)(c1 - c0);
+  const int n_mt = a.HP / 128;
+
+  auto issue = [&](int s) {            // stage s of this CTA's run -> ring slot s % IL_NST
+    const long long c = c0 + s;
+    const int part = c >= a.nch ? 1 : 0;
+    const long long ci = c - (long long)part * a.nch;
+    const uint32_t slot = (uint32_t)(s % IL_NST);
+    const uint32_t dst = smem_u32(il_smem) + slot * stage_bytes;
+    mbar_expect_tx(smem_u32(&full[slot]), stage_bytes);
+    bulk_g2s(dst, a.wpk + ((size_t)part * a.nch + (size_t)ci) * w_bytes, w_bytes, smem_u32(&full[slot]));
+    bulk_g2s(dst + w_bytes, a.act[part] + (size_t)ci * act_bytes, act_bytes, smem_u32(&full[slot]));
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < IL_NST; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    mbar_init(smem_u32(&accum), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < IL_NST && s < n; ++s) issue(s);      // the first ring fill overlaps the TMEM allocation
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    // instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = NBP
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.NBP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t w_lbo = (uint32_t)a.HP * 16u, b_lbo = (uint32_t)a.NBP * 16u, sbo = 128u;
+    for (int s = 0; s < n; ++s) {
+      const uint32_t slot = (uint32_t)(s % IL_NST), ph = (uint32_t)(s / IL_NST) & 1u;
+      mbar_wait(smem_u32(&full[slot]), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t w_base = smem_u32(il_smem) + slot * stage_bytes, b_base = w_base + w_bytes;
+      for (int mt = 0; mt < n_mt; ++mt) {
+#pragma unroll
+        for (int kk = 0; kk < IL_KC / 16; ++kk) {
+          const uint64_t ad = umma_desc(w_base + (2 * kk) * w_lbo + mt * (128 * 16), w_lbo, sbo);
+          const uint64_t bd = umma_desc(b_base + (2 * kk) * b_lbo, b_lbo, sbo);
+          umma_f16(tmem + mt * a.NBP, ad, bd, idesc, (s | kk) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(smem_u32(&empty[slot]));
+      if (s + IL_NST < n) {
+        mbar_wait(smem_u32(&empty[slot]), ph);
+        issue(s + IL_NST);
+      }
+    }
+    umma_commit(smem_u32(&accum));
+  }
+  __syncwarp();
+  // ---- drain: TMEM lane = h (row of the weight tile), column = chain ----------------------------------------
+  mbar_wait<128>(smem_u32(&accum), 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int mt = 0; mt < n_mt; ++mt) {
+    float* row = a.part + ((size_t)blockIdx.x * a.HP + mt * 128 + warp * 32 + lane) * a.NBP;
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + mt * a.NBP;
+    for (int c = 0; c < a.NBP; c += 8) {
+      uint32_t r[8];
+      tmem_ld8(trow + c, r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      *reinterpret_cast<uint4*>(row + c) = make_uint4(r[0], r[1], r[2], r[3]);
+      *reinterpret_cast<uint4*>(row + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// activations of the reference (network.py:40-46): 0 identity, 1 tanh, 2 relu, 3 swish (SiLU), 4 leaky_relu(0.01), 5 elu
+__device__ __forceinline__ float il_act(float x, int act) {
+  switch (act) {
+    case 1: return tanhf(x);
+    case 2: return fmaxf(x, 0.f);
+    case 3: return x / (1.f + __expf(-x));
+    case 4: return x > 0.f ? x : 0.01f * x;
+    case 5: return x > 0.f ? x : expm1f(x);
+    default: return x;
+  }
+}
+
+// z[b][h] = act( sum_cta part[cta][h][b] + bx[h] + bv[h] ); block = 32 chains x 8 rows of h, transposed through
+// shared memory so that both the partial reads (b fastest) and the z writes (h fastest) are contiguous
+__global__ void __launch_bounds__(256) k_su3_input_reduce(const float* __restrict__ part, int ncta, int HP, int NBP,
+                                                          const float* __restrict__ bx, const float* __restrict__ bv,
+                                                          int act, int H, int nb, __nv_bfloat16* __restrict__ z) {
+  __shared__ float tile[32][33];
+  const int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int hh = ty; hh < 32; hh += 8) {
+    const int h = h0 + hh, b = b0 + tx;
+    float s = 0.f;
+    if (h < H && b < NBP) {
+      const float* p = part + (size_t)h * NBP + b;
+      for (int c = 0; c < ncta; ++c) s += p[(size_t)c * HP * NBP];
+      s += bx[h] + bv[h];
+    }
+    tile[hh][tx] = il_act(s, act);
+  }
+  __syncthreads();
+  for (int bb = ty; bb < 32; bb += 8) {
+    const int b = b0 + bb, h = h0 + tx;
+    if (b < nb && h < H) z[(size_t)b * H + h] = __float2bfloat16(tile[tx][bb]);
+  }
+}
+
+// W_x, W_v [H, K] (nn.Linear layout; f64 / f32 / bf16), K = 8 * nlinks -> [part][chunk][kcore][row < HP][8] bf16
+template <typename W>
+__global__ void __launch_bounds__(256) k_pack_input(const W* __restrict__ wx, const W* __restrict__ wv,
+                                                    uint4* __restrict__ packed, int H, int HP, int nch, size_t n16) {
+  const size_t id = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (id >= n16) return;
+  const int r = (int)(id % HP);
+  size_t rest = id / HP;
+  const int kcore = (int)(rest % 8);
+  rest /= 8;
+  const size_t chunk = rest % nch;
+  const int part = (int)(rest / nch);
+  const W* w = part == 0 ? wx : wv;
+  const size_t K = (size_t)nch * IL_KC;
+  __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    h[e] = __float2bfloat16(r < H ? w_load(w + (size_t)r * K + chunk * IL_KC + kcore * 8 + e) : 0.0f);
+  packed[id] = *reinterpret_cast<const uint4*>(h);
+}
+
 }  // namespace
 }  // namespace l2b
 
 using namespace l2b;
 
 extern "C" {
+
+size_t l2b_su3_input_packed_bytes(int nlinks, int hidden) {
+  if (nlinks <= 0 || nlinks % 8 != 0 || hidden <= 0 || hidden > 256) return 0;
+  const size_t HP = hidden <= 128 ? 128 : 256;
+  return (size_t)2 * (nlinks / 8) * 8 * HP * 16;
+}
+
+size_t l2b_su3_input_ws_bytes(int nb_pad, int hidden) {
+  if (nb_pad <= 0 || hidden <= 0 || hidden > 256) return 0;
+  int dev = 0, nsm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return 0;
+  const size_t HP = hidden <= 128 ? 128 : 256;
+  return align_up((size_t)nsm * HP * nb_pad * sizeof(float), 256);
+}
+
+int l2b_su3_input_pack(const void* w_x, const void* w_v, int w_dtype, void* packed, int nlinks, int hidden,
+                       void* stream) {
+  L2B_REQUIRE(w_x && w_v && packed, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nlinks > 0 && nlinks % 8 == 0, L2B_ERR_UNSUPPORTED, "nlinks must be a positive multiple of 8 (got %d)", nlinks);
+  L2B_REQUIRE(hidden > 0 && hidden <= 256, L2B_ERR_UNSUPPORTED, "hidden must be in [1, 256] (got %d)", hidden);
+  L2B_REQUIRE(((uintptr_t)packed & 15) == 0, L2B_ERR_INVALID, "packed image must be 16-byte aligned");
+  const int HP = hidden <= 128 ? 128 : 256, nch = nlinks / 8;
+  const size_t n16 = l2b_su3_input_packed_bytes(nlinks, hidden) / 16;
+  const unsigned nblk = (unsigned)((n16 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w_dtype == L2B_F32)
+    k_pack_input<float><<<nblk, 256, 0, st>>>((const float*)w_x, (const float*)w_v, (uint4*)packed, hidden, HP, nch, n16);
+  else if (w_dtype == L2B_F64)
+    k_pack_input<double><<<nblk, 256, 0, st>>>((const double*)w_x, (const double*)w_v, (uint4*)packed, hidden, HP, nch, n16);
+  else if (w_dtype == L2B_BF16)
+    k_pack_input<__nv_bfloat16><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)w_x, (const __nv_bfloat16*)w_v, (uint4*)packed, hidden, HP, nch, n16);
+  else
+    L2B_REQUIRE(false, L2B_ERR_UNSUPPORTED, "w_dtype must be L2B_F32, L2B_F64 or L2B_BF16");
+  L2B_LAUNCHED("k_pack_input");
+  return L2B_OK;
+}
+
+int l2b_su3_input_layer(const void* act_x, const void* act_f, const void* packed, const float* bias_x,
+                        const float* bias_v, int activation, void* z_bf16, int nb, int nb_pad, int nlinks, int hidden,
+                        void* ws, size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(act_x && act_f && packed && bias_x && bias_v && z_bf16, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb > 0 && nb_pad >= nb && nb_pad % 16 == 0 && nb_pad <= 256, L2B_ERR_UNSUPPORTED,
+              "nb_pad must be a multiple of 16 in [nb, 256] (nb=%d nb_pad=%d)", nb, nb_pad);
+  L2B_REQUIRE(nlinks > 0 && nlinks % 8 == 0, L2B_ERR_UNSUPPORTED, "nlinks must be a positive multiple of 8 (got %d)", nlinks);
+  L2B_REQUIRE(hidden > 0 && hidden <= 256, L2B_ERR_UNSUPPORTED, "hidden must be in [1, 256] (got %d)", hidden);
+  L2B_REQUIRE(activation >= 0 && activation <= 5, L2B_ERR_INVALID, "activation code must be in [0, 5]");
+  L2B_REQUIRE((((uintptr_t)act_x | (uintptr_t)act_f | (uintptr_t)packed | (uintptr_t)ws) & 15) == 0, L2B_ERR_INVALID,
+              "act_x, act_f, packed, ws must be 16-byte aligned");
+  L2B_REQUIRE(ws != nullptr && ws_bytes >= l2b_su3_input_ws_bytes(nb_pad, hidden), L2B_ERR_WORKSPACE,
+              "workspace too small for the split-K partials");
+  int dev = 0, nsm = 0;
+  L2B_CUDA(cudaGetDevice(&dev));
+  L2B_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  InputArgs a;
+  a.wpk = (const unsigned char*)packed;
+  a.act[0] = (const unsigned char*)act_x;
+  a.act[1] = (const unsigned char*)act_f;
+  a.part = (float*)ws;
+  a.nch = nlinks / 8;
+  a.HP = hidden <= 128 ? 128 : 256;
+  a.NBP = nb_pad;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)((a.HP / 128) * a.NBP)) cols <<= 1;
+  a.tmem_cols = cols;
+  const long long total = 2ll * a.nch;
+  const int ncta = (int)(total < nsm ? total : nsm);
+  const size_t smem = (size_t)IL_NST * ((size_t)a.HP + a.NBP) * 128;
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_CUDA(cudaFuncSetAttribute((const void*)k_su3_input_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_su3_input_gemm<<<ncta, IL_NTH, smem, st>>>(a);
+  L2B_LAUNCHED("k_su3_input_gemm");
+  const dim3 rgrid((nb_pad + 31) / 32, (hidden + 31) / 32);
+  k_su3_input_reduce<<<rgrid, 256, 0, st>>>(a.part, ncta, a.HP, a.NBP, bias_x, bias_v, activation, hidden, nb,
+                                             (__nv_bfloat16*)z_bf16);
+  L2B_LAUNCHED("k_su3_input_reduce");
+  return L2B_OK;
+}
 
 size_t l2b_vnet_heads_packed_bytes(int xdim, int hidden) {
   if (xdim <= 0 || hidden <= 0) return 0;
@@ -553,15 +835,18 @@ int l2b_vnet_pack_heads(const void* w_s, const void* w_t, const void* w_q, int w
   return L2B_OK;
 }
 
-int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
-                          const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
-                          const void* v, const void* force, double eps, const double* eps_dev, int sign, void* v_out,
-                          double* logdet,
-                          float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream) {
+static int heads_vupdate_impl(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                              const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                              const void* v, const void* force, double eps, const double* eps_dev, int sign,
+                              double eps2, const double* eps2_dev, int sign2, int negate, void* v_out, double* logdet,
+                              float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes,
+                              void* stream) {
   L2B_REQUIRE(z && packed && bias_s && bias_t && bias_q && scale_s && scale_q && v && force && v_out,
               L2B_ERR_INVALID, "null pointer");
   L2B_REQUIRE(nb > 0 && xdim > 0, L2B_ERR_INVALID, "nb and xdim must be positive");
   L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
+  L2B_REQUIRE(sign2 == 0 || sign2 == 1 || sign2 == -1, L2B_ERR_INVALID, "sign2 must be 0, +1 or -1");
+  L2B_REQUIRE(sign2 == 0 || stq_or_null == nullptr, L2B_ERR_UNSUPPORTED, "the paired update has no (s, t, q) dump");
   L2B_REQUIRE(hidden > 0 && hidden % 8 == 0 && hidden <= KMAX, L2B_ERR_UNSUPPORTED,
               "fused heads kernel needs hidden %% 8 == 0 and hidden <= %d (got %d)", KMAX, hidden);
   L2B_REQUIRE((((uintptr_t)z | (uintptr_t)packed | (uintptr_t)v | (uintptr_t)force | (uintptr_t)v_out) & 15) == 0,
@@ -574,6 +859,7 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
   a.v = (const double2*)v; a.f = (const double2*)force; a.out = (double2*)v_out;
   a.stq = stq_or_null;
   a.eps = eps; a.eps_dev = eps_dev; a.sign = sign; a.nb = nb; a.xdim = xdim; a.H = hidden;
+  a.eps2 = eps2; a.eps2_dev = eps2_dev; a.sign2 = sign2; a.negate = negate;
   a.KP = (hidden + KC - 1) / KC * KC;
   a.ntiles = (xdim + BM - 1) / BM;
   a.part = nullptr;
@@ -595,6 +881,26 @@ int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s
     L2B_LAUNCHED("k_sum_rows");
   }
   return L2B_OK;
+}
+
+int l2b_su3_heads_vupdate(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                          const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                          const void* v, const void* force, double eps, const double* eps_dev, int sign, void* v_out,
+                          double* logdet,
+                          float* stq_or_null, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream) {
+  return heads_vupdate_impl(z, packed, bias_s, bias_t, bias_q, scale_s, scale_q, scale_t, v, force, eps, eps_dev, sign,
+                            0.0, nullptr, 0, 0, v_out, logdet, stq_or_null, nb, xdim, hidden, ws, ws_bytes, stream);
+}
+
+int l2b_su3_heads_vupdate_pair(const void* z, const void* packed, const float* bias_s, const float* bias_t,
+                               const float* bias_q, const float* scale_s, const float* scale_q, float scale_t,
+                               const void* v, const void* force, double eps1, const double* eps1_dev, int sign1,
+                               double eps2, const double* eps2_dev, int sign2, int negate_between, void* v_out,
+                               double* logdet, int nb, int xdim, int hidden, void* ws, size_t ws_bytes, void* stream) {
+  L2B_REQUIRE(sign2 == 1 || sign2 == -1, L2B_ERR_INVALID, "sign2 must be +1 or -1");
+  return heads_vupdate_impl(z, packed, bias_s, bias_t, bias_q, scale_s, scale_q, scale_t, v, force, eps1, eps1_dev,
+                            sign1, eps2, eps2_dev, sign2, negate_between ? 1 : 0, v_out, logdet, nullptr, nb, xdim,
+                            hidden, ws, ws_bytes, stream);
 }
 
 int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq, const float* scale_s,

@@ -482,9 +482,33 @@ class Dynamics(nn.Module):
             self._planar_cache = c
         return c
 
+    def _eps_tensors(self) -> tuple[Tensor, Tensor]:
+        """(x step sizes, v step sizes) = sigmoid(log(.)) of all 2 nlf parameters (dynamics.py:82-83,1270,1394) as ONE
+        float64 device vector, so that a sweep costs five tiny element-wise launches for its step sizes instead of
+        five per update; entries are handed to the kernels as device pointers (`eps_dev`)"""
+        params = list(self.xeps) + list(self.veps)
+        t = sigmoid(torch.stack([q.detach().reshape(()) for q in params]).log()).to(torch.float64)
+        n = len(self.xeps)
+        return t[:n], t[n:]
+
+    def _fused_input(self, vnet, nb: int) -> bool:
+        """vnet input layer on the tensor cores (ops.su3_input_layer): dense input, <= 256 units and chains, one of
+        the reference's activations; `tensor_core_input`: 'auto' (default) / 'never'"""
+        if getattr(self, 'tensor_core_input', 'auto') == 'never' or not vnet.dense_input():
+            return False
+        V = int(np.prod(self.config.latvolume))
+        return (ops.input_layer_supported(4 * V, vnet.units[0], nb) and vnet.input_activation_name() is not None
+                and not isinstance(vnet.input_layer.xlayer, nn.modules.lazy.LazyModuleMixin))
+
     def _transition_kernel_fb_planar(self, state: State) -> tuple[State, dict]:
-        """transition_kernel_fb (dynamics.py:956-1029) with the state planar between the two layout
-        conversions at its ends; same kernels' arithmetic per link as the boundary-layout path"""
+        """transition_kernel_fb (dynamics.py:956-1029) with the state planar between the two layout conversions at
+        its ends; same arithmetic per link and per update as the boundary-layout path.  The schedule exploits what
+        the reference recomputes: between two link updates the links do not move, so the force, the vnet inputs and
+        -- when the layers share one vnet -- the network outputs of the two momentum updates in between are the
+        same: they are evaluated once and both updates run as ONE pass of the heads kernel
+        (`l2b_su3_heads_vupdate_pair`, including the v -> -v of the turn-around); the two masked link updates of a
+        layer share exp(eps v) and run as one pass too (`l2b_su3_update_gauge_planar_pair`).
+        `pair_updates = 'never'` keeps one kernel per update (tests compare the two)."""
         nb = state.x.shape[0]
         perm, pmasks = self._planar_consts()
         beta = _fbeta(state.beta)
@@ -492,44 +516,88 @@ class Dynamics(nn.Module):
         vs = ops.su3_aos_to_soa(self.unflatten(state.v))
         sumlogdet = torch.zeros(nb, dtype=torch.float64, device=xs.device)
         nlf = self.config.nleapfrog
-
         reuse = self._reuse_force()
-        cache: dict = {}            # force and vnet inputs of the current links; emptied by every x-update
+        pair = getattr(self, 'pair_updates', 'auto') != 'never' and reuse
+        xeps, veps = self._eps_tensors()
+        dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else None
+        lm_bufs: list = [None, None]      # link-major activation images, reused across the sweep
 
-        def v_update(step, vs_, sign):
-            vnet = self._get_vnet(step)
-            dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
-            if not reuse:
-                cache.clear()
-            if 'f' not in cache:
-                cache['f'] = ops.su3_force_planar(xs, beta)
-            f = cache['f']
-            if dt not in cache:
-                cache[dt] = (ops.su3_project_vec_planar(xs, dt), ops.su3_project_vec_planar(f, dt))
-            z = vnet.hidden(cache[dt])
-            return ops.su3_heads_vupdate(z, vnet.heads_pack(perm), vs_.reshape(nb, -1), f.reshape(nb, -1),
-                                         self._eps_t(self.veps[step]).to(torch.float64), sign)
+        def net_inputs(xs_):
+            """force and vnet input producers at the current links"""
+            f = ops.su3_force_planar(xs_, beta)
+            memo: dict = {'f': f}
 
-        def x_update(step, xs_, vs_, complement, sign):
-            cache.clear()
-            return ops.su3_update_gauge_planar(xs_, vs_.reshape(xs_.shape), self._eps_t(self.xeps[step]).to(torch.float64),
-                                               pmasks[step], complement, eps_mult=float(sign))
+            def z_of(vnet):
+                if id(vnet) in memo:
+                    return memo[id(vnet)]
+                ndt = dt or next(vnet.parameters()).dtype
+                if ndt == torch.bfloat16 and self._fused_input(vnet, nb):
+                    if 'lm' not in memo:
+                        lm_bufs[0] = ops.su3_project_vec_planar_lm(xs_, lm_bufs[0])
+                        lm_bufs[1] = ops.su3_project_vec_planar_lm(f, lm_bufs[1])
+                        memo['lm'] = True
+                    z = vnet.hidden_tail(ops.su3_input_layer(lm_bufs[0], lm_bufs[1], vnet.input_pack(), nb))
+                else:
+                    if ndt not in memo:
+                        memo[ndt] = (ops.su3_project_vec_planar(xs_, ndt), ops.su3_project_vec_planar(f, ndt))
+                    z = vnet.hidden(memo[ndt])
+                memo[id(vnet)] = z
+                return z
+            return f, z_of
+
+        # the sweep as a flat list: ('v', step, sign) | ('x', step, first_complement, sign) | ('neg',)
+        seq: list = []
         for step in range(nlf):                     # _forward_lf
-            vs, ld = v_update(step, vs, +1)
-            sumlogdet = sumlogdet + ld
-            xs = x_update(step, xs, vs, False, +1)
-            xs = x_update(step, xs, vs, True, +1)
-            vs, ld = v_update(step, vs, +1)
-            sumlogdet = sumlogdet + ld
-        vs = -vs
+            seq += [('v', step, +1), ('x', step, False, +1), ('v', step, +1)]
+        seq.append(('neg',))
         for step in range(nlf):                     # _backward_lf
             r = nlf - step - 1
-            vs, ld = v_update(r, vs, -1)
-            sumlogdet = sumlogdet + ld
-            xs = x_update(r, xs, vs, True, -1)
-            xs = x_update(r, xs, vs, False, -1)
-            vs, ld = v_update(r, vs, -1)
-            sumlogdet = sumlogdet + ld
+            seq += [('v', r, -1), ('x', r, True, -1), ('v', r, -1)]
+        k = 0
+        while k < len(seq):
+            op = seq[k]
+            if op[0] == 'x':
+                _, step, first_c, sign = op
+                if pair:
+                    xs = ops.su3_update_gauge_planar_pair(xs, vs.reshape(xs.shape), xeps[step], pmasks[step], first_c,
+                                                          eps_mult=float(sign))
+                else:
+                    for comp in (first_c, not first_c):
+                        xs = ops.su3_update_gauge_planar(xs, vs.reshape(xs.shape), xeps[step], pmasks[step], comp,
+                                                         eps_mult=float(sign))
+                k += 1
+                continue
+            # a run of momentum updates (with at most the turn-around negation inside) at fixed links
+            run = []
+            while k < len(seq) and seq[k][0] != 'x':
+                run.append(seq[k])
+                k += 1
+            f, z_of = net_inputs(xs)
+            i = 0
+            while i < len(run):
+                if run[i][0] == 'neg':
+                    vs = -vs
+                    i += 1
+                    continue
+                _, s1, g1 = run[i]
+                vnet1 = self._get_vnet(s1)
+                nxt = i + 1
+                neg = nxt < len(run) and run[nxt][0] == 'neg'
+                if neg:
+                    nxt += 1
+                second = run[nxt] if nxt < len(run) and run[nxt][0] == 'v' else None
+                if pair and second is not None and self._get_vnet(second[1]) is vnet1:
+                    vs, ld = ops.su3_heads_vupdate_pair(z_of(vnet1), vnet1.heads_pack(perm), vs.reshape(nb, -1),
+                                                        f.reshape(nb, -1), veps[s1], g1, veps[second[1]], second[2],
+                                                        negate_between=neg)
+                    i = nxt + 1
+                else:
+                    vs, ld = ops.su3_heads_vupdate(z_of(vnet1), vnet1.heads_pack(perm), vs.reshape(nb, -1),
+                                                   f.reshape(nb, -1), veps[s1], g1)
+                    i += 1
+                sumlogdet = sumlogdet + ld
+                if not reuse and i < len(run):
+                    f, z_of = net_inputs(xs)          # the reference's schedule: recompute for every update
         xo = ops.su3_soa_to_aos(xs)
         vo = ops.su3_soa_to_aos(vs.reshape(xs.shape))
         out = State(x=xo, v=vo, beta=state.beta)

@@ -278,6 +278,47 @@ class LeapfrogLayer(nn.Module):
             z = self.batch_norm(z)
         return z
 
+    def hidden_tail(self, z: Tensor) -> Tensor:
+        """`hidden` from the output of the input layer on (network.py:538-545): the remaining hidden Linears,
+        dropout, batch norm"""
+        for layer in self.hidden_layers:
+            z = self.activation_fn(layer(z))
+        if self.net_config.dropout_prob > 0:
+            z = self.dropout(z)
+        if self.net_config.use_batch_norm:
+            z = self.batch_norm(z)
+        return z
+
+    def input_activation_name(self) -> Optional[str]:
+        """name of the input layer's activation as the fused kernel knows it (None: not one of them)"""
+        a = self.activation_fn
+        if isinstance(a, nn.Tanh):
+            return 'tanh'
+        if isinstance(a, nn.ReLU):
+            return 'relu'
+        if isinstance(a, nn.SiLU):
+            return 'swish'
+        if isinstance(a, nn.LeakyReLU) and abs(a.negative_slope - 0.01) < 1e-12:
+            return 'leaky_relu'
+        if isinstance(a, nn.ELU) and abs(a.alpha - 1.0) < 1e-12:
+            return 'elu'
+        return None
+
+    def input_pack(self):
+        """bf16 K-major image of the two input Linears for the tensor-core input layer (ops.su3_input_layer);
+        rebuilt only when one of the four parameters changed (same keys as `heads_pack`)"""
+        from ... import ops
+        il = self.input_layer
+        ps = (il.xlayer.weight, il.xlayer.bias, il.vlayer.weight, il.vlayer.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps) + (weights_generation(),)
+        cached = getattr(self, '_input_pack', None)
+        if cached is None or cached[0] != key:
+            with torch.no_grad():
+                pack = ops.su3_input_pack(ps[0], ps[2], ps[1], ps[3], self.input_activation_name())
+            cached = (key, pack)
+            self._input_pack = cached
+        return cached[1]
+
     def dense_input(self) -> bool:
         """no conv stack in front of the input Linears"""
         return isinstance(self.input_layer.conv_stack, nn.Identity)

@@ -337,6 +337,23 @@ def su3_project_vec_planar(x_planar: Tensor, dtype: torch.dtype = torch.float64)
     return v
 
 
+def su3_update_gauge_planar_pair(x_planar: Tensor, p_planar: Tensor, eps, mask_planar: Tensor,
+                                 first_complement: bool = False, eps_mult: float = 1.0) -> Tensor:
+    """both masked link updates of one leapfrog layer in one pass (mask, then its complement; swapped when
+    `first_complement`): include/l2b.h, l2b_su3_update_gauge_planar_pair"""
+    x, nb, dims = _su3_field(x_planar)
+    p, _, _ = _su3_field(p_planar, dims)
+    _need_cuda(mask_planar)
+    mask_planar = mask_planar.to(torch.float32).contiguous()
+    if mask_planar.numel() != x[0].numel():
+        raise L2BError(f'mask has {mask_planar.numel()} entries, expected {x[0].numel()}')
+    out = torch.empty_like(x)
+    ev, ep, _keep = _eps_args(eps, torch.float64, eps_mult)
+    call('l2b_su3_update_gauge_planar_pair', _ptr(x), _ptr(p), ev, ep, _ptr(mask_planar), int(first_complement),
+         _ptr(out), nb, dims4(dims), L2B_F64, _stream())
+    return out
+
+
 def su3_update_gauge_planar(x_planar: Tensor, p_planar: Tensor, eps=1.0, mask_planar: Optional[Tensor] = None,
                             mask_complement: bool = False, eps_mult: float = 1.0) -> Tensor:
     x, nb, dims = _su3_field(x_planar)
@@ -670,6 +687,76 @@ def su3_to_vec_bwd(gvec: Tensor) -> Tensor:
 
 
 # ---------------------------------------------------------------------------
+# vnet input layer on the tensor cores (split-K tcgen05 GEMM fed by link-major vec8 images)
+# ---------------------------------------------------------------------------
+INPUT_ACTIVATIONS = {'identity': 0, 'tanh': 1, 'relu': 2, 'swish': 3, 'leaky_relu': 4, 'elu': 5}
+
+
+class InputPack:
+    """bf16 K-major image of (W_x, W_v) of the vnet InputLayer + both biases (include/l2b.h, l2b_su3_input_pack)"""
+    __slots__ = ('packed', 'bias_x', 'bias_v', 'nlinks', 'hidden', 'activation')
+
+    def __init__(self, packed, bias_x, bias_v, nlinks, hidden, activation):
+        self.packed, self.bias_x, self.bias_v = packed, bias_x, bias_v
+        self.nlinks, self.hidden, self.activation = int(nlinks), int(hidden), int(activation)
+
+
+def input_layer_supported(nlinks: int, hidden: int, nb: int) -> bool:
+    return nlinks % 8 == 0 and 0 < hidden <= 256 and 0 < nb <= 256
+
+
+def input_nb_pad(nb: int) -> int:
+    return (int(nb) + 15) // 16 * 16
+
+
+def su3_input_pack(w_x: Tensor, w_v: Tensor, b_x: Tensor, b_v: Tensor, activation: str) -> InputPack:
+    """w_x, w_v: [hidden, 8 * nlinks] as nn.Linear stores them (x part, force part)"""
+    _need_cuda(w_x, w_v)
+    hidden, K = int(w_x.shape[0]), int(w_x.shape[1])
+    if w_v.shape != w_x.shape or w_v.dtype != w_x.dtype or K % 64 != 0:
+        raise L2BError('input weights must share shape and dtype, with in_features a multiple of 64')
+    if activation not in INPUT_ACTIVATIONS:
+        raise L2BError(f'activation {activation!r} not supported by the fused input layer')
+    nlinks = K // 8
+    nbytes = int(_lib._lib.l2b_su3_input_packed_bytes(nlinks, hidden))
+    if nbytes == 0:
+        raise L2BError(f'fused input layer does not support nlinks={nlinks}, hidden={hidden}')
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=w_x.device)
+    call('l2b_su3_input_pack', _ptr(w_x.detach().contiguous()), _ptr(w_v.detach().contiguous()), _net_dt(w_x.dtype),
+         _ptr(packed), nlinks, hidden, _stream())
+    f32 = lambda a: a.detach().to(torch.float32).reshape(-1).contiguous()  # noqa: E731
+    return InputPack(packed, f32(b_x), f32(b_v), nlinks, hidden, INPUT_ACTIVATIONS[activation])
+
+
+def su3_project_vec_planar_lm(x_planar: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """su3_to_vec(projectSU(x)) of a planar field as the link-major bf16 operand image of `su3_input_layer`:
+    [4 V links, nb_pad, 8].  `out`: a buffer from a previous call (its pad rows are already zero)."""
+    x, nb, dims = _su3_field(x_planar)
+    nbp = input_nb_pad(nb)
+    V = int(dims[0] * dims[1] * dims[2] * dims[3])
+    if out is None:
+        out = (torch.zeros if nbp != nb else torch.empty)((4 * V, nbp, 8), dtype=torch.bfloat16, device=x.device)
+    call('l2b_su3_project_vec_planar_lm', _ptr(x), _ptr(out), nb, nbp, dims4(dims), L2B_F64, _stream())
+    return out
+
+
+def su3_input_layer(act_x: Tensor, act_f: Tensor, pack: InputPack, nb: int) -> Tensor:
+    """z [nb, hidden] bf16 = act(W_x vec_x + b_x + W_v vec_f + b_v) from two link-major images"""
+    _need_cuda(act_x, act_f)
+    nbp = int(act_x.shape[1])
+    if act_x.shape != act_f.shape or act_x.dtype != torch.bfloat16 or act_f.dtype != torch.bfloat16:
+        raise L2BError('act_x / act_f must be bf16 images of the same shape')
+    if int(act_x.shape[0]) != pack.nlinks or nbp < nb:
+        raise L2BError(f'activation image {tuple(act_x.shape)} does not match nlinks={pack.nlinks}, nb={nb}')
+    z = torch.empty((nb, pack.hidden), dtype=torch.bfloat16, device=act_x.device)
+    nws = int(_lib._lib.l2b_su3_input_ws_bytes(nbp, pack.hidden))
+    ws = _workspace(nws, act_x.device)
+    call('l2b_su3_input_layer', _ptr(act_x), _ptr(act_f), _ptr(pack.packed), _ptr(pack.bias_x), _ptr(pack.bias_v),
+         pack.activation, _ptr(z), int(nb), nbp, pack.nlinks, pack.hidden, _ptr(ws), nws, _stream())
+    return z
+
+
+# ---------------------------------------------------------------------------
 # vnet output heads on the tensor cores, fused with the momentum update
 # ---------------------------------------------------------------------------
 class HeadsPack:
@@ -732,6 +819,35 @@ def su3_heads_vupdate(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps,
          _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), ev, ep,
          int(sign), _ptr(out), _ptr(logdet), _ptr(stq), nb, pack.xdim, pack.hidden, _ptr(ws), nws, _stream())
     return (out, logdet, stq) if want_stq else (out, logdet)
+
+
+def su3_heads_vupdate_pair(z: Tensor, pack: HeadsPack, v: Tensor, force: Tensor, eps1, sign1: int, eps2, sign2: int,
+                           negate_between: bool = False):
+    """(v'', logdet_1 + logdet_2): two consecutive momentum updates that share (s, t, q) and the force -- no link
+    update in between, one vnet for all layers -- in one pass (include/l2b.h, l2b_su3_heads_vupdate_pair)"""
+    _need_cuda(z, v, force)
+    if z.dtype != torch.bfloat16:
+        z = z.to(torch.bfloat16)
+    z = z.contiguous()
+    nb = int(z.shape[0])
+    if int(z.shape[1]) != pack.hidden:
+        raise L2BError(f'z has {z.shape[1]} features, the packed heads expect {pack.hidden}')
+    if v.dtype != torch.complex128 or force.dtype != torch.complex128:
+        raise L2BError('v and force must be complex128')
+    v, force = v.contiguous(), force.contiguous()
+    if v.numel() != nb * pack.xdim or force.numel() != nb * pack.xdim:
+        raise L2BError(f'v / force must have {nb * pack.xdim} complex entries')
+    out = torch.empty_like(v)
+    logdet = torch.empty(nb, dtype=torch.float64, device=v.device)
+    nws = int(_lib._lib.l2b_vnet_heads_ws_bytes(nb, pack.xdim))
+    ws = _workspace(nws, v.device)
+    e1, p1, _k1 = _eps_args(eps1, torch.float64)
+    e2, p2, _k2 = _eps_args(eps2, torch.float64)
+    call('l2b_su3_heads_vupdate_pair', _ptr(z), _ptr(pack.packed), _ptr(pack.bias[0]), _ptr(pack.bias[1]),
+         _ptr(pack.bias[2]), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t, _ptr(v), _ptr(force), e1, p1,
+         int(sign1), e2, p2, int(sign2), int(bool(negate_between)), _ptr(out), _ptr(logdet), nb, pack.xdim, pack.hidden,
+         _ptr(ws), nws, _stream())
+    return out, logdet
 
 
 # ---------------------------------------------------------------------------

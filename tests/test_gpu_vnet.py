@@ -59,6 +59,44 @@ def test_heads_vupdate_matches_float64_reference(nb, xdim, hidden, sign):
     assert torch.equal(out3, out2) and torch.equal(logdet3, logdet2), 'run-to-run bit-reproducible'
 
 
+@pytest.mark.parametrize('nb,xdim,hidden', [(64, 1152, 256), (70, 4320, 128), (5, 256, 64)])
+@pytest.mark.parametrize('sign1,sign2,negate', [(+1, +1, False), (+1, -1, True), (-1, -1, False)])
+def test_paired_heads_update_equals_two_single_updates(nb, xdim, hidden, sign1, sign2, negate):
+    """l2b_su3_heads_vupdate_pair: two consecutive momentum updates on the same (s, t, q, F) in one pass -- the
+    pairs of an L2HMC sweep (dynamics.py:1187-1228) incl. the v -> -v of the turn-around (dynamics.py:1002)"""
+    from l2hmc_b200 import ops
+    w, b, cs, cq, z, v, f = _case(nb, xdim, hidden, seed=3 * nb + hidden)
+    pack = ops.vnet_pack_heads(w[0], w[1], w[2], b[0], b[1], b[2], cs, cq, 0.7, 1.3, 0.9)
+    e1, e2 = 0.11, torch.tensor(0.07, dtype=torch.float64, device=DEV)      # by value and device-resident
+    v1, ld1 = ops.su3_heads_vupdate(z, pack, v, f, e1, sign1)
+    if negate:
+        v1 = -v1
+    v2, ld2 = ops.su3_heads_vupdate(z, pack, v1, f, e2, sign2)
+    vp, ldp = ops.su3_heads_vupdate_pair(z, pack, v, f, e1, sign1, e2, sign2, negate_between=negate)
+    assert torch.equal(vp, v2), 'same arithmetic per update'
+    assert float((ldp - (ld1 + ld2)).abs().max()) <= 2e-6 * max(1.0, float((ld1 + ld2).abs().max()))
+
+
+def test_paired_link_update_equals_two_masked_updates():
+    """l2b_su3_update_gauge_planar_pair == l2b_su3_update_gauge_planar(mask) then (1 - mask), both orders"""
+    from l2hmc_b200 import ops
+    torch.manual_seed(12)
+    nb, shape = 3, [4, 2, 4, 6]
+    dev_ = torch.device(DEV)
+    x = ops.su3_project(torch.complex(torch.randn(nb, 4, *shape, 3, 3, dtype=torch.float64, device=dev_),
+                                      torch.randn(nb, 4, *shape, 3, 3, dtype=torch.float64, device=dev_)))
+    p = ops.su3_rand_momentum(nb, shape, 9, 0, dev_) * torch.rand(nb, 4, *shape, 3, 3, device=dev_, dtype=torch.float64)
+    xs, ps = ops.su3_aos_to_soa(x), ops.su3_aos_to_soa(p)
+    mask = (torch.rand(xs[0].numel(), device=dev_) > 0.5).float()
+    eps = torch.tensor(0.13, dtype=torch.float64, device=dev_)
+    for first_c in (False, True):
+        for sign in (+1.0, -1.0):
+            a = ops.su3_update_gauge_planar(xs, ps, eps, mask, first_c, eps_mult=sign)
+            a = ops.su3_update_gauge_planar(a, ps, eps, mask, not first_c, eps_mult=sign)
+            b = ops.su3_update_gauge_planar_pair(xs, ps, eps, mask, first_c, eps_mult=sign)
+            assert torch.equal(a, b)
+
+
 def test_heads_unsupported_hidden_raises():
     from l2hmc_b200 import ops
     w, b, cs, cq, z, v, f = _case(4, 128, 260, seed=1)
@@ -189,17 +227,71 @@ def test_planar_inference_sweep_matches_boundary_layout_sweep():
         v = lat.random_momentum()
         beta = torch.tensor(5.9)
         res = {}
-        for mode in ('never', 'auto'):
-            dyn.planar_sweep = mode
+        # (planar sweep, paired updates, tensor-core input layer)
+        settings = {'boundary': ('never', 'never', 'never'), 'planar': ('auto', 'never', 'never'),
+                    'paired': ('auto', 'auto', 'never'), 'fused': ('auto', 'auto', 'auto')}
+        for name, (planar, pair, tci) in settings.items():
+            dyn.planar_sweep, dyn.pair_updates, dyn.tensor_core_input = planar, pair, tci
             n0 = _lib.launch_count()
             with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
                 st, met = dyn.transition_kernel_fb(State(x, v, beta))
-            res[mode] = (st.x.reshape(x.shape), st.v.reshape(x.shape), met['sumlogdet'], met['acc'],
+            res[name] = (st.x.reshape(x.shape), st.v.reshape(x.shape), met['sumlogdet'], met['acc'],
                          _lib.launch_count() - n0)
-        a, b = res['never'], res['auto']
+        dyn.planar_sweep = dyn.pair_updates = dyn.tensor_core_input = 'auto'
+        a, b, c, d = res['boundary'], res['planar'], res['paired'], res['fused']
         assert b[4] < a[4], 'fewer launches: no conversions around the force'
+        assert c[4] < b[4], 'fewer launches: two updates per pass'
         assert float((a[0] - b[0]).abs().max()) < 1e-13 and float((a[1] - b[1]).abs().max()) < 1e-12
         assert float((a[2] - b[2]).abs().max()) < 1e-5 * max(1.0, float(a[2].abs().max()))
         assert float((a[3] - b[3]).abs().max()) < 1e-5
+        # paired passes: the same arithmetic per update on the same network outputs -> the same links and momenta
+        assert float((b[0] - c[0]).abs().max()) < 1e-13 and float((b[1] - c[1]).abs().max()) < 1e-12
+        assert float((b[2] - c[2]).abs().max()) < 1e-5 * max(1.0, float(b[2].abs().max()))
+        # tensor-core input layer: another bf16 GEMM (fp32 accumulation in another order, z rounded to bf16 either
+        # way) -> agreement at bf16 level only; the kernel itself is pinned by test_input_layer_matches_float64_reference
+        assert float((c[0] - d[0]).abs().max()) < 2e-2 and float((c[1] - d[1]).abs().max()) < 5e-2 * float(c[1].abs().max())
     finally:
         torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('nb,shape,hidden,act', [(256, (8, 8, 8, 8), 256, 'tanh'), (32, (8, 8, 8, 8), 256, 'tanh'),
+                                                  (3, (4, 2, 4, 6), 32, 'relu'), (20, (4, 4, 4, 4), 136, 'swish'),
+                                                  (17, (2, 2, 2, 4), 8, 'leaky_relu')])
+def test_input_layer_matches_float64_reference(nb, shape, hidden, act):
+    """tcgen05 split-K input layer (l2b_su3_input_layer fed by l2b_su3_project_vec_planar_lm) against a float64
+    evaluation of  act(W_x vec_x + b_x + W_v vec_f + b_v)  on the SAME bf16-rounded operands: what is checked is the
+    kernel (operand images, UMMA descriptors, split-K partials, reduction, epilogue), not bf16 rounding.
+    Reference semantics: network/pytorch/network.py:349-451 with the inputs of dynamics.py:1142-1160."""
+    from l2hmc_b200 import ops
+    torch.manual_seed(hidden + nb)
+    V = int(np.prod(shape))
+    K = 8 * 4 * V
+    dev_ = torch.device(DEV)
+    x = ops.su3_project(torch.complex(torch.randn(nb, 4, *shape, 3, 3, dtype=torch.float64, device=dev_),
+                                      torch.randn(nb, 4, *shape, 3, 3, dtype=torch.float64, device=dev_)))
+    f = ops.su3_rand_momentum(nb, list(shape), 5, 0, dev_)
+    xs, fs = ops.su3_aos_to_soa(x), ops.su3_aos_to_soa(f)
+    wx = (torch.randn(hidden, K, device=dev_) / K ** 0.5)
+    wv = (torch.randn(hidden, K, device=dev_) / K ** 0.5)
+    bx, bv = torch.randn(hidden, device=dev_), torch.randn(hidden, device=dev_)
+    pack = ops.su3_input_pack(wx, wv, bx, bv, act)
+    ax, af = ops.su3_project_vec_planar_lm(xs), ops.su3_project_vec_planar_lm(fs)
+    nbp = ops.input_nb_pad(nb)
+    assert ax.shape == (4 * V, nbp, 8) and ax.dtype == torch.bfloat16
+    # the link-major image holds exactly the vec8 the unfused path produces, transposed
+    vx = ops.su3_project_vec_planar(xs, torch.bfloat16).reshape(nb, 4 * V, 8)
+    vf = ops.su3_project_vec_planar(fs, torch.bfloat16).reshape(nb, 4 * V, 8)
+    assert torch.equal(ax[:, :nb].permute(1, 0, 2), vx) and torch.equal(af[:, :nb].permute(1, 0, 2), vf)
+    assert float(ax[:, nb:].abs().sum()) == 0.0
+    z = ops.su3_input_layer(ax, af, pack, nb)
+    assert z.shape == (nb, hidden) and z.dtype == torch.bfloat16
+    r = lambda t: t.to(torch.bfloat16).double()   # noqa: E731
+    pre = r(vx).reshape(nb, K) @ r(wx).t() + r(vf).reshape(nb, K) @ r(wv).t() + bx.double() + bv.double()
+    fn = {'tanh': torch.tanh, 'relu': torch.relu, 'swish': torch.nn.functional.silu,
+          'leaky_relu': torch.nn.functional.leaky_relu}[act]
+    want = fn(pre)
+    # fp32 accumulation over K = 2 * 8 * 4 V terms, then one bf16 rounding of z (2^-9 relative)
+    err = (z.double() - want).abs()
+    assert float(err.max()) < 6e-3 * max(1.0, float(want.abs().max())), float(err.max())
+    z2 = ops.su3_input_layer(ax, af, pack, nb)
+    assert torch.equal(z, z2), 'fixed-order split-K reduction: bit-reproducible'

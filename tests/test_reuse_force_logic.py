@@ -113,6 +113,23 @@ def test_planar_sweep_schedule_with_fake_ops(monkeypatch):
             m = (1 - mask) if complement else mask
             return xs + m * eps * eps_mult * vs
 
+        @staticmethod
+        def su3_heads_vupdate_pair(z, pack, v, f, eps1, sign1, eps2, sign2, negate_between=False):
+            count('vupdate_pair')
+            v1 = v + sign1 * eps1 * (f + z.to(v.dtype))
+            if negate_between:
+                v1 = -v1
+            v2 = v1 + sign2 * eps2 * (f + z.to(v.dtype))
+            return v2, (z.double() * sign1 * eps1).sum(1) + (z.double() * sign2 * eps2).sum(1)
+
+        @staticmethod
+        def su3_update_gauge_planar_pair(xs, vs, eps, mask, first_complement, eps_mult=1.0):
+            count('xupdate_pair')
+            for comp in (first_complement, not first_complement):
+                m = (1 - mask) if comp else mask
+                xs = xs + m * eps * eps_mult * vs
+            return xs
+
     class FakeVnet:
         def parameters(self):
             return iter([torch.zeros(1, dtype=torch.float64)])
@@ -125,24 +142,36 @@ def test_planar_sweep_schedule_with_fake_ops(monkeypatch):
 
     monkeypatch.setattr(dmod, 'ops', FakeOps)
     masks = [(torch.arange(n) % 2 == k % 2).double() for k in range(nlf)]
+    shared = FakeVnet()            # one vnet for all layers (use_separate_networks = false, conf/dynamics/su3.yaml)
+    veps = torch.linspace(0.04, 0.06, nlf, dtype=torch.float64)
+    xeps = torch.linspace(0.06, 0.08, nlf, dtype=torch.float64)
     fake = types.SimpleNamespace(
         config=types.SimpleNamespace(nleapfrog=nlf), _fcache=None,
-        veps=[torch.tensor(0.05)] * nlf, xeps=[torch.tensor(0.07)] * nlf,
-        _planar_consts=lambda: (None, masks), unflatten=lambda t: t, _get_vnet=lambda step: FakeVnet(),
-        _eps_t=lambda p: p, compute_accept_prob=lambda s0, s1, sld: torch.exp(-sld.abs()))
+        _eps_tensors=lambda: (xeps, veps), _fused_input=lambda vnet, nb_: False,
+        _planar_consts=lambda: (None, masks), unflatten=lambda t: t, _get_vnet=lambda step: shared,
+        compute_accept_prob=lambda s0, s1, sld: torch.exp(-sld.abs()))
     fake._reuse_force = lambda: dmod.Dynamics._reuse_force(fake)
     torch.manual_seed(0)
     st = State(torch.randn(nb, n, dtype=torch.float64), torch.randn(nb, n, dtype=torch.float64), torch.tensor(2.0))
     res = {}
-    for mode in ('never', 'always'):
-        fake.reuse_force = mode
+    for mode, pair in (('never', 'auto'), ('always', 'never'), ('always', 'auto')):
+        fake.reuse_force, fake.pair_updates = mode, pair
         calls.clear()
         out, met = dmod.Dynamics._transition_kernel_fb_planar(fake, st)
-        res[mode] = (out.x, out.v, met['acc'], met['sumlogdet'], dict(calls))
-    assert res['never'][4] == {'force': 4 * nlf, 'project': 8 * nlf, 'vupdate': 4 * nlf, 'xupdate': 4 * nlf}
-    assert res['always'][4] == {'force': 2 * nlf + 1, 'project': 2 * (2 * nlf + 1), 'vupdate': 4 * nlf, 'xupdate': 4 * nlf}
-    for a, b in zip(res['never'][:4], res['always'][:4]):
-        assert torch.equal(a, b)
+        res[(mode, pair)] = (out.x, out.v, met['acc'], met['sumlogdet'], dict(calls))
+    # the reference's schedule: everything recomputed for every update, one kernel per update
+    assert res[('never', 'auto')][4] == {'force': 4 * nlf, 'project': 8 * nlf, 'vupdate': 4 * nlf, 'xupdate': 4 * nlf}
+    # reuse: once per distinct link configuration
+    assert res[('always', 'never')][4] == {'force': 2 * nlf + 1, 'project': 2 * (2 * nlf + 1), 'vupdate': 4 * nlf,
+                                           'xupdate': 4 * nlf}
+    # paired passes: the first and the last momentum update stand alone, all others (turn-around included) pair up
+    assert res[('always', 'auto')][4] == {'force': 2 * nlf + 1, 'project': 2 * (2 * nlf + 1), 'vupdate': 2,
+                                          'vupdate_pair': 2 * nlf - 1, 'xupdate_pair': 2 * nlf}
+    for key in (('always', 'never'), ('always', 'auto')):
+        for a, b in zip(res[('never', 'auto')][:2], res[key][:2]):
+            assert torch.equal(a, b), key              # links and momenta: the same operations in the same order
+        for a, b in zip(res[('never', 'auto')][2:4], res[key][2:4]):
+            assert torch.allclose(a, b, rtol=1e-14, atol=1e-14), key    # log-Jacobians are added pairwise
 
 
 def test_call_vnet_packs_projected_inputs_in_the_reference_order():
