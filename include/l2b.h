@@ -281,6 +281,28 @@ int l2b_su3_input_layer(const void* act_x, const void* act_f, const void* packed
                         void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* dense layers: general bf16 GEMM on the tensor cores (tcgen05)              */
+/* ------------------------------------------------------------------------ */
+/* Every nn.Linear of the networks the fused kernels do not cover -- the hidden Linears (network/pytorch/
+ * network.py:489-493, 538-541), the input Linears under autograd (:415-422) -- and the GEMMs of every Linear's
+ * backward pass that the reference gets from ATen autograd (dX = dY W, dW = dY^T X; trainer.py:1326-1345 calls
+ * loss.backward()):
+ *     D[m][n] = act( sum_{seg < nseg} sum_{k < K} A_seg(m, k) B_seg(n, k) + bias[n] )  (+ D when accumulate)
+ * bf16 operands, fp32 accumulation in TMEM.  Operands are plain row-major matrices; `*_kmajor` says which axis is
+ * contracted: 1 = stored [MN][K] (leading dimension ld >= K), 0 = stored [K][MN] (ld >= MN) -- no transposed copy
+ * is needed for any of the three GEMMs of a Linear.  a_ptrs / b_ptrs: HOST arrays of nseg (1..3) device pointers,
+ * all segments share the shapes and leading dimensions.  out: [M][ldo] in out_dtype (L2B_BF16 or L2B_F32).
+ * splits > 1 cuts the concatenated K axis over that many CTAs per tile (fp32 partials in ws, summed in a fixed
+ * order); l2b_gemm_bf16_splits proposes a value that fills the GPU.  activation codes as l2b_su3_input_layer.
+ * Stored row lengths, leading dimensions and N must be multiples of 8 (16-byte units), pointers 16-byte aligned,
+ * else L2B_ERR_UNSUPPORTED / L2B_ERR_INVALID. */
+int l2b_gemm_bf16_splits(int M, int N, int K, int nseg, int b_kmajor);
+size_t l2b_gemm_bf16_ws_bytes(int M, int N, int splits);
+int l2b_gemm_bf16(const void* const* a_ptrs, long long lda, int a_kmajor, const void* const* b_ptrs, long long ldb,
+                  int b_kmajor, int nseg, int M, int N, int K, void* out, int out_dtype, long long ldo, int accumulate,
+                  const float* bias, int activation, int splits, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */
 /* ------------------------------------------------------------------------ */
 /* The three heads of the vnet LeapfrogLayer (network/pytorch/network.py:536-548:

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p, POINTER
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -111,6 +111,8 @@ _SIGS = {
                                    c_int, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P],
     'l2b_su3_input_pack': [_P, _P, c_int, _P, c_int, c_int, _P],
     'l2b_su3_input_layer': [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
+    'l2b_gemm_bf16': [POINTER(_P), c_longlong, c_int, POINTER(_P), c_longlong, c_int, c_int, c_int, c_int, c_int, _P, c_int,
+                      c_longlong, c_int, _P, c_int, c_int, _P, c_size_t, _P],
     'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
@@ -151,6 +153,8 @@ _RES = {
     'l2b_vnet_heads_ws_bytes': ([c_int, c_int], c_size_t),
     'l2b_su3_input_packed_bytes': ([c_int, c_int], c_size_t),
     'l2b_su3_input_ws_bytes': ([c_int, c_int], c_size_t),
+    'l2b_gemm_bf16_splits': ([c_int, c_int, c_int, c_int, c_int], c_int),
+    'l2b_gemm_bf16_ws_bytes': ([c_int, c_int, c_int], c_size_t),
     'l2b_u1_heads_ws_bytes': ([c_int, c_int], c_size_t),
     'l2b_u1_input_ws_bytes': ([c_int, c_int], c_size_t),
 }

@@ -757,6 +757,112 @@ def su3_input_layer(act_x: Tensor, act_f: Tensor, pack: InputPack, nb: int) -> T
 
 
 # ---------------------------------------------------------------------------
+# dense layers: the general bf16 tensor-core GEMM (include/l2b.h, l2b_gemm_bf16)
+# ---------------------------------------------------------------------------
+_ACT_CODES = {None: 0, 'identity': 0, 'tanh': 1, 'relu': 2, 'swish': 3, 'leaky_relu': 4, 'elu': 5}
+
+
+def _pad2(t: Tensor, rows: int, cols: int) -> Tensor:
+    """zero-pad a 2-D matrix to [rows, cols]; a no-op (no copy) for the production shapes"""
+    r, c = int(t.shape[0]), int(t.shape[1])
+    if r == rows and c == cols:
+        return t
+    return torch.nn.functional.pad(t, (0, cols - c, 0, rows - r))
+
+
+def _gemm_operand(t: Tensor) -> Tensor:
+    if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
+def _r8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmajor: bool, b_kmajor: bool, *,
+              out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bias: Optional[Tensor] = None,
+              act: Optional[str] = None, accumulate: bool = False, splits: int = 0) -> Tensor:
+    """D[m, n] = act(sum_seg sum_k A_seg(m, k) B_seg(n, k) + bias[n]) on the tensor cores (bf16 in, fp32 accumulate).
+
+    a / b: one matrix or a list of up to three same-shaped matrices (segments summed in one launch).  K-major
+    operands are stored [MN, K], MN-major ones [K, MN]; `out` may be a (row-strided) view, bf16 or fp32.
+    Extents that are not multiples of 8 (16-byte units) are zero-padded here (a copy); the production shapes
+    never are."""
+    a_list = [a] if isinstance(a, Tensor) else list(a)
+    b_list = [b] if isinstance(b, Tensor) else list(b)
+    if len(a_list) != len(b_list) or not 1 <= len(a_list) <= 3:
+        raise L2BError('gemm_bf16: 1..3 (A, B) segment pairs')
+    _need_cuda(*a_list, *b_list, out, bias)
+    for t in a_list + b_list:
+        if t.dtype != torch.bfloat16 or t.dim() != 2:
+            raise L2BError(f'gemm operands must be 2-D bfloat16 matrices (got {t.dtype}, {tuple(t.shape)})')
+    if any(t.shape != a_list[0].shape for t in a_list) or any(t.shape != b_list[0].shape for t in b_list):
+        raise L2BError('gemm_bf16: segments must share shapes')
+    M, K = (int(d) for d in (a_list[0].shape if a_kmajor else a_list[0].shape[::-1]))
+    N, Kb = (int(d) for d in (b_list[0].shape if b_kmajor else b_list[0].shape[::-1]))
+    if Kb != K:
+        raise L2BError(f'gemm_bf16: contraction lengths differ ({K} vs {Kb})')
+    Kp = _r8(K) if (a_kmajor or b_kmajor) else K
+    Mp = M if a_kmajor else _r8(M)
+    Np = _r8(N)
+    a_list = [_gemm_operand(_pad2(t, M, Kp) if a_kmajor else _pad2(t, Kp, Mp)) for t in a_list]
+    b_list = [_gemm_operand(_pad2(t, Np, Kp) if b_kmajor else _pad2(t, Kp, Np)) for t in b_list]
+    if len({int(t.stride(0)) for t in a_list}) != 1:
+        a_list = [t.contiguous() for t in a_list]
+    if len({int(t.stride(0)) for t in b_list}) != 1:
+        b_list = [t.contiguous() for t in b_list]
+    dev = a_list[0].device
+    direct = (out is not None and Mp == M and Np == N and out.dim() == 2 and tuple(out.shape) == (M, N)
+              and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0
+              and out.dtype in (torch.bfloat16, torch.float32))
+    if direct:
+        dst = out
+    else:
+        if accumulate:
+            raise L2BError('gemm_bf16: accumulate needs an aligned bf16 / fp32 `out` of an unpadded shape')
+        dst = torch.empty((Mp, Np), dtype=out_dtype, device=dev)
+    if bias is not None:
+        bias = bias.detach().to(torch.float32).reshape(-1).contiguous()
+        if Np != N:
+            bias = torch.nn.functional.pad(bias, (0, Np - N))
+    if splits <= 0:
+        splits = int(_lib._lib.l2b_gemm_bf16_splits(Mp, Np, Kp, len(a_list), int(b_kmajor)))
+    splits = max(1, splits)
+    nws = int(_lib._lib.l2b_gemm_bf16_ws_bytes(Mp, Np, splits))
+    ws = _workspace(nws, dev) if nws else None
+    ap = (c_void_p * len(a_list))(*[t.data_ptr() for t in a_list])
+    bp = (c_void_p * len(b_list))(*[t.data_ptr() for t in b_list])
+    call('l2b_gemm_bf16', ap, int(a_list[0].stride(0)), int(a_kmajor), bp, int(b_list[0].stride(0)), int(b_kmajor),
+         len(a_list), Mp, Np, Kp, _ptr(dst), L2B_BF16 if dst.dtype == torch.bfloat16 else L2B_F32,
+         int(dst.stride(0)), int(accumulate), _ptr(bias), _ACT_CODES[act], splits, _ptr(ws), nws, _stream())
+    if direct:
+        return out
+    res = dst if (Mp == M and Np == N) else dst[:M, :N].contiguous()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, act: Optional[str] = None,
+               out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
+    """act(x W^T + b): x [nb, in], W [out, in] (nn.Linear layout), both contracted over their contiguous axis"""
+    return gemm_bf16(x, w, True, True, bias=bias, act=act, out_dtype=out_dtype)
+
+
+def linear_dx(gy: Sequence[Tensor] | Tensor, w: Sequence[Tensor] | Tensor, out_dtype: torch.dtype = torch.bfloat16) -> Tensor:
+    """dX = sum_seg dY_seg W_seg: dY [nb, out] K-major, W [out, in] contracted over its ROWS (MN-major) -- no W^T copy"""
+    return gemm_bf16(gy, w, True, False, out_dtype=out_dtype)
+
+
+def linear_dw(gy: Tensor, x: Tensor, out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.float32,
+              accumulate: bool = False) -> Tensor:
+    """dW = dY^T X: dY [r, out], X [r, in], both contracted over their rows (MN-major) -- no transposed copies"""
+    return gemm_bf16(gy, x, False, False, out=out, out_dtype=out_dtype, accumulate=accumulate)
+
+
+# ---------------------------------------------------------------------------
 # vnet output heads on the tensor cores, fused with the momentum update
 # ---------------------------------------------------------------------------
 class HeadsPack:

@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests/test_gpu_reuse_force.py -m gpu -q -k bit_identical 2>&1 | grep -v Warning | tail -40
+timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x 2>&1 | grep -v Warning | tail -40
