@@ -290,7 +290,7 @@ int l2b_su3_input_layer(const void* act_x, const void* act_f, const void* packed
  *     D[m][n] = act( sum_{seg < nseg} sum_{k < K} A_seg(m, k) B_seg(n, k) + bias[n] )  (+ D when accumulate)
  * bf16 operands, fp32 accumulation in TMEM.  Operands are plain row-major matrices; `*_kmajor` says which axis is
  * contracted: 1 = stored [MN][K] (leading dimension ld >= K), 0 = stored [K][MN] (ld >= MN) -- no transposed copy
- * is needed for any of the three GEMMs of a Linear.  a_ptrs / b_ptrs: HOST arrays of nseg (1..3) device pointers,
+ * is needed for any of the three GEMMs of a Linear.  a_ptrs / b_ptrs: HOST arrays of nseg (1..32) device pointers,
  * all segments share the shapes and leading dimensions.  out: [M][ldo] in out_dtype (L2B_BF16 or L2B_F32).
  * splits > 1 cuts the concatenated K axis over that many CTAs per tile (fp32 partials in ws, summed in a fixed
  * order); l2b_gemm_bf16_splits proposes a value that fills the GPU.  activation codes as l2b_su3_input_layer.

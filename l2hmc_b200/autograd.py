@@ -313,14 +313,48 @@ DEFER_HEAD_GRADS = False
 HEAD_GRAD_SINK = None
 
 
+def _weight_grad_segments(param, gs, xs, sink) -> None:
+    """dW = sum_u g_u^T x_u for ONE weight matrix from the stashed (cotangent, input) pairs of all the updates that
+    share it: one tensor-core launch (l2b_gemm_bf16, up to 32 segments; both operands contracted over their rows, no
+    concatenation and no transposed copy) written straight into the gradient exchange buffer when there is one
+    (its all-reduce starts at once), else into / onto `param.grad`.  Non-bf16 cotangents (fp32 nets without
+    autocast) keep the library GEMM."""
+    if not param.requires_grad:
+        return
+    bf16 = all(t.dtype == torch.bfloat16 for t in gs + xs)
+    use_sink = sink is not None and param.grad is None and id(param) in sink.offsets
+
+    def form(out, out_dtype):
+        if bf16:
+            for i in range(0, len(gs), 32):
+                out = ops.gemm_bf16(gs[i:i + 32], xs[i:i + 32], False, False, out=out, out_dtype=out_dtype,
+                                    accumulate=i > 0)
+            return out
+        g, x = torch.cat(gs), torch.cat(xs)
+        res = (g.t() @ x).to(out_dtype)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+    if use_sink:
+        out = sink.view(param)
+        if bf16 and out.dtype in (torch.bfloat16, torch.float32):
+            form(out, out.dtype)
+        else:
+            out.copy_(form(None, torch.float32))
+        sink.reduce_async(param)             # its all-reduce starts while the next weight's GEMM runs
+        return
+    g = form(None, torch.float32).to(param.dtype).reshape(param.shape)
+    param.grad = g if param.grad is None else param.grad + g
+
+
 def _flush_head_grads(net) -> None:
     pend = net._pending_head_grads
     net._pending_head_grads = None
     if not pend:
         return
     ws, bs, cs, wt, bt, wq, bq, cq = net.head_params()
-    z = torch.cat([p[3] for p in pend])
-
+    zs = [p[3] for p in pend]
     sink = HEAD_GRAD_SINK
 
     def acc(param, g):
@@ -328,19 +362,109 @@ def _flush_head_grads(net) -> None:
             g = g.to(param.dtype).reshape(param.shape)
             param.grad = g if param.grad is None else param.grad + g
     for k, (w, b_) in enumerate(((ws, bs), (wt, bt), (wq, bq))):
-        g = torch.cat([p[k] for p in pend])              # [n_updates * nb, xdim] pre-activation cotangents
-        if sink is not None and w.requires_grad and w.grad is None and id(w) in sink.offsets:
-            out = sink.view(w)
-            if out.dtype == g.dtype == z.dtype:
-                torch.mm(g.t(), z, out=out)              # dW lands in the exchange buffer, no cast, no copy
-            else:
-                out.copy_(g.t() @ z)
-            sink.reduce_async(w)                         # its all-reduce starts while the next head's GEMM runs
-        else:
-            acc(w, g.t() @ z)
-        acc(b_, g.sum(0, dtype=torch.float32))
+        gs = [p[k] for p in pend]                        # per update: [nb, xdim] pre-activation cotangents
+        _weight_grad_segments(w, gs, zs, sink)
+        acc(b_, torch.stack([g.sum(0, dtype=torch.float32) for g in gs]).sum(0))
     acc(cs, torch.stack([p[4] for p in pend]).sum(0))
     acc(cq, torch.stack([p[5] for p in pend]).sum(0))
+
+
+# ---------------------------------------------------------------------------
+# dense layers of the networks on the tensor-core GEMM (csrc/l2b_gemm.cu)
+# ---------------------------------------------------------------------------
+_PENDING_DENSE: dict = {}         # id(weight) -> (weight, [cotangents], [inputs]) of the current backward pass
+
+
+def _flush_dense_grads() -> None:
+    pend = dict(_PENDING_DENSE)
+    _PENDING_DENSE.clear()
+    for w, gs, xs in pend.values():
+        _weight_grad_segments(w, gs, xs, HEAD_GRAD_SINK)
+
+
+def _act_grad(act, y: Tensor, pre, g: Tensor) -> Tensor:
+    """cotangent of the pre-activation from the cotangent of y = act(pre); tanh / relu / leaky_relu / elu from the
+    output alone (what ATen's own backward formulas use), swish from the stored pre-activation"""
+    g = g.float()
+    if act in (None, 'identity'):
+        return g
+    yf = y.float()
+    if act == 'tanh':
+        return g * (1.0 - yf * yf)
+    if act == 'relu':
+        return g * (yf > 0)
+    if act == 'leaky_relu':
+        return g * torch.where(yf > 0, 1.0, 0.01)
+    if act == 'elu':
+        return g * torch.where(yf > 0, 1.0, yf + 1.0)
+    if act == 'swish':
+        pf = pre.float()
+        sg = torch.sigmoid(pf)
+        return g * (sg * (1.0 + pf * (1.0 - sg)))
+    raise ValueError(f'unknown activation {act!r}')
+
+
+class TCDense(torch.autograd.Function):
+    """y = act(sum_i x_i W_i^T + sum_i b_i) in bf16 with fp32 accumulation: ONE Linear (a hidden layer, reference
+    network/pytorch/network.py:538-541; an output head :546-548) or the InputLayer's pair sharing one output
+    (:415-451), as a single launch of the tensor-core GEMM with bias and activation in its epilogue.  Backward:
+    dX_i = (g act') W_i and dW_i = (g act')^T x_i on the same kernel (W_i and the cotangent contracted over their
+    rows: no transposed copies); under DEFER_HEAD_GRADS the dW of all the updates sharing a weight matrix are formed
+    by one launch when the backward pass ends.  args = (x_0, W_0, b_0[, x_1, W_1, b_1])."""
+
+    @staticmethod
+    def forward(ctx, act, owner, *args):
+        n = len(args) // 3
+        xs, ws, bs = [args[3 * i] for i in range(n)], [args[3 * i + 1] for i in range(n)], [args[3 * i + 2] for i in range(n)]
+        xb = [x.detach().reshape(x.shape[0], -1).to(torch.bfloat16) for x in xs]
+        wb = [owner.weight_as_bf16(w) for w in ws]
+        bias = None
+        for b_ in bs:
+            if b_ is not None:
+                bias = b_.detach().float() if bias is None else bias + b_.detach().float()
+        fused = None if act == 'swish' else act
+        y = ops.gemm_bf16(xb, wb, True, True, bias=bias, act=fused)
+        pre = None
+        if act == 'swish':
+            pre, y = y, torch.nn.functional.silu(y)
+        ctx.act, ctx.n = act, n
+        ctx.meta = [(x.shape, x.dtype) for x in xs]
+        ctx.save_for_backward(y, pre, *xb, *wb, *ws, *[b_ for b_ in bs])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n = ctx.n
+        y, pre = ctx.saved_tensors[:2]
+        xb = ctx.saved_tensors[2:2 + n]
+        wb = ctx.saved_tensors[2 + n:2 + 2 * n]
+        ws = ctx.saved_tensors[2 + 2 * n:2 + 3 * n]
+        bs = ctx.saved_tensors[2 + 3 * n:2 + 4 * n]
+        gpre32 = _act_grad(ctx.act, y, pre, gy)
+        gpre = gpre32.to(torch.bfloat16)
+        grads = []
+        gb = None
+        for i in range(n):
+            need_x, need_w, need_b = ctx.needs_input_grad[2 + 3 * i:5 + 3 * i]
+            gx = gw = gbi = None
+            if need_x:
+                shp, dt = ctx.meta[i]
+                gx = ops.linear_dx(gpre, wb[i]).reshape(shp).to(dt)
+            if need_w:
+                if DEFER_HEAD_GRADS:
+                    if not _PENDING_DENSE:
+                        torch.autograd.Variable._execution_engine.queue_callback(_flush_dense_grads)
+                    ent = _PENDING_DENSE.setdefault(id(ws[i]), (ws[i], [], []))
+                    ent[1].append(gpre)
+                    ent[2].append(xb[i])
+                else:
+                    gw = ops.linear_dw(gpre, xb[i]).to(ws[i].dtype)
+            if need_b and bs[i] is not None:
+                if gb is None:
+                    gb = gpre32.sum(0)
+                gbi = gb.to(bs[i].dtype).reshape(bs[i].shape)
+            grads += [gx, gw, gbi]
+        return (None, None, *grads)
 
 
 class SU3HeadsVUpdate(torch.autograd.Function):
@@ -348,9 +472,10 @@ class SU3HeadsVUpdate(torch.autograd.Function):
     tensor cores and s, t, q kept on chip (l2b_su3_heads_vupdate, csrc/l2b_vnet.cu).
     When a gradient is needed the kernel also writes (s, t, q) once (fp32) for the backward pass:
     ONE element-wise adjoint kernel (l2b_su3_heads_vupdate_bwd) then yields gv, gF, d/d eps and the
-    cotangents of the heads' pre-activations in the GEMM dtype, and the three small GEMMs of the Linear
-    backward run on cuBLAS (dz now, dW either now or, under DEFER_HEAD_GRADS, once per backward pass for
-    all the v-updates sharing the net)."""
+    cotangents of the heads' pre-activations in the GEMM dtype, and the GEMMs of the Linear backward run on
+    the tensor-core GEMM l2b_gemm_bf16 (dz now: one split-K launch over the three heads; dW either now or, under
+    DEFER_HEAD_GRADS, once per backward pass for all the v-updates sharing the net); fp32 / fp64 nets without
+    autocast keep the library GEMM."""
 
     @staticmethod
     def forward(ctx, z, v, force, eps, sign, eps_value, net, *head_params):
@@ -380,7 +505,11 @@ class SU3HeadsVUpdate(torch.autograd.Function):
         gp = (gpre[0], gpre[1], gpre[2])
         gcs, gcq = gss.sum(0, keepdim=True), gqq.sum(0, keepdim=True)
         wc = net.head_weights_as(cdt)
-        gz = (gp[0] @ wc[0] + gp[1] @ wc[1] + gp[2] @ wc[2]).to(z.dtype)
+        if cdt == torch.bfloat16:
+            # dz = sum_heads g_h W_h: one launch, three segments, the weights contracted over their rows (split-K)
+            gz = ops.linear_dx(list(gp), list(wc)).to(z.dtype)
+        else:
+            gz = (gp[0] @ wc[0] + gp[1] @ wc[1] + gp[2] @ wc[2]).to(z.dtype)
         zc = z.detach().to(cdt)
         if DEFER_HEAD_GRADS:
             if getattr(net, '_pending_head_grads', None) is None:
@@ -390,7 +519,12 @@ class SU3HeadsVUpdate(torch.autograd.Function):
             gparams = (None,) * 8
         else:
             need = ctx.needs_input_grad[7:]
-            gw = [(g.t() @ zc).to(w.dtype) if nd else None for g, w, nd in zip(gp, (ws, wt, wq), (need[0], need[3], need[5]))]
+            if cdt == torch.bfloat16:
+                gw = [ops.linear_dw(g, zc).to(w.dtype) if nd else None
+                      for g, w, nd in zip(gp, (ws, wt, wq), (need[0], need[3], need[5]))]
+            else:
+                gw = [(g.t() @ zc).to(w.dtype) if nd else None
+                      for g, w, nd in zip(gp, (ws, wt, wq), (need[0], need[3], need[5]))]
             gb = [g.sum(0, dtype=torch.float32).to(b_.dtype) if nd else None
                   for g, b_, nd in zip(gp, (bs, bt, bq), (need[1], need[4], need[6]))]
             gparams = (gw[0], gb[0], gcs.to(cs.dtype) if need[2] else None, gw[1], gb[1], gw[2], gb[2],

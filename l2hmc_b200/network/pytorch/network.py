@@ -8,9 +8,11 @@ reference `state_dict` loads unchanged:
     z = act(W_x flat(conv?(x)) + W_v flat(v));  z = act(W_i z) ...
     s = a_s e^{c_s} tanh(W_s z),  t = a_t W_t z,  q = a_q e^{c_q} tanh(W_q z)
 
-The dense / conv layers run on cuBLAS / cuDNN through torch.nn (library GEMMs);
-everything the integrator does with (s, t, q) afterwards is in libl2b's fused
-epilogue kernels (`l2b_su3_vupdate`, `l2b_u1_vupdate`, `l2b_u1_xupdate`).
+Where the nets run in bf16 (autocast, BASELINE cfg 5) every dense layer -- input pair, hidden Linears, heads, and
+all three GEMMs of their backward passes -- is the hand-written tcgen05 GEMM `l2b_gemm_bf16` (`autograd.TCDense`;
+the SU(3) heads and input layer have their own fused kernels on top, `l2b_su3_heads_vupdate`, `l2b_su3_input_layer`).
+fp32 / fp64 nets without autocast and the U(1) conv stack go through torch.nn (library calls); everything the
+integrator does with (s, t, q) afterwards is in libl2b's fused epilogue kernels.
 """
 from __future__ import annotations
 
@@ -255,11 +257,50 @@ class LeapfrogLayer(nn.Module):
     def set_net_weight(self, net_weight: NetWeight):
         self.nw = net_weight
 
+    # ---- dense layers on the tensor-core GEMM (csrc/l2b_gemm.cu) -----------------------------------------------
+    def weight_as_bf16(self, w: Tensor) -> Tensor:
+        """bf16 copy of a weight matrix (what autocast would re-create on every call), cached per weight version;
+        re-cast inside a CUDA-graph capture of a training step, where the weights change on every replay"""
+        if w.dtype == torch.bfloat16:
+            return w.detach()
+        cache = self.__dict__.setdefault('_bf16_weights', {})
+        key = (w._version, w.data_ptr(), weights_generation())
+        hit = cache.get(id(w))
+        if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
+            hit = (key, w.detach().to(torch.bfloat16))
+            cache[id(w)] = hit
+        return hit[1]
+
+    def tensor_core_dense(self, *inputs: Tensor) -> bool:
+        """run the dense layers on l2b_gemm_bf16: whenever the nets run in bf16 anyway (autocast, BASELINE cfg 5,
+        or bf16 parameters) and the activation is one of the reference's (network.py:40-46).
+        `self.tc_dense`: 'auto' (default) | 'never'"""
+        if getattr(self, 'tc_dense', 'auto') == 'never' or self.input_activation_name() is None:
+            return False
+        if not all(t.is_cuda for t in inputs):
+            return False
+        if torch.is_autocast_enabled('cuda'):
+            return torch.get_autocast_dtype('cuda') == torch.bfloat16
+        return self.transl.weight.dtype == torch.bfloat16
+
+    def _hidden_tc(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
+        from ... import autograd as ag
+        il, act = self.input_layer, self.input_activation_name()
+        x, v = inputs
+        z = ag.TCDense.apply(act, self, flatten(x), il.xlayer.weight, il.xlayer.bias,
+                             flatten(v), il.vlayer.weight, il.vlayer.bias)
+        for layer in self.hidden_layers:
+            z = ag.TCDense.apply(act, self, z, layer.weight, layer.bias)
+        return z
+
     def hidden(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
         """everything in front of the three output heads (network.py:536-545)"""
-        z = self.input_layer(inputs)
-        for layer in self.hidden_layers:
-            z = self.activation_fn(layer(z))
+        if self.dense_input() and self.tensor_core_dense(*inputs):
+            z = self._hidden_tc(inputs)
+        else:
+            z = self.input_layer(inputs)
+            for layer in self.hidden_layers:
+                z = self.activation_fn(layer(z))
         if self.net_config.dropout_prob > 0:
             z = self.dropout(z)
         if self.net_config.use_batch_norm:
@@ -281,8 +322,13 @@ class LeapfrogLayer(nn.Module):
     def hidden_tail(self, z: Tensor) -> Tensor:
         """`hidden` from the output of the input layer on (network.py:538-545): the remaining hidden Linears,
         dropout, batch norm"""
-        for layer in self.hidden_layers:
-            z = self.activation_fn(layer(z))
+        if self.hidden_layers and self.tensor_core_dense(z):
+            from ... import autograd as ag
+            for layer in self.hidden_layers:
+                z = ag.TCDense.apply(self.input_activation_name(), self, z, layer.weight, layer.bias)
+        else:
+            for layer in self.hidden_layers:
+                z = self.activation_fn(layer(z))
         if self.net_config.dropout_prob > 0:
             z = self.dropout(z)
         if self.net_config.use_batch_norm:
@@ -325,6 +371,14 @@ class LeapfrogLayer(nn.Module):
 
     def heads(self, z: Tensor) -> tuple[Tensor, Tensor, Tensor]:
         """network.py:546-548"""
+        if self.tensor_core_dense(z):
+            from ... import autograd as ag
+            s = self.nw.s * (self.scale.coeff.exp() * ag.TCDense.apply('tanh', self, z, self.scale.layer.weight,
+                                                                       self.scale.layer.bias))
+            t = self.nw.t * ag.TCDense.apply(None, self, z, self.transl.weight, self.transl.bias)
+            q = self.nw.q * (self.transf.coeff.exp() * ag.TCDense.apply('tanh', self, z, self.transf.layer.weight,
+                                                                        self.transf.layer.bias))
+            return s, t, q
         s = self.nw.s * self.scale(z)
         t = self.nw.t * self.transl(z)
         q = self.nw.q * self.transf(z)

@@ -785,14 +785,14 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
               act: Optional[str] = None, accumulate: bool = False, splits: int = 0) -> Tensor:
     """D[m, n] = act(sum_seg sum_k A_seg(m, k) B_seg(n, k) + bias[n]) on the tensor cores (bf16 in, fp32 accumulate).
 
-    a / b: one matrix or a list of up to three same-shaped matrices (segments summed in one launch).  K-major
+    a / b: one matrix or a list of up to 32 same-shaped matrices (segments summed in one launch).  K-major
     operands are stored [MN, K], MN-major ones [K, MN]; `out` may be a (row-strided) view, bf16 or fp32.
     Extents that are not multiples of 8 (16-byte units) are zero-padded here (a copy); the production shapes
     never are."""
     a_list = [a] if isinstance(a, Tensor) else list(a)
     b_list = [b] if isinstance(b, Tensor) else list(b)
-    if len(a_list) != len(b_list) or not 1 <= len(a_list) <= 3:
-        raise L2BError('gemm_bf16: 1..3 (A, B) segment pairs')
+    if len(a_list) != len(b_list) or not 1 <= len(a_list) <= 32:
+        raise L2BError('gemm_bf16: 1..32 (A, B) segment pairs')
     _need_cuda(*a_list, *b_list, out, bias)
     for t in a_list + b_list:
         if t.dtype != torch.bfloat16 or t.dim() != 2:

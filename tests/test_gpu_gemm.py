@@ -50,6 +50,12 @@ CASES = [
     (2, 16, 16, True, True, 1, 1),           # tiny
     (5, 12, 20, True, False, 1, 1),          # extents that need zero padding on the Python side
     (7, 9, 3, False, False, 1, 1),
+    (256, 320, 32, False, False, 16, 1),     # dW over 16 updates of 32 chains: two segments share one 64-row stage
+    (136, 72, 24, False, False, 5, 1),       # ... odd segment count, K < 32, ragged
+    (200, 64, 32, False, False, 7, 2),       # ... with split-K
+    (32, 1024, 256, True, False, 1, 1),      # skinny M, short K: computed as D^T (dX of the input layer)
+    (16, 520, 72, True, True, 2, 1),
+    (64, 200, 40, False, False, 1, 1),
 ]
 
 
@@ -70,9 +76,10 @@ def test_gemm_matches_float64_of_the_same_bf16_operands(M, N, K, a_k, b_k, nseg,
 
 @pytest.mark.parametrize('act', [None, 'tanh', 'relu', 'swish', 'leaky_relu', 'elu'])
 @pytest.mark.parametrize('splits', [1, 4])
-def test_gemm_bias_activation(act, splits):
+@pytest.mark.parametrize('M', [48, 160])
+def test_gemm_bias_activation(act, splits, M):
     from l2hmc_b200 import ops
-    M, N, K = 48, 64, 1024
+    N, K = 64, 1024
     a, b = _mk((M, K), 1) * 0.05, _mk((N, K), 2)
     bias = torch.linspace(-1, 1, N, device=DEV)
     want = _ref([a], [b], True, True, bias=bias, act=act)
