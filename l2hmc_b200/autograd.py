@@ -35,6 +35,31 @@ def _eps_grad(geps_per_chain: Tensor, eps: Tensor):
     return geps_per_chain.sum().to(eps.dtype).reshape(eps.shape)
 
 
+class EpsPrime(torch.autograd.Function):
+    """eps' = sigmoid(log eps) = eps / (1 + eps) (reference dynamics.py:1270,1394) of ALL step-size parameters of a
+    sweep in one pass: 3 tiny launches forward and 4 backward per sweep instead of ~10 per update (the training step
+    is launch-bound on the host; each update used to pay for its own log / sigmoid and their autograd nodes).
+    Returns one 0-dim tensor per parameter, attached to the graph."""
+
+    @staticmethod
+    def forward(ctx, *params):
+        p = torch.stack([q.detach().reshape(()) for q in params])
+        e = torch.sigmoid(p.log())
+        ctx.save_for_backward(p, e)
+        ctx.shapes = [q.shape for q in params]
+        # each step size in the parameters' dtype and as float64 (what the SU(3) kernels read)
+        return tuple(e.unbind(0)) + tuple(e.to(torch.float64).unbind(0))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        p, e = ctx.saved_tensors
+        n = p.shape[0]
+        z = torch.zeros((), dtype=p.dtype, device=p.device)
+        g = torch.stack([z if gi is None else gi.to(p.dtype).reshape(()) for gi in gs])
+        gp = (g[:n] + g[n:]) * (e * (1.0 - e) / p)
+        return tuple(gi.reshape(shp) for gi, shp in zip(gp.unbind(0), ctx.shapes))
+
+
 class U1WilsonLoops(torch.autograd.Function):
     """w = x0 + roll(x1,-1,T) - roll(x0,-1,X) - x1"""
 

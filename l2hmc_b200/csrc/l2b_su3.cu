@@ -852,6 +852,9 @@ template <> struct Vec8IO<__nv_bfloat16> {
   }
 };
 
+template <typename V> constexpr bool kVecIsBf16 = false;
+template <> constexpr bool kVecIsBf16<__nv_bfloat16> = true;
+
 // vec8 = su3_to_vec(projectSU(x)) written straight in the nets' element type
 template <typename V>
 __global__ void __launch_bounds__(NTL) k_project_vec(const C* __restrict__ x, V* __restrict__ vec8, size_t nmat) {
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(NTL) k_project_vec(const C* __restrict__ x, V*
   Mat3<T> m, r;
   block_load_mat<NTL>(m, sm, x, first, n);
   if ((int)threadIdx.x < n) {
-    project_su(r, m);
+    project_su<T, kVecIsBf16<V>>(r, m);               // bf16 output: links already in SU(3) pass through (see project_su)
     T v[8];
     su3_to_vec(v, r);
     Vec8IO<V>::store(vec8 + (first + threadIdx.x) * 8, v);
@@ -906,7 +909,7 @@ __global__ void __launch_bounds__(NTL) k_project_vec_planar(const C* __restrict_
   const size_t plane = blockIdx.y;                        // b * 4 + mu
   Mat3<T> m, r;
   soa_load(m, x + plane * 9 * (size_t)Vs, Vs, site);
-  project_su(r, m);
+  project_su<T, kVecIsBf16<V>>(r, m);
   T v[8];
   su3_to_vec(v, r);
   Vec8IO<V>::store(vec8 + (plane * Vs + site) * 8, v);    // [b][mu][site][8]: the order the vnet input expects
@@ -966,7 +969,7 @@ __global__ void __launch_bounds__(NTL) k_project_vec_planar_lm(const C* __restri
   const int b = (int)(plane >> 2), mu = (int)(plane & 3);
   Mat3<T> m, r;
   soa_load(m, x + plane * 9 * (size_t)Vs, Vs, site);
-  project_su(r, m);
+  project_su<T, true>(r, m);
   T v[8];
   su3_to_vec(v, r);
   Vec8IO<__nv_bfloat16>::store(vec8 + (((size_t)mu * Vs + site) * nbp + b) * 8, v);

@@ -607,6 +607,10 @@ class Dynamics(nn.Module):
     def transition_kernel_fb(self, state: State) -> tuple[State, dict]:
         if self._planar_ok():
             return self._transition_kernel_fb_planar(state)
+        with self._eps_sweep():
+            return self._transition_kernel_fb_eager(state)
+
+    def _transition_kernel_fb_eager(self, state: State) -> tuple[State, dict]:
         nb = state.x.shape[0]
         sumlogdet = self._zeros(nb)
         sldf, sldb = torch.zeros_like(sumlogdet), torch.zeros_like(sumlogdet)
@@ -638,6 +642,10 @@ class Dynamics(nn.Module):
         return state_, (self._stack_history(history) if verbose else history)
 
     def transition_kernel(self, state: State, forward: bool) -> tuple[State, dict]:
+        with self._eps_sweep():
+            return self._transition_kernel_eager(state, forward)
+
+    def _transition_kernel_eager(self, state: State, forward: bool) -> tuple[State, dict]:
         lf_fn = self._forward_lf if forward else self._backward_lf
         sinit = State(x=state.x, v=state.v, beta=state.beta)
         sumlogdet = self._zeros(state.x.shape[0])
@@ -776,9 +784,36 @@ class Dynamics(nn.Module):
             return cache[1][id(p)]
         return float(sigmoid(p.detach().log()))
 
-    def _eps_t(self, p: Tensor) -> Tensor:
-        """same, as a 0-dim tensor attached to the graph (trainable step sizes)"""
-        return sigmoid(p.log())
+    def _eps_t(self, p: Tensor, f64: bool = False) -> Tensor:
+        """same, as a 0-dim tensor attached to the graph (trainable step sizes), optionally as float64.  Inside a
+        sweep (`_eps_sweep`) all 2 nlf of them come from ONE batched autograd node (`ag.EpsPrime`)."""
+        cache = getattr(self, '_eps_cache', None)
+        if cache is not None:
+            if cache.get('vals') is None:
+                params = list(self.xeps) + list(self.veps)
+                cache['index'] = {id(q): i for i, q in enumerate(params)}
+                cache['vals'] = ag.EpsPrime.apply(*params)
+            i = cache['index'].get(id(p))
+            if i is not None:
+                return cache['vals'][i + len(cache['index']) if f64 else i]
+        e = sigmoid(p.log())
+        return e.to(torch.float64) if f64 else e
+
+    def _eps_sweep(self):
+        """context manager around one sweep of leapfrog layers: the step sizes are transformed once"""
+        dyn = self
+
+        class _Ctx:
+            def __enter__(self_):
+                self_.outer = getattr(dyn, '_eps_cache', None)
+                if self_.outer is None:
+                    dyn._eps_cache = {}
+
+            def __exit__(self_, *exc):
+                if self_.outer is None:
+                    dyn._eps_cache = None
+                return False
+        return _Ctx()
 
     def _forward_lf(self, step: int, state: State) -> tuple[State, Tensor]:
         m, mb = self._get_mask(step)
@@ -878,7 +913,7 @@ class Dynamics(nn.Module):
         if hmc:
             if self._su3:
                 return State(state.x, ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), None, None,
-                                                          None, self._eps_t(self.veps[step]).to(torch.float64), sign,
+                                                          None, self._eps_t(self.veps[step], f64=True), sign,
                                                           eps)[0], state.beta), self._zeros(state.x.shape[0])
             f = force.reshape_as(state.v)
             return State(state.x, ag.U1VUpdate.apply(state.v, f, None, None, None, self._eps_t(self.veps[step]), sign,
@@ -888,7 +923,7 @@ class Dynamics(nn.Module):
             dt = torch.bfloat16 if torch.is_autocast_enabled('cuda') else next(vnet.parameters()).dtype
             z = vnet.hidden(self._vnet_vecs(state, force, dt))
             v, logdet = ag.SU3HeadsVUpdate.apply(z, self.unflatten(state.v), self.unflatten(force),
-                                                 self._eps_t(self.veps[step]).to(torch.float64), sign, eps, vnet,
+                                                 self._eps_t(self.veps[step], f64=True), sign, eps, vnet,
                                                  *vnet.head_params())
             return State(state.x, v, state.beta), logdet
         if not self._su3 and self._u1_fused(self._get_vnet(step), state.v):
@@ -900,7 +935,7 @@ class Dynamics(nn.Module):
         s, t, q = self._call_vnet(step, (state.x, force))
         if self._su3:
             v, logdet = ag.SU3VUpdate.apply(self.unflatten(state.v), self.unflatten(force), s, t, q,
-                                            self._eps_t(self.veps[step]).to(torch.float64), sign, eps)
+                                            self._eps_t(self.veps[step], f64=True), sign, eps)
         else:
             v, logdet = ag.U1VUpdate.apply(state.v, force, s, t, q, self._eps_t(self.veps[step]), sign, eps)
         return State(state.x, v, state.beta), logdet
@@ -917,7 +952,7 @@ class Dynamics(nn.Module):
         x = self.unflatten(state.x)
         if self._su3:
             # x' = m*x + exp(+-eps v) @ ((1-m)*x); xnet is never called, logdet = 0
-            xn = ag.SU3UpdateGauge.apply(x, self.unflatten(state.v), self._eps_t(self.xeps[step]).to(torch.float64),
+            xn = ag.SU3UpdateGauge.apply(x, self.unflatten(state.v), self._eps_t(self.xeps[step], f64=True),
                                          m, sign, eps)
             return State(x=xn, v=state.v, beta=state.beta), self._zeros(x.shape[0])
         xnet = self._get_xnet(step, first)

@@ -130,6 +130,22 @@ def bump_weights_generation() -> int:
     return _WEIGHTS_GENERATION[0]
 
 
+# A training step captured into a CUDA graph must contain the kernels that derive the bf16 weight images from the
+# live weights (the replay moves the weights), but only ONCE per step: `Trainer.train_step` opens a new step token,
+# and while a stream is capturing the weight-derived caches are valid exactly within one token.
+_STEP_TOKEN = [0]
+
+
+def new_step_token() -> int:
+    _STEP_TOKEN[0] += 1
+    return _STEP_TOKEN[0]
+
+
+def _capture_token() -> int:
+    """-1 outside a capture (caches live as long as the weights' versions), else the current step token"""
+    return _STEP_TOKEN[0] if torch.cuda.is_current_stream_capturing() else -1
+
+
 class PeriodicPadding(nn.Module):
     """wraps `size` on BOTH sides of the last two axes (network.py:151-172)"""
 
@@ -260,13 +276,13 @@ class LeapfrogLayer(nn.Module):
     # ---- dense layers on the tensor-core GEMM (csrc/l2b_gemm.cu) -----------------------------------------------
     def weight_as_bf16(self, w: Tensor) -> Tensor:
         """bf16 copy of a weight matrix (what autocast would re-create on every call), cached per weight version;
-        re-cast inside a CUDA-graph capture of a training step, where the weights change on every replay"""
+        re-cast once per step inside a CUDA-graph capture of a training step, where the weights change on every replay"""
         if w.dtype == torch.bfloat16:
             return w.detach()
         cache = self.__dict__.setdefault('_bf16_weights', {})
-        key = (w._version, w.data_ptr(), weights_generation())
+        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
         hit = cache.get(id(w))
-        if hit is None or hit[0] != key or torch.cuda.is_current_stream_capturing():
+        if hit is None or hit[0] != key:
             hit = (key, w.detach().to(torch.bfloat16))
             cache[id(w)] = hit
         return hit[1]
@@ -397,9 +413,9 @@ class LeapfrogLayer(nn.Module):
         ws, _, _, wt, _, wq, _, _ = self.head_params()
         if ws.dtype == dtype:
             return ws.detach(), wt.detach(), wq.detach()
-        key = (dtype, ws._version, wt._version, wq._version, ws.data_ptr(), weights_generation())
+        key = (dtype, ws._version, wt._version, wq._version, ws.data_ptr(), weights_generation(), _capture_token())
         cached = getattr(self, '_head_weights_cast', None)
-        if cached is None or cached[0] != key or torch.cuda.is_current_stream_capturing():
+        if cached is None or cached[0] != key:
             cached = (key, tuple(w.detach().to(dtype) for w in (ws, wt, wq)))
             self._head_weights_cast = cached
         return cached[1]
@@ -413,6 +429,10 @@ class LeapfrogLayer(nn.Module):
         from ... import ops
         ps = self.head_params()
         key = tuple((p.data_ptr(), p._version) for p in ps) + (self.nw.s, self.nw.t, self.nw.q, weights_generation())
+        if self.training and any(p.requires_grad for p in ps):
+            # a training step captured in a CUDA graph changes the weights on every replay without Python running:
+            # the pack kernel must then be part of the graph -- once per step (`_capture_token`)
+            key = key + (_capture_token(),)
         if perm is not None:
             cached = getattr(self, '_heads_pack_perm', None)
             if cached is None or cached[0] != key or cached[2] is not perm:
@@ -425,10 +445,7 @@ class LeapfrogLayer(nn.Module):
                 self._heads_pack_perm = cached
             return cached[1]
         cached = getattr(self, '_heads_pack', None)
-        # a training step captured in a CUDA graph changes the weights on every replay without
-        # Python running: the pack kernel must then be part of the graph
-        repack = torch.cuda.is_current_stream_capturing() and self.training and any(p.requires_grad for p in ps)
-        if cached is None or cached[0] != key or repack:
+        if cached is None or cached[0] != key:
             ws, bs, cs, wt, bt, wq, bq, cq = ps
             with torch.no_grad():
                 pack = ops.vnet_pack_heads(ws, wt, wq, bs, bt, bq, cs, cq, self.nw.s, self.nw.t, self.nw.q)

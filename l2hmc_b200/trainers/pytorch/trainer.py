@@ -17,7 +17,7 @@ from ... import dist as l2dist
 from ...configs import LossConfig
 from ...dynamics.pytorch.dynamics import Dynamics
 from ...loss.pytorch.loss import LatticeLoss
-from ...network.pytorch.network import bump_weights_generation, weights_generation
+from ...network.pytorch.network import bump_weights_generation, new_step_token, weights_generation
 
 Tensor = torch.Tensor
 
@@ -168,6 +168,7 @@ class Trainer:
             bump_weights_generation()     # the replay moved the weights without Python touching a parameter
             return out
         self.dynamics.train()
+        new_step_token()        # weight-derived caches built during a capture live for exactly this step
         xi, beta = inputs
         with torch.no_grad():
             xi = self._x(xi.to(self.dynamics.device))

@@ -295,3 +295,33 @@ def test_input_layer_matches_float64_reference(nb, shape, hidden, act):
     assert float(err.max()) < 6e-3 * max(1.0, float(want.abs().max())), float(err.max())
     z2 = ops.su3_input_layer(ax, af, pack, nb)
     assert torch.equal(z, z2), 'fixed-order split-K reduction: bit-reproducible'
+
+
+def test_bf16_vnet_inputs_of_unitary_links_equal_the_full_projection():
+    """bf16 producers of the vnet inputs return links that are already in SU(3) as they are (project_su<NEAR>):
+    against the float64 full projection (dynamics.py:1154-1156, utils.py:227-346) rounded to bf16 the result may
+    differ only where the ~1e-8 noise of the closed-form eigen-solve at a triply degenerate X^+X crosses a bf16
+    rounding boundary; non-unitary inputs (the force) still take the full path"""
+    from l2hmc_b200 import ops
+    from oracle import su3 as osu3
+    rng = np.random.default_rng(11)
+    nb, shape = 4, (4, 4, 2, 6)
+    x = torch.from_numpy(osu3.random_su3(rng, (nb, 4, *shape, 3, 3))).to(DEV)
+    f = torch.from_numpy(osu3.random_momentum(rng, (nb, 4, *shape, 3, 3))).to(DEV)
+    for field, unitary in ((x, True), (f, False)):
+        want = ops.su3_project_vec(field, torch.float64)
+        got = ops.su3_project_vec(field, torch.bfloat16)
+        ulp = want.abs().clamp(min=2.0 ** -120) * 2.0 ** -8            # one bf16 ulp at each element, at least
+        assert bool(((got.double() - want).abs() <= ulp).all())
+        exact = got == want.to(torch.bfloat16)
+        assert float(exact.float().mean()) > 0.999
+        if unitary:                                                   # and the vec8 of the link itself, bit for bit
+            direct = ops.su3_to_vec(field).to(torch.bfloat16) if hasattr(ops, 'su3_to_vec') else None
+            if direct is not None:
+                assert torch.equal(got, direct.reshape(got.shape))
+        xs = ops.su3_aos_to_soa(field)
+        V = int(np.prod(shape))
+        pl = ops.su3_project_vec_planar(xs, torch.bfloat16).reshape(nb, 4 * V, 8)
+        assert torch.equal(pl.reshape(-1), got.reshape(-1))
+        lm = ops.su3_project_vec_planar_lm(xs)                        # [link][chain_pad][8]
+        assert torch.equal(lm[:, :nb].permute(1, 0, 2).reshape(-1), got.reshape(-1))
