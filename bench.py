@@ -452,44 +452,48 @@ def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: i
 
 def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, tdt) -> dict:
     """Every step: H2D of that step's links from pinned host memory, the public `Dynamics.apply_transition_hmc`
-    call, D2H of the step's results: the accept probabilities AND the new configuration x_out.  Three streams:
-    the upload of step i+1 and the download of step i-1 run while step i computes (two device input buffers, two
-    device/host output buffers), as a production sampler feeding independent batches would do."""
+    call, D2H of the step's results: the accept probabilities AND the new configuration x_out.  Three streams and
+    three buffers per direction: the uploads of steps i+1, i+2 and the download of step i-1 run while step i
+    computes, so neither copy engine ever waits for a kernel (with two buffers the upload of step i+2 could only
+    start when step i had finished: 66.9 ms per step against the 52.9 ms both directions need on this host link,
+    `profiles/exp_pcie_bidir.py`) -- as a production sampler feeding independent batches would do."""
     torch = ctx.torch
     dev = ctx.dev
     nb = x.shape[0]
+    NBUF = 3
     xh = x.detach().cpu().pin_memory()
     field_bytes = x.numel() * x.element_size()
-    xo_h = [torch.empty((nb, x.numel() // nb), dtype=x.dtype).pin_memory() for _ in range(2)]
+    xo_h = [torch.empty((nb, x.numel() // nb), dtype=x.dtype).pin_memory() for _ in range(NBUF)]
     acc_h = torch.empty(nb, dtype=torch.float64 if su3 else tdt).pin_memory()
     bt = torch.tensor(beta)
     up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
-    xin = [torch.empty_like(x), torch.empty_like(x)]
-    xout = [None, None]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
-    drained = [torch.cuda.Event(), torch.cuda.Event()]
+    xin = [torch.empty_like(x) for _ in range(NBUF)]
+    xout = [None] * NBUF
+    ready = [torch.cuda.Event() for _ in range(NBUF)]
+    freed = [torch.cuda.Event() for _ in range(NBUF)]
+    done = [torch.cuda.Event() for _ in range(NBUF)]
+    drained = [torch.cuda.Event() for _ in range(NBUF)]
 
     def stage(i):
-        buf = i % 2
+        buf = i % NBUF
         with torch.cuda.stream(up):
             up.wait_event(freed[buf])                     # previous user of this input buffer is done
             xin[buf].copy_(xh, non_blocking=True)         # H2D of step i's links
             ready[buf].record(up)
 
     def run(n):
-        for b_ in (0, 1):
+        for b_ in range(NBUF):
             freed[b_].record(main)
             drained[b_].record(down)
-        stage(0)
+        for i in range(min(NBUF - 1, n)):
+            stage(i)
         for i in range(n):
-            if i + 1 < n:
-                stage(i + 1)
-            buf = i % 2
+            if i + NBUF - 1 < n:
+                stage(i + NBUF - 1)
+            buf = i % NBUF
             main.wait_event(ready[buf])
-            main.wait_event(drained[buf])                 # step i-2's x_out has left its device buffer
+            main.wait_event(drained[buf])                 # step i-3's x_out has left its device buffer
             xo, met = dyn.apply_transition_hmc((xin[buf], bt), eps=eps, nleapfrog=nlf)
             xout[buf] = xo
             freed[buf].record(main)
@@ -506,7 +510,7 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
         run(max(1, min(warmup, 2)))
         ctx.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(2, min(steps, 6))
+        n_e2e = max(steps, 12)                  # pipeline fill (first upload) and drain (last download) amortised
         e2.record()
         run(n_e2e)
         e3.record()
@@ -525,8 +529,8 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
             'h2d_bytes_per_step': field_bytes, 'd2h_bytes_per_step': field_bytes + acc_h.numel() * acc_h.element_size(),
             'steps': n_e2e, 'ms_per_step': ms / n_e2e,
             'h2d_GBps_per_gpu_all_ranks_copying': field_bytes / (h2d_ms * 1e-3) / 1e9,
-            'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta)); H2D of step i+1 and D2H of step '
-                   'i-1 (x_out, acc) overlapped with step i on two copy streams'}
+            'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta)); H2D of steps i+1, i+2 and D2H of '
+                   'step i-1 (x_out, acc) overlapped with step i: two copy streams, three buffers per direction'}
 
 
 def parity_of_timed_batch(ctx: Ctx, x, v, out, beta, eps, nlf, lattice) -> dict:
