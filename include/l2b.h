@@ -293,14 +293,23 @@ int l2b_su3_input_layer(const void* act_x, const void* act_f, const void* packed
  * is needed for any of the three GEMMs of a Linear.  a_ptrs / b_ptrs: HOST arrays of nseg (1..32) device pointers,
  * all segments share the shapes and leading dimensions.  out: [M][ldo] in out_dtype (L2B_BF16 or L2B_F32).
  * splits > 1 cuts the concatenated K axis over that many CTAs per tile (fp32 partials in ws, summed in a fixed
- * order); l2b_gemm_bf16_splits proposes a value that fills the GPU.  activation codes as l2b_su3_input_layer.
+ * order); l2b_gemm_bf16_splits proposes a value that fills the GPU.  seg_inner: order of the (segment, K chunk) loop,
+ * 0 = each segment front to back, 1 = all segments of a K chunk before the next chunk.  activation codes as l2b_su3_input_layer.
  * Stored row lengths, leading dimensions and N must be multiples of 8 (16-byte units), pointers 16-byte aligned,
  * else L2B_ERR_UNSUPPORTED / L2B_ERR_INVALID. */
 int l2b_gemm_bf16_splits(int M, int N, int K, int nseg, int b_kmajor);
 size_t l2b_gemm_bf16_ws_bytes(int M, int N, int splits);
 int l2b_gemm_bf16(const void* const* a_ptrs, long long lda, int a_kmajor, const void* const* b_ptrs, long long ldb,
-                  int b_kmajor, int nseg, int M, int N, int K, void* out, int out_dtype, long long ldo, int accumulate,
-                  const float* bias, int activation, int splits, void* ws, size_t ws_bytes, void* stream);
+                  int b_kmajor, int nseg, int seg_inner, int M, int N, int K, void* out, int out_dtype, long long ldo,
+                  int accumulate, const float* bias, int activation, int splits, void* ws, size_t ws_bytes,
+                  void* stream);
+/* fp32 nets without autocast (the reference's default precision, configs.py `precision: float32`): an fp32-accurate
+ * Linear on the same kernel.  l2b_split_bf16x3 writes x = x1 + x2 + x3 as three bf16 matrices out[3][rows][out_ld]
+ * (zero padded columns); the six products a_i b_j with i + j <= 4 are six segments of one l2b_gemm_bf16 launch
+ * (seg_inner = 1: the segments of one K chunk run back to back, so the re-read operands hit L2).  Relative error
+ * ~ 2^-22, that of an fp32 GEMM. */
+int l2b_split_bf16x3(const float* x, long long rows, long long cols, long long ld, void* out, long long out_ld,
+                     void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */

@@ -111,8 +111,9 @@ _SIGS = {
                                    c_int, _P, _P, c_int, c_int, c_int, _P, c_size_t, _P],
     'l2b_su3_input_pack': [_P, _P, c_int, _P, c_int, c_int, _P],
     'l2b_su3_input_layer': [_P, _P, _P, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P],
-    'l2b_gemm_bf16': [POINTER(_P), c_longlong, c_int, POINTER(_P), c_longlong, c_int, c_int, c_int, c_int, c_int, _P, c_int,
-                      c_longlong, c_int, _P, c_int, c_int, _P, c_size_t, _P],
+    'l2b_gemm_bf16': [POINTER(_P), c_longlong, c_int, POINTER(_P), c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                      c_int, c_longlong, c_int, _P, c_int, c_int, _P, c_size_t, _P],
+    'l2b_split_bf16x3': [_P, c_longlong, c_longlong, c_longlong, _P, c_longlong, _P],
     'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],
     'l2b_su3_force_kick_planar': [_P, _P, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],

@@ -338,18 +338,23 @@ DEFER_HEAD_GRADS = False
 HEAD_GRAD_SINK = None
 
 
-def _weight_grad_segments(param, gs, xs, sink) -> None:
+def _weight_grad_segments(param, gs, xs, sink, mode: str = 'auto') -> None:
     """dW = sum_u g_u^T x_u for ONE weight matrix from the stashed (cotangent, input) pairs of all the updates that
     share it: one tensor-core launch (l2b_gemm_bf16, up to 32 segments; both operands contracted over their rows, no
     concatenation and no transposed copy) written straight into the gradient exchange buffer when there is one
-    (its all-reduce starts at once), else into / onto `param.grad`.  Non-bf16 cotangents (fp32 nets without
-    autocast) keep the library GEMM."""
+    (its all-reduce starts at once), else into / onto `param.grad`.  mode 'x3': the operands are bf16x3 splits of
+    fp32 matrices (fp32-accurate product, ops.gemm_f32).  Non-bf16 cotangents in mode 'auto' (fp64 nets) keep the
+    library GEMM."""
     if not param.requires_grad:
         return
-    bf16 = all(t.dtype == torch.bfloat16 for t in gs + xs)
+    x3 = mode == 'x3'
+    bf16 = (not x3) and all(t.dtype == torch.bfloat16 for t in gs + xs)
     use_sink = sink is not None and param.grad is None and id(param) in sink.offsets
 
     def form(out, out_dtype):
+        if x3:
+            res = ops.gemm_f32(gs, xs, False, False)
+            return res[:param.shape[0], :param.shape[1]]
         if bf16:
             for i in range(0, len(gs), 32):
                 out = ops.gemm_bf16(gs[i:i + 32], xs[i:i + 32], False, False, out=out, out_dtype=out_dtype,
@@ -403,8 +408,8 @@ _PENDING_DENSE: dict = {}         # id(weight) -> (weight, [cotangents], [inputs
 def _flush_dense_grads() -> None:
     pend = dict(_PENDING_DENSE)
     _PENDING_DENSE.clear()
-    for w, gs, xs in pend.values():
-        _weight_grad_segments(w, gs, xs, HEAD_GRAD_SINK)
+    for w, gs, xs, mode in pend.values():
+        _weight_grad_segments(w, gs, xs, HEAD_GRAD_SINK, mode)
 
 
 def _act_grad(act, y: Tensor, pre, g: Tensor) -> Tensor:
@@ -430,58 +435,83 @@ def _act_grad(act, y: Tensor, pre, g: Tensor) -> Tensor:
 
 
 class TCDense(torch.autograd.Function):
-    """y = act(sum_i x_i W_i^T + sum_i b_i) in bf16 with fp32 accumulation: ONE Linear (a hidden layer, reference
-    network/pytorch/network.py:538-541; an output head :546-548) or the InputLayer's pair sharing one output
-    (:415-451), as a single launch of the tensor-core GEMM with bias and activation in its epilogue.  Backward:
-    dX_i = (g act') W_i and dW_i = (g act')^T x_i on the same kernel (W_i and the cotangent contracted over their
-    rows: no transposed copies); under DEFER_HEAD_GRADS the dW of all the updates sharing a weight matrix are formed
-    by one launch when the backward pass ends.  args = (x_0, W_0, b_0[, x_1, W_1, b_1])."""
+    """y = act(sum_i x_i W_i^T + sum_i b_i): ONE Linear (a hidden layer, reference network/pytorch/network.py:538-541;
+    an output head :546-548) or the InputLayer's pair sharing one output (:415-451), as a single launch of the
+    tensor-core GEMM with bias and activation in its epilogue.  mode 'bf16': bf16 operands, fp32 accumulation (what
+    autocast runs); mode 'x3': fp32 nets without autocast -- every operand as its bf16x3 split, six products per pair,
+    fp32-accurate.  Backward: dX_i = (g act') W_i and dW_i = (g act')^T x_i on the same kernel (W_i and the cotangent
+    contracted over their rows: no transposed copies); under DEFER_HEAD_GRADS the dW of all the updates sharing a
+    weight matrix are formed by one launch when the backward pass ends.  args = (x_0, W_0, b_0[, x_1, W_1, b_1])."""
 
     @staticmethod
-    def forward(ctx, act, owner, *args):
+    def forward(ctx, act, owner, mode, *args):
         n = len(args) // 3
         xs, ws, bs = [args[3 * i] for i in range(n)], [args[3 * i + 1] for i in range(n)], [args[3 * i + 2] for i in range(n)]
-        xb = [x.detach().reshape(x.shape[0], -1).to(torch.bfloat16) for x in xs]
-        wb = [owner.weight_as_bf16(w) for w in ws]
         bias = None
         for b_ in bs:
             if b_ is not None:
                 bias = b_.detach().float() if bias is None else bias + b_.detach().float()
         fused = None if act == 'swish' else act
-        y = ops.gemm_bf16(xb, wb, True, True, bias=bias, act=fused)
+        nout = int(ws[0].shape[0])
+        # inputs of different widths (the U(1) xnet: 4TX cos / sin values against 2TX momenta) cannot be segments of
+        # one launch: they are concatenated along K instead (small matrices; the SU(3) pair shares its shape)
+        ragged = n == 2 and xs[0].numel() // xs[0].shape[0] != xs[1].numel() // xs[1].shape[0]
+        if mode == 'x3':
+            xb = [ops.split_bf16x3(x.detach().reshape(x.shape[0], -1).float()) for x in xs]
+            wb = [owner.weight_split3(w) for w in ws]
+            if ragged:
+                y = ops.gemm_f32(torch.cat(xb, 2), torch.cat(wb, 2), True, True, bias=bias, act=fused)
+            else:
+                y = ops.gemm_f32(xb, wb, True, True, bias=bias, act=fused)
+            if y.shape[1] != nout:
+                y = y[:, :nout].contiguous()
+        else:
+            xb = [x.detach().reshape(x.shape[0], -1).to(torch.bfloat16) for x in xs]
+            wb = [owner.weight_as_bf16(w) for w in ws]
+            if ragged:
+                y = ops.gemm_bf16(torch.cat(xb, 1), torch.cat(wb, 1), True, True, bias=bias, act=fused)
+            else:
+                y = ops.gemm_bf16(xb, wb, True, True, bias=bias, act=fused)
         pre = None
         if act == 'swish':
             pre, y = y, torch.nn.functional.silu(y)
-        ctx.act, ctx.n = act, n
+        ctx.act, ctx.n, ctx.mode = act, n, mode
         ctx.meta = [(x.shape, x.dtype) for x in xs]
         ctx.save_for_backward(y, pre, *xb, *wb, *ws, *[b_ for b_ in bs])
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        n = ctx.n
+        n, x3 = ctx.n, ctx.mode == 'x3'
         y, pre = ctx.saved_tensors[:2]
         xb = ctx.saved_tensors[2:2 + n]
         wb = ctx.saved_tensors[2 + n:2 + 2 * n]
         ws = ctx.saved_tensors[2 + 2 * n:2 + 3 * n]
         bs = ctx.saved_tensors[2 + 3 * n:2 + 4 * n]
         gpre32 = _act_grad(ctx.act, y, pre, gy)
-        gpre = gpre32.to(torch.bfloat16)
+        gpre = ops.split_bf16x3(gpre32.contiguous()) if x3 else gpre32.to(torch.bfloat16)
         grads = []
         gb = None
         for i in range(n):
-            need_x, need_w, need_b = ctx.needs_input_grad[2 + 3 * i:5 + 3 * i]
+            need_x, need_w, need_b = ctx.needs_input_grad[3 + 3 * i:6 + 3 * i]
             gx = gw = gbi = None
             if need_x:
                 shp, dt = ctx.meta[i]
-                gx = ops.linear_dx(gpre, wb[i]).reshape(shp).to(dt)
+                if x3:
+                    gx = ops.gemm_f32(gpre, wb[i], True, False)
+                    nin = int(ws[i].shape[1])
+                    gx = (gx if gx.shape[1] == nin else gx[:, :nin]).reshape(shp).to(dt)
+                else:
+                    gx = ops.linear_dx(gpre, wb[i]).reshape(shp).to(dt)
             if need_w:
                 if DEFER_HEAD_GRADS:
                     if not _PENDING_DENSE:
                         torch.autograd.Variable._execution_engine.queue_callback(_flush_dense_grads)
-                    ent = _PENDING_DENSE.setdefault(id(ws[i]), (ws[i], [], []))
+                    ent = _PENDING_DENSE.setdefault(id(ws[i]), (ws[i], [], [], ctx.mode))
                     ent[1].append(gpre)
                     ent[2].append(xb[i])
+                elif x3:
+                    gw = ops.gemm_f32(gpre, xb[i], False, False)[:ws[i].shape[0], :ws[i].shape[1]].to(ws[i].dtype)
                 else:
                     gw = ops.linear_dw(gpre, xb[i]).to(ws[i].dtype)
             if need_b and bs[i] is not None:
@@ -489,7 +519,7 @@ class TCDense(torch.autograd.Function):
                     gb = gpre32.sum(0)
                 gbi = gb.to(bs[i].dtype).reshape(bs[i].shape)
             grads += [gx, gw, gbi]
-        return (None, None, *grads)
+        return (None, None, None, *grads)
 
 
 class SU3HeadsVUpdate(torch.autograd.Function):

@@ -59,14 +59,16 @@ struct GemmArgs {
   float* part;                       // [splits][M][N] fp32 (splits > 1)
   uint32_t tmem_cols;
   int nst;                           // pipeline stages in use: 2 (two CTAs per SM) .. G_NST
+  int seg_inner;                     // chunk order: 1 = segments innermost (all segments of K chunk 0, then chunk 1, ...)
   int kpack;                         // 2: both operands MN-major with K <= 32: two segments share one 64-row stage
   int trans;                         // the kernel computes D^T (operands swapped by the host): out[n][m] <- D'[m][n]
 };
 
 // the reference's activations (codes as il_act) on the SFU: ex2.approx / rcp.approx, absolute error ~2e-7 -- the
-// results are rounded to bf16 or feed a bf16 GEMM next
-template <int ACT>
+// results are rounded to bf16 (bf16 nets); fp32 outputs use the libm-accurate functions
+template <int ACT, bool PRECISE>
 __device__ __forceinline__ float act_fast(float x) {
+  if (PRECISE) return il_act(x, ACT);          // fp32 output (fp32 nets): libm-accurate tanhf / expf / expm1f
   if (ACT == 1) return tanh_fast(x);
   if (ACT == 2) return fmaxf(x, 0.f);
   if (ACT == 3) return x * rcp_approx(1.f + exp_fast(-x));
@@ -140,8 +142,10 @@ __global__ void __launch_bounds__(G_NTH, 2) k_gemm_bf16(const __grid_constant__ 
         }
         continue;
       }
-      const int seg = (int)(c / nkc);
-      const int k0 = (int)(c - (long long)seg * nkc) * G_BK;
+      // segments outermost (streams each operand once, front to back) or innermost (the bf16x3 products of an fp32
+      // GEMM re-use the same K chunk of a1, a2, a3 / b1, b2, b3 in consecutive stages: L2 hits)
+      const int seg = g.seg_inner ? (int)(c % g.nseg) : (int)(c / nkc);
+      const int k0 = (g.seg_inner ? (int)(c / g.nseg) : (int)(c - (long long)seg * nkc)) * G_BK;
       if (g.a_kmajor) tma2d(a_dst, &maps.a[seg], k0, m0, bar);
       else {
         tma2d(a_dst, &maps.a[seg], m0, k0, bar);
@@ -230,14 +234,20 @@ __global__ void __launch_bounds__(G_NTH, 2) k_gemm_bf16(const __grid_constant__ 
         }
         // the activation is chosen once per 16 columns, not per element (a per-element switch compiles to an
         // indirect branch each: measured 3.4 k cycles per 16 columns against 0.4 k for the plain path)
-#define L2B_ACT_LOOP(CODE)                                                                             \
-  _Pragma("unroll") for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(act_fast<CODE>(__uint_as_float(r[i]) + bv[i]))
-        if (g.act == 1) { L2B_ACT_LOOP(1); }
-        else if (g.act == 2) { L2B_ACT_LOOP(2); }
-        else if (g.act == 3) { L2B_ACT_LOOP(3); }
-        else if (g.act == 4) { L2B_ACT_LOOP(4); }
-        else if (g.act == 5) { L2B_ACT_LOOP(5); }
-        else { L2B_ACT_LOOP(0); }
+#define L2B_ACT_LOOP(CODE)                                                                                      \
+  if (g.out_f32) {                                                                                              \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                              \
+        r[i] = __float_as_uint(act_fast<CODE, true>(__uint_as_float(r[i]) + bv[i]));                            \
+  } else {                                                                                                      \
+    _Pragma("unroll") for (int i = 0; i < 16; ++i)                                                              \
+        r[i] = __float_as_uint(act_fast<CODE, false>(__uint_as_float(r[i]) + bv[i]));                           \
+  }
+        if (g.act == 1) { L2B_ACT_LOOP(1) }
+        else if (g.act == 2) { L2B_ACT_LOOP(2) }
+        else if (g.act == 3) { L2B_ACT_LOOP(3) }
+        else if (g.act == 4) { L2B_ACT_LOOP(4) }
+        else if (g.act == 5) { L2B_ACT_LOOP(5) }
+        else { L2B_ACT_LOOP(0) }
 #undef L2B_ACT_LOOP
       }
       if (g.trans) {                                            // out[nn + i][m]: lanes write consecutive addresses
@@ -370,6 +380,30 @@ __global__ void __launch_bounds__(256) k_gemm_reduce(const float* __restrict__ p
   }
 }
 
+// x = x1 + x2 + x3 with three bf16 terms (8 + 8 + 8 mantissa bits): the operands of an fp32-accurate GEMM on the
+// bf16 tensor cores (six products a_i b_j, i + j <= 4, fp32 accumulation).  out[t][r][c], c < out_ld, zero padded.
+__global__ void __launch_bounds__(256) k_split_bf16x3(const float* __restrict__ x, long long rows, long long cols,
+                                                      long long ld, __nv_bfloat16* __restrict__ out, long long out_ld) {
+  const long long id = (long long)blockIdx.x * 256 + threadIdx.x;          // one thread per 8 output columns
+  const long long per_row = out_ld / 8;
+  if (id >= rows * per_row) return;
+  const long long r = id / per_row, c0 = (id % per_row) * 8;
+  __align__(16) __nv_bfloat16 h[3][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float v = (c0 + i < cols) ? __ldg(x + r * ld + c0 + i) : 0.f;
+    const __nv_bfloat16 a = __float2bfloat16(v);
+    const float r1 = v - __bfloat162float(a);
+    const __nv_bfloat16 b = __float2bfloat16(r1);
+    const float r2 = r1 - __bfloat162float(b);
+    h[0][i] = a; h[1][i] = b; h[2][i] = __float2bfloat16(r2);
+  }
+  const size_t plane = (size_t)rows * out_ld;
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+    *reinterpret_cast<uint4*>(out + t * plane + r * out_ld + c0) = *reinterpret_cast<const uint4*>(h[t]);
+}
+
 int pick_bn(int N, int b_kmajor, int M = 0, long long chunks = 1 << 30, int nsm = 0) {
   const int q = b_kmajor ? 16 : 64;
   int bn = (N + q - 1) / q * q;
@@ -459,9 +493,23 @@ size_t l2b_gemm_bf16_ws_bytes(int M, int N, int splits) {
   return align_up((size_t)splits * M * N * sizeof(float), 256);
 }
 
+int l2b_split_bf16x3(const float* x, long long rows, long long cols, long long ld, void* out, long long out_ld,
+                     void* stream) {
+  L2B_REQUIRE(x && out, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(rows > 0 && cols > 0 && ld >= cols, L2B_ERR_INVALID, "rows, cols must be positive and ld >= cols");
+  L2B_REQUIRE(out_ld % 8 == 0 && out_ld >= cols && ((uintptr_t)out & 15) == 0, L2B_ERR_INVALID,
+              "out_ld must be a multiple of 8 >= cols and out 16-byte aligned");
+  const long long n = rows * (out_ld / 8);
+  k_split_bf16x3<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ld, (__nv_bfloat16*)out,
+                                                                                out_ld);
+  L2B_LAUNCHED("k_split_bf16x3");
+  return L2B_OK;
+}
+
 int l2b_gemm_bf16(const void* const* a_ptrs, long long lda, int a_kmajor, const void* const* b_ptrs, long long ldb,
-                  int b_kmajor, int nseg, int M, int N, int K, void* out, int out_dtype, long long ldo, int accumulate,
-                  const float* bias, int activation, int splits, void* ws, size_t ws_bytes, void* stream) {
+                  int b_kmajor, int nseg, int seg_inner, int M, int N, int K, void* out, int out_dtype, long long ldo,
+                  int accumulate, const float* bias, int activation, int splits, void* ws, size_t ws_bytes,
+                  void* stream) {
   L2B_REQUIRE(a_ptrs && b_ptrs && out, L2B_ERR_INVALID, "null pointer");
   L2B_REQUIRE(nseg >= 1 && nseg <= G_MAXSEG, L2B_ERR_INVALID, "nseg must be in [1, %d] (got %d)", G_MAXSEG, nseg);
   L2B_REQUIRE(M > 0 && N > 0 && K > 0, L2B_ERR_INVALID, "M, N, K must be positive");
@@ -483,7 +531,8 @@ int l2b_gemm_bf16(const void* const* a_ptrs, long long lda, int a_kmajor, const 
   }
   GemmArgs g;
   // dW = sum_u dY_u^T X_u with 32 chains per update: two updates fill one 64-row stage
-  g.kpack = (!a_kmajor && !b_kmajor && K <= 32 && nseg >= 2) ? 2 : 1;
+  g.kpack = (!a_kmajor && !b_kmajor && K <= 32 && nseg >= 2 && !seg_inner) ? 2 : 1;
+  g.seg_inner = seg_inner ? 1 : 0;
   const long long chunks = g.kpack == 2 ? (nseg + 1) / 2 : (long long)nseg * ((K + G_BK - 1) / G_BK);
   if (splits > chunks) splits = (int)chunks;
   // A skinny M with a short K loop (dX = dY W of the input layer: 32 chains x 131 072 columns) would leave three of

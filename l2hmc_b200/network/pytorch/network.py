@@ -287,32 +287,54 @@ class LeapfrogLayer(nn.Module):
             cache[id(w)] = hit
         return hit[1]
 
-    def tensor_core_dense(self, *inputs: Tensor) -> bool:
-        """run the dense layers on l2b_gemm_bf16: whenever the nets run in bf16 anyway (autocast, BASELINE cfg 5,
-        or bf16 parameters) and the activation is one of the reference's (network.py:40-46).
+    def weight_split3(self, w: Tensor) -> Tensor:
+        """bf16x3 split of an fp32 weight matrix ([3, out, in8], ops.split_bf16x3) for the fp32-accurate tensor-core
+        GEMM, cached like `weight_as_bf16`"""
+        from ... import ops
+        cache = self.__dict__.setdefault('_x3_weights', {})
+        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
+        hit = cache.get(id(w))
+        if hit is None or hit[0] != key:
+            hit = (key, ops.split_bf16x3(w.detach().float()))
+            cache[id(w)] = hit
+        return hit[1]
+
+    def tensor_core_dense(self, *inputs: Tensor) -> Optional[str]:
+        """how the dense layers run on the hand-written tensor-core GEMM (l2b_gemm_bf16), or None (library path):
+        'bf16' whenever the nets run in bf16 anyway (autocast, BASELINE cfg 5, or bf16 parameters); 'x3' for fp32
+        parameters without autocast (the reference's default precision): bf16x3 operand splits, fp32-accurate.
+        fp64 nets and activations outside the reference's list (network.py:40-46) stay on torch.
         `self.tc_dense`: 'auto' (default) | 'never'"""
         if getattr(self, 'tc_dense', 'auto') == 'never' or self.input_activation_name() is None:
-            return False
+            return None
         if not all(t.is_cuda for t in inputs):
-            return False
+            return None
+        if isinstance(self.input_layer.xlayer, nn.modules.lazy.LazyModuleMixin):
+            return None                     # the materialising dummy call (network.py:572-631) goes through torch
         if torch.is_autocast_enabled('cuda'):
-            return torch.get_autocast_dtype('cuda') == torch.bfloat16
-        return self.transl.weight.dtype == torch.bfloat16
+            return 'bf16' if torch.get_autocast_dtype('cuda') == torch.bfloat16 else None
+        dt = self.transl.weight.dtype
+        if dt == torch.bfloat16:
+            return 'bf16'
+        if dt == torch.float32 and all(t.dtype in (torch.float32, torch.bfloat16) for t in inputs):
+            return 'x3'
+        return None
 
-    def _hidden_tc(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
+    def _hidden_tc(self, inputs: tuple[Tensor, Tensor], mode: str) -> Tensor:
         from ... import autograd as ag
         il, act = self.input_layer, self.input_activation_name()
         x, v = inputs
-        z = ag.TCDense.apply(act, self, flatten(x), il.xlayer.weight, il.xlayer.bias,
+        z = ag.TCDense.apply(act, self, mode, flatten(x), il.xlayer.weight, il.xlayer.bias,
                              flatten(v), il.vlayer.weight, il.vlayer.bias)
         for layer in self.hidden_layers:
-            z = ag.TCDense.apply(act, self, z, layer.weight, layer.bias)
+            z = ag.TCDense.apply(act, self, mode, z, layer.weight, layer.bias)
         return z
 
     def hidden(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
         """everything in front of the three output heads (network.py:536-545)"""
-        if self.dense_input() and self.tensor_core_dense(*inputs):
-            z = self._hidden_tc(inputs)
+        mode = self.tensor_core_dense(*inputs) if self.dense_input() else None
+        if mode is not None:
+            z = self._hidden_tc(inputs, mode)
         else:
             z = self.input_layer(inputs)
             for layer in self.hidden_layers:
@@ -338,10 +360,11 @@ class LeapfrogLayer(nn.Module):
     def hidden_tail(self, z: Tensor) -> Tensor:
         """`hidden` from the output of the input layer on (network.py:538-545): the remaining hidden Linears,
         dropout, batch norm"""
-        if self.hidden_layers and self.tensor_core_dense(z):
+        mode = self.tensor_core_dense(z) if self.hidden_layers else None
+        if mode is not None:
             from ... import autograd as ag
             for layer in self.hidden_layers:
-                z = ag.TCDense.apply(self.input_activation_name(), self, z, layer.weight, layer.bias)
+                z = ag.TCDense.apply(self.input_activation_name(), self, mode, z, layer.weight, layer.bias)
         else:
             for layer in self.hidden_layers:
                 z = self.activation_fn(layer(z))
@@ -387,12 +410,13 @@ class LeapfrogLayer(nn.Module):
 
     def heads(self, z: Tensor) -> tuple[Tensor, Tensor, Tensor]:
         """network.py:546-548"""
-        if self.tensor_core_dense(z):
+        mode = self.tensor_core_dense(z)
+        if mode is not None:
             from ... import autograd as ag
-            s = self.nw.s * (self.scale.coeff.exp() * ag.TCDense.apply('tanh', self, z, self.scale.layer.weight,
+            s = self.nw.s * (self.scale.coeff.exp() * ag.TCDense.apply('tanh', self, mode, z, self.scale.layer.weight,
                                                                        self.scale.layer.bias))
-            t = self.nw.t * ag.TCDense.apply(None, self, z, self.transl.weight, self.transl.bias)
-            q = self.nw.q * (self.transf.coeff.exp() * ag.TCDense.apply('tanh', self, z, self.transf.layer.weight,
+            t = self.nw.t * ag.TCDense.apply(None, self, mode, z, self.transl.weight, self.transl.bias)
+            q = self.nw.q * (self.transf.coeff.exp() * ag.TCDense.apply('tanh', self, mode, z, self.transf.layer.weight,
                                                                         self.transf.layer.bias))
             return s, t, q
         s = self.nw.s * self.scale(z)

@@ -782,7 +782,7 @@ def _r8(n: int) -> int:
 
 def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmajor: bool, b_kmajor: bool, *,
               out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bias: Optional[Tensor] = None,
-              act: Optional[str] = None, accumulate: bool = False, splits: int = 0) -> Tensor:
+              act: Optional[str] = None, accumulate: bool = False, splits: int = 0, seg_inner: bool = False) -> Tensor:
     """D[m, n] = act(sum_seg sum_k A_seg(m, k) B_seg(n, k) + bias[n]) on the tensor cores (bf16 in, fp32 accumulate).
 
     a / b: one matrix or a list of up to 32 same-shaped matrices (segments summed in one launch).  K-major
@@ -802,7 +802,10 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
     M, K = (int(d) for d in (a_list[0].shape if a_kmajor else a_list[0].shape[::-1]))
     N, Kb = (int(d) for d in (b_list[0].shape if b_kmajor else b_list[0].shape[::-1]))
     if Kb != K:
-        raise L2BError(f'gemm_bf16: contraction lengths differ ({K} vs {Kb})')
+        # one side may carry the zero padding of a previous call (a sliced fp32 result re-split to a multiple of 8)
+        if _r8(Kb) != _r8(K):
+            raise L2BError(f'gemm_bf16: contraction lengths differ ({K} vs {Kb})')
+        K = max(K, Kb)
     Kp = _r8(K) if (a_kmajor or b_kmajor) else K
     Mp = M if a_kmajor else _r8(M)
     Np = _r8(N)
@@ -834,7 +837,7 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
     ap = (c_void_p * len(a_list))(*[t.data_ptr() for t in a_list])
     bp = (c_void_p * len(b_list))(*[t.data_ptr() for t in b_list])
     call('l2b_gemm_bf16', ap, int(a_list[0].stride(0)), int(a_kmajor), bp, int(b_list[0].stride(0)), int(b_kmajor),
-         len(a_list), Mp, Np, Kp, _ptr(dst), L2B_BF16 if dst.dtype == torch.bfloat16 else L2B_F32,
+         len(a_list), int(seg_inner), Mp, Np, Kp, _ptr(dst), L2B_BF16 if dst.dtype == torch.bfloat16 else L2B_F32,
          int(dst.stride(0)), int(accumulate), _ptr(bias), _ACT_CODES[act], splits, _ptr(ws), nws, _stream())
     if direct:
         return out
@@ -842,6 +845,48 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
     if out is not None:
         out.copy_(res)
         return out
+    return res
+
+
+def split_bf16x3(x: Tensor) -> Tensor:
+    """x [R, C] float32 -> [3, R, C8] bfloat16 with x = x1 + x2 + x3 (C8 = C rounded up to a multiple of 8, zero
+    padded): the operands of the fp32-accurate GEMM `gemm_f32`"""
+    _need_cuda(x)
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise L2BError(f'split_bf16x3 expects a 2-D float32 matrix (got {x.dtype}, {tuple(x.shape)})')
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    R, C = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((3, R, _r8(C)), dtype=torch.bfloat16, device=x.device)
+    call('l2b_split_bf16x3', _ptr(x), R, C, int(x.stride(0)), _ptr(out), int(out.shape[2]), _stream())
+    return out
+
+
+# (a_i, b_j) pairs with i + j <= 4, smallest contributions first
+_X3_PAIRS = ((2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0))
+
+
+def gemm_f32(a3: Sequence[Tensor] | Tensor, b3: Sequence[Tensor] | Tensor, a_kmajor: bool, b_kmajor: bool, *,
+             out: Optional[Tensor] = None, bias: Optional[Tensor] = None, act: Optional[str] = None,
+             accumulate: bool = False) -> Tensor:
+    """fp32-accurate D = act(sum_u A_u B_u^T + bias) on the bf16 tensor cores: every operand comes as its bf16x3 split
+    (`split_bf16x3`, [3, R, C8]); a3 / b3 may be lists (the updates whose dW share a weight matrix).  Six products per
+    pair, at most 30 segments per launch (the rest accumulates in further launches)."""
+    a_list = [a3] if isinstance(a3, Tensor) else list(a3)
+    b_list = [b3] if isinstance(b3, Tensor) else list(b3)
+    if len(a_list) > 5 and (act is not None or bias is not None):
+        raise L2BError('gemm_f32: bias / activation need all segments in one launch (at most 5 operand pairs)')
+    res = out
+    for i in range(0, len(a_list), 5):
+        segs_a, segs_b = [], []
+        for a_, b_ in zip(a_list[i:i + 5], b_list[i:i + 5]):
+            for ia, ib in _X3_PAIRS:
+                segs_a.append(a_[ia])
+                segs_b.append(b_[ib])
+        last = i + 5 >= len(a_list)
+        res = gemm_bf16(segs_a, segs_b, a_kmajor, b_kmajor, out=res, out_dtype=torch.float32,
+                        bias=bias if last else None, act=act if last else None, accumulate=accumulate or i > 0,
+                        seg_inner=True)
     return res
 
 

@@ -25,6 +25,44 @@ def _net(xshape, units, act='tanh', seed=0):
 
 
 @pytest.mark.parametrize('act', ['tanh', 'relu', 'swish', 'leaky_relu', 'elu'])
+@pytest.mark.parametrize('units', [(64,), (20, 12)])
+def test_tcdense_fp32_network_matches_torch_fp32(act, units):
+    """fp32 nets without autocast (the reference's default precision): TCDense in 'x3' mode against torch's fp32
+    Linear + autograd, values and every gradient at fp32 accuracy"""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        nb, shape = 6, (2, 4, 2, 3)
+        xshape = (nb, 4, *shape, 3, 3)
+        net = _net(xshape, units, act=act, seed=7)
+        g = torch.Generator(device='cpu').manual_seed(8)
+        x0 = torch.randn(nb, 4, *shape, 8, generator=g).to(DEV)
+        f0 = torch.randn(nb, 4, *shape, 8, generator=g).to(DEV)
+        ws = [torch.randn(nb, net.xdim, generator=g).to(DEV) for _ in range(3)]
+        res = {}
+        for mode in ('never', 'auto'):
+            net.tc_dense = mode
+            net.zero_grad(set_to_none=True)
+            x, f = x0.clone().requires_grad_(True), f0.clone().requires_grad_(True)
+            assert net.tensor_core_dense(x, f) == (None if mode == 'never' else 'x3')
+            s, t, q = net((x, f))
+            loss = (s * ws[0]).sum() + (t * ws[1]).sum() + (q * ws[2]).sum()
+            loss.backward()
+            res[mode] = ([o.detach() for o in (s, t, q)], x.grad, f.grad,
+                         {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None})
+        a, b = res['auto'], res['never']
+        for o1, o0 in zip(a[0], b[0]):
+            assert o1.dtype == torch.float32 and float((o1 - o0).abs().max()) <= 2e-5 * max(1e-3, float(o0.abs().max()))
+        for k in (1, 2):
+            assert float((a[k] - b[k]).abs().max()) <= 5e-5 * max(1e-6, float(b[k].abs().max()))
+        assert set(a[3]) == set(b[3]) and len(a[3]) >= 10
+        for n_, g0 in b[3].items():
+            assert float((a[3][n_] - g0).abs().max()) <= 5e-5 * max(1e-6, float(g0.abs().max())), n_
+    finally:
+        torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('act', ['tanh', 'relu', 'swish', 'leaky_relu', 'elu'])
 @pytest.mark.parametrize('units', [(64,), (48, 32)])
 def test_tcdense_network_matches_torch_autocast(act, units):
     old = torch.get_default_dtype()

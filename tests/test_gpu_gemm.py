@@ -130,3 +130,28 @@ def test_gemm_rejects_bad_arguments():
         ops.gemm_bf16(a.float(), a.float(), True, True)       # not bf16
     with pytest.raises(L2BError):
         ops.gemm_bf16(a.cpu(), a.cpu(), True, True)           # no CPU fallback
+
+
+@pytest.mark.parametrize('M,N,K,a_k,b_k,npair', [
+    (32, 256, 512, True, True, 1), (32, 64, 4096, True, True, 2), (40, 72, 200, True, False, 1),
+    (256, 136, 32, False, False, 7), (5, 12, 20, True, True, 1), (130, 40, 24, False, True, 1),
+])
+def test_fp32_accurate_gemm_from_bf16x3_splits(M, N, K, a_k, b_k, npair):
+    """gemm_f32: six bf16 products per operand pair reproduce an fp32 GEMM (relative error ~1e-6 of the row scale)"""
+    from l2hmc_b200 import ops
+    g = torch.Generator(device='cpu').manual_seed(31)
+    a = [torch.randn((M, K) if a_k else (K, M), generator=g).to(DEV) for _ in range(npair)]
+    b = [torch.randn((N, K) if b_k else (K, N), generator=g).to(DEV) for _ in range(npair)]
+    for t in a + b:
+        s3 = ops.split_bf16x3(t)
+        rec = s3.double().sum(0)[:, :t.shape[1]]
+        assert float((rec - t.double()).abs().max()) <= 2.0 ** -22 * float(t.abs().max())
+        assert float(s3[:, :, t.shape[1]:].abs().max() if s3.shape[2] > t.shape[1] else 0.0) == 0.0
+    want = sum((x.double() if a_k else x.double().t()) @ (y.double() if b_k else y.double().t()).t() for x, y in zip(a, b))
+    got = ops.gemm_f32([ops.split_bf16x3(t) for t in a], [ops.split_bf16x3(t) for t in b], a_k, b_k)
+    got = got[:M, :N]
+    scale = float(want.abs().max())
+    assert float((got.double() - want).abs().max()) <= 4e-6 * scale
+    # an fp32 cuBLAS GEMM of the same operands is no closer
+    lib = sum((x if a_k else x.t()) @ (y if b_k else y.t()).t() for x, y in zip(a, b))
+    assert float((got.double() - want).abs().max()) <= 8 * float((lib.double() - want).abs().max()) + 1e-7 * scale
