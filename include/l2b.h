@@ -312,6 +312,30 @@ int l2b_split_bf16x3(const float* x, long long rows, long long cols, long long l
                      void* stream);
 
 /* ------------------------------------------------------------------------ */
+/* U(1) xnet convolution stack                                                */
+/* ------------------------------------------------------------------------ */
+/* ConvStack (network/pytorch/network.py:240-346): blocks of PeriodicPadding(n - 1) (:151-172: n - 1 wrapped rows /
+ * columns on BOTH sides) + Conv2d(f, n), MaxPool2d after every second block, activation.  A block is
+ *     out[(b, oh, ow)][co] = sum_k col[(b, oh, ow)][k] W[co][k] + bias[co],   OH = H + n - 1,  k = (ci, kh, kw),
+ *     col[(b, oh, ow)][(ci, kh, kw)] = in[b, ci, (oh + kh - n + 1) mod H, (ow + kw - n + 1) mod W]
+ * i.e. l2b_gemm_bf16 on the gathered matrix `col` and Conv2d's own weight viewed as [Cout, Cin n^2]; the output is
+ * the next block's input in NHWC.  l2b_conv_im2col writes col[planes][nb OH OW][K8] bf16 (K8 = Cin n^2 rounded up
+ * to a multiple of 8, zero padded; planes = 1: bf16 nets, 3: the bf16x3 split of fp32 nets) from an input with
+ * element strides (batch, channel, row, column) -- NCHW for the network input, NHWC between blocks.
+ * l2b_conv_col2im is its adjoint (dcol [nb OH OW][ldc] f32 / bf16 -> din f32 with free output strides), a gather
+ * with a fixed summation order.  l2b_pool_act = MaxPool2d(pool) (floor, first maximum wins as in ATen) followed by
+ * the activation (codes as l2b_su3_input_layer) on NHWC; idx keeps the winning tap, pre the pooled pre-activation
+ * (needed for swish only); l2b_pool_act_bwd scatters gy * act' back (gx is zero-filled first). */
+int l2b_conv_im2col(const void* in, int in_dtype, int nb, int C, int H, int W, int n, const long long strides[4],
+                    void* col, int planes, void* stream);
+int l2b_conv_col2im(const void* dcol, int dcol_dtype, long long ldc, int nb, int C, int H, int W, int n, float* din,
+                    const long long out_strides[4], void* stream);
+int l2b_pool_act(const void* x, int dtype, int nb, int H, int W, int C, int pool, int activation, void* y,
+                 unsigned char* idx, float* pre, void* stream);
+int l2b_pool_act_bwd(const float* gy, const void* y, int dtype, const float* pre, const unsigned char* idx, int nb, int H,
+                     int W, int C, int pool, int activation, float* gx, void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* vnet output heads on the tensor cores (tcgen05), fused with the momentum update */
 /* ------------------------------------------------------------------------ */
 /* The three heads of the vnet LeapfrogLayer (network/pytorch/network.py:536-548:

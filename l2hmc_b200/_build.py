@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libl2b.so'
-SOURCES = ['l2b_capi.cu', 'l2b_su3.cu', 'l2b_u1.cu', 'l2b_vnet.cu', 'l2b_gemm.cu']
+SOURCES = ['l2b_capi.cu', 'l2b_su3.cu', 'l2b_u1.cu', 'l2b_vnet.cu', 'l2b_gemm.cu', 'l2b_conv.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC',

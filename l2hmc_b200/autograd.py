@@ -522,6 +522,90 @@ class TCDense(torch.autograd.Function):
         return (None, None, None, *grads)
 
 
+class ConvPeriodic(torch.autograd.Function):
+    """One block of the U(1) xnet's ConvStack (reference network/pytorch/network.py:296-313): PeriodicPadding(n - 1)
+    + Conv2d(f, n) [+ the activation, when no pooling sits in between] as gather -> tensor-core GEMM
+    (ops.conv_im2col, ops.gemm_bf16 / gemm_f32); output NHWC.  Backward: the gathered matrix is rebuilt from the saved
+    input (it is 25 - 100 x the input's size), dW = g^T col (split-K over the nb OH OW rows), dcol = g W, and the
+    gather's adjoint (ops.conv_col2im)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, nchw, mode, act, owner):
+        n = int(weight.shape[-1])
+        cout = int(weight.shape[0])
+        x3 = mode == 'x3'
+        xd = x.detach()
+        if xd.dtype not in (torch.float32, torch.bfloat16):
+            xd = xd.float()
+        if not x3 and xd.dtype != torch.bfloat16:
+            xd = xd.to(torch.bfloat16)
+        col = ops.conv_im2col(xd, n, nchw, 3 if x3 else 1)
+        fused = None if act == 'swish' else act
+        b_ = None if bias is None else bias.detach().float()
+        if x3:
+            y = ops.gemm_f32(col, owner.weight_split3(weight), True, True, bias=b_, act=fused)
+        else:
+            y = ops.gemm_bf16(col[0], owner.weight_as_bf16(weight), True, True, bias=b_, act=fused)
+        if y.shape[1] != cout:
+            y = y[:, :cout].contiguous()
+        nb = int(x.shape[0])
+        H, W = (int(x.shape[2]), int(x.shape[3])) if nchw else (int(x.shape[1]), int(x.shape[2]))
+        y = y.reshape(nb, H + n - 1, W + n - 1, cout)
+        pre = None
+        if act == 'swish':
+            pre, y = y, torch.nn.functional.silu(y)
+        ctx.cfg = (n, nchw, mode, act, owner)
+        ctx.xmeta = (x.shape, x.dtype)
+        ctx.save_for_backward(xd, weight, bias, y if act is not None else None, pre)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, nchw, mode, act, owner = ctx.cfg
+        xd, weight, bias, y, pre = ctx.saved_tensors
+        x3 = mode == 'x3'
+        cout = int(weight.shape[0])
+        K = int(weight.numel() // cout)
+        g32 = _act_grad(act, y, pre, gy).reshape(-1, cout).contiguous()
+        gx = gw = gb = None
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g = ops.split_bf16x3(g32) if x3 else g32.to(torch.bfloat16)
+        if need_w:
+            col = ops.conv_im2col(xd, n, nchw, 3 if x3 else 1)
+            if x3:
+                gw = ops.gemm_f32(g, col, False, False)
+            else:
+                gw = ops.gemm_bf16(g, col[0], False, False, out_dtype=torch.float32)
+            gw = gw[:cout, :K].reshape(weight.shape).to(weight.dtype)
+            del col
+        if need_x:
+            if x3:
+                dcol = ops.gemm_f32(g, owner.weight_split3(weight), True, False)
+            else:
+                dcol = ops.gemm_bf16(g, owner.weight_as_bf16(weight), True, False, out_dtype=torch.bfloat16)
+            gx = ops.conv_col2im(dcol, xd, n, nchw).to(ctx.xmeta[1]).reshape(ctx.xmeta[0])
+        if need_b and bias is not None:
+            gb = g32.sum(0).to(bias.dtype)
+        return gx, gw, gb, None, None, None, None
+
+
+class PoolAct(torch.autograd.Function):
+    """MaxPool2d(p) followed by the activation (network.py:314-322) on NHWC, one kernel each way"""
+
+    @staticmethod
+    def forward(ctx, x, pool, act):
+        y, idx, pre = ops.pool_act(x.detach(), pool, act)
+        ctx.cfg = (pool, act, x.shape, x.dtype)
+        ctx.save_for_backward(y, idx, pre)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        pool, act, shape, dt = ctx.cfg
+        y, idx, pre = ctx.saved_tensors
+        return ops.pool_act_bwd(gy, y, pre, idx, shape, pool, act).to(dt), None, None
+
+
 class SU3HeadsVUpdate(torch.autograd.Function):
     """(v', logdet) = vupdate(v, F, heads(z); eps, sign) with the three head GEMMs on the
     tensor cores and s, t, q kept on chip (l2b_su3_heads_vupdate, csrc/l2b_vnet.cu).

@@ -146,6 +146,52 @@ def _capture_token() -> int:
     return _STEP_TOKEN[0] if torch.cuda.is_current_stream_capturing() else -1
 
 
+def activation_name(a) -> Optional[str]:
+    """name of an activation module as the fused kernels know it (None: not one of the reference's, network.py:40-46)"""
+    if isinstance(a, nn.Tanh):
+        return 'tanh'
+    if isinstance(a, nn.ReLU):
+        return 'relu'
+    if isinstance(a, nn.SiLU):
+        return 'swish'
+    if isinstance(a, nn.LeakyReLU) and abs(a.negative_slope - 0.01) < 1e-12:
+        return 'leaky_relu'
+    if isinstance(a, nn.ELU) and abs(a.alpha - 1.0) < 1e-12:
+        return 'elu'
+    return None
+
+
+class _WeightImages:
+    """bf16 / bf16x3 images of a module's weight matrices for the tensor-core GEMM, cached per weight version
+    (and, inside a CUDA-graph capture of a training step, per step: `_capture_token`).  Conv weights are viewed as
+    [Cout, Cin n^2]."""
+
+    def weight_as_bf16(self, w: Tensor) -> Tensor:
+        """bf16 copy of a weight matrix (what autocast would re-create on every call), cached per weight version;
+        re-cast once per step inside a CUDA-graph capture of a training step, where the weights change on every replay"""
+        if w.dtype == torch.bfloat16:
+            return w.detach().reshape(w.shape[0], -1)
+        cache = self.__dict__.setdefault('_bf16_weights', {})
+        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
+        hit = cache.get(id(w))
+        if hit is None or hit[0] != key:
+            hit = (key, w.detach().reshape(w.shape[0], -1).to(torch.bfloat16))
+            cache[id(w)] = hit
+        return hit[1]
+
+    def weight_split3(self, w: Tensor) -> Tensor:
+        """bf16x3 split of an fp32 weight matrix ([3, out, in8], ops.split_bf16x3) for the fp32-accurate tensor-core
+        GEMM, cached like `weight_as_bf16`"""
+        from ... import ops
+        cache = self.__dict__.setdefault('_x3_weights', {})
+        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
+        hit = cache.get(id(w))
+        if hit is None or hit[0] != key:
+            hit = (key, ops.split_bf16x3(w.detach().reshape(w.shape[0], -1).float()))
+            cache[id(w)] = hit
+        return hit[1]
+
+
 class PeriodicPadding(nn.Module):
     """wraps `size` on BOTH sides of the last two axes (network.py:151-172)"""
 
@@ -171,7 +217,7 @@ class ScaledTanh(nn.Module):
         return self.coeff.exp() * torch.tanh(self.layer(x))
 
 
-class ConvStack(nn.Module):
+class ConvStack(nn.Module, _WeightImages):
     """network.py:240-346; same `layers` ordering so indices (hence state_dict
     keys) match."""
 
@@ -210,12 +256,78 @@ class ConvStack(nn.Module):
         self.layers.append(nn.LazyLinear(self.xdim))
         self.layers.append(self.activation_fn)
 
+    def tensor_core_mode(self, x: Tensor) -> Optional[str]:
+        """'bf16' (autocast / bf16 parameters) or 'x3' (fp32 parameters, the reference's default precision) when the
+        stack can run on the hand-written path (gather + tensor-core GEMM + pooling kernels, `_forward_tc`), else
+        None: fp64 nets, an activation outside the reference's list, non-square / strided convolutions, lazy layers
+        not yet materialised.  `self.tc_conv`: 'auto' (default) | 'never'"""
+        if getattr(self, 'tc_conv', 'auto') == 'never' or not x.is_cuda or activation_name(self.activation_fn) is None:
+            return None
+        convs = [m for m in self.layers if isinstance(m, nn.Conv2d)]
+        lins = [m for m in self.layers if isinstance(m, nn.Linear)]
+        if not convs or any(isinstance(m, nn.modules.lazy.LazyModuleMixin) for m in convs + lins):
+            return None
+        for c in convs:
+            # (size 1: the reference's PeriodicPadding(0) slices x[:, :, -0:] = all of x and doubles the image)
+            if (c.kernel_size[0] < 2 or c.kernel_size[0] != c.kernel_size[1] or tuple(c.stride) != (1, 1) or tuple(c.dilation) != (1, 1)
+                    or tuple(c.padding) != (0, 0) or c.groups != 1):
+                return None
+        if torch.is_autocast_enabled('cuda'):
+            return 'bf16' if torch.get_autocast_dtype('cuda') == torch.bfloat16 else None
+        dt = convs[0].weight.dtype
+        if dt == torch.bfloat16:
+            return 'bf16'
+        if dt == torch.float32 and x.dtype in (torch.float32, torch.bfloat16):
+            return 'x3'
+        return None
+
+    def _forward_tc(self, x: Tensor, mode: str) -> Tensor:
+        """the same layer list, block by block, on the hand-written kernels; activations travel NHWC"""
+        from ... import autograd as ag
+        act = activation_name(self.activation_fn)
+        layers = list(self.layers)
+        nchw, i = True, 0
+        while i < len(layers):
+            m = layers[i]
+            if isinstance(m, PeriodicPadding):
+                conv = layers[i + 1]
+                assert isinstance(conv, nn.Conv2d) and m.size == conv.kernel_size[0] - 1
+                nxt = layers[i + 2] if i + 2 < len(layers) else None
+                if isinstance(nxt, nn.MaxPool2d):
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, None, self)
+                    p = nxt.kernel_size if isinstance(nxt.kernel_size, int) else nxt.kernel_size[0]
+                    x = ag.PoolAct.apply(x, int(p), act)
+                    i += 4                                   # pad, conv, pool, activation
+                elif nxt is self.activation_fn:
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, act, self)
+                    i += 3
+                else:                                        # the first block: no activation (network.py:296-307)
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, None, self)
+                    i += 2
+                nchw = False
+            elif isinstance(m, nn.Flatten):
+                if not nchw:                                 # the Linear's columns are in NCHW order
+                    x = x.permute(0, 3, 1, 2)
+                x = x.reshape(x.shape[0], -1)
+                i += 1
+            elif isinstance(m, nn.Linear):
+                fused = act if (i + 1 < len(layers) and layers[i + 1] is self.activation_fn) else None
+                x = ag.TCDense.apply(fused, self, mode, x, m.weight, m.bias)
+                i += 2 if fused is not None else 1
+            else:                                            # batch norm
+                x = m(x.float() if mode == 'x3' else x)
+                i += 1
+        return x
+
     def forward(self, x: Tensor) -> Tensor:
         if tuple(x.shape) != tuple(self.xshape):
             try:
                 x = x.reshape(x.shape[0], self.d + 2, self.nt, self.nx)
             except (ValueError, RuntimeError):
                 x = x.reshape((x.shape[0], *self.xshape[1:]))
+        mode = self.tensor_core_mode(x)
+        if mode is not None:
+            return self._forward_tc(x, mode)
         for layer in self.layers:
             x = layer(x)
         return x
@@ -244,7 +356,7 @@ class InputLayer(nn.Module):
         return self.activation_fn(x + v)
 
 
-class LeapfrogLayer(nn.Module):
+class LeapfrogLayer(nn.Module, _WeightImages):
     """network.py:454-551"""
 
     def __init__(self, xshape: Sequence[int], network_config: NetworkConfig,
@@ -274,31 +386,6 @@ class LeapfrogLayer(nn.Module):
         self.nw = net_weight
 
     # ---- dense layers on the tensor-core GEMM (csrc/l2b_gemm.cu) -----------------------------------------------
-    def weight_as_bf16(self, w: Tensor) -> Tensor:
-        """bf16 copy of a weight matrix (what autocast would re-create on every call), cached per weight version;
-        re-cast once per step inside a CUDA-graph capture of a training step, where the weights change on every replay"""
-        if w.dtype == torch.bfloat16:
-            return w.detach()
-        cache = self.__dict__.setdefault('_bf16_weights', {})
-        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
-        hit = cache.get(id(w))
-        if hit is None or hit[0] != key:
-            hit = (key, w.detach().to(torch.bfloat16))
-            cache[id(w)] = hit
-        return hit[1]
-
-    def weight_split3(self, w: Tensor) -> Tensor:
-        """bf16x3 split of an fp32 weight matrix ([3, out, in8], ops.split_bf16x3) for the fp32-accurate tensor-core
-        GEMM, cached like `weight_as_bf16`"""
-        from ... import ops
-        cache = self.__dict__.setdefault('_x3_weights', {})
-        key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
-        hit = cache.get(id(w))
-        if hit is None or hit[0] != key:
-            hit = (key, ops.split_bf16x3(w.detach().float()))
-            cache[id(w)] = hit
-        return hit[1]
-
     def tensor_core_dense(self, *inputs: Tensor) -> Optional[str]:
         """how the dense layers run on the hand-written tensor-core GEMM (l2b_gemm_bf16), or None (library path):
         'bf16' whenever the nets run in bf16 anyway (autocast, BASELINE cfg 5, or bf16 parameters); 'x3' for fp32
@@ -332,7 +419,12 @@ class LeapfrogLayer(nn.Module):
 
     def hidden(self, inputs: tuple[Tensor, Tensor]) -> Tensor:
         """everything in front of the three output heads (network.py:536-545)"""
-        mode = self.tensor_core_dense(*inputs) if self.dense_input() else None
+        mode = self.tensor_core_dense(*inputs)
+        if mode is not None and not self.dense_input():
+            cs = self.input_layer.conv_stack             # U(1) xnet: the conv stack on its own hand-written path
+            mode = mode if cs.tensor_core_mode(inputs[0]) == mode else None
+            if mode is not None:
+                inputs = (cs(inputs[0]), inputs[1])
         if mode is not None:
             z = self._hidden_tc(inputs, mode)
         else:
@@ -376,18 +468,7 @@ class LeapfrogLayer(nn.Module):
 
     def input_activation_name(self) -> Optional[str]:
         """name of the input layer's activation as the fused kernel knows it (None: not one of them)"""
-        a = self.activation_fn
-        if isinstance(a, nn.Tanh):
-            return 'tanh'
-        if isinstance(a, nn.ReLU):
-            return 'relu'
-        if isinstance(a, nn.SiLU):
-            return 'swish'
-        if isinstance(a, nn.LeakyReLU) and abs(a.negative_slope - 0.01) < 1e-12:
-            return 'leaky_relu'
-        if isinstance(a, nn.ELU) and abs(a.alpha - 1.0) < 1e-12:
-            return 'elu'
-        return None
+        return activation_name(self.activation_fn)
 
     def input_pack(self):
         """bf16 K-major image of the two input Linears for the tensor-core input layer (ops.su3_input_layer);

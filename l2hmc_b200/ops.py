@@ -908,6 +908,65 @@ def linear_dw(gy: Tensor, x: Tensor, out: Optional[Tensor] = None, out_dtype: to
 
 
 # ---------------------------------------------------------------------------
+# U(1) xnet convolution stack: periodic-padding gather / its adjoint, pooling + activation (csrc/l2b_conv.cu)
+# ---------------------------------------------------------------------------
+def _strides4(t: Tensor, nchw: bool):
+    """element strides (batch, channel, row, column) of a 4-D activation stored NCHW or NHWC"""
+    sb, s1, s2, s3 = (int(v) for v in t.stride())
+    return (ctypes.c_longlong * 4)(*((sb, s1, s2, s3) if nchw else (sb, s3, s1, s2)))
+
+
+def conv_im2col(x: Tensor, n: int, nchw: bool, planes: int) -> Tensor:
+    """col[planes, nb OH OW, K8] bf16 of a periodic-padding convolution block (see include/l2b.h); x float32 / bf16,
+    [nb, C, H, W] (nchw) or [nb, H, W, C]"""
+    _need_cuda(x)
+    if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
+        raise L2BError(f'conv_im2col expects a 4-D float32 / bfloat16 activation (got {x.dtype}, {tuple(x.shape)})')
+    nb = int(x.shape[0])
+    C, H, W = (int(x.shape[1]), int(x.shape[2]), int(x.shape[3])) if nchw else (int(x.shape[3]), int(x.shape[1]), int(x.shape[2]))
+    OH, OW, K8 = H + n - 1, W + n - 1, _r8(C * n * n)
+    col = torch.empty((planes, nb * OH * OW, K8), dtype=torch.bfloat16, device=x.device)
+    call('l2b_conv_im2col', _ptr(x), _net_dt(x.dtype), nb, C, H, W, int(n), _strides4(x, nchw), _ptr(col), int(planes),
+         _stream())
+    return col
+
+
+def conv_col2im(dcol: Tensor, like: Tensor, n: int, nchw: bool) -> Tensor:
+    """adjoint of conv_im2col: dcol [nb OH OW, ld] float32 / bf16 -> float32 gradient shaped and laid out like `like`"""
+    _need_cuda(dcol)
+    if dcol.dtype not in (torch.float32, torch.bfloat16) or dcol.dim() != 2 or dcol.stride(1) != 1:
+        raise L2BError('conv_col2im expects a row-major 2-D float32 / bfloat16 matrix')
+    nb = int(like.shape[0])
+    C, H, W = (int(like.shape[1]), int(like.shape[2]), int(like.shape[3])) if nchw else (int(like.shape[3]), int(like.shape[1]), int(like.shape[2]))
+    din = torch.empty(like.shape, dtype=torch.float32, device=dcol.device)
+    call('l2b_conv_col2im', _ptr(dcol), _net_dt(dcol.dtype), int(dcol.stride(0)), nb, C, H, W, int(n), _ptr(din),
+         _strides4(din, nchw), _stream())
+    return din
+
+
+def pool_act(x: Tensor, pool: int, act: Optional[str]):
+    """MaxPool2d(pool) + activation on an NHWC activation; returns (y, idx, pre) (pre only for swish)"""
+    _need_cuda(x)
+    x = x.contiguous()
+    nb, H, W, C = (int(v) for v in x.shape)
+    y = torch.empty((nb, H // pool, W // pool, C), dtype=x.dtype, device=x.device)
+    idx = torch.empty(y.shape, dtype=torch.uint8, device=x.device)
+    pre = torch.empty(y.shape, dtype=torch.float32, device=x.device) if act == 'swish' else None
+    call('l2b_pool_act', _ptr(x), _net_dt(x.dtype), nb, H, W, C, int(pool), _ACT_CODES[act], _ptr(y), _ptr(idx), _ptr(pre),
+         _stream())
+    return y, idx, pre
+
+
+def pool_act_bwd(gy: Tensor, y: Tensor, pre: Optional[Tensor], idx: Tensor, in_shape, pool: int, act: Optional[str]) -> Tensor:
+    nb, H, W, C = (int(v) for v in in_shape)
+    gy = gy.to(torch.float32).contiguous()
+    gx = torch.empty((nb, H, W, C), dtype=torch.float32, device=gy.device)
+    call('l2b_pool_act_bwd', _ptr(gy), _ptr(y), _net_dt(y.dtype), _ptr(pre), _ptr(idx), nb, H, W, C, int(pool),
+         _ACT_CODES[act], _ptr(gx), _stream())
+    return gx
+
+
+# ---------------------------------------------------------------------------
 # vnet output heads on the tensor cores, fused with the momentum update
 # ---------------------------------------------------------------------------
 class HeadsPack:
