@@ -533,17 +533,18 @@ class ConvPeriodic(torch.autograd.Function):
     def forward(ctx, x, weight, bias, nchw, mode, act, owner):
         n = int(weight.shape[-1])
         cout = int(weight.shape[0])
-        x3 = mode == 'x3'
+        x3 = mode in ('x3', 'x2')
+        planes = {'x3': 3, 'x2': 2}.get(mode, 1)
         xd = x.detach()
         if xd.dtype not in (torch.float32, torch.bfloat16):
             xd = xd.float()
         if not x3 and xd.dtype != torch.bfloat16:
             xd = xd.to(torch.bfloat16)
-        col = ops.conv_im2col(xd, n, nchw, 3 if x3 else 1)
+        col = ops.conv_im2col(xd, n, nchw, planes)
         fused = None if act == 'swish' else act
         b_ = None if bias is None else bias.detach().float()
         if x3:
-            y = ops.gemm_f32(col, owner.weight_split3(weight), True, True, bias=b_, act=fused)
+            y = ops.gemm_f32(col, owner.weight_split3(weight)[:planes], True, True, bias=b_, act=fused)
         else:
             y = ops.gemm_bf16(col[0], owner.weight_as_bf16(weight), True, True, bias=b_, act=fused)
         if y.shape[1] != cout:
@@ -563,15 +564,16 @@ class ConvPeriodic(torch.autograd.Function):
     def backward(ctx, gy):
         n, nchw, mode, act, owner = ctx.cfg
         xd, weight, bias, y, pre = ctx.saved_tensors
-        x3 = mode == 'x3'
+        x3 = mode in ('x3', 'x2')
+        planes = {'x3': 3, 'x2': 2}.get(mode, 1)
         cout = int(weight.shape[0])
         K = int(weight.numel() // cout)
         g32 = _act_grad(act, y, pre, gy).reshape(-1, cout).contiguous()
         gx = gw = gb = None
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        g = ops.split_bf16x3(g32) if x3 else g32.to(torch.bfloat16)
+        g = ops.split_bf16x3(g32)[:planes] if x3 else g32.to(torch.bfloat16)
         if need_w:
-            col = ops.conv_im2col(xd, n, nchw, 3 if x3 else 1)
+            col = ops.conv_im2col(xd, n, nchw, planes)
             if x3:
                 gw = ops.gemm_f32(g, col, False, False)
             else:
@@ -580,7 +582,7 @@ class ConvPeriodic(torch.autograd.Function):
             del col
         if need_x:
             if x3:
-                dcol = ops.gemm_f32(g, owner.weight_split3(weight), True, False)
+                dcol = ops.gemm_f32(g, owner.weight_split3(weight)[:planes], True, False)
             else:
                 dcol = ops.gemm_bf16(g, owner.weight_as_bf16(weight), True, False, out_dtype=torch.bfloat16)
             gx = ops.conv_col2im(dcol, xd, n, nchw).to(ctx.xmeta[1]).reshape(ctx.xmeta[0])

@@ -40,24 +40,28 @@ __global__ void __launch_bounds__(256) k_im2col_periodic(const TIN* __restrict__
   const long long b = m / ((long long)g.OW * g.OH);
   const int n2 = g.n * g.n;
   __align__(16) __nv_bfloat16 h[NT][8];
+  // (ci, kh, kw) of the first column by division, of the next seven by counting; the wrapped source coordinates lie
+  // in (-H, 2H), so one conditional add / subtract replaces the modulo
+  int ci = k0 / n2, r0 = k0 - ci * n2, kh = r0 / g.n, kw = r0 - kh * g.n;
+  const TIN* src_b = in + b * g.sb;
+  const int oh1 = oh - (g.n - 1), ow1 = ow - (g.n - 1);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int k = k0 + i;
     float v = 0.f;
-    if (k < g.K) {
-      const int ci = k / n2, r = k - ci * n2, kh = r / g.n, kw = r - kh * g.n;
-      int ih = oh + kh - (g.n - 1), iw = ow + kw - (g.n - 1);
-      ih = ((ih % g.H) + g.H) % g.H;
-      iw = ((iw % g.W) + g.W) % g.W;
-      v = ld_f<TIN>(in + b * g.sb + ci * g.sc + ih * g.sh + iw * g.sw);
+    if (k0 + i < g.K) {
+      int ih = oh1 + kh, iw = ow1 + kw;
+      ih += ih < 0 ? g.H : 0; ih -= ih >= g.H ? g.H : 0;
+      iw += iw < 0 ? g.W : 0; iw -= iw >= g.W ? g.W : 0;
+      v = ld_f<TIN>(src_b + ci * g.sc + ih * g.sh + iw * g.sw);
     }
+    if (++kw == g.n) { kw = 0; if (++kh == g.n) { kh = 0; ++ci; } }
     const __nv_bfloat16 a = __float2bfloat16(v);
     h[0][i] = a;
-    if (NT == 3) {
+    if (NT >= 2) {
       const float r1 = v - __bfloat162float(a);
       const __nv_bfloat16 b2 = __float2bfloat16(r1);
       h[1][i] = b2;
-      h[2][i] = __float2bfloat16(r1 - __bfloat162float(b2));
+      if (NT == 3) h[2][i] = __float2bfloat16(r1 - __bfloat162float(b2));
     }
   }
   const size_t plane = (size_t)M * g.K8;
@@ -82,9 +86,11 @@ __global__ void __launch_bounds__(256) k_col2im_periodic(const TG* __restrict__ 
   const long long b = id / ((long long)g.C * g.W * g.H);
   float acc = 0.f;
   for (int kh = 0; kh < g.n; ++kh) {
-    const int oh0 = (((h - kh + g.n - 1) % g.H) + g.H) % g.H;
+    int oh0 = h - kh + g.n - 1;                       // in (-H, 2H): the modulo is one conditional add / subtract
+    oh0 += oh0 < 0 ? g.H : 0; oh0 -= oh0 >= g.H ? g.H : 0;
     for (int kw = 0; kw < g.n; ++kw) {
-      const int ow0 = (((w - kw + g.n - 1) % g.W) + g.W) % g.W;
+      int ow0 = w - kw + g.n - 1;
+      ow0 += ow0 < 0 ? g.W : 0; ow0 -= ow0 >= g.W ? g.W : 0;
       const int k = (ci * g.n + kh) * g.n + kw;
       for (int oh = oh0; oh < g.OH; oh += g.H)
         for (int ow = ow0; ow < g.OW; ow += g.W)
@@ -169,7 +175,7 @@ static int conv_geo(ConvGeo& g, int nb, int C, int H, int W, int n, const long l
 int l2b_conv_im2col(const void* in, int in_dtype, int nb, int C, int H, int W, int n, const long long strides[4],
                     void* col, int planes, void* stream) {
   L2B_REQUIRE(in && col && strides, L2B_ERR_INVALID, "null pointer");
-  L2B_REQUIRE(planes == 1 || planes == 3, L2B_ERR_INVALID, "planes must be 1 (bf16) or 3 (bf16x3)");
+  L2B_REQUIRE(planes >= 1 && planes <= 3, L2B_ERR_INVALID, "planes must be 1 (bf16), 2 (bf16x2) or 3 (bf16x3)");
   L2B_REQUIRE(in_dtype == L2B_F32 || in_dtype == L2B_BF16, L2B_ERR_UNSUPPORTED, "in_dtype must be L2B_F32 or L2B_BF16");
   L2B_REQUIRE(((uintptr_t)col & 15) == 0, L2B_ERR_INVALID, "col must be 16-byte aligned");
   ConvGeo g;
@@ -181,9 +187,11 @@ int l2b_conv_im2col(const void* in, int in_dtype, int nb, int C, int H, int W, i
   __nv_bfloat16* c = (__nv_bfloat16*)col;
   if (in_dtype == L2B_F32) {
     if (planes == 3) k_im2col_periodic<float, 3><<<nblk, 256, 0, st>>>((const float*)in, g, c, M);
+    else if (planes == 2) k_im2col_periodic<float, 2><<<nblk, 256, 0, st>>>((const float*)in, g, c, M);
     else k_im2col_periodic<float, 1><<<nblk, 256, 0, st>>>((const float*)in, g, c, M);
   } else {
     if (planes == 3) k_im2col_periodic<__nv_bfloat16, 3><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)in, g, c, M);
+    else if (planes == 2) k_im2col_periodic<__nv_bfloat16, 2><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)in, g, c, M);
     else k_im2col_periodic<__nv_bfloat16, 1><<<nblk, 256, 0, st>>>((const __nv_bfloat16*)in, g, c, M);
   }
   L2B_LAUNCHED("k_im2col_periodic");

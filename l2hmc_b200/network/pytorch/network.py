@@ -287,6 +287,10 @@ class ConvStack(nn.Module, _WeightImages):
         act = activation_name(self.activation_fn)
         layers = list(self.layers)
         nchw, i = True, 0
+        # `self.conv_precision`: 'fp32' (default: bf16x3 operands, fp32-accurate -- parity with the reference's CPU
+        # path) | 'tf32' (bf16x2 operands: 16 mantissa bits, still above the TF32 cuDNN convolution the reference
+        # itself runs on this GPU; two thirds of the gathered bytes, half the products)
+        cmode = 'x2' if (mode == 'x3' and getattr(self, 'conv_precision', 'fp32') == 'tf32') else mode
         while i < len(layers):
             m = layers[i]
             if isinstance(m, PeriodicPadding):
@@ -294,15 +298,15 @@ class ConvStack(nn.Module, _WeightImages):
                 assert isinstance(conv, nn.Conv2d) and m.size == conv.kernel_size[0] - 1
                 nxt = layers[i + 2] if i + 2 < len(layers) else None
                 if isinstance(nxt, nn.MaxPool2d):
-                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, None, self)
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, cmode, None, self)
                     p = nxt.kernel_size if isinstance(nxt.kernel_size, int) else nxt.kernel_size[0]
                     x = ag.PoolAct.apply(x, int(p), act)
                     i += 4                                   # pad, conv, pool, activation
                 elif nxt is self.activation_fn:
-                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, act, self)
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, cmode, act, self)
                     i += 3
                 else:                                        # the first block: no activation (network.py:296-307)
-                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, mode, None, self)
+                    x = ag.ConvPeriodic.apply(x, conv.weight, conv.bias, nchw, cmode, None, self)
                     i += 2
                 nchw = False
             elif isinstance(m, nn.Flatten):

@@ -862,8 +862,9 @@ def split_bf16x3(x: Tensor) -> Tensor:
     return out
 
 
-# (a_i, b_j) pairs with i + j <= 4, smallest contributions first
+# (a_i, b_j) pairs (0-based planes) with i + j <= planes - 1, smallest contributions first
 _X3_PAIRS = ((2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0))
+_X2_PAIRS = ((1, 0), (0, 1), (0, 0))
 
 
 def gemm_f32(a3: Sequence[Tensor] | Tensor, b3: Sequence[Tensor] | Tensor, a_kmajor: bool, b_kmajor: bool, *,
@@ -876,11 +877,14 @@ def gemm_f32(a3: Sequence[Tensor] | Tensor, b3: Sequence[Tensor] | Tensor, a_kma
     b_list = [b3] if isinstance(b3, Tensor) else list(b3)
     if len(a_list) > 5 and (act is not None or bias is not None):
         raise L2BError('gemm_f32: bias / activation need all segments in one launch (at most 5 operand pairs)')
+    # two planes per operand (bf16x2: 16 mantissa bits, three products) is the TF32-class variant used for the
+    # convolutions on request; three planes (six products) is fp32-accurate
+    pairs = _X3_PAIRS if min(int(a_list[0].shape[0]), int(b_list[0].shape[0])) >= 3 else _X2_PAIRS
     res = out
     for i in range(0, len(a_list), 5):
         segs_a, segs_b = [], []
         for a_, b_ in zip(a_list[i:i + 5], b_list[i:i + 5]):
-            for ia, ib in _X3_PAIRS:
+            for ia, ib in pairs:
                 segs_a.append(a_[ia])
                 segs_b.append(b_[ib])
         last = i + 5 >= len(a_list)

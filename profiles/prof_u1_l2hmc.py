@@ -1,7 +1,7 @@
 """Driver for the U(1) L2HMC path with the reference's DEFAULT experiment config
 (conf/config.yaml: 16x16, N_LF = 8, separate + split networks, conv stack
 [8,16,32,64,128], units [16,16,16,16], dropout 0.2, batch norm, fp32):
-    python profiles/prof_u1_l2hmc.py eval|train|hmc [nb] [reps] [--graph] [--table]
+    [L2B_TC=never] python profiles/prof_u1_l2hmc.py eval|train|hmc [nb] [reps] [--graph] [--table]
 Prints ms per step (CUDA events + wall).  Numbers under a profiler are never reported."""
 import os
 import sys
@@ -41,6 +41,12 @@ fac = NetworkFactory(input_spec=get_input_spec(cfg),
                      net_weights=None)
 lat = LatticeU1(nb, shape)
 dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+if os.environ.get('L2B_TC', 'auto') == 'never':       # A/B: dense / conv layers through torch (cuBLAS / cuDNN)
+    for m_ in dyn.modules():
+        m_.tc_dense = m_.tc_conv = 'never'
+if os.environ.get('L2B_CONV_PRECISION'):                # 'tf32': bf16x2 operands for the convolutions
+    for m_ in dyn.modules():
+        m_.conv_precision = os.environ['L2B_CONV_PRECISION']
 kw = {'cuda_graphs': True} if graph else {}
 tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.01), lr=1e-3, clip_val=1.0, **kw)
 x = lat.random()

@@ -141,3 +141,78 @@ def test_conv_stack_bf16_autocast_is_as_close_to_fp32_as_torch_autocast():
             assert err(ours[2][n_], g0) <= 2.0 * err(lib[2][n_], g0) + 1e-3, n_
     finally:
         torch.set_default_dtype(old)
+
+
+def test_conv_stack_tf32_class_mode():
+    """conv_precision = 'tf32' (bf16x2 operands, 16 mantissa bits): within TF32-class distance of the fp32 stack,
+    closer to it than cuDNN's own TF32 convolution (what the reference runs on this GPU by default)"""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        L = 16
+        cs = _stack((8, 16, 32, 64, 128), (5, 3, 3, 3, 2), (2, 2, 2, 2, 2), 'leaky_relu', T=L, X=L, seed=9)
+        g = torch.Generator(device='cpu').manual_seed(10)
+        x0 = torch.randn(6, 4, L, L, generator=g).to(DEV)
+        cs.tc_conv = 'never'
+        with torch.no_grad():
+            ref = cs(x0)
+            torch.backends.cudnn.allow_tf32 = True
+            lib = cs(x0)
+            torch.backends.cudnn.allow_tf32 = False
+            cs.tc_conv, cs.conv_precision = 'auto', 'tf32'
+            got = cs(x0)
+        e_got = float((got - ref).abs().max() / ref.abs().max())
+        e_lib = float((lib - ref).abs().max() / ref.abs().max())
+        assert e_got <= 2e-4 and e_got <= max(e_lib, 1e-5) * 1.5, (e_got, e_lib)
+    finally:
+        torch.set_default_dtype(old)
+
+
+def test_u1_train_step_launches_no_library_gemm_or_conv():
+    """U(1) L2HMC training with the reference's default conv stack in fp32 (its default precision): every GEMM and
+    every convolution of a training step is one of ours (kernel-name census with torch.profiler)"""
+    from torch.profiler import ProfilerActivity, profile
+    from l2hmc_b200.configs import (ConvolutionConfig, DynamicsConfig, LossConfig, NetworkConfig, get_input_spec)
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    from l2hmc_b200.trainers.pytorch.trainer import Trainer
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        torch.manual_seed(3)
+        np.random.seed(3)
+        nb, shape = 16, [16, 16]
+        cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=2, eps=0.1, eps_hmc=None, use_ncp=True,
+                             verbose=False, eps_fixed=False, use_split_xnets=True, merge_directions=True,
+                             use_separate_networks=True)
+        fac = NetworkFactory(input_spec=get_input_spec(cfg),
+                             network_config=NetworkConfig(units=[16, 16], activation_fn='leaky_relu', dropout_prob=0.0,
+                                                          use_batch_norm=False),
+                             conv_config=ConvolutionConfig(filters=[8, 16, 32, 64, 128], sizes=[5, 3, 3, 3, 2],
+                                                           pool=[2, 2, 2, 2, 2]), net_weights=None)
+        lat = LatticeU1(nb, shape)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+        tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.01), lr=1e-3, clip_val=1.0)
+        x, beta = lat.random(), torch.tensor(4.0)
+        for _ in range(2):
+            xo, m = tr.train_step((x, beta))
+        assert torch.isfinite(m['loss'])
+        torch.cuda.synchronize()
+        try:
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                tr.train_step((x, beta))
+                torch.cuda.synchronize()
+            names = [e.key for e in prof.key_averages() if e.key]
+        except Exception as e:
+            pytest.skip(f'torch.profiler unavailable: {e}')
+        if not names:
+            pytest.skip('profiler returned no kernels')
+        markers = ('nvjet', 'cutlass', 'gemm', 'cublas', 'cudnn', 'conv', 'xmma', 'implicit', 'sm90_', 'sm100_', 'wgrad', 'dgrad')
+        lib = [n for n in names if any(k in n.lower() for k in markers) and 'l2b::' not in n]
+        ours = [n for n in names if 'l2b::' in n]
+        assert any('k_im2col_periodic' in n for n in ours) and any('k_gemm_bf16' in n for n in ours)
+        assert any('k_col2im_periodic' in n for n in ours) and any('k_pool_act' in n for n in ours)
+        assert not lib, lib
+    finally:
+        torch.set_default_dtype(old)
