@@ -216,3 +216,42 @@ def test_u1_train_step_launches_no_library_gemm_or_conv():
         assert not lib, lib
     finally:
         torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('act', ['leaky_relu', 'tanh'])
+def test_xnet_with_conv_stack_matches_the_numpy_oracle(act):
+    """a whole U(1) xnet LeapfrogLayer with the default conv stack in fp32 -- conv blocks, pooling, the input pair,
+    hidden Linears and the three heads, all on the hand-written kernels -- against oracle/network.py (float64 numpy
+    restatement of network.py:240-346, 454-551) on the same weights"""
+    from l2hmc_b200.configs import ConvolutionConfig, NetworkConfig
+    from l2hmc_b200.network.pytorch.network import LeapfrogLayer
+    from oracle import network as onet
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        torch.manual_seed(21)
+        T = X = 16
+        nb = 4
+        conv = dict(filters=[8, 16, 32, 64, 128], sizes=[5, 3, 3, 3, 2], pool=[2, 2, 2, 2, 2])
+        net = LeapfrogLayer((nb, 2, T, X), NetworkConfig(units=[16, 16], activation_fn=act, dropout_prob=0.0,
+                                                         use_batch_norm=False),
+                            conv_config=ConvolutionConfig(**conv)).to(DEV)
+        net.eval()
+        with torch.no_grad():
+            _ = net((torch.zeros(2, 4, T, X, device=DEV), torch.zeros(2, 2 * T * X, device=DEV)))
+            net.scale.coeff.normal_(0, 0.1)
+            net.transf.coeff.normal_(0, 0.1)
+        g = torch.Generator(device='cpu').manual_seed(22)
+        x = torch.randn(nb, 4, T, X, generator=g)
+        v = torch.randn(nb, 2 * T * X, generator=g)
+        assert net.tensor_core_dense(x.to(DEV), v.to(DEV)) == 'x3'
+        assert net.input_layer.conv_stack.tensor_core_mode(x.to(DEV)) == 'x3'
+        with torch.no_grad():
+            s, t, q = net((x.to(DEV), v.to(DEV)))
+        sd = {k: p.detach().double().cpu().numpy() for k, p in net.state_dict().items()}
+        ws, wt, wq = onet.leapfrog_layer(x.double().numpy(), v.double().numpy(), sd, activation=act, conv=conv,
+                                         conv_in_shape=[4, T, X])
+        for got, want in ((s, ws), (t, wt), (q, wq)):
+            assert float(np.abs(got.double().cpu().numpy() - want).max()) <= 5e-5 * max(1e-2, float(np.abs(want).max()))
+    finally:
+        torch.set_default_dtype(old)
