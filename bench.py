@@ -423,9 +423,14 @@ def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: i
                           'frac_of_peak': value / world * gb / 1e9 / ctx.peak, 'peak_GBps': ctx.peak,
                           'peak_kind': ctx.peak_kind},
         }
+        # ---- e2e through the public API with host buffers (before the parity / roofline legs: the reference's own
+        # CUDA path leaves the caching allocator fragmented, which cost the e2e loop 13 ms per step when it ran after)
+        if e2e:
+            res['e2e'] = hmc_e2e(ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, tdt)
         # ---- parity of the timed batch: chain 0's proposal against the oracle, after the timed region ----------
         if parity and su3:
             res['parity'] = parity_of_timed_batch(ctx, x, v, out, beta, eps, nlf, lattice)
+            ctx.free()
         # ---- per-kernel CUDA-event timing of the dominant kernel ------------------------------------------------
         if roofline:
             if su3:
@@ -440,9 +445,6 @@ def hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, thermalise: i
                                    'traffic': None,
                                    'note': 'streaming model 24 B/link-update; actual DRAM traffic is 16 B/link per TRAJECTORY'}
         del out, en
-        # ---- e2e through the public API with host buffers ------------------------------------------------------
-        if e2e:
-            res['e2e'] = hmc_e2e(ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, tdt)
         del x, v, dyn, lat
         ctx.free()
         return res
