@@ -133,6 +133,8 @@ class Trainer:
         xo, metrics = self.dynamics.apply_transition_hmc((xi, beta), eps=eps, nleapfrog=nleapfrog)
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
+        if self.dynamics.config.verbose:      # trainer.py:922-924: plaqs, charges, dQint / dQsin join the metrics
+            metrics.update(self.loss_fn.lattice_metrics(xinit=xi, xout=xo))
         metrics['loss'] = loss
         return xo.detach(), metrics
 
@@ -151,7 +153,33 @@ class Trainer:
         xo, metrics = self.dynamics((xi, beta))
         xp = metrics.pop('mc_states').proposed.x
         metrics['loss'] = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
+        if self.dynamics.config.verbose:      # trainer.py:948-950
+            metrics.update(self.loss_fn.lattice_metrics(xinit=xi, xout=xo))
         return xo.detach(), metrics
+
+    def warmup(self, beta, nsteps: int = 100, tol: float = 1e-5, x: Optional[Tensor] = None,
+               nchains: Optional[int] = None) -> Tensor:
+        """Thermalise configurations with accept / reject HMC steps (trainer.py:1699-1744).  For U(1) with verbose
+        metrics the loop stops early once the plaquette agrees with the exact I1(beta) / I0(beta) to `tol` (summed
+        over chains), as upstream; SU(3) runs all `nsteps`."""
+        self.dynamics.eval()
+        if x is None:
+            x = self.dynamics.lattice.random().to(self.dynamics.device)
+        if nchains is not None:
+            x = x[:nchains]
+        if not isinstance(beta, Tensor):
+            beta = torch.tensor(float(beta))
+        pexact = None
+        if self.dynamics.config.group == 'U1':
+            from ...lattice.u1.pytorch.lattice import plaq_exact
+            pexact = plaq_exact(beta).to(self.dynamics.device)
+        for _ in range(nsteps):
+            x, metrics = self.hmc_step((x, beta))
+            plaqs = metrics.get('plaqs', None)
+            if plaqs is not None and pexact is not None and float((plaqs - pexact).abs().sum()) < tol:
+                return x
+        self.dynamics.train()
+        return x
 
     def train_step(self, inputs):
         """forward, loss, backward, (all-reduce), clip, Adam   (trainer.py:1266-1367)"""

@@ -108,3 +108,34 @@ def test_u1_trainer_steps(default_dtype):
     assert all(np.isfinite(losses))
     x, m = tr.eval_step((x, beta))
     assert m['acc'].shape == (nb,) and float(x.abs().max()) <= np.pi + 1e-5
+
+
+def test_trainer_warmup_thermalises_u1_towards_the_exact_plaquette():
+    """Trainer.warmup (trainer.py:1699-1744): accept / reject HMC from a hot start; the U(1) plaquette approaches
+    I1(beta) / I0(beta); verbose step metrics carry the lattice observables (trainer.py:922-924)"""
+    from l2hmc_b200.configs import DynamicsConfig, LossConfig
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1, plaq_exact
+    from l2hmc_b200.trainers.pytorch.trainer import Trainer
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float32)
+    try:
+        torch.manual_seed(4)
+        np.random.seed(4)
+        nb, shape, beta = 256, [16, 16], 2.0
+        cfg = DynamicsConfig(nchains=nb, group='U1', latvolume=shape, nleapfrog=8, eps=0.1, eps_hmc=0.125, verbose=True)
+        lat = LatticeU1(nb, shape)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=None)
+        tr = Trainer(dyn, LossConfig())
+        x0 = lat.random()
+        p0 = float(lat.plaqs(x0).mean())
+        x = tr.warmup(beta, nsteps=60, x=x0)
+        assert x.shape[0] == nb
+        want = float(plaq_exact(torch.tensor(beta)))
+        p1 = float(lat.plaqs(x.reshape(x0.shape)).mean())
+        assert abs(p0) < 0.05 and abs(p1 - want) < 0.02, (p0, p1, want)
+        assert tr.warmup(beta, nsteps=1, x=x0, nchains=7).shape[0] == 7
+        _, m = tr.hmc_step((x, torch.tensor(beta)))
+        assert {'plaqs', 'intQ', 'sinQ', 'dQint', 'dQsin'} <= set(m)
+    finally:
+        torch.set_default_dtype(old)
