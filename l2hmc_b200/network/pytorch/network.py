@@ -146,6 +146,12 @@ def _capture_token() -> int:
     return _STEP_TOKEN[0] if torch.cuda.is_current_stream_capturing() else -1
 
 
+def _tc_tensor_ok(t: Tensor) -> bool:
+    """tensors the hand-written kernels can take (the CPU test tier swaps this check together with the `ops` entry
+    points, tests/cpu_emulation.py)"""
+    return t.is_cuda
+
+
 def activation_name(a) -> Optional[str]:
     """name of an activation module as the fused kernels know it (None: not one of the reference's, network.py:40-46)"""
     if isinstance(a, nn.Tanh):
@@ -261,7 +267,7 @@ class ConvStack(nn.Module, _WeightImages):
         stack can run on the hand-written path (gather + tensor-core GEMM + pooling kernels, `_forward_tc`), else
         None: fp64 nets, an activation outside the reference's list, non-square / strided convolutions, lazy layers
         not yet materialised.  `self.tc_conv`: 'auto' (default) | 'never'"""
-        if getattr(self, 'tc_conv', 'auto') == 'never' or not x.is_cuda or activation_name(self.activation_fn) is None:
+        if getattr(self, 'tc_conv', 'auto') == 'never' or not _tc_tensor_ok(x) or activation_name(self.activation_fn) is None:
             return None
         convs = [m for m in self.layers if isinstance(m, nn.Conv2d)]
         lins = [m for m in self.layers if isinstance(m, nn.Linear)]
@@ -398,7 +404,7 @@ class LeapfrogLayer(nn.Module, _WeightImages):
         `self.tc_dense`: 'auto' (default) | 'never'"""
         if getattr(self, 'tc_dense', 'auto') == 'never' or self.input_activation_name() is None:
             return None
-        if not all(t.is_cuda for t in inputs):
+        if not all(_tc_tensor_ok(t) for t in inputs):
             return None
         if isinstance(self.input_layer.xlayer, nn.modules.lazy.LazyModuleMixin):
             return None                     # the materialising dummy call (network.py:572-631) goes through torch

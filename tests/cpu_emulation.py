@@ -474,3 +474,112 @@ def u1_host_logic_on_cpu(monkeypatch):
     monkeypatch.setattr(dmod, 'torch', _TorchProxy())
     monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)   # Trainer.train_step asks
     yield
+
+
+# ---------------------------------------------------------------------------
+# stand-ins for the tensor-core GEMM and the conv-stack kernels (csrc/l2b_gemm.cu, l2b_conv.cu): plain CPU torch
+# restatements of what include/l2b.h says they compute, so that the HOST wiring on top of them -- autograd.TCDense /
+# ConvPeriodic / PoolAct, the deferred weight gradients, ConvStack's layer walk, ops.gemm_f32's segment lists --
+# runs on the CPU tier.  bf16 rounding of operands and outputs is reproduced; accumulation is float32.
+# ---------------------------------------------------------------------------
+def _act_cpu(x, act):
+    import torch.nn.functional as F
+    return {None: lambda t: t, 'identity': lambda t: t, 'tanh': torch.tanh, 'relu': torch.relu, 'swish': F.silu,
+            'leaky_relu': lambda t: F.leaky_relu(t, 0.01), 'elu': F.elu}[act](x)
+
+
+def gemm_bf16(a, b, a_kmajor, b_kmajor, *, out=None, out_dtype=torch.bfloat16, bias=None, act=None, accumulate=False,
+              splits=0, seg_inner=False):
+    a_list = [a] if isinstance(a, torch.Tensor) else list(a)
+    b_list = [b] if isinstance(b, torch.Tensor) else list(b)
+    assert len(a_list) == len(b_list) and 1 <= len(a_list) <= 32
+    acc = None
+    for x, y in zip(a_list, b_list):
+        assert x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+        A = x.float() if a_kmajor else x.float().t()
+        B = y.float() if b_kmajor else y.float().t()
+        K = min(A.shape[1], B.shape[1])
+        assert (A.shape[1] + 7) // 8 == (B.shape[1] + 7) // 8, 'contraction lengths differ'
+        assert float(A[:, K:].abs().sum()) == 0.0 and float(B[:, K:].abs().sum()) == 0.0   # only zero padding beyond K
+        d = A[:, :K] @ B[:, :K].t()
+        acc = d if acc is None else acc + d
+    if bias is not None:
+        acc = acc + bias.float().reshape(1, -1)[:, :acc.shape[1]]
+    acc = _act_cpu(acc, act)
+    if out is not None:
+        out.copy_((out.float() + acc if accumulate else acc).to(out.dtype))
+        return out
+    return acc.to(out_dtype)
+
+
+def split_bf16x3(x):
+    assert x.dtype == torch.float32 and x.dim() == 2
+    c8 = (x.shape[1] + 7) // 8 * 8
+    xp = torch.nn.functional.pad(x, (0, c8 - x.shape[1]))
+    a = xp.to(torch.bfloat16)
+    r1 = xp - a.float()
+    b = r1.to(torch.bfloat16)
+    return torch.stack([a, b, (r1 - b.float()).to(torch.bfloat16)])
+
+
+def _im2col_f32(x_nchw, n):
+    size = n - 1
+    xp = torch.cat([x_nchw[:, :, -size:, :], x_nchw, x_nchw[:, :, :size, :]], 2)
+    xp = torch.cat([xp[:, :, :, -size:], xp, xp[:, :, :, :size]], 3)
+    nb, C = x_nchw.shape[0], x_nchw.shape[1]
+    return torch.nn.functional.unfold(xp, n).transpose(1, 2).reshape(-1, C * n * n)
+
+
+def conv_im2col(x, n, nchw, planes):
+    xf = (x if nchw else x.permute(0, 3, 1, 2)).float()
+    col = _im2col_f32(xf, n)
+    s3 = split_bf16x3(col.contiguous())
+    return s3[:planes].contiguous()
+
+
+def conv_col2im(dcol, like, n, nchw):
+    shape = like.shape if nchw else (like.shape[0], like.shape[3], like.shape[1], like.shape[2])
+    K = shape[1] * n * n
+    with torch.enable_grad():                  # called from inside a Function.backward (grad mode off)
+        probe = torch.zeros(shape, dtype=torch.float32, requires_grad=True)
+        col = _im2col_f32(probe, n)
+        (gx,) = torch.autograd.grad(col, probe, dcol.float()[:, :K])
+    return gx if nchw else gx.permute(0, 2, 3, 1).contiguous()
+
+
+def pool_act(x, pool, act):
+    nb, H, W, C = x.shape
+    xn = x.float().permute(0, 3, 1, 2)
+    win = torch.nn.functional.unfold(xn, pool, stride=pool).reshape(nb, C, pool * pool, H // pool, W // pool)
+    best, idx = win.max(2)
+    y = _act_cpu(best, act).permute(0, 2, 3, 1).contiguous().to(x.dtype)
+    return y, idx.permute(0, 2, 3, 1).contiguous().to(torch.uint8), (best.permute(0, 2, 3, 1).contiguous() if act == 'swish' else None)
+
+
+def pool_act_bwd(gy, y, pre, idx, in_shape, pool, act):
+    nb, H, W, C = in_shape
+    yf = y.float()
+    d = {None: lambda: torch.ones_like(yf), 'tanh': lambda: 1 - yf * yf, 'relu': lambda: (yf > 0).float(),
+         'leaky_relu': lambda: torch.where(yf > 0, 1.0, 0.01), 'elu': lambda: torch.where(yf > 0, 1.0, yf + 1.0),
+         'swish': lambda: torch.sigmoid(pre) * (1 + pre * (1 - torch.sigmoid(pre)))}[act]()
+    g = gy.float() * d
+    gx = torch.zeros(nb, H, W, C)
+    PH, PW = H // pool, W // pool
+    ii, jj = idx.long() // pool, idx.long() % pool
+    b_, ph, pw, c = torch.meshgrid(torch.arange(nb), torch.arange(PH), torch.arange(PW), torch.arange(C), indexing='ij')
+    gx[b_, ph * pool + ii, pw * pool + jj, c] = g
+    return gx
+
+
+@contextlib.contextmanager
+def tensor_core_layers_on_cpu(monkeypatch):
+    """the dense / conv layers' tensor-core path (TCDense, ConvPeriodic, PoolAct) on the CPU stand-ins above"""
+    from l2hmc_b200 import ops
+    from l2hmc_b200.network.pytorch import network as net
+    for name in ('gemm_bf16', 'split_bf16x3', 'conv_im2col', 'conv_col2im', 'pool_act', 'pool_act_bwd'):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(ops, '_need_cuda', lambda *ts: None)
+    monkeypatch.setattr(net, '_tc_tensor_ok', lambda t: True)
+    monkeypatch.setattr(net, '_device', lambda: torch.device('cpu'))
+    monkeypatch.setattr(torch.cuda, 'is_current_stream_capturing', lambda: False)
+    yield
