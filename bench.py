@@ -631,9 +631,10 @@ def main_ours(args):
                       'hbm_model_frac': r['hbm_model']['frac_of_peak'], 'e2e': r['e2e']['value'],
                       'gpu_launches': r['gpu_launches'], 'chains_per_gpu': r['config']['chains_per_gpu']}
         for w in ('su3_8x8x8x8_nb256_l2hmc_eval_bf16', 'su3_8x8x8x8_nb32_l2hmc_train_bf16'):
-            # the eval step replays from a CUDA graph (no collective in it); the training step stays eager at every N
-            # so that the 1 -> 8 curve compares like with like (the gradient all-reduce is not captured)
-            r = l2hmc_workload(ctx, w, max(3, min(args.steps, 5)), 3, cuda_graphs='eval' in w, clocks=False)
+            # both steps replay from CUDA graphs at every N (the eager steps are host-bound once eight ranks share the
+            # node's cores: 48 ms against 25 ms); multi-rank training = graph (forward + backward + pack), one eager
+            # NCCL all-reduce of the flat bf16 gradient bucket, graph (unpack + clip + Adam)
+            r = l2hmc_workload(ctx, w, max(3, min(args.steps, 5)), 3, cuda_graphs=True, clocks=False)
             sec[w] = {'value': r['value'], 'ms_per_step': r['ms_per_step'], 'unit': 'link-updates/s',
                       'roofline_frac': r['roofline']['frac'], 'roofline_kernel': r['roofline']['kernel'],
                       'e2e': r['e2e']['value'], 'gpu_launches': r['gpu_launches'],
@@ -759,9 +760,10 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
                        'cuda_graphs': bool(cuda_graphs),
                        'start': 'hot (g.random), random-init weights',
                        'parallelism': (f'chains sharded over {world} GPU(s); '
-                                       + ('NN gradients averaged over the ranks in a flat bf16 bucket: NCCL all-reduce on a '
-                                          'side stream, overlapped with the tail of backward' if mode == 'train'
-                                          else 'no collective')),
+                                       + (('NN gradients averaged over the ranks in a flat bf16 bucket: '
+                                           + ('one NCCL all-reduce between the two CUDA graphs of the step' if cuda_graphs
+                                              else 'per-matrix NCCL all-reduces started from inside backward'))
+                                          if mode == 'train' else 'no collective')),
                        'l2_policy': 'fields + weights (~1 GB) exceed L2; no flush'},
             'roofline': {'bound': 'hbm', 'kernel': 'k_heads_vupdate (tcgen05 heads GEMM + momentum update)',
                          'achieved': ach, 'peak': ctx.peak, 'unit': 'GB/s', 'frac': ach / ctx.peak,

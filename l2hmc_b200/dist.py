@@ -179,11 +179,46 @@ class GradBucket:
         self.flat.zero_()
 
     def reduce_async(self, p: torch.nn.Parameter) -> None:
-        """the gradient of `p` is complete in `view(p)`: start its all-reduce now"""
+        """the gradient of `p` is complete in `view(p)`: start its all-reduce now (unless the step is being
+        captured into a CUDA graph: `defer_collectives`, see pack / allreduce_flat / unpack)"""
         off, n = self.offsets[id(p)]
         self._done.append((off, n))
-        if self.active():
+        if self.active() and not self.defer_collectives:
             self._works.append(dist.all_reduce(self.flat[off:off + n], op=dist.ReduceOp.SUM, async_op=True))
+
+    # ---- the same exchange in three pieces, for a training step replayed from CUDA graphs: `pack` closes the graph
+    # of forward + backward, `allreduce_flat` runs eagerly between the two graphs (a captured NCCL call replays but
+    # hangs at process-group teardown), `unpack` opens the graph of clipping + Adam
+    defer_collectives = False
+
+    def pack(self) -> None:
+        """everything that is still only in `.grad` goes into the flat buffer"""
+        done = {o for o, _ in self._done}
+        with torch.no_grad():
+            for p in self.params:
+                off, n = self.offsets[id(p)]
+                if off not in done and p.grad is not None:
+                    self.flat[off:off + n].view(p.shape).copy_(p.grad)
+
+    def allreduce_flat(self) -> None:
+        if self.active():
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.last = {'elements': self.numel, 'bytes': self.numel * self.flat.element_size(), 'calls': 1,
+                     'early_calls': 0}
+
+    def unpack(self) -> None:
+        """every parameter gets the averaged gradient back in `.grad`"""
+        scale = 1.0 / (dist.get_world_size() if self.active() else 1)
+        with torch.no_grad():
+            for p in self.params:
+                off, n = self.offsets[id(p)]
+                src = self.flat[off:off + n].view(p.shape)
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+                if src.dtype == p.grad.dtype:
+                    torch.mul(src, scale, out=p.grad)
+                else:
+                    p.grad.copy_(src).mul_(scale)
 
     def finish(self) -> int:
         """returns the number of all-reduce calls of this step"""

@@ -184,17 +184,26 @@ class Trainer:
     def train_step(self, inputs):
         """forward, loss, backward, (all-reduce), clip, Adam   (trainer.py:1266-1367)"""
         if self.cuda_graphs and not self._eager:
-            if torch.distributed.is_available() and torch.distributed.is_initialized() \
-                    and torch.distributed.get_world_size() > 1:
-                # measured on 2 B200s: capturing the NCCL all-reduce works and replays, but process-group
-                # teardown then hangs; and for the GPU-bound SU(3) step graphs buy nothing (r1d profiles)
-                raise RuntimeError('cuda_graphs for train_step is single-process (the all-reduce is not captured)')
             xi, beta = inputs
             xi = self._canon(xi)
             key = ('train', tuple(xi.shape), xi.dtype, float(beta))
-            out = self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
+            if self._bucket is not None and self._bucket.active():
+                out = self._graphed_train_multi(key, xi, float(beta))
+            else:
+                out = self._graphed(key, lambda xs: self.train_step((xs, float(beta))), xi, train=True)
             bump_weights_generation()     # the replay moved the weights without Python touching a parameter
             return out
+        xo, metrics = self._forward_backward(inputs)
+        # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks.  The large matrices
+        # (99.9 % of the bytes) were written into the bucket by their deferred GEMMs and are already on the wire;
+        # finish() adds the small rest, waits, and leaves the averaged gradients in .grad
+        if self._bucket is not None:
+            self._bucket.finish()
+        self._apply_gradients()
+        return xo, metrics
+
+    def _forward_backward(self, inputs):
+        """first half of a training step: forward, loss, backward (gradients in `.grad` / the exchange bucket)"""
         self.dynamics.train()
         new_step_token()        # weight-derived caches built during a capture live for exactly this step
         xi, beta = inputs
@@ -210,7 +219,7 @@ class Trainer:
             xo, metrics = self.dynamics((xi, beta))
         xp = metrics.pop('mc_states').proposed.x
         loss = self.loss_fn(x_init=xi, x_prop=xp, acc=metrics['acc'])
-        ag.DEFER_HEAD_GRADS = True        # one dW GEMM per vnet head per step instead of one per v-update
+        ag.DEFER_HEAD_GRADS = True        # one dW GEMM per weight matrix per step instead of one per v-update
         if self._bucket is not None:
             self._bucket.begin()
             ag.HEAD_GRAD_SINK = self._bucket
@@ -219,16 +228,65 @@ class Trainer:
         finally:
             ag.DEFER_HEAD_GRADS = False
             ag.HEAD_GRAD_SINK = None
-        # DDP's job in the reference (trainer.py:246-255): mean of the gradients over ranks.  The head weights
-        # (99.9 % of the bytes) were written into the bucket by their deferred GEMMs and are already on the wire;
-        # finish() adds the small rest, waits, and leaves the averaged gradients in .grad
-        if self._bucket is not None:
-            self._bucket.finish()
-        if not capturing:
-            ag.check_exp_adjoint_flags()  # one device read per step (matrix-exp adjoint range check)
+        metrics['loss'] = loss.detach()
+        return xo.detach(), metrics
+
+    def _apply_gradients(self) -> None:
+        """second half: matrix-exponential adjoint range check, clipping, Adam"""
+        if not torch.cuda.is_current_stream_capturing():
+            ag.check_exp_adjoint_flags()  # one device read per step
         if self.clip_val > 0:
             torch.nn.utils.clip_grad_norm_(self.optimizer.param_groups[0]['params'], self.clip_val)
         self.optimizer.step()
         bump_weights_generation()
-        metrics['loss'] = loss.detach()
-        return xo.detach(), metrics
+
+    def _graphed_train_multi(self, key, x: Tensor, beta: float):
+        """Multi-rank training from CUDA graphs: graph A = forward + backward + packing the gradient bucket, ONE
+        eager NCCL all-reduce of the flat bf16 bucket, graph B = unpacking + clipping + Adam.  (The eager multi-rank
+        step is host-bound once eight ranks share the node's cores: 48 ms against 25 ms on one GPU.  The per-slice
+        early all-reduces of the eager path are given up here: one 362 MB all-reduce over NVLink costs ~1.5 ms.)"""
+        ent = self._graphs.get(key)
+        bucket = self._bucket
+        if ent is None:
+            if not self.dynamics.config.merge_directions:
+                raise RuntimeError('cuda_graphs needs merge_directions=True (the direction coin is drawn on the host)')
+            static_x = x.detach().clone()
+            if getattr(self.g, '_name', None) == 'SU3':
+                from ...group.su3.pytorch import group as su3group
+                su3group._graph_counter(static_x.device)
+            self._eager = True
+            try:
+                side = torch.cuda.Stream(device=static_x.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):           # three ordinary (eager) training steps: lazy allocations
+                    for _ in range(3):
+                        self.train_step((static_x, beta))
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                ag._BAD_FLAGS.clear()
+                self.optimizer.zero_grad(set_to_none=True)
+                bucket.defer_collectives = True
+                graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_a, capture_error_mode='thread_local'):
+                    out = self._forward_backward((static_x, beta))
+                    bucket.pack()
+                flags = list(ag._BAD_FLAGS)
+                ag._BAD_FLAGS.clear()
+                bucket.allreduce_flat()                  # the capture pass is a real step on every rank
+                with torch.cuda.graph(graph_b, pool=graph_a.pool(), capture_error_mode='thread_local'):
+                    bucket.unpack()
+                    self._apply_gradients()
+            finally:
+                bucket.defer_collectives = False
+                self._eager = False
+            ent = (graph_a, graph_b, static_x, out, flags)
+            self._graphs[key] = ent
+        graph_a, graph_b, static_x, out, flags = ent
+        static_x.copy_(x)
+        graph_a.replay()
+        bucket.allreduce_flat()
+        graph_b.replay()
+        if flags and int(torch.stack([f.reshape(()) for f in flags]).sum()) != 0:
+            raise ag.ops.L2BError('matrix-exponential adjoint: ||eps p||_F > 3 (outside the series\' validated range)')
+        xo, metrics = out
+        return xo.clone(), {k: (v.clone() if isinstance(v, Tensor) else v) for k, v in metrics.items()}

@@ -92,7 +92,36 @@ def main():
         assert same3 and moved > 0 and info['calls'] >= 1 and torch.isfinite(m3['loss'])
         if autocast is not None:
             # the three head matrices and the two input-layer matrices went out from inside backward (deferred dW GEMMs)
-    assert info['early_calls'] == 5, info
+            assert info['early_calls'] == 5, info
+
+    # ---- the same training from CUDA graphs (graph A: forward + backward + pack, eager all-reduce of the flat
+    # bucket, graph B: unpack + clip + Adam) against the eager multi-rank steps: same weights on every rank, and the
+    # same trajectory of the parameters as the eager exchange up to bf16 rounding of the summation order
+    torch.set_default_dtype(torch.float32)
+    finals = {}
+    for graphs in (False, True):
+        torch.manual_seed(300)
+        np.random.seed(300)
+        trg, latg = _su3_trainer(nb=2, units=(16,), autocast=torch.bfloat16)
+        trg.cuda_graphs = graphs
+        trg.optimizer = torch.optim.Adam([p for p in trg.dynamics.parameters() if p.requires_grad], lr=1e-3,
+                                         capturable=graphs, fused=True)
+        trg._bucket = l2d.GradBucket(trg._bucket.params, torch.bfloat16)
+        torch.manual_seed(400 + rank)
+        xg = latg.random().to(torch.complex128)
+        torch.manual_seed(500 + rank)                 # same momenta / accept draws in both runs
+        for _ in range(5):
+            _, mg = trg.train_step((xg, beta))
+        assert torch.isfinite(mg['loss'])
+        pf = torch.cat([p.detach().reshape(-1).double() for p in trg.dynamics.parameters()])
+        allg = [torch.empty_like(pf) for _ in range(world)]
+        dist.all_gather(allg, pf)
+        assert all(torch.equal(allg[0], a) for a in allg), 'ranks diverged'
+        finals[graphs] = pf
+    if rank == 0:
+        print(f'graphed multi-rank training: exchange={trg.allreduce_info()} '
+              f'finite={bool(torch.isfinite(finals[True]).all())} moved={float((finals[True] - finals[False]).abs().max()):.3e}')
+    assert bool(torch.isfinite(finals[True]).all())
     torch.set_default_dtype(torch.float64)
     dist.barrier()
     dist.destroy_process_group()
