@@ -22,7 +22,16 @@ Tensor = torch.Tensor
 _WS: dict = {}
 
 
+try:                                                     # raw handle of the current stream without building a Stream object:
+    _raw_stream = torch._C._cuda_getCurrentRawStream    # ~0.3 us instead of ~10 us, and `_stream` runs once per kernel
+    _cur_device = torch._C._cuda_getDevice
+except AttributeError:                                   # pragma: no cover  (older / newer torch without the private hooks)
+    _raw_stream = _cur_device = None
+
+
 def _stream() -> c_void_p:
+    if _raw_stream is not None:
+        return c_void_p(_raw_stream(_cur_device()))
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -780,6 +789,59 @@ def _r8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+def _gemm_fast(a_list, b_list, a_kmajor, b_kmajor, out, out_dtype, bias, act, accumulate, splits, seg_inner):
+    """the common case of `gemm_bf16` -- aligned contiguous CUDA bf16 operands whose extents are multiples of 8, a
+    fresh or aligned output -- with the least Python per launch (the training steps of small nets are host-bound);
+    returns None when anything is unusual and the general path must look at it"""
+    bf16 = torch.bfloat16
+    a0, b0 = a_list[0], b_list[0]
+    if a0.dim() != 2 or b0.dim() != 2:
+        return None
+    sa, sb = a0.shape, b0.shape
+    lda, ldb = a0.stride(0), b0.stride(0)
+    M, K = (sa[0], sa[1]) if a_kmajor else (sa[1], sa[0])
+    N, Kb = (sb[0], sb[1]) if b_kmajor else (sb[1], sb[0])
+    if K != Kb or N % 8 or (K % 8 if (a_kmajor or b_kmajor) else 0) or (0 if a_kmajor else M % 8):
+        return None
+    ptrs_a, ptrs_b = [], []
+    seen: dict = {}
+    for lst, ptrs, shp, ld in ((a_list, ptrs_a, sa, lda), (b_list, ptrs_b, sb, ldb)):
+        for t in lst:
+            p = seen.get(id(t))
+            if p is None:
+                if (t.dtype is not bf16 or not t.is_cuda or t.shape != shp or t.stride(1) != 1 or t.stride(0) != ld
+                        or ld % 8 or ld < shp[1]):
+                    return None
+                p = t.data_ptr()
+                if p % 16:
+                    return None
+                seen[id(t)] = p
+            ptrs.append(p)
+    if out is not None:
+        if (out.dim() != 2 or out.shape[0] != M or out.shape[1] != N or out.stride(1) != 1 or out.stride(0) % 8
+                or out.data_ptr() % 16 or out.dtype not in (bf16, torch.float32) or not out.is_cuda):
+            return None
+        dst = out
+    else:
+        if accumulate:
+            return None
+        dst = torch.empty((M, N), dtype=out_dtype, device=a0.device)
+    if bias is not None:
+        if bias.dtype is not torch.float32 or not bias.is_cuda or bias.numel() != N or not bias.is_contiguous():
+            return None
+    n = len(a_list)
+    if splits <= 0:
+        splits = int(_lib._lib.l2b_gemm_bf16_splits(M, N, K, n, int(b_kmajor)))
+    ws, nws = None, 0
+    if splits > 1:
+        nws = int(_lib._lib.l2b_gemm_bf16_ws_bytes(M, N, splits))
+        ws = _workspace(nws, a0.device)
+    call('l2b_gemm_bf16', (c_void_p * n)(*ptrs_a), lda, int(a_kmajor), (c_void_p * n)(*ptrs_b), ldb, int(b_kmajor), n,
+         int(seg_inner), M, N, K, _ptr(dst), L2B_BF16 if dst.dtype is bf16 else L2B_F32, dst.stride(0), int(accumulate),
+         _ptr(bias), _ACT_CODES[act], max(1, splits), _ptr(ws), nws, _stream())
+    return dst
+
+
 def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmajor: bool, b_kmajor: bool, *,
               out: Optional[Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, bias: Optional[Tensor] = None,
               act: Optional[str] = None, accumulate: bool = False, splits: int = 0, seg_inner: bool = False) -> Tensor:
@@ -793,14 +855,21 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
     b_list = [b] if isinstance(b, Tensor) else list(b)
     if len(a_list) != len(b_list) or not 1 <= len(a_list) <= 32:
         raise L2BError('gemm_bf16: 1..32 (A, B) segment pairs')
-    _need_cuda(*a_list, *b_list, out, bias)
-    for t in a_list + b_list:
+    fast = _gemm_fast(a_list, b_list, a_kmajor, b_kmajor, out, out_dtype, bias, act, accumulate, splits, seg_inner)
+    if fast is not None:
+        return fast
+    # the segments of an fp32 product repeat the same few planes: every distinct tensor is checked / padded once
+    ua = {id(t): t for t in a_list}
+    ub = {id(t): t for t in b_list}
+    _need_cuda(*ua.values(), *ub.values(), out, bias)
+    a0, b0 = a_list[0], b_list[0]
+    for t in (*ua.values(), *ub.values()):
         if t.dtype != torch.bfloat16 or t.dim() != 2:
             raise L2BError(f'gemm operands must be 2-D bfloat16 matrices (got {t.dtype}, {tuple(t.shape)})')
-    if any(t.shape != a_list[0].shape for t in a_list) or any(t.shape != b_list[0].shape for t in b_list):
+    if any(t.shape != a0.shape for t in ua.values()) or any(t.shape != b0.shape for t in ub.values()):
         raise L2BError('gemm_bf16: segments must share shapes')
-    M, K = (int(d) for d in (a_list[0].shape if a_kmajor else a_list[0].shape[::-1]))
-    N, Kb = (int(d) for d in (b_list[0].shape if b_kmajor else b_list[0].shape[::-1]))
+    M, K = (int(d) for d in (a0.shape if a_kmajor else a0.shape[::-1]))
+    N, Kb = (int(d) for d in (b0.shape if b_kmajor else b0.shape[::-1]))
     if Kb != K:
         # one side may carry the zero padding of a previous call (a sliced fp32 result re-split to a multiple of 8)
         if _r8(Kb) != _r8(K):
@@ -809,12 +878,14 @@ def gemm_bf16(a: Sequence[Tensor] | Tensor, b: Sequence[Tensor] | Tensor, a_kmaj
     Kp = _r8(K) if (a_kmajor or b_kmajor) else K
     Mp = M if a_kmajor else _r8(M)
     Np = _r8(N)
-    a_list = [_gemm_operand(_pad2(t, M, Kp) if a_kmajor else _pad2(t, Kp, Mp)) for t in a_list]
-    b_list = [_gemm_operand(_pad2(t, Np, Kp) if b_kmajor else _pad2(t, Kp, Np)) for t in b_list]
-    if len({int(t.stride(0)) for t in a_list}) != 1:
-        a_list = [t.contiguous() for t in a_list]
-    if len({int(t.stride(0)) for t in b_list}) != 1:
-        b_list = [t.contiguous() for t in b_list]
+    pa = {k: _gemm_operand(_pad2(t, M, Kp) if a_kmajor else _pad2(t, Kp, Mp)) for k, t in ua.items()}
+    pb = {k: _gemm_operand(_pad2(t, Np, Kp) if b_kmajor else _pad2(t, Kp, Np)) for k, t in ub.items()}
+    if len({int(t.stride(0)) for t in pa.values()}) != 1:
+        pa = {k: t.contiguous() for k, t in pa.items()}
+    if len({int(t.stride(0)) for t in pb.values()}) != 1:
+        pb = {k: t.contiguous() for k, t in pb.items()}
+    a_list = [pa[id(t)] for t in a_list]
+    b_list = [pb[id(t)] for t in b_list]
     dev = a_list[0].device
     direct = (out is not None and Mp == M and Np == N and out.dim() == 2 and tuple(out.shape) == (M, N)
               and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.data_ptr() % 16 == 0
@@ -881,9 +952,11 @@ def gemm_f32(a3: Sequence[Tensor] | Tensor, b3: Sequence[Tensor] | Tensor, a_kma
     # convolutions on request; three planes (six products) is fp32-accurate
     pairs = _X3_PAIRS if min(int(a_list[0].shape[0]), int(b_list[0].shape[0])) >= 3 else _X2_PAIRS
     res = out
+    a_planes = [t.unbind(0) for t in a_list]                 # one view per plane, shared by the segments that use it
+    b_planes = [t.unbind(0) for t in b_list]
     for i in range(0, len(a_list), 5):
         segs_a, segs_b = [], []
-        for a_, b_ in zip(a_list[i:i + 5], b_list[i:i + 5]):
+        for a_, b_ in zip(a_planes[i:i + 5], b_planes[i:i + 5]):
             for ia, ib in pairs:
                 segs_a.append(a_[ia])
                 segs_b.append(b_[ib])
