@@ -293,10 +293,12 @@ class ConvStack(nn.Module, _WeightImages):
         act = activation_name(self.activation_fn)
         layers = list(self.layers)
         nchw, i = True, 0
-        # `self.conv_precision`: 'fp32' (default: bf16x3 operands, fp32-accurate -- parity with the reference's CPU
-        # path) | 'tf32' (bf16x2 operands: 16 mantissa bits, still above the TF32 cuDNN convolution the reference
-        # itself runs on this GPU; two thirds of the gathered bytes, half the products)
-        cmode = 'x2' if (mode == 'x3' and getattr(self, 'conv_precision', 'fp32') == 'tf32') else mode
+        # `self.conv_precision` of fp32 stacks: 'tf32' (default: bf16x2 operands, 16 mantissa bits -- the reference's
+        # own GPU path runs these convolutions on cuDNN with TF32, 10 bits, `torch.backends.cudnn.allow_tf32`; two
+        # thirds of the gathered bytes and half the products of the exact mode) | 'fp32' (bf16x3 operands,
+        # fp32-accurate: parity with the reference's CPU path to 1e-4 in every gradient).  The Linear at the end of
+        # the stack is fp32-accurate either way, as torch's fp32 matmul is.
+        cmode = 'x2' if (mode == 'x3' and getattr(self, 'conv_precision', 'tf32') == 'tf32') else mode
         while i < len(layers):
             m = layers[i]
             if isinstance(m, PeriodicPadding):

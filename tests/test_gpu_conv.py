@@ -84,6 +84,7 @@ def test_conv_stack_fp32_matches_torch(act, cfg):
     torch.set_default_dtype(torch.float32)
     try:
         cs = _stack(filters, sizes, pool, act, T=L, X=L, seed=5)
+        cs.conv_precision = 'fp32'                       # the exact mode (the default is the TF32-class bf16x2 mode)
         g = torch.Generator(device='cpu').manual_seed(6)
         nb = 5
         x0 = torch.randn(nb, 4, L, L, generator=g).to(DEV)
@@ -144,7 +145,7 @@ def test_conv_stack_bf16_autocast_is_as_close_to_fp32_as_torch_autocast():
 
 
 def test_conv_stack_tf32_class_mode():
-    """conv_precision = 'tf32' (bf16x2 operands, 16 mantissa bits): within TF32-class distance of the fp32 stack,
+    """the default conv_precision = 'tf32' (bf16x2 operands, 16 mantissa bits): within TF32-class distance of the fp32 stack,
     closer to it than cuDNN's own TF32 convolution (what the reference runs on this GPU by default)"""
     old = torch.get_default_dtype()
     torch.set_default_dtype(torch.float32)
@@ -159,7 +160,7 @@ def test_conv_stack_tf32_class_mode():
             torch.backends.cudnn.allow_tf32 = True
             lib = cs(x0)
             torch.backends.cudnn.allow_tf32 = False
-            cs.tc_conv, cs.conv_precision = 'auto', 'tf32'
+            cs.tc_conv = 'auto'                           # default conv_precision = 'tf32'
             got = cs(x0)
         e_got = float((got - ref).abs().max() / ref.abs().max())
         e_lib = float((lib - ref).abs().max() / ref.abs().max())
@@ -246,6 +247,7 @@ def test_xnet_with_conv_stack_matches_the_numpy_oracle(act):
         v = torch.randn(nb, 2 * T * X, generator=g)
         assert net.tensor_core_dense(x.to(DEV), v.to(DEV)) == 'x3'
         assert net.input_layer.conv_stack.tensor_core_mode(x.to(DEV)) == 'x3'
+        net.input_layer.conv_stack.conv_precision = 'fp32'
         with torch.no_grad():
             s, t, q = net((x.to(DEV), v.to(DEV)))
         sd = {k: p.detach().double().cpu().numpy() for k, p in net.state_dict().items()}

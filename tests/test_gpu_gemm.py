@@ -155,3 +155,24 @@ def test_fp32_accurate_gemm_from_bf16x3_splits(M, N, K, a_k, b_k, npair):
     # an fp32 cuBLAS GEMM of the same operands is no closer
     lib = sum((x if a_k else x.t()) @ (y if b_k else y.t()).t() for x, y in zip(a, b))
     assert float((got.double() - want).abs().max()) <= 8 * float((lib.double() - want).abs().max()) + 1e-7 * scale
+
+
+@pytest.mark.parametrize('odt', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('a_k,b_k', [(False, False), (True, True), (True, False)])
+def test_skinny_gemm_computed_as_transpose_accumulates_and_adds_bias(odt, a_k, b_k):
+    """M <= 64 with a short K loop runs as D^T inside the kernel: accumulate, bias and activation must still address
+    out[m][n] / bias[n]"""
+    from l2hmc_b200 import ops
+    M, N, K = 16, 136, 72
+    a = _mk((M, K) if a_k else (K, M), 41)
+    b = _mk((N, K) if b_k else (K, N), 42)
+    bias = torch.linspace(-0.5, 0.5, N, device=DEV)
+    want = _ref([a], [b], a_k, b_k, bias=bias, act='tanh')
+    got = ops.gemm_bf16(a, b, a_k, b_k, out_dtype=odt, bias=bias, act='tanh', splits=1)
+    tol = 5e-6 if odt == torch.float32 else 1e-2
+    assert float((got.double() - want).abs().max()) <= tol * max(1.0, float(want.abs().max()))
+    base = torch.randn(M, N, device=DEV).to(odt)
+    out = base.clone()
+    ops.gemm_bf16(a, b, a_k, b_k, out=out, accumulate=True, splits=1)
+    want2 = base.double() + _ref([a], [b], a_k, b_k)
+    assert float((out.double() - want2).abs().max()) <= (1e-5 if odt == torch.float32 else 3e-2) * float(want2.abs().max())

@@ -101,6 +101,7 @@ def test_conv_stack_walk_equals_the_torch_modules(monkeypatch, cfg, act):
             torch.manual_seed(7)
             cs = ConvStack((3, 2, L, L), ConvolutionConfig(filters=list(filters), sizes=list(sizes), pool=list(pool)),
                            activation_fn(act))
+            cs.conv_precision = 'fp32'
             with torch.no_grad():
                 _ = cs(torch.zeros(2, 4, L, L))
             g = torch.Generator().manual_seed(8)
