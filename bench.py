@@ -471,6 +471,33 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
     up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     xin = [torch.empty_like(x) for _ in range(NBUF)]
+    # Full duplex or one direction at a time?  On one GPU both directions together move 2 x 45.7 GB/s against 55.6 / 51.7
+    # alone, so duplex wins; with eight ranks behind the VM's shared host path the picture can invert.  One upload and
+    # one download of a field are timed both ways on all ranks at once, and the faster policy runs the timed loop.
+    probe_out = torch.empty_like(x)
+
+    def probe(duplex: bool) -> float:
+        ctx.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        up.wait_stream(main)
+        with torch.cuda.stream(up):
+            xin[0].copy_(xh, non_blocking=True)
+        s_down = down if duplex else up
+        s_down.wait_stream(main)
+        with torch.cuda.stream(s_down):
+            xo_h[0].copy_(probe_out.reshape(xo_h[0].shape), non_blocking=True)
+        main.wait_stream(up)
+        main.wait_stream(down)
+        t1.record(main)
+        ctx.barrier()
+        return ctx.max_over_ranks(t0.elapsed_time(t1))
+    probe(True)
+    ms_duplex, ms_serial = probe(True), probe(False)
+    duplex = ms_duplex <= ms_serial
+    if not duplex:
+        down = up                                          # one copy stream: transfers take turns
+    del probe_out
     xout = [None] * NBUF
     ready = [torch.cuda.Event() for _ in range(NBUF)]
     freed = [torch.cuda.Event() for _ in range(NBUF)]
@@ -531,6 +558,8 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
             'h2d_bytes_per_step': field_bytes, 'd2h_bytes_per_step': field_bytes + acc_h.numel() * acc_h.element_size(),
             'steps': n_e2e, 'ms_per_step': ms / n_e2e,
             'h2d_GBps_per_gpu_all_ranks_copying': field_bytes / (h2d_ms * 1e-3) / 1e9,
+            'copy_policy': 'duplex (two copy streams)' if duplex else 'one direction at a time (one copy stream)',
+            'copy_probe_ms': {'duplex': ms_duplex, 'serial': ms_serial},
             'api': 'Dynamics.apply_transition_hmc((x_host_pinned -> device, beta)); H2D of steps i+1, i+2 and D2H of '
                    'step i-1 (x_out, acc) overlapped with step i: two copy streams, three buffers per direction'}
 
