@@ -378,6 +378,9 @@ size_t l2b_u1_ws_bytes(int nb, int T, int X, int dtype);
 
 /* LatticeU1.wilson_loops (lattice/u1/pytorch/lattice.py:154-159): w[nb, T, X] */
 int l2b_u1_wilson_loops(const void* x, void* w, int nb, int T, int X, int dtype, void* stream);
+/* the reference's 4x4 loop angles (lattice/u1/pytorch/lattice.py:161-186, the sixteen rolled terms in its order;
+ * `plaqs4x4` = mean cos of them, :205-219), w [nb, T, X] -- the caller applies upstream's trailing `.T` */
+int l2b_u1_wilson_loops4x4(const void* x, void* w, int nb, int T, int X, int dtype, void* stream);
 /* LatticeU1._action / plaqs / _sin_charges / _int_charges in one pass
  * (lattice.py:80-86,188-228): obs[nb, 4] = (action, plaq, sinQ, intQ), in `dtype` */
 int l2b_u1_observables(const void* x, double beta, void* obs, int nb, int T, int X, int dtype,

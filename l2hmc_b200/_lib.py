@@ -129,6 +129,7 @@ _SIGS = {
     'l2b_su3_heads_vupdate': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, _P, c_int, _P, _P, _P, c_int, c_int,
                               c_int, _P, c_size_t, _P],
     'l2b_u1_wilson_loops': [_P, _P, c_int, c_int, c_int, c_int, _P],
+    'l2b_u1_wilson_loops4x4': [_P, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_observables': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_force': [_P, c_double, _P, c_int, c_int, c_int, c_int, _P],
     'l2b_u1_hmc_trajectory': [_P, _P, c_double, c_double, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P],

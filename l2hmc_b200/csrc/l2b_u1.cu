@@ -72,6 +72,30 @@ __global__ void __launch_bounds__(256) k_u1_wloops(const T* __restrict__ x, T* _
   if (i < N) w[(size_t)blockIdx.y * N + i] = plaq_angle(x0, x1, i / X, i % X, Tt, X);
 }
 
+// the reference's "4x4 Wilson loop" (lattice/u1/pytorch/lattice.py:161-186), term by term and in its summation order
+// (five x0 links along x at row t, three x1 links up the far side, three x0 links back along row t + 4, five x1 links
+// down the near side -- the roll arguments as upstream has them):
+//   w(t, x) = x0(t,x) + x0(t,x+1) + x0(t,x+2) + x0(t,x+3) + x0(t,x+4) + x1(t+1,x+4) + x1(t+2,x+4) + x1(t+3,x+4)
+//             - x0(t+4,x+3) - x0(t+4,x+2) - x0(t+4,x+1) - x1(t+4,x) - x1(t+3,x) - x1(t+2,x) - x1(t+1,x) - x1(t,x)
+template <typename T>
+__global__ void __launch_bounds__(256) k_u1_wloops4x4(const T* __restrict__ x, T* __restrict__ w, int Tt, int X) {
+  const int N = Tt * X;
+  const T* x0 = x + (size_t)blockIdx.y * 2 * N;
+  const T* x1 = x0 + N;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= N) return;
+  const int t = i / X, xx = i % X;
+  int tr[5], xc[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { tr[k] = ((t + k) % Tt) * X; xc[k] = (xx + k) % X; }
+  T s = x0[tr[0] + xc[0]];
+  s += x0[tr[0] + xc[1]]; s += x0[tr[0] + xc[2]]; s += x0[tr[0] + xc[3]]; s += x0[tr[0] + xc[4]];
+  s += x1[tr[1] + xc[4]]; s += x1[tr[2] + xc[4]]; s += x1[tr[3] + xc[4]];
+  s -= x0[tr[4] + xc[3]]; s -= x0[tr[4] + xc[2]]; s -= x0[tr[4] + xc[1]];
+  s -= x1[tr[4] + xc[0]]; s -= x1[tr[3] + xc[0]]; s -= x1[tr[2] + xc[0]]; s -= x1[tr[1] + xc[0]]; s -= x1[tr[0] + xc[0]];
+  w[(size_t)blockIdx.y * N + i] = s;
+}
+
 // obs[b] = (action, plaq, sinQ, intQ); one block per chain, fixed-order reduction
 template <typename T>
 __global__ void __launch_bounds__(256) k_u1_obs(const T* __restrict__ x, T beta, T* __restrict__ obs, int Tt, int X) {
@@ -797,6 +821,18 @@ int l2b_u1_wilson_loops(const void* x, void* w, int nb, int T, int X, int dtype,
   L2B_DISPATCH_T(dtype, (k_u1_wloops<float><<<grid, 256, 0, st>>>((const float*)x, (float*)w, T, X)),
                  (k_u1_wloops<double><<<grid, 256, 0, st>>>((const double*)x, (double*)w, T, X)));
   L2B_LAUNCHED("k_u1_wloops");
+  return L2B_OK;
+}
+
+int l2b_u1_wilson_loops4x4(const void* x, void* w, int nb, int T, int X, int dtype, void* stream) {
+  if (int rc = check_u1(nb, T, X, dtype)) return rc;
+  L2B_REQUIRE(x && w, L2B_ERR_INVALID, "null pointer");
+  L2B_REQUIRE(nb <= 65535, L2B_ERR_UNSUPPORTED, "nb exceeds grid.y limit");
+  const dim3 grid((T * X + 255) / 256, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  L2B_DISPATCH_T(dtype, (k_u1_wloops4x4<float><<<grid, 256, 0, st>>>((const float*)x, (float*)w, T, X)),
+                 (k_u1_wloops4x4<double><<<grid, 256, 0, st>>>((const double*)x, (double*)w, T, X)));
+  L2B_LAUNCHED("k_u1_wloops4x4");
   return L2B_OK;
 }
 

@@ -122,8 +122,11 @@ class LatticeU1(Lattice):
         return plaq_exact(beta).to(plaqs.device) * torch.ones_like(plaqs) - plaqs
 
     def wilson_loops4x4(self, x: Tensor) -> Tensor:
-        """4x4 loops (lattice.py:161-186); off the integrator path -> plain torch"""
+        """4x4 loops (lattice.py:161-186): `l2b_u1_wilson_loops4x4`; under autograd the same sixteen rolled terms
+        as torch ops"""
         x = self._field(x)
+        if x.is_cuda and not (torch.is_grad_enabled() and x.requires_grad):
+            return ops.u1_wilson_loops4x4(x.detach()).permute(2, 1, 0)        # upstream's `.T` of a 3-D tensor
         xu, xv = x[:, 0], x[:, 1]
         return (
             xu + xu.roll(-1, dims=2) + xu.roll(-2, dims=2) + xu.roll(-3, dims=2) + xu.roll(-4, dims=2)

@@ -409,6 +409,14 @@ def u1_wilson_loops(x: Tensor, shape=None) -> Tensor:
     return w
 
 
+def u1_wilson_loops4x4(x: Tensor, shape=None) -> Tensor:
+    """[nb, T, X] angles of the reference's 4x4 loops (before its trailing `.T`)"""
+    x, nb, T, X = _u1_field(x, shape)
+    w = torch.empty((nb, T, X), dtype=x.dtype, device=x.device)
+    call('l2b_u1_wilson_loops4x4', _ptr(x), _ptr(w), nb, T, X, _dt(x), _stream())
+    return w
+
+
 def u1_observables(x: Tensor, beta: float, shape=None) -> Tensor:
     """[nb, 4] = (action, plaq, sinQ, intQ)"""
     x, nb, T, X = _u1_field(x, shape)

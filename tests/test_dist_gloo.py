@@ -74,6 +74,29 @@ def _worker(rank, world, port, nchains, q):
         ok_bucket &= torch.allclose(ps[2].grad, torch.tensor(2.0 * mean))
         ok_bucket &= torch.allclose(ps[3].grad, torch.full((2, 5), 1.0 / world))
         ok_bucket &= all(pp.grad.dtype == torch.float32 for pp in ps)
+    # the same exchange in the three pieces a CUDA-graph replayed step uses (pack | eager all-reduce | unpack), with
+    # the early per-slice collectives deferred: identical averaged gradients
+    for bdt in (None, torch.bfloat16):
+        bucket = l2d.GradBucket(ps, bdt)
+        bucket.defer_collectives = True
+        bucket.begin()
+        for pp in ps:
+            pp.grad = None
+        bucket.view(ps[0]).copy_(torch.full((4, 3), float(rank + 1)))
+        bucket.reduce_async(ps[0])                                       # recorded only: no collective yet
+        ok_bucket &= len(bucket._works) == 0
+        ps[1].grad = torch.arange(7, dtype=torch.float32) * (rank + 1)
+        ps[2].grad = torch.tensor(2.0 * (rank + 1))
+        if rank == 0:
+            ps[3].grad = torch.ones(2, 5)
+        bucket.pack()
+        bucket.allreduce_flat()
+        bucket.unpack()
+        ok_bucket &= bucket.last['calls'] == 1 and bucket.last['early_calls'] == 0
+        ok_bucket &= torch.allclose(ps[0].grad, torch.full((4, 3), mean))
+        ok_bucket &= torch.allclose(ps[1].grad, torch.arange(7, dtype=torch.float32) * mean)
+        ok_bucket &= torch.allclose(ps[2].grad, torch.tensor(2.0 * mean))
+        ok_bucket &= torch.allclose(ps[3].grad, torch.full((2, 5), 1.0 / world))
     # broadcast_module_state: rank 0's parameters, buffers and extra tensors everywhere
     torch.manual_seed(100 + rank)
     mod = torch.nn.Sequential(torch.nn.Linear(3, 2), torch.nn.BatchNorm1d(2))

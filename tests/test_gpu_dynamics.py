@@ -264,3 +264,45 @@ def test_u1_hmc_beyond_one_block_of_shared_memory_and_zero_steps(default_dtype, 
     same, met0 = dyn.transition_kernel_hmc(st, eps=eps, nleapfrog=0)
     assert torch.equal(same.x.reshape(nb, -1), st.x.reshape(nb, -1)) and torch.equal(same.v, st.v)
     assert torch.equal(met0['acc'], torch.ones_like(met0['acc']))
+
+
+def test_checkpoint_save_load_round_trip(tmp_path):
+    """Dynamics.save / load / save_eps / restore_eps (dynamics.py:544-586): a second Dynamics built from other seeds
+    reproduces the first one's sweep bit for bit after loading its checkpoint; the step sizes survive the .npy files"""
+    from tests._helpers import _su3_trainer
+    from l2hmc_b200.dynamics.pytorch.dynamics import State
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        torch.manual_seed(1)
+        np.random.seed(1)
+        tr1, lat = _su3_trainer(nb=2, units=(8,))
+        torch.manual_seed(2)
+        np.random.seed(1)                                 # same leapfrog masks (numpy), different weights (torch)
+        tr2, _ = _su3_trainer(nb=2, units=(8,))
+        d1, d2 = tr1.dynamics, tr2.dynamics
+        with torch.no_grad():
+            for p in list(d1.xeps) + list(d1.veps):
+                p.mul_(1.37)
+        x = lat.random().to(torch.complex128)
+        v = lat.random_momentum()
+        st = State(x, v, torch.tensor(6.0))
+        d1.eval()
+        d2.eval()
+        with torch.no_grad():
+            a, ma = d1.transition_kernel_fb(st)
+            b0, _ = d2.transition_kernel_fb(st)
+        assert float((a.x - b0.x).abs().max()) > 1e-6            # different weights: different proposal
+        d1.save(tmp_path)
+        d2.load(tmp_path)
+        with torch.no_grad():
+            b, mb = d2.transition_kernel_fb(st)
+        assert torch.equal(a.x, b.x) and torch.equal(a.v, b.v) and torch.equal(ma['acc'], mb['acc'])
+        with torch.no_grad():
+            for p in list(d2.xeps) + list(d2.veps):
+                p.fill_(0.5)
+        d2.restore_eps(tmp_path)
+        for p1, p2 in zip(list(d1.xeps) + list(d1.veps), list(d2.xeps) + list(d2.veps)):
+            assert float((p1 - p2).abs().max()) == 0.0
+    finally:
+        torch.set_default_dtype(old)

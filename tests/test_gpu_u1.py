@@ -180,3 +180,35 @@ def test_fused_u1_sweep_is_as_accurate_as_the_unfused_one():
             assert err['auto'][k] <= 3.0 * err['never'][k] + 1e-6, (k, err)
     finally:
         torch.set_default_dtype(old)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_u1_wilson_loops4x4_kernel_equals_the_reference(dtype):
+    """LatticeU1.wilson_loops4x4 / plaqs4x4 (lattice/u1/pytorch/lattice.py:161-219) on `l2b_u1_wilson_loops4x4`
+    against the reference's own rolled sum (oracle/_ref when it travelled) and our torch restatement of it under
+    autograd; same summation order, so fp32 agrees to the last bit with the torch path"""
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        for nb, T, X in ((5, 8, 8), (3, 6, 10), (2, 16, 16), (2, 5, 7)):
+            lat = LatticeU1(nb, [T, X])
+            g = torch.Generator(device='cpu').manual_seed(7)
+            x = ((torch.rand(nb, 2, T, X, generator=g, dtype=dtype) - 0.5) * 6.2).cuda()
+            got = lat.wilson_loops4x4(x)
+            xg = x.clone().requires_grad_(True)
+            via_torch = lat.wilson_loops4x4(xg)                      # autograd branch: the rolled torch ops
+            assert got.shape == via_torch.shape == (X, T, nb)
+            assert torch.equal(got, via_torch.detach())
+            assert float((lat.plaqs4x4(x) - via_torch.detach().cos().mean((1, 2))).abs().max()) == 0.0
+            from oracle import ref_shim
+            if ref_shim.available():
+                try:
+                    ref = ref_shim.load_reference(dtype)
+                except RuntimeError:                     # one default dtype per process for the reference copy
+                    continue
+                rl = ref.LatticeU1(nb, [T, X])
+                want = rl.wilson_loops4x4(x.cpu())
+                assert float((got.cpu() - want).abs().max()) <= (1e-5 if dtype == torch.float32 else 1e-13)
+    finally:
+        torch.set_default_dtype(old)
