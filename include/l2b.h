@@ -226,15 +226,16 @@ int l2b_su3_force_kick_drift_planar(const void* u_in_planar, void* p_planar, voi
                                     double eps_kick, double eps_drift, double* sums_or_null, int nb,
                                     const int dims[4], int dtype, void* ws, size_t ws_bytes, void* stream);
 
-/* adjoint of l2b_su3_heads_vupdate (network.py:536-548 + dynamics.py:1266-1297), element-wise part (the three small GEMMs of the Linear backward stay library
- * calls): from (s, t, q) as dumped by the forward (stq f32 [3, nb, xdim]) and the cotangents gv_out, glogdet it
- * writes gv, gforce (may be NULL), geps[nb], the cotangents of the heads' PRE-activations gpre [3, nb, xdim] in
- * gpre_dtype (L2B_F32 / L2B_BF16: the dtype of the dz / dW GEMMs) and gss = gs*s, gqq = gq*q (f32 [nb, xdim])
- * whose sums over the chains are the ScaledTanh.coeff gradients.  ws: nb * ceil(xdim/256) doubles. */
+/* adjoint of l2b_su3_heads_vupdate (network.py:536-548 + dynamics.py:1266-1297), element-wise part (the GEMMs of
+ * the Linear backward are l2b_gemm_bf16 calls): from (s, t, q) as dumped by the forward (stq f32 [3, nb, xdim]) and the
+ * cotangents gv_out, glogdet it writes gv, gforce (may be NULL), geps[nb], the cotangents of the heads' PRE-activations
+ * gpre [3, nb, xdim] in gpre_dtype (L2B_F32 / L2B_BF16: the dtype of the dz / dW GEMMs) and their sums over the
+ * chains colsum f32 [5, xdim]: rows 0-2 = the three heads' bias gradients, rows 3, 4 = sum_b gs*s and sum_b gq*q,
+ * the ScaledTanh.coeff gradients.  ws: nb * ceil(xdim/256) doubles. */
 int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq, const float* scale_s,
                               const float* scale_q, float scale_t, double eps, const double* eps_dev, int sign,
                               const void* gv_out, const double* glogdet, void* gv, void* gforce_or_null, void* gpre,
-                              int gpre_dtype, float* gss, float* gqq, double* geps, int nb, int xdim, void* ws,
+                              int gpre_dtype, float* colsum, double* geps, int nb, int xdim, void* ws,
                               size_t ws_bytes, void* stream);
 
 /* L2HMC sweep (Dynamics.transition_kernel_fb, dynamics.py:956-1029) with the state kept in the planar layout

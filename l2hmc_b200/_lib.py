@@ -123,7 +123,7 @@ _SIGS = {
     'l2b_su3_force_kick_drift_planar': [_P, _P, _P, c_double, c_double, c_double, _P, c_int, _DIMS, c_int, _P, c_size_t, _P],
     'l2b_su3_drift_planar': [_P, _P, c_double, c_int, _DIMS, c_int, _P],
     'l2b_set_option': [c_char_p, c_int],
-    'l2b_su3_heads_vupdate_bwd': [_P, _P, _P, _P, _P, c_float, c_double, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P,
+    'l2b_su3_heads_vupdate_bwd': [_P, _P, _P, _P, _P, c_float, c_double, _P, c_int, _P, _P, _P, _P, _P, c_int, _P, _P,
                                   c_int, c_int, _P, c_size_t, _P],
     'l2b_vnet_pack_heads': [_P, _P, _P, c_int, _P, c_int, c_int, _P],
     'l2b_su3_heads_vupdate': [_P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, c_double, _P, c_int, _P, _P, _P, c_int, c_int,

@@ -394,9 +394,12 @@ def _flush_head_grads(net) -> None:
     for k, (w, b_) in enumerate(((ws, bs), (wt, bt), (wq, bq))):
         gs = [p[k] for p in pend]                        # per update: [nb, xdim] pre-activation cotangents
         _weight_grad_segments(w, gs, zs, sink)
-        acc(b_, torch.stack([g.sum(0, dtype=torch.float32) for g in gs]).sum(0))
-    acc(cs, torch.stack([p[4] for p in pend]).sum(0))
-    acc(cq, torch.stack([p[5] for p in pend]).sum(0))
+    # bias and ScaledTanh.coeff gradients: the adjoint kernel's own sums over the chains, summed over the updates
+    col = torch.stack([p[4] for p in pend]).sum(0)       # [5, xdim]
+    for k, b_ in enumerate((bs, bt, bq)):
+        acc(b_, col[k])
+    acc(cs, col[3:4])
+    acc(cq, col[4:5])
 
 
 # ---------------------------------------------------------------------------
@@ -640,11 +643,10 @@ class SU3HeadsVUpdate(torch.autograd.Function):
             cdt = torch.float32
         # one element-wise kernel: gv, gF, d/d eps, the pre-activation cotangents of the three heads in the
         # GEMM dtype, and gs*s / gq*q for the ScaledTanh.coeff gradients
-        gv, gf, gpre, gss, gqq, geps = ops.su3_heads_vupdate_bwd(v.detach(), force.detach(), stq, ctx.pack,
-                                                                 ctx.eps_value, ctx.sign, gout, glogdet, cdt,
-                                                                 want_gforce=ctx.needs_input_grad[2])
+        gv, gf, gpre, colsum, geps = ops.su3_heads_vupdate_bwd(v.detach(), force.detach(), stq, ctx.pack,
+                                                               ctx.eps_value, ctx.sign, gout, glogdet, cdt,
+                                                               want_gforce=ctx.needs_input_grad[2])
         gp = (gpre[0], gpre[1], gpre[2])
-        gcs, gcq = gss.sum(0, keepdim=True), gqq.sum(0, keepdim=True)
         wc = net.head_weights_as(cdt)
         if cdt == torch.bfloat16:
             # dz = sum_heads g_h W_h: one launch, three segments, the weights contracted over their rows (split-K)
@@ -656,7 +658,7 @@ class SU3HeadsVUpdate(torch.autograd.Function):
             if getattr(net, '_pending_head_grads', None) is None:
                 net._pending_head_grads = []
                 torch.autograd.Variable._execution_engine.queue_callback(lambda: _flush_head_grads(net))
-            net._pending_head_grads.append((gp[0], gp[1], gp[2], zc, gcs, gcq))
+            net._pending_head_grads.append((gp[0], gp[1], gp[2], zc, colsum))
             gparams = (None,) * 8
         else:
             need = ctx.needs_input_grad[7:]
@@ -666,10 +668,10 @@ class SU3HeadsVUpdate(torch.autograd.Function):
             else:
                 gw = [(g.t() @ zc).to(w.dtype) if nd else None
                       for g, w, nd in zip(gp, (ws, wt, wq), (need[0], need[3], need[5]))]
-            gb = [g.sum(0, dtype=torch.float32).to(b_.dtype) if nd else None
-                  for g, b_, nd in zip(gp, (bs, bt, bq), (need[1], need[4], need[6]))]
-            gparams = (gw[0], gb[0], gcs.to(cs.dtype) if need[2] else None, gw[1], gb[1], gw[2], gb[2],
-                       gcq.to(cq.dtype) if need[7] else None)
+            gb = [colsum[k].to(b_.dtype) if nd else None
+                  for k, (b_, nd) in enumerate(zip((bs, bt, bq), (need[1], need[4], need[6])))]
+            gparams = (gw[0], gb[0], colsum[3:4].to(cs.dtype) if need[2] else None, gw[1], gb[1], gw[2], gb[2],
+                       colsum[4:5].to(cq.dtype) if need[7] else None)
         return (gz, gv.reshape(v.shape), None if gf is None else gf.reshape(force.shape), _eps_grad(geps, eps), None,
                 None, None, *gparams)
 

@@ -405,50 +405,64 @@ __global__ void __launch_bounds__(256) k_heads_vupdate_bwd(const double2* __rest
                                                            const double2* __restrict__ gout,
                                                            const double* __restrict__ glogdet,
                                                            double2* __restrict__ gv, double2* __restrict__ gf,
-                                                           GP* __restrict__ gpre, float* __restrict__ gss,
-                                                           float* __restrict__ gqq, double* __restrict__ part, int nb,
-                                                           int xdim) {
+                                                           GP* __restrict__ gpre, float* __restrict__ colsum,
+                                                           double* __restrict__ part, int nb, int xdim) {
+  // One thread owns a column j and walks the chains: the five sums over the chains that the parameter gradients need
+  // -- the three heads' bias gradients sum_b gpre_h[b][j] and sum_b gs s, sum_b gq q for the ScaledTanh coefficients --
+  // stay in registers and are written once (colsum [5][xdim]); the first version wrote gs s / gq q as [nb, xdim]
+  // arrays and left five reductions per update to torch.  Chains in a fixed order: deterministic.
   __shared__ double red[8];
   const double eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
-  const int b = blockIdx.y;
   const int j = blockIdx.x * 256 + threadIdx.x;
-  double ge = 0.0;
-  if (j < xdim) {
-    const size_t at = (size_t)b * xdim + j, plane = (size_t)nb * xdim;
-    const double sv = (double)stq[at], tv = (double)stq[plane + at], qv = (double)stq[2 * plane + at];
-    const double2 V = v[at], F = f[at], G = gout[at];
-    const double gl = glogdet ? glogdet[b] : 0.0;
-    const double sg = (double)sign, he = 0.5 * eps;
-    const double lj = sg * eps * sv / 2.0;
-    const double es = exp(lj), eq = exp(eps * qv);
-    const double fr = fma(F.x, eq, tv), fi = F.y * eq;
-    double g_es, g_fr, g_fi;
-    if (sign > 0) {
-      g_es = G.x * V.x + G.y * V.y;
-      g_fr = -he * G.x; g_fi = -he * G.y;
-      ge += -0.5 * (fr * G.x + fi * G.y);
-    } else {
-      g_es = G.x * (V.x + he * fr) + G.y * (V.y + he * fi);
-      g_fr = es * he * G.x; g_fi = es * he * G.y;
-      ge += 0.5 * es * (fr * G.x + fi * G.y);
+  const bool live = j < xdim;
+  const size_t plane = (size_t)nb * xdim;
+  const double as = live ? (double)scale_s[j] : 0.0, aq = live ? (double)scale_q[j] : 0.0;
+  const double sg = (double)sign, he = 0.5 * eps;
+  float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f, cs4 = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    double ge = 0.0;
+    if (live) {
+      const size_t at = (size_t)b * xdim + j;
+      const double sv = (double)stq[at], tv = (double)stq[plane + at], qv = (double)stq[2 * plane + at];
+      const double2 V = v[at], F = f[at], G = gout[at];
+      const double gl = glogdet ? glogdet[b] : 0.0;
+      const double lj = sg * eps * sv / 2.0;
+      const double es = exp(lj), eq = exp(eps * qv);
+      const double fr = fma(F.x, eq, tv), fi = F.y * eq;
+      double g_es, g_fr, g_fi;
+      if (sign > 0) {
+        g_es = G.x * V.x + G.y * V.y;
+        g_fr = -he * G.x; g_fi = -he * G.y;
+        ge += -0.5 * (fr * G.x + fi * G.y);
+      } else {
+        g_es = G.x * (V.x + he * fr) + G.y * (V.y + he * fi);
+        g_fr = es * he * G.x; g_fi = es * he * G.y;
+        ge += 0.5 * es * (fr * G.x + fi * G.y);
+      }
+      gv[at] = make_double2(es * G.x, es * G.y);
+      if (gf != nullptr) gf[at] = make_double2(g_fr * eq, g_fi * eq);
+      const double g_lj = g_es * es + gl;
+      ge += g_lj * sg * sv / 2.0;
+      const double g_eq = g_fr * F.x + g_fi * F.y;
+      ge += g_eq * eq * qv;
+      const double gs = g_lj * sg * eps / 2.0, gt = g_fr, gq = g_eq * eq * eps;
+      const double ths = as != 0.0 ? sv / as : 0.0, thq = aq != 0.0 ? qv / aq : 0.0;
+      const float p0 = (float)(gs * as * (1.0 - ths * ths)), p1 = (float)(gt * (double)scale_t),
+                  p2 = (float)(gq * aq * (1.0 - thq * thq));
+      gpre[at] = to_gp<GP>(p0);
+      gpre[plane + at] = to_gp<GP>(p1);
+      gpre[2 * plane + at] = to_gp<GP>(p2);
+      cs0 += p0; cs1 += p1; cs2 += p2;
+      cs3 += (float)(gs * sv);
+      cs4 += (float)(gq * qv);
     }
-    gv[at] = make_double2(es * G.x, es * G.y);
-    if (gf != nullptr) gf[at] = make_double2(g_fr * eq, g_fi * eq);
-    const double g_lj = g_es * es + gl;
-    ge += g_lj * sg * sv / 2.0;
-    const double g_eq = g_fr * F.x + g_fi * F.y;
-    ge += g_eq * eq * qv;
-    const double gs = g_lj * sg * eps / 2.0, gt = g_fr, gq = g_eq * eq * eps;
-    const double as = (double)scale_s[j], aq = (double)scale_q[j];
-    const double ths = as != 0.0 ? sv / as : 0.0, thq = aq != 0.0 ? qv / aq : 0.0;
-    gpre[at] = to_gp<GP>((float)(gs * as * (1.0 - ths * ths)));
-    gpre[plane + at] = to_gp<GP>((float)(gt * (double)scale_t));
-    gpre[2 * plane + at] = to_gp<GP>((float)(gq * aq * (1.0 - thq * thq)));
-    gss[at] = (float)(gs * sv);
-    gqq[at] = (float)(gq * qv);
+    ge = block_sum<256>(ge, red, threadIdx.x);
+    if (threadIdx.x == 0) part[(size_t)b * gridDim.x + blockIdx.x] = ge;
   }
-  ge = block_sum<256>(ge, red, threadIdx.x);
-  if (threadIdx.x == 0) part[(size_t)b * gridDim.x + blockIdx.x] = ge;
+  if (live) {
+    const size_t xd = (size_t)xdim;
+    colsum[j] = cs0; colsum[xd + j] = cs1; colsum[2 * xd + j] = cs2; colsum[3 * xd + j] = cs3; colsum[4 * xd + j] = cs4;
+  }
 }
 
 // fixed-order sum of the per-tile partials: out[b] = sum_tile part[b][tile]
@@ -818,21 +832,21 @@ int l2b_su3_heads_vupdate_pair(const void* z, const void* packed, const float* b
 int l2b_su3_heads_vupdate_bwd(const void* v, const void* force, const float* stq, const float* scale_s,
                               const float* scale_q, float scale_t, double eps, const double* eps_dev, int sign,
                               const void* gv_out, const double* glogdet, void* gv, void* gforce_or_null, void* gpre,
-                              int gpre_dtype, float* gss, float* gqq, double* geps, int nb, int xdim, void* ws,
+                              int gpre_dtype, float* colsum, double* geps, int nb, int xdim, void* ws,
                               size_t ws_bytes, void* stream) {
-  L2B_REQUIRE(v && force && stq && scale_s && scale_q && gv_out && gv && gpre && gss && gqq && geps, L2B_ERR_INVALID,
+  L2B_REQUIRE(v && force && stq && scale_s && scale_q && gv_out && gv && gpre && colsum && geps, L2B_ERR_INVALID,
               "null pointer");
   L2B_REQUIRE(nb > 0 && xdim > 0 && nb <= 65535, L2B_ERR_INVALID, "nb must be in [1, 65535], xdim positive");
   L2B_REQUIRE(sign == 1 || sign == -1, L2B_ERR_INVALID, "sign must be +1 or -1");
   const int nblk = (xdim + 255) / 256;
   L2B_REQUIRE(ws && ws_bytes >= (size_t)nb * nblk * sizeof(double), L2B_ERR_WORKSPACE, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const dim3 grid(nblk, nb);
+  const dim3 grid(nblk, 1);
   double* part = (double*)ws;
 #define L2B_HVB(GP)                                                                                               \
   k_heads_vupdate_bwd<GP><<<grid, 256, 0, st>>>((const double2*)v, (const double2*)force, stq, scale_s, scale_q,    \
                                                 scale_t, eps, eps_dev, sign, (const double2*)gv_out, glogdet,      \
-                                                (double2*)gv, (double2*)gforce_or_null, (GP*)gpre, gss, gqq, part, \
+                                                (double2*)gv, (double2*)gforce_or_null, (GP*)gpre, colsum, part,  \
                                                 nb, xdim)
   if (gpre_dtype == L2B_F32) L2B_HVB(float);
   else if (gpre_dtype == L2B_BF16) L2B_HVB(__nv_bfloat16);

@@ -1215,7 +1215,8 @@ def u1_input_layer(mode: int, x: Tensor, v: Tensor, w_x: Tensor, b_x: Tensor, w_
 
 def su3_heads_vupdate_bwd(v: Tensor, force: Tensor, stq: Tensor, pack: HeadsPack, eps, sign: int, gv_out: Tensor,
                           glogdet: Optional[Tensor], gpre_dtype: torch.dtype, want_gforce: bool = True):
-    """element-wise adjoint of su3_heads_vupdate -> (gv, gforce, gpre[3, nb, xdim], gss, gqq, geps[nb])"""
+    """element-wise adjoint of su3_heads_vupdate -> (gv, gforce, gpre[3, nb, xdim], colsum[5, xdim], geps[nb]);
+    colsum rows: the three heads' bias gradients, then sum_b gs*s and sum_b gq*q (the ScaledTanh.coeff gradients)"""
     _need_cuda(v, force, stq, gv_out)
     nb, xdim = int(stq.shape[1]), int(stq.shape[2])
     v2, f2 = v.contiguous(), force.contiguous()
@@ -1227,8 +1228,7 @@ def su3_heads_vupdate_bwd(v: Tensor, force: Tensor, stq: Tensor, pack: HeadsPack
     gv = torch.empty_like(v2)
     gf = torch.empty_like(v2) if want_gforce else None
     gpre = torch.empty((3, nb, xdim), dtype=gpre_dtype, device=v.device)
-    gss = torch.empty((nb, xdim), dtype=torch.float32, device=v.device)
-    gqq = torch.empty_like(gss)
+    colsum = torch.empty((5, xdim), dtype=torch.float32, device=v.device)
     geps = torch.empty(nb, dtype=torch.float64, device=v.device)
     nws = nb * ((xdim + 255) // 256) * 8
     ws = _workspace(nws, v.device)
@@ -1236,6 +1236,6 @@ def su3_heads_vupdate_bwd(v: Tensor, force: Tensor, stq: Tensor, pack: HeadsPack
         raise L2BError(f'gpre dtype must be float32 or bfloat16 (got {gpre_dtype})')
     ev, ep, _keep = _eps_args(eps, torch.float64)
     call('l2b_su3_heads_vupdate_bwd', _ptr(v2), _ptr(f2), _ptr(stq), _ptr(pack.scale_s), _ptr(pack.scale_q), pack.scale_t,
-         ev, ep, int(sign), _ptr(go), _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gpre), _net_dt(gpre_dtype), _ptr(gss), _ptr(gqq),
+         ev, ep, int(sign), _ptr(go), _ptr(gl), _ptr(gv), _ptr(gf), _ptr(gpre), _net_dt(gpre_dtype), _ptr(colsum),
          _ptr(geps), nb, xdim, _ptr(ws), nws, _stream())
-    return gv, gf, gpre, gss, gqq, geps
+    return gv, gf, gpre, colsum, geps
