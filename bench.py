@@ -539,7 +539,7 @@ def hmc_e2e(ctx: Ctx, dyn, x, beta, eps, nlf, units_rank, steps, warmup, su3, td
         run(max(1, min(warmup, 2)))
         ctx.barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_e2e = max(steps, 12)                  # pipeline fill (first upload) and drain (last download) amortised
+        n_e2e = max(steps, 24)                  # pipeline fill (first upload) and drain (last download) amortised
         e2.record()
         run(n_e2e)
         e3.record()
@@ -741,6 +741,8 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
         e1.record()
         ctx.barrier()
         launches = _lib.launch_count() - l0
+        if cuda_graphs:       # a replay does not pass through the host-side counter: kernels recorded at capture
+            launches = steps * int(tr.graph_launches.get(mode, 0))
         clk = sampler.stop() if sampler else None
         ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
         value = world * units_rank / (ms * 1e-3)

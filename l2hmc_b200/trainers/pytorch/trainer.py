@@ -12,6 +12,7 @@ from typing import Optional
 
 import torch
 
+from ... import _lib
 from ... import autograd as ag
 from ... import dist as l2dist
 from ...configs import LossConfig
@@ -43,6 +44,9 @@ class Trainer:
         self.autocast_dtype = autocast_dtype
         self.grad_bucket_dtype = grad_bucket_dtype
         self._graphs: dict = {}
+        # kernels of libl2b recorded into each captured step ('hmc' / 'eval' / 'train'): what ONE replay launches
+        # (the host-side launch counter does not move on a replay)
+        self.graph_launches: dict = {}
         self._eager = False            # True while warming up / capturing: step functions run their eager body
         # more than one rank: start from rank 0's weights, buffers and leapfrog masks (what wrapping the model in
         # DDP does in the reference, trainer.py:246-255), and exchange gradients through one flat bucket over the
@@ -95,9 +99,11 @@ class Trainer:
                 if train:
                     self.optimizer.zero_grad(set_to_none=True)
                 graph = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
                 # thread_local: the NCCL watchdog thread may touch the CUDA runtime while we capture
                 with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                     out = fn(static_x)
+                self.graph_launches[key[0]] = _lib.launch_count() - n0
             finally:
                 self._eager = False
             flags = list(ag._BAD_FLAGS)                 # matrix-exp adjoint range flags: static, re-read per replay
@@ -267,6 +273,7 @@ class Trainer:
                 self.optimizer.zero_grad(set_to_none=True)
                 bucket.defer_collectives = True
                 graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
                 with torch.cuda.graph(graph_a, capture_error_mode='thread_local'):
                     out = self._forward_backward((static_x, beta))
                     bucket.pack()
@@ -276,6 +283,7 @@ class Trainer:
                 with torch.cuda.graph(graph_b, pool=graph_a.pool(), capture_error_mode='thread_local'):
                     bucket.unpack()
                     self._apply_gradients()
+                self.graph_launches[key[0]] = _lib.launch_count() - n0
             finally:
                 bucket.defer_collectives = False
                 self._eager = False
