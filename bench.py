@@ -63,6 +63,14 @@ L2HMC_WORKLOADS = {
     'su3_8x8x8x8_nb256_l2hmc_eval_bf16': ('eval', [8, 8, 8, 8], 256, 4, 256, 6.0),
     'su3_8x8x8x8_nb32_l2hmc_train_bf16': ('train', [8, 8, 8, 8], 32, 4, 256, 6.0),
 }
+# BASELINE cfg 1: the reference's own default experiment (conf/config.yaml: U(1) 16x16, 128 chains, N_LF = 8, fp32,
+# separate + split networks, conv stack [8,16,32,64,128] / sizes [5,3,3,3,2] / pool 2, units [16,16,16,16], dropout
+# 0.2, batch norm) -- the one config the CPU arm runs at full size, chain for chain.
+U1_L2HMC_WORKLOADS = {
+    # name: (mode, lattice, chains per GPU, N_LF, beta)
+    'u1_16x16_nb128_l2hmc_eval_f32': ('eval', [16, 16], 128, 8, 4.0),
+    'u1_16x16_nb128_l2hmc_train_f32': ('train', [16, 16], 128, 8, 4.0),
+}
 DEFAULT_WORKLOAD = 'su3_16x16x16x16_nb64_nlf10_c128'
 METRIC = 'link-updates/sec (chains*V*d*Nlf/s)'
 SEED = 9992  # conf/config.yaml:11
@@ -268,6 +276,72 @@ def run_reference_l2hmc(workload: str, steps: int, warmup: int):
     units_ = nb_s * 4 * V * 2 * nlf
     sample = (f'SU3 {"x".join(map(str, lattice))} L2HMC {mode} step, {nb_s} chains, N_LF {nlf}, units [{units}], '
               f'float64 nets + complex128 lattice, torch {torch.__version__} CPU, {cores} threads')
+    return {'value': units_ * steps / dt_s, 'unit': 'link-updates/s', 'cores': cores, 'kind': 'reference',
+            'sample': sample}, dt_s / steps * 1e3
+
+
+def u1_default_configs(mod, nb, lattice, nlf):
+    """the default experiment's dynamics / network / conv configs (conf/config.yaml), built from the config classes
+    of `mod` (ours or the reference's: field-compatible dataclasses)"""
+    cfg = mod.DynamicsConfig(nchains=nb, group='U1', latvolume=lattice, nleapfrog=nlf, eps=0.1, eps_hmc=None,
+                             use_ncp=True, verbose=False, eps_fixed=False, use_split_xnets=True, merge_directions=True,
+                             use_separate_networks=True)
+    ncfg = mod.NetworkConfig(units=[16, 16, 16, 16], activation_fn='leaky_relu', dropout_prob=0.2, use_batch_norm=True)
+    ccfg = mod.ConvolutionConfig(filters=[8, 16, 32, 64, 128], sizes=[5, 3, 3, 3, 2], pool=[2, 2, 2, 2, 2])
+    return cfg, ncfg, ccfg
+
+
+def run_reference_u1_l2hmc(workload: str, steps: int, warmup: int):
+    """BASELINE cfg 1 on the reference itself (unmodified modules under oracle/_ref), host cores, the FULL config:
+    128 chains, `Dynamics.forward` (eval) or forward + LatticeLoss + backward + Adam (train)."""
+    import numpy as np
+    import torch
+    mode, lattice, nb, nlf, beta = U1_L2HMC_WORKLOADS[workload]
+    assert not torch.cuda.is_available(), 'the CPU arm must not see a GPU'
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None, 'oracle/_ref did not travel to this box'
+    ref = ref_shim.load_reference(torch.float32)
+    torch.manual_seed(SEED)
+    np.random.seed(SEED)
+    cfg, ncfg, ccfg = u1_default_configs(ref.cfgs, nb, lattice, nlf)
+    V = lattice[0] * lattice[1]
+    xdim = 2 * V
+    ispec = ref.InputSpec(xshape=cfg.xshape, xnet={'x': [xdim, 2], 'v': [xdim]},     # trainers/trainer.py:292-309
+                          vnet={'x': [xdim], 'v': [xdim]})
+    lat = ref.LatticeU1(nb, lattice)
+    fac = ref.NetworkFactory(input_spec=ispec, network_config=ncfg, conv_config=ccfg, net_weights=ref.NetWeights())
+    dyn = ref.Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+    x = lat.random().detach()           # [nb, 2, T, X], as the trainer hands it over (trainer.py:935-938)
+    b = torch.tensor(beta)
+    loss_fn = ref.LatticeLoss(lat, ref.cfgs.LossConfig(use_mixed_loss=True, charge_weight=0.01))
+    opt = torch.optim.Adam([p for p in dyn.parameters() if p.requires_grad], lr=1e-3)
+    dyn.train(mode == 'train')
+
+    def step():
+        if mode == 'train':
+            opt.zero_grad()
+            xo, m = dyn((x, b))
+            xp = m.pop('mc_states').proposed.x
+            loss = loss_fn(x_init=x, x_prop=xp, acc=m['acc'])
+            loss.backward()
+            opt.step()
+        else:      # the reference's eval_step runs with autograd on (its U(1) force IS an autograd call), trainer.py:930-956
+            xo, m = dyn((x, b))
+            xp = m.pop('mc_states').proposed.x
+            loss = loss_fn(x_init=x, x_prop=xp, acc=m['acc'])
+        return float(loss)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt_s = time.perf_counter() - t0
+    units_ = nb * 2 * V * 2 * nlf
+    sample = (f'U1 {"x".join(map(str, lattice))} L2HMC {mode} step, the full {nb} chains, N_LF {nlf}, default experiment '
+              f'config (conv stack + units [16,16,16,16]), fp32, torch {torch.__version__} CPU, {cores} threads')
     return {'value': units_ * steps / dt_s, 'unit': 'link-updates/s', 'cores': cores, 'kind': 'reference',
             'sample': sample}, dt_s / steps * 1e3
 
@@ -670,6 +744,15 @@ def main_ours(args):
                       'chains_per_gpu': r['config']['chains_per_gpu'], 'parallelism': r['config']['parallelism'],
                       'cuda_graphs': r['config']['cuda_graphs'],
                       'grad_allreduce': r.get('grad_allreduce')}
+        if ctx.world == 1:
+            # BASELINE cfg 1 (the reference's default experiment; the CPU arm runs it at full size: `--impl reference
+            # --workload u1_16x16_nb128_l2hmc_train_f32`)
+            for w in sorted(U1_L2HMC_WORKLOADS):
+                r = u1_l2hmc_workload(ctx, w, max(3, min(args.steps, 10)), 3, cuda_graphs=True, clocks=False)
+                sec[w] = {'value': r['value'], 'ms_per_step': r['ms_per_step'], 'unit': 'link-updates/s',
+                          'roofline_frac': None, 'roofline_kernel': None, 'e2e': r['e2e']['value'],
+                          'gpu_launches': r['gpu_launches'], 'chains_per_gpu': r['config']['chains_per_gpu'],
+                          'cuda_graphs': True, 'note': r['config']['l2_policy']}
         line['secondary'] = sec
     if ctx.rank == 0:
         if ctx.world == 1 and not args.no_cpu_baseline:
@@ -814,9 +897,103 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
         torch.set_default_dtype(old_dt)
 
 
+def u1_l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs: bool = True,
+                      clocks: bool = True) -> dict:
+    """BASELINE cfg 1 -- the reference's default experiment (U(1) 16x16, 128 chains, N_LF 8, conv + dense nets, fp32)
+    -- through the public Trainer API: eval_step / train_step, every layer on the hand-written kernels (conv stack as
+    periodic gather + tcgen05 GEMM, fp32 Linears through bf16x3 splits).  At this size the step is launch-latency
+    bound (a few thousand small kernels), so it is timed as the CUDA-graph replay `Trainer(cuda_graphs=True)` gives."""
+    import numpy as np
+    torch = ctx.torch
+    rank, world = ctx.rank, ctx.world
+    from l2hmc_b200 import _lib, configs
+    from l2hmc_b200.dynamics.pytorch.dynamics import Dynamics
+    from l2hmc_b200.lattice.u1.pytorch.lattice import LatticeU1
+    from l2hmc_b200.network.pytorch.network import NetworkFactory
+    from l2hmc_b200.trainers.pytorch.trainer import Trainer
+    mode, lattice, nb, nlf, beta = U1_L2HMC_WORKLOADS[workload]
+    old_dt = torch.get_default_dtype()
+    torch.manual_seed(SEED)
+    np.random.seed(SEED)
+    torch.set_default_dtype(torch.float32)
+    try:
+        cfg, ncfg, ccfg = u1_default_configs(configs, nb, lattice, nlf)
+        fac = NetworkFactory(input_spec=configs.get_input_spec(cfg), network_config=ncfg, conv_config=ccfg,
+                             net_weights=None)
+        lat = LatticeU1(nb, lattice)
+        dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
+        tr = Trainer(dyn, configs.LossConfig(use_mixed_loss=True, charge_weight=0.01), lr=1e-3, clip_val=1.0,
+                     cuda_graphs=cuda_graphs)
+        torch.manual_seed(SEED + 1 + rank)
+        x = lat.random()
+        bt = torch.tensor(beta)
+        units_rank = nb * 2 * lattice[0] * lattice[1] * 2 * nlf
+
+        def step(xin):
+            return tr.eval_step((xin, bt)) if mode == 'eval' else tr.train_step((xin, bt))
+
+        for _ in range(warmup):
+            step(x)
+        ctx.barrier()
+        sampler = ClockSampler(ctx.local) if (rank == 0 and clocks) else None
+        if sampler:
+            sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.barrier()
+        e0.record()
+        for _ in range(steps):
+            xo, met = step(x)
+        e1.record()
+        ctx.barrier()
+        launches = _lib.launch_count() - l0
+        if cuda_graphs:
+            launches = steps * int(tr.graph_launches.get(mode, 0))
+        clk = sampler.stop() if sampler else None
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        assert torch.isfinite(torch.as_tensor(met['loss'])), 'non-finite loss'
+        # e2e: links from pinned host memory every step, loss read back to the host
+        xh = x.cpu().pin_memory()
+        loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+        xin = torch.empty_like(x)
+        ctx.barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(steps):
+            xin.copy_(xh, non_blocking=True)
+            xo, met = step(xin)
+            loss_h.copy_(torch.as_tensor(met['loss']).to(torch.float32), non_blocking=True)
+        e3.record()
+        ctx.barrier()
+        e2e_val = world * units_rank * steps / (ctx.max_over_ranks(e2.elapsed_time(e3)) * 1e-3)
+        res = {
+            'workload': workload, 'value': world * units_rank / (ms * 1e-3), 'ms_per_step': ms,
+            'gpu_launches': launches, 'clocks': clk, 'dtype': 'f32',
+            'config': {'workload': workload, 'group': 'U1', 'lattice': lattice, 'chains_per_gpu': nb,
+                       'global_chains': nb * world, 'nleapfrog': nlf, 'beta': beta, 'step': mode,
+                       'network': 'conf/config.yaml defaults: conv [8,16,32,64,128] / sizes [5,3,3,3,2] / pool 2, units '
+                                  '[16,16,16,16], leaky_relu, dropout 0.2, batch norm, separate + split networks',
+                       'cuda_graphs': bool(cuda_graphs), 'start': 'hot (g.random), random-init weights',
+                       'parallelism': f'chains sharded over {world} GPU(s)',
+                       'l2_policy': 'working set (< 100 MB) fits L2: the step is launch-latency bound, not HBM bound'},
+            'roofline': None,
+            'e2e': {'value': e2e_val, 'unit': 'link-updates/s', 'h2d_bytes_per_step': x.numel() * x.element_size(),
+                    'd2h_bytes_per_step': 4, 'steps': steps, 'api': f'Trainer.{mode}_step((x_host_pinned -> device, beta))'},
+        }
+        del tr, dyn, fac, lat, x, xin, xo, met
+        ctx.free()
+        return res
+    finally:
+        torch.set_default_dtype(old_dt)
+
+
 def main_l2hmc(args):
     ctx = Ctx()
-    r = l2hmc_workload(ctx, args.workload, args.steps, args.warmup, cuda_graphs=args.cuda_graphs)
+    if args.workload in U1_L2HMC_WORKLOADS:
+        r = u1_l2hmc_workload(ctx, args.workload, args.steps, args.warmup, cuda_graphs=True)
+        r['grad_allreduce'] = None
+    else:
+        r = l2hmc_workload(ctx, args.workload, args.steps, args.warmup, cuda_graphs=args.cuda_graphs)
     if ctx.rank == 0:
         line = {
             'metric': METRIC, 'value': r['value'], 'unit': 'link-updates/s', 'n_gpus': ctx.world, 'steps': args.steps,
@@ -908,7 +1085,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--workload', choices=sorted(WORKLOADS) + sorted(L2HMC_WORKLOADS), default=DEFAULT_WORKLOAD)
+    ap.add_argument('--workload', choices=sorted(WORKLOADS) + sorted(L2HMC_WORKLOADS) + sorted(U1_L2HMC_WORKLOADS),
+                    default=DEFAULT_WORKLOAD)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--thermalise', type=int, default=0,
                     help='HMC trajectories run before timing (default 0: hot start, as the reference\'s g.random)')
@@ -924,6 +1102,25 @@ def main():
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':
+        if args.workload in U1_L2HMC_WORKLOADS:
+            if int(os.environ.get('RANK', '0')) != 0:
+                return
+            os.environ['CUDA_VISIBLE_DEVICES'] = ''
+            base, ms = run_reference_u1_l2hmc(args.workload, max(1, min(args.steps, 3)), min(args.warmup, 1))
+            if base is None:
+                print(json.dumps({'impl': 'reference', 'unavailable': ms}))
+                return
+            mode, lattice, nb, nlf, beta = U1_L2HMC_WORKLOADS[args.workload]
+            print(json.dumps({
+                'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'link-updates/s',
+                'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': args.workload, 'group': 'U1', 'lattice': lattice, 'chains_per_gpu': nb,
+                           'nleapfrog': nlf, 'beta': beta, 'step': mode, 'sample': base['sample']},
+                'cpu_baseline': base,
+                'e2e': {'value': base['value'], 'unit': 'link-updates/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+            return
         if args.workload in L2HMC_WORKLOADS:
             if int(os.environ.get('RANK', '0')) != 0:
                 return
@@ -945,7 +1142,7 @@ def main():
                         'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
             return
         main_reference(args)
-    elif args.workload in L2HMC_WORKLOADS:
+    elif args.workload in L2HMC_WORKLOADS or args.workload in U1_L2HMC_WORKLOADS:
         main_l2hmc(args)
     else:
         main_ours(args)

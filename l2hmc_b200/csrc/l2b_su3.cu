@@ -742,7 +742,11 @@ __global__ void __launch_bounds__(NTL) k_vupdate_bwd(const C* __restrict__ v, co
 // adjoint of k_update_gauge:  R = m*X + E ((1-m)*X),  E = exp(eps P)
 //   G_X = m*G + (1-m)*(E^+ G),  G_E = G ((1-m)*X)^+,  G_P = eps * expadj(eps P; G_E),
 //   g_eps = Re sum conj(G_A) P
-__global__ void __launch_bounds__(NTL) k_update_gauge_bwd(const C* __restrict__ x, const C* __restrict__ p, double eps_in, const double* __restrict__ eps_dev,
+// Two phases, so that the matrix exponential and the exponential's adjoint never hold their registers at the same
+// time: G_X leaves first; the adjoint then runs column by column on (P^+, G_E) and puts each finished column of
+// G_P straight into the block's staging buffer.
+template <int MINB>
+__global__ void __launch_bounds__(NTL, MINB) k_update_gauge_bwd(const C* __restrict__ x, const C* __restrict__ p, double eps_in, const double* __restrict__ eps_dev,
                                                           const float* __restrict__ mask, int mask_complement,
                                                           const C* __restrict__ gout, C* __restrict__ gx,
                                                           C* __restrict__ gp, double* __restrict__ part,
@@ -753,45 +757,60 @@ __global__ void __launch_bounds__(NTL) k_update_gauge_bwd(const C* __restrict__ 
   const size_t row0 = (size_t)blockIdx.y * links_per_chain;
   const size_t l0 = (size_t)blockIdx.x * NTL;
   const int n = (int)min((size_t)NTL, links_per_chain - l0);
-  Mat3<T> X, Pm, G, E, Xb, GX, GE, GA;
-  block_load_mat<NTL>(Pm, sm, p, row0 + l0, n);
-  block_load_mat<NTL>(X, sm, x, row0 + l0, n);
-  block_load_mat<NTL>(G, sm, gout, row0 + l0, n);
-  double ge = 0.0;
-  if ((int)threadIdx.x < n) {
-    Mat3<T> A;
+  const bool live = (int)threadIdx.x < n;
+  Mat3<T> Pb, GE;       // P^+ and G_E: all the second phase needs
+  {
+    Mat3<T> X, Pm, G, E, Xb, GX;
+    block_load_mat<NTL>(Pm, sm, p, row0 + l0, n);
+    block_load_mat<NTL>(X, sm, x, row0 + l0, n);
+    block_load_mat<NTL>(G, sm, gout, row0 + l0, n);
+    if (live) {
+      Mat3<T> A;
 #pragma unroll
-    for (int e = 0; e < 9; ++e) { A.re[e] = eps * Pm.re[e]; A.im[e] = eps * Pm.im[e]; }
-    mat_exp(E, A);
-    T md[9];
+      for (int e = 0; e < 9; ++e) { A.re[e] = eps * Pm.re[e]; A.im[e] = eps * Pm.im[e]; }
+      mat_exp(E, A);
+      T md[9];
 #pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      float m = (mask == nullptr) ? 0.0f : __ldg(mask + (l0 + threadIdx.x) * 9 + e);
-      if (mask != nullptr && mask_complement) m = 1.0f - m;
-      md[e] = (T)m;
-      const T mb = (T)(1.0f - m);
-      Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+      for (int e = 0; e < 9; ++e) {
+        float m = (mask == nullptr) ? 0.0f : __ldg(mask + (l0 + threadIdx.x) * 9 + e);
+        if (mask != nullptr && mask_complement) m = 1.0f - m;
+        md[e] = (T)m;
+        const T mb = (T)(1.0f - m);
+        Xb.re[e] = mb * X.re[e]; Xb.im[e] = mb * X.im[e];
+      }
+      mat_mul<true, false, false>(GX, E, G);          // E^+ G
+      mat_mul<false, true, false>(GE, G, Xb);         // G Xb^+
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        const T mb = T(1) - md[e];
+        GX.re[e] = md[e] * G.re[e] + mb * GX.re[e];
+        GX.im[e] = md[e] * G.im[e] + mb * GX.im[e];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { Pb.re[3 * i + j] = Pm.re[3 * j + i]; Pb.im[3 * i + j] = -Pm.im[3 * j + i]; }
+      }
     }
-    mat_mul<true, false, false>(GX, E, G);          // E^+ G
-    mat_mul<false, true, false>(GE, G, Xb);         // G Xb^+
-#pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      const T mb = T(1) - md[e];
-      GX.re[e] = md[e] * G.re[e] + mb * GX.re[e];
-      GX.im[e] = md[e] * G.im[e] + mb * GX.im[e];
-    }
-    bool ok;
-    mat_exp_adjoint(GA, A, GE, ok);
-    if (!ok) atomicExch(bad, 1);
-#pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      ge = fma(GA.re[e], Pm.re[e], ge);
-      ge = fma(GA.im[e], Pm.im[e], ge);
-      GA.re[e] *= eps; GA.im[e] *= eps;
-    }
+    block_store_mat<NTL>(gx, sm, GX, row0 + l0, n);   // ends with a barrier: `sm` is free again
   }
-  block_store_mat<NTL>(gx, sm, GX, row0 + l0, n);
-  block_store_mat<NTL>(gp, sm, GA, row0 + l0, n);
+  double ge = 0.0;
+  if (live) {
+    bool ok;
+    C* mine = sm + threadIdx.x * 9;
+    mat_exp_adjoint_cols(Pb, (T)eps, GE, ok, [&](int c, const T r[3], const T i[3]) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        // P(k, c) = conj(Pb(c, k))
+        ge = fma(r[k], Pb.re[3 * c + k], ge);
+        ge = fma(-i[k], Pb.im[3 * c + k], ge);
+        mine[3 * k + c] = make_double2(eps * r[k], eps * i[k]);
+      }
+    });
+    if (!ok) atomicExch(bad, 1);
+  }
+  __syncthreads();
+  stage_out<NTL>(gp, sm, row0 + l0, n, 9);
   ge = block_sum<NTL>(ge, red, threadIdx.x);
   if (threadIdx.x == 0) part[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = ge;
 }
@@ -1394,6 +1413,7 @@ constexpr int kNumForceVariants = (int)(sizeof(kForceVariants) / sizeof(kForceVa
 int g_fuse_conversions = 1;   // fold the momentum / output layout conversions into the trajectory's end launches
 int g_force_variant = 22;   // r1d: momentum loads issued before the last staple direction (-10 % on the 16^4 trajectory)
 int g_fuse_drift = 1;
+int g_gauge_bwd_minb = 3;
 int g_force_carveout = -1;   // -1: driver default; 0..100: preferred shared-memory carve-out in percent
 
 struct Geo {
@@ -1575,6 +1595,11 @@ int l2b_set_option(const char* key, int value) {
   if (strcmp(key, "su3_force_carveout") == 0) {
     L2B_REQUIRE(value >= -1 && value <= 100, L2B_ERR_INVALID, "su3_force_carveout must be in [-1, 100]");
     g_force_carveout = value;
+    return L2B_OK;
+  }
+  if (strcmp(key, "su3_gauge_bwd_minb") == 0) {
+    L2B_REQUIRE(value == 2 || value == 3, L2B_ERR_INVALID, "su3_gauge_bwd_minb must be 2 or 3");
+    g_gauge_bwd_minb = value;
     return L2B_OK;
   }
   if (strcmp(key, "su3_fuse_drift") == 0) {
@@ -2034,7 +2059,11 @@ int l2b_su3_update_gauge_bwd(const void* x, const void* p, double eps, const dou
   L2B_TRY(carve(w, g, ws, ws_bytes));
   L2B_REQUIRE(x && p && gx_out && gx && gp && geps && bad_flag, L2B_ERR_INVALID, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  k_update_gauge_bwd<<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, eps_dev, mask, mask_complement,
+  // register cap: 3 resident blocks per SM (168 registers, small spill) or 2 (240, none); option su3_gauge_bwd_minb
+  if (g_gauge_bwd_minb == 2) k_update_gauge_bwd<2><<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, eps_dev, mask, mask_complement,
+                                                            (const C*)gx_out, (C*)gx, (C*)gp, w.part, bad_flag,
+                                                            g.links_per_chain);
+  else k_update_gauge_bwd<3><<<dim3(g.nblk_link, nb), NTL, 0, st>>>((const C*)x, (const C*)p, eps, eps_dev, mask, mask_complement,
                                                             (const C*)gx_out, (C*)gx, (C*)gp, w.part, bad_flag,
                                                             g.links_per_chain);
   L2B_LAUNCHED("k_update_gauge_bwd");

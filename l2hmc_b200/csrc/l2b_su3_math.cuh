@@ -487,58 +487,138 @@ L2B_HD void tah_from_normals(Mat3<T>& m, const T n[8]) {
 // G_Z = dL/dRe Z + i dL/dIm Z, so for Y = A B:  G_A = G_Y B^+,  G_B = A^+ G_Y)
 // ---------------------------------------------------------------------------
 
-// Adjoint of E = exp(A):  G_A = sum_{n>=1} 1/n! sum_{k<n} B^k G_E B^(n-1-k),  B = A^+.
-// With B^m = a_m + b_m B + c_m B^2 (Cayley-Hamilton, as in mat_exp) the inner sums obey
-//   D_1 = G,  D_n = B D_{n-1} + G B^{n-1} = B D_{n-1} + a G + b (G B) + c (G B^2),
-// one matrix product per Taylor term.  No scaling/squaring: at most 34 terms (3^34/34! ~ 6e-23
-// at ||A||_F = 3), fewer at the small norms of a leapfrog step (11 at ||A||_F <= 0.1); L2HMC arguments are eps*v
-// with eps < 1, ||v||_F ~ 2.8.  `ok` is cleared when the norm is outside that range.
+// Adjoint of E = exp(A):  G_A = sum_{n>=1} 1/n! sum_{j+k=n-1} B^j G_E B^k,  B = A^+.
+// With B^m = alpha_0(m) + alpha_1(m) B + alpha_2(m) B^2 (Cayley-Hamilton, as in mat_exp) the double sum collapses to
+//   G_A = sum_{p,q=0..2} w_pq B^p G B^q,   w = sum_n W(n) / n!,   W(n) = sum_{j+k=n-1} alpha(j) alpha(k)^T,
+// and W obeys a SCALAR recurrence: alpha(m+1) = M alpha(m) with the companion matrix M of the characteristic
+// polynomial (B^3 = t B^2 - c B + d), hence  W(n+1) = alpha(n) e_0^T + W(n) M^T  (W is symmetric: six complex
+// numbers per term, ~70 flops, against one 3x3 product + three matrix axpys = 255 flops per term of the matrix
+// recurrence D_n = B D_{n-1} + G B^{n-1} this replaces: k_update_gauge_bwd 260 -> 178 us at 8^4 x 32 chains).
+// The matrix work is done one COLUMN of G_A at a time (Horner in B from the left):
+//   u_q = G (B^q e_c),   s_p = sum_q w_pq u_q,   G_A e_c = s_0 + B (s_1 + B s_2),
+// five matrix-vector products per column; only B, G and a few 3-vectors are live (the matrix form held six
+// matrices).  The argument is passed as B = eps * pb with pb = P^+ unscaled, so that the caller can form
+// d/d eps = Re sum conj(G_A) P from pb and never needs P itself; the powers of eps are folded into w_pq.
+// `sink(c, r, i)` receives column c of G_A (r[k], i[k]: row k).
+// No scaling/squaring: at most 34 terms (3^34/34! ~ 6e-23 at ||A||_F = 3), fewer at the small norms of a
+// leapfrog step (11 at ||A||_F <= 0.1); L2HMC arguments are eps*v with eps < 1, ||v||_F ~ 2.8.  `ok` is cleared
+// when the norm is outside that range.
+template <typename T, typename Sink>
+L2B_HD void mat_exp_adjoint_cols(const Mat3<T>& pb, T eps, const Mat3<T>& ge, bool& ok, Sink&& sink) {
+  const T n2a = eps * eps * norm2(pb);
+  ok = n2a <= T(9);
+  // invariants of B = eps pb:  t = tr B,  tr B^2 = sum_ij B_ij B_ji,  c = (t^2 - tr B^2) / 2,  d = det B
+  const T tr = eps * (pb.re[0] + pb.re[4] + pb.re[8]), ti = eps * (pb.im[0] + pb.im[4] + pb.im[8]);
+  T t2r = T(0), t2i = T(0);
+  L2B_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    L2B_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      t2r = fma(pb.re[3 * i + j], pb.re[3 * j + i], t2r); t2r = fma(-pb.im[3 * i + j], pb.im[3 * j + i], t2r);
+      t2i = fma(pb.re[3 * i + j], pb.im[3 * j + i], t2i); t2i = fma(pb.im[3 * i + j], pb.re[3 * j + i], t2i);
+    }
+  }
+  const T e2 = eps * eps;
+  t2r *= e2; t2i *= e2;
+  const T cr = T(0.5) * (tr * tr - ti * ti - t2r), ci = T(0.5) * (T(2) * tr * ti - t2i);
+  T dr, di;
+  det3(pb, dr, di);
+  dr *= e2 * eps; di *= e2 * eps;
+  // alpha(n-1) and the upper triangle of W(n), at n = 1: alpha(0) = e_0, W(1) = e_0 e_0^T; s = sum_n W(n) / n!
+  T a0r = T(1), a0i = T(0), a1r = T(0), a1i = T(0), a2r = T(0), a2i = T(0);
+  T w00r = T(1), w00i = T(0), w01r = T(0), w01i = T(0), w02r = T(0), w02i = T(0);
+  T w11r = T(0), w11i = T(0), w12r = T(0), w12i = T(0), w22r = T(0), w22i = T(0);
+  T s00r = T(1), s00i = T(0), s01r = T(0), s01i = T(0), s02r = T(0), s02i = T(0);
+  T s11r = T(0), s11i = T(0), s12r = T(0), s12i = T(0), s22r = T(0), s22i = T(0);
+  T inv_fact = T(1);
+  // terms needed at this norm: the n-th term is bounded by rho^(n-1) / (n-1)!  (rho = ||A||_F <= 3)
+  const int nterms = (n2a <= T(0.01)) ? 11 : (n2a <= T(0.09)) ? 14 : (n2a <= T(0.25)) ? 17
+                     : (n2a <= T(1)) ? 21 : (n2a <= T(4)) ? 28 : 34;
+  for (int n = 2; n <= nterms; ++n) {
+    // alpha(n-2) -> alpha(n-1) = M alpha(n-2):  (d a2,  a0 - c a2,  a1 + t a2)
+    const T n0r = dr * a2r - di * a2i, n0i = dr * a2i + di * a2r;
+    const T n1r = a0r - (cr * a2r - ci * a2i), n1i = a0i - (cr * a2i + ci * a2r);
+    const T n2r = a1r + (tr * a2r - ti * a2i), n2i = a1i + (tr * a2i + ti * a2r);
+    a0r = n0r; a0i = n0i; a1r = n1r; a1i = n1i; a2r = n2r; a2i = n2i;
+    // W(n) = alpha(n-1) e_0^T + W(n-1) M^T, rows p <= columns q:
+    //   (p,0) = alpha_p + d W(p,2),  (p,1) = W(p,0) - c W(p,2),  (p,2) = W(p,1) + t W(p,2)
+    const T v00r = a0r + (dr * w02r - di * w02i), v00i = a0i + (dr * w02i + di * w02r);
+    const T v01r = w00r - (cr * w02r - ci * w02i), v01i = w00i - (cr * w02i + ci * w02r);
+    const T v02r = w01r + (tr * w02r - ti * w02i), v02i = w01i + (tr * w02i + ti * w02r);
+    const T v11r = w01r - (cr * w12r - ci * w12i), v11i = w01i - (cr * w12i + ci * w12r);
+    const T v12r = w11r + (tr * w12r - ti * w12i), v12i = w11i + (tr * w12i + ti * w12r);
+    const T v22r = w12r + (tr * w22r - ti * w22i), v22i = w12i + (tr * w22i + ti * w22r);
+    w00r = v00r; w00i = v00i; w01r = v01r; w01i = v01i; w02r = v02r; w02i = v02i;
+    w11r = v11r; w11i = v11i; w12r = v12r; w12i = v12i; w22r = v22r; w22i = v22i;
+    inv_fact /= T(n);
+    s00r = fma(inv_fact, w00r, s00r); s00i = fma(inv_fact, w00i, s00i);
+    s01r = fma(inv_fact, w01r, s01r); s01i = fma(inv_fact, w01i, s01i);
+    s02r = fma(inv_fact, w02r, s02r); s02i = fma(inv_fact, w02i, s02i);
+    s11r = fma(inv_fact, w11r, s11r); s11i = fma(inv_fact, w11i, s11i);
+    s12r = fma(inv_fact, w12r, s12r); s12i = fma(inv_fact, w12i, s12i);
+    s22r = fma(inv_fact, w22r, s22r); s22i = fma(inv_fact, w22i, s22i);
+  }
+  // B^p G B^q = eps^(p+q) pb^p G pb^q
+  s01r *= eps; s01i *= eps;
+  s02r *= e2; s02i *= e2; s11r *= e2; s11i *= e2;
+  s12r *= e2 * eps; s12i *= e2 * eps;
+  s22r *= e2 * e2; s22i *= e2 * e2;
+  // y = M x for a 3-vector (complex)
+  auto mv = [](const Mat3<T>& m, const T xr[3], const T xi[3], T yr[3], T yi[3]) {
+    L2B_UNROLL
+    for (int i = 0; i < 3; ++i) {
+      T r = T(0), im = T(0);
+      L2B_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        r = fma(m.re[3 * i + k], xr[k], r); r = fma(-m.im[3 * i + k], xi[k], r);
+        im = fma(m.re[3 * i + k], xi[k], im); im = fma(m.im[3 * i + k], xr[k], im);
+      }
+      yr[i] = r; yi[i] = im;
+    }
+  };
+  L2B_UNROLL
+  for (int c = 0; c < 3; ++c) {
+    T u0r[3], u0i[3], u1r[3], u1i[3], u2r[3], u2i[3], br[3], bi[3], vr[3], vi[3], tr_[3], ti_[3];
+    L2B_UNROLL
+    for (int k = 0; k < 3; ++k) {
+      u0r[k] = ge.re[3 * k + c]; u0i[k] = ge.im[3 * k + c];
+      br[k] = pb.re[3 * k + c]; bi[k] = pb.im[3 * k + c];
+    }
+    mv(ge, br, bi, u1r, u1i);             // G pb e_c
+    mv(pb, br, bi, vr, vi);               // pb^2 e_c
+    mv(ge, vr, vi, u2r, u2i);             // G pb^2 e_c
+    auto comb = [&](T x0r, T x0i, T x1r, T x1i, T x2r, T x2i, T or_[3], T oi_[3], bool add) {
+      L2B_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        T r = add ? or_[k] : T(0), im = add ? oi_[k] : T(0);
+        r = fma(x0r, u0r[k], r); r = fma(-x0i, u0i[k], r); im = fma(x0r, u0i[k], im); im = fma(x0i, u0r[k], im);
+        r = fma(x1r, u1r[k], r); r = fma(-x1i, u1i[k], r); im = fma(x1r, u1i[k], im); im = fma(x1i, u1r[k], im);
+        r = fma(x2r, u2r[k], r); r = fma(-x2i, u2i[k], r); im = fma(x2r, u2i[k], im); im = fma(x2i, u2r[k], im);
+        or_[k] = r; oi_[k] = im;
+      }
+    };
+    comb(s02r, s02i, s12r, s12i, s22r, s22i, vr, vi, false);      // s_2
+    mv(pb, vr, vi, tr_, ti_);                                     // pb s_2
+    comb(s01r, s01i, s11r, s11i, s12r, s12i, tr_, ti_, true);     // + s_1
+    mv(pb, tr_, ti_, vr, vi);                                     // pb (s_1 + pb s_2)
+    comb(s00r, s00i, s01r, s01i, s02r, s02i, vr, vi, true);       // + s_0
+    sink(c, vr, vi);
+  }
+}
+
+// matrix-argument form: G_A for E = exp(A)
 template <typename T>
 L2B_HD void mat_exp_adjoint(Mat3<T>& ga, const Mat3<T>& a, const Mat3<T>& ge, bool& ok) {
-  ok = norm2(a) <= T(9);
-  Mat3<T> b, b2, gb, gb2, d, tmp;
+  Mat3<T> b;
   L2B_UNROLL
   for (int i = 0; i < 3; ++i) {
     L2B_UNROLL
     for (int j = 0; j < 3; ++j) { b.re[3 * i + j] = a.re[3 * j + i]; b.im[3 * i + j] = -a.im[3 * j + i]; }
   }
-  mat_mul<false, false, false>(b2, b, b);
-  mat_mul<false, false, false>(gb, ge, b);
-  mat_mul<false, false, false>(gb2, gb, b);
-  const T tr = b.re[0] + b.re[4] + b.re[8], ti = b.im[0] + b.im[4] + b.im[8];
-  const T t2r = b2.re[0] + b2.re[4] + b2.re[8], t2i = b2.im[0] + b2.im[4] + b2.im[8];
-  const T cr = T(0.5) * (tr * tr - ti * ti - t2r), ci = T(0.5) * (T(2) * tr * ti - t2i);
-  T dr, di;
-  det3(b, dr, di);
-  // (a_m, b_m, c_m) of B^m, starting at m = 0: (1, 0, 0)
-  T amr = T(1), ami = T(0), bmr = T(0), bmi = T(0), cmr = T(0), cmi = T(0);
-  d = ge;          // D_1
-  ga = ge;         // n = 1 term, 1/1!
-  T inv_fact = T(1);
-  // terms needed at this norm: the n-th term is bounded by rho^(n-1) / (n-1)!  (rho = ||A||_F <= 3)
-  const T n2a = norm2(a);
-  const int nterms = (n2a <= T(0.01)) ? 11 : (n2a <= T(0.09)) ? 14 : (n2a <= T(0.25)) ? 17
-                     : (n2a <= T(1)) ? 21 : (n2a <= T(4)) ? 28 : 34;
-  for (int n = 2; n <= nterms; ++n) {
-    // advance B^{n-2} -> B^{n-1}
-    const T nar = dr * cmr - di * cmi, nai = dr * cmi + di * cmr;
-    const T nbr = amr - (cr * cmr - ci * cmi), nbi = ami - (cr * cmi + ci * cmr);
-    const T ncr = bmr + (tr * cmr - ti * cmi), nci = bmi + (tr * cmi + ti * cmr);
-    amr = nar; ami = nai; bmr = nbr; bmi = nbi; cmr = ncr; cmi = nci;
-    // D_n = B D_{n-1} + a G + b GB + c GB2
-    mat_mul<false, false, false>(tmp, b, d);
+  mat_exp_adjoint_cols(b, T(1), ge, ok, [&](int c, const T r[3], const T i[3]) {
     L2B_UNROLL
-    for (int e = 0; e < 9; ++e) {
-      T r = tmp.re[e], i = tmp.im[e];
-      r += amr * ge.re[e] - ami * ge.im[e];   i += amr * ge.im[e] + ami * ge.re[e];
-      r += bmr * gb.re[e] - bmi * gb.im[e];   i += bmr * gb.im[e] + bmi * gb.re[e];
-      r += cmr * gb2.re[e] - cmi * gb2.im[e]; i += cmr * gb2.im[e] + cmi * gb2.re[e];
-      d.re[e] = r; d.im[e] = i;
-    }
-    inv_fact /= T(n);
-    L2B_UNROLL
-    for (int e = 0; e < 9; ++e) { ga.re[e] = fma(inv_fact, d.re[e], ga.re[e]); ga.im[e] = fma(inv_fact, d.im[e], ga.im[e]); }
-  }
+    for (int k = 0; k < 3; ++k) { ga.re[3 * k + c] = r[k]; ga.im[3 * k + c] = i[k]; }
+  });
 }
 
 // adjoint of su3_to_vec (a real-linear map of the matrix entries)
