@@ -323,14 +323,16 @@ int l2b_split_bf16x3(const float* x, long long rows, long long cols, long long l
  * the next block's input in NHWC.  l2b_conv_im2col writes col[planes][nb OH OW][K8] bf16 (K8 = Cin n^2 rounded up
  * to a multiple of 8, zero padded; planes = 1: bf16 nets, 3: the bf16x3 split of fp32 nets) from an input with
  * element strides (batch, channel, row, column) -- NCHW for the network input, NHWC between blocks.
+ * k_order = 0: columns in Conv2d's own order k = (ci, kh, kw); 1: tap-major k = (kh, kw, ci) (the caller passes the
+ * weight as [Cout, n, n, Cin]) -- on NHWC activations with Cin % 8 == 0 the gather then moves 32-byte vectors.
  * l2b_conv_col2im is its adjoint (dcol [nb OH OW][ldc] f32 / bf16 -> din f32 with free output strides), a gather
  * with a fixed summation order.  l2b_pool_act = MaxPool2d(pool) (floor, first maximum wins as in ATen) followed by
  * the activation (codes as l2b_su3_input_layer) on NHWC; idx keeps the winning tap, pre the pooled pre-activation
  * (needed for swish only); l2b_pool_act_bwd scatters gy * act' back (gx is zero-filled first). */
 int l2b_conv_im2col(const void* in, int in_dtype, int nb, int C, int H, int W, int n, const long long strides[4],
-                    void* col, int planes, void* stream);
+                    void* col, int planes, int k_order, void* stream);
 int l2b_conv_col2im(const void* dcol, int dcol_dtype, long long ldc, int nb, int C, int H, int W, int n, float* din,
-                    const long long out_strides[4], void* stream);
+                    const long long out_strides[4], int k_order, void* stream);
 int l2b_pool_act(const void* x, int dtype, int nb, int H, int W, int C, int pool, int activation, void* y,
                  unsigned char* idx, float* pre, void* stream);
 int l2b_pool_act_bwd(const float* gy, const void* y, int dtype, const float* pre, const unsigned char* idx, int nb, int H,

@@ -114,8 +114,8 @@ _SIGS = {
     'l2b_gemm_bf16': [POINTER(_P), c_longlong, c_int, POINTER(_P), c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, _P,
                       c_int, c_longlong, c_int, _P, c_int, c_int, _P, c_size_t, _P],
     'l2b_split_bf16x3': [_P, c_longlong, c_longlong, c_longlong, _P, c_longlong, _P],
-    'l2b_conv_im2col': [_P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_longlong), _P, c_int, _P],
-    'l2b_conv_col2im': [_P, c_int, c_longlong, c_int, c_int, c_int, c_int, c_int, _P, POINTER(c_longlong), _P],
+    'l2b_conv_im2col': [_P, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_longlong), _P, c_int, c_int, _P],
+    'l2b_conv_col2im': [_P, c_int, c_longlong, c_int, c_int, c_int, c_int, c_int, _P, POINTER(c_longlong), c_int, _P],
     'l2b_pool_act': [_P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     'l2b_pool_act_bwd': [_P, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P],
     'l2b_su3_project_bwd': [_P, _P, _P, c_int, _P, c_size_t, c_int, _P],

@@ -530,7 +530,9 @@ class ConvPeriodic(torch.autograd.Function):
     + Conv2d(f, n) [+ the activation, when no pooling sits in between] as gather -> tensor-core GEMM
     (ops.conv_im2col, ops.gemm_bf16 / gemm_f32); output NHWC.  Backward: the gathered matrix is rebuilt from the saved
     input (it is 25 - 100 x the input's size), dW = g^T col (split-K over the nb OH OW rows), dcol = g W, and the
-    gather's adjoint (ops.conv_col2im)."""
+    gather's adjoint (ops.conv_col2im).  On NHWC inputs with Cin % 8 == 0 (every block after the first of the default
+    stack) the gathered columns are tap-major, k = (kh, kw, ci): the gather moves 32-byte channel vectors and the
+    weight is viewed as [Cout, n, n, Cin] (cached image); dW comes back in that order and is permuted once."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, nchw, mode, act, owner):
@@ -543,13 +545,14 @@ class ConvPeriodic(torch.autograd.Function):
             xd = xd.float()
         if not x3 and xd.dtype != torch.bfloat16:
             xd = xd.to(torch.bfloat16)
-        col = ops.conv_im2col(xd, n, nchw, planes)
+        tap = (not nchw) and int(weight.shape[1]) % 8 == 0
+        col = ops.conv_im2col(xd, n, nchw, planes, tap)
         fused = None if act == 'swish' else act
         b_ = None if bias is None else bias.detach().float()
         if x3:
-            y = ops.gemm_f32(col, owner.weight_split3(weight)[:planes], True, True, bias=b_, act=fused)
+            y = ops.gemm_f32(col, owner.weight_split3(weight, tap)[:planes], True, True, bias=b_, act=fused)
         else:
-            y = ops.gemm_bf16(col[0], owner.weight_as_bf16(weight), True, True, bias=b_, act=fused)
+            y = ops.gemm_bf16(col[0], owner.weight_as_bf16(weight, tap), True, True, bias=b_, act=fused)
         if y.shape[1] != cout:
             y = y[:, :cout].contiguous()
         nb = int(x.shape[0])
@@ -558,14 +561,14 @@ class ConvPeriodic(torch.autograd.Function):
         pre = None
         if act == 'swish':
             pre, y = y, torch.nn.functional.silu(y)
-        ctx.cfg = (n, nchw, mode, act, owner)
+        ctx.cfg = (n, nchw, mode, act, owner, tap)
         ctx.xmeta = (x.shape, x.dtype)
         ctx.save_for_backward(xd, weight, bias, y if act is not None else None, pre)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        n, nchw, mode, act, owner = ctx.cfg
+        n, nchw, mode, act, owner, tap = ctx.cfg
         xd, weight, bias, y, pre = ctx.saved_tensors
         x3 = mode in ('x3', 'x2')
         planes = {'x3': 3, 'x2': 2}.get(mode, 1)
@@ -576,19 +579,22 @@ class ConvPeriodic(torch.autograd.Function):
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         g = ops.split_bf16x3(g32)[:planes] if x3 else g32.to(torch.bfloat16)
         if need_w:
-            col = ops.conv_im2col(xd, n, nchw, planes)
+            col = ops.conv_im2col(xd, n, nchw, planes, tap)
             if x3:
                 gw = ops.gemm_f32(g, col, False, False)
             else:
                 gw = ops.gemm_bf16(g, col[0], False, False, out_dtype=torch.float32)
-            gw = gw[:cout, :K].reshape(weight.shape).to(weight.dtype)
+            if tap:
+                gw = gw[:cout, :K].reshape(cout, n, n, K // (n * n)).permute(0, 3, 1, 2).to(weight.dtype).contiguous()
+            else:
+                gw = gw[:cout, :K].reshape(weight.shape).to(weight.dtype)
             del col
         if need_x:
             if x3:
-                dcol = ops.gemm_f32(g, owner.weight_split3(weight)[:planes], True, False)
+                dcol = ops.gemm_f32(g, owner.weight_split3(weight, tap)[:planes], True, False)
             else:
-                dcol = ops.gemm_bf16(g, owner.weight_as_bf16(weight), True, False, out_dtype=torch.bfloat16)
-            gx = ops.conv_col2im(dcol, xd, n, nchw).to(ctx.xmeta[1]).reshape(ctx.xmeta[0])
+                dcol = ops.gemm_bf16(g, owner.weight_as_bf16(weight, tap), True, False, out_dtype=torch.bfloat16)
+            gx = ops.conv_col2im(dcol, xd, n, nchw, tap).to(ctx.xmeta[1]).reshape(ctx.xmeta[0])
         if need_b and bias is not None:
             gb = g32.sum(0).to(bias.dtype)
         return gx, gw, gb, None, None, None, None

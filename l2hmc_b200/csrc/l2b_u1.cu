@@ -311,7 +311,9 @@ template <> struct FNum<float> : Num<float> {
   static __device__ __forceinline__ float div_(float a, float b) { return __fdividef(a, b); }
 };
 
-constexpr int kHeadsChains = 64;      // chains per block tile (amortises the per-thread weight-row loads)
+constexpr int kHeadsChains = 64;      // most chains per block tile (amortises the per-thread weight-row loads); small
+                                      // batches take shorter tiles (`cpb`) so that the grid still fills the GPU:
+                                      // 128 chains x 512 columns were 4 blocks of 64 chains (62 us), now 64 of 4
 
 template <typename T, int HP, int MODE>
 __global__ void __launch_bounds__(256, 3) k_u1_heads_update(
@@ -319,15 +321,15 @@ __global__ void __launch_bounds__(256, 3) k_u1_heads_update(
     const T* __restrict__ bs, const T* __restrict__ bt, const T* __restrict__ bq, const T* __restrict__ cs,
     const T* __restrict__ cq, T nws, T nwt, T nwq, const T* __restrict__ a, const T* __restrict__ bfield,
     const float* __restrict__ mask, T eps_in, const T* __restrict__ eps_dev, int sign, int use_ncp,
-    T* __restrict__ out, double* __restrict__ part, int nb, int xdim) {
+    T* __restrict__ out, double* __restrict__ part, int nb, int xdim, int cpb) {
   __shared__ T zt[kHeadsChains][HP];
   __shared__ double ldw[8][kHeadsChains];
   const T eps = eps_dev ? eps_in * eps_dev[0] : eps_in;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = blockIdx.x * 256 + tid;
-  const int b0 = blockIdx.y * kHeadsChains;
-  const int nbt = min(kHeadsChains, nb - b0);
-  for (int idx = tid; idx < kHeadsChains * HP; idx += 256) {
+  const int b0 = blockIdx.y * cpb;
+  const int nbt = min(cpb, nb - b0);
+  for (int idx = tid; idx < cpb * HP; idx += 256) {
     const int c = idx / HP, k = idx % HP;
     zt[c][k] = (c < nbt && k < H) ? z[(size_t)(b0 + c) * H + k] : T(0);
   }
@@ -789,12 +791,12 @@ template <typename T, int MODE>
 int launch_u1_heads(int hp, dim3 grid, cudaStream_t st, const void* z, int H, const void* const w[3],
                     const void* const b[3], const void* cs, const void* cq, const double nw[3], const void* a,
                     const void* bf, const float* mask, double eps, const void* eps_dev, int sign, int use_ncp,
-                    void* out, double* part, int nb, int xdim) {
+                    void* out, double* part, int nb, int xdim, int cpb) {
 #define L2B_U1H(HP)                                                                                              \
   k_u1_heads_update<T, HP, MODE><<<grid, 256, 0, st>>>(                                                           \
       (const T*)z, H, (const T*)w[0], (const T*)w[1], (const T*)w[2], (const T*)b[0], (const T*)b[1],             \
       (const T*)b[2], (const T*)cs, (const T*)cq, (T)nw[0], (T)nw[1], (T)nw[2], (const T*)a, (const T*)bf, mask,   \
-      (T)eps, (const T*)eps_dev, sign, use_ncp, (T*)out, part, nb, xdim)
+      (T)eps, (const T*)eps_dev, sign, use_ncp, (T*)out, part, nb, xdim, cpb)
   if (hp == 8) L2B_U1H(8);
   else if (hp == 16) L2B_U1H(16);
   else L2B_U1H(32);
@@ -1038,7 +1040,11 @@ int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, co
     L2B_REQUIRE(ws && ws_bytes >= l2b_u1_heads_ws_bytes(nb, xdim), L2B_ERR_WORKSPACE, "workspace too small");
     part = (double*)ws;
   }
-  const int nyb = (nb + kHeadsChains - 1) / kHeadsChains;
+  // chains per block: 64, halved while the grid is short of two blocks per SM (results do not depend on it: the
+  // per-chain sums run over the columns of a block, in a fixed order)
+  int cpb = kHeadsChains;
+  while (cpb > 4 && (long long)nblk * ((nb + cpb - 1) / cpb) < 2 * 148) cpb >>= 1;
+  const int nyb = (nb + cpb - 1) / cpb;
   L2B_REQUIRE(nyb <= 65535, L2B_ERR_UNSUPPORTED, "too many chains for one launch");
   const dim3 grid(nblk, nyb);
   const int hp = hidden <= 8 ? 8 : (hidden <= 16 ? 16 : 32);
@@ -1048,11 +1054,11 @@ int l2b_u1_heads_update(int mode, const void* z, int hidden, const void* w_s, co
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (dtype == L2B_F32)
-    rc = mode == 0 ? launch_u1_heads<float, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim)
-                   : launch_u1_heads<float, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim);
+    rc = mode == 0 ? launch_u1_heads<float, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim, cpb)
+                   : launch_u1_heads<float, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim, cpb);
   else
-    rc = mode == 0 ? launch_u1_heads<double, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim)
-                   : launch_u1_heads<double, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim);
+    rc = mode == 0 ? launch_u1_heads<double, 0>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim, cpb)
+                   : launch_u1_heads<double, 1>(hp, grid, st, z, hidden, w, bb, coeff_s, coeff_q, nw, a, b, mask, eps, eps_dev, sign, use_ncp, out, part, nb, xdim, cpb);
   if (rc != L2B_OK) return rc;
   if (logdet) {
     if (dtype == L2B_F32) k_u1_sum_rows<float><<<nb, 256, 0, st>>>(part, nblk, (float*)logdet);

@@ -172,29 +172,38 @@ class _WeightImages:
     (and, inside a CUDA-graph capture of a training step, per step: `_capture_token`).  Conv weights are viewed as
     [Cout, Cin n^2]."""
 
-    def weight_as_bf16(self, w: Tensor) -> Tensor:
+    @staticmethod
+    def _as_matrix(w: Tensor, tap_major: bool) -> Tensor:
+        """[out, in] view of a Linear / Conv2d weight; `tap_major`: a Conv2d weight [Cout, Cin, n, n] as
+        [Cout, (kh, kw, ci)] (channel fastest), the column order of `ops.conv_im2col(..., tap_major=True)`"""
+        w = w.detach()
+        if tap_major:
+            w = w.permute(0, 2, 3, 1)
+        return w.reshape(w.shape[0], -1)
+
+    def weight_as_bf16(self, w: Tensor, tap_major: bool = False) -> Tensor:
         """bf16 copy of a weight matrix (what autocast would re-create on every call), cached per weight version;
         re-cast once per step inside a CUDA-graph capture of a training step, where the weights change on every replay"""
-        if w.dtype == torch.bfloat16:
+        if w.dtype == torch.bfloat16 and not tap_major:
             return w.detach().reshape(w.shape[0], -1)
         cache = self.__dict__.setdefault('_bf16_weights', {})
         key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
-        hit = cache.get(id(w))
+        hit = cache.get((id(w), tap_major))
         if hit is None or hit[0] != key:
-            hit = (key, w.detach().reshape(w.shape[0], -1).to(torch.bfloat16))
-            cache[id(w)] = hit
+            hit = (key, self._as_matrix(w, tap_major).to(torch.bfloat16).contiguous())
+            cache[(id(w), tap_major)] = hit
         return hit[1]
 
-    def weight_split3(self, w: Tensor) -> Tensor:
+    def weight_split3(self, w: Tensor, tap_major: bool = False) -> Tensor:
         """bf16x3 split of an fp32 weight matrix ([3, out, in8], ops.split_bf16x3) for the fp32-accurate tensor-core
         GEMM, cached like `weight_as_bf16`"""
         from ... import ops
         cache = self.__dict__.setdefault('_x3_weights', {})
         key = (w._version, w.data_ptr(), weights_generation(), _capture_token())
-        hit = cache.get(id(w))
+        hit = cache.get((id(w), tap_major))
         if hit is None or hit[0] != key:
-            hit = (key, ops.split_bf16x3(w.detach().reshape(w.shape[0], -1).float()))
-            cache[id(w)] = hit
+            hit = (key, ops.split_bf16x3(self._as_matrix(w, tap_major).float().contiguous()))
+            cache[(id(w), tap_major)] = hit
         return hit[1]
 
 

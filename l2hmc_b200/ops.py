@@ -1001,9 +1001,9 @@ def _strides4(t: Tensor, nchw: bool):
     return (ctypes.c_longlong * 4)(*((sb, s1, s2, s3) if nchw else (sb, s3, s1, s2)))
 
 
-def conv_im2col(x: Tensor, n: int, nchw: bool, planes: int) -> Tensor:
+def conv_im2col(x: Tensor, n: int, nchw: bool, planes: int, tap_major: bool = False) -> Tensor:
     """col[planes, nb OH OW, K8] bf16 of a periodic-padding convolution block (see include/l2b.h); x float32 / bf16,
-    [nb, C, H, W] (nchw) or [nb, H, W, C]"""
+    [nb, C, H, W] (nchw) or [nb, H, W, C]; columns k = (ci, kh, kw), or (kh, kw, ci) with `tap_major`"""
     _need_cuda(x)
     if x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
         raise L2BError(f'conv_im2col expects a 4-D float32 / bfloat16 activation (got {x.dtype}, {tuple(x.shape)})')
@@ -1012,11 +1012,11 @@ def conv_im2col(x: Tensor, n: int, nchw: bool, planes: int) -> Tensor:
     OH, OW, K8 = H + n - 1, W + n - 1, _r8(C * n * n)
     col = torch.empty((planes, nb * OH * OW, K8), dtype=torch.bfloat16, device=x.device)
     call('l2b_conv_im2col', _ptr(x), _net_dt(x.dtype), nb, C, H, W, int(n), _strides4(x, nchw), _ptr(col), int(planes),
-         _stream())
+         int(bool(tap_major)), _stream())
     return col
 
 
-def conv_col2im(dcol: Tensor, like: Tensor, n: int, nchw: bool) -> Tensor:
+def conv_col2im(dcol: Tensor, like: Tensor, n: int, nchw: bool, tap_major: bool = False) -> Tensor:
     """adjoint of conv_im2col: dcol [nb OH OW, ld] float32 / bf16 -> float32 gradient shaped and laid out like `like`"""
     _need_cuda(dcol)
     if dcol.dtype not in (torch.float32, torch.bfloat16) or dcol.dim() != 2 or dcol.stride(1) != 1:
@@ -1025,7 +1025,7 @@ def conv_col2im(dcol: Tensor, like: Tensor, n: int, nchw: bool) -> Tensor:
     C, H, W = (int(like.shape[1]), int(like.shape[2]), int(like.shape[3])) if nchw else (int(like.shape[3]), int(like.shape[1]), int(like.shape[2]))
     din = torch.empty(like.shape, dtype=torch.float32, device=dcol.device)
     call('l2b_conv_col2im', _ptr(dcol), _net_dt(dcol.dtype), int(dcol.stride(0)), nb, C, H, W, int(n), _ptr(din),
-         _strides4(din, nchw), _stream())
+         _strides4(din, nchw), int(bool(tap_major)), _stream())
     return din
 
 

@@ -530,19 +530,28 @@ def _im2col_f32(x_nchw, n):
     return torch.nn.functional.unfold(xp, n).transpose(1, 2).reshape(-1, C * n * n)
 
 
-def conv_im2col(x, n, nchw, planes):
+def _tap_major(col, C, n):
+    """columns (ci, kh, kw) -> (kh, kw, ci)"""
+    return col.reshape(col.shape[0], C, n * n).transpose(1, 2).reshape(col.shape[0], C * n * n)
+
+
+def conv_im2col(x, n, nchw, planes, tap_major=False):
     xf = (x if nchw else x.permute(0, 3, 1, 2)).float()
     col = _im2col_f32(xf, n)
+    if tap_major:
+        col = _tap_major(col, xf.shape[1], n)
     s3 = split_bf16x3(col.contiguous())
     return s3[:planes].contiguous()
 
 
-def conv_col2im(dcol, like, n, nchw):
+def conv_col2im(dcol, like, n, nchw, tap_major=False):
     shape = like.shape if nchw else (like.shape[0], like.shape[3], like.shape[1], like.shape[2])
     K = shape[1] * n * n
     with torch.enable_grad():                  # called from inside a Function.backward (grad mode off)
         probe = torch.zeros(shape, dtype=torch.float32, requires_grad=True)
         col = _im2col_f32(probe, n)
+        if tap_major:
+            col = _tap_major(col, shape[1], n)
         (gx,) = torch.autograd.grad(col, probe, dcol.float()[:, :K])
     return gx if nchw else gx.permute(0, 2, 3, 1).contiguous()
 

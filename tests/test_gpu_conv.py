@@ -45,6 +45,39 @@ def test_im2col_is_periodic_padding_plus_unfold():
         assert float((gx2.permute(0, 3, 1, 2) - gx).abs().max()) == 0.0
 
 
+def test_tap_major_gather_is_a_column_permutation_of_the_channel_major_one():
+    """k_order 1 (columns (kh, kw, ci), vector loads when Cin % 8 == 0 on NHWC) against k_order 0 (columns
+    (ci, kh, kw)): bit-equal after the permutation, for the vector path, the scalar fallbacks (Cin % 8 != 0, NCHW,
+    an unaligned view) and the adjoint"""
+    from l2hmc_b200 import ops
+    g = torch.Generator(device='cpu').manual_seed(4)
+    for (nb, C, H, W, n) in [(3, 8, 6, 5, 3), (2, 16, 4, 4, 2), (2, 32, 12, 12, 3), (2, 5, 4, 6, 3), (1, 24, 7, 3, 4)]:
+        K = C * n * n
+        x = torch.randn(nb, H, W, C, generator=g).to(DEV)
+        for planes, xin in ((3, x), (2, x), (1, x.to(torch.bfloat16))):
+            c0 = ops.conv_im2col(xin, n, False, planes)
+            c1 = ops.conv_im2col(xin, n, False, planes, tap_major=True)
+            want = c0[:, :, :K].reshape(planes, -1, C, n * n).transpose(2, 3).reshape(planes, -1, K)
+            assert torch.equal(c1[:, :, :K], want)
+            assert float(c1[:, :, K:].abs().sum()) == 0.0
+        # NCHW input and an unaligned NHWC view take the scalar path of the same kernel
+        xn = x.permute(0, 3, 1, 2).contiguous()
+        c0 = ops.conv_im2col(xn, n, True, 3)
+        c1 = ops.conv_im2col(xn, n, True, 3, tap_major=True)
+        assert torch.equal(c1[:, :, :K], c0[:, :, :K].reshape(3, -1, C, n * n).transpose(2, 3).reshape(3, -1, K))
+        big = torch.randn(nb * H * W * C + 1, generator=g).to(DEV)
+        xv = big[1:].view(nb, H, W, C)
+        assert torch.equal(ops.conv_im2col(xv, n, False, 3, tap_major=True), ops.conv_im2col(xv.clone(), n, False, 3, tap_major=True))
+        # adjoint
+        M = nb * (H + n - 1) * (W + n - 1)
+        d = torch.randn(M, K + 3, generator=g).to(DEV)
+        d_tap = torch.cat([d[:, :K].reshape(M, C, n * n).transpose(1, 2).reshape(M, K), d[:, K:]], 1).contiguous()
+        for dt in (torch.float32, torch.bfloat16):
+            g0 = ops.conv_col2im(d.to(dt), x, n, False)
+            g1 = ops.conv_col2im(d_tap.to(dt), x, n, False, tap_major=True)
+            assert torch.equal(g0, g1)
+
+
 @pytest.mark.parametrize('act', [None, 'tanh', 'relu', 'swish', 'leaky_relu', 'elu'])
 def test_pool_act_matches_torch(act):
     from l2hmc_b200 import autograd as ag
