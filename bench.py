@@ -1066,8 +1066,8 @@ def su3_kernel_roofline(ops, _lib, x, v, lattice, nb, nlf, beta, eps, steps, pea
     return {'bound': 'hbm', 'kernel': 'k_force_ep<32,3,DRIFT,3> (one fused leapfrog step: staples + TAH + kick + exp + link update)',
             'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'peak_kind': peak_kind,
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at 16^4 x 64 (ncu --set full,
-            # profiles/r1e_force_fused_ncu_full.md: 10.00 GB vs 9.66 GB the kernel has to move)
-            'traffic': 9.999e9 if (list(lattice) == [16, 16, 16, 16] and nb == 64) else None,
+            # profiles/r2_force_ep_ncu_full.md: 10.04 GB vs 9.66 GB the kernel has to move)
+            'traffic': 10.043e9 if (list(lattice) == [16, 16, 16, 16] and nb == 64) else None,
             'algorithmic_bytes_per_launch': bytes_model, 'avg_launch_ms': ms_s,
             'share_of_step': nlf * ms_s / ms_traj,
             'note': ('algorithmic bytes = SURVEY 8(d) streaming model, 864 B per link-update (6 transfers); '
