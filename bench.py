@@ -742,7 +742,7 @@ def main_ours(args):
                       'roofline_frac': r['roofline']['frac'], 'roofline_kernel': r['roofline']['kernel'],
                       'e2e': r['e2e']['value'], 'gpu_launches': r['gpu_launches'],
                       'chains_per_gpu': r['config']['chains_per_gpu'], 'parallelism': r['config']['parallelism'],
-                      'cuda_graphs': r['config']['cuda_graphs'],
+                      'cuda_graphs': r['config']['cuda_graphs'], 'ms_each_step': r['ms_each_step'],
                       'grad_allreduce': r.get('grad_allreduce')}
         if ctx.world == 1:
             # BASELINE cfg 1 (the reference's default experiment; the CPU arm runs it at full size: `--impl reference
@@ -752,7 +752,7 @@ def main_ours(args):
                 sec[w] = {'value': r['value'], 'ms_per_step': r['ms_per_step'], 'unit': 'link-updates/s',
                           'roofline_frac': None, 'roofline_kernel': None, 'e2e': r['e2e']['value'],
                           'gpu_launches': r['gpu_launches'], 'chains_per_gpu': r['config']['chains_per_gpu'],
-                          'cuda_graphs': True, 'note': r['config']['l2_policy']}
+                          'cuda_graphs': True, 'ms_each_step': r['ms_each_step'], 'note': r['config']['l2_policy']}
         line['secondary'] = sec
     if ctx.rank == 0:
         if ctx.world == 1 and not args.no_cpu_baseline:
@@ -819,8 +819,11 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.barrier()
         e0.record()
+        marks = [e0]
         for _ in range(steps):
             xo, met = step(x)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         ctx.barrier()
         launches = _lib.launch_count() - l0
@@ -828,6 +831,7 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
             launches = steps * int(tr.graph_launches.get(mode, 0))
         clk = sampler.stop() if sampler else None
         ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        per_step = [a_.elapsed_time(b_) for a_, b_ in zip(marks[:-1], marks[1:])]     # this rank's steps, one by one
         value = world * units_rank / (ms * 1e-3)
         assert torch.isfinite(met['loss']), 'non-finite loss'
         # e2e: links from pinned host memory every step, loss read back to the host
@@ -868,6 +872,7 @@ def l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_graphs
         flops = 2.0 * 3 * nb * xdim * units
         res = {
             'workload': workload, 'value': value, 'ms_per_step': ms, 'gpu_launches': launches, 'clocks': clk,
+            'ms_each_step': [round(t_, 3) for t_ in per_step],
             'dtype': 'f64 lattice + bf16 nets (fp32 accumulate)',
             'config': {'workload': workload, 'group': 'SU3', 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'units': [units], 'beta': beta, 'step': mode,
@@ -942,8 +947,11 @@ def u1_l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_gra
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ctx.barrier()
         e0.record()
+        marks = [e0]
         for _ in range(steps):
             xo, met = step(x)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         ctx.barrier()
         launches = _lib.launch_count() - l0
@@ -951,6 +959,7 @@ def u1_l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_gra
             launches = steps * int(tr.graph_launches.get(mode, 0))
         clk = sampler.stop() if sampler else None
         ms = ctx.max_over_ranks(e0.elapsed_time(e1)) / steps
+        per_step = [a_.elapsed_time(b_) for a_, b_ in zip(marks[:-1], marks[1:])]
         assert torch.isfinite(torch.as_tensor(met['loss'])), 'non-finite loss'
         # e2e: links from pinned host memory every step, loss read back to the host
         xh = x.cpu().pin_memory()
@@ -968,6 +977,7 @@ def u1_l2hmc_workload(ctx: Ctx, workload: str, steps: int, warmup: int, cuda_gra
         e2e_val = world * units_rank * steps / (ctx.max_over_ranks(e2.elapsed_time(e3)) * 1e-3)
         res = {
             'workload': workload, 'value': world * units_rank / (ms * 1e-3), 'ms_per_step': ms,
+            'ms_each_step': [round(t_, 3) for t_ in per_step],
             'gpu_launches': launches, 'clocks': clk, 'dtype': 'f32',
             'config': {'workload': workload, 'group': 'U1', 'lattice': lattice, 'chains_per_gpu': nb,
                        'global_chains': nb * world, 'nleapfrog': nlf, 'beta': beta, 'step': mode,
