@@ -28,6 +28,13 @@ units = int(args[4]) if len(args) > 4 else 256
 reps = int(args[5]) if len(args) > 5 else 3
 table = '--table' in sys.argv
 
+import os  # noqa: E402
+world = int(os.environ.get('WORLD_SIZE', '1'))
+rank = 0
+if world > 1:          # torchrun: one rank per GPU, NN gradients all-reduced in the flat bf16 bucket (as bench.py does)
+    from l2hmc_b200 import dist as l2dist
+    rank, _, local = l2dist.init()
+    torch.cuda.set_device(local)
 torch.manual_seed(9992)
 np.random.seed(9992)
 torch.set_default_dtype(torch.float32)
@@ -42,7 +49,9 @@ fac = NetworkFactory(input_spec=get_input_spec(cfg),
 lat = LatticeSU3(nb, shape)
 dyn = Dynamics(potential_fn=lat.action, config=cfg, network_factory=fac)
 tr = Trainer(dyn, LossConfig(use_mixed_loss=True, charge_weight=0.0, rmse_weight=0.1, plaq_weight=0.1), lr=1e-4,
-             clip_val=1.0, autocast_dtype=torch.bfloat16, cuda_graphs='--graph' in sys.argv)
+             clip_val=1.0, autocast_dtype=torch.bfloat16, grad_bucket_dtype=torch.bfloat16,
+             cuda_graphs='--graph' in sys.argv)
+torch.manual_seed(9993 + rank)
 x = lat.random().to(torch.complex128)
 beta = torch.tensor(6.0)
 
@@ -66,12 +75,18 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 links = nb * 4 * L ** 4
-print(f'{mode} SU3 {L}^4 nb={nb} nlf={nlf} units={units}: {ms:.2f} ms/call (wall {1e3 * (time.perf_counter() - t0) / reps:.2f}), '
-      f'{links * 2 * nlf / (ms * 1e-3):.3e} link-updates/s, acc={float(m["acc"].mean()):.3f}, '
-      f'mem={torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
+if rank == 0:
+  print(f'{mode} SU3 {L}^4 nb={nb} nlf={nlf} units={units} world={world}: {ms:.2f} ms/call (wall {1e3 * (time.perf_counter() - t0) / reps:.2f}), '
+        f'{links * 2 * nlf / (ms * 1e-3):.3e} link-updates/s, acc={float(m["acc"].mean()):.3f}, '
+        f'mem={torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
 if table:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         step()
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=70))
+    if rank == 0:
+        print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=40 if world > 1 else 25,
+                                        max_name_column_width=70))
+if world > 1:
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
