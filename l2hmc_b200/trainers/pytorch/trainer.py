@@ -31,7 +31,8 @@ class Trainer:
         arguments) on first use and replay it afterwards -- the whole step, including backward
         and Adam for `train_step`, becomes ONE graph launch.  Step sizes and the
         SU(3) momentum RNG counter live on the device, so replays stay correct while parameters
-        train.  Needs `merge_directions` (the default) and a single process for `train_step`."""
+        train.  Needs `merge_directions` (the default).  With more than one rank `train_step` replays as two
+        graphs around one eager NCCL all-reduce of the flat gradient bucket (`_graphed_train_multi`)."""
         self.dynamics = dynamics
         self.lattice = dynamics.lattice
         self.g = dynamics.g
