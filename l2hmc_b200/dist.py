@@ -208,14 +208,23 @@ class GradBucket:
 
     def unpack(self) -> None:
         """every parameter gets the averaged gradient back in `.grad`"""
-        scale = 1.0 / (dist.get_world_size() if self.active() else 1)
+        self._hand_back()
+
+    def _hand_back(self) -> None:
+        """every parameter of the bucket gets the averaged gradient in `.grad`, own dtype (zero where no rank produced
+        one: a decision taken per rank from `p.grad is None` could differ between ranks).  ONE pass per parameter when
+        the scale is a power of two (1, 2, 4, 8 ranks): a product by 2^-k is exact in the bucket's dtype, so the
+        conversion to the gradient's dtype can ride on the same kernel; otherwise convert first, then scale."""
+        world = dist.get_world_size() if self.active() else 1
+        scale = 1.0 / world
+        exact = world & (world - 1) == 0
         with torch.no_grad():
             for p in self.params:
                 off, n = self.offsets[id(p)]
                 src = self.flat[off:off + n].view(p.shape)
                 if p.grad is None:
                     p.grad = torch.empty_like(p)
-                if src.dtype == p.grad.dtype:
+                if src.dtype == p.grad.dtype or exact:
                     torch.mul(src, scale, out=p.grad)
                 else:
                     p.grad.copy_(src).mul_(scale)
@@ -242,19 +251,7 @@ class GradBucket:
                 self._works.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
             for w in self._works:
                 w.wait()                              # stream-level wait: the current stream orders after NCCL's
-        scale = 1.0 / (dist.get_world_size() if self.active() else 1)
-        with torch.no_grad():
-            for p in self.params:
-                # every parameter of the bucket gets the averaged gradient (zero where no rank produced one: a
-                # decision taken per rank from `p.grad is None` could differ between ranks)
-                off, n = self.offsets[id(p)]
-                src = self.flat[off:off + n].view(p.shape)
-                if p.grad is None:
-                    p.grad = torch.empty_like(p)
-                if src.dtype == p.grad.dtype:
-                    torch.mul(src, scale, out=p.grad)
-                else:
-                    p.grad.copy_(src).mul_(scale)
+        self._hand_back()
         self.last = {'elements': self.numel, 'bytes': self.numel * self.flat.element_size(),
                      'calls': len(self._works), 'early_calls': early}
         n_calls = len(self._works)
