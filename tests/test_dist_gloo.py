@@ -111,9 +111,10 @@ def _worker(rank, world, port, nchains, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('nchains', [8, 7])
-def test_world2_gloo(nchains):
-    world, port = 2, _free_port()
+@pytest.mark.parametrize('nchains,world', [(8, 2), (7, 2), (7, 3)])
+def test_world2_gloo(nchains, world):
+    """world 3: ragged shards and the bucket's convert-then-scale hand-back (1/3 is not exact in bf16)"""
+    port = _free_port()
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, nchains, q)) for r in range(world)]
@@ -123,4 +124,4 @@ def test_world2_gloo(nchains):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res == [(0, True, True), (1, True, True)]
+    assert res == [(r, True, True) for r in range(world)]
